@@ -1,0 +1,251 @@
+"""ctypes front-end for oracle/_ref/libcmref.so -- TEST INFRASTRUCTURE.
+
+libcmref.so is the UNMODIFIED reference clip-map code (code/qcommon/cm_*.c,
+q_math.c, q_shared.c) built by oracle/Makefile plus oracle/ref_shim.c.  It is
+the checker for parity tests and the timed subject of ``bench.py --impl
+reference`` / the ``cpu_baseline`` leg.  Product code never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libcmref.so")
+
+TRACE_DTYPE = np.dtype([
+    ("allsolid", "<i4"), ("startsolid", "<i4"), ("fraction", "<f4"), ("endpos", "<f4", (3,)),
+    ("plane_normal", "<f4", (3,)), ("plane_dist", "<f4"), ("plane_type", "u1"),
+    ("plane_signbits", "u1"), ("plane_pad", "u1", (2,)),
+    ("surfaceFlags", "<i4"), ("contents", "<i4"), ("entityNum", "<i4")])
+assert TRACE_DTYPE.itemsize == 56     # q_shared.h:976-986
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def build(quiet=True) -> bool:
+    """(Re)build via the Makefile when the reference tree is present."""
+    import subprocess
+    r = subprocess.run(["make", "-C", HERE, "ref"], capture_output=quiet, text=True)
+    return r.returncode == 0 and available()
+
+
+_f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+_i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+_p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RefCM:
+    """One loaded map in the reference library (the library is a process-wide singleton)."""
+
+    def __init__(self):
+        if not available():
+            raise RuntimeError("oracle/_ref/libcmref.so missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(LIB_PATH)
+        self.lib.cmref_last_error.restype = C.c_char_p
+        self.lib.cmref_shared_alloc.restype = C.c_void_p
+        self.lib.cmref_shared_alloc.argtypes = [C.c_size_t]
+        self.lib.cmref_shared_free.argtypes = [C.c_void_p, C.c_size_t]
+        assert self.lib.cmref_sizeof_trace() == 56
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {self.lib.cmref_last_error().decode(errors='replace')}")
+
+    def load(self, data: bytes):
+        self._data = bytes(data)
+        self._check(self.lib.cmref_load(self._data, len(self._data)), "CM_LoadMap")
+        return self
+
+    def set_cvars(self, noCurves=0, playerCurveClip=1):
+        self.lib.cmref_set_cvars(int(noCurves), int(playerCurveClip))
+
+    def num_inline_models(self):
+        return self.lib.cmref_num_inline_models()
+
+    @staticmethod
+    def _hull(n, mins, maxs):
+        if mins is None:
+            return None, None, 0
+        mins = _f(mins)
+        maxs = _f(maxs)
+        if mins.ndim == 1:
+            return mins, maxs, 0
+        assert mins.shape == (n, 3)
+        return mins, maxs, 1
+
+    @staticmethod
+    def _mask(n, mask):
+        m = np.asarray(mask)
+        if m.ndim == 0:
+            return np.array([int(m)], dtype=np.int64).astype(np.int32), 0
+        assert m.shape == (n,)
+        return _i(m), 1
+
+    def box_trace(self, starts, ends, mins=None, maxs=None, model=0, mask=1):
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        mins, maxs, hs = self._hull(n, mins, maxs)
+        m, ms = self._mask(n, mask)
+        models = None
+        if not np.isscalar(model) or model != 0:
+            models = _i(np.broadcast_to(_i(model), (n,)))
+        out = np.zeros(n, dtype=TRACE_DTYPE)
+        self._check(self.lib.cmref_box_trace_batch(n, _p(starts), _p(ends), _p(mins), _p(maxs), hs,
+                                                   _p(models), _p(m), ms, _p(out)), "CM_BoxTrace")
+        return out
+
+    def transformed_box_trace(self, starts, ends, mins, maxs, models, mask, origins, angles,
+                              boxmins=None, boxmaxs=None):
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        mins, maxs, hs = self._hull(n, mins, maxs)
+        m, ms = self._mask(n, mask)
+        models = _i(np.broadcast_to(_i(models), (n,)))
+        origins, angles = _f(origins), _f(angles)
+        if boxmins is None:
+            boxmins = np.zeros((n, 3), np.float32)
+            boxmaxs = np.zeros((n, 3), np.float32)
+        boxmins, boxmaxs = _f(boxmins), _f(boxmaxs)
+        out = np.zeros(n, dtype=TRACE_DTYPE)
+        self._check(self.lib.cmref_transformed_box_trace_batch(
+            n, _p(starts), _p(ends), _p(mins), _p(maxs), hs, _p(models), _p(m), ms,
+            _p(origins), _p(angles), _p(boxmins), _p(boxmaxs), _p(out)), "CM_TransformedBoxTrace")
+        return out
+
+    def point_contents(self, pts, models=None, boxmins=None, boxmaxs=None):
+        pts = _f(pts)
+        n = pts.shape[0]
+        if models is not None:
+            models = _i(np.broadcast_to(_i(models), (n,)))
+            if boxmins is None:
+                boxmins = np.zeros((n, 3), np.float32)
+                boxmaxs = np.zeros((n, 3), np.float32)
+            boxmins, boxmaxs = _f(boxmins), _f(boxmaxs)
+        out = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.cmref_point_contents_batch(n, _p(pts), _p(models), _p(boxmins), _p(boxmaxs), _p(out)),
+                    "CM_PointContents")
+        return out
+
+    def transformed_point_contents(self, pts, models, origins, angles, boxmins=None, boxmaxs=None):
+        pts = _f(pts)
+        n = pts.shape[0]
+        models = _i(np.broadcast_to(_i(models), (n,)))
+        origins, angles = _f(origins), _f(angles)
+        if boxmins is None:
+            boxmins = np.zeros((n, 3), np.float32)
+            boxmaxs = np.zeros((n, 3), np.float32)
+        boxmins, boxmaxs = _f(boxmins), _f(boxmaxs)
+        out = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.cmref_transformed_point_contents_batch(
+            n, _p(pts), _p(models), _p(origins), _p(angles), _p(boxmins), _p(boxmaxs), _p(out)),
+            "CM_TransformedPointContents")
+        return out
+
+    def point_leafnum(self, pts):
+        pts = _f(pts)
+        out = np.zeros(pts.shape[0], dtype=np.int32)
+        self._check(self.lib.cmref_point_leafnum_batch(pts.shape[0], _p(pts), _p(out)), "CM_PointLeafnum")
+        return out
+
+    def box_leafnums(self, mins, maxs, listsize=64):
+        mins, maxs = _f(mins), _f(maxs)
+        n = mins.shape[0]
+        lists = np.full((n, listsize), -1, dtype=np.int32)
+        counts = np.zeros(n, np.int32)
+        last = np.zeros(n, np.int32)
+        self._check(self.lib.cmref_box_leafnums_batch(n, _p(mins), _p(maxs), listsize, _p(lists), _p(counts), _p(last)),
+                    "CM_BoxLeafnums")
+        return lists, counts, last
+
+    def angle_vectors(self, angles):
+        a = _f(angles)
+        f = np.zeros(3, np.float32)
+        r = np.zeros(3, np.float32)
+        u = np.zeros(3, np.float32)
+        self.lib.cmref_angle_vectors(_p(a), _p(f), _p(r), _p(u))
+        return f, r, u
+
+    def bench_box_trace(self, starts, ends, mins, maxs, mask, nworkers, repeats=1, want_results=False):
+        """All-core throughput run: fork()ed workers, one per core, slowest worker's time."""
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        mins = _f(mins) if mins is not None else None
+        maxs = _f(maxs) if maxs is not None else None
+        secs = C.c_double(0.0)
+        wsecs = np.zeros(max(nworkers, 1), dtype=np.float64)
+        shared = None
+        nbytes = n * 56
+        if want_results:
+            shared = self.lib.cmref_shared_alloc(nbytes)
+        rc = self.lib.cmref_box_trace_bench(n, _p(starts), _p(ends), _p(mins), _p(maxs), int(mask),
+                                            int(nworkers), int(repeats), C.c_void_p(shared),
+                                            C.byref(secs), _p(wsecs))
+        out = None
+        if want_results and shared:
+            buf = (C.c_char * nbytes).from_address(shared)
+            out = np.frombuffer(bytes(buf), dtype=TRACE_DTYPE).copy()
+            self.lib.cmref_shared_free(C.c_void_p(shared), nbytes)
+        self._check(rc, "bench")
+        return secs.value, wsecs[:nworkers], out
+
+    # ---- dumps of the loaded clipMap_t -----------------------------------
+    COUNT_NAMES = ["planes", "nodes", "leafs", "leafbrushes", "leafsurfaces", "brushes", "brushsides",
+                   "models", "surfaces", "shaders", "patches", "patchplanes", "facets", "borders"]
+
+    def counts(self):
+        c = np.zeros(len(self.COUNT_NAMES), np.int32)
+        self.lib.cmref_counts(_p(c))
+        return dict(zip(self.COUNT_NAMES, (int(x) for x in c)))
+
+    def dump(self):
+        n = self.counts()
+        d = dict(counts=n)
+        d["planes"] = np.zeros((n["planes"], 4), np.float32)
+        d["plane_type"] = np.zeros(n["planes"], np.uint8)
+        d["plane_signbits"] = np.zeros(n["planes"], np.uint8)
+        self.lib.cmref_dump_planes(_p(d["planes"]), _p(d["plane_type"]), _p(d["plane_signbits"]))
+        d["nodes"] = np.zeros((n["nodes"], 3), np.int32)
+        self.lib.cmref_dump_nodes(_p(d["nodes"]))
+        d["leafs"] = np.zeros((n["leafs"], 6), np.int32)
+        self.lib.cmref_dump_leafs(_p(d["leafs"]))
+        d["leafbrushes"] = np.zeros(n["leafbrushes"], np.int32)
+        self.lib.cmref_dump_leafbrushes(_p(d["leafbrushes"]))
+        d["leafsurfaces"] = np.zeros(max(n["leafsurfaces"], 1), np.int32)
+        self.lib.cmref_dump_leafsurfaces(_p(d["leafsurfaces"]))
+        d["leafsurfaces"] = d["leafsurfaces"][:n["leafsurfaces"]]
+        d["brush_meta"] = np.zeros((n["brushes"], 4), np.int32)
+        d["brush_bounds"] = np.zeros((n["brushes"], 6), np.float32)
+        self.lib.cmref_dump_brushes(_p(d["brush_meta"]), _p(d["brush_bounds"]))
+        d["brushsides"] = np.zeros((n["brushsides"], 3), np.int32)
+        self.lib.cmref_dump_brushsides(_p(d["brushsides"]))
+        d["model_bounds"] = np.zeros((n["models"], 6), np.float32)
+        d["model_nums"] = np.zeros((n["models"], 2), np.int32)
+        self.lib.cmref_dump_models(_p(d["model_bounds"]), _p(d["model_nums"]))
+        d["model_brushlist"] = np.zeros(max(int(d["model_nums"][:, 0].sum()), 1), np.int32)
+        d["model_surflist"] = np.zeros(max(int(d["model_nums"][:, 1].sum()), 1), np.int32)
+        self.lib.cmref_dump_model_lists(_p(d["model_brushlist"]), _p(d["model_surflist"]))
+        d["model_brushlist"] = d["model_brushlist"][:int(d["model_nums"][:, 0].sum())]
+        d["model_surflist"] = d["model_surflist"][:int(d["model_nums"][:, 1].sum())]
+        d["surf2patch"] = np.zeros(max(n["surfaces"], 1), np.int32)
+        d["patch_meta"] = np.zeros((max(n["patches"], 1), 4), np.int32)
+        d["patch_bounds"] = np.zeros((max(n["patches"], 1), 6), np.float32)
+        d["patch_planes"] = np.zeros((max(n["patchplanes"], 1), 4), np.float32)
+        d["patch_plane_signbits"] = np.zeros(max(n["patchplanes"], 1), np.int32)
+        d["facet_meta"] = np.zeros((max(n["facets"], 1), 2), np.int32)
+        d["borders"] = np.zeros((max(n["borders"], 1), 3), np.int32)
+        self.lib.cmref_dump_patches(_p(d["surf2patch"]), _p(d["patch_meta"]), _p(d["patch_bounds"]),
+                                    _p(d["patch_planes"]), _p(d["patch_plane_signbits"]),
+                                    _p(d["facet_meta"]), _p(d["borders"]))
+        d["surf2patch"] = d["surf2patch"][:n["surfaces"]]
+        d["patch_meta"] = d["patch_meta"][:n["patches"]]
+        d["patch_bounds"] = d["patch_bounds"][:n["patches"]]
+        d["patch_planes"] = d["patch_planes"][:n["patchplanes"]]
+        d["patch_plane_signbits"] = d["patch_plane_signbits"][:n["patchplanes"]]
+        d["facet_meta"] = d["facet_meta"][:n["facets"]]
+        d["borders"] = d["borders"][:n["borders"]]
+        return d
