@@ -1,0 +1,205 @@
+/*
+ * cm_gpu.h -- C ABI of the B200 batched collision-trace engine (libcmgpu.so).
+ *
+ * This is the boundary the ThreeCore host code binds to.  Every entry point is
+ * extern "C", takes plain pointers and sizes, and returns an int status
+ * (CMGPU_OK == 0).  Nothing here longjmp()s: the engine-side shim turns a
+ * non-zero status into Com_Error(ERR_DROP, ...) exactly where the reference
+ * raises it (code/qcommon/cm_load.c:770,792-795).
+ *
+ * Reference interfaces each group replaces (paths relative to the reference
+ * tree, code/qcommon unless noted):
+ *
+ *   cmgpu_flatmap, cmgpu_upload      the upload hook after cm_load.c:734; the
+ *                                    arrays are clipMap_t (cm_local.h:120-172)
+ *                                    with every pointer turned into an index
+ *   cmgpu_flatmap_from_bsp           CM_LoadMap's lump parsing, cm_load.c:606-745
+ *   cmgpu_box_trace_batch            CM_BoxTrace / CM_Trace, cm_public.h:45-48
+ *                                    (cm_trace.c:545-698), one call per item
+ *   cmgpu_transformed_box_trace_batch  CM_TransformedBoxTrace, cm_public.h:49-52
+ *                                    (cm_trace.c:708-805) incl. CM_TempBoxModel
+ *                                    (cm_load.c:927-949) for handle 1023
+ *   cmgpu_point_contents_batch       CM_PointContents / CM_TransformedPointContents,
+ *                                    cm_public.h:42-43 (cm_test.c:217-294)
+ *   cmgpu_clear                      CM_ClearMap, cm_load.c:753
+ *
+ * Results are bit-for-bit what the reference writes into trace_t
+ * (q_shared.h:976-986), including the stale plane.type/signbits bytes a patch
+ * hit leaves behind (cm_patch.c:1309-1310).  entityNum is left 0, as CM does
+ * (it is set by the server layer, server/sv_world.c:577).
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * returns CMGPU_ERR_NO_DEVICE / CMGPU_ERR_CUDA.
+ */
+#ifndef CM_GPU_H
+#define CM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+
+#define CMGPU_ABI_VERSION 1
+
+#define CMGPU_BOX_MODEL_HANDLE 1023   /* BOX_MODEL_HANDLE, cm_local.h:28 */
+#define CMGPU_MAX_SUBMODELS    1024   /* MAX_SUBMODELS,   cm_local.h:27 */
+
+enum {
+	CMGPU_OK = 0,
+	CMGPU_ERR_INVALID = 1,      /* bad argument (NULL pointer, negative count) */
+	CMGPU_ERR_NO_DEVICE = 2,    /* no CUDA device / wrong architecture */
+	CMGPU_ERR_CUDA = 3,         /* CUDA runtime failure, see cmgpu_last_error */
+	CMGPU_ERR_NO_MAP = 4,       /* compute call with no map uploaded (reference: zeroed trace, cm_trace.c:562) */
+	CMGPU_ERR_BAD_HANDLE = 5,   /* CM_ClipHandleToModel: bad handle, cm_load.c:768-798 */
+	CMGPU_ERR_BAD_MAP = 6,      /* malformed lump / index out of range (the reference's ERR_DROPs in cm_load.c) */
+	CMGPU_ERR_NOMEM = 7,
+	CMGPU_ERR_LIMIT = 8         /* traversal stack overflow (tree deeper than CMGPU_MAX_DEPTH) */
+};
+
+/* trace_t, q_shared.h:976-986: 56 bytes, layout is ABI (QVM memory, botlib copies). */
+typedef struct cmgpu_trace_s {
+	int32_t allsolid;
+	int32_t startsolid;
+	float   fraction;
+	float   endpos[3];
+	float   plane_normal[3];
+	float   plane_dist;
+	uint8_t plane_type;
+	uint8_t plane_signbits;
+	uint8_t plane_pad[2];
+	int32_t surfaceFlags;
+	int32_t contents;
+	int32_t entityNum;
+} cmgpu_trace_t;
+
+/*
+ * The loaded clip map as index arrays.  Counts INCLUDE the box-hull extras the
+ * reference appends in CM_InitBoxHull (cm_load.c:45-50,873-916): the last 12
+ * planes, last 6 brush sides, last brush, and leafbrushes[boxLeafBrush].
+ * Submodel brush/surface lists (cm_load.c:170-182) live in the same
+ * leafbrushes[]/leafsurfaces[] arrays and are addressed by modelLeafs[].
+ */
+typedef struct cmgpu_flatmap_s {
+	int32_t numPlanes;        const float   *planes;         /* [n][4] normal.xyz, dist */
+	                          const uint8_t *planeType;      /* cplane_t.type */
+	                          const uint8_t *planeSignbits;  /* cplane_t.signbits */
+	int32_t numNodes;         const int32_t *nodes;          /* [n][3] plane, children[0], children[1] */
+	int32_t numLeafs;         const int32_t *leafs;          /* [n][4] firstLeafBrush, numLeafBrushes, firstLeafSurface, numLeafSurfaces */
+	int32_t numLeafBrushes;   const int32_t *leafbrushes;
+	int32_t numLeafSurfaces;  const int32_t *leafsurfaces;
+	int32_t numBrushes;       const int32_t *brushes;        /* [n][3] contents, firstSide, numSides */
+	                          const float   *brushBounds;    /* [n][6] mins, maxs */
+	int32_t numBrushSides;    const int32_t *brushsides;     /* [n][2] plane, surfaceFlags */
+	int32_t numModels;        const int32_t *modelLeafs;     /* [n][4] as leafs[]; entry 0 (world) unused */
+	                          const float   *modelBounds;    /* [n][6] cmodel_t mins, maxs (already spread by 1, cm_load.c:159-163) */
+	int32_t numSurfaces;      const int32_t *surf2patch;     /* [n] patch ordinal, -1 where cm.surfaces[i] == NULL */
+	int32_t numPatches;       const int32_t *patches;        /* [n][6] surfaceFlags, contents, firstPlane, numPlanes, firstFacet, numFacets */
+	                          const float   *patchBounds;    /* [n][6] */
+	int32_t numPatchPlanes;   const float   *patchPlanes;    /* [n][4] patchPlane_t.plane, cm_patch.h:26-29 */
+	                          const int32_t *patchPlaneSignbits;
+	int32_t numFacets;        const int32_t *facets;         /* [n][3] surfacePlane, numBorders, firstBorder */
+	int32_t numBorders;       const int32_t *borders;        /* [n][2] plane (patch-local index), borderInward */
+	const int32_t *leafClusterArea;                           /* [numLeafs][2] cluster, area (may be NULL) */
+	int32_t boxBrush;        /* = numBrushes-1 */
+	int32_t boxFirstPlane;   /* = numPlanes-12 */
+	int32_t boxFirstSide;    /* = numBrushSides-6 */
+	int32_t boxLeafBrush;    /* leafbrushes[] slot holding boxBrush */
+} cmgpu_flatmap;
+
+typedef struct cmgpu_ctx_s cmgpu_ctx;
+
+/* ---- lifetime ------------------------------------------------------------ */
+int  cmgpu_abi_version(void);
+int  cmgpu_device_count(void);
+int  cmgpu_create(cmgpu_ctx **out, int device);
+void cmgpu_destroy(cmgpu_ctx *ctx);
+const char *cmgpu_last_error(const cmgpu_ctx *ctx);   /* ctx may be NULL: last error of a failed create */
+
+/* ---- map ------------------------------------------------------------------ */
+/* Parse an IBSP v46 image the way CM_LoadMap does (brushes, planes, nodes, leafs,
+ * inline models, box hull; patches are tessellated on the host as
+ * CM_GeneratePatchCollide does).  Free with cmgpu_flatmap_free. */
+int  cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen);
+void cmgpu_flatmap_free(cmgpu_flatmap *map);
+
+/* Validate, pack into the device layout and copy to the context's GPU. Replaces any previous map. */
+int  cmgpu_upload(cmgpu_ctx *ctx, const cmgpu_flatmap *map);
+int  cmgpu_clear(cmgpu_ctx *ctx);
+/* cvars that change results: cm_noCurves (cm_trace.c:159,405), cm_playerCurveClip (cm_patch.c:1234) */
+int  cmgpu_set_cvars(cmgpu_ctx *ctx, int noCurves, int playerCurveClip);
+int  cmgpu_num_inline_models(const cmgpu_ctx *ctx);
+
+/* ---- batched queries, HOST pointers (copies in, kernel, copies out) -------
+ * starts/ends [n][3]; mins/maxs [1][3] when hull_stride==0 or [n][3] when 1,
+ * NULL means (0,0,0) as in cm_trace.c:569-574; models NULL = world (0);
+ * masks [1] (mask_stride 0) or [n] (1).  boxmins/boxmaxs [n][3] are read only
+ * for items whose model is CMGPU_BOX_MODEL_HANDLE (the CM_TempBoxModel box).
+ * hit_ids (optional, may be NULL) receives the brush index that produced the
+ * result, -2-patch for a patch, -1 for none.                                */
+int cmgpu_box_trace_batch(cmgpu_ctx *ctx, int n,
+                          const float *starts, const float *ends,
+                          const float *mins, const float *maxs, int hull_stride,
+                          const int32_t *models, const int32_t *masks, int mask_stride,
+                          const float *boxmins, const float *boxmaxs,
+                          cmgpu_trace_t *results, int32_t *hit_ids);
+
+int cmgpu_transformed_box_trace_batch(cmgpu_ctx *ctx, int n,
+                          const float *starts, const float *ends,
+                          const float *mins, const float *maxs, int hull_stride,
+                          const int32_t *models, const int32_t *masks, int mask_stride,
+                          const float *origins, const float *angles,
+                          const float *boxmins, const float *boxmaxs,
+                          cmgpu_trace_t *results, int32_t *hit_ids);
+
+/* origins/angles NULL: CM_PointContents; otherwise CM_TransformedPointContents */
+int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
+                               const int32_t *models, const float *origins, const float *angles,
+                               const float *boxmins, const float *boxmaxs, int32_t *contents);
+
+/* ---- batched queries, DEVICE pointers (inputs resident in HBM) -----------
+ * Same meaning as above; every pointer is a device pointer on the context's
+ * GPU, `stream` is a cudaStream_t (NULL = default stream).  The call only
+ * enqueues work.  rotations: [n][9] row-major rotation matrices
+ * (CreateRotationMatrix, cm_trace.c:65-68) with rot_index[i] == -1 for an
+ * unrotated item; build them with cmgpu_rotation_matrices on the host.     */
+int cmgpu_box_trace_batch_device(cmgpu_ctx *ctx, int n,
+                          const float *starts, const float *ends,
+                          const float *mins, const float *maxs, int hull_stride,
+                          const int32_t *models, const int32_t *masks, int mask_stride,
+                          const float *origins, const float *rotations, const int32_t *rot_index,
+                          const float *boxmins, const float *boxmaxs,
+                          cmgpu_trace_t *results, int32_t *hit_ids, void *stream);
+
+int cmgpu_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points,
+                               const int32_t *models, const float *origins,
+                               const float *rotations, const int32_t *rot_index,
+                               const float *boxmins, const float *boxmaxs,
+                               int32_t *contents, void *stream);
+
+/* AngleVectors (q_math.c:999-1032) + CreateRotationMatrix on the host, same libm.
+ * matrices [n][9]; rot_index[i] = i if any angle is non-zero, else -1. */
+void cmgpu_rotation_matrices(int n, const float *angles, float *matrices, int32_t *rot_index);
+
+/* Device status word of the last launches: 0, or CMGPU_ERR_LIMIT if any item overflowed its stack. */
+int cmgpu_check_status(cmgpu_ctx *ctx, void *stream);
+
+/* ---- instrumentation (successor of c_traces/c_brush_traces, cm_load.c:60-61) */
+typedef struct cmgpu_counters_s {
+	unsigned long long traces, nodes, leafs, brushRefs, brushBounds, brushSides, crossings, splits,
+	                   patches, patchPlanes, facets;
+} cmgpu_counters;
+/* enable != 0 switches the trace kernels to their counting variant (slower). */
+int cmgpu_enable_counters(cmgpu_ctx *ctx, int enable);
+int cmgpu_read_counters(cmgpu_ctx *ctx, cmgpu_counters *out, int reset);
+
+/* number of kernels this context has launched (for bench.py's gpu_launches) */
+unsigned long long cmgpu_launch_count(const cmgpu_ctx *ctx);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* CM_GPU_H */

@@ -1,0 +1,65 @@
+"""Shared helpers for the parity tests: map/ray fixtures and record comparison."""
+from __future__ import annotations
+
+import functools
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import cmoracle, cmref  # noqa: E402  (test infrastructure)
+from threecore_b200 import bspgen  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def have_ref() -> bool:
+    return cmref.available()
+
+
+@functools.lru_cache(maxsize=None)
+def get_map(kind: str):
+    """Small deterministic maps used across tests."""
+    if kind == "tiny":
+        return bspgen.tiny_map()
+    if kind == "room":
+        return bspgen.room_map(n_brushes=500, seed=0xC0FFEE01)
+    if kind == "arena_small":
+        return bspgen.arena_map(n_brushes=2500, seed=0xC0FFEE12, size_xy=4096.0, size_z=2048.0,
+                                rotated_frac=0.15, nonaxial_node_prob=0.05)
+    if kind == "arena_models":
+        return bspgen.arena_map(n_brushes=1500, seed=0xC0FFEE14, size_xy=4096.0, size_z=2048.0,
+                                rotated_frac=0.15, nonaxial_node_prob=0.05, n_models=48)
+    if kind == "patches_small":
+        return bspgen.patch_map(n_brushes=300, n_patches=64, seed=0xC0FFEE13, size_xy=3072.0, size_z=1536.0,
+                                n_models=6)
+    raise KeyError(kind)
+
+
+def oracle_for(flat: dict, **cvars) -> "cmoracle.OracleCM":
+    return cmoracle.OracleCM(flat, **cvars)
+
+
+def flat_from_ref(data: bytes) -> dict:
+    r = cmref.RefCM().load(data)
+    return cmoracle.flat_from_ref_dump(r.dump())
+
+
+def trace_bytes(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a).view(np.uint8).reshape(len(a), 56)
+
+
+def assert_traces_equal(got: np.ndarray, want: np.ndarray, what: str = ""):
+    """Bit-exact comparison of 56-byte trace_t records with a readable first mismatch."""
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    g, w = trace_bytes(got), trace_bytes(want)
+    bad = (g != w).any(axis=1)
+    if bad.any():
+        i = int(np.flatnonzero(bad)[0])
+        fields = [f for f in got.dtype.names if not np.array_equal(got[i][f], want[i][f])]
+        raise AssertionError(f"{what}: {int(bad.sum())} of {len(got)} records differ; first at {i}, fields {fields}\n"
+                             f" got  {got[i]}\n want {want[i]}")

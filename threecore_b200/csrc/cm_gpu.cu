@@ -1,0 +1,723 @@
+// cm_gpu.cu -- C ABI of libcmgpu.so: context, map upload (flat arrays -> packed
+// device layout), batch launches and the host<->device pipeline.
+//
+// Boundary it implements: include/cm_gpu.h.  Reference call sites it stands in
+// for: CM_BoxTrace / CM_TransformedBoxTrace / CM_PointContents
+// (code/qcommon/cm_public.h:42-52) and the upload hook after
+// code/qcommon/cm_load.c:734.
+#include "cm_kernels.cuh"
+#include "../../include/cm_gpu.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+using namespace cmgpu;
+
+static_assert(sizeof(cmgpu_trace_t) == 56, "trace_t layout is ABI (q_shared.h:976-986)");
+static_assert(sizeof(Counters) == sizeof(cmgpu_counters), "counter layouts must agree");
+
+namespace {
+
+thread_local std::string g_createError;
+
+constexpr int kBlock = 128;
+constexpr int kPipeChunks = 8;           // host batches are split so copies overlap the kernel
+constexpr size_t kMinChunkItems = 1 << 16;
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+}  // namespace
+
+struct cmgpu_ctx_s {
+	int device = 0;
+	std::string err;
+	bool hasMap = false;
+	DevMap map{};
+	std::vector<void *> mapAllocs;
+	int numModels = 0;
+	int noCurves = 0, playerCurveClip = 1;
+	bool counting = false;
+	Counters *dCounters = nullptr;
+	int *dStatus = nullptr;
+	int *hStatus = nullptr;              // pinned
+	unsigned long long launches = 0;
+	cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t evt[kPipeChunks] = {};
+	// grow-only staging for the host-pointer entry points
+	DevBuf bStarts, bEnds, bMins, bMaxs, bModels, bMasks, bOrigins, bRot, bRotIdx, bBoxMins, bBoxMaxs, bOut, bHit;
+	std::vector<float> hostRot;
+	std::vector<int32_t> hostRotIdx;
+};
+
+namespace {
+
+int fail(cmgpu_ctx *ctx, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (ctx) ctx->err = buf; else g_createError = buf;
+	return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                     \
+	do {                                                                                        \
+		cudaError_t e_ = (expr);                                                                \
+		if (e_ != cudaSuccess)                                                                  \
+			return fail(ctx, CMGPU_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+			            __FILE__, __LINE__);                                                    \
+	} while (0)
+
+int reserve(cmgpu_ctx *ctx, DevBuf &b, size_t bytes) {
+	if (bytes <= b.cap) return CMGPU_OK;
+	if (b.p) cudaFree(b.p);
+	b.p = nullptr;
+	b.cap = 0;
+	size_t want = bytes + bytes / 4 + 256;
+	CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+	b.cap = want;
+	return CMGPU_OK;
+}
+
+void releaseBuf(DevBuf &b) {
+	if (b.p) cudaFree(b.p);
+	b.p = nullptr;
+	b.cap = 0;
+}
+
+template <typename T>
+int uploadArray(cmgpu_ctx *ctx, const std::vector<T> &host, const T **dev) {
+	void *p = nullptr;
+	size_t bytes = (host.size() ? host.size() : 1) * sizeof(T);
+	CUDA_TRY(ctx, cudaMalloc(&p, bytes));
+	ctx->mapAllocs.push_back(p);
+	if (host.size()) CUDA_TRY(ctx, cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+	else CUDA_TRY(ctx, cudaMemset(p, 0, bytes));
+	*dev = (const T *)p;
+	return CMGPU_OK;
+}
+
+void freeMap(cmgpu_ctx *ctx) {
+	for (void *p : ctx->mapAllocs) cudaFree(p);
+	ctx->mapAllocs.clear();
+	ctx->hasMap = false;
+	ctx->numModels = 0;
+	memset(&ctx->map, 0, sizeof(ctx->map));
+}
+
+inline int signbitsOf(const float *n) {
+	return (n[0] < 0.0f ? 1 : 0) | (n[1] < 0.0f ? 2 : 0) | (n[2] < 0.0f ? 4 : 0);
+}
+
+// Everything the kernels index is range-checked here so that a malformed map is
+// a CMGPU_ERR_BAD_MAP on the host instead of an out-of-bounds access on the GPU.
+int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
+#define NEED(cond, ...) do { if (!(cond)) return fail(ctx, CMGPU_ERR_BAD_MAP, __VA_ARGS__); } while (0)
+	NEED(f->numPlanes >= 12 && f->planes && f->planeType && f->planeSignbits, "map with no planes");
+	NEED(f->numNodes >= 1 && f->nodes, "map has no nodes");
+	NEED(f->numLeafs >= 1 && f->leafs, "map with no leafs");
+	NEED(f->numBrushes >= 1 && f->brushes && f->brushBounds, "map with no brushes");
+	NEED(f->numBrushSides >= 6 && f->brushsides, "map with no brush sides");
+	NEED(f->numModels >= 1 && f->numModels <= CMGPU_MAX_SUBMODELS, "MAX_SUBMODELS exceeded");
+	NEED(f->numLeafBrushes >= 1 && f->leafbrushes, "no leafbrushes");
+	NEED(f->boxBrush >= 0 && f->boxBrush < f->numBrushes, "bad boxBrush");
+	NEED(f->boxLeafBrush >= 0 && f->boxLeafBrush < f->numLeafBrushes, "bad boxLeafBrush");
+	NEED(f->boxFirstPlane >= 0 && f->boxFirstPlane + 12 <= f->numPlanes, "bad boxFirstPlane");
+	NEED(f->leafbrushes[f->boxLeafBrush] == f->boxBrush, "boxLeafBrush does not name boxBrush");
+	NEED(f->brushes[3 * (size_t)f->boxBrush + 2] == 6, "box brush must have 6 sides");
+
+	for (int i = 0; i < f->numNodes; i++) {
+		const int32_t *nd = f->nodes + 3 * (size_t)i;
+		NEED(nd[0] >= 0 && nd[0] < f->numPlanes, "node %d: bad plane %d", i, nd[0]);
+		for (int c = 1; c <= 2; c++) {
+			if (nd[c] >= 0) NEED(nd[c] < f->numNodes, "node %d: bad child %d", i, nd[c]);
+			else NEED(-1 - nd[c] < f->numLeafs, "node %d: bad leaf %d", i, -1 - nd[c]);
+		}
+	}
+	{   // the node graph must be a tree: a cycle would never terminate on the device
+		std::vector<unsigned char> seen((size_t)f->numNodes, 0);
+		std::vector<int> st;
+		st.push_back(0);
+		while (!st.empty()) {
+			int n = st.back();
+			st.pop_back();
+			NEED(!seen[n], "node %d reachable twice: BSP is not a tree", n);
+			seen[n] = 1;
+			for (int c = 1; c <= 2; c++) {
+				int ch = f->nodes[3 * (size_t)n + c];
+				if (ch >= 0) st.push_back(ch);
+			}
+		}
+	}
+	auto checkLeaf = [&](const int32_t *lf, const char *what, int i) -> int {
+		NEED(lf[1] >= 0 && lf[0] >= 0 && (long long)lf[0] + lf[1] <= f->numLeafBrushes, "%s %d: bad leafbrush range", what, i);
+		NEED(lf[3] >= 0 && lf[2] >= 0 && (long long)lf[2] + lf[3] <= f->numLeafSurfaces, "%s %d: bad leafsurface range", what, i);
+		return CMGPU_OK;
+	};
+	for (int i = 0; i < f->numLeafs; i++) {
+		int rc = checkLeaf(f->leafs + 4 * (size_t)i, "leaf", i);
+		if (rc) return rc;
+	}
+	if (f->numModels > 1) NEED(f->modelLeafs != nullptr, "modelLeafs missing");
+	for (int i = 1; i < f->numModels; i++) {
+		int rc = checkLeaf(f->modelLeafs + 4 * (size_t)i, "model", i);
+		if (rc) return rc;
+	}
+	for (int i = 0; i < f->numLeafBrushes; i++)
+		NEED(f->leafbrushes[i] >= 0 && f->leafbrushes[i] < f->numBrushes, "leafbrush %d out of range", i);
+	for (int i = 0; i < f->numLeafSurfaces; i++)
+		NEED(f->leafsurfaces[i] >= 0 && f->leafsurfaces[i] < f->numSurfaces, "leafsurface %d out of range", i);
+	for (int i = 0; i < f->numBrushes; i++) {
+		const int32_t *b = f->brushes + 3 * (size_t)i;
+		NEED(b[2] >= 0 && b[1] >= 0 && (long long)b[1] + b[2] <= f->numBrushSides, "brush %d: bad side range", i);
+	}
+	for (int i = 0; i < f->numBrushSides; i++) {
+		int pl = f->brushsides[2 * (size_t)i];
+		NEED(pl >= 0 && pl < f->numPlanes, "brushside %d: bad plane", i);
+		NEED(f->planeSignbits[pl] == signbitsOf(f->planes + 4 * (size_t)pl),
+		     "plane %d: signbits do not follow the normal's signs", pl);
+	}
+	for (int i = 0; i < f->numSurfaces; i++)
+		NEED(f->surf2patch[i] >= -1 && f->surf2patch[i] < f->numPatches, "surface %d: bad patch", i);
+	for (int i = 0; i < f->numPatches; i++) {
+		const int32_t *p = f->patches + 6 * (size_t)i;
+		NEED(p[2] >= 0 && p[3] >= 0 && (long long)p[2] + p[3] <= f->numPatchPlanes, "patch %d: bad plane range", i);
+		NEED(p[4] >= 0 && p[5] >= 0 && (long long)p[4] + p[5] <= f->numFacets, "patch %d: bad facet range", i);
+		for (int k = 0; k < p[5]; k++) {
+			const int32_t *fc = f->facets + 3 * (size_t)(p[4] + k);
+			NEED(fc[0] >= 0 && fc[0] < p[3], "patch %d facet %d: bad surface plane", i, k);
+			NEED(fc[1] >= 0 && fc[2] >= 0 && (long long)fc[2] + fc[1] <= f->numBorders, "patch %d facet %d: bad borders", i, k);
+			for (int j = 0; j < fc[1]; j++) {
+				int bp = f->borders[2 * (size_t)(fc[2] + j)];
+				NEED(bp >= 0 && bp < p[3], "patch %d facet %d border %d: bad plane", i, k, j);
+			}
+		}
+	}
+	for (int i = 0; i < f->numPatchPlanes; i++)
+		NEED(f->patchPlaneSignbits[i] == signbitsOf(f->patchPlanes + 4 * (size_t)i),
+		     "patch plane %d: signbits do not follow the normal's signs", i);
+#undef NEED
+	return CMGPU_OK;
+}
+
+inline float bitsToFloat(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
+inline int32_t floatToBits(float f) { int32_t v; memcpy(&v, &f, 4); return v; }
+
+int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
+	DevMap &m = ctx->map;
+	std::vector<int4> nodes((size_t)f->numNodes);
+	std::vector<float4> nodePlanes((size_t)f->numNodes);
+	for (int i = 0; i < f->numNodes; i++) {
+		const int32_t *nd = f->nodes + 3 * (size_t)i;
+		const float *pl = f->planes + 4 * (size_t)nd[0];
+		int type = f->planeType[nd[0]] < 3 ? f->planeType[nd[0]] : 3;
+		nodes[i] = make_int4(nd[1], nd[2], type, floatToBits(pl[3]));
+		nodePlanes[i] = make_float4(pl[0], pl[1], pl[2], pl[3]);
+	}
+	std::vector<int4> leafs((size_t)f->numLeafs);
+	for (int i = 0; i < f->numLeafs; i++) {
+		const int32_t *l = f->leafs + 4 * (size_t)i;
+		leafs[i] = make_int4(l[0], l[1], l[2], l[3]);
+	}
+	std::vector<int> leafbrushes(f->leafbrushes, f->leafbrushes + f->numLeafBrushes);
+	std::vector<int> leafsurfaces;
+	if (f->numLeafSurfaces) leafsurfaces.assign(f->leafsurfaces, f->leafsurfaces + f->numLeafSurfaces);
+	std::vector<float4> brushBox(2 * (size_t)f->numBrushes);
+	std::vector<int> brushNumSides((size_t)f->numBrushes);
+	for (int i = 0; i < f->numBrushes; i++) {
+		const int32_t *b = f->brushes + 3 * (size_t)i;
+		const float *bb = f->brushBounds + 6 * (size_t)i;
+		brushBox[2 * (size_t)i] = make_float4(bb[0], bb[1], bb[2], bitsToFloat(b[0]));
+		brushBox[2 * (size_t)i + 1] = make_float4(bb[3], bb[4], bb[5], bitsToFloat(b[1]));
+		brushNumSides[i] = b[2];
+	}
+	std::vector<float4> sidePlanes((size_t)f->numBrushSides);
+	std::vector<int2> sideMeta((size_t)f->numBrushSides);
+	for (int i = 0; i < f->numBrushSides; i++) {
+		int pl = f->brushsides[2 * (size_t)i];
+		const float *p = f->planes + 4 * (size_t)pl;
+		sidePlanes[i] = make_float4(p[0], p[1], p[2], p[3]);
+		sideMeta[i] = make_int2(f->brushsides[2 * (size_t)i + 1], (int)f->planeType[pl] | ((int)f->planeSignbits[pl] << 8));
+	}
+	std::vector<int4> modelLeafs((size_t)f->numModels);
+	for (int i = 0; i < f->numModels; i++) {
+		if (i == 0 || !f->modelLeafs) { modelLeafs[i] = make_int4(0, 0, 0, 0); continue; }
+		const int32_t *l = f->modelLeafs + 4 * (size_t)i;
+		modelLeafs[i] = make_int4(l[0], l[1], l[2], l[3]);
+	}
+	std::vector<int> surf2patch;
+	if (f->numSurfaces) surf2patch.assign(f->surf2patch, f->surf2patch + f->numSurfaces);
+	std::vector<int4> patchInfo(2 * (size_t)f->numPatches);
+	std::vector<float4> patchBox(2 * (size_t)f->numPatches);
+	for (int i = 0; i < f->numPatches; i++) {
+		const int32_t *p = f->patches + 6 * (size_t)i;
+		const float *pb = f->patchBounds + 6 * (size_t)i;
+		patchInfo[2 * (size_t)i] = make_int4(p[0], p[1], p[2], p[3]);
+		patchInfo[2 * (size_t)i + 1] = make_int4(p[4], p[5], 0, 0);
+		patchBox[2 * (size_t)i] = make_float4(pb[0], pb[1], pb[2], 0.0f);
+		patchBox[2 * (size_t)i + 1] = make_float4(pb[3], pb[4], pb[5], 0.0f);
+	}
+	std::vector<float4> patchPlanes((size_t)f->numPatchPlanes);
+	for (int i = 0; i < f->numPatchPlanes; i++) {
+		const float *p = f->patchPlanes + 4 * (size_t)i;
+		patchPlanes[i] = make_float4(p[0], p[1], p[2], p[3]);
+	}
+	std::vector<int4> facets((size_t)f->numFacets);
+	for (int i = 0; i < f->numFacets; i++) {
+		const int32_t *fc = f->facets + 3 * (size_t)i;
+		facets[i] = make_int4(fc[0], fc[1], fc[2], 0);
+	}
+	std::vector<int> borders((size_t)f->numBorders);
+	for (int i = 0; i < f->numBorders; i++) {
+		borders[i] = f->borders[2 * (size_t)i] | (f->borders[2 * (size_t)i + 1] ? (int)0x80000000u : 0);
+	}
+
+	int rc;
+#define UP(vec, field) if ((rc = uploadArray(ctx, vec, &m.field)) != CMGPU_OK) return rc
+	UP(nodes, nodes); UP(nodePlanes, nodePlanes); UP(leafs, leafs); UP(leafbrushes, leafbrushes);
+	UP(leafsurfaces, leafsurfaces); UP(brushBox, brushBox); UP(brushNumSides, brushNumSides);
+	UP(sidePlanes, sidePlanes); UP(sideMeta, sideMeta); UP(modelLeafs, modelLeafs); UP(surf2patch, surf2patch);
+	UP(patchInfo, patchInfo); UP(patchBox, patchBox); UP(patchPlanes, patchPlanes); UP(facets, facets);
+	UP(borders, borders);
+#undef UP
+	m.numNodes = f->numNodes;
+	m.numModels = f->numModels;
+	m.boxBrush = f->boxBrush;
+	m.boxLeafBrush = f->boxLeafBrush;
+	m.noCurves = ctx->noCurves;
+	m.playerCurveClip = ctx->playerCurveClip;
+	ctx->numModels = f->numModels;
+	ctx->hasMap = true;
+	return CMGPU_OK;
+}
+
+// CM_ClipHandleToModel (cm_load.c:768-798): a handle is a loaded inline model or 1023
+int checkHandles(cmgpu_ctx *ctx, int n, const int32_t *models) {
+	if (!models) return CMGPU_OK;
+	for (int i = 0; i < n; i++) {
+		int h = models[i];
+		if (h == CMGPU_BOX_MODEL_HANDLE) continue;
+		if (h < 0 || h >= ctx->numModels) return fail(ctx, CMGPU_ERR_BAD_HANDLE, "CM_ClipHandleToModel: bad handle %i (item %d)", h, i);
+	}
+	return CMGPU_OK;
+}
+
+int launchTrace(cmgpu_ctx *ctx, const TraceBatch &q, cudaStream_t s) {
+	if (q.n <= 0) return CMGPU_OK;
+	ctx->map.noCurves = ctx->noCurves;
+	ctx->map.playerCurveClip = ctx->playerCurveClip;
+	int grid = (q.n + kBlock - 1) / kBlock;
+	if (ctx->counting) traceKernel<true><<<grid, kBlock, 0, s>>>(ctx->map, q);
+	else               traceKernel<false><<<grid, kBlock, 0, s>>>(ctx->map, q);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int cmgpu_abi_version(void) { return CMGPU_ABI_VERSION; }
+
+int cmgpu_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+const char *cmgpu_last_error(const cmgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int cmgpu_create(cmgpu_ctx **out, int device) {
+	if (!out) return fail(nullptr, CMGPU_ERR_INVALID, "cmgpu_create: out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		return fail(nullptr, CMGPU_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU path",
+		            e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+	}
+	if (device < 0 || device >= n) return fail(nullptr, CMGPU_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, CMGPU_ERR_CUDA, "cudaGetDeviceProperties failed");
+	if (prop.major != 10) {
+		return fail(nullptr, CMGPU_ERR_NO_DEVICE, "device %d is sm_%d%d; libcmgpu is built for sm_100a only", device, prop.major, prop.minor);
+	}
+	cmgpu_ctx *ctx = new cmgpu_ctx_s();
+	ctx->device = device;
+	cudaSetDevice(device);
+	bool ok = true;
+	for (auto &s : ctx->streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+	for (auto &ev : ctx->evt) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaMalloc(&ctx->dCounters, sizeof(Counters)) == cudaSuccess;
+	ok = ok && cudaMemset(ctx->dCounters, 0, sizeof(Counters)) == cudaSuccess;
+	ok = ok && cudaMalloc(&ctx->dStatus, sizeof(int)) == cudaSuccess;
+	ok = ok && cudaMemset(ctx->dStatus, 0, sizeof(int)) == cudaSuccess;
+	ok = ok && cudaMallocHost(&ctx->hStatus, sizeof(int)) == cudaSuccess;
+	if (!ok) {
+		g_createError = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+		cmgpu_destroy(ctx);
+		return CMGPU_ERR_CUDA;
+	}
+	*out = ctx;
+	return CMGPU_OK;
+}
+
+void cmgpu_destroy(cmgpu_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	freeMap(ctx);
+	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
+	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit}) releaseBuf(*b);
+	if (ctx->dCounters) cudaFree(ctx->dCounters);
+	if (ctx->dStatus) cudaFree(ctx->dStatus);
+	if (ctx->hStatus) cudaFreeHost(ctx->hStatus);
+	for (auto &s : ctx->streams) if (s) cudaStreamDestroy(s);
+	for (auto &ev : ctx->evt) if (ev) cudaEventDestroy(ev);
+	delete ctx;
+}
+
+int cmgpu_upload(cmgpu_ctx *ctx, const cmgpu_flatmap *map) {
+	if (!ctx || !map) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_upload: NULL argument");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	int rc = validate(ctx, map);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaDeviceSynchronize());
+	freeMap(ctx);
+	rc = packAndUpload(ctx, map);
+	if (rc) freeMap(ctx);
+	return rc;
+}
+
+int cmgpu_clear(cmgpu_ctx *ctx) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	freeMap(ctx);
+	return CMGPU_OK;
+}
+
+int cmgpu_set_cvars(cmgpu_ctx *ctx, int noCurves, int playerCurveClip) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	ctx->noCurves = noCurves;
+	ctx->playerCurveClip = playerCurveClip;
+	return CMGPU_OK;
+}
+
+int cmgpu_num_inline_models(const cmgpu_ctx *ctx) { return ctx ? ctx->numModels : 0; }
+
+void cmgpu_rotation_matrices(int n, const float *angles, float *matrices, int32_t *rot_index) {
+	// AngleVectors, q_math.c:999-1032: angle scaled in double and rounded to float, sin/cos of that
+	// float in double rounded to float, all products/sums in float (this TU is built with -fmad=false
+	// for device AND host code, so nothing below is contracted).
+	const double k = M_PI * 2 / 360;
+	for (int i = 0; i < n; i++) {
+		const float *a = angles + 3 * (size_t)i;
+		if (!(a[0] || a[1] || a[2])) {
+			rot_index[i] = -1;
+			continue;
+		}
+		rot_index[i] = i;
+		float ang;
+		ang = (float)((double)a[1] * k); const float sy = (float)sin((double)ang), cy = (float)cos((double)ang);
+		ang = (float)((double)a[0] * k); const float sp = (float)sin((double)ang), cp = (float)cos((double)ang);
+		ang = (float)((double)a[2] * k); const float sr = (float)sin((double)ang), cr = (float)cos((double)ang);
+		float *m = matrices + 9 * (size_t)i;
+		// row 0: forward
+		m[0] = cp * cy;
+		m[1] = cp * sy;
+		m[2] = -sp;
+		// row 1: -right (CreateRotationMatrix negates the right vector, cm_trace.c:65-68)
+		const float nsr = -1 * sr, ncr = -1 * cr;
+		m[3] = -((nsr * sp) * cy + ncr * -sy);
+		m[4] = -((nsr * sp) * sy + ncr * cy);
+		m[5] = -(nsr * cp);
+		// row 2: up
+		m[6] = (cr * sp) * cy + -sr * -sy;
+		m[7] = (cr * sp) * sy + -sr * cy;
+		m[8] = cr * cp;
+	}
+}
+
+int cmgpu_enable_counters(cmgpu_ctx *ctx, int enable) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	ctx->counting = enable != 0;
+	return CMGPU_OK;
+}
+
+int cmgpu_read_counters(cmgpu_ctx *ctx, cmgpu_counters *out, int reset) {
+	if (!ctx || !out) return CMGPU_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaDeviceSynchronize());
+	CUDA_TRY(ctx, cudaMemcpy(out, ctx->dCounters, sizeof(Counters), cudaMemcpyDeviceToHost));
+	if (reset) CUDA_TRY(ctx, cudaMemset(ctx->dCounters, 0, sizeof(Counters)));
+	return CMGPU_OK;
+}
+
+unsigned long long cmgpu_launch_count(const cmgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int cmgpu_check_status(cmgpu_ctx *ctx, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	cudaStream_t s = (cudaStream_t)stream;
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hStatus, ctx->dStatus, sizeof(int), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	if (*ctx->hStatus) {
+		CUDA_TRY(ctx, cudaMemsetAsync(ctx->dStatus, 0, sizeof(int), s));
+		return fail(ctx, CMGPU_ERR_LIMIT, "traversal stack overflow: BSP deeper than %d pending splits", kMaxDepth);
+	}
+	return CMGPU_OK;
+}
+
+// ---- device-pointer entry points ---------------------------------------------------------
+int cmgpu_box_trace_batch_device(cmgpu_ctx *ctx, int n,
+                                 const float *starts, const float *ends,
+                                 const float *mins, const float *maxs, int hull_stride,
+                                 const int32_t *models, const int32_t *masks, int mask_stride,
+                                 const float *origins, const float *rotations, const int32_t *rot_index,
+                                 const float *boxmins, const float *boxmaxs,
+                                 cmgpu_trace_t *results, int32_t *hit_ids, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!starts || !ends || !masks || !results)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_box_trace_batch_device: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if ((mins == nullptr) != (maxs == nullptr)) return fail(ctx, CMGPU_ERR_INVALID, "mins and maxs must both be given or both be NULL");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	TraceBatch q{};
+	q.n = n; q.starts = starts; q.ends = ends; q.mins = mins; q.maxs = maxs; q.hullStride = hull_stride ? 1 : 0;
+	q.models = models; q.masks = masks; q.maskStride = mask_stride ? 1 : 0;
+	q.origins = origins; q.rotations = rotations; q.rotIndex = rotations ? rot_index : nullptr;
+	q.boxmins = boxmins; q.boxmaxs = boxmins ? boxmaxs : nullptr;
+	if (!q.boxmaxs) q.boxmins = nullptr;
+	q.out = reinterpret_cast<uint2 *>(results); q.hitIds = hit_ids;
+	q.status = ctx->dStatus; q.counters = ctx->dCounters;
+	return launchTrace(ctx, q, (cudaStream_t)stream);
+}
+
+int cmgpu_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points,
+                                      const int32_t *models, const float *origins,
+                                      const float *rotations, const int32_t *rot_index,
+                                      const float *boxmins, const float *boxmaxs,
+                                      int32_t *contents, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !contents))) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_point_contents_batch_device: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	PointBatch q{};
+	q.n = n; q.points = points; q.models = models; q.origins = origins;
+	q.rotations = rotations; q.rotIndex = rotations ? rot_index : nullptr;
+	q.boxmins = boxmins; q.boxmaxs = boxmins ? boxmaxs : nullptr;
+	if (!q.boxmaxs) q.boxmins = nullptr;
+	q.out = contents;
+	int grid = (n + kBlock - 1) / kBlock;
+	pointContentsKernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+// ---- host-pointer entry points -----------------------------------------------------------
+// The batch is cut into chunks; chunk c's H2D copy, kernel and D2H copy are issued on stream
+// c % 3, so the copy engines (one per direction) and the SMs work on different chunks at once.
+static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                     const float *mins, const float *maxs, int hull_stride,
+                     const int32_t *models, const int32_t *masks, int mask_stride,
+                     const float *origins, const float *angles,
+                     const float *boxmins, const float *boxmaxs,
+                     cmgpu_trace_t *results, int32_t *hit_ids) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!starts || !ends || !masks || !results)))
+		return fail(ctx, CMGPU_ERR_INVALID, "trace batch: bad argument");
+	if ((mins == nullptr) != (maxs == nullptr)) return fail(ctx, CMGPU_ERR_INVALID, "mins and maxs must both be given or both be NULL");
+	if (origins && !angles) return fail(ctx, CMGPU_ERR_INVALID, "origins without angles");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (n == 0) return CMGPU_OK;
+	int rc = checkHandles(ctx, n, models);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	hull_stride = hull_stride ? 1 : 0;
+	mask_stride = mask_stride ? 1 : 0;
+	if (!boxmins || !boxmaxs) boxmins = boxmaxs = nullptr;
+
+	const size_t N = (size_t)n;
+	const size_t v3 = 3 * sizeof(float);
+	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
+	if ((rc = reserve(ctx, ctx->bEnds, N * v3))) return rc;
+	if (mins) {
+		if ((rc = reserve(ctx, ctx->bMins, (hull_stride ? N : 1) * v3))) return rc;
+		if ((rc = reserve(ctx, ctx->bMaxs, (hull_stride ? N : 1) * v3))) return rc;
+	}
+	if (models && (rc = reserve(ctx, ctx->bModels, N * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bMasks, (mask_stride ? N : 1) * 4))) return rc;
+	if (origins) {
+		if ((rc = reserve(ctx, ctx->bOrigins, N * v3))) return rc;
+		if ((rc = reserve(ctx, ctx->bRot, N * 9 * sizeof(float)))) return rc;
+		if ((rc = reserve(ctx, ctx->bRotIdx, N * 4))) return rc;
+		ctx->hostRot.resize(N * 9);
+		ctx->hostRotIdx.resize(N);
+		cmgpu_rotation_matrices(n, angles, ctx->hostRot.data(), ctx->hostRotIdx.data());
+	}
+	if (boxmins) {
+		if ((rc = reserve(ctx, ctx->bBoxMins, N * v3))) return rc;
+		if ((rc = reserve(ctx, ctx->bBoxMaxs, N * v3))) return rc;
+	}
+	if ((rc = reserve(ctx, ctx->bOut, N * sizeof(cmgpu_trace_t)))) return rc;
+	if (hit_ids && (rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
+
+	cudaStream_t s0 = ctx->streams[0];
+	if (mins && !hull_stride) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMins.p, mins, v3, cudaMemcpyHostToDevice, s0));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMaxs.p, maxs, v3, cudaMemcpyHostToDevice, s0));
+	}
+	if (!mask_stride) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMasks.p, masks, 4, cudaMemcpyHostToDevice, s0));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s0));
+
+	int chunks = (int)((N + kMinChunkItems - 1) / kMinChunkItems);
+	if (chunks > kPipeChunks) chunks = kPipeChunks;
+	if (chunks < 1) chunks = 1;
+	for (int c = 0; c < chunks; c++) {
+		const size_t lo = N * (size_t)c / (size_t)chunks, hi = N * (size_t)(c + 1) / (size_t)chunks;
+		const size_t cnt = hi - lo;
+		if (!cnt) continue;
+		cudaStream_t s = ctx->streams[c % 3];
+#define H2D(buf, src, elem) CUDA_TRY(ctx, cudaMemcpyAsync((char *)(buf).p + lo * (elem), (const char *)(src) + lo * (elem), cnt * (elem), cudaMemcpyHostToDevice, s))
+		H2D(ctx->bStarts, starts, v3);
+		H2D(ctx->bEnds, ends, v3);
+		if (mins && hull_stride) { H2D(ctx->bMins, mins, v3); H2D(ctx->bMaxs, maxs, v3); }
+		if (models) H2D(ctx->bModels, models, 4);
+		if (mask_stride) H2D(ctx->bMasks, masks, 4);
+		if (origins) {
+			H2D(ctx->bOrigins, origins, v3);
+			H2D(ctx->bRot, ctx->hostRot.data(), 9 * sizeof(float));
+			H2D(ctx->bRotIdx, ctx->hostRotIdx.data(), 4);
+		}
+		if (boxmins) { H2D(ctx->bBoxMins, boxmins, v3); H2D(ctx->bBoxMaxs, boxmaxs, v3); }
+#undef H2D
+		TraceBatch q{};
+		q.n = (int)cnt;
+		q.starts = (const float *)ctx->bStarts.p + 3 * lo;
+		q.ends = (const float *)ctx->bEnds.p + 3 * lo;
+		if (mins) {
+			q.mins = (const float *)ctx->bMins.p + (hull_stride ? 3 * lo : 0);
+			q.maxs = (const float *)ctx->bMaxs.p + (hull_stride ? 3 * lo : 0);
+		}
+		q.hullStride = hull_stride;
+		q.models = models ? (const int *)ctx->bModels.p + lo : nullptr;
+		q.masks = (const int *)ctx->bMasks.p + (mask_stride ? lo : 0);
+		q.maskStride = mask_stride;
+		if (origins) {
+			q.origins = (const float *)ctx->bOrigins.p + 3 * lo;
+			// rot_index values are absolute item numbers: keep the base pointer unshifted
+			q.rotations = (const float *)ctx->bRot.p;
+			q.rotIndex = (const int *)ctx->bRotIdx.p + lo;
+		}
+		if (boxmins) {
+			q.boxmins = (const float *)ctx->bBoxMins.p + 3 * lo;
+			q.boxmaxs = (const float *)ctx->bBoxMaxs.p + 3 * lo;
+		}
+		q.out = reinterpret_cast<uint2 *>((cmgpu_trace_t *)ctx->bOut.p + lo);
+		q.hitIds = hit_ids ? (int *)ctx->bHit.p + lo : nullptr;
+		q.status = ctx->dStatus;
+		q.counters = ctx->dCounters;
+		if ((rc = launchTrace(ctx, q, s))) return rc;
+		CUDA_TRY(ctx, cudaMemcpyAsync(results + lo, (cmgpu_trace_t *)ctx->bOut.p + lo, cnt * sizeof(cmgpu_trace_t), cudaMemcpyDeviceToHost, s));
+		if (hit_ids) CUDA_TRY(ctx, cudaMemcpyAsync(hit_ids + lo, (int *)ctx->bHit.p + lo, cnt * 4, cudaMemcpyDeviceToHost, s));
+	}
+	for (auto &s : ctx->streams) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return cmgpu_check_status(ctx, ctx->streams[0]);
+}
+
+int cmgpu_box_trace_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                          const float *mins, const float *maxs, int hull_stride,
+                          const int32_t *models, const int32_t *masks, int mask_stride,
+                          const float *boxmins, const float *boxmaxs,
+                          cmgpu_trace_t *results, int32_t *hit_ids) {
+	return traceHost(ctx, n, starts, ends, mins, maxs, hull_stride, models, masks, mask_stride,
+	                 nullptr, nullptr, boxmins, boxmaxs, results, hit_ids);
+}
+
+int cmgpu_transformed_box_trace_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                                      const float *mins, const float *maxs, int hull_stride,
+                                      const int32_t *models, const int32_t *masks, int mask_stride,
+                                      const float *origins, const float *angles,
+                                      const float *boxmins, const float *boxmaxs,
+                                      cmgpu_trace_t *results, int32_t *hit_ids) {
+	if (ctx && (!origins || !angles)) return fail(ctx, CMGPU_ERR_INVALID, "transformed trace needs origins and angles");
+	if (ctx && n > 0 && !models) return fail(ctx, CMGPU_ERR_INVALID, "transformed trace needs models");
+	return traceHost(ctx, n, starts, ends, mins, maxs, hull_stride, models, masks, mask_stride,
+	                 origins, angles, boxmins, boxmaxs, results, hit_ids);
+}
+
+int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
+                               const int32_t *models, const float *origins, const float *angles,
+                               const float *boxmins, const float *boxmaxs, int32_t *contents) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !contents))) return fail(ctx, CMGPU_ERR_INVALID, "point contents batch: bad argument");
+	if (origins && !angles) return fail(ctx, CMGPU_ERR_INVALID, "origins without angles");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (n == 0) return CMGPU_OK;
+	int rc = checkHandles(ctx, n, models);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if (!boxmins || !boxmaxs) boxmins = boxmaxs = nullptr;
+	const size_t N = (size_t)n, v3 = 3 * sizeof(float);
+	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
+	if (models && (rc = reserve(ctx, ctx->bModels, N * 4))) return rc;
+	if (origins) {
+		if ((rc = reserve(ctx, ctx->bOrigins, N * v3))) return rc;
+		if ((rc = reserve(ctx, ctx->bRot, N * 9 * sizeof(float)))) return rc;
+		if ((rc = reserve(ctx, ctx->bRotIdx, N * 4))) return rc;
+		ctx->hostRot.resize(N * 9);
+		ctx->hostRotIdx.resize(N);
+		cmgpu_rotation_matrices(n, angles, ctx->hostRot.data(), ctx->hostRotIdx.data());
+	}
+	if (boxmins) {
+		if ((rc = reserve(ctx, ctx->bBoxMins, N * v3))) return rc;
+		if ((rc = reserve(ctx, ctx->bBoxMaxs, N * v3))) return rc;
+	}
+	if ((rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, points, N * v3, cudaMemcpyHostToDevice, s));
+	if (models) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bModels.p, models, N * 4, cudaMemcpyHostToDevice, s));
+	if (origins) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bOrigins.p, origins, N * v3, cudaMemcpyHostToDevice, s));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bRot.p, ctx->hostRot.data(), N * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bRotIdx.p, ctx->hostRotIdx.data(), N * 4, cudaMemcpyHostToDevice, s));
+	}
+	if (boxmins) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bBoxMins.p, boxmins, N * v3, cudaMemcpyHostToDevice, s));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bBoxMaxs.p, boxmaxs, N * v3, cudaMemcpyHostToDevice, s));
+	}
+	rc = cmgpu_point_contents_batch_device(ctx, n, (const float *)ctx->bStarts.p,
+	                                       models ? (const int32_t *)ctx->bModels.p : nullptr,
+	                                       origins ? (const float *)ctx->bOrigins.p : nullptr,
+	                                       origins ? (const float *)ctx->bRot.p : nullptr,
+	                                       origins ? (const int32_t *)ctx->bRotIdx.p : nullptr,
+	                                       boxmins ? (const float *)ctx->bBoxMins.p : nullptr,
+	                                       boxmins ? (const float *)ctx->bBoxMaxs.p : nullptr,
+	                                       (int32_t *)ctx->bHit.p, s);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(contents, ctx->bHit.p, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return CMGPU_OK;
+}
+
+}  // extern "C"

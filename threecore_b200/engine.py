@@ -1,0 +1,398 @@
+"""Python host binding of libcmgpu.so (include/cm_gpu.h) -- plumbing only.
+
+The product is the CUDA library; this module loads it with ctypes, mirrors the
+C structs and offers numpy (host-pointer) and torch (device-pointer) call
+styles.  PyTorch is used for device memory, streams and torch.distributed.
+There is NO CPU implementation here: if the library is missing or no B200 is
+visible, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcmgpu.so")
+BOX_MODEL_HANDLE = 1023
+
+TRACE_DTYPE = np.dtype([
+    ("allsolid", "<i4"), ("startsolid", "<i4"), ("fraction", "<f4"), ("endpos", "<f4", (3,)),
+    ("plane_normal", "<f4", (3,)), ("plane_dist", "<f4"), ("plane_type", "u1"),
+    ("plane_signbits", "u1"), ("plane_pad", "u1", (2,)),
+    ("surfaceFlags", "<i4"), ("contents", "<i4"), ("entityNum", "<i4")])
+assert TRACE_DTYPE.itemsize == 56
+
+ERR_NAMES = {0: "OK", 1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "NO_MAP", 5: "BAD_HANDLE", 6: "BAD_MAP",
+             7: "NOMEM", 8: "LIMIT"}
+
+
+class CMGPUError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cmgpu error {code} ({ERR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class _FlatMap(C.Structure):
+    _fields_ = [
+        ("numPlanes", C.c_int32), ("planes", C.c_void_p), ("planeType", C.c_void_p), ("planeSignbits", C.c_void_p),
+        ("numNodes", C.c_int32), ("nodes", C.c_void_p),
+        ("numLeafs", C.c_int32), ("leafs", C.c_void_p),
+        ("numLeafBrushes", C.c_int32), ("leafbrushes", C.c_void_p),
+        ("numLeafSurfaces", C.c_int32), ("leafsurfaces", C.c_void_p),
+        ("numBrushes", C.c_int32), ("brushes", C.c_void_p), ("brushBounds", C.c_void_p),
+        ("numBrushSides", C.c_int32), ("brushsides", C.c_void_p),
+        ("numModels", C.c_int32), ("modelLeafs", C.c_void_p), ("modelBounds", C.c_void_p),
+        ("numSurfaces", C.c_int32), ("surf2patch", C.c_void_p),
+        ("numPatches", C.c_int32), ("patches", C.c_void_p), ("patchBounds", C.c_void_p),
+        ("numPatchPlanes", C.c_int32), ("patchPlanes", C.c_void_p), ("patchPlaneSignbits", C.c_void_p),
+        ("numFacets", C.c_int32), ("facets", C.c_void_p),
+        ("numBorders", C.c_int32), ("borders", C.c_void_p),
+        ("leafClusterArea", C.c_void_p),
+        ("boxBrush", C.c_int32), ("boxFirstPlane", C.c_int32), ("boxFirstSide", C.c_int32), ("boxLeafBrush", C.c_int32),
+    ]
+
+
+class _Counters(C.Structure):
+    _fields_ = [(k, C.c_ulonglong) for k in ("traces", "nodes", "leafs", "brushRefs", "brushBounds", "brushSides",
+                                             "crossings", "splits", "patches", "patchPlanes", "facets")]
+
+
+# flat-dict key -> (struct count field, struct pointer field, dtype, columns)
+_ARRAYS = [
+    ("planes", "numPlanes", "planes", np.float32, 4),
+    ("plane_type", "numPlanes", "planeType", np.uint8, 0),
+    ("plane_signbits", "numPlanes", "planeSignbits", np.uint8, 0),
+    ("nodes", "numNodes", "nodes", np.int32, 3),
+    ("leafs", "numLeafs", "leafs", np.int32, 4),
+    ("leaf_cluster_area", "numLeafs", "leafClusterArea", np.int32, 2),
+    ("leafbrushes", "numLeafBrushes", "leafbrushes", np.int32, 0),
+    ("leafsurfaces", "numLeafSurfaces", "leafsurfaces", np.int32, 0),
+    ("brushes", "numBrushes", "brushes", np.int32, 3),
+    ("brush_bounds", "numBrushes", "brushBounds", np.float32, 6),
+    ("brushsides", "numBrushSides", "brushsides", np.int32, 2),
+    ("model_leafs", "numModels", "modelLeafs", np.int32, 4),
+    ("model_bounds", "numModels", "modelBounds", np.float32, 6),
+    ("surf2patch", "numSurfaces", "surf2patch", np.int32, 0),
+    ("patches", "numPatches", "patches", np.int32, 6),
+    ("patch_bounds", "numPatches", "patchBounds", np.float32, 6),
+    ("patch_planes", "numPatchPlanes", "patchPlanes", np.float32, 4),
+    ("patch_plane_signbits", "numPatchPlanes", "patchPlaneSignbits", np.int32, 0),
+    ("facets", "numFacets", "facets", np.int32, 3),
+    ("borders", "numBorders", "borders", np.int32, 2),
+]
+_SCALARS = [("box_brush", "boxBrush"), ("box_first_plane", "boxFirstPlane"), ("box_first_side", "boxFirstSide"),
+            ("box_leaf_brush", "boxLeafBrush")]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libcmgpu.so; loud failure when it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C threecore_b200/csrc). The engine has no CPU path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.cmgpu_last_error.restype = C.c_char_p
+    lib.cmgpu_last_error.argtypes = [C.c_void_p]
+    lib.cmgpu_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.cmgpu_destroy.argtypes = [C.c_void_p]
+    lib.cmgpu_destroy.restype = None
+    lib.cmgpu_flatmap_from_bsp.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(_FlatMap)), C.c_char_p, C.c_size_t]
+    lib.cmgpu_flatmap_free.argtypes = [C.POINTER(_FlatMap)]
+    lib.cmgpu_flatmap_free.restype = None
+    lib.cmgpu_upload.argtypes = [C.c_void_p, C.POINTER(_FlatMap)]
+    lib.cmgpu_clear.argtypes = [C.c_void_p]
+    lib.cmgpu_set_cvars.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.cmgpu_num_inline_models.argtypes = [C.c_void_p]
+    lib.cmgpu_launch_count.argtypes = [C.c_void_p]
+    lib.cmgpu_launch_count.restype = C.c_ulonglong
+    lib.cmgpu_enable_counters.argtypes = [C.c_void_p, C.c_int]
+    lib.cmgpu_read_counters.argtypes = [C.c_void_p, C.POINTER(_Counters), C.c_int]
+    lib.cmgpu_check_status.argtypes = [C.c_void_p, C.c_void_p]
+    vp = C.c_void_p
+    lib.cmgpu_box_trace_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.cmgpu_transformed_box_trace_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int,
+                                                      vp, vp, vp, vp, vp, vp]
+    lib.cmgpu_point_contents_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.cmgpu_box_trace_batch_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int,
+                                                 vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cmgpu_point_contents_batch_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cmgpu_rotation_matrices.argtypes = [C.c_int, vp, vp, vp]
+    lib.cmgpu_rotation_matrices.restype = None
+    if lib.cmgpu_abi_version() != 1:
+        raise ImportError("libcmgpu.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class FlatMap:
+    """A cmgpu_flatmap: either produced by the library's own BSP loader or assembled from arrays."""
+
+    def __init__(self):
+        self._ptr = None          # POINTER(_FlatMap) owned by the library
+        self._struct = None       # _FlatMap assembled here
+        self._keep = []
+
+    @classmethod
+    def from_bsp(cls, data: bytes) -> "FlatMap":
+        lib = load_library()
+        self = cls()
+        out = C.POINTER(_FlatMap)()
+        err = C.create_string_buffer(512)
+        rc = lib.cmgpu_flatmap_from_bsp(bytes(data), len(data), C.byref(out), err, len(err))
+        if rc:
+            raise CMGPUError(rc, err.value.decode(errors="replace"))
+        self._ptr = out
+        return self
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "FlatMap":
+        """From a flat dict (same keys as to_dict); used to upload a map flattened elsewhere,
+        e.g. by the engine-side shim out of a loaded clipMap_t."""
+        self = cls()
+        s = _FlatMap()
+        for key, cnt, ptr, dtype, cols in _ARRAYS:
+            if key not in d:
+                if key == "leaf_cluster_area":
+                    continue
+                raise KeyError(key)
+            a = np.ascontiguousarray(d[key], dtype=dtype)
+            n = a.shape[0]
+            if a.size == 0:
+                a = np.zeros(8, dtype=dtype)
+            self._keep.append(a)
+            setattr(s, cnt, n)
+            setattr(s, ptr, a.ctypes.data)
+        for key, fld in _SCALARS:
+            setattr(s, fld, int(d[key]))
+        self._struct = s
+        return self
+
+    @property
+    def struct(self) -> _FlatMap:
+        return self._ptr.contents if self._ptr is not None else self._struct
+
+    def pointer(self):
+        return self._ptr if self._ptr is not None else C.pointer(self._struct)
+
+    def to_dict(self) -> dict:
+        s = self.struct
+        d = {}
+        for key, cnt, ptr, dtype, cols in _ARRAYS:
+            n = getattr(s, cnt)
+            addr = getattr(s, ptr)
+            shape = (n, cols) if cols else (n,)
+            if not addr or n == 0:
+                d[key] = np.zeros(shape, dtype=dtype)
+                continue
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            buf = (C.c_char * nbytes).from_address(addr)
+            d[key] = np.frombuffer(buf, dtype=dtype).reshape(shape).copy()
+        for key, fld in _SCALARS:
+            d[key] = int(getattr(s, fld))
+        return d
+
+    def __del__(self):
+        if self._ptr is not None and _lib is not None:
+            _lib.cmgpu_flatmap_free(self._ptr)
+            self._ptr = None
+
+
+def _f(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def rotation_matrices(angles):
+    """Host AngleVectors + CreateRotationMatrix (q_math.c:999, cm_trace.c:65): ([n,9] float32, [n] int32)."""
+    lib = load_library()
+    a = _f(angles).reshape(-1, 3)
+    m = np.zeros((a.shape[0], 9), np.float32)
+    idx = np.zeros(a.shape[0], np.int32)
+    lib.cmgpu_rotation_matrices(a.shape[0], _p(a), _p(m), _p(idx))
+    return m, idx
+
+
+class Engine:
+    """One cmgpu context on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.cmgpu_create(C.byref(h), int(device))
+        if rc:
+            raise CMGPUError(rc, self.lib.cmgpu_last_error(None).decode(errors="replace"))
+        self.h = h
+        self.device = int(device)
+        self.map = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cmgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise CMGPUError(rc, self.lib.cmgpu_last_error(self.h).decode(errors="replace"))
+
+    # ---- map ---------------------------------------------------------------
+    def load_bsp(self, data: bytes) -> FlatMap:
+        fm = FlatMap.from_bsp(data)
+        self.upload(fm)
+        return fm
+
+    def upload(self, fm: FlatMap):
+        self._check(self.lib.cmgpu_upload(self.h, fm.pointer()))
+        self.map = fm
+
+    def clear(self):
+        self._check(self.lib.cmgpu_clear(self.h))
+        self.map = None
+
+    def set_cvars(self, noCurves=0, playerCurveClip=1):
+        self._check(self.lib.cmgpu_set_cvars(self.h, int(noCurves), int(playerCurveClip)))
+
+    def num_inline_models(self):
+        return self.lib.cmgpu_num_inline_models(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.cmgpu_launch_count(self.h))
+
+    def enable_counters(self, on=True):
+        self._check(self.lib.cmgpu_enable_counters(self.h, int(bool(on))))
+
+    def read_counters(self, reset=True) -> dict:
+        c = _Counters()
+        self._check(self.lib.cmgpu_read_counters(self.h, C.byref(c), int(reset)))
+        return {k: int(getattr(c, k)) for k, _ in _Counters._fields_}
+
+    # ---- host-pointer calls (numpy) -------------------------------------------
+    @staticmethod
+    def _hull(n, mins, maxs):
+        if mins is None:
+            return None, None, 0
+        mins, maxs = _f(mins), _f(maxs)
+        if mins.ndim == 1:
+            return mins, maxs, 0
+        assert mins.shape == (n, 3) and maxs.shape == (n, 3)
+        return mins, maxs, 1
+
+    @staticmethod
+    def _mask(n, mask):
+        m = np.asarray(mask)
+        if m.ndim == 0:
+            return np.array([int(m)], dtype=np.int64).astype(np.int32), 0
+        assert m.shape == (n,)
+        return _i(m), 1
+
+    def box_trace(self, starts, ends, mins=None, maxs=None, model=0, mask=1, boxmins=None, boxmaxs=None,
+                  want_hit=False, out=None):
+        """cmgpu_box_trace_batch on host arrays: n x CM_BoxTrace."""
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        mins, maxs, hs = self._hull(n, mins, maxs)
+        m, ms = self._mask(n, mask)
+        models = None
+        if not np.isscalar(model) or model != 0:
+            models = _i(np.broadcast_to(_i(model), (n,)))
+        boxmins, boxmaxs = _f(boxmins), _f(boxmaxs)
+        if out is None:
+            out = np.zeros(n, dtype=TRACE_DTYPE)
+        hit = np.zeros(n, np.int32) if want_hit else None
+        self._check(self.lib.cmgpu_box_trace_batch(self.h, n, _p(starts), _p(ends), _p(mins), _p(maxs), hs,
+                                                   _p(models), _p(m), ms, _p(boxmins), _p(boxmaxs), _p(out), _p(hit)))
+        return (out, hit) if want_hit else out
+
+    def transformed_box_trace(self, starts, ends, mins, maxs, models, mask, origins, angles,
+                              boxmins=None, boxmaxs=None, want_hit=False):
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        mins, maxs, hs = self._hull(n, mins, maxs)
+        m, ms = self._mask(n, mask)
+        models = _i(np.broadcast_to(_i(models), (n,)))
+        origins, angles = _f(origins), _f(angles)
+        boxmins, boxmaxs = _f(boxmins), _f(boxmaxs)
+        out = np.zeros(n, dtype=TRACE_DTYPE)
+        hit = np.zeros(n, np.int32) if want_hit else None
+        self._check(self.lib.cmgpu_transformed_box_trace_batch(
+            self.h, n, _p(starts), _p(ends), _p(mins), _p(maxs), hs, _p(models), _p(m), ms,
+            _p(origins), _p(angles), _p(boxmins), _p(boxmaxs), _p(out), _p(hit)))
+        return (out, hit) if want_hit else out
+
+    def point_contents(self, pts, models=None, origins=None, angles=None, boxmins=None, boxmaxs=None):
+        pts = _f(pts)
+        n = pts.shape[0]
+        if models is not None:
+            models = _i(np.broadcast_to(_i(models), (n,)))
+        out = np.zeros(n, np.int32)
+        self._check(self.lib.cmgpu_point_contents_batch(self.h, n, _p(pts), _p(models), _p(_f(origins)), _p(_f(angles)),
+                                                        _p(_f(boxmins)), _p(_f(boxmaxs)), _p(out)))
+        return out
+
+    def box_trace_hostptr(self, n, starts_ptr, ends_ptr, mins, maxs, mask, out_ptr):
+        """Raw host-pointer call (pinned torch tensors): shared hull and mask, world model."""
+        mins, maxs = _f(mins), _f(maxs)
+        m = np.array([int(mask)], dtype=np.int64).astype(np.int32)
+        self._check(self.lib.cmgpu_box_trace_batch(self.h, int(n), starts_ptr, ends_ptr, _p(mins), _p(maxs), 0,
+                                                   None, _p(m), 0, None, None, out_ptr, None))
+
+    # ---- device-pointer calls (torch tensors on this GPU) -----------------------
+    def box_trace_device(self, starts, ends, mins, maxs, masks, out, models=None, origins=None, rotations=None,
+                         rot_index=None, boxmins=None, boxmaxs=None, hit_ids=None, stream=None):
+        """cmgpu_box_trace_batch_device: every argument is a CUDA tensor (or None); only enqueues work.
+
+        starts/ends float32 [n,3]; mins/maxs float32 [3] (shared) or [n,3]; masks int32 [1] or [n];
+        out uint8 [n,56].  Uses torch's current stream unless `stream` (a cudaStream_t int) is given.
+        """
+        import torch
+        n = starts.shape[0]
+        if stream is None:
+            stream = torch.cuda.current_stream(starts.device).cuda_stream
+        ptr = lambda t: None if t is None else t.data_ptr()
+        hs = 0 if (mins is None or mins.dim() == 1) else 1
+        ms = 0 if masks.numel() == 1 else 1
+        self._check(self.lib.cmgpu_box_trace_batch_device(
+            self.h, n, ptr(starts), ptr(ends), ptr(mins), ptr(maxs), hs, ptr(models), ptr(masks), ms,
+            ptr(origins), ptr(rotations), ptr(rot_index), ptr(boxmins), ptr(boxmaxs), ptr(out), ptr(hit_ids),
+            C.c_void_p(stream)))
+
+    def point_contents_device(self, points, out, models=None, origins=None, rotations=None, rot_index=None,
+                              boxmins=None, boxmaxs=None, stream=None):
+        import torch
+        n = points.shape[0]
+        if stream is None:
+            stream = torch.cuda.current_stream(points.device).cuda_stream
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self._check(self.lib.cmgpu_point_contents_batch_device(
+            self.h, n, ptr(points), ptr(models), ptr(origins), ptr(rotations), ptr(rot_index),
+            ptr(boxmins), ptr(boxmaxs), ptr(out), C.c_void_p(stream)))
+
+    def check_status(self, stream=None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.cmgpu_check_status(self.h, C.c_void_p(stream)))
+
+
+def traces_from_tensor(t) -> np.ndarray:
+    """uint8 [n,56] CUDA/CPU tensor -> numpy structured trace_t array."""
+    return t.detach().cpu().numpy().view(TRACE_DTYPE).reshape(-1)
