@@ -153,11 +153,12 @@ class MapBuilder:
         self.brushes.append(_Brush(sides, shader, mins.copy(), maxs.copy()))
         return len(self.brushes) - 1
 
-    def hull_brush(self, normals, dists, shader=0, snap=True) -> int:
+    def hull_brush(self, normals, dists, shader=0, snap=True, verts=None) -> int:
         """Convex brush from outward planes; the six axial bounding sides come first."""
         normals = np.asarray(normals, dtype=np.float64)
         dists = np.asarray(dists, dtype=np.float64)
-        verts = _hull_vertices(normals, dists)
+        if verts is None:
+            verts = _hull_vertices(normals, dists)
         if verts.shape[0] < 4:
             raise ValueError("degenerate hull brush")
         mins = verts.min(axis=0)
@@ -186,7 +187,9 @@ class MapBuilder:
                 n = s * m[:, a]
                 normals.append(n)
                 dists.append(float(n @ center) + half[a])
-        return self.hull_brush(normals, dists, shader)
+        signs = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64)
+        verts = center[None, :] + (signs * np.asarray(half, dtype=np.float64)[None, :]) @ m.T
+        return self.hull_brush(normals, dists, shader, verts=verts)
 
     def wedge_brush(self, mins, maxs, axis=0, flip=False, shader=0) -> int:
         """Ramp: the box cut by a slanted plane rising along `axis`."""
@@ -603,14 +606,14 @@ def arena_map(n_brushes=20000, seed=0xC0FFEE02, size_xy=16384.0, size_z=4096.0,
     n_pillars = n // 5
     # pillars: tall thin boxes standing on the floor
     for _ in range(n_pillars):
-        w = np.floor(rng.uniform(32, 160, size=2))
-        hgt = float(np.floor(rng.uniform(128, 1024)))
+        w = np.floor(rng.uniform(24, 96, size=2))
+        hgt = float(np.floor(rng.uniform(128, 768)))
         c = np.floor(rng.uniform([-hx + 128, -hx + 128], [hx - 128, hx - 128]))
         mb.box_brush([c[0] - w[0] / 2, c[1] - w[1] / 2, 0.0], [c[0] + w[0] / 2, c[1] + w[1] / 2, hgt],
                      int(rng.choice([0, 1])))
     # everything else within the lower slab where movement happens
-    _scatter_brushes(mb, rng, n - n_pillars, [-hx, -hx, 0.0], [hx, hx, min(size_z, 1536.0)],
-                     32, 320, rotated_frac, SOLID_MIX)
+    _scatter_brushes(mb, rng, n - n_pillars, [-hx, -hx, 0.0], [hx, hx, min(size_z, 2048.0)],
+                     24, 224, rotated_frac, SOLID_MIX)
     if n_models:
         _add_models(mb, np.random.default_rng(model_seed if model_seed is not None else seed + 77), n_models)
     return mb.finish(seed=seed, leaf_max=4, nonaxial_node_prob=nonaxial_node_prob)
