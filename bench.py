@@ -198,13 +198,10 @@ def run_ours(args):
     # ---- device-resident arm -------------------------------------------------------------
     d_starts = torch.from_numpy(starts).to(dev)
     d_ends = torch.from_numpy(ends).to(dev)
-    d_mins = torch.from_numpy(bspgen.PLAYER_MINS.copy()).to(dev)
-    d_maxs = torch.from_numpy(bspgen.PLAYER_MAXS.copy()).to(dev)
-    d_mask = torch.tensor([bspgen.MASK_PLAYERSOLID], dtype=torch.int32, device=dev)
     d_out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
 
     def step():
-        eng.box_trace_device(d_starts, d_ends, d_mins, d_maxs, d_mask, d_out)
+        eng.box_trace_device(d_starts, d_ends, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, d_out)
 
     for _ in range(args.warmup):
         step()

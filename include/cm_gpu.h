@@ -160,9 +160,11 @@ int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
                                const float *boxmins, const float *boxmaxs, int32_t *contents);
 
 /* ---- batched queries, DEVICE pointers (inputs resident in HBM) -----------
- * Same meaning as above; every pointer is a device pointer on the context's
- * GPU, `stream` is a cudaStream_t (NULL = default stream).  The call only
- * enqueues work.  rotations: [n][9] row-major rotation matrices
+ * Same meaning as above; per-item arrays are device pointers on the context's
+ * GPU.  A SHARED hull (hull_stride == 0: mins/maxs, 3 floats each, may be NULL)
+ * and a SHARED mask (mask_stride == 0: 1 int) are HOST pointers read at call
+ * time, like the by-value arguments of CM_BoxTrace.  `stream` is a cudaStream_t
+ * (NULL = default stream).  The call only enqueues work.  rotations: [n][9] row-major rotation matrices
  * (CreateRotationMatrix, cm_trace.c:65-68) with rot_index[i] == -1 for an
  * unrotated item; build them with cmgpu_rotation_matrices on the host.     */
 int cmgpu_box_trace_batch_device(cmgpu_ctx *ctx, int n,

@@ -22,8 +22,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
 m, starts, ends = bench.make_workload(n)
 eng = Engine(0); eng.load_bsp(m.data)
 dev = torch.device("cuda", 0)
-d_mins = torch.from_numpy(bspgen.PLAYER_MINS.copy()).to(dev); d_maxs = torch.from_numpy(bspgen.PLAYER_MAXS.copy()).to(dev)
-d_mask = torch.tensor([bspgen.MASK_PLAYERSOLID], dtype=torch.int32, device=dev)
+d_mins = bspgen.PLAYER_MINS; d_maxs = bspgen.PLAYER_MAXS
+d_mask = bspgen.MASK_PLAYERSOLID
 d_out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
 def run(s, e, label):
     ds = torch.from_numpy(np.ascontiguousarray(s)).to(dev); de = torch.from_numpy(np.ascontiguousarray(e)).to(dev)

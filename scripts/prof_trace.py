@@ -14,8 +14,8 @@ eng = Engine(0)
 eng.load_bsp(m.data)
 dev = torch.device("cuda", 0)
 d_starts = torch.from_numpy(starts).to(dev); d_ends = torch.from_numpy(ends).to(dev)
-d_mins = torch.from_numpy(bspgen.PLAYER_MINS.copy()).to(dev); d_maxs = torch.from_numpy(bspgen.PLAYER_MAXS.copy()).to(dev)
-d_mask = torch.tensor([bspgen.MASK_PLAYERSOLID], dtype=torch.int32, device=dev)
+d_mins = bspgen.PLAYER_MINS; d_maxs = bspgen.PLAYER_MAXS
+d_mask = bspgen.MASK_PLAYERSOLID
 d_out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
 for _ in range(steps):
     eng.box_trace_device(d_starts, d_ends, d_mins, d_maxs, d_mask, d_out)

@@ -26,7 +26,7 @@ namespace {
 
 thread_local std::string g_createError;
 
-constexpr int kBlock = 128;
+constexpr int kCursorSlots = 64;
 constexpr int kPipeChunks = 8;           // host batches are split so copies overlap the kernel
 constexpr size_t kMinChunkItems = 1 << 16;
 
@@ -48,6 +48,9 @@ struct cmgpu_ctx_s {
 	bool counting = false;
 	Counters *dCounters = nullptr;
 	int *dStatus = nullptr;
+	int *dCursor = nullptr;              // work cursors of the persistent kernel, one per launch slot
+	int cursorSlot = 0;
+	int gridPlain = 0, gridCount = 0;    // resident CTAs of the two kernel variants
 	int *hStatus = nullptr;              // pinned
 	unsigned long long launches = 0;
 	cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
@@ -213,6 +216,25 @@ int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 inline float bitsToFloat(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
 inline int32_t floatToBits(float f) { int32_t v; memcpy(&v, &f, 4); return v; }
 
+// true when sides 0..5 of brush i are exactly the planes -x,+x,-y,+y,-z,+z through its bounds
+// (what CM_BoundBrush, cm_load.c:230-239, assumes); such sides are evaluated from the box alone.
+bool canonicalAxialSides(const cmgpu_flatmap *f, int i) {
+	const int32_t *b = f->brushes + 3 * (size_t)i;
+	if (b[2] < 6 || i == f->boxBrush) return false;
+	const float *bb = f->brushBounds + 6 * (size_t)i;
+	for (int s = 0; s < 6; s++) {
+		const float *pl = f->planes + 4 * (size_t)f->brushsides[2 * (size_t)(b[1] + s)];
+		const int axis = s >> 1;
+		const float want = (s & 1) ? 1.0f : -1.0f;
+		for (int j = 0; j < 3; j++) {
+			if (j == axis ? pl[j] != want : pl[j] != 0.0f) return false;
+		}
+		const float dist = (s & 1) ? bb[3 + axis] : -bb[axis];
+		if (memcmp(&dist, &pl[3], 4) != 0) return false;
+	}
+	return true;
+}
+
 int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 	DevMap &m = ctx->map;
 	std::vector<int4> nodes((size_t)f->numNodes);
@@ -229,17 +251,22 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		const int32_t *l = f->leafs + 4 * (size_t)i;
 		leafs[i] = make_int4(l[0], l[1], l[2], l[3]);
 	}
-	std::vector<int> leafbrushes(f->leafbrushes, f->leafbrushes + f->numLeafBrushes);
 	std::vector<int> leafsurfaces;
 	if (f->numLeafSurfaces) leafsurfaces.assign(f->leafsurfaces, f->leafsurfaces + f->numLeafSurfaces);
-	std::vector<float4> brushBox(2 * (size_t)f->numBrushes);
-	std::vector<int> brushNumSides((size_t)f->numBrushes);
+	// every leafbrush entry carries the brush's box, contents and index, so a leaf's brush list is
+	// one sequential stream of 32-byte records instead of index -> brush -> bounds pointer chasing
+	std::vector<float4> leafBrushBox(2 * (size_t)f->numLeafBrushes);
+	for (int k = 0; k < f->numLeafBrushes; k++) {
+		const int bi = f->leafbrushes[k];
+		const int32_t *b = f->brushes + 3 * (size_t)bi;
+		const float *bb = f->brushBounds + 6 * (size_t)bi;
+		leafBrushBox[2 * (size_t)k] = make_float4(bb[0], bb[1], bb[2], bitsToFloat(b[0]));
+		leafBrushBox[2 * (size_t)k + 1] = make_float4(bb[3], bb[4], bb[5], bitsToFloat(bi));
+	}
+	std::vector<int4> brushInfo((size_t)f->numBrushes);
 	for (int i = 0; i < f->numBrushes; i++) {
 		const int32_t *b = f->brushes + 3 * (size_t)i;
-		const float *bb = f->brushBounds + 6 * (size_t)i;
-		brushBox[2 * (size_t)i] = make_float4(bb[0], bb[1], bb[2], bitsToFloat(b[0]));
-		brushBox[2 * (size_t)i + 1] = make_float4(bb[3], bb[4], bb[5], bitsToFloat(b[1]));
-		brushNumSides[i] = b[2];
+		brushInfo[i] = make_int4(b[1], b[2], b[0], canonicalAxialSides(f, i) ? 1 : 0);
 	}
 	std::vector<float4> sidePlanes((size_t)f->numBrushSides);
 	std::vector<int2> sideMeta((size_t)f->numBrushSides);
@@ -284,8 +311,8 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 
 	int rc;
 #define UP(vec, field) if ((rc = uploadArray(ctx, vec, &m.field)) != CMGPU_OK) return rc
-	UP(nodes, nodes); UP(nodePlanes, nodePlanes); UP(leafs, leafs); UP(leafbrushes, leafbrushes);
-	UP(leafsurfaces, leafsurfaces); UP(brushBox, brushBox); UP(brushNumSides, brushNumSides);
+	UP(nodes, nodes); UP(nodePlanes, nodePlanes); UP(leafs, leafs); UP(leafBrushBox, leafBrushBox);
+	UP(leafsurfaces, leafsurfaces); UP(brushInfo, brushInfo);
 	UP(sidePlanes, sidePlanes); UP(sideMeta, sideMeta); UP(modelLeafs, modelLeafs); UP(surf2patch, surf2patch);
 	UP(patchInfo, patchInfo); UP(patchBox, patchBox); UP(patchPlanes, patchPlanes); UP(facets, facets);
 	UP(borders, borders);
@@ -312,13 +339,21 @@ int checkHandles(cmgpu_ctx *ctx, int n, const int32_t *models) {
 	return CMGPU_OK;
 }
 
-int launchTrace(cmgpu_ctx *ctx, const TraceBatch &q, cudaStream_t s) {
+int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s) {
 	if (q.n <= 0) return CMGPU_OK;
 	ctx->map.noCurves = ctx->noCurves;
 	ctx->map.playerCurveClip = ctx->playerCurveClip;
-	int grid = (q.n + kBlock - 1) / kBlock;
-	if (ctx->counting) traceKernel<true><<<grid, kBlock, 0, s>>>(ctx->map, q);
-	else               traceKernel<false><<<grid, kBlock, 0, s>>>(ctx->map, q);
+	// persistent kernel: as many CTAs as fit on the GPU (fewer for tiny batches), each warp pulls
+	// kChunk items at a time from a cursor that must be zero at launch
+	q.cursor = ctx->dCursor + (ctx->cursorSlot++ % kCursorSlots);
+	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
+	const int resident = ctx->counting ? ctx->gridCount : ctx->gridPlain;
+	const long long warpsWanted = ((long long)q.n + kChunk - 1) / kChunk;
+	long long blocks = (warpsWanted + (kBlock / 32) - 1) / (kBlock / 32);
+	if (blocks > resident) blocks = resident;
+	if (blocks < 1) blocks = 1;
+	if (ctx->counting) traceKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
+	else               traceKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return CMGPU_OK;
@@ -371,6 +406,15 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 	ok = ok && cudaMalloc(&ctx->dStatus, sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMemset(ctx->dStatus, 0, sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMallocHost(&ctx->hStatus, sizeof(int)) == cudaSuccess;
+	ok = ok && cudaMalloc(&ctx->dCursor, kCursorSlots * sizeof(int)) == cudaSuccess;
+	if (ok) {
+		int perSm = 0;
+		ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, traceKernel<false>, kBlock, 0) == cudaSuccess && perSm > 0;
+		ctx->gridPlain = perSm * prop.multiProcessorCount;
+		int perSmC = 0;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmC, traceKernel<true>, kBlock, 0) == cudaSuccess && perSmC > 0;
+		ctx->gridCount = perSmC * prop.multiProcessorCount;
+	}
 	if (!ok) {
 		g_createError = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
 		cmgpu_destroy(ctx);
@@ -389,6 +433,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit}) releaseBuf(*b);
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->dStatus) cudaFree(ctx->dStatus);
+	if (ctx->dCursor) cudaFree(ctx->dCursor);
 	if (ctx->hStatus) cudaFreeHost(ctx->hStatus);
 	for (auto &s : ctx->streams) if (s) cudaStreamDestroy(s);
 	for (auto &ev : ctx->evt) if (ev) cudaEventDestroy(ev);
@@ -499,11 +544,16 @@ int cmgpu_box_trace_batch_device(cmgpu_ctx *ctx, int n,
 		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_box_trace_batch_device: bad argument");
 	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
 	if ((mins == nullptr) != (maxs == nullptr)) return fail(ctx, CMGPU_ERR_INVALID, "mins and maxs must both be given or both be NULL");
+	if (hull_stride && !mins) hull_stride = 0;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	TraceBatch q{};
-	q.n = n; q.starts = starts; q.ends = ends; q.mins = mins; q.maxs = maxs; q.hullStride = hull_stride ? 1 : 0;
-	q.models = models; q.masks = masks; q.maskStride = mask_stride ? 1 : 0;
+	q.n = n; q.starts = starts; q.ends = ends;
+	if (hull_stride) { q.mins = mins; q.maxs = maxs; }
+	else if (mins) { memcpy(q.sharedMins, mins, 12); memcpy(q.sharedMaxs, maxs, 12); }   // host [3], by value
+	q.models = models;
+	if (mask_stride) q.masks = masks; else q.sharedMask = masks[0];                         // host [1], by value
 	q.origins = origins; q.rotations = rotations; q.rotIndex = rotations ? rot_index : nullptr;
+	if (origins && !q.rotations) q.rotIndex = nullptr;
 	q.boxmins = boxmins; q.boxmaxs = boxmins ? boxmaxs : nullptr;
 	if (!q.boxmaxs) q.boxmins = nullptr;
 	q.out = reinterpret_cast<uint2 *>(results); q.hitIds = hit_ids;
@@ -527,8 +577,8 @@ int cmgpu_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points
 	q.boxmins = boxmins; q.boxmaxs = boxmins ? boxmaxs : nullptr;
 	if (!q.boxmaxs) q.boxmins = nullptr;
 	q.out = contents;
-	int grid = (n + kBlock - 1) / kBlock;
-	pointContentsKernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	const int grid = (n + 127) / 128;
+	pointContentsKernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return CMGPU_OK;
@@ -561,12 +611,13 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	const size_t v3 = 3 * sizeof(float);
 	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
 	if ((rc = reserve(ctx, ctx->bEnds, N * v3))) return rc;
-	if (mins) {
-		if ((rc = reserve(ctx, ctx->bMins, (hull_stride ? N : 1) * v3))) return rc;
-		if ((rc = reserve(ctx, ctx->bMaxs, (hull_stride ? N : 1) * v3))) return rc;
+	if (!mins) hull_stride = 0;
+	if (hull_stride) {
+		if ((rc = reserve(ctx, ctx->bMins, N * v3))) return rc;
+		if ((rc = reserve(ctx, ctx->bMaxs, N * v3))) return rc;
 	}
 	if (models && (rc = reserve(ctx, ctx->bModels, N * 4))) return rc;
-	if ((rc = reserve(ctx, ctx->bMasks, (mask_stride ? N : 1) * 4))) return rc;
+	if (mask_stride && (rc = reserve(ctx, ctx->bMasks, N * 4))) return rc;
 	if (origins) {
 		if ((rc = reserve(ctx, ctx->bOrigins, N * v3))) return rc;
 		if ((rc = reserve(ctx, ctx->bRot, N * 9 * sizeof(float)))) return rc;
@@ -582,14 +633,6 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	if ((rc = reserve(ctx, ctx->bOut, N * sizeof(cmgpu_trace_t)))) return rc;
 	if (hit_ids && (rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
 
-	cudaStream_t s0 = ctx->streams[0];
-	if (mins && !hull_stride) {
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMins.p, mins, v3, cudaMemcpyHostToDevice, s0));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMaxs.p, maxs, v3, cudaMemcpyHostToDevice, s0));
-	}
-	if (!mask_stride) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMasks.p, masks, 4, cudaMemcpyHostToDevice, s0));
-	CUDA_TRY(ctx, cudaStreamSynchronize(s0));
-
 	int chunks = (int)((N + kMinChunkItems - 1) / kMinChunkItems);
 	if (chunks > kPipeChunks) chunks = kPipeChunks;
 	if (chunks < 1) chunks = 1;
@@ -601,7 +644,7 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 #define H2D(buf, src, elem) CUDA_TRY(ctx, cudaMemcpyAsync((char *)(buf).p + lo * (elem), (const char *)(src) + lo * (elem), cnt * (elem), cudaMemcpyHostToDevice, s))
 		H2D(ctx->bStarts, starts, v3);
 		H2D(ctx->bEnds, ends, v3);
-		if (mins && hull_stride) { H2D(ctx->bMins, mins, v3); H2D(ctx->bMaxs, maxs, v3); }
+		if (hull_stride) { H2D(ctx->bMins, mins, v3); H2D(ctx->bMaxs, maxs, v3); }
 		if (models) H2D(ctx->bModels, models, 4);
 		if (mask_stride) H2D(ctx->bMasks, masks, 4);
 		if (origins) {
@@ -615,14 +658,15 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 		q.n = (int)cnt;
 		q.starts = (const float *)ctx->bStarts.p + 3 * lo;
 		q.ends = (const float *)ctx->bEnds.p + 3 * lo;
-		if (mins) {
-			q.mins = (const float *)ctx->bMins.p + (hull_stride ? 3 * lo : 0);
-			q.maxs = (const float *)ctx->bMaxs.p + (hull_stride ? 3 * lo : 0);
+		if (hull_stride) {
+			q.mins = (const float *)ctx->bMins.p + 3 * lo;
+			q.maxs = (const float *)ctx->bMaxs.p + 3 * lo;
+		} else if (mins) {
+			memcpy(q.sharedMins, mins, 12);
+			memcpy(q.sharedMaxs, maxs, 12);
 		}
-		q.hullStride = hull_stride;
 		q.models = models ? (const int *)ctx->bModels.p + lo : nullptr;
-		q.masks = (const int *)ctx->bMasks.p + (mask_stride ? lo : 0);
-		q.maskStride = mask_stride;
+		if (mask_stride) q.masks = (const int *)ctx->bMasks.p + lo; else q.sharedMask = masks[0];
 		if (origins) {
 			q.origins = (const float *)ctx->bOrigins.p + 3 * lo;
 			// rot_index values are absolute item numbers: keep the base pointer unshifted

@@ -1,18 +1,28 @@
 // cm_kernels.cuh -- sm_100a device code of the batched clip-map trace engine.
 //
-// One thread owns one work item (a CM_BoxTrace / CM_TransformedBoxTrace /
-// CM_PointContents call of the reference, code/qcommon/cm_trace.c, cm_test.c,
-// cm_patch.c) and walks the flattened BSP with an explicit per-thread stack.
-// The map is read-only, index-based and packed in 16-byte records so that every
-// node / leaf / brush-box / side-plane fetch is one LDG.128 that hits L1/L2.
+// Work items are the reference's CM_BoxTrace / CM_TransformedBoxTrace /
+// CM_PointContents calls (code/qcommon/cm_trace.c, cm_test.c, cm_patch.c).
+//
+// traceKernel is a PERSISTENT kernel: one CTA slot per SM slot, every warp pulls
+// chunks of consecutive items from a global cursor, and every lane runs one item
+// as a FLAT STATE MACHINE (fetch -> node steps -> leaf/brush steps -> side steps
+// -> finish -> fetch ...).  The reference's nested recursion/loops are unrolled
+// into "one step per loop iteration" so that lanes that are in the same state
+// execute together no matter how far along their own item they are, and a lane
+// that finishes takes a new item at once (no tail wait for the slowest ray of a
+// warp).  The first kernel of this project kept the nested loops and ran with
+// 2 of 32 lanes active per instruction (profiles/r01_v0_*).
+//
+// The map is read-only, index-based and packed in 16-byte records: every node,
+// leaf, per-leaf brush box and side plane is one or two LDG.128 that hit L1/L2.
 //
 // Arithmetic contract (SURVEY.md 8a'): the reference mixes float and double in
 // the same expressions and is compiled without FMA contraction.  This TU is
-// built with -fmad=false; every float op below is therefore a separately
-// rounded IEEE op, exactly like the SSE2 code of the reference.  Double dot
-// products of float inputs use explicit fma(): each float*float product is
-// exact in double, so fma(a,b,c) == (a*b)+c bit for bit and only saves issue
-// slots.  Divisions are IEEE (no fast-math), conversions round-to-nearest.
+// built with -fmad=false; every float op below is a separately rounded IEEE op,
+// exactly like the SSE2 code of the reference.  Double dot products of float
+// inputs use explicit fma(): each float*float product is exact in double, so
+// fma(a,b,c) == (a*b)+c bit for bit and only saves issue slots.  Divisions are
+// IEEE (no fast-math), conversions round-to-nearest.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -20,6 +30,8 @@
 
 namespace cmgpu {
 
+constexpr int    kBlock          = 128;     // threads per CTA of the trace kernel
+constexpr int    kChunk          = 256;     // items a warp takes from the global cursor at a time
 constexpr int    kMaxDepth       = 64;      // traversal stack entries per item (CMGPU_ERR_LIMIT beyond)
 constexpr int    kMaxPosLeafs    = 1024;    // MAX_POSITION_LEAFS, cm_trace.c:190
 constexpr int    kBoxModelHandle = 1023;    // BOX_MODEL_HANDLE, cm_local.h:28
@@ -31,10 +43,9 @@ struct DevMap {
 	const int4   *nodes;        // child0, child1, plane type (0..2 axial, 3 general), float bits of dist
 	const float4 *nodePlanes;   // normal.xyz, dist (read only for type 3)
 	const int4   *leafs;        // firstLeafBrush, numLeafBrushes, firstLeafSurface, numLeafSurfaces
-	const int    *leafbrushes;
+	const float4 *leafBrushBox; // per LEAFBRUSH ENTRY: [2k] mins.xyz + contents bits, [2k+1] maxs.xyz + brush index bits
 	const int    *leafsurfaces;
-	const float4 *brushBox;     // [2b] mins.xyz + contents bits, [2b+1] maxs.xyz + firstSide bits
-	const int    *brushNumSides;
+	const int4   *brushInfo;    // firstSide, numSides, contents, canonical (first six sides are -x,+x,-y,+y,-z,+z of the bounds)
 	const float4 *sidePlanes;   // normal.xyz, dist per brush side (plane copied next to its side)
 	const int2   *sideMeta;     // surfaceFlags, type | signbits << 8
 	const int4   *modelLeafs;   // pseudo leaf per inline model
@@ -61,11 +72,11 @@ struct Counters {
 struct TraceBatch {
 	int n;
 	const float *starts, *ends;          // [n][3]
-	const float *mins, *maxs;            // [1][3] or [n][3]; may be null
-	int hullStride;
+	const float *mins, *maxs;            // per item [n][3], or null: use sharedMins/sharedMaxs
+	float sharedMins[3], sharedMaxs[3];
 	const int *models;                   // may be null (world)
-	const int *masks;
-	int maskStride;
+	const int *masks;                    // per item, or null: use sharedMask
+	int sharedMask;
 	const float *origins;                // null: untransformed (CM_BoxTrace)
 	const float *rotations;              // [*][9]
 	const int *rotIndex;                 // -1: not rotated
@@ -73,7 +84,8 @@ struct TraceBatch {
 	uint2 *out;                          // 56-byte trace records viewed as 7 x 8 bytes
 	int *hitIds;                         // may be null
 	int *status;                         // device status word
-	Counters *counters;                  // only read by the counting variant
+	int *cursor;                         // work cursor, zero at launch
+	Counters *counters;                  // only touched by the counting variant
 };
 
 struct PointBatch {
@@ -87,26 +99,37 @@ struct PointBatch {
 	int *out;
 };
 
-// ---- per-item working set (registers) ----------------------------------------------
-struct Work {
-	float sx, sy, sz, ex, ey, ez;        // symmetrised sweep end points (tw.start / tw.end)
+enum Mode : int { M_FETCH = 0, M_NODE, M_LEAF, M_SIDE, M_PATCH, M_PNODE, M_PLEAF, M_FINISH };
+
+// ---- per-lane working set (registers) -----------------------------------------------------
+struct Lane {
+	int   idx;                           // item number
+	float sx, sy, sz, ex, ey, ez;        // symmetrised sweep end points in the model frame (tw.start / tw.end)
 	float n0x, n0y, n0z, p0x, p0y, p0z;  // tw.size[0], tw.size[1]
-	float extx, exty, extz;              // tw.extents
 	float lox, loy, loz, hix, hiy, hiz;  // tw.bounds
 	int   mask;
-	bool  isPoint;
-	bool  isBox;                         // model == 1023
-	float bmnx, bmny, bmnz, bmxx, bmxy, bmxz;   // temp-box mins/maxs
+	int   flags;                         // F_* below
 	// running result (tw.trace)
-	int   allsolid, startsolid;
+	int   solid;                         // bit0 allsolid, bit1 startsolid
 	float fraction;
 	float pnx, pny, pnz, pd;
 	int   ptypesign;                     // plane.type | plane.signbits << 8
 	int   surfaceFlags, contents;
 	int   hitId;
+	// tree cursor
+	int   num, sp;
+	float f1, f2, ax, ay, az, bx, by, bz;
+	// leaf cursor: brush entries [k, kEnd), surface entries [ps, psEnd)
+	int   k, kEnd, ps, psEnd;
+	// brush cursor
+	int   brush, side, sideEnd, firstSide, lead, bcontents;
+	float enter, leave;
+	int   found;                         // leafs seen by the position test
 	// visit counts (counting variant only)
 	unsigned cNodes, cLeafs, cBrushRefs, cBrushBounds, cBrushSides, cCross, cSplits, cPatches, cPatchPlanes, cFacets;
 };
+
+enum : int { F_POINT = 1, F_BOX = 2, F_ROTATED = 4, F_STARTOUT = 8, F_ENDOUT = 16, F_BOXBRUSH = 32, F_POSTEST = 64 };
 
 template <bool COUNT> struct Cnt {
 	static __device__ __forceinline__ void add(unsigned &c, unsigned v = 1) { if (COUNT) c += v; }
@@ -116,7 +139,7 @@ __device__ __forceinline__ float sel3(float x, float y, float z, int i) {
 	return i == 0 ? x : (i == 1 ? y : z);
 }
 
-// DotProduct (q_shared.h:489): ((a0*b0 + a1*b1) + a2*b2), three roundings + two, no contraction
+// DotProduct (q_shared.h:489): ((a0*b0 + a1*b1) + a2*b2), no contraction
 __device__ __forceinline__ float dotf(float ax, float ay, float az, float bx, float by, float bz) {
 	float s = ax * bx;
 	s = s + ay * by;
@@ -134,82 +157,71 @@ __device__ __forceinline__ double dotd(double ax, double ay, double az, float bx
 
 // temp-box side s (CM_InitBoxHull / CM_TempBoxModel, cm_load.c:873-949):
 // sides +x,-x,+y,-y,+z,-z carry dist maxs[0], -mins[0], maxs[1], -mins[1], maxs[2], -mins[2]
-__device__ __forceinline__ float boxSideDist(const Work &w, int s) {
-	int axis = s >> 1;
-	if (s & 1) return -sel3(w.bmnx, w.bmny, w.bmnz, axis);
-	return sel3(w.bmxx, w.bmxy, w.bmxz, axis);
+__device__ __forceinline__ float boxSideDist(const TraceBatch &q, int idx, int s) {
+	const int axis = s >> 1;
+	if (!q.boxmins) return 0.0f;
+	if (s & 1) return -q.boxmins[3 * (size_t)idx + axis];
+	return q.boxmaxs[3 * (size_t)idx + axis];
 }
 
-// ---- CM_TraceThroughBrush, cm_trace.c:261-363 ------------------------------------------
+// one brush side against the sweep: the body of the loop in CM_TraceThroughBrush, cm_trace.c:291-332.
+// returns false when the sweep is wholly in front of this face (the brush is missed).
 template <bool COUNT>
-__device__ void sweepBrush(const DevMap &m, Work &w, int b, int firstSide, int nsides, int contents, bool boxBrush) {
-	if (nsides == 0) return;
-	float enter = -1.0f, leave = 1.0f;
-	int lead = -1;
-	bool endOut = false, startOut = false;
-	const double sx = w.sx, sy = w.sy, sz = w.sz, ex = w.ex, ey = w.ey, ez = w.ez;
-
-	for (int s = 0; s < nsides; s++) {
-		float4 pl = __ldg(&m.sidePlanes[firstSide + s]);
-		if (boxBrush) pl.w = boxSideDist(w, s);
-		Cnt<COUNT>::add(w.cBrushSides);
-		// tw.offsets[signbits]: the box corner that touches the plane first
-		const float cx = pl.x < 0.0f ? w.p0x : w.n0x;
-		const float cy = pl.y < 0.0f ? w.p0y : w.n0y;
-		const float cz = pl.z < 0.0f ? w.p0z : w.n0z;
-		const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
-		const double d1 = dotd(sx, sy, sz, pl.x, pl.y, pl.z) - dist;
-		const double d2 = dotd(ex, ey, ez, pl.x, pl.y, pl.z) - dist;
-		if (d2 > 0) endOut = true;
-		if (d1 > 0) startOut = true;
-		if (d1 > 0 && (d2 >= kClipEps || d2 >= d1)) return;     // wholly in front of one face
-		if (d1 <= 0 && d2 <= 0) continue;                        // face not crossed
-		Cnt<COUNT>::add(w.cCross);
-		if (d1 > d2) {
-			float f = (float)((d1 - kClipEps) / (d1 - d2));
-			if (f < 0) f = 0;
-			if (f > enter) { enter = f; lead = s; }
-		} else {
-			float f = (float)((d1 + kClipEps) / (d1 - d2));
-			if (f > 1) f = 1;
-			if (f < leave) leave = f;
-		}
+__device__ __forceinline__ bool clipSide(Lane &L, const double d1, const double d2, const int side) {
+	if (d2 > 0) L.flags |= F_ENDOUT;
+	if (d1 > 0) L.flags |= F_STARTOUT;
+	if (d1 > 0 && (d2 >= kClipEps || d2 >= d1)) return false;
+	if (d1 <= 0 && d2 <= 0) return true;
+	Cnt<COUNT>::add(L.cCross);
+	if (d1 > d2) {
+		float f = (float)((d1 - kClipEps) / (d1 - d2));
+		if (f < 0) f = 0;
+		if (f > L.enter) { L.enter = f; L.lead = side; }
+	} else {
+		float f = (float)((d1 + kClipEps) / (d1 - d2));
+		if (f > 1) f = 1;
+		if (f < L.leave) L.leave = f;
 	}
+	return true;
+}
 
-	if (!startOut) {
-		w.startsolid = 1;
-		if (!endOut) {
-			w.allsolid = 1;
-			w.fraction = 0;
-			w.contents = contents;
-			w.hitId = b;
+// the tail of CM_TraceThroughBrush, cm_trace.c:338-362
+__device__ __forceinline__ void finishBrush(const DevMap &m, const TraceBatch &q, Lane &L) {
+	if (!(L.flags & F_STARTOUT)) {
+		L.solid |= 2;
+		if (!(L.flags & F_ENDOUT)) {
+			L.solid |= 1;
+			L.fraction = 0;
+			L.contents = L.bcontents;
+			L.hitId = L.brush;
 		}
 		return;
 	}
-	if (enter < leave && enter > -1 && enter < w.fraction) {
+	float enter = L.enter;
+	if (enter < L.leave && enter > -1 && enter < L.fraction) {
 		if (enter < 0) enter = 0;
-		w.fraction = enter;
-		if (lead >= 0) {
-			float4 pl = __ldg(&m.sidePlanes[firstSide + lead]);
-			if (boxBrush) pl.w = boxSideDist(w, lead);
-			const int2 meta = __ldg(&m.sideMeta[firstSide + lead]);
-			w.pnx = pl.x; w.pny = pl.y; w.pnz = pl.z; w.pd = pl.w;
-			w.ptypesign = meta.y;
-			w.surfaceFlags = meta.x;
+		L.fraction = enter;
+		if (L.lead >= 0) {
+			float4 pl = __ldg(&m.sidePlanes[L.firstSide + L.lead]);
+			if (L.flags & F_BOXBRUSH) pl.w = boxSideDist(q, L.idx, L.lead);
+			const int2 meta = __ldg(&m.sideMeta[L.firstSide + L.lead]);
+			L.pnx = pl.x; L.pny = pl.y; L.pnz = pl.z; L.pd = pl.w;
+			L.ptypesign = meta.y;
+			L.surfaceFlags = meta.x;
 		}
-		w.contents = contents;
-		w.hitId = b;
+		L.contents = L.bcontents;
+		L.hitId = L.brush;
 	}
 }
 
 // ---- patch facets, cm_patch.c:1220-1531 ------------------------------------------------
 
 // CM_CheckFacetPlane, cm_patch.c:1321-1360
-__device__ __forceinline__ bool clipFacetPlane(float px, float py, float pz, float pw, const Work &w,
+__device__ __forceinline__ bool clipFacetPlane(float px, float py, float pz, float pw, const Lane &L,
                                                float &enter, float &leave, bool &hit) {
 	hit = false;
-	const float d1 = dotf(w.sx, w.sy, w.sz, px, py, pz) - pw;
-	const float d2 = dotf(w.ex, w.ey, w.ez, px, py, pz) - pw;
+	const float d1 = dotf(L.sx, L.sy, L.sz, px, py, pz) - pw;
+	const float d2 = dotf(L.ex, L.ey, L.ez, px, py, pz) - pw;
 	if (d1 > 0 && (d2 >= 0.125f || d2 >= d1)) return false;
 	if (d1 <= 0 && d2 <= 0) return true;
 	if (d1 > d2) {
@@ -226,13 +238,13 @@ __device__ __forceinline__ bool clipFacetPlane(float px, float py, float pz, flo
 
 // relation of the point sweep to one patch plane (the two tables of
 // CM_TracePointThroughPatchCollide, cm_patch.c:1239-1261, evaluated on demand)
-__device__ __forceinline__ void pointPlaneRelation(const float4 pl, const Work &w, bool &front, float &cross) {
-	const float cx = pl.x < 0.0f ? w.p0x : w.n0x;
-	const float cy = pl.y < 0.0f ? w.p0y : w.n0y;
-	const float cz = pl.z < 0.0f ? w.p0z : w.n0z;
+__device__ __forceinline__ void pointPlaneRelation(const float4 pl, const Lane &L, bool &front, float &cross) {
+	const float cx = pl.x < 0.0f ? L.p0x : L.n0x;
+	const float cy = pl.y < 0.0f ? L.p0y : L.n0y;
+	const float cz = pl.z < 0.0f ? L.p0z : L.n0z;
 	const float off = dotf(cx, cy, cz, pl.x, pl.y, pl.z);
-	const float d1 = dotf(w.sx, w.sy, w.sz, pl.x, pl.y, pl.z) - pl.w + off;
-	const float d2 = dotf(w.ex, w.ey, w.ez, pl.x, pl.y, pl.z) - pl.w + off;
+	const float d1 = dotf(L.sx, L.sy, L.sz, pl.x, pl.y, pl.z) - pl.w + off;
+	const float d2 = dotf(L.ex, L.ey, L.ez, pl.x, pl.y, pl.z) - pl.w + off;
 	front = !(d1 <= 0);
 	if (d1 == d2) {
 		cross = 99999.0f;
@@ -243,25 +255,25 @@ __device__ __forceinline__ void pointPlaneRelation(const float4 pl, const Work &
 }
 
 template <bool COUNT>
-__device__ void sweepPatchPoint(const DevMap &m, Work &w, int firstPlane, int firstFacet, int numFacets) {
-	if (!m.playerCurveClip || !w.isPoint) return;
+__device__ __forceinline__ void sweepPatchPoint(const DevMap &m, Lane &L, int firstPlane, int firstFacet, int numFacets) {
+	if (!m.playerCurveClip || !(L.flags & F_POINT)) return;
 	for (int f = 0; f < numFacets; f++) {
 		const int4 fc = __ldg(&m.facets[firstFacet + f]);
-		Cnt<COUNT>::add(w.cFacets);
+		Cnt<COUNT>::add(L.cFacets);
 		const float4 sp = __ldg(&m.patchPlanes[firstPlane + fc.x]);
 		bool front; float t;
-		pointPlaneRelation(sp, w, front, t);
-		Cnt<COUNT>::add(w.cPatchPlanes);
+		pointPlaneRelation(sp, L, front, t);
+		Cnt<COUNT>::add(L.cPatchPlanes);
 		if (!front) continue;
 		if (t < 0) continue;
-		if (t > w.fraction) continue;
+		if (t > L.fraction) continue;
 		int j;
 		for (j = 0; j < fc.y; j++) {
 			const int bd = __ldg(&m.borders[fc.z + j]);
 			const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
 			bool bfront; float bt;
-			pointPlaneRelation(bp, w, bfront, bt);
-			Cnt<COUNT>::add(w.cPatchPlanes);
+			pointPlaneRelation(bp, L, bfront, bt);
+			Cnt<COUNT>::add(L.cPatchPlanes);
 			const bool inward = bd < 0;
 			if (bfront != inward) {
 				if (bt > t) break;
@@ -271,215 +283,111 @@ __device__ void sweepPatchPoint(const DevMap &m, Work &w, int firstPlane, int fi
 		}
 		if (j != fc.y) continue;
 		// hit: recompute with the 1/8 push-off, mixed widths as cm_patch.c:1300-1303
-		const float cx = sp.x < 0.0f ? w.p0x : w.n0x;
-		const float cy = sp.y < 0.0f ? w.p0y : w.n0y;
-		const float cz = sp.z < 0.0f ? w.p0z : w.n0z;
+		const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
+		const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
+		const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
 		const float off = dotf(cx, cy, cz, sp.x, sp.y, sp.z);
-		const float d1 = dotf(w.sx, w.sy, w.sz, sp.x, sp.y, sp.z) - sp.w + off;
-		const float d2 = dotf(w.ex, w.ey, w.ez, sp.x, sp.y, sp.z) - sp.w + off;
+		const float d1 = dotf(L.sx, L.sy, L.sz, sp.x, sp.y, sp.z) - sp.w + off;
+		const float d2 = dotf(L.ex, L.ey, L.ez, sp.x, sp.y, sp.z) - sp.w + off;
 		float fr = (float)(((double)d1 - kClipEps) / (double)(d1 - d2));
 		if (fr < 0) fr = 0;
-		w.fraction = fr;
-		w.pnx = sp.x; w.pny = sp.y; w.pnz = sp.z; w.pd = sp.w;   // type/signbits stay stale
+		L.fraction = fr;
+		L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;   // type/signbits stay stale
 	}
 }
 
 // CM_TraceThroughPatchCollide, cm_patch.c:1368-1463
 template <bool COUNT>
-__device__ void sweepPatch(const DevMap &m, Work &w, int p) {
+__device__ __forceinline__ void sweepPatch(const DevMap &m, Lane &L, int p) {
 	const float4 bmn = __ldg(&m.patchBox[2 * p]);
 	const float4 bmx = __ldg(&m.patchBox[2 * p + 1]);
-	if (w.hix < bmn.x - kBoundsEps || w.hiy < bmn.y - kBoundsEps || w.hiz < bmn.z - kBoundsEps ||
-	    w.lox > bmx.x + kBoundsEps || w.loy > bmx.y + kBoundsEps || w.loz > bmx.z + kBoundsEps) return;
-	Cnt<COUNT>::add(w.cPatches);
+	if (L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
+	    L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps) return;
+	Cnt<COUNT>::add(L.cPatches);
 	const int4 pa = __ldg(&m.patchInfo[2 * p]);
 	const int4 pb = __ldg(&m.patchInfo[2 * p + 1]);
 	const int firstPlane = pa.z, firstFacet = pb.x, numFacets = pb.y;
-	if (w.isPoint) {
-		sweepPatchPoint<COUNT>(m, w, firstPlane, firstFacet, numFacets);
+	if (L.flags & F_POINT) {
+		sweepPatchPoint<COUNT>(m, L, firstPlane, firstFacet, numFacets);
 		return;
 	}
 	float bx = 0, by = 0, bz = 0, bw = 0;
 	for (int f = 0; f < numFacets; f++) {
 		const int4 fc = __ldg(&m.facets[firstFacet + f]);
-		Cnt<COUNT>::add(w.cFacets);
+		Cnt<COUNT>::add(L.cFacets);
 		float enter = -1.0f, leave = 1.0f;
 		int hitnum = -1;
 		bool hit;
 		const float4 sp = __ldg(&m.patchPlanes[firstPlane + fc.x]);
 		{
-			const float cx = sp.x < 0.0f ? w.p0x : w.n0x;
-			const float cy = sp.y < 0.0f ? w.p0y : w.n0y;
-			const float cz = sp.z < 0.0f ? w.p0z : w.n0z;
+			const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
+			const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
+			const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
 			const float pw = sp.w - dotf(cx, cy, cz, sp.x, sp.y, sp.z);
-			if (!clipFacetPlane(sp.x, sp.y, sp.z, pw, w, enter, leave, hit)) continue;
+			if (!clipFacetPlane(sp.x, sp.y, sp.z, pw, L, enter, leave, hit)) continue;
 			if (hit) { bx = sp.x; by = sp.y; bz = sp.z; bw = pw; }
 		}
 		int j;
 		for (j = 0; j < fc.y; j++) {
 			const int bd = __ldg(&m.borders[fc.z + j]);
 			const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
-			Cnt<COUNT>::add(w.cPatchPlanes);
+			Cnt<COUNT>::add(L.cPatchPlanes);
 			// corner by the ORIGINAL plane's sign bits, dotted with the possibly flipped plane
-			const float cx = bp.x < 0.0f ? w.p0x : w.n0x;
-			const float cy = bp.y < 0.0f ? w.p0y : w.n0y;
-			const float cz = bp.z < 0.0f ? w.p0z : w.n0z;
+			const float cx = bp.x < 0.0f ? L.p0x : L.n0x;
+			const float cy = bp.y < 0.0f ? L.p0y : L.n0y;
+			const float cz = bp.z < 0.0f ? L.p0z : L.n0z;
 			float px = bp.x, py = bp.y, pz = bp.z, pw = bp.w;
 			if (bd < 0) { px = -px; py = -py; pz = -pz; pw = -pw; }
 			const float off = dotf(cx, cy, cz, px, py, pz);
 			pw = pw + fabsf(off);        // double add of two floats rounded to float == float add
-			if (!clipFacetPlane(px, py, pz, pw, w, enter, leave, hit)) break;
+			if (!clipFacetPlane(px, py, pz, pw, L, enter, leave, hit)) break;
 			if (hit) { hitnum = j; bx = px; by = py; bz = pz; bw = pw; }
 		}
 		if (j < fc.y) continue;
 		if (hitnum == fc.y - 1) continue;    // never clip against the back side
-		if (enter < leave && enter >= 0 && enter < w.fraction) {
-			w.fraction = enter;
-			w.pnx = bx; w.pny = by; w.pnz = bz; w.pd = bw;
+		if (enter < leave && enter >= 0 && enter < L.fraction) {
+			L.fraction = enter;
+			L.pnx = bx; L.pny = by; L.pnz = bz; L.pd = bw;
 		}
 	}
 }
 
 // CM_PositionTestInPatchCollide, cm_patch.c:1479-1531
 template <bool COUNT>
-__device__ bool boxInPatch(const DevMap &m, Work &w, int p) {
-	if (w.isPoint) return false;
+__device__ __forceinline__ bool boxInPatch(const DevMap &m, Lane &L, int p) {
+	if (L.flags & F_POINT) return false;
 	const int4 pa = __ldg(&m.patchInfo[2 * p]);
 	const int4 pb = __ldg(&m.patchInfo[2 * p + 1]);
 	const int firstPlane = pa.z, firstFacet = pb.x, numFacets = pb.y;
 	for (int f = 0; f < numFacets; f++) {
 		const int4 fc = __ldg(&m.facets[firstFacet + f]);
-		Cnt<COUNT>::add(w.cFacets);
+		Cnt<COUNT>::add(L.cFacets);
 		const float4 sp = __ldg(&m.patchPlanes[firstPlane + fc.x]);
 		{
-			const float cx = sp.x < 0.0f ? w.p0x : w.n0x;
-			const float cy = sp.y < 0.0f ? w.p0y : w.n0y;
-			const float cz = sp.z < 0.0f ? w.p0z : w.n0z;
+			const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
+			const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
+			const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
 			const float pw = sp.w - dotf(cx, cy, cz, sp.x, sp.y, sp.z);
-			if (dotf(sp.x, sp.y, sp.z, w.sx, w.sy, w.sz) - pw > 0.0f) continue;
+			if (dotf(sp.x, sp.y, sp.z, L.sx, L.sy, L.sz) - pw > 0.0f) continue;
 		}
 		int j;
 		for (j = 0; j < fc.y; j++) {
 			const int bd = __ldg(&m.borders[fc.z + j]);
 			const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
-			const float cx = bp.x < 0.0f ? w.p0x : w.n0x;
-			const float cy = bp.y < 0.0f ? w.p0y : w.n0y;
-			const float cz = bp.z < 0.0f ? w.p0z : w.n0z;
+			const float cx = bp.x < 0.0f ? L.p0x : L.n0x;
+			const float cy = bp.y < 0.0f ? L.p0y : L.n0y;
+			const float cz = bp.z < 0.0f ? L.p0z : L.n0z;
 			float px = bp.x, py = bp.y, pz = bp.z, pw = bp.w;
 			if (bd < 0) { px = -px; py = -py; pz = -pz; pw = -pw; }
 			const float off = dotf(cx, cy, cz, px, py, pz);
 			pw = pw + fabsf(off);
-			if (dotf(px, py, pz, w.sx, w.sy, w.sz) - pw > 0.0f) break;
+			if (dotf(px, py, pz, L.sx, L.sy, L.sz) - pw > 0.0f) break;
 		}
 		if (j < fc.y) continue;
 		return true;
 	}
 	return false;
 }
-
-// ---- leaf level ----------------------------------------------------------------------------
-
-// CM_TraceThroughLeaf + CM_TraceThroughPatch, cm_trace.c:370-427,241-254
-template <bool COUNT>
-__device__ void sweepLeaf(const DevMap &m, Work &w, const int4 leaf) {
-	Cnt<COUNT>::add(w.cLeafs);
-	for (int k = 0; k < leaf.y; k++) {
-		const int b = __ldg(&m.leafbrushes[leaf.x + k]);
-		Cnt<COUNT>::add(w.cBrushRefs);
-		float4 bmn = __ldg(&m.brushBox[2 * b]);
-		const int contents = __float_as_int(bmn.w);
-		if (!(contents & w.mask)) continue;
-		float4 bmx = __ldg(&m.brushBox[2 * b + 1]);
-		const bool boxBrush = w.isBox && b == m.boxBrush;
-		if (boxBrush) {
-			bmn.x = w.bmnx; bmn.y = w.bmny; bmn.z = w.bmnz;
-			bmx.x = w.bmxx; bmx.y = w.bmxy; bmx.z = w.bmxz;
-		}
-		Cnt<COUNT>::add(w.cBrushBounds);
-		// CM_BoundsIntersect, cm_test.c:481-494
-		if (w.hix < bmn.x - kBoundsEps || w.hiy < bmn.y - kBoundsEps || w.hiz < bmn.z - kBoundsEps ||
-		    w.lox > bmx.x + kBoundsEps || w.loy > bmx.y + kBoundsEps || w.loz > bmx.z + kBoundsEps) continue;
-		sweepBrush<COUNT>(m, w, b, __float_as_int(bmx.w), __ldg(&m.brushNumSides[b]), contents, boxBrush);
-		if (w.fraction == 0.0f) return;
-	}
-	if (m.noCurves) return;
-	for (int k = 0; k < leaf.w; k++) {
-		const int p = __ldg(&m.surf2patch[__ldg(&m.leafsurfaces[leaf.z + k])]);
-		if (p < 0) continue;
-		const int4 pa = __ldg(&m.patchInfo[2 * p]);
-		if (!(pa.y & w.mask)) continue;
-		const float before = w.fraction;
-		sweepPatch<COUNT>(m, w, p);
-		if (w.fraction < before) {
-			w.surfaceFlags = pa.x;
-			w.contents = pa.y;
-			w.hitId = -2 - p;
-		}
-		if (w.fraction == 0.0f) return;
-	}
-}
-
-// CM_TestBoxInBrush, cm_trace.c:83-123
-template <bool COUNT>
-__device__ void boxInBrush(const DevMap &m, Work &w, int b, float4 bmn, float4 bmx, int contents, bool boxBrush) {
-	const int nsides = __ldg(&m.brushNumSides[b]);
-	if (!nsides) return;
-	Cnt<COUNT>::add(w.cBrushBounds);
-	if (w.lox > bmx.x || w.loy > bmx.y || w.loz > bmx.z || w.hix < bmn.x || w.hiy < bmn.y || w.hiz < bmn.z) return;
-	const int firstSide = __float_as_int(bmx.w);
-	for (int s = 6; s < nsides; s++) {
-		float4 pl = __ldg(&m.sidePlanes[firstSide + s]);
-		if (boxBrush) pl.w = boxSideDist(w, s);
-		Cnt<COUNT>::add(w.cBrushSides);
-		const float cx = pl.x < 0.0f ? w.p0x : w.n0x;
-		const float cy = pl.y < 0.0f ? w.p0y : w.n0y;
-		const float cz = pl.z < 0.0f ? w.p0z : w.n0z;
-		const float distf = pl.w - dotf(cx, cy, cz, pl.x, pl.y, pl.z);    // all-float (cm_trace.c:111)
-		const double d1 = dotd((double)w.sx, (double)w.sy, (double)w.sz, pl.x, pl.y, pl.z) - (double)distf;
-		if (d1 > 0) return;
-	}
-	w.startsolid = w.allsolid = 1;
-	w.fraction = 0;
-	w.contents = contents;
-	w.hitId = b;
-}
-
-// CM_TestInLeaf, cm_trace.c:130-183
-template <bool COUNT>
-__device__ void testLeaf(const DevMap &m, Work &w, const int4 leaf) {
-	Cnt<COUNT>::add(w.cLeafs);
-	for (int k = 0; k < leaf.y; k++) {
-		const int b = __ldg(&m.leafbrushes[leaf.x + k]);
-		Cnt<COUNT>::add(w.cBrushRefs);
-		float4 bmn = __ldg(&m.brushBox[2 * b]);
-		const int contents = __float_as_int(bmn.w);
-		if (!(contents & w.mask)) continue;
-		float4 bmx = __ldg(&m.brushBox[2 * b + 1]);
-		const bool boxBrush = w.isBox && b == m.boxBrush;
-		if (boxBrush) {
-			bmn.x = w.bmnx; bmn.y = w.bmny; bmn.z = w.bmnz;
-			bmx.x = w.bmxx; bmx.y = w.bmxy; bmx.z = w.bmxz;
-		}
-		boxInBrush<COUNT>(m, w, b, bmn, bmx, contents, boxBrush);
-		if (w.allsolid) return;
-	}
-	if (m.noCurves) return;
-	for (int k = 0; k < leaf.w; k++) {
-		const int p = __ldg(&m.surf2patch[__ldg(&m.leafsurfaces[leaf.z + k])]);
-		if (p < 0) continue;
-		const int4 pa = __ldg(&m.patchInfo[2 * p]);
-		if (!(pa.y & w.mask)) continue;
-		if (boxInPatch<COUNT>(m, w, p)) {
-			w.startsolid = w.allsolid = 1;
-			w.fraction = 0;
-			w.contents = pa.y;
-			w.hitId = -2 - p;
-			return;
-		}
-	}
-}
-
-// ---- tree level ------------------------------------------------------------------------------
 
 // BoxOnPlaneSide, q_math.c:724-758
 __device__ __forceinline__ int boxPlaneSide(const DevMap &m, int num, const int4 nd,
@@ -502,260 +410,461 @@ __device__ __forceinline__ int boxPlaneSide(const DevMap &m, int num, const int4
 	return s;
 }
 
-// CM_PositionTest, cm_trace.c:191-226 (+ CM_BoxLeafnums_r / CM_StoreLeafs, cm_test.c:131-156,73-88).
-// The reference first lists <= 1024 leafs and then tests them in list order;
-// testing each leaf when it is discovered is the same sequence of tests.
-template <bool COUNT>
-__device__ void positionTestWorld(const DevMap &m, Work &w, int *status) {
-	const float lox = (w.sx + w.n0x) - 1.0f, loy = (w.sy + w.n0y) - 1.0f, loz = (w.sz + w.n0z) - 1.0f;
-	const float hix = (w.sx + w.p0x) + 1.0f, hiy = (w.sy + w.p0y) + 1.0f, hiz = (w.sz + w.p0z) + 1.0f;
-	int stack[kMaxDepth];
-	int sp = 0, found = 0, num = 0;
-	for (;;) {
-		if (num < 0) {
-			if (found >= kMaxPosLeafs) return;
-			found++;
-			testLeaf<COUNT>(m, w, __ldg(&m.leafs[-1 - num]));
-			if (w.allsolid) return;
-			if (!sp) return;
-			num = stack[--sp];
-			continue;
-		}
-		const int4 nd = __ldg(&m.nodes[num]);
-		Cnt<COUNT>::add(w.cNodes);
-		const int s = boxPlaneSide(m, num, nd, lox, loy, loz, hix, hiy, hiz);
-		if (s == 1) {
-			num = nd.x;
-		} else if (s == 2) {
-			num = nd.y;
-		} else {
-			if (sp < kMaxDepth) stack[sp++] = nd.y; else atomicOr(status, 1);
-			num = nd.x;
-		}
-	}
-}
-
 struct Seg { int num; float f1, f2, ax, ay, az, bx, by, bz; };
 
-// CM_TraceThroughTree, cm_trace.c:439-538, as a loop with an explicit stack of
-// pending far halves.  Split points are carried (computed from the CURRENT
-// segment in float), never recomputed from the root segment.
-template <bool COUNT>
-__device__ void sweepWorld(const DevMap &m, Work &w, int *status) {
-	Seg stack[kMaxDepth];
-	int sp = 0;
-	Seg cur;
-	cur.num = 0; cur.f1 = 0.0f; cur.f2 = 1.0f;
-	cur.ax = w.sx; cur.ay = w.sy; cur.az = w.sz;
-	cur.bx = w.ex; cur.by = w.ey; cur.bz = w.ez;
-
-	for (;;) {
-		bool done = false;
-		if (w.fraction <= cur.f1) {
-			done = true;
-		} else if (cur.num < 0) {
-			sweepLeaf<COUNT>(m, w, __ldg(&m.leafs[-1 - cur.num]));
-			done = true;
-		}
-		if (done) {
-			if (!sp) return;
-			cur = stack[--sp];
-			continue;
-		}
-
-		const int4 nd = __ldg(&m.nodes[cur.num]);
-		Cnt<COUNT>::add(w.cNodes);
-		double t1, t2, off;
-		if (nd.z < 3) {
-			const float dist = __int_as_float(nd.w);
-			t1 = (double)(sel3(cur.ax, cur.ay, cur.az, nd.z) - dist);   // float subtract, then widened
-			t2 = (double)(sel3(cur.bx, cur.by, cur.bz, nd.z) - dist);
-			off = (double)sel3(w.extx, w.exty, w.extz, nd.z);
-		} else {
-			const float4 pl = __ldg(&m.nodePlanes[cur.num]);
-			t1 = dotd((double)pl.x, (double)pl.y, (double)pl.z, cur.ax, cur.ay, cur.az) - (double)pl.w;
-			t2 = dotd((double)pl.x, (double)pl.y, (double)pl.z, cur.bx, cur.by, cur.bz) - (double)pl.w;
-			off = w.isPoint ? 0.0 : 2048.0;
-		}
-		if (t1 >= off + 1 && t2 >= off + 1) { cur.num = nd.x; continue; }
-		if (t1 < -off - 1 && t2 < -off - 1) { cur.num = nd.y; continue; }
-
-		int side;
-		float fnear, ffar;
-		if (t1 < t2) {
-			const float inv = (float)(1.0 / (t1 - t2));
-			side = 1;
-			ffar = (float)((t1 + off + kClipEps) * (double)inv);
-			fnear = (float)((t1 - off + kClipEps) * (double)inv);
-		} else if (t1 > t2) {
-			const float inv = (float)(1.0 / (t1 - t2));
-			side = 0;
-			ffar = (float)((t1 - off - kClipEps) * (double)inv);
-			fnear = (float)((t1 + off + kClipEps) * (double)inv);
-		} else {
-			side = 0;
-			fnear = 1.0f;
-			ffar = 0.0f;
-		}
-		if (fnear < 0) fnear = 0; else if (fnear > 1) fnear = 1;
-		if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
-		Cnt<COUNT>::add(w.cSplits);
-
-		Seg far;
-		far.num = side ? nd.x : nd.y;
-		far.f1 = cur.f1 + (cur.f2 - cur.f1) * ffar;
-		far.f2 = cur.f2;
-		far.ax = cur.ax + ffar * (cur.bx - cur.ax);
-		far.ay = cur.ay + ffar * (cur.by - cur.ay);
-		far.az = cur.az + ffar * (cur.bz - cur.az);
-		far.bx = cur.bx; far.by = cur.by; far.bz = cur.bz;
-		const float midf = cur.f1 + (cur.f2 - cur.f1) * fnear;
-		const float mx = cur.ax + fnear * (cur.bx - cur.ax);
-		const float my = cur.ay + fnear * (cur.by - cur.ay);
-		const float mz = cur.az + fnear * (cur.bz - cur.az);
-		if (sp < kMaxDepth) stack[sp++] = far; else atomicOr(status, 1);
-		cur.num = side ? nd.y : nd.x;
-		cur.f2 = midf;
-		cur.bx = mx; cur.by = my; cur.bz = mz;
-	}
+// take the next pending far half, or finish the item (the returns of the reference's recursion)
+__device__ __forceinline__ int popSegment(Lane &L, const Seg *stack) {
+	if (L.sp == 0) return M_FINISH;
+	const Seg s = stack[--L.sp];
+	L.num = s.num; L.f1 = s.f1; L.f2 = s.f2;
+	L.ax = s.ax; L.ay = s.ay; L.az = s.az; L.bx = s.bx; L.by = s.by; L.bz = s.bz;
+	return M_NODE;
 }
 
-// ---- CM_Trace (cm_trace.c:545-687) and CM_TransformedBoxTrace (cm_trace.c:708-805) ---------------
-template <bool COUNT>
-__global__ void __launch_bounds__(128) traceKernel(const DevMap m, const TraceBatch q) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= q.n) return;
+__device__ __forceinline__ void enterLeaf(Lane &L, const int4 leaf) {
+	L.k = leaf.x; L.kEnd = leaf.x + leaf.y;
+	L.ps = leaf.z; L.psEnd = leaf.z + leaf.w;
+}
 
-	Work w;
-	// raw inputs
+// ---- item setup: CM_Trace (cm_trace.c:545-669) and the head of CM_TransformedBoxTrace (cm_trace.c:708-786) -----
+__device__ __forceinline__ int beginItem(const DevMap &m, const TraceBatch &q, Lane &L, int i) {
+	L.idx = i;
 	const float s0x = q.starts[3 * (size_t)i], s0y = q.starts[3 * (size_t)i + 1], s0z = q.starts[3 * (size_t)i + 2];
 	const float e0x = q.ends[3 * (size_t)i], e0y = q.ends[3 * (size_t)i + 1], e0z = q.ends[3 * (size_t)i + 2];
-	float mnx = 0, mny = 0, mnz = 0, mxx = 0, mxy = 0, mxz = 0;
-	if (q.mins) { const float *p = q.mins + 3 * (size_t)i * q.hullStride; mnx = p[0]; mny = p[1]; mnz = p[2]; }
-	if (q.maxs) { const float *p = q.maxs + 3 * (size_t)i * q.hullStride; mxx = p[0]; mxy = p[1]; mxz = p[2]; }
-	const int model = q.models ? q.models[i] : 0;
-	w.mask = q.masks[(size_t)i * q.maskStride];
-	w.isBox = (model == kBoxModelHandle);
-	w.bmnx = w.bmny = w.bmnz = w.bmxx = w.bmxy = w.bmxz = 0.0f;
-	if (w.isBox && q.boxmins) {
-		w.bmnx = q.boxmins[3 * (size_t)i]; w.bmny = q.boxmins[3 * (size_t)i + 1]; w.bmnz = q.boxmins[3 * (size_t)i + 2];
-		w.bmxx = q.boxmaxs[3 * (size_t)i]; w.bmxy = q.boxmaxs[3 * (size_t)i + 1]; w.bmxz = q.boxmaxs[3 * (size_t)i + 2];
+	float mnx, mny, mnz, mxx, mxy, mxz;
+	if (q.mins) {
+		const float *a = q.mins + 3 * (size_t)i, *b = q.maxs + 3 * (size_t)i;
+		mnx = a[0]; mny = a[1]; mnz = a[2]; mxx = b[0]; mxy = b[1]; mxz = b[2];
+	} else {
+		mnx = q.sharedMins[0]; mny = q.sharedMins[1]; mnz = q.sharedMins[2];
+		mxx = q.sharedMaxs[0]; mxy = q.sharedMaxs[1]; mxz = q.sharedMaxs[2];
 	}
+	const int model = q.models ? q.models[i] : 0;
+	L.mask = q.masks ? q.masks[i] : q.sharedMask;
+	L.flags = (model == kBoxModelHandle) ? F_BOX : 0;
 
 	// symmetrise the box (cm_trace.c:582-588 / 756-762): (mins+maxs)*0.5 is a float add and an exact halving
 	const float ox = (mnx + mxx) * 0.5f, oy = (mny + mxy) * 0.5f, oz = (mnz + mxz) * 0.5f;
-	w.n0x = mnx - ox; w.n0y = mny - oy; w.n0z = mnz - oz;
-	w.p0x = mxx - ox; w.p0y = mxy - oy; w.p0z = mxz - oz;
+	L.n0x = mnx - ox; L.n0y = mny - oy; L.n0z = mnz - oz;
+	L.p0x = mxx - ox; L.p0y = mxy - oy; L.p0z = mxz - oz;
 	float lsx = s0x + ox, lsy = s0y + oy, lsz = s0z + oz;
 	float lex = e0x + ox, ley = e0y + oy, lez = e0z + oz;
+	float ts0x = s0x, ts0y = s0y, ts0z = s0z, te0x = e0x, te0y = e0y, te0z = e0z;   // CM_Trace's own start/end arguments
 
-	// CM_TransformedBoxTrace: into the model's frame (cm_trace.c:764-779)
-	bool rotated = false;
-	float r00 = 0, r01 = 0, r02 = 0, r10 = 0, r11 = 0, r12 = 0, r20 = 0, r21 = 0, r22 = 0;
 	if (q.origins) {
+		// into the model's frame (cm_trace.c:764-779)
 		const float gx = q.origins[3 * (size_t)i], gy = q.origins[3 * (size_t)i + 1], gz = q.origins[3 * (size_t)i + 2];
 		lsx = lsx - gx; lsy = lsy - gy; lsz = lsz - gz;
 		lex = lex - gx; ley = ley - gy; lez = lez - gz;
 		const int ri = q.rotIndex ? q.rotIndex[i] : -1;
 		if (ri >= 0) {
-			rotated = true;
+			L.flags |= F_ROTATED;
 			const float *r = q.rotations + 9 * (size_t)ri;
-			r00 = r[0]; r01 = r[1]; r02 = r[2]; r10 = r[3]; r11 = r[4]; r12 = r[5]; r20 = r[6]; r21 = r[7]; r22 = r[8];
 			float tx = lsx, ty = lsy, tz = lsz;
-			lsx = dotf(r00, r01, r02, tx, ty, tz); lsy = dotf(r10, r11, r12, tx, ty, tz); lsz = dotf(r20, r21, r22, tx, ty, tz);
+			lsx = dotf(r[0], r[1], r[2], tx, ty, tz); lsy = dotf(r[3], r[4], r[5], tx, ty, tz); lsz = dotf(r[6], r[7], r[8], tx, ty, tz);
 			tx = lex; ty = ley; tz = lez;
-			lex = dotf(r00, r01, r02, tx, ty, tz); ley = dotf(r10, r11, r12, tx, ty, tz); lez = dotf(r20, r21, r22, tx, ty, tz);
+			lex = dotf(r[0], r[1], r[2], tx, ty, tz); ley = dotf(r[3], r[4], r[5], tx, ty, tz); lez = dotf(r[6], r[7], r[8], tx, ty, tz);
 		}
-	}
-
-	// CM_Trace proper.  With origins the reference symmetrises a second time inside CM_Trace
-	// (cm_trace.c:582-588); the box is already symmetric, but the float ops are repeated verbatim.
-	float ts0x = lsx, ts0y = lsy, ts0z = lsz, te0x = lex, te0y = ley, te0z = lez;   // CM_Trace's start/end arguments
-	if (q.origins) {
-		const float o2x = (w.n0x + w.p0x) * 0.5f, o2y = (w.n0y + w.p0y) * 0.5f, o2z = (w.n0z + w.p0z) * 0.5f;
-		const float a0x = w.n0x - o2x, a0y = w.n0y - o2y, a0z = w.n0z - o2z;
-		const float a1x = w.p0x - o2x, a1y = w.p0y - o2y, a1z = w.p0z - o2z;
-		w.n0x = a0x; w.n0y = a0y; w.n0z = a0z; w.p0x = a1x; w.p0y = a1y; w.p0z = a1z;
+		ts0x = lsx; ts0y = lsy; ts0z = lsz; te0x = lex; te0y = ley; te0z = lez;
+		// CM_Trace symmetrises a second time (cm_trace.c:582-588); the float ops are repeated verbatim
+		const float o2x = (L.n0x + L.p0x) * 0.5f, o2y = (L.n0y + L.p0y) * 0.5f, o2z = (L.n0z + L.p0z) * 0.5f;
+		const float a0x = L.n0x - o2x, a0y = L.n0y - o2y, a0z = L.n0z - o2z;
+		const float a1x = L.p0x - o2x, a1y = L.p0y - o2y, a1z = L.p0z - o2z;
+		L.n0x = a0x; L.n0y = a0y; L.n0z = a0z; L.p0x = a1x; L.p0y = a1y; L.p0z = a1z;
 		lsx = lsx + o2x; lsy = lsy + o2y; lsz = lsz + o2z;
 		lex = lex + o2x; ley = ley + o2y; lez = lez + o2z;
-	} else {
-		ts0x = s0x; ts0y = s0y; ts0z = s0z; te0x = e0x; te0y = e0y; te0z = e0z;
 	}
-	w.sx = lsx; w.sy = lsy; w.sz = lsz; w.ex = lex; w.ey = ley; w.ez = lez;
+	L.sx = lsx; L.sy = lsy; L.sz = lsz; L.ex = lex; L.ey = ley; L.ez = lez;
 
-	w.allsolid = 0; w.startsolid = 0; w.fraction = 1.0f;
-	w.pnx = w.pny = w.pnz = w.pd = 0.0f; w.ptypesign = 0;
-	w.surfaceFlags = 0; w.contents = 0; w.hitId = -1;
-	w.isPoint = false;
-	w.extx = w.exty = w.extz = 0.0f;
-	w.cNodes = w.cLeafs = w.cBrushRefs = w.cBrushBounds = w.cBrushSides = w.cCross = w.cSplits = 0;
-	w.cPatches = w.cPatchPlanes = w.cFacets = 0;
+	L.solid = 0; L.fraction = 1.0f;
+	L.pnx = L.pny = L.pnz = L.pd = 0.0f; L.ptypesign = 0;
+	L.surfaceFlags = 0; L.contents = 0; L.hitId = -1;
+	L.sp = 0; L.found = 0;
+	L.cNodes = L.cLeafs = L.cBrushRefs = L.cBrushBounds = L.cBrushSides = L.cCross = L.cSplits = 0;
+	L.cPatches = L.cPatchPlanes = L.cFacets = 0;
 
 	// swept bounds (cm_trace.c:628-636)
-	if (w.sx < w.ex) { w.lox = w.sx + w.n0x; w.hix = w.ex + w.p0x; } else { w.lox = w.ex + w.n0x; w.hix = w.sx + w.p0x; }
-	if (w.sy < w.ey) { w.loy = w.sy + w.n0y; w.hiy = w.ey + w.p0y; } else { w.loy = w.ey + w.n0y; w.hiy = w.sy + w.p0y; }
-	if (w.sz < w.ez) { w.loz = w.sz + w.n0z; w.hiz = w.ez + w.p0z; } else { w.loz = w.ez + w.n0z; w.hiz = w.sz + w.p0z; }
+	if (L.sx < L.ex) { L.lox = L.sx + L.n0x; L.hix = L.ex + L.p0x; } else { L.lox = L.ex + L.n0x; L.hix = L.sx + L.p0x; }
+	if (L.sy < L.ey) { L.loy = L.sy + L.n0y; L.hiy = L.ey + L.p0y; } else { L.loy = L.ey + L.n0y; L.hiy = L.sy + L.p0y; }
+	if (L.sz < L.ez) { L.loz = L.sz + L.n0z; L.hiz = L.ez + L.p0z; } else { L.loz = L.ez + L.n0z; L.hiz = L.sz + L.p0z; }
 
 	int4 mleaf = make_int4(0, 0, 0, 0);
-	if (model) {
-		mleaf = w.isBox ? make_int4(m.boxLeafBrush, 1, 0, 0) : __ldg(&m.modelLeafs[model]);
-	}
+	if (model) mleaf = (L.flags & F_BOX) ? make_int4(m.boxLeafBrush, 1, 0, 0) : __ldg(&m.modelLeafs[model]);
 
 	if (ts0x == te0x && ts0y == te0y && ts0z == te0z) {
 		// position test: isPoint stays false and extents zero here (cm_trace.c:641-646)
-		if (model) testLeaf<COUNT>(m, w, mleaf);
-		else       positionTestWorld<COUNT>(m, w, q.status);
-	} else {
-		if (w.n0x == 0.0f && w.n0y == 0.0f && w.n0z == 0.0f) {
-			w.isPoint = true;
-		} else {
-			w.extx = w.p0x; w.exty = w.p0y; w.extz = w.p0z;
-		}
-		if (model) sweepLeaf<COUNT>(m, w, mleaf);
-		else       sweepWorld<COUNT>(m, w, q.status);
+		L.flags |= F_POSTEST;
+		if (model) { enterLeaf(L, mleaf); return M_PLEAF; }
+		L.num = 0;
+		return M_PNODE;
 	}
+	if (L.n0x == 0.0f && L.n0y == 0.0f && L.n0z == 0.0f) L.flags |= F_POINT;
+	if (model) { enterLeaf(L, mleaf); return M_LEAF; }
+	L.num = 0; L.f1 = 0.0f; L.f2 = 1.0f;
+	L.ax = L.sx; L.ay = L.sy; L.az = L.sz; L.bx = L.ex; L.by = L.ey; L.bz = L.ez;
+	return M_NODE;
+}
 
+// ---- item epilogue: cm_trace.c:671-686 and 788-801 ----------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ void finishItem(const TraceBatch &q, Lane &L) {
+	const int i = L.idx;
+	const float s0x = q.starts[3 * (size_t)i], s0y = q.starts[3 * (size_t)i + 1], s0z = q.starts[3 * (size_t)i + 2];
+	const float e0x = q.ends[3 * (size_t)i], e0y = q.ends[3 * (size_t)i + 1], e0z = q.ends[3 * (size_t)i + 2];
 	// plane back to world space (cm_trace.c:789-793): rows of the transpose are columns of the matrix
-	if (rotated && w.fraction != 1.0f) {
-		const float tx = w.pnx, ty = w.pny, tz = w.pnz;
-		w.pnx = dotf(r00, r10, r20, tx, ty, tz);
-		w.pny = dotf(r01, r11, r21, tx, ty, tz);
-		w.pnz = dotf(r02, r12, r22, tx, ty, tz);
+	if ((L.flags & F_ROTATED) && L.fraction != 1.0f) {
+		const float *r = q.rotations + 9 * (size_t)q.rotIndex[i];
+		const float tx = L.pnx, ty = L.pny, tz = L.pnz;
+		L.pnx = dotf(r[0], r[3], r[6], tx, ty, tz);
+		L.pny = dotf(r[1], r[4], r[7], tx, ty, tz);
+		L.pnz = dotf(r[2], r[5], r[8], tx, ty, tz);
 	}
-
 	// endpos from the caller's start/end (cm_trace.c:672-678, 797-799)
 	float px, py, pz;
-	if (!q.origins && w.fraction == 1.0f) {
+	if (!q.origins && L.fraction == 1.0f) {
 		px = e0x; py = e0y; pz = e0z;
 	} else {
-		px = s0x + w.fraction * (e0x - s0x);
-		py = s0y + w.fraction * (e0y - s0y);
-		pz = s0z + w.fraction * (e0z - s0z);
+		px = s0x + L.fraction * (e0x - s0x);
+		py = s0y + L.fraction * (e0y - s0y);
+		pz = s0z + L.fraction * (e0z - s0z);
 	}
-
 	uint2 *o = q.out + 7 * (size_t)i;
-	o[0] = make_uint2((unsigned)w.allsolid, (unsigned)w.startsolid);
-	o[1] = make_uint2(__float_as_uint(w.fraction), __float_as_uint(px));
+	o[0] = make_uint2((unsigned)(L.solid & 1), (unsigned)((L.solid >> 1) & 1));
+	o[1] = make_uint2(__float_as_uint(L.fraction), __float_as_uint(px));
 	o[2] = make_uint2(__float_as_uint(py), __float_as_uint(pz));
-	o[3] = make_uint2(__float_as_uint(w.pnx), __float_as_uint(w.pny));
-	o[4] = make_uint2(__float_as_uint(w.pnz), __float_as_uint(w.pd));
-	o[5] = make_uint2((unsigned)w.ptypesign & 0xffffu, (unsigned)w.surfaceFlags);
-	o[6] = make_uint2((unsigned)w.contents, 0u);
-	if (q.hitIds) q.hitIds[i] = w.hitId;
-
+	o[3] = make_uint2(__float_as_uint(L.pnx), __float_as_uint(L.pny));
+	o[4] = make_uint2(__float_as_uint(L.pnz), __float_as_uint(L.pd));
+	o[5] = make_uint2((unsigned)L.ptypesign & 0xffffu, (unsigned)L.surfaceFlags);
+	o[6] = make_uint2((unsigned)L.contents, 0u);
+	if (q.hitIds) q.hitIds[i] = L.hitId;
 	if (COUNT) {
 		Counters *c = q.counters;
 		atomicAdd(&c->traces, 1ull);
-		atomicAdd(&c->nodes, (unsigned long long)w.cNodes);
-		atomicAdd(&c->leafs, (unsigned long long)w.cLeafs);
-		atomicAdd(&c->brushRefs, (unsigned long long)w.cBrushRefs);
-		atomicAdd(&c->brushBounds, (unsigned long long)w.cBrushBounds);
-		atomicAdd(&c->brushSides, (unsigned long long)w.cBrushSides);
-		atomicAdd(&c->crossings, (unsigned long long)w.cCross);
-		atomicAdd(&c->splits, (unsigned long long)w.cSplits);
-		atomicAdd(&c->patches, (unsigned long long)w.cPatches);
-		atomicAdd(&c->patchPlanes, (unsigned long long)w.cPatchPlanes);
-		atomicAdd(&c->facets, (unsigned long long)w.cFacets);
+		atomicAdd(&c->nodes, (unsigned long long)L.cNodes);
+		atomicAdd(&c->leafs, (unsigned long long)L.cLeafs);
+		atomicAdd(&c->brushRefs, (unsigned long long)L.cBrushRefs);
+		atomicAdd(&c->brushBounds, (unsigned long long)L.cBrushBounds);
+		atomicAdd(&c->brushSides, (unsigned long long)L.cBrushSides);
+		atomicAdd(&c->crossings, (unsigned long long)L.cCross);
+		atomicAdd(&c->splits, (unsigned long long)L.cSplits);
+		atomicAdd(&c->patches, (unsigned long long)L.cPatches);
+		atomicAdd(&c->patchPlanes, (unsigned long long)L.cPatchPlanes);
+		atomicAdd(&c->facets, (unsigned long long)L.cFacets);
+	}
+}
+
+// =====================================================================================
+// the trace kernel
+// =====================================================================================
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const TraceBatch q) {
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned laneLt = (1u << lane) - 1u;
+	Seg stack[kMaxDepth];
+	Lane L;
+	int mode = M_FETCH;
+	int chunkNext = 0, chunkEnd = 0;     // warp-uniform
+	bool supply = true;                   // warp-uniform: the global cursor may still have items
+
+	for (;;) {
+		// ---------------- fetch: all lanes arrive here together --------------------------
+		const unsigned need = __ballot_sync(0xffffffffu, mode == M_FETCH);
+		if (need) {
+			if (chunkNext >= chunkEnd && supply) {
+				int base = 0;
+				if (lane == 0) base = atomicAdd(q.cursor, kChunk);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
+				else { chunkNext = base; chunkEnd = min(base + kChunk, q.n); }
+			}
+			if (chunkNext >= chunkEnd) {
+				if (need == 0xffffffffu) break;           // nothing in flight, nothing left
+			} else {
+				if (mode == M_FETCH) {
+					const int my = chunkNext + __popc(need & laneLt);
+					if (my < chunkEnd) mode = beginItem(m, q, L, my);
+				}
+				chunkNext = min(chunkNext + __popc(need), chunkEnd);
+			}
+		}
+
+		// ---------------- one node of CM_TraceThroughTree, cm_trace.c:439-538 -----------------
+		if (mode == M_NODE) {
+			if (L.fraction <= L.f1) {
+				mode = popSegment(L, stack);                  // already hit something nearer
+			} else if (L.num < 0) {
+				enterLeaf(L, __ldg(&m.leafs[-1 - L.num]));
+				Cnt<COUNT>::add(L.cLeafs);
+				mode = M_LEAF;
+			} else {
+				const int4 nd = __ldg(&m.nodes[L.num]);
+				Cnt<COUNT>::add(L.cNodes);
+				double t1, t2, off;
+				if (nd.z < 3) {
+					const float dist = __int_as_float(nd.w);
+					t1 = (double)(sel3(L.ax, L.ay, L.az, nd.z) - dist);   // float subtract, then widened
+					t2 = (double)(sel3(L.bx, L.by, L.bz, nd.z) - dist);
+					off = (L.flags & F_POINT) ? 0.0 : (double)sel3(L.p0x, L.p0y, L.p0z, nd.z);
+				} else {
+					const float4 pl = __ldg(&m.nodePlanes[L.num]);
+					t1 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.ax, L.ay, L.az) - (double)pl.w;
+					t2 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.bx, L.by, L.bz) - (double)pl.w;
+					off = (L.flags & F_POINT) ? 0.0 : 2048.0;
+				}
+				if (t1 >= off + 1 && t2 >= off + 1) {
+					L.num = nd.x;
+				} else if (t1 < -off - 1 && t2 < -off - 1) {
+					L.num = nd.y;
+				} else {
+					int side;
+					float fnear, ffar;
+					if (t1 < t2) {
+						const float inv = (float)(1.0 / (t1 - t2));
+						side = 1;
+						ffar = (float)((t1 + off + kClipEps) * (double)inv);
+						fnear = (float)((t1 - off + kClipEps) * (double)inv);
+					} else if (t1 > t2) {
+						const float inv = (float)(1.0 / (t1 - t2));
+						side = 0;
+						ffar = (float)((t1 - off - kClipEps) * (double)inv);
+						fnear = (float)((t1 + off + kClipEps) * (double)inv);
+					} else {
+						side = 0;
+						fnear = 1.0f;
+						ffar = 0.0f;
+					}
+					if (fnear < 0) fnear = 0; else if (fnear > 1) fnear = 1;
+					if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
+					Cnt<COUNT>::add(L.cSplits);
+					// the far half [mid(ffar), b] waits on the stack; the near half [a, mid(fnear)] goes on.
+					// split points are computed from the CURRENT segment in float and carried.
+					Seg far;
+					far.num = side ? nd.x : nd.y;
+					far.f1 = L.f1 + (L.f2 - L.f1) * ffar;
+					far.f2 = L.f2;
+					far.ax = L.ax + ffar * (L.bx - L.ax);
+					far.ay = L.ay + ffar * (L.by - L.ay);
+					far.az = L.az + ffar * (L.bz - L.az);
+					far.bx = L.bx; far.by = L.by; far.bz = L.bz;
+					const float midf = L.f1 + (L.f2 - L.f1) * fnear;
+					const float mx = L.ax + fnear * (L.bx - L.ax);
+					const float my = L.ay + fnear * (L.by - L.ay);
+					const float mz = L.az + fnear * (L.bz - L.az);
+					if (L.sp < kMaxDepth) stack[L.sp++] = far; else atomicOr(q.status, 1);
+					L.num = side ? nd.y : nd.x;
+					L.f2 = midf;
+					L.bx = mx; L.by = my; L.bz = mz;
+				}
+			}
+		}
+
+		// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-399 -----------------
+		if (mode == M_LEAF) {
+			if (L.k >= L.kEnd) {
+				mode = (L.ps < L.psEnd && !m.noCurves) ? M_PATCH : popSegment(L, stack);
+			} else {
+				float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
+				float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
+				L.k++;
+				Cnt<COUNT>::add(L.cBrushRefs);
+				const int contents = __float_as_int(bmn.w);
+				if (contents & L.mask) {
+					const int b = __float_as_int(bmx.w);
+					const bool boxBrush = (L.flags & F_BOX) && b == m.boxBrush;
+					if (boxBrush && q.boxmins) {
+						const float *a = q.boxmins + 3 * (size_t)L.idx, *c = q.boxmaxs + 3 * (size_t)L.idx;
+						bmn.x = a[0]; bmn.y = a[1]; bmn.z = a[2];
+						bmx.x = c[0]; bmx.y = c[1]; bmx.z = c[2];
+					}
+					Cnt<COUNT>::add(L.cBrushBounds);
+					// CM_BoundsIntersect, cm_test.c:481-494
+					if (!(L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
+					      L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps)) {
+						const int4 bi = __ldg(&m.brushInfo[b]);
+						if (bi.y > 0) {
+							L.brush = b; L.firstSide = bi.x; L.sideEnd = bi.y; L.bcontents = contents;
+							L.enter = -1.0f; L.leave = 1.0f; L.lead = -1;
+							L.flags = (L.flags & ~(F_STARTOUT | F_ENDOUT | F_BOXBRUSH)) | (boxBrush ? F_BOXBRUSH : 0);
+							L.side = 0;
+							bool alive = true;
+							if (bi.w) {
+								// the six axial sides straight from the box already in registers:
+								// side 2a   : normal -e_a, dist -mins[a], corner component size[1][a]
+								// side 2a+1 : normal +e_a, dist  maxs[a], corner component size[0][a]
+								// (DotProductDP with a unit normal is exactly +-component)
+								const double sx = L.sx, sy = L.sy, sz = L.sz, ex = L.ex, ey = L.ey, ez = L.ez;
+								Cnt<COUNT>::add(L.cBrushSides, 6);
+								{
+									const double dn = (double)L.p0x - (double)bmn.x, dp = (double)bmx.x - (double)L.n0x;
+									alive = clipSide<COUNT>(L, -sx - dn, -ex - dn, 0);
+									if (alive) alive = clipSide<COUNT>(L, sx - dp, ex - dp, 1);
+								}
+								if (alive) {
+									const double dn = (double)L.p0y - (double)bmn.y, dp = (double)bmx.y - (double)L.n0y;
+									alive = clipSide<COUNT>(L, -sy - dn, -ey - dn, 2);
+									if (alive) alive = clipSide<COUNT>(L, sy - dp, ey - dp, 3);
+								}
+								if (alive) {
+									const double dn = (double)L.p0z - (double)bmn.z, dp = (double)bmx.z - (double)L.n0z;
+									alive = clipSide<COUNT>(L, -sz - dn, -ez - dn, 4);
+									if (alive) alive = clipSide<COUNT>(L, sz - dp, ez - dp, 5);
+								}
+								L.side = 6;
+							}
+							if (alive) {
+								if (L.side < L.sideEnd) {
+									mode = M_SIDE;
+								} else {
+									finishBrush(m, q, L);
+									if (L.fraction == 0.0f) mode = M_FINISH;
+								}
+							}
+						}
+					}
+				}
+			}
+		}
+
+		// ---------------- one general side of CM_TraceThroughBrush, cm_trace.c:291-332 -----------------
+		if (mode == M_SIDE) {
+			float4 pl = __ldg(&m.sidePlanes[L.firstSide + L.side]);
+			if (L.flags & F_BOXBRUSH) pl.w = boxSideDist(q, L.idx, L.side);
+			Cnt<COUNT>::add(L.cBrushSides);
+			// tw.offsets[signbits]: the box corner that touches the plane first
+			const float cx = pl.x < 0.0f ? L.p0x : L.n0x;
+			const float cy = pl.y < 0.0f ? L.p0y : L.n0y;
+			const float cz = pl.z < 0.0f ? L.p0z : L.n0z;
+			const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
+			const double d1 = dotd((double)L.sx, (double)L.sy, (double)L.sz, pl.x, pl.y, pl.z) - dist;
+			const double d2 = dotd((double)L.ex, (double)L.ey, (double)L.ez, pl.x, pl.y, pl.z) - dist;
+			if (!clipSide<COUNT>(L, d1, d2, L.side)) {
+				mode = M_LEAF;                               // wholly in front of one face
+			} else if (++L.side >= L.sideEnd) {
+				finishBrush(m, q, L);
+				mode = (L.fraction == 0.0f) ? M_FINISH : M_LEAF;
+			}
+		}
+
+		// ---------------- one patch of CM_TraceThroughLeaf, cm_trace.c:405-426 (+ :241-254) -----------------
+		if (mode == M_PATCH) {
+			if (L.ps >= L.psEnd) {
+				mode = popSegment(L, stack);
+			} else {
+				const int p = __ldg(&m.surf2patch[__ldg(&m.leafsurfaces[L.ps])]);
+				L.ps++;
+				if (p >= 0) {
+					const int4 pa = __ldg(&m.patchInfo[2 * p]);
+					if (pa.y & L.mask) {
+						const float before = L.fraction;
+						sweepPatch<COUNT>(m, L, p);
+						if (L.fraction < before) {
+							L.surfaceFlags = pa.x;
+							L.contents = pa.y;
+							L.hitId = -2 - p;
+						}
+						if (L.fraction == 0.0f) mode = M_FINISH;
+					}
+				}
+			}
+		}
+
+		// ---------------- position test: CM_PositionTest / CM_BoxLeafnums_r, cm_trace.c:191-226, cm_test.c:131-156 -----
+		// The reference lists <= 1024 leafs, then tests them in list order; testing each leaf when it is
+		// discovered is the same sequence of tests.
+		if (mode == M_PNODE) {
+			if (L.num < 0) {
+				if (L.found >= kMaxPosLeafs) {
+					mode = M_FINISH;
+				} else {
+					L.found++;
+					enterLeaf(L, __ldg(&m.leafs[-1 - L.num]));
+					Cnt<COUNT>::add(L.cLeafs);
+					mode = M_PLEAF;
+				}
+			} else {
+				const int4 nd = __ldg(&m.nodes[L.num]);
+				Cnt<COUNT>::add(L.cNodes);
+				const int s = boxPlaneSide(m, L.num, nd, L.lox - 1.0f, L.loy - 1.0f, L.loz - 1.0f,
+				                           L.hix + 1.0f, L.hiy + 1.0f, L.hiz + 1.0f);
+				if (s == 1) {
+					L.num = nd.x;
+				} else if (s == 2) {
+					L.num = nd.y;
+				} else {
+					if (L.sp < kMaxDepth) stack[L.sp++].num = nd.y; else atomicOr(q.status, 1);
+					L.num = nd.x;
+				}
+			}
+		}
+
+		// ---------------- CM_TestInLeaf / CM_TestBoxInBrush, cm_trace.c:130-183, 83-123 -----------------
+		if (mode == M_PLEAF) {
+			if (L.k < L.kEnd) {
+				float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
+				float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
+				L.k++;
+				Cnt<COUNT>::add(L.cBrushRefs);
+				const int contents = __float_as_int(bmn.w);
+				if (contents & L.mask) {
+					const int b = __float_as_int(bmx.w);
+					const bool boxBrush = (L.flags & F_BOX) && b == m.boxBrush;
+					if (boxBrush && q.boxmins) {
+						const float *a = q.boxmins + 3 * (size_t)L.idx, *c = q.boxmaxs + 3 * (size_t)L.idx;
+						bmn.x = a[0]; bmn.y = a[1]; bmn.z = a[2];
+						bmx.x = c[0]; bmx.y = c[1]; bmx.z = c[2];
+					}
+					const int4 bi = __ldg(&m.brushInfo[b]);
+					if (bi.y > 0) {
+						Cnt<COUNT>::add(L.cBrushBounds);
+						if (!(L.lox > bmx.x || L.loy > bmx.y || L.loz > bmx.z || L.hix < bmn.x || L.hiy < bmn.y || L.hiz < bmn.z)) {
+							bool inside = true;
+							for (int s = 6; s < bi.y; s++) {
+								float4 pl = __ldg(&m.sidePlanes[bi.x + s]);
+								if (boxBrush) pl.w = boxSideDist(q, L.idx, s);
+								Cnt<COUNT>::add(L.cBrushSides);
+								const float cx = pl.x < 0.0f ? L.p0x : L.n0x;
+								const float cy = pl.y < 0.0f ? L.p0y : L.n0y;
+								const float cz = pl.z < 0.0f ? L.p0z : L.n0z;
+								const float distf = pl.w - dotf(cx, cy, cz, pl.x, pl.y, pl.z);    // all-float (cm_trace.c:111)
+								const double d1 = dotd((double)L.sx, (double)L.sy, (double)L.sz, pl.x, pl.y, pl.z) - (double)distf;
+								if (d1 > 0) { inside = false; break; }
+							}
+							if (inside) {
+								L.solid = 3;
+								L.fraction = 0;
+								L.contents = contents;
+								L.hitId = b;
+								mode = M_FINISH;
+							}
+						}
+					}
+				}
+			} else if (L.ps < L.psEnd && !m.noCurves) {
+				const int p = __ldg(&m.surf2patch[__ldg(&m.leafsurfaces[L.ps])]);
+				L.ps++;
+				if (p >= 0) {
+					const int4 pa = __ldg(&m.patchInfo[2 * p]);
+					if ((pa.y & L.mask) && boxInPatch<COUNT>(m, L, p)) {
+						L.solid = 3;
+						L.fraction = 0;
+						L.contents = pa.y;
+						L.hitId = -2 - p;
+						mode = M_FINISH;
+					}
+				}
+			} else if (L.sp == 0) {
+				mode = M_FINISH;
+			} else {
+				L.num = stack[--L.sp].num;
+				mode = M_PNODE;
+			}
+		}
+
+		// ---------------- write the result, free the lane -----------------
+		if (mode == M_FINISH) {
+			finishItem<COUNT>(q, L);
+			mode = M_FETCH;
+		}
 	}
 }
 
@@ -805,9 +914,9 @@ __global__ void __launch_bounds__(128) pointContentsKernel(const DevMap m, const
 	}
 	int contents = 0;
 	for (int k = 0; k < leaf.y; k++) {
-		const int b = __ldg(&m.leafbrushes[leaf.x + k]);
-		float4 bmn = __ldg(&m.brushBox[2 * b]);
-		float4 bmx = __ldg(&m.brushBox[2 * b + 1]);
+		float4 bmn = __ldg(&m.leafBrushBox[2 * (leaf.x + k)]);
+		float4 bmx = __ldg(&m.leafBrushBox[2 * (leaf.x + k) + 1]);
+		const int b = __float_as_int(bmx.w);
 		const bool boxBrush = isBox && b == m.boxBrush;
 		if (boxBrush) {
 			bmn.x = bmnx; bmn.y = bmny; bmn.z = bmnz;
@@ -816,18 +925,17 @@ __global__ void __launch_bounds__(128) pointContentsKernel(const DevMap m, const
 		// CM_BoundsIntersectPoint, cm_test.c:502-515
 		if (bmx.x < px - kBoundsEps || bmx.y < py - kBoundsEps || bmx.z < pz - kBoundsEps ||
 		    bmn.x > px + kBoundsEps || bmn.y > py + kBoundsEps || bmn.z > pz + kBoundsEps) continue;
-		const int firstSide = __float_as_int(bmx.w);
-		const int nsides = __ldg(&m.brushNumSides[b]);
+		const int4 bi = __ldg(&m.brushInfo[b]);
 		int s;
-		for (s = 0; s < nsides; s++) {
-			float4 pl = __ldg(&m.sidePlanes[firstSide + s]);
+		for (s = 0; s < bi.y; s++) {
+			float4 pl = __ldg(&m.sidePlanes[bi.x + s]);
 			if (boxBrush) {
 				const int axis = s >> 1;
 				pl.w = (s & 1) ? -sel3(bmnx, bmny, bmnz, axis) : sel3(bmxx, bmxy, bmxz, axis);
 			}
 			if (dotf(px, py, pz, pl.x, pl.y, pl.z) > pl.w) break;
 		}
-		if (s == nsides) contents |= __float_as_int(bmn.w);
+		if (s == bi.y) contents |= __float_as_int(bmn.w);
 	}
 	q.out[i] = contents;
 }

@@ -356,11 +356,12 @@ class Engine:
                                                    None, _p(m), 0, None, None, out_ptr, None))
 
     # ---- device-pointer calls (torch tensors on this GPU) -----------------------
-    def box_trace_device(self, starts, ends, mins, maxs, masks, out, models=None, origins=None, rotations=None,
+    def box_trace_device(self, starts, ends, mins, maxs, mask, out, models=None, origins=None, rotations=None,
                          rot_index=None, boxmins=None, boxmaxs=None, hit_ids=None, stream=None):
-        """cmgpu_box_trace_batch_device: every argument is a CUDA tensor (or None); only enqueues work.
+        """cmgpu_box_trace_batch_device: per-item arguments are CUDA tensors; only enqueues work.
 
-        starts/ends float32 [n,3]; mins/maxs float32 [3] (shared) or [n,3]; masks int32 [1] or [n];
+        starts/ends float32 [n,3] CUDA tensors.  mins/maxs: a shared hull as 3 host floats (numpy / list /
+        None) or per-item CUDA tensors [n,3].  mask: a shared int or a per-item int32 CUDA tensor [n].
         out uint8 [n,56].  Uses torch's current stream unless `stream` (a cudaStream_t int) is given.
         """
         import torch
@@ -368,10 +369,25 @@ class Engine:
         if stream is None:
             stream = torch.cuda.current_stream(starts.device).cuda_stream
         ptr = lambda t: None if t is None else t.data_ptr()
-        hs = 0 if (mins is None or mins.dim() == 1) else 1
-        ms = 0 if masks.numel() == 1 else 1
+        keep = []
+        if mins is None or not isinstance(mins, torch.Tensor):
+            hs = 0
+            pmins = pmaxs = None
+            if mins is not None:
+                hm, hx = _f(mins).reshape(3), _f(maxs).reshape(3)
+                keep += [hm, hx]
+                pmins, pmaxs = hm.ctypes.data, hx.ctypes.data
+        else:
+            hs = 1
+            pmins, pmaxs = mins.data_ptr(), maxs.data_ptr()
+        if isinstance(mask, torch.Tensor):
+            ms, pmask = 1, mask.data_ptr()
+        else:
+            hmask = np.array([int(mask)], dtype=np.int64).astype(np.int32)
+            keep.append(hmask)
+            ms, pmask = 0, hmask.ctypes.data
         self._check(self.lib.cmgpu_box_trace_batch_device(
-            self.h, n, ptr(starts), ptr(ends), ptr(mins), ptr(maxs), hs, ptr(models), ptr(masks), ms,
+            self.h, n, ptr(starts), ptr(ends), pmins, pmaxs, hs, ptr(models), pmask, ms,
             ptr(origins), ptr(rotations), ptr(rot_index), ptr(boxmins), ptr(boxmaxs), ptr(out), ptr(hit_ids),
             C.c_void_p(stream)))
 
