@@ -164,25 +164,31 @@ __device__ __forceinline__ float boxSideDist(const TraceBatch &q, int idx, int s
 	return q.boxmaxs[3 * (size_t)idx + axis];
 }
 
-// one brush side against the sweep: the body of the loop in CM_TraceThroughBrush, cm_trace.c:291-332.
-// returns false when the sweep is wholly in front of this face (the brush is missed).
+// One brush side against the sweep: the body of the loop in CM_TraceThroughBrush, cm_trace.c:291-332,
+// split in two branch-free halves so that all lanes of a warp stay together.
+//   classifySide: start/end-outside flags and the "wholly in front of this face" early-out.  The reference
+//                 returns at the first such face; OR-ing the condition over all faces and discarding the
+//                 brush afterwards is the same result, because nothing is kept from a discarded brush.
+//   crossSide:    the enter/leave fraction of a face the sweep crosses; faces it does not cross are
+//                 divided by 1 and ignored, so every lane issues the same instructions.
+__device__ __forceinline__ bool classifySide(int &flags, const double d1, const double d2) {
+	if (d2 > 0) flags |= F_ENDOUT;
+	if (d1 > 0) flags |= F_STARTOUT;
+	return d1 > 0 && (d2 >= kClipEps || d2 >= d1);
+}
+
 template <bool COUNT>
-__device__ __forceinline__ bool clipSide(Lane &L, const double d1, const double d2, const int side) {
-	if (d2 > 0) L.flags |= F_ENDOUT;
-	if (d1 > 0) L.flags |= F_STARTOUT;
-	if (d1 > 0 && (d2 >= kClipEps || d2 >= d1)) return false;
-	if (d1 <= 0 && d2 <= 0) return true;
-	Cnt<COUNT>::add(L.cCross);
-	if (d1 > d2) {
-		float f = (float)((d1 - kClipEps) / (d1 - d2));
-		if (f < 0) f = 0;
-		if (f > L.enter) { L.enter = f; L.lead = side; }
-	} else {
-		float f = (float)((d1 + kClipEps) / (d1 - d2));
-		if (f > 1) f = 1;
-		if (f < L.leave) L.leave = f;
-	}
-	return true;
+__device__ __forceinline__ void crossSide(Lane &L, const double d1, const double d2, const int side) {
+	const bool cross = !(d1 <= 0 && d2 <= 0);
+	const bool entering = d1 > d2;
+	const double num = entering ? d1 - kClipEps : d1 + kClipEps;
+	const double den = cross ? d1 - d2 : 1.0;
+	const float q = (float)(num / den);
+	if (COUNT) L.cCross += cross ? 1u : 0u;
+	const float fe = q < 0 ? 0.0f : q;          // enter: clamp below
+	const float fl = q > 1 ? 1.0f : q;          // leave: clamp above
+	if (cross && entering && fe > L.enter) { L.enter = fe; L.lead = side; }
+	if (cross && !entering && fl < L.leave) L.leave = fl;
 }
 
 // the tail of CM_TraceThroughBrush, cm_trace.c:338-362
@@ -694,20 +700,28 @@ __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const Trac
 								// (DotProductDP with a unit normal is exactly +-component)
 								const double sx = L.sx, sy = L.sy, sz = L.sz, ex = L.ex, ey = L.ey, ez = L.ez;
 								Cnt<COUNT>::add(L.cBrushSides, 6);
-								{
-									const double dn = (double)L.p0x - (double)bmn.x, dp = (double)bmx.x - (double)L.n0x;
-									alive = clipSide<COUNT>(L, -sx - dn, -ex - dn, 0);
-									if (alive) alive = clipSide<COUNT>(L, sx - dp, ex - dp, 1);
-								}
+								const double dnx = (double)L.p0x - (double)bmn.x, dpx = (double)bmx.x - (double)L.n0x;
+								const double dny = (double)L.p0y - (double)bmn.y, dpy = (double)bmx.y - (double)L.n0y;
+								const double dnz = (double)L.p0z - (double)bmn.z, dpz = (double)bmx.z - (double)L.n0z;
+								const double a0 = -sx - dnx, b0 = -ex - dnx, a1 = sx - dpx, b1 = ex - dpx;
+								const double a2 = -sy - dny, b2 = -ey - dny, a3 = sy - dpy, b3 = ey - dpy;
+								const double a4 = -sz - dnz, b4 = -ez - dnz, a5 = sz - dpz, b5 = ez - dpz;
+								int fl = L.flags;
+								bool miss = classifySide(fl, a0, b0);
+								miss |= classifySide(fl, a1, b1);
+								miss |= classifySide(fl, a2, b2);
+								miss |= classifySide(fl, a3, b3);
+								miss |= classifySide(fl, a4, b4);
+								miss |= classifySide(fl, a5, b5);
+								L.flags = fl;
+								alive = !miss;
 								if (alive) {
-									const double dn = (double)L.p0y - (double)bmn.y, dp = (double)bmx.y - (double)L.n0y;
-									alive = clipSide<COUNT>(L, -sy - dn, -ey - dn, 2);
-									if (alive) alive = clipSide<COUNT>(L, sy - dp, ey - dp, 3);
-								}
-								if (alive) {
-									const double dn = (double)L.p0z - (double)bmn.z, dp = (double)bmx.z - (double)L.n0z;
-									alive = clipSide<COUNT>(L, -sz - dn, -ez - dn, 4);
-									if (alive) alive = clipSide<COUNT>(L, sz - dp, ez - dp, 5);
+									crossSide<COUNT>(L, a0, b0, 0);
+									crossSide<COUNT>(L, a1, b1, 1);
+									crossSide<COUNT>(L, a2, b2, 2);
+									crossSide<COUNT>(L, a3, b3, 3);
+									crossSide<COUNT>(L, a4, b4, 4);
+									crossSide<COUNT>(L, a5, b5, 5);
 								}
 								L.side = 6;
 							}
@@ -737,9 +751,12 @@ __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const Trac
 			const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
 			const double d1 = dotd((double)L.sx, (double)L.sy, (double)L.sz, pl.x, pl.y, pl.z) - dist;
 			const double d2 = dotd((double)L.ex, (double)L.ey, (double)L.ez, pl.x, pl.y, pl.z) - dist;
-			if (!clipSide<COUNT>(L, d1, d2, L.side)) {
+			if (classifySide(L.flags, d1, d2)) {
 				mode = M_LEAF;                               // wholly in front of one face
-			} else if (++L.side >= L.sideEnd) {
+			} else {
+				crossSide<COUNT>(L, d1, d2, L.side);
+			}
+			if (mode == M_SIDE && ++L.side >= L.sideEnd) {
 				finishBrush(m, q, L);
 				mode = (L.fraction == 0.0f) ? M_FINISH : M_LEAF;
 			}
