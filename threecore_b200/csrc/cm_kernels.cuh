@@ -32,6 +32,7 @@ namespace cmgpu {
 
 constexpr int    kBlock          = 128;     // threads per CTA of the trace kernel
 constexpr int    kChunk          = 256;     // items a warp takes from the global cursor at a time
+constexpr int    kGang           = 4;       // lanes that must gather before a heavy block runs
 constexpr int    kMaxDepth       = 64;      // traversal stack entries per item (CMGPU_ERR_LIMIT beyond)
 constexpr int    kMaxPosLeafs    = 1024;    // MAX_POSITION_LEAFS, cm_trace.c:190
 constexpr int    kBoxModelHandle = 1023;    // BOX_MODEL_HANDLE, cm_local.h:28
@@ -85,6 +86,7 @@ struct TraceBatch {
 	int *hitIds;                         // may be null
 	int *status;                         // device status word
 	int *cursor;                         // work cursor, zero at launch
+	int gang;                            // lanes that must gather before a heavy block runs
 	Counters *counters;                  // only touched by the counting variant
 };
 
@@ -99,7 +101,7 @@ struct PointBatch {
 	int *out;
 };
 
-enum Mode : int { M_FETCH = 0, M_NODE, M_LEAF, M_SIDE, M_PATCH, M_PNODE, M_PLEAF, M_FINISH };
+enum Mode : int { M_FETCH = 0, M_NODE, M_SPLIT, M_LEAF, M_BRUSH, M_SIDE, M_PATCH, M_PNODE, M_PLEAF, M_FINISH };
 
 // ---- per-lane working set (registers) -----------------------------------------------------
 struct Lane {
@@ -562,6 +564,14 @@ __device__ __forceinline__ void finishItem(const TraceBatch &q, Lane &L) {
 // =====================================================================================
 // the trace kernel
 // =====================================================================================
+//
+// Scheduling.  A lane is always in exactly one Mode.  "Light" modes (M_NODE without a split,
+// M_LEAF) are a few dozen instructions and run every iteration.  "Heavy" modes (item fetch,
+// segment split, brush clip, general side, finish) cost hundreds of instructions, so a lane
+// that reaches one PARKS there and the block only runs once a gang of lanes has gathered
+// (>= kGang, or at least as many as there are lanes still doing light work, or nothing else
+// can make progress).  Running the expensive blocks with a full gang instead of whichever
+// one or two lanes happen to need them is what keeps the warp's lanes busy.
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const TraceBatch q) {
 	const unsigned lane = threadIdx.x & 31u;
@@ -573,28 +583,52 @@ __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const Trac
 	bool supply = true;                   // warp-uniform: the global cursor may still have items
 
 	for (;;) {
-		// ---------------- fetch: all lanes arrive here together --------------------------
-		const unsigned need = __ballot_sync(0xffffffffu, mode == M_FETCH);
-		if (need) {
-			if (chunkNext >= chunkEnd && supply) {
-				int base = 0;
-				if (lane == 0) base = atomicAdd(q.cursor, kChunk);
-				base = __shfl_sync(0xffffffffu, base, 0);
-				if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
-				else { chunkNext = base; chunkEnd = min(base + kChunk, q.n); }
-			}
-			if (chunkNext >= chunkEnd) {
-				if (need == 0xffffffffu) break;           // nothing in flight, nothing left
-			} else {
-				if (mode == M_FETCH) {
-					const int my = chunkNext + __popc(need & laneLt);
-					if (my < chunkEnd) mode = beginItem(m, q, L, my);
-				}
-				chunkNext = min(chunkNext + __popc(need), chunkEnd);
+		// ---------------- census of parked lanes: one REDUX, 6-bit counters ------------------
+		unsigned key = 0u;
+		if (mode == M_FETCH) key = 1u;
+		else if (mode == M_SPLIT) key = 1u << 6;
+		else if (mode == M_BRUSH) key = 1u << 12;
+		else if (mode == M_SIDE) key = 1u << 18;
+		else if (mode == M_FINISH) key = 1u << 24;
+		const unsigned census = __reduce_add_sync(0xffffffffu, key);
+		const int nFetch = census & 63, nSplit = (census >> 6) & 63, nBrush = (census >> 12) & 63;
+		const int nSide = (census >> 18) & 63, nFinish = (census >> 24) & 63;
+		const int nLight = 32 - (nFetch + nSplit + nBrush + nSide + nFinish);
+		const int gang = min(q.gang, nLight);          // 0 when only parked lanes are left: run everything
+
+		// ---------------- write results, free lanes -----------------
+		if (nFinish > 0 && nFinish >= gang) {
+			if (mode == M_FINISH) {
+				finishItem<COUNT>(q, L);
+				mode = M_FETCH;
 			}
 		}
 
-		// ---------------- one node of CM_TraceThroughTree, cm_trace.c:439-538 -----------------
+		// ---------------- fetch: hand out new items to idle lanes --------------------------
+		{
+			const unsigned need = __ballot_sync(0xffffffffu, mode == M_FETCH);
+			const int nNeed = __popc(need);
+			if (nNeed > 0 && nNeed >= min(q.gang, 32 - nNeed)) {
+				if (chunkNext >= chunkEnd && supply) {
+					int base = 0;
+					if (lane == 0) base = atomicAdd(q.cursor, kChunk);
+					base = __shfl_sync(0xffffffffu, base, 0);
+					if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
+					else { chunkNext = base; chunkEnd = min(base + kChunk, q.n); }
+				}
+				if (chunkNext >= chunkEnd) {
+					if (need == 0xffffffffu) break;           // nothing in flight, nothing left
+				} else {
+					if (mode == M_FETCH) {
+						const int my = chunkNext + __popc(need & laneLt);
+						if (my < chunkEnd) mode = beginItem(m, q, L, my);
+					}
+					chunkNext = min(chunkNext + nNeed, chunkEnd);
+				}
+			}
+		}
+
+		// ---------------- one node of CM_TraceThroughTree, cm_trace.c:439-486 (light) -----------------
 		if (mode == M_NODE) {
 			if (L.fraction <= L.f1) {
 				mode = popSegment(L, stack);                  // already hit something nearer
@@ -622,143 +656,174 @@ __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const Trac
 				} else if (t1 < -off - 1 && t2 < -off - 1) {
 					L.num = nd.y;
 				} else {
-					int side;
-					float fnear, ffar;
-					if (t1 < t2) {
-						const float inv = (float)(1.0 / (t1 - t2));
-						side = 1;
-						ffar = (float)((t1 + off + kClipEps) * (double)inv);
-						fnear = (float)((t1 - off + kClipEps) * (double)inv);
-					} else if (t1 > t2) {
-						const float inv = (float)(1.0 / (t1 - t2));
-						side = 0;
-						ffar = (float)((t1 - off - kClipEps) * (double)inv);
-						fnear = (float)((t1 + off + kClipEps) * (double)inv);
-					} else {
-						side = 0;
-						fnear = 1.0f;
-						ffar = 0.0f;
-					}
-					if (fnear < 0) fnear = 0; else if (fnear > 1) fnear = 1;
-					if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
-					Cnt<COUNT>::add(L.cSplits);
-					// the far half [mid(ffar), b] waits on the stack; the near half [a, mid(fnear)] goes on.
-					// split points are computed from the CURRENT segment in float and carried.
-					Seg far;
-					far.num = side ? nd.x : nd.y;
-					far.f1 = L.f1 + (L.f2 - L.f1) * ffar;
-					far.f2 = L.f2;
-					far.ax = L.ax + ffar * (L.bx - L.ax);
-					far.ay = L.ay + ffar * (L.by - L.ay);
-					far.az = L.az + ffar * (L.bz - L.az);
-					far.bx = L.bx; far.by = L.by; far.bz = L.bz;
-					const float midf = L.f1 + (L.f2 - L.f1) * fnear;
-					const float mx = L.ax + fnear * (L.bx - L.ax);
-					const float my = L.ay + fnear * (L.by - L.ay);
-					const float mz = L.az + fnear * (L.bz - L.az);
-					if (L.sp < kMaxDepth) stack[L.sp++] = far; else atomicOr(q.status, 1);
-					L.num = side ? nd.y : nd.x;
-					L.f2 = midf;
-					L.bx = mx; L.by = my; L.bz = mz;
+					mode = M_SPLIT;                               // park: the split is done by a gang
 				}
 			}
 		}
 
-		// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-399 -----------------
+		// ---------------- split a segment at a node, cm_trace.c:492-537 (heavy) -----------------
+		if (nSplit > 0 && nSplit >= gang) {
+			if (mode == M_SPLIT) {
+				const int4 nd = __ldg(&m.nodes[L.num]);
+				double t1, t2, off;
+				if (nd.z < 3) {
+					const float dist = __int_as_float(nd.w);
+					t1 = (double)(sel3(L.ax, L.ay, L.az, nd.z) - dist);
+					t2 = (double)(sel3(L.bx, L.by, L.bz, nd.z) - dist);
+					off = (L.flags & F_POINT) ? 0.0 : (double)sel3(L.p0x, L.p0y, L.p0z, nd.z);
+				} else {
+					const float4 pl = __ldg(&m.nodePlanes[L.num]);
+					t1 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.ax, L.ay, L.az) - (double)pl.w;
+					t2 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.bx, L.by, L.bz) - (double)pl.w;
+					off = (L.flags & F_POINT) ? 0.0 : 2048.0;
+				}
+				// branch-free form of the three cases t1<t2, t1>t2, t1==t2
+				const bool fwd = t1 < t2, eq = !(t1 < t2) && !(t1 > t2);
+				const float inv = (float)(1.0 / (eq ? 1.0 : (t1 - t2)));
+				const int side = fwd ? 1 : 0;
+				const double nfar = fwd ? (t1 + off + kClipEps) : (t1 - off - kClipEps);
+				const double nnear = fwd ? (t1 - off + kClipEps) : (t1 + off + kClipEps);
+				float ffar = (float)(nfar * (double)inv);
+				float fnear = (float)(nnear * (double)inv);
+				if (eq) { fnear = 1.0f; ffar = 0.0f; }
+				if (fnear < 0) fnear = 0; else if (fnear > 1) fnear = 1;
+				if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
+				Cnt<COUNT>::add(L.cSplits);
+				// the far half [mid(ffar), b] waits on the stack; the near half [a, mid(fnear)] goes on.
+				// split points are computed from the CURRENT segment in float and carried.
+				Seg far;
+				far.num = side ? nd.x : nd.y;
+				far.f1 = L.f1 + (L.f2 - L.f1) * ffar;
+				far.f2 = L.f2;
+				far.ax = L.ax + ffar * (L.bx - L.ax);
+				far.ay = L.ay + ffar * (L.by - L.ay);
+				far.az = L.az + ffar * (L.bz - L.az);
+				far.bx = L.bx; far.by = L.by; far.bz = L.bz;
+				const float midf = L.f1 + (L.f2 - L.f1) * fnear;
+				const float mx = L.ax + fnear * (L.bx - L.ax);
+				const float my = L.ay + fnear * (L.by - L.ay);
+				const float mz = L.az + fnear * (L.bz - L.az);
+				if (L.sp < kMaxDepth) stack[L.sp++] = far; else atomicOr(q.status, 1);
+				L.num = side ? nd.y : nd.x;
+				L.f2 = midf;
+				L.bx = mx; L.by = my; L.bz = mz;
+				mode = M_NODE;
+			}
+		}
+
+		// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393 (light) -----------------
 		if (mode == M_LEAF) {
 			if (L.k >= L.kEnd) {
 				mode = (L.ps < L.psEnd && !m.noCurves) ? M_PATCH : popSegment(L, stack);
 			} else {
-				float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
-				float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
+				const float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
+				const float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
 				L.k++;
 				Cnt<COUNT>::add(L.cBrushRefs);
+				if (__float_as_int(bmn.w) & L.mask) {
+					Cnt<COUNT>::add(L.cBrushBounds);
+					if ((L.flags & F_BOX) && __float_as_int(bmx.w) == m.boxBrush) {
+						mode = M_BRUSH;                           // temp box: bounds come from the item
+					} else if (!(L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
+					             L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps)) {
+						mode = M_BRUSH;                           // CM_BoundsIntersect passed (cm_test.c:481-494): park
+					}
+				}
+			}
+		}
+
+		// ---------------- clip against the brush at entry k-1: CM_TraceThroughBrush, cm_trace.c:261-363 (heavy) -----
+		if (nBrush > 0 && nBrush >= gang) {
+			if (mode == M_BRUSH) {
+				float4 bmn = __ldg(&m.leafBrushBox[2 * (L.k - 1)]);
+				float4 bmx = __ldg(&m.leafBrushBox[2 * (L.k - 1) + 1]);
 				const int contents = __float_as_int(bmn.w);
-				if (contents & L.mask) {
-					const int b = __float_as_int(bmx.w);
-					const bool boxBrush = (L.flags & F_BOX) && b == m.boxBrush;
-					if (boxBrush && q.boxmins) {
+				const int b = __float_as_int(bmx.w);
+				const bool boxBrush = (L.flags & F_BOX) && b == m.boxBrush;
+				bool overlap = true;
+				if (boxBrush) {
+					if (q.boxmins) {
 						const float *a = q.boxmins + 3 * (size_t)L.idx, *c = q.boxmaxs + 3 * (size_t)L.idx;
 						bmn.x = a[0]; bmn.y = a[1]; bmn.z = a[2];
 						bmx.x = c[0]; bmx.y = c[1]; bmx.z = c[2];
 					}
-					Cnt<COUNT>::add(L.cBrushBounds);
-					// CM_BoundsIntersect, cm_test.c:481-494
-					if (!(L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
-					      L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps)) {
-						const int4 bi = __ldg(&m.brushInfo[b]);
-						if (bi.y > 0) {
-							L.brush = b; L.firstSide = bi.x; L.sideEnd = bi.y; L.bcontents = contents;
-							L.enter = -1.0f; L.leave = 1.0f; L.lead = -1;
-							L.flags = (L.flags & ~(F_STARTOUT | F_ENDOUT | F_BOXBRUSH)) | (boxBrush ? F_BOXBRUSH : 0);
-							L.side = 0;
-							bool alive = true;
-							if (bi.w) {
-								// the six axial sides straight from the box already in registers:
-								// side 2a   : normal -e_a, dist -mins[a], corner component size[1][a]
-								// side 2a+1 : normal +e_a, dist  maxs[a], corner component size[0][a]
-								// (DotProductDP with a unit normal is exactly +-component)
-								const double sx = L.sx, sy = L.sy, sz = L.sz, ex = L.ex, ey = L.ey, ez = L.ez;
-								Cnt<COUNT>::add(L.cBrushSides, 6);
-								const double dnx = (double)L.p0x - (double)bmn.x, dpx = (double)bmx.x - (double)L.n0x;
-								const double dny = (double)L.p0y - (double)bmn.y, dpy = (double)bmx.y - (double)L.n0y;
-								const double dnz = (double)L.p0z - (double)bmn.z, dpz = (double)bmx.z - (double)L.n0z;
-								const double a0 = -sx - dnx, b0 = -ex - dnx, a1 = sx - dpx, b1 = ex - dpx;
-								const double a2 = -sy - dny, b2 = -ey - dny, a3 = sy - dpy, b3 = ey - dpy;
-								const double a4 = -sz - dnz, b4 = -ez - dnz, a5 = sz - dpz, b5 = ez - dpz;
-								int fl = L.flags;
-								bool miss = classifySide(fl, a0, b0);
-								miss |= classifySide(fl, a1, b1);
-								miss |= classifySide(fl, a2, b2);
-								miss |= classifySide(fl, a3, b3);
-								miss |= classifySide(fl, a4, b4);
-								miss |= classifySide(fl, a5, b5);
-								L.flags = fl;
-								alive = !miss;
-								if (alive) {
-									crossSide<COUNT>(L, a0, b0, 0);
-									crossSide<COUNT>(L, a1, b1, 1);
-									crossSide<COUNT>(L, a2, b2, 2);
-									crossSide<COUNT>(L, a3, b3, 3);
-									crossSide<COUNT>(L, a4, b4, 4);
-									crossSide<COUNT>(L, a5, b5, 5);
-								}
-								L.side = 6;
-							}
-							if (alive) {
-								if (L.side < L.sideEnd) {
-									mode = M_SIDE;
-								} else {
-									finishBrush(m, q, L);
-									if (L.fraction == 0.0f) mode = M_FINISH;
-								}
-							}
+					overlap = !(L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
+					            L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps);
+				}
+				const int4 bi = __ldg(&m.brushInfo[b]);
+				mode = M_LEAF;
+				if (overlap && bi.y > 0) {
+					L.brush = b; L.firstSide = bi.x; L.sideEnd = bi.y; L.bcontents = contents;
+					L.enter = -1.0f; L.leave = 1.0f; L.lead = -1;
+					L.flags = (L.flags & ~(F_STARTOUT | F_ENDOUT | F_BOXBRUSH)) | (boxBrush ? F_BOXBRUSH : 0);
+					L.side = 0;
+					bool alive = true;
+					if (bi.w) {
+						// the six axial sides straight from the box:
+						// side 2a   : normal -e_a, dist -mins[a], corner component size[1][a]
+						// side 2a+1 : normal +e_a, dist  maxs[a], corner component size[0][a]
+						// (DotProductDP with a unit normal is exactly +-component)
+						const double sx = L.sx, sy = L.sy, sz = L.sz, ex = L.ex, ey = L.ey, ez = L.ez;
+						Cnt<COUNT>::add(L.cBrushSides, 6);
+						const double dnx = (double)L.p0x - (double)bmn.x, dpx = (double)bmx.x - (double)L.n0x;
+						const double dny = (double)L.p0y - (double)bmn.y, dpy = (double)bmx.y - (double)L.n0y;
+						const double dnz = (double)L.p0z - (double)bmn.z, dpz = (double)bmx.z - (double)L.n0z;
+						const double a0 = -sx - dnx, b0 = -ex - dnx, a1 = sx - dpx, b1 = ex - dpx;
+						const double a2 = -sy - dny, b2 = -ey - dny, a3 = sy - dpy, b3 = ey - dpy;
+						const double a4 = -sz - dnz, b4 = -ez - dnz, a5 = sz - dpz, b5 = ez - dpz;
+						int fl = L.flags;
+						bool miss = classifySide(fl, a0, b0);
+						miss |= classifySide(fl, a1, b1);
+						miss |= classifySide(fl, a2, b2);
+						miss |= classifySide(fl, a3, b3);
+						miss |= classifySide(fl, a4, b4);
+						miss |= classifySide(fl, a5, b5);
+						L.flags = fl;
+						alive = !miss;
+						if (alive) {
+							crossSide<COUNT>(L, a0, b0, 0);
+							crossSide<COUNT>(L, a1, b1, 1);
+							crossSide<COUNT>(L, a2, b2, 2);
+							crossSide<COUNT>(L, a3, b3, 3);
+							crossSide<COUNT>(L, a4, b4, 4);
+							crossSide<COUNT>(L, a5, b5, 5);
+						}
+						L.side = 6;
+					}
+					if (alive) {
+						if (L.side < L.sideEnd) {
+							mode = M_SIDE;
+						} else {
+							finishBrush(m, q, L);
+							if (L.fraction == 0.0f) mode = M_FINISH;
 						}
 					}
 				}
 			}
 		}
 
-		// ---------------- one general side of CM_TraceThroughBrush, cm_trace.c:291-332 -----------------
-		if (mode == M_SIDE) {
-			float4 pl = __ldg(&m.sidePlanes[L.firstSide + L.side]);
-			if (L.flags & F_BOXBRUSH) pl.w = boxSideDist(q, L.idx, L.side);
-			Cnt<COUNT>::add(L.cBrushSides);
-			// tw.offsets[signbits]: the box corner that touches the plane first
-			const float cx = pl.x < 0.0f ? L.p0x : L.n0x;
-			const float cy = pl.y < 0.0f ? L.p0y : L.n0y;
-			const float cz = pl.z < 0.0f ? L.p0z : L.n0z;
-			const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
-			const double d1 = dotd((double)L.sx, (double)L.sy, (double)L.sz, pl.x, pl.y, pl.z) - dist;
-			const double d2 = dotd((double)L.ex, (double)L.ey, (double)L.ez, pl.x, pl.y, pl.z) - dist;
-			if (classifySide(L.flags, d1, d2)) {
-				mode = M_LEAF;                               // wholly in front of one face
-			} else {
-				crossSide<COUNT>(L, d1, d2, L.side);
-			}
-			if (mode == M_SIDE && ++L.side >= L.sideEnd) {
-				finishBrush(m, q, L);
-				mode = (L.fraction == 0.0f) ? M_FINISH : M_LEAF;
+		// ---------------- one general side of CM_TraceThroughBrush, cm_trace.c:291-332 (heavy) -----------------
+		if (nSide > 0 && nSide >= gang) {
+			if (mode == M_SIDE) {
+				float4 pl = __ldg(&m.sidePlanes[L.firstSide + L.side]);
+				if (L.flags & F_BOXBRUSH) pl.w = boxSideDist(q, L.idx, L.side);
+				Cnt<COUNT>::add(L.cBrushSides);
+				// tw.offsets[signbits]: the box corner that touches the plane first
+				const float cx = pl.x < 0.0f ? L.p0x : L.n0x;
+				const float cy = pl.y < 0.0f ? L.p0y : L.n0y;
+				const float cz = pl.z < 0.0f ? L.p0z : L.n0z;
+				const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
+				const double d1 = dotd((double)L.sx, (double)L.sy, (double)L.sz, pl.x, pl.y, pl.z) - dist;
+				const double d2 = dotd((double)L.ex, (double)L.ey, (double)L.ez, pl.x, pl.y, pl.z) - dist;
+				if (classifySide(L.flags, d1, d2)) {
+					mode = M_LEAF;                               // wholly in front of one face
+				} else {
+					crossSide<COUNT>(L, d1, d2, L.side);
+					if (++L.side >= L.sideEnd) {
+						finishBrush(m, q, L);
+						mode = (L.fraction == 0.0f) ? M_FINISH : M_LEAF;
+					}
+				}
 			}
 		}
 
@@ -875,12 +940,6 @@ __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const Trac
 				L.num = stack[--L.sp].num;
 				mode = M_PNODE;
 			}
-		}
-
-		// ---------------- write the result, free the lane -----------------
-		if (mode == M_FINISH) {
-			finishItem<COUNT>(q, L);
-			mode = M_FETCH;
 		}
 	}
 }
