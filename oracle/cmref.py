@@ -86,7 +86,7 @@ class RefCM:
         assert m.shape == (n,)
         return _i(m), 1
 
-    def box_trace(self, starts, ends, mins=None, maxs=None, model=0, mask=1):
+    def box_trace(self, starts, ends, mins=None, maxs=None, model=0, mask=1, boxmins=None, boxmaxs=None):
         starts, ends = _f(starts), _f(ends)
         n = starts.shape[0]
         mins, maxs, hs = self._hull(n, mins, maxs)
@@ -95,8 +95,11 @@ class RefCM:
         if not np.isscalar(model) or model != 0:
             models = _i(np.broadcast_to(_i(model), (n,)))
         out = np.zeros(n, dtype=TRACE_DTYPE)
+        boxmins = _f(boxmins) if boxmins is not None else None
+        boxmaxs = _f(boxmaxs) if boxmaxs is not None else None
         self._check(self.lib.cmref_box_trace_batch(n, _p(starts), _p(ends), _p(mins), _p(maxs), hs,
-                                                   _p(models), _p(m), ms, _p(out)), "CM_BoxTrace")
+                                                   _p(models), _p(m), ms, _p(boxmins), _p(boxmaxs), _p(out)),
+                    "CM_BoxTrace")
         return out
 
     def transformed_box_trace(self, starts, ends, mins, maxs, models, mask, origins, angles,

@@ -199,13 +199,17 @@ API int cmref_num_inline_models(void) { return CM_NumInlineModels(); }
 API int cmref_box_trace_batch(int n, const float *starts, const float *ends,
                               const float *mins, const float *maxs, int hull_stride,
                               const int *models, const int *masks, int mask_stride,
+                              const float *boxmins, const float *boxmaxs,
                               trace_t *out) {
 	GUARD_BEGIN();
 	for (int i = 0; i < n; i++) {
 		const float *mn = mins ? mins + 3 * (size_t)i * hull_stride : NULL;
 		const float *mx = maxs ? maxs + 3 * (size_t)i * hull_stride : NULL;
-		CM_BoxTrace(&out[i], starts + 3 * (size_t)i, ends + 3 * (size_t)i, mn, mx,
-		            models ? models[i] : 0, masks[(size_t)i * mask_stride]);
+		int h = models ? models[i] : 0;
+		if (h == BOX_MODEL_HANDLE && boxmins) {
+			h = CM_TempBoxModel(boxmins + 3 * (size_t)i, boxmaxs + 3 * (size_t)i);
+		}
+		CM_BoxTrace(&out[i], starts + 3 * (size_t)i, ends + 3 * (size_t)i, mn, mx, h, masks[(size_t)i * mask_stride]);
 	}
 	GUARD_END();
 	return 0;

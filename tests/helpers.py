@@ -63,3 +63,34 @@ def assert_traces_equal(got: np.ndarray, want: np.ndarray, what: str = ""):
         fields = [f for f in got.dtype.names if not np.array_equal(got[i][f], want[i][f])]
         raise AssertionError(f"{what}: {int(bad.sum())} of {len(got)} records differ; first at {i}, fields {fields}\n"
                              f" got  {got[i]}\n want {want[i]}")
+
+
+def flat_for(data: bytes, prefer_product: bool = False) -> dict:
+    """Flat dict for the oracle: from the reference's own loaded clipMap_t when the reference library
+    is available, otherwise from the product's host loader (which test_loader.py checks against it)."""
+    if have_ref() and not prefer_product:
+        return flat_from_ref(data)
+    from threecore_b200.engine import FlatMap
+    return FlatMap.from_bsp(data).to_dict()
+
+
+def load_golden(name: str):
+    """-> (bsp bytes, [(case dict, expected output)])"""
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    out = []
+    for i in range(int(z["num_cases"])):
+        c = {"name": str(z[f"c{i}_name"]), "kind": str(z[f"c{i}_kind"]), "mins": None, "maxs": None}
+        pre = f"c{i}_in_"
+        for k in z.files:
+            if k.startswith(pre):
+                v = z[k]
+                c[k[len(pre):]] = v if v.ndim else v.item()
+        want = z[f"c{i}_out"]
+        if want.dtype == np.uint8:
+            want = np.ascontiguousarray(want).view(cmref.TRACE_DTYPE).reshape(-1)
+        out.append((c, want))
+    return z["bsp"].tobytes(), out
+
+
+GOLDEN_SETS = ["tiny_world", "room_world", "models_world", "models_entities", "patches_world", "patches_entities"]
