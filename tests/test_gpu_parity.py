@@ -1,0 +1,232 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the oracle (and the golden vectors).
+
+Bar: byte-identical 56-byte trace_t records and identical contents words -- which implies the stated
+tolerance (classification bit-exact, fraction/endpos within 1e-5 relative) with room to spare."""
+import numpy as np
+import pytest
+
+import cases
+from helpers import (GOLDEN_SETS, assert_traces_equal, bspgen, cmoracle, flat_for, get_map, load_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from threecore_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+_loaded = {}
+
+
+def load(eng, kind):
+    """upload `kind` (cached flat dict for the oracle)"""
+    m = get_map(kind)
+    fm = eng.load_bsp(m.data)
+    if kind not in _loaded:
+        _loaded[kind] = cmoracle.OracleCM(fm.to_dict())
+    return m, _loaded[kind]
+
+
+def check(eng, oracle, case):
+    got = cases.run_case(eng, case)
+    want = cases.run_case(oracle, case)
+    if case["kind"] == "points":
+        assert np.array_equal(got, want), f"{case['name']}: {(got != want).sum()} contents words differ"
+    else:
+        assert_traces_equal(got, want, case["name"])
+    return want
+
+
+@pytest.mark.parametrize("kind", ["tiny", "room", "arena_small", "arena_models", "patches_small"])
+def test_world_traces(eng, kind):
+    m, o = load(eng, kind)
+    launches = eng.launch_count
+    for case in cases.world_cases(kind, n=60000):
+        check(eng, o, case)
+    assert eng.launch_count > launches, "no kernel launched: not the CUDA path"
+
+
+@pytest.mark.parametrize("kind", ["arena_models", "patches_small"])
+def test_entity_traces_and_point_contents(eng, kind):
+    m, o = load(eng, kind)
+    for case in cases.entity_cases(kind, n=60000):
+        check(eng, o, case)
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_golden_vectors(eng, name):
+    """fixtures produced by the unmodified reference (tests/golden/make_golden.py)"""
+    bsp, items = load_golden(name)
+    eng.load_bsp(bsp)
+    for case, want in items:
+        got = cases.run_case(eng, case)
+        if case["kind"] == "points":
+            assert np.array_equal(got, want), case["name"]
+        else:
+            assert_traces_equal(got, want, case["name"])
+
+
+def test_hit_ids_match_oracle(eng):
+    m, o = load(eng, "patches_small")
+    s, e, mins, maxs = bspgen.make_patch_sweeps(m, 50000, 5)
+    got, hit = eng.box_trace(s, e, mins, maxs, mask=bspgen.MASK_ALL, want_hit=True)
+    want, info = o.box_trace(s, e, mins, maxs, mask=bspgen.MASK_ALL, want_info=True)
+    assert_traces_equal(got, want, "patch sweeps")
+    want_hit = np.where(info["hitPatch"] >= 0, -2 - info["hitPatch"], info["hitBrush"])
+    assert np.array_equal(hit, want_hit)
+    assert (hit <= -2).mean() > 0.1, "patch hits are not being exercised"
+
+
+@pytest.mark.parametrize("cvars", [dict(noCurves=1, playerCurveClip=1), dict(noCurves=0, playerCurveClip=0)])
+def test_patch_cvars(eng, cvars):
+    m, _ = load(eng, "patches_small")
+    o = cmoracle.OracleCM(eng.map.to_dict(), **cvars)
+    eng.set_cvars(**cvars)
+    try:
+        s, e, mins, maxs = bspgen.make_patch_sweeps(m, 30000, 6)
+        got = eng.box_trace(s, e, mins, maxs, mask=bspgen.MASK_ALL)
+        want = o.box_trace(s, e, mins, maxs, mask=bspgen.MASK_ALL)
+        assert_traces_equal(got, want, f"cvars {cvars}")
+    finally:
+        eng.set_cvars(0, 1)
+
+
+def test_counters_match_oracle_visit_counts(eng):
+    """the instrumented kernel variant visits exactly what the oracle visits (drives the L2 roofline model)"""
+    m, o = load(eng, "arena_small")
+    s, e = bspgen.make_sweeps(m, 40000, 8)
+    eng.enable_counters(True)
+    try:
+        eng.read_counters(reset=True)
+        got = eng.box_trace(s, e, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID)
+        c = eng.read_counters()
+    finally:
+        eng.enable_counters(False)
+    want, info = o.box_trace(s, e, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID, want_info=True)
+    assert_traces_equal(got, want, "counting variant")
+    assert c["traces"] == len(s)
+    for k in ("nodes", "leafs", "brushRefs", "splits"):
+        assert c[k] == int(info[k].sum()), (k, c[k], int(info[k].sum()))
+
+
+def test_edge_batches(eng):
+    m, o = load(eng, "room")
+    # empty batch
+    out = eng.box_trace(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert out.shape == (0,)
+    # ragged sizes around the warp/chunk boundaries
+    s, e = bspgen.make_sweeps(m, 1025, 3)
+    for n in (1, 2, 31, 32, 33, 255, 256, 257, 1025):
+        got = eng.box_trace(s[:n], e[:n], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID)
+        want = o.box_trace(s[:n], e[:n], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID)
+        assert_traces_equal(got, want, f"n={n}")
+
+
+def test_error_codes(eng):
+    from threecore_b200.engine import CMGPUError, Engine
+    m, _ = load(eng, "arena_models")
+    s, e = bspgen.make_sweeps(m, 16, 1)
+    with pytest.raises(CMGPUError) as ex:
+        eng.box_trace(s, e, model=np.full(16, 999, np.int32))          # CM_ClipHandleToModel: bad handle
+    assert ex.value.code == 5
+    with pytest.raises(CMGPUError) as ex:
+        eng.box_trace(s, e, model=np.full(16, -1, np.int32))
+    assert ex.value.code == 5
+    e2 = Engine(0)
+    with pytest.raises(CMGPUError) as ex:
+        e2.box_trace(s, e)                                             # no map uploaded
+    assert ex.value.code == 4
+    e2.close()
+
+
+def test_deep_tree_reports_limit(eng):
+    """a degenerate BSP deeper than the traversal stack must be refused loudly, not traced wrongly"""
+    from threecore_b200.engine import CMGPUError, Engine
+    mb = bspgen.MapBuilder()
+    bspgen._room_walls(mb, [-4096, -64, -64], [4096, 64, 64])
+    for i in range(100):                                               # 100 thin slabs in a row: a comb tree
+        mb.box_brush([-4000 + 80 * i, -32, -32], [-4000 + 80 * i + 8, 32, 32], 0)
+    m = mb.finish(seed=1, leaf_max=1)
+    e2 = Engine(0)
+    e2.load_bsp(m.data)
+    s = np.array([[-4050, 0, 0]], np.float32).repeat(64, 0)
+    en = np.array([[4050, 0, 0]], np.float32).repeat(64, 0)
+    o = cmoracle.OracleCM(e2.map.to_dict())
+    want, info = o.box_trace(s, en, want_info=True)
+    try:
+        got = e2.box_trace(s, en)
+        assert_traces_equal(got, want, "deep tree within the stack limit")
+    except CMGPUError as ex:
+        assert ex.code == 8
+    e2.close()
+
+
+# ---- full-size properties (BASELINE.json sizes; the oracle only checks a sample) -----------------
+@pytest.fixture(scope="module")
+def big(eng):
+    import torch
+    m = bspgen.arena_map(n_brushes=20000, seed=0xC0FFEE02)
+    n = 1 << 22
+    s, e = bspgen.make_sweeps(m, n, 0xBADC0DE2, z_range=(24.0, 2048.0))
+    eng.load_bsp(m.data)
+    dev = torch.device("cuda", 0)
+    ds, de = torch.from_numpy(s).to(dev), torch.from_numpy(e).to(dev)
+    out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
+    eng.box_trace_device(ds, de, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, out)
+    torch.cuda.synchronize()
+    eng.check_status()
+    return dict(m=m, s=s, e=e, ds=ds, de=de, out=out, n=n)
+
+
+def test_full_size_sample_against_oracle(eng, big):
+    from threecore_b200.engine import traces_from_tensor
+    idx = np.random.default_rng(1).choice(big["n"], size=150000, replace=False)
+    got = traces_from_tensor(big["out"])[idx]
+    o = cmoracle.OracleCM(eng.map.to_dict())
+    want = o.box_trace(big["s"][idx], big["e"][idx], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID)
+    assert_traces_equal(got, want, "4Mi-ray batch, 150k sample")
+
+
+def test_full_size_permutation_invariance(eng, big):
+    """results belong to items, not to lanes: a permuted batch gives the permuted records (scheduler independence)"""
+    import torch
+    n = big["n"]
+    perm = torch.randperm(n, device=big["ds"].device, generator=torch.Generator(device=big["ds"].device).manual_seed(3))
+    out2 = torch.empty_like(big["out"])
+    eng.box_trace_device(big["ds"][perm].contiguous(), big["de"][perm].contiguous(), bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS,
+                         bspgen.MASK_PLAYERSOLID, out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, big["out"][perm])
+
+
+def test_full_size_host_api_equals_device_api(eng, big):
+    from threecore_b200.engine import traces_from_tensor
+    n = 1 << 20
+    got = eng.box_trace(big["s"][:n], big["e"][:n], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID)
+    assert_traces_equal(got, traces_from_tensor(big["out"][:n]), "host-pointer path vs device-pointer path")
+
+
+def test_full_size_trace_invariants(eng, big):
+    """size-independent properties of trace_t over the whole batch"""
+    from threecore_b200.engine import traces_from_tensor
+    t = traces_from_tensor(big["out"])
+    f = t["fraction"]
+    assert ((f >= 0) & (f <= 1)).all()
+    assert (t["entityNum"] == 0).all() and (t["plane_pad"] == 0).all()
+    assert ((t["allsolid"] == 0) | (t["startsolid"] == 1)).all()            # allsolid implies startsolid
+    assert (f[t["allsolid"] == 1] == 0).all()
+    miss = f == 1
+    assert np.array_equal(t["endpos"][miss], big["e"][miss])                 # untouched sweeps end at `end`
+    hit = (f < 1) & (t["allsolid"] == 0)
+    nrm = np.linalg.norm(t["plane_normal"][hit].astype(np.float64), axis=1)
+    assert np.abs(nrm - 1).max() < 1e-3                                       # the assert the reference compiles out (cm_trace.c:683)
+    assert (t["contents"][hit] & bspgen.MASK_PLAYERSOLID != 0).all()
+    # endpos lies on the segment at `fraction`
+    want = big["s"][hit] + f[hit, None] * (big["e"][hit] - big["s"][hit])
+    assert np.array_equal(t["endpos"][hit], want.astype(np.float32))
+    # idempotence: re-tracing to the reported endpos is not blocked earlier than the push-off epsilon allows
+    assert 0.3 < hit.mean() < 0.7
