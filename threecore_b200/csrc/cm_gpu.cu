@@ -52,6 +52,7 @@ struct cmgpu_ctx_s {
 	int cursorSlot = 0;
 	int gridPlain = 0, gridCount = 0;    // resident CTAs of the two kernel variants
 	int gang = kGang;
+	int lightReps = 3;
 	int *hStatus = nullptr;              // pinned
 	unsigned long long launches = 0;
 	cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
@@ -348,6 +349,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s) {
 	// kChunk items at a time from a cursor that must be zero at launch
 	q.cursor = ctx->dCursor + (ctx->cursorSlot++ % kCursorSlots);
 	q.gang = ctx->gang;
+	q.lightReps = ctx->lightReps;
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
 	const int resident = ctx->counting ? ctx->gridCount : ctx->gridPlain;
 	const long long warpsWanted = ((long long)q.n + kChunk - 1) / kChunk;
@@ -399,7 +401,8 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 	}
 	cmgpu_ctx *ctx = new cmgpu_ctx_s();
 	ctx->device = device;
-	if (const char *g = getenv("CMGPU_GANG")) ctx->gang = atoi(g);   // tuning knob
+	if (const char *g = getenv("CMGPU_GANG")) ctx->gang = atoi(g);   // tuning knobs
+	if (const char *g = getenv("CMGPU_LIGHT_REPS")) ctx->lightReps = atoi(g) > 0 ? atoi(g) : 1;
 	cudaSetDevice(device);
 	bool ok = true;
 	for (auto &s : ctx->streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;

@@ -87,6 +87,7 @@ struct TraceBatch {
 	int *status;                         // device status word
 	int *cursor;                         // work cursor, zero at launch
 	int gang;                            // lanes that must gather before a heavy block runs
+	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
 	Counters *counters;                  // only touched by the counting variant
 };
 
@@ -572,8 +573,11 @@ __device__ __forceinline__ void finishItem(const TraceBatch &q, Lane &L) {
 // (>= kGang, or at least as many as there are lanes still doing light work, or nothing else
 // can make progress).  Running the expensive blocks with a full gang instead of whichever
 // one or two lanes happen to need them is what keeps the warp's lanes busy.
+#ifndef CMGPU_MIN_BLOCKS
+#define CMGPU_MIN_BLOCKS 1
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const TraceBatch q) {
+__global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const DevMap m, const TraceBatch q) {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned laneLt = (1u << lane) - 1u;
 	Seg stack[kMaxDepth];
@@ -628,37 +632,63 @@ __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const Trac
 			}
 		}
 
-		// ---------------- one node of CM_TraceThroughTree, cm_trace.c:439-486 (light) -----------------
-		if (mode == M_NODE) {
-			if (L.fraction <= L.f1) {
-				mode = popSegment(L, stack);                  // already hit something nearer
-			} else if (L.num < 0) {
-				enterLeaf(L, __ldg(&m.leafs[-1 - L.num]));
-				Cnt<COUNT>::add(L.cLeafs);
-				mode = M_LEAF;
-			} else {
-				const int4 nd = __ldg(&m.nodes[L.num]);
-				Cnt<COUNT>::add(L.cNodes);
-				double t1, t2, off;
-				if (nd.z < 3) {
-					const float dist = __int_as_float(nd.w);
-					t1 = (double)(sel3(L.ax, L.ay, L.az, nd.z) - dist);   // float subtract, then widened
-					t2 = (double)(sel3(L.bx, L.by, L.bz, nd.z) - dist);
-					off = (L.flags & F_POINT) ? 0.0 : (double)sel3(L.p0x, L.p0y, L.p0z, nd.z);
+		// ---------------- light steps: a few per iteration, so the census/fetch overhead is shared -----------------
+		#pragma unroll 1
+		for (int rep = 0; rep < q.lightReps; rep++) {
+			// ---------------- one node of CM_TraceThroughTree, cm_trace.c:439-486 (light) -----------------
+			if (mode == M_NODE) {
+				if (L.fraction <= L.f1) {
+					mode = popSegment(L, stack);                  // already hit something nearer
+				} else if (L.num < 0) {
+					enterLeaf(L, __ldg(&m.leafs[-1 - L.num]));
+					Cnt<COUNT>::add(L.cLeafs);
+					mode = M_LEAF;
 				} else {
-					const float4 pl = __ldg(&m.nodePlanes[L.num]);
-					t1 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.ax, L.ay, L.az) - (double)pl.w;
-					t2 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.bx, L.by, L.bz) - (double)pl.w;
-					off = (L.flags & F_POINT) ? 0.0 : 2048.0;
-				}
-				if (t1 >= off + 1 && t2 >= off + 1) {
-					L.num = nd.x;
-				} else if (t1 < -off - 1 && t2 < -off - 1) {
-					L.num = nd.y;
-				} else {
-					mode = M_SPLIT;                               // park: the split is done by a gang
+					const int4 nd = __ldg(&m.nodes[L.num]);
+					Cnt<COUNT>::add(L.cNodes);
+					double t1, t2, off;
+					if (nd.z < 3) {
+						const float dist = __int_as_float(nd.w);
+						t1 = (double)(sel3(L.ax, L.ay, L.az, nd.z) - dist);   // float subtract, then widened
+						t2 = (double)(sel3(L.bx, L.by, L.bz, nd.z) - dist);
+						off = (L.flags & F_POINT) ? 0.0 : (double)sel3(L.p0x, L.p0y, L.p0z, nd.z);
+					} else {
+						const float4 pl = __ldg(&m.nodePlanes[L.num]);
+						t1 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.ax, L.ay, L.az) - (double)pl.w;
+						t2 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.bx, L.by, L.bz) - (double)pl.w;
+						off = (L.flags & F_POINT) ? 0.0 : 2048.0;
+					}
+					if (t1 >= off + 1 && t2 >= off + 1) {
+						L.num = nd.x;
+					} else if (t1 < -off - 1 && t2 < -off - 1) {
+						L.num = nd.y;
+					} else {
+						mode = M_SPLIT;                               // park: the split is done by a gang
+					}
 				}
 			}
+
+			// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393 (light) -----------------
+			if (mode == M_LEAF) {
+				if (L.k >= L.kEnd) {
+					mode = (L.ps < L.psEnd && !m.noCurves) ? M_PATCH : popSegment(L, stack);
+				} else {
+					const float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
+					const float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
+					L.k++;
+					Cnt<COUNT>::add(L.cBrushRefs);
+					if (__float_as_int(bmn.w) & L.mask) {
+						Cnt<COUNT>::add(L.cBrushBounds);
+						if ((L.flags & F_BOX) && __float_as_int(bmx.w) == m.boxBrush) {
+							mode = M_BRUSH;                           // temp box: bounds come from the item
+						} else if (!(L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
+						             L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps)) {
+							mode = M_BRUSH;                           // CM_BoundsIntersect passed (cm_test.c:481-494): park
+						}
+					}
+				}
+			}
+
 		}
 
 		// ---------------- split a segment at a node, cm_trace.c:492-537 (heavy) -----------------
@@ -708,27 +738,6 @@ __global__ void __launch_bounds__(kBlock) traceKernel(const DevMap m, const Trac
 				L.f2 = midf;
 				L.bx = mx; L.by = my; L.bz = mz;
 				mode = M_NODE;
-			}
-		}
-
-		// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393 (light) -----------------
-		if (mode == M_LEAF) {
-			if (L.k >= L.kEnd) {
-				mode = (L.ps < L.psEnd && !m.noCurves) ? M_PATCH : popSegment(L, stack);
-			} else {
-				const float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
-				const float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
-				L.k++;
-				Cnt<COUNT>::add(L.cBrushRefs);
-				if (__float_as_int(bmn.w) & L.mask) {
-					Cnt<COUNT>::add(L.cBrushBounds);
-					if ((L.flags & F_BOX) && __float_as_int(bmx.w) == m.boxBrush) {
-						mode = M_BRUSH;                           // temp box: bounds come from the item
-					} else if (!(L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
-					             L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps)) {
-						mode = M_BRUSH;                           // CM_BoundsIntersect passed (cm_test.c:481-494): park
-					}
-				}
 			}
 		}
 

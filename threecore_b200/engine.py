@@ -93,10 +93,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("CMGPU_LIB", LIB_PATH)      # experiments may point at another build of the same library
+    if not os.path.exists(path):
         raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(make -C threecore_b200/csrc). The engine has no CPU path.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.cmgpu_last_error.restype = C.c_char_p
     lib.cmgpu_last_error.argtypes = [C.c_void_p]
     lib.cmgpu_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
