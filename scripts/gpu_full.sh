@@ -1,0 +1,15 @@
+#!/bin/bash
+# Runs ON the GPU box (via gpurun): GPU tests, bench (both arms), ncu launch list, one ncu --set full capture.
+# usage: gpurun --timeout 1500 -- 'bash scripts/gpu_full.sh <tag>'
+tag=${1:-rXX}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -n 3 gpurun_out/${tag}_pytest_gpu.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"
+python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${tag}_bench.json | cut -c1-400
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_list.log 2>&1; echo "ncu list rc=$?"
+python scripts/prof_trace.py 2097152 3 > gpurun_out/${tag}_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:traceKernel -s 1 -c 1 -f -o gpurun_out/prof_${tag} \
+    python scripts/prof_trace.py 2097152 3 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
