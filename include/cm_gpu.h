@@ -131,6 +131,10 @@ int  cmgpu_clear(cmgpu_ctx *ctx);
 /* cvars that change results: cm_noCurves (cm_trace.c:159,405), cm_playerCurveClip (cm_patch.c:1234) */
 int  cmgpu_set_cvars(cmgpu_ctx *ctx, int noCurves, int playerCurveClip);
 int  cmgpu_num_inline_models(const cmgpu_ctx *ctx);
+/* Tuning knobs; none of them changes results.  "bin" (0/1: trace large batches in the order of their
+ * start cell), "bin_min_items", "bin_cell" (world units; takes effect at the next cmgpu_upload),
+ * "bin_long_len", "gang", "light_reps".  Unknown names are CMGPU_ERR_INVALID. */
+int  cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value);
 
 /* ---- batched queries, HOST pointers (copies in, kernel, copies out) -------
  * starts/ends [n][3]; mins/maxs [1][3] when hull_stride==0 or [n][3] when 1,

@@ -230,3 +230,31 @@ def test_full_size_trace_invariants(eng, big):
     assert np.array_equal(t["endpos"][hit], want.astype(np.float32))
     # idempotence: re-tracing to the reported endpos is not blocked earlier than the push-off epsilon allows
     assert 0.3 < hit.mean() < 0.7
+
+
+def test_binned_order_equals_input_order(eng, big):
+    """tracing a batch in start-cell order (cmgpu_set_option "bin") must not change a single byte"""
+    import torch
+    n = 1 << 20
+    outs = []
+    for on in (1, 0):
+        eng.set_option("bin", on)
+        o = torch.empty((n, 56), dtype=torch.uint8, device=big["ds"].device)
+        eng.box_trace_device(big["ds"][:n], big["de"][:n], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, o)
+        torch.cuda.synchronize()
+        outs.append(o)
+    eng.set_option("bin", 1)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], big["out"][:n])
+
+
+def test_binning_small_batches_all_query_kinds(eng):
+    """force the binned path on small batches of every query kind (per-item hulls, models, temp boxes, rotations)"""
+    eng.set_option("bin_min_items", 1)
+    try:
+        for kind in ("arena_models", "patches_small"):
+            m, o = load(eng, kind)
+            for case in cases.world_cases(kind, n=5000) + cases.entity_cases(kind, n=5000):
+                check(eng, o, case)
+    finally:
+        eng.set_option("bin_min_items", 1 << 15)

@@ -6,6 +6,7 @@
 // (code/qcommon/cm_public.h:42-52) and the upload hook after
 // code/qcommon/cm_load.c:734.
 #include "cm_kernels.cuh"
+#include "cm_trace_fast.cuh"
 #include "../../include/cm_gpu.h"
 
 #include <math.h>
@@ -27,6 +28,7 @@ namespace {
 thread_local std::string g_createError;
 
 constexpr int kCursorSlots = 64;
+constexpr int kBinSlots = 3;             // histogram tables, one per pipeline stream
 constexpr int kPipeChunks = 8;           // host batches are split so copies overlap the kernel
 constexpr size_t kMinChunkItems = 1 << 16;
 
@@ -51,8 +53,21 @@ struct cmgpu_ctx_s {
 	int *dCursor = nullptr;              // work cursors of the persistent kernel, one per launch slot
 	int cursorSlot = 0;
 	int gridPlain = 0, gridCount = 0;    // resident CTAs of the two kernel variants
+	int gridFast = 0, gridFastCount = 0;
+	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
+	int numPatches = 0;
+	bool useFast = true;
 	int gang = kGang;
 	int lightReps = 3;
+	// spatial binning of large batches (counting sort by start cell)
+	BinGrid grid{};
+	bool binning = true;
+	int binMinItems = 1 << 15;           // smaller batches are traced in input order
+	float binCell = 256.0f, binLongLen = 512.0f;
+	DevBuf bKeys, bRecs, bHist[kBinSlots];
+	cudaEvent_t binDone = nullptr;       // the workspace above is free again once this has fired
+	cudaStream_t binStream = nullptr;    // stream of the device-pointer call that last used the workspace
+	bool binBusy = false;                // binDone has been recorded by such a call
 	int *hStatus = nullptr;              // pinned
 	unsigned long long launches = 0;
 	cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
@@ -85,7 +100,7 @@ int fail(cmgpu_ctx *ctx, int code, const char *fmt, ...) {
 
 int reserve(cmgpu_ctx *ctx, DevBuf &b, size_t bytes) {
 	if (bytes <= b.cap) return CMGPU_OK;
-	if (b.p) cudaFree(b.p);
+	if (b.p) cudaFree(b.p);                      // cudaFree synchronises the device: nothing is still reading the old block
 	b.p = nullptr;
 	b.cap = 0;
 	size_t want = bytes + bytes / 4 + 256;
@@ -118,6 +133,8 @@ void freeMap(cmgpu_ctx *ctx) {
 	ctx->hasMap = false;
 	ctx->numModels = 0;
 	memset(&ctx->map, 0, sizeof(ctx->map));
+	memset(&ctx->fast, 0, sizeof(ctx->fast));
+	ctx->numPatches = 0;
 }
 
 inline int signbitsOf(const float *n) {
@@ -311,14 +328,93 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		borders[i] = f->borders[2 * (size_t)i] | (f->borders[2 * (size_t)i + 1] ? (int)0x80000000u : 0);
 	}
 
-	int rc;
+	int rc = CMGPU_OK;
 #define UP(vec, field) if ((rc = uploadArray(ctx, vec, &m.field)) != CMGPU_OK) return rc
 	UP(nodes, nodes); UP(nodePlanes, nodePlanes); UP(leafs, leafs); UP(leafBrushBox, leafBrushBox);
 	UP(leafsurfaces, leafsurfaces); UP(brushInfo, brushInfo);
 	UP(sidePlanes, sidePlanes); UP(sideMeta, sideMeta); UP(modelLeafs, modelLeafs); UP(surf2patch, surf2patch);
 	UP(patchInfo, patchInfo); UP(patchBox, patchBox); UP(patchPlanes, patchPlanes); UP(facets, facets);
 	UP(borders, borders);
+	{	// ---- layout of the hot kernel: leafs as sentinel-terminated streams of widened brush boxes ----
+		std::vector<int> streamStart((size_t)f->numLeafs);
+		std::vector<float4> stream;
+		stream.reserve(2 * ((size_t)f->numLeafBrushes + (size_t)f->numLeafs));
+		for (int l = 0; l < f->numLeafs; l++) {
+			const int32_t *lf = f->leafs + 4 * (size_t)l;
+			streamStart[l] = (int)(stream.size() / 2);
+			for (int k = 0; k < lf[1]; k++) {
+				const int bi = f->leafbrushes[lf[0] + k];
+				const float *bb = f->brushBounds + 6 * (size_t)bi;
+				// CM_BoundsIntersect's own float ops (cm_test.c:481-494), done once
+				stream.push_back(make_float4(bb[0] - kBoundsEps, bb[1] - kBoundsEps, bb[2] - kBoundsEps,
+				                             bitsToFloat(f->brushes[3 * (size_t)bi])));
+				stream.push_back(make_float4(bb[3] + kBoundsEps, bb[4] + kBoundsEps, bb[5] + kBoundsEps, bitsToFloat(bi)));
+			}
+			stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(0)));
+			stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(-1)));
+		}
+		std::vector<int4> fnodes((size_t)f->numNodes);
+		for (int i = 0; i < f->numNodes; i++) {
+			int4 nd = nodes[i];
+			if (nd.x < 0) nd.x = -1 - streamStart[-1 - nd.x];
+			if (nd.y < 0) nd.y = -1 - streamStart[-1 - nd.y];
+			fnodes[i] = nd;
+		}
+		std::vector<float4> brushRec(2 * (size_t)f->numBrushes);
+		std::vector<int> brushContents((size_t)f->numBrushes);
+		for (int i = 0; i < f->numBrushes; i++) {
+			const int32_t *b = f->brushes + 3 * (size_t)i;
+			const float *bb = f->brushBounds + 6 * (size_t)i;
+			brushRec[2 * (size_t)i] = make_float4(bb[0], bb[1], bb[2], bitsToFloat(b[1]));
+			brushRec[2 * (size_t)i + 1] = make_float4(bb[3], bb[4], bb[5], bitsToFloat((b[2] & 0xffffff) | (brushInfo[i].w ? (1 << 30) : 0)));
+			brushContents[i] = b[0];
+		}
+		FastMap &fm = ctx->fast;
+		if ((rc = uploadArray(ctx, fnodes, &fm.nodes)) != CMGPU_OK) return rc;
+		if ((rc = uploadArray(ctx, stream, &fm.stream)) != CMGPU_OK) return rc;
+		if ((rc = uploadArray(ctx, brushRec, &fm.brushRec)) != CMGPU_OK) return rc;
+		if ((rc = uploadArray(ctx, brushContents, &fm.brushContents)) != CMGPU_OK) return rc;
+		fm.nodePlanes = m.nodePlanes;
+		fm.sidePlanes = m.sidePlanes;
+		fm.sideMeta = m.sideMeta;
+		ctx->numPatches = f->numPatches;
+	}
 #undef UP
+	{	// binning grid over the bounds of the world's brushes
+		float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+		for (int i = 0; i < f->numBrushes; i++) {
+			if (i == f->boxBrush) continue;
+			const float *bb = f->brushBounds + 6 * (size_t)i;
+			for (int a = 0; a < 3; a++) {
+				if (bb[a] < lo[a]) lo[a] = bb[a];
+				if (bb[3 + a] > hi[a]) hi[a] = bb[3 + a];
+			}
+		}
+		BinGrid &g = ctx->grid;
+		int totalBits = 0;
+		for (int a = 0; a < 3; a++) {
+			float ext = hi[a] - lo[a];
+			if (!(ext > 1.0f) || !(ext < 1e9f)) { ext = 1.0f; lo[a] = 0.0f; }
+			int bits = 0;
+			while (bits < 8 && (float)(1 << bits) * ctx->binCell < ext) bits++;
+			g.bits[a] = bits;
+			totalBits += bits;
+		}
+		while (totalBits > 19) {                     // keep the histogram at a few MB
+			int a = g.bits[0] >= g.bits[1] ? (g.bits[0] >= g.bits[2] ? 0 : 2) : (g.bits[1] >= g.bits[2] ? 1 : 2);
+			g.bits[a]--;
+			totalBits--;
+		}
+		for (int a = 0; a < 3; a++) {
+			float ext = hi[a] - lo[a];
+			if (!(ext > 1.0f) || !(ext < 1e9f)) ext = 1.0f;
+			g.cells[a] = 1 << g.bits[a];
+			g.lo[a] = lo[a];
+			g.inv[a] = (float)g.cells[a] / ext;
+		}
+		g.longLen2 = ctx->binLongLen * ctx->binLongLen;
+		g.numBins = kBinClasses * g.cells[0] * g.cells[1] * g.cells[2];
+	}
 	m.numNodes = f->numNodes;
 	m.numModels = f->numModels;
 	m.boxBrush = f->boxBrush;
@@ -341,25 +437,92 @@ int checkHandles(cmgpu_ctx *ctx, int n, const int32_t *models) {
 	return CMGPU_OK;
 }
 
-int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s) {
+// Per-batch constants of the hot kernel.  The float ops are CM_Trace's own (cm_trace.c:582-588, 650-659).
+// nodeHi/nodeLo: CM_TraceThroughTree compares the float differences t1,t2 (widened) with the doubles
+// offset+1 and -offset-1 (cm_trace.c:483,487).  For a float t and a double x: t >= x <=> t >= RU(x) and
+// t < -x <=> t < -RD(x), RU/RD = x rounded up/down to float; so the comparison can stay in float.
+FastHull makeFastHull(const float *mins, const float *maxs, int mask) {
+	FastHull h{};
+	bool point = true;
+	for (int a = 0; a < 3; a++) {
+		const float off = (mins[a] + maxs[a]) * 0.5f;
+		h.off[a] = off;
+		h.n0[a] = mins[a] - off;
+		h.p0[a] = maxs[a] - off;
+		if (h.n0[a] != 0.0f) point = false;
+	}
+	h.isPoint = point ? 1 : 0;
+	for (int a = 0; a < 3; a++) {
+		const double x = (double)(point ? 0.0f : h.p0[a]) + 1.0;
+		float up = (float)x, dn = (float)x;
+		if ((double)up < x) up = nextafterf(up, INFINITY);
+		if ((double)dn > x) dn = nextafterf(dn, -INFINITY);
+		h.nodeHi[a] = up;
+		h.nodeLo[a] = -dn;
+	}
+	h.mask = mask;
+	return h;
+}
+
+// wsOffset: first item of this launch inside the context's binning workspace (the host pipeline gives
+// every chunk its own range); histSlot: which histogram table to use (one per pipeline stream).
+int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1) {
 	if (q.n <= 0) return CMGPU_OK;
 	ctx->map.noCurves = ctx->noCurves;
 	ctx->map.playerCurveClip = ctx->playerCurveClip;
+	if (ctx->binning && q.n >= ctx->binMinItems) {
+		int rc;
+		const bool external = histSlot < 0;          // device-pointer call on the caller's stream
+		if (external) {
+			histSlot = 0;
+			wsOffset = 0;
+			if ((rc = reserve(ctx, ctx->bKeys, (size_t)q.n * 4))) return rc;
+			if ((rc = reserve(ctx, ctx->bRecs, (size_t)q.n * 32))) return rc;
+			// a launch on another stream may still be reading the workspace
+			if (ctx->binBusy && ctx->binStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->binDone, 0));
+		}
+		const int numTiles = (ctx->grid.numBins + kScanTile - 1) / kScanTile;
+		if ((rc = reserve(ctx, ctx->bHist[histSlot], ((size_t)ctx->grid.numBins + (size_t)numTiles) * 4))) return rc;
+		unsigned *keys = (unsigned *)ctx->bKeys.p + wsOffset;
+		float4 *recs = (float4 *)ctx->bRecs.p + 2 * wsOffset;
+		unsigned *hist = (unsigned *)ctx->bHist[histSlot].p;
+		CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, (size_t)ctx->grid.numBins * 4, s));
+		const int g256 = (q.n + 255) / 256;
+		binCountKernel<<<g256, 256, 0, s>>>(ctx->grid, q.n, q.starts, q.ends, q.models, keys, hist);
+		unsigned *tileSums = hist + ctx->grid.numBins;
+		binTileSumKernel<<<numTiles, 256, 0, s>>>(hist, ctx->grid.numBins, tileSums);
+		binTileScanKernel<<<1, 256, 0, s>>>(tileSums, numTiles);
+		binScanKernel<<<numTiles, 256, 0, s>>>(hist, ctx->grid.numBins, tileSums);
+		binScatterKernel<<<g256, 256, 0, s>>>(q.n, q.starts, q.ends, keys, hist, recs);
+		ctx->launches += 5;
+		q.recs = recs;
+		if (external) { ctx->binStream = s; ctx->binBusy = true; }
+		else ctx->binBusy = false;
+	}
 	// persistent kernel: as many CTAs as fit on the GPU (fewer for tiny batches), each warp pulls
 	// kChunk items at a time from a cursor that must be zero at launch
 	q.cursor = ctx->dCursor + (ctx->cursorSlot++ % kCursorSlots);
 	q.gang = ctx->gang;
 	q.lightReps = ctx->lightReps;
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
-	const int resident = ctx->counting ? ctx->gridCount : ctx->gridPlain;
+	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
+	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
+	const int resident = fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
 	const long long warpsWanted = ((long long)q.n + kChunk - 1) / kChunk;
 	long long blocks = (warpsWanted + (kBlock / 32) - 1) / (kBlock / 32);
 	if (blocks > resident) blocks = resident;
 	if (blocks < 1) blocks = 1;
-	if (ctx->counting) traceKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
-	else               traceKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
+	if (fast) {
+		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask);
+		if (ctx->counting) traceFastKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
+		else               traceFastKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
+	} else {
+		if (ctx->counting) traceKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
+		else               traceKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
+	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
+	if (q.recs && ctx->binBusy) CUDA_TRY(ctx, cudaEventRecord(ctx->binDone, s));
 	return CMGPU_OK;
 }
 
@@ -403,10 +566,14 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 	ctx->device = device;
 	if (const char *g = getenv("CMGPU_GANG")) ctx->gang = atoi(g);   // tuning knobs
 	if (const char *g = getenv("CMGPU_LIGHT_REPS")) ctx->lightReps = atoi(g) > 0 ? atoi(g) : 1;
+	if (const char *g = getenv("CMGPU_BIN")) ctx->binning = atoi(g) != 0;
+	if (const char *g = getenv("CMGPU_BIN_CELL")) ctx->binCell = atof(g) > 1.0 ? (float)atof(g) : 128.0f;
+	if (const char *g = getenv("CMGPU_BIN_LONG")) ctx->binLongLen = (float)atof(g);
 	cudaSetDevice(device);
 	bool ok = true;
 	for (auto &s : ctx->streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
 	for (auto &ev : ctx->evt) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->binDone, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaMalloc(&ctx->dCounters, sizeof(Counters)) == cudaSuccess;
 	ok = ok && cudaMemset(ctx->dCounters, 0, sizeof(Counters)) == cudaSuccess;
 	ok = ok && cudaMalloc(&ctx->dStatus, sizeof(int)) == cudaSuccess;
@@ -420,6 +587,11 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 		int perSmC = 0;
 		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmC, traceKernel<true>, kBlock, 0) == cudaSuccess && perSmC > 0;
 		ctx->gridCount = perSmC * prop.multiProcessorCount;
+		int perSmF = 0, perSmFC = 0;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmF, traceFastKernel<false>, kBlock, 0) == cudaSuccess && perSmF > 0;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFC, traceFastKernel<true>, kBlock, 0) == cudaSuccess && perSmFC > 0;
+		ctx->gridFast = perSmF * prop.multiProcessorCount;
+		ctx->gridFastCount = perSmFC * prop.multiProcessorCount;
 	}
 	if (!ok) {
 		g_createError = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -436,7 +608,9 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	cudaDeviceSynchronize();
 	freeMap(ctx);
 	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
-	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit}) releaseBuf(*b);
+	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit,
+	                  &ctx->bKeys, &ctx->bRecs, &ctx->bHist[0], &ctx->bHist[1], &ctx->bHist[2]}) releaseBuf(*b);
+	if (ctx->binDone) cudaEventDestroy(ctx->binDone);
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->dStatus) cudaFree(ctx->dStatus);
 	if (ctx->dCursor) cudaFree(ctx->dCursor);
@@ -474,6 +648,20 @@ int cmgpu_set_cvars(cmgpu_ctx *ctx, int noCurves, int playerCurveClip) {
 }
 
 int cmgpu_num_inline_models(const cmgpu_ctx *ctx) { return ctx ? ctx->numModels : 0; }
+
+int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
+	if (!ctx || !name) return CMGPU_ERR_INVALID;
+	const std::string k(name);
+	if (k == "bin") ctx->binning = value != 0;
+	else if (k == "bin_min_items") ctx->binMinItems = value < 1 ? 1 : (int)value;
+	else if (k == "bin_cell") { if (!(value > 1.0)) return fail(ctx, CMGPU_ERR_INVALID, "bin_cell must be > 1"); ctx->binCell = (float)value; }
+	else if (k == "bin_long_len") ctx->binLongLen = (float)value;
+	else if (k == "fast") ctx->useFast = value != 0;
+	else if (k == "gang") ctx->gang = (int)value;
+	else if (k == "light_reps") ctx->lightReps = value < 1 ? 1 : (int)value;
+	else return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_set_option: unknown option '%s'", name);
+	return CMGPU_OK;
+}
 
 void cmgpu_rotation_matrices(int n, const float *angles, float *matrices, int32_t *rot_index) {
 	// AngleVectors, q_math.c:999-1032: angle scaled in double and rounded to float, sin/cos of that
@@ -638,6 +826,13 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	}
 	if ((rc = reserve(ctx, ctx->bOut, N * sizeof(cmgpu_trace_t)))) return rc;
 	if (hit_ids && (rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
+	if (ctx->binning && N >= (size_t)ctx->binMinItems) {
+		if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
+		if (ctx->binBusy) CUDA_TRY(ctx, cudaEventSynchronize(ctx->binDone));   // an earlier device-pointer call
+		ctx->binBusy = false;
+		if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
+		if ((rc = reserve(ctx, ctx->bRecs, N * 32))) return rc;
+	}
 
 	int chunks = (int)((N + kMinChunkItems - 1) / kMinChunkItems);
 	if (chunks > kPipeChunks) chunks = kPipeChunks;
@@ -687,7 +882,7 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 		q.hitIds = hit_ids ? (int *)ctx->bHit.p + lo : nullptr;
 		q.status = ctx->dStatus;
 		q.counters = ctx->dCounters;
-		if ((rc = launchTrace(ctx, q, s))) return rc;
+		if ((rc = launchTrace(ctx, q, s, lo, c % 3))) return rc;
 		CUDA_TRY(ctx, cudaMemcpyAsync(results + lo, (cmgpu_trace_t *)ctx->bOut.p + lo, cnt * sizeof(cmgpu_trace_t), cudaMemcpyDeviceToHost, s));
 		if (hit_ids) CUDA_TRY(ctx, cudaMemcpyAsync(hit_ids + lo, (int *)ctx->bHit.p + lo, cnt * 4, cudaMemcpyDeviceToHost, s));
 	}

@@ -89,7 +89,22 @@ struct TraceBatch {
 	int gang;                            // lanes that must gather before a heavy block runs
 	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
 	Counters *counters;                  // only touched by the counting variant
+	const float4 *recs;                  // binned batch: [2*slot] start.xyz + item bits, [2*slot+1] end.xyz + 0; null = input order
 };
+
+// ---- spatial binning of a batch (counting sort by start cell) -------------------------------
+// Items are independent, so the order in which lanes take them is free.  Taking them in the
+// order of the cell their start point lies in makes the lanes of a warp walk the same nodes,
+// leafs and brushes (same L1 lines, same trip counts).  Results are still written by item number.
+struct BinGrid {
+	float lo[3], inv[3];                 // cell = (p - lo) * inv, clamped
+	int   cells[3];                      // cells per axis (powers of two)
+	int   bits[3];
+	float longLen2;                      // sweeps longer than this form their own class
+	int   numBins;                       // classes * cells
+};
+constexpr int kBinClasses = 4;           // 0 short sweep, 1 long sweep, 2 position test (start == end), 3 inline model / temp box
+
 
 struct PointBatch {
 	int n;
@@ -436,10 +451,18 @@ __device__ __forceinline__ void enterLeaf(Lane &L, const int4 leaf) {
 }
 
 // ---- item setup: CM_Trace (cm_trace.c:545-669) and the head of CM_TransformedBoxTrace (cm_trace.c:708-786) -----
-__device__ __forceinline__ int beginItem(const DevMap &m, const TraceBatch &q, Lane &L, int i) {
+__device__ __forceinline__ int beginItem(const DevMap &m, const TraceBatch &q, Lane &L, int slot) {
+	int i = slot;
+	float s0x, s0y, s0z, e0x, e0y, e0z;
+	if (q.recs) {
+		const float4 a = __ldcs(&q.recs[2 * (size_t)slot]), b = __ldcs(&q.recs[2 * (size_t)slot + 1]);
+		s0x = a.x; s0y = a.y; s0z = a.z; e0x = b.x; e0y = b.y; e0z = b.z;
+		i = __float_as_int(a.w);
+	} else {
+		s0x = q.starts[3 * (size_t)i]; s0y = q.starts[3 * (size_t)i + 1]; s0z = q.starts[3 * (size_t)i + 2];
+		e0x = q.ends[3 * (size_t)i]; e0y = q.ends[3 * (size_t)i + 1]; e0z = q.ends[3 * (size_t)i + 2];
+	}
 	L.idx = i;
-	const float s0x = q.starts[3 * (size_t)i], s0y = q.starts[3 * (size_t)i + 1], s0z = q.starts[3 * (size_t)i + 2];
-	const float e0x = q.ends[3 * (size_t)i], e0y = q.ends[3 * (size_t)i + 1], e0z = q.ends[3 * (size_t)i + 2];
 	float mnx, mny, mnz, mxx, mxy, mxz;
 	if (q.mins) {
 		const float *a = q.mins + 3 * (size_t)i, *b = q.maxs + 3 * (size_t)i;
@@ -1023,6 +1046,120 @@ __global__ void __launch_bounds__(128) pointContentsKernel(const DevMap m, const
 		if (s == bi.y) contents |= __float_as_int(bmn.w);
 	}
 	q.out[i] = contents;
+}
+
+// ---- binning kernels ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned binOf(const BinGrid &g, float sx, float sy, float sz, float ex, float ey, float ez, int model) {
+	const int qx = (int)fminf(fmaxf((sx - g.lo[0]) * g.inv[0], 0.0f), (float)(g.cells[0] - 1));
+	const int qy = (int)fminf(fmaxf((sy - g.lo[1]) * g.inv[1], 0.0f), (float)(g.cells[1] - 1));
+	const int qz = (int)fminf(fmaxf((sz - g.lo[2]) * g.inv[2], 0.0f), (float)(g.cells[2] - 1));
+	// interleave the cell coordinates (Morton order) so that neighbouring bins are neighbouring cells
+	unsigned key = 0u;
+	int pos = 0;
+	#pragma unroll
+	for (int b = 0; b < 10; b++) {
+		if (b < g.bits[0]) key |= ((unsigned)(qx >> b) & 1u) << pos++;
+		if (b < g.bits[1]) key |= ((unsigned)(qy >> b) & 1u) << pos++;
+		if (b < g.bits[2]) key |= ((unsigned)(qz >> b) & 1u) << pos++;
+	}
+	const float dx = ex - sx, dy = ey - sy, dz = ez - sz;
+	int cls;
+	if (model) cls = 3;
+	else if (sx == ex && sy == ey && sz == ez) cls = 2;
+	else cls = (dx * dx + dy * dy + dz * dz > g.longLen2) ? 1 : 0;
+	return (unsigned)cls * (unsigned)(g.cells[0] * g.cells[1] * g.cells[2]) + key;
+}
+
+// pass 1: bin of every item + histogram
+__global__ void __launch_bounds__(256) binCountKernel(const BinGrid g, int n, const float *starts, const float *ends,
+                                                      const int *models, unsigned *keys, unsigned *hist) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const size_t o = 3 * (size_t)i;
+	const unsigned k = binOf(g, starts[o], starts[o + 1], starts[o + 2], ends[o], ends[o + 1], ends[o + 2], models ? models[i] : 0);
+	keys[i] = k;
+	atomicAdd(&hist[k], 1u);
+}
+
+// pass 2: exclusive prefix sum of the histogram in three small launches: per-tile totals, scan of the totals
+// (one CTA), per-tile scan with the tile's base.  Tiles are kScanTile bins.
+constexpr int kScanTile = 2048;          // 256 threads x 8 bins
+
+__device__ __forceinline__ unsigned blockExclusiveScan256(unsigned v, unsigned *warpSums, unsigned &total) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	unsigned incl = v;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const unsigned u = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += u;
+	}
+	if (lane == 31) warpSums[w] = incl;
+	__syncthreads();
+	if (w == 0) {
+		const unsigned x = lane < 8 ? warpSums[lane] : 0u;
+		unsigned inc = x;
+		#pragma unroll
+		for (int d = 1; d < 8; d <<= 1) {
+			const unsigned u = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += u;
+		}
+		if (lane < 8) warpSums[lane] = inc - x;
+		if (lane == 7) warpSums[8] = inc;
+	}
+	__syncthreads();
+	total = warpSums[8];
+	return warpSums[w] + incl - v;
+}
+
+__global__ void __launch_bounds__(256) binTileSumKernel(const unsigned *hist, int numBins, unsigned *tileSums) {
+	__shared__ unsigned warpSums[9];
+	const int base = blockIdx.x * kScanTile + threadIdx.x * 8;
+	unsigned v = 0;
+	#pragma unroll
+	for (int j = 0; j < 8; j++) if (base + j < numBins) v += hist[base + j];
+	unsigned total;
+	blockExclusiveScan256(v, warpSums, total);
+	if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) binTileScanKernel(unsigned *tileSums, int numTiles) {
+	__shared__ unsigned warpSums[9];
+	unsigned run = 0;
+	for (int base = 0; base < numTiles; base += 256) {
+		const int i = base + threadIdx.x;
+		const unsigned v = i < numTiles ? tileSums[i] : 0u;
+		unsigned total;
+		const unsigned ex = blockExclusiveScan256(v, warpSums, total);
+		if (i < numTiles) tileSums[i] = run + ex;
+		run += total;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(256) binScanKernel(unsigned *hist, int numBins, const unsigned *tileSums) {
+	__shared__ unsigned warpSums[9];
+	const int base = blockIdx.x * kScanTile + threadIdx.x * 8;
+	unsigned c[8], v = 0;
+	#pragma unroll
+	for (int j = 0; j < 8; j++) { c[j] = base + j < numBins ? hist[base + j] : 0u; v += c[j]; }
+	unsigned total;
+	unsigned run = tileSums[blockIdx.x] + blockExclusiveScan256(v, warpSums, total);
+	#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		if (base + j < numBins) hist[base + j] = run;
+		run += c[j];
+	}
+}
+
+// pass 3: every item takes the next slot of its bin and leaves its ray there
+__global__ void __launch_bounds__(256) binScatterKernel(int n, const float *starts, const float *ends, const unsigned *keys,
+                                                        unsigned *hist, float4 *recs) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const size_t o = 3 * (size_t)i;
+	const unsigned slot = atomicAdd(&hist[keys[i]], 1u);
+	recs[2 * (size_t)slot] = make_float4(starts[o], starts[o + 1], starts[o + 2], __int_as_float(i));
+	recs[2 * (size_t)slot + 1] = make_float4(ends[o], ends[o + 1], ends[o + 2], 0.0f);
 }
 
 }  // namespace cmgpu

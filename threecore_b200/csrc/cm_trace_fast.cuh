@@ -1,0 +1,558 @@
+// cm_trace_fast.cuh -- the hot kernel: CM_BoxTrace against the WORLD with a hull and a mask shared by
+// the whole batch (BASELINE configs 1, 2 and 5), on maps without patches (or with cm_noCurves set).
+// Everything else (inline models, temp boxes, rotations, per-item hulls, patches) runs traceKernel
+// in cm_kernels.cuh.
+//
+// Same persistent flat-state-machine scheduling as traceKernel (see there), re-cut so that every
+// step is a handful of instructions:
+//   * leafs are STREAMS of 32-byte brush entries terminated by a sentinel; a node's child refers
+//     straight to its leaf's stream, so there is no leaf record to load (cm_trace.c:370-393);
+//   * the entries carry the brush bounds already widened by BOUNDS_CLIP_EPSILON (the float ops
+//     of cm_test.c:481-494 done once at upload), so CM_BoundsIntersect is six compares;
+//   * an axial node compares the FLOAT differences t1,t2 with float images of offset+1 and
+//     -offset-1 computed once per batch (exact, see nodeThresholds in cm_gpu.cu);
+//   * the running result is (fraction, reference to the clip side, contents); the plane and surface
+//     flags are fetched when the record is written;
+//   * the brush clip first runs with float quotients that are only used to REJECT (enterFrac
+//     certainly >= leaveFrac, or certainly >= trace.fraction); the exact double divisions of
+//     cm_trace.c:314,324 are done only for brushes that survive that;
+//   * a brush that has just been clipped is not clipped again in the next leaf (the reference's
+//     checkcount, cm_trace.c:381-384; a repeat is a no-op anyway).
+#pragma once
+
+#include "cm_kernels.cuh"
+
+namespace cmgpu {
+
+struct FastMap {
+	const int4   *nodes;         // child0, child1, type (0..2 axial, 3 general), dist bits; child c < 0: leaf stream at entry -1-c
+	const float4 *nodePlanes;    // normal.xyz, dist (type 3 only)
+	const float4 *stream;        // [2k] mins-eps.xyz + contents ; [2k+1] maxs+eps.xyz + brush index, -1 ends the leaf
+	const float4 *brushRec;      // [2b] mins.xyz + firstSide ; [2b+1] maxs.xyz + (numSides | canonical << 30)
+	const int    *brushContents;
+	const float4 *sidePlanes;
+	const int2   *sideMeta;
+};
+
+// what depends only on the batch's hull and mask; by value in the kernel parameters (constant bank)
+struct FastHull {
+	float n0[3], p0[3];          // tw.size[0], tw.size[1]  (cm_trace.c:582-588)
+	float off[3];                // offset added to start and end
+	float nodeHi[3], nodeLo[3];  // t >= offset+1  <=>  t >= nodeHi ;  t < -offset-1  <=>  t < nodeLo   (t float)
+	int   isPoint;
+	int   mask;
+};
+
+enum FastMode : int { FM_IDLE = 0, FM_NODE, FM_LEAF, FM_POP, FM_SPLIT, FM_BRUSH, FM_DONE, FM_PNODE, FM_PLEAF };
+
+struct __align__(16) FastSeg { int num; float f1, f2, ax; float ay, az, bx, by; float bz, pad0, pad1, pad2; };
+
+struct FastLane {
+	int   slot;                          // position in the (binned) batch
+	float sx, sy, sz, ex, ey, ez;        // tw.start / tw.end
+	float lox, loy, loz, hix, hiy, hiz;  // tw.bounds
+	float fraction;
+	int   solid;                         // bit0 allsolid, bit1 startsolid
+	int   planeRef;                      // brush side whose plane / surfaceFlags the result carries, -1 none
+	int   contents, hitId;
+	int   num, sp;                       // tree cursor
+	float f1, f2, ax, ay, az, bx, by, bz;
+	int   k;                             // leaf stream cursor
+	int   pend;                          // brush waiting to be clipped
+	int   last0, last1;                  // brushes clipped most recently
+	int   found;                         // leafs seen by the position test
+	unsigned cNodes, cLeafs, cBrushRefs, cBrushBounds, cBrushSides, cCross, cSplits;
+};
+
+__device__ __forceinline__ float rcpApprox(float x) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+// one side for the rejection pass: exact distances and flags, approximate quotient
+struct ClipApprox {
+	bool so, go, miss, anyEnter;
+	float qe, ql;
+};
+
+__device__ __forceinline__ void approxSide(ClipApprox &c, const double d1, const double d2) {
+	c.go |= d2 > 0;
+	c.so |= d1 > 0;
+	c.miss |= d1 > 0 && (d2 >= kClipEps || d2 >= d1);
+	const bool cross = !(d1 <= 0 && d2 <= 0);
+	const bool entering = d1 > d2;
+	const float numf = (float)(entering ? d1 - kClipEps : d1 + kClipEps);
+	const float denf = (float)(d1 - d2);
+	const float q = numf * rcpApprox(denf);
+	if (cross && entering) { c.anyEnter = true; c.qe = fmaxf(c.qe, fmaxf(q, 0.0f)); }
+	if (cross && !entering) c.ql = fminf(c.ql, fminf(q, 1.0f));
+}
+
+// CM_TraceThroughBrush (cm_trace.c:261-363) for brush b.  Returns true when the trace is over (fraction 0).
+template <bool COUNT>
+__device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull &h, FastLane &L, const int b) {
+	const float4 r0 = __ldg(&fm.brushRec[2 * b]);
+	const float4 r1 = __ldg(&fm.brushRec[2 * b + 1]);
+	const int firstSide = __float_as_int(r0.w);
+	const int ns = __float_as_int(r1.w) & 0xffffff;
+	const bool canonical = (__float_as_int(r1.w) >> 30) & 1;
+	if (ns == 0) return false;
+	const double sx = L.sx, sy = L.sy, sz = L.sz, ex = L.ex, ey = L.ey, ez = L.ez;
+	// the six axial sides straight from the bounds (canonical brushes):
+	// side 2a   : normal -e_a, dist -mins[a], corner component size[1][a]
+	// side 2a+1 : normal +e_a, dist  maxs[a], corner component size[0][a]
+	// (DotProductDP with a unit normal is exactly +-component)
+	double a0, b0, a1, b1, a2, b2, a3, b3, a4, b4, a5, b5;
+	if (canonical) {
+		const double dnx = (double)h.p0[0] - (double)r0.x, dpx = (double)r1.x - (double)h.n0[0];
+		const double dny = (double)h.p0[1] - (double)r0.y, dpy = (double)r1.y - (double)h.n0[1];
+		const double dnz = (double)h.p0[2] - (double)r0.z, dpz = (double)r1.z - (double)h.n0[2];
+		a0 = -sx - dnx; b0 = -ex - dnx; a1 = sx - dpx; b1 = ex - dpx;
+		a2 = -sy - dny; b2 = -ey - dny; a3 = sy - dpy; b3 = ey - dpy;
+		a4 = -sz - dnz; b4 = -ez - dnz; a5 = sz - dpz; b5 = ez - dpz;
+	}
+	// ---- pass 1: flags (exact) and quotients (approximate, used only to reject) ----
+	ClipApprox c;
+	c.so = c.go = c.miss = c.anyEnter = false;
+	c.qe = -1.0f; c.ql = 1.0f;
+	int side = 0;
+	if (canonical) {
+		approxSide(c, a0, b0); approxSide(c, a1, b1); approxSide(c, a2, b2);
+		approxSide(c, a3, b3); approxSide(c, a4, b4); approxSide(c, a5, b5);
+		side = 6;
+		if (COUNT) L.cBrushSides += 6;
+	}
+	for (; side < ns && !c.miss; side++) {
+		const float4 pl = __ldg(&fm.sidePlanes[firstSide + side]);
+		if (COUNT) L.cBrushSides++;
+		const float cx = pl.x < 0.0f ? h.p0[0] : h.n0[0];
+		const float cy = pl.y < 0.0f ? h.p0[1] : h.n0[1];
+		const float cz = pl.z < 0.0f ? h.p0[2] : h.n0[2];
+		const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
+		const double d1 = dotd(sx, sy, sz, pl.x, pl.y, pl.z) - dist;
+		const double d2 = dotd(ex, ey, ez, pl.x, pl.y, pl.z) - dist;
+		approxSide(c, d1, d2);
+	}
+	if (c.miss) return false;                       // wholly in front of one face
+	if (!c.so) {                                    // original point was inside the brush
+		L.solid |= 2;
+		if (!c.go) {
+			L.solid |= 1;
+			L.fraction = 0.0f;
+			L.contents = __ldg(&fm.brushContents[b]);
+			L.hitId = b;
+			return true;
+		}
+		return false;
+	}
+	if (!c.anyEnter) return false;                  // enterFrac stays -1
+	{
+		// |q - f| <= 2^-21 |f| for every quotient (two conversions, rcp.approx, one product, the two roundings of
+		// the reference's own f); 2^-19 leaves a factor 4.  NaN/inf never satisfy a comparison below.
+		const float kRel = 1.9073486e-6f, kAbs = 1e-30f;
+		const float eLo = c.qe - (c.qe * kRel + kAbs);
+		const float lHi = c.ql + (fabsf(c.ql) * kRel + kAbs);
+		if (c.anyEnter && c.qe >= 0.0f) {
+			if (eLo > lHi) return false;            // enterFrac >= leaveFrac
+			if (eLo > L.fraction) return false;     // enterFrac >= trace.fraction
+		}
+	}
+	// ---- pass 2: the reference's own arithmetic ----
+	float enter = -1.0f, leave = 1.0f;
+	int lead = -1;
+	auto cross = [&](const double d1, const double d2, const int s) {
+		const bool crossing = !(d1 <= 0 && d2 <= 0);
+		const bool entering = d1 > d2;
+		const double num = entering ? d1 - kClipEps : d1 + kClipEps;
+		const double den = crossing ? d1 - d2 : 1.0;
+		const float q = (float)(num / den);
+		if (COUNT) L.cCross += crossing ? 1u : 0u;
+		const float fe = q < 0 ? 0.0f : q;
+		const float fl = q > 1 ? 1.0f : q;
+		if (crossing && entering && fe > enter) { enter = fe; lead = s; }
+		if (crossing && !entering && fl < leave) leave = fl;
+	};
+	side = 0;
+	if (canonical) {
+		cross(a0, b0, 0); cross(a1, b1, 1); cross(a2, b2, 2);
+		cross(a3, b3, 3); cross(a4, b4, 4); cross(a5, b5, 5);
+		side = 6;
+	}
+	for (; side < ns; side++) {
+		const float4 pl = __ldg(&fm.sidePlanes[firstSide + side]);
+		const float cx = pl.x < 0.0f ? h.p0[0] : h.n0[0];
+		const float cy = pl.y < 0.0f ? h.p0[1] : h.n0[1];
+		const float cz = pl.z < 0.0f ? h.p0[2] : h.n0[2];
+		const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
+		const double d1 = dotd(sx, sy, sz, pl.x, pl.y, pl.z) - dist;
+		const double d2 = dotd(ex, ey, ez, pl.x, pl.y, pl.z) - dist;
+		cross(d1, d2, side);
+	}
+	if (enter < leave && enter > -1 && enter < L.fraction) {
+		if (enter < 0) enter = 0;
+		L.fraction = enter;
+		if (lead >= 0) L.planeRef = firstSide + lead;
+		L.contents = __ldg(&fm.brushContents[b]);
+		L.hitId = b;
+	}
+	return L.fraction == 0.0f;
+}
+
+// ---- item setup: CM_Trace, cm_trace.c:545-669 ------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ int beginFast(const TraceBatch &q, const FastHull &h, FastLane &L, const int slot) {
+	float s0x, s0y, s0z, e0x, e0y, e0z;
+	if (q.recs) {
+		const float4 a = __ldcs(&q.recs[2 * (size_t)slot]), b = __ldcs(&q.recs[2 * (size_t)slot + 1]);
+		s0x = a.x; s0y = a.y; s0z = a.z; e0x = b.x; e0y = b.y; e0z = b.z;
+	} else {
+		const size_t o = 3 * (size_t)slot;
+		s0x = q.starts[o]; s0y = q.starts[o + 1]; s0z = q.starts[o + 2];
+		e0x = q.ends[o]; e0y = q.ends[o + 1]; e0z = q.ends[o + 2];
+	}
+	L.slot = slot;
+	L.sx = s0x + h.off[0]; L.sy = s0y + h.off[1]; L.sz = s0z + h.off[2];
+	L.ex = e0x + h.off[0]; L.ey = e0y + h.off[1]; L.ez = e0z + h.off[2];
+	L.solid = 0; L.fraction = 1.0f; L.planeRef = -1; L.contents = 0; L.hitId = -1;
+	L.sp = 0; L.found = 0; L.last0 = L.last1 = -1; L.pend = -1; L.k = 0;
+	if (COUNT) L.cNodes = L.cLeafs = L.cBrushRefs = L.cBrushBounds = L.cBrushSides = L.cCross = L.cSplits = 0;
+	// swept bounds (cm_trace.c:628-636)
+	if (L.sx < L.ex) { L.lox = L.sx + h.n0[0]; L.hix = L.ex + h.p0[0]; } else { L.lox = L.ex + h.n0[0]; L.hix = L.sx + h.p0[0]; }
+	if (L.sy < L.ey) { L.loy = L.sy + h.n0[1]; L.hiy = L.ey + h.p0[1]; } else { L.loy = L.ey + h.n0[1]; L.hiy = L.sy + h.p0[1]; }
+	if (L.sz < L.ez) { L.loz = L.sz + h.n0[2]; L.hiz = L.ez + h.p0[2]; } else { L.loz = L.ez + h.n0[2]; L.hiz = L.sz + h.p0[2]; }
+	L.num = 0; L.f1 = 0.0f; L.f2 = 1.0f;
+	L.ax = L.sx; L.ay = L.sy; L.az = L.sz; L.bx = L.ex; L.by = L.ey; L.bz = L.ez;
+	if (s0x == e0x && s0y == e0y && s0z == e0z) return FM_PNODE;     // position test (cm_trace.c:641-646)
+	return FM_NODE;
+}
+
+// ---- item epilogue: cm_trace.c:671-686 -------------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &q, FastLane &L) {
+	int i = L.slot;
+	float s0x, s0y, s0z, e0x, e0y, e0z;
+	if (q.recs) {
+		const float4 a = __ldcs(&q.recs[2 * (size_t)i]), b = __ldcs(&q.recs[2 * (size_t)i + 1]);
+		s0x = a.x; s0y = a.y; s0z = a.z; e0x = b.x; e0y = b.y; e0z = b.z;
+		i = __float_as_int(a.w);
+	} else {
+		const size_t o = 3 * (size_t)i;
+		s0x = q.starts[o]; s0y = q.starts[o + 1]; s0z = q.starts[o + 2];
+		e0x = q.ends[o]; e0y = q.ends[o + 1]; e0z = q.ends[o + 2];
+	}
+	float4 pl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	int2 meta = make_int2(0, 0);
+	if (L.planeRef >= 0) {
+		pl = __ldg(&fm.sidePlanes[L.planeRef]);
+		meta = __ldg(&fm.sideMeta[L.planeRef]);
+	}
+	float px, py, pz;
+	if (L.fraction == 1.0f) {
+		px = e0x; py = e0y; pz = e0z;
+	} else {
+		px = s0x + L.fraction * (e0x - s0x);
+		py = s0y + L.fraction * (e0y - s0y);
+		pz = s0z + L.fraction * (e0z - s0z);
+	}
+	uint2 *o = q.out + 7 * (size_t)i;
+	__stcs(&o[0], make_uint2((unsigned)(L.solid & 1), (unsigned)((L.solid >> 1) & 1)));
+	__stcs(&o[1], make_uint2(__float_as_uint(L.fraction), __float_as_uint(px)));
+	__stcs(&o[2], make_uint2(__float_as_uint(py), __float_as_uint(pz)));
+	__stcs(&o[3], make_uint2(__float_as_uint(pl.x), __float_as_uint(pl.y)));
+	__stcs(&o[4], make_uint2(__float_as_uint(pl.z), __float_as_uint(pl.w)));
+	__stcs(&o[5], make_uint2((unsigned)meta.y & 0xffffu, (unsigned)meta.x));
+	__stcs(&o[6], make_uint2((unsigned)L.contents, 0u));
+	if (q.hitIds) q.hitIds[i] = L.hitId;
+	if (COUNT) {
+		Counters *c = q.counters;
+		atomicAdd(&c->traces, 1ull);
+		atomicAdd(&c->nodes, (unsigned long long)L.cNodes);
+		atomicAdd(&c->leafs, (unsigned long long)L.cLeafs);
+		atomicAdd(&c->brushRefs, (unsigned long long)L.cBrushRefs);
+		atomicAdd(&c->brushBounds, (unsigned long long)L.cBrushBounds);
+		atomicAdd(&c->brushSides, (unsigned long long)L.cBrushSides);
+		atomicAdd(&c->crossings, (unsigned long long)L.cCross);
+		atomicAdd(&c->splits, (unsigned long long)L.cSplits);
+	}
+}
+
+// follow a child reference: a node, or the stream of a leaf
+template <bool COUNT>
+__device__ __forceinline__ int gotoChild(FastLane &L, const int c) {
+	if (c < 0) {
+		L.k = -1 - c;
+		if (COUNT) L.cLeafs++;
+		return FM_LEAF;
+	}
+	L.num = c;
+	return FM_NODE;
+}
+
+#ifndef CMGPU_FAST_MIN_BLOCKS
+#define CMGPU_FAST_MIN_BLOCKS 5
+#endif
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, CMGPU_FAST_MIN_BLOCKS)
+traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned laneLt = (1u << lane) - 1u;
+	FastSeg stack[kMaxDepth];
+	FastLane L;
+	int mode = FM_IDLE;
+	int chunkNext = 0, chunkEnd = 0;     // warp-uniform
+	bool supply = true;                   // warp-uniform: the global cursor may still have items
+
+	for (;;) {
+		// ---------------- census: one REDUX over 6-bit counters ------------------
+		unsigned key;
+		if (mode == FM_IDLE) key = 1u;
+		else if (mode == FM_DONE) key = 1u << 6;
+		else if (mode == FM_SPLIT) key = 1u << 12;
+		else if (mode == FM_BRUSH) key = 1u << 18;
+		else if (mode >= FM_PNODE) key = 1u << 24;
+		else key = 0u;
+		const unsigned census = __reduce_add_sync(0xffffffffu, key);
+		const int nIdle = census & 63, nDone = (census >> 6) & 63, nSplit = (census >> 12) & 63;
+		const int nBrush = (census >> 18) & 63, nPos = (census >> 24) & 63;
+		const int nLight = 32 - (nIdle + nDone + nSplit + nBrush);      // position tests count as light work
+		const int gang = min(q.gang, nLight);                          // 0 when only parked lanes are left
+
+		// ---------------- write results and hand out new items --------------------------
+		{
+			const int nWant = nDone + (supply ? nIdle : 0);
+			if (nIdle == 32 && !supply) break;
+			if (nWant > 0 && nWant >= gang) {
+				if (mode == FM_DONE) {
+					finishFast<COUNT>(fm, q, L);
+					mode = FM_IDLE;
+				}
+				const unsigned need = __ballot_sync(0xffffffffu, mode == FM_IDLE);
+				const int nNeed = __popc(need);
+				if (chunkNext >= chunkEnd && supply) {
+					int base = 0;
+					if (lane == 0) base = atomicAdd(q.cursor, kChunk);
+					base = __shfl_sync(0xffffffffu, base, 0);
+					if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
+					else { chunkNext = base; chunkEnd = min(base + kChunk, q.n); }
+				}
+				if (chunkNext < chunkEnd) {
+					if (mode == FM_IDLE) {
+						const int my = chunkNext + __popc(need & laneLt);
+						if (my < chunkEnd) mode = beginFast<COUNT>(q, h, L, my);
+					}
+					chunkNext = min(chunkNext + nNeed, chunkEnd);
+				} else if (need == 0xffffffffu) {
+					break;                                           // nothing in flight, nothing left
+				}
+			}
+		}
+
+		// ---------------- light steps -----------------
+		#pragma unroll 1
+		for (int rep = 0; rep < q.lightReps; rep++) {
+			// one axial node of CM_TraceThroughTree, cm_trace.c:456-486
+			if (mode == FM_NODE) {
+				const int4 nd = __ldg(&fm.nodes[L.num]);
+				if (COUNT) L.cNodes++;
+				const bool ax0 = nd.z == 0, ax1 = nd.z == 1;
+				const float dist = __int_as_float(nd.w);
+				const float t1 = (ax0 ? L.ax : (ax1 ? L.ay : L.az)) - dist;
+				const float t2 = (ax0 ? L.bx : (ax1 ? L.by : L.bz)) - dist;
+				const float hi = ax0 ? h.nodeHi[0] : (ax1 ? h.nodeHi[1] : h.nodeHi[2]);
+				const float lo = ax0 ? h.nodeLo[0] : (ax1 ? h.nodeLo[1] : h.nodeLo[2]);
+				const bool front = t1 >= hi && t2 >= hi;
+				const bool back = t1 < lo && t2 < lo;
+				if (nd.z < 3 && (front || back)) mode = gotoChild<COUNT>(L, front ? nd.x : nd.y);
+				else mode = FM_SPLIT;                       // park: split (or a non-axial node) is done by a gang
+			}
+			// one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393
+			if (mode == FM_LEAF) {
+				const float4 e0 = __ldg(&fm.stream[2 * L.k]);
+				const float4 e1 = __ldg(&fm.stream[2 * L.k + 1]);
+				L.k++;
+				const int b = __float_as_int(e1.w);
+				if (b < 0) {
+					mode = FM_POP;
+				} else {
+					if (COUNT) L.cBrushRefs++;
+					const bool want = (__float_as_int(e0.w) & h.mask) != 0 && b != L.last0 && b != L.last1;
+					const bool apart = L.hix < e0.x || L.hiy < e0.y || L.hiz < e0.z || L.lox > e1.x || L.loy > e1.y || L.loz > e1.z;
+					if (COUNT) L.cBrushBounds += want ? 1u : 0u;
+					if (want && !apart) { L.pend = b; mode = FM_BRUSH; }
+				}
+			}
+			// return to the pending far half of a split (the returns of the reference's recursion)
+			if (mode == FM_POP) {
+				if (L.sp == 0) {
+					mode = FM_DONE;
+				} else {
+					const FastSeg s = stack[--L.sp];
+					if (!(L.fraction <= s.f1)) {                // cm_trace.c:449: already hit something nearer
+						L.f1 = s.f1; L.f2 = s.f2;
+						L.ax = s.ax; L.ay = s.ay; L.az = s.az; L.bx = s.bx; L.by = s.by; L.bz = s.bz;
+						mode = gotoChild<COUNT>(L, s.num);
+					}
+				}
+			}
+		}
+
+		// ---------------- a node that is not a plain axial descent, cm_trace.c:456-537 (heavy) -----------------
+		if (nSplit > 0 && nSplit >= gang) {
+			if (mode == FM_SPLIT) {
+				const int4 nd = __ldg(&fm.nodes[L.num]);
+				double t1, t2, off;
+				if (nd.z < 3) {
+					const float dist = __int_as_float(nd.w);
+					t1 = (double)(sel3(L.ax, L.ay, L.az, nd.z) - dist);      // float subtract, then widened
+					t2 = (double)(sel3(L.bx, L.by, L.bz, nd.z) - dist);
+					off = h.isPoint ? 0.0 : (double)sel3(h.p0[0], h.p0[1], h.p0[2], nd.z);
+				} else {
+					const float4 pl = __ldg(&fm.nodePlanes[L.num]);
+					t1 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.ax, L.ay, L.az) - (double)pl.w;
+					t2 = dotd((double)pl.x, (double)pl.y, (double)pl.z, L.bx, L.by, L.bz) - (double)pl.w;
+					off = h.isPoint ? 0.0 : 2048.0;
+				}
+				if (t1 >= off + 1 && t2 >= off + 1) {
+					mode = gotoChild<COUNT>(L, nd.x);
+				} else if (t1 < -off - 1 && t2 < -off - 1) {
+					mode = gotoChild<COUNT>(L, nd.y);
+				} else {
+					// branch-free form of the three cases t1<t2, t1>t2, t1==t2
+					const bool fwd = t1 < t2, eq = !(t1 < t2) && !(t1 > t2);
+					const float inv = (float)(1.0 / (eq ? 1.0 : (t1 - t2)));
+					const double nfar = fwd ? (t1 + off + kClipEps) : (t1 - off - kClipEps);
+					const double nnear = fwd ? (t1 - off + kClipEps) : (t1 + off + kClipEps);
+					float ffar = (float)(nfar * (double)inv);
+					float fnear = (float)(nnear * (double)inv);
+					if (eq) { fnear = 1.0f; ffar = 0.0f; }
+					if (fnear < 0) fnear = 0; else if (fnear > 1) fnear = 1;
+					if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
+					if (COUNT) L.cSplits++;
+					// the far half [mid(ffar), b] waits on the stack; the near half [a, mid(fnear)] goes on.
+					// split points are float lerps of the CURRENT segment (cm_trace.c:516-535) and are carried.
+					FastSeg far;
+					far.num = fwd ? nd.x : nd.y;
+					far.f1 = L.f1 + (L.f2 - L.f1) * ffar;
+					far.f2 = L.f2;
+					far.ax = L.ax + ffar * (L.bx - L.ax);
+					far.ay = L.ay + ffar * (L.by - L.ay);
+					far.az = L.az + ffar * (L.bz - L.az);
+					far.bx = L.bx; far.by = L.by; far.bz = L.bz;
+					far.pad0 = far.pad1 = far.pad2 = 0.0f;
+					const float midf = L.f1 + (L.f2 - L.f1) * fnear;
+					const float mx = L.ax + fnear * (L.bx - L.ax);
+					const float my = L.ay + fnear * (L.by - L.ay);
+					const float mz = L.az + fnear * (L.bz - L.az);
+					if (L.sp < kMaxDepth) stack[L.sp++] = far; else atomicOr(q.status, 1);
+					L.f2 = midf;
+					L.bx = mx; L.by = my; L.bz = mz;
+					mode = gotoChild<COUNT>(L, fwd ? nd.y : nd.x);
+				}
+			}
+		}
+
+		// ---------------- CM_TraceThroughBrush for the pending brush (heavy) -----
+		if (nBrush > 0 && nBrush >= gang) {
+			if (mode == FM_BRUSH) {
+				const int b = L.pend;
+				const bool over = clipBrushFast<COUNT>(fm, h, L, b);
+				L.last1 = L.last0; L.last0 = b;
+				mode = over ? FM_DONE : FM_LEAF;
+			}
+		}
+
+		// ---------------- position test: CM_PositionTest / CM_BoxLeafnums_r / CM_TestInLeaf / CM_TestBoxInBrush,
+		// cm_trace.c:83-226, cm_test.c:131-156.  The reference lists <= 1024 leafs and then tests them in list order;
+		// testing each leaf when it is found is the same sequence of tests.  Binned batches keep these items
+		// together (class 2), so whole warps run this block.
+		if (nPos > 0) {
+			if (mode == FM_PNODE) {
+				const int c = L.num;
+				if (c < 0) {
+					if (L.found >= kMaxPosLeafs) {
+						mode = FM_DONE;
+					} else {
+						L.found++;
+						L.k = -1 - c;
+						if (COUNT) L.cLeafs++;
+						mode = FM_PLEAF;
+					}
+				} else {
+					const int4 nd = __ldg(&fm.nodes[c]);
+					if (COUNT) L.cNodes++;
+					const float lox = L.lox - 1.0f, loy = L.loy - 1.0f, loz = L.loz - 1.0f;
+					const float hix = L.hix + 1.0f, hiy = L.hiy + 1.0f, hiz = L.hiz + 1.0f;
+					int s;
+					const float dist = __int_as_float(nd.w);
+					if (nd.z < 3) {                                    // BoxOnPlaneSide, q_math.c:724-758
+						if (dist <= sel3(lox, loy, loz, nd.z)) s = 1;
+						else if (dist >= sel3(hix, hiy, hiz, nd.z)) s = 2;
+						else s = 3;
+					} else {
+						const float4 pl = __ldg(&fm.nodePlanes[c]);
+						float a = 0.0f, bb = 0.0f;
+						if (pl.x < 0.0f) { bb = bb + pl.x * hix; a = a + pl.x * lox; } else { a = a + pl.x * hix; bb = bb + pl.x * lox; }
+						if (pl.y < 0.0f) { bb = bb + pl.y * hiy; a = a + pl.y * loy; } else { a = a + pl.y * hiy; bb = bb + pl.y * loy; }
+						if (pl.z < 0.0f) { bb = bb + pl.z * hiz; a = a + pl.z * loz; } else { a = a + pl.z * hiz; bb = bb + pl.z * loz; }
+						s = 0;
+						if (a >= dist) s = 1;
+						if (bb < dist) s |= 2;
+					}
+					if (s == 1) {
+						L.num = nd.x;
+					} else if (s == 2) {
+						L.num = nd.y;
+					} else {
+						if (L.sp < kMaxDepth) stack[L.sp++].num = nd.y; else atomicOr(q.status, 1);
+						L.num = nd.x;
+					}
+				}
+			} else if (mode == FM_PLEAF) {
+				const float4 e0 = __ldg(&fm.stream[2 * L.k]);
+				const float4 e1 = __ldg(&fm.stream[2 * L.k + 1]);
+				L.k++;
+				const int b = __float_as_int(e1.w);
+				if (b < 0) {
+					if (L.sp == 0) mode = FM_DONE;
+					else { L.num = stack[--L.sp].num; mode = FM_PNODE; }
+				} else {
+					if (COUNT) L.cBrushRefs++;
+					const int contents = __float_as_int(e0.w);
+					if (contents & h.mask) {
+						const float4 r0 = __ldg(&fm.brushRec[2 * b]);
+						const float4 r1 = __ldg(&fm.brushRec[2 * b + 1]);
+						const int firstSide = __float_as_int(r0.w);
+						const int ns = __float_as_int(r1.w) & 0xffffff;
+						if (ns > 0) {
+							if (COUNT) L.cBrushBounds++;
+							if (!(L.lox > r1.x || L.loy > r1.y || L.loz > r1.z || L.hix < r0.x || L.hiy < r0.y || L.hiz < r0.z)) {
+								bool inside = true;
+								for (int s = 6; s < ns; s++) {
+									const float4 pl = __ldg(&fm.sidePlanes[firstSide + s]);
+									if (COUNT) L.cBrushSides++;
+									const float cx = pl.x < 0.0f ? h.p0[0] : h.n0[0];
+									const float cy = pl.y < 0.0f ? h.p0[1] : h.n0[1];
+									const float cz = pl.z < 0.0f ? h.p0[2] : h.n0[2];
+									const float distf = pl.w - dotf(cx, cy, cz, pl.x, pl.y, pl.z);    // all-float (cm_trace.c:111)
+									const double d1 = dotd((double)L.sx, (double)L.sy, (double)L.sz, pl.x, pl.y, pl.z) - (double)distf;
+									if (d1 > 0) { inside = false; break; }
+								}
+								if (inside) {
+									L.solid = 3;
+									L.fraction = 0.0f;
+									L.contents = contents;
+									L.hitId = b;
+									mode = FM_DONE;
+								}
+							}
+						}
+					}
+				}
+			}
+		}
+	}
+}
+
+}  // namespace cmgpu

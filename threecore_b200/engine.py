@@ -110,6 +110,7 @@ def load_library() -> C.CDLL:
     lib.cmgpu_clear.argtypes = [C.c_void_p]
     lib.cmgpu_set_cvars.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.cmgpu_num_inline_models.argtypes = [C.c_void_p]
+    lib.cmgpu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.cmgpu_launch_count.argtypes = [C.c_void_p]
     lib.cmgpu_launch_count.restype = C.c_ulonglong
     lib.cmgpu_enable_counters.argtypes = [C.c_void_p, C.c_int]
@@ -273,6 +274,10 @@ class Engine:
 
     def num_inline_models(self):
         return self.lib.cmgpu_num_inline_models(self.h)
+
+    def set_option(self, name: str, value: float):
+        """Tuning knobs of cmgpu_set_option (cm_gpu.h); none changes results."""
+        self._check(self.lib.cmgpu_set_option(self.h, name.encode(), float(value)))
 
     @property
     def launch_count(self) -> int:
