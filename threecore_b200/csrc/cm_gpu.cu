@@ -57,6 +57,8 @@ struct cmgpu_ctx_s {
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	bool useFast = true;
+	bool slabOK = false;                 // all brush bounds below 2^15 in magnitude
+	bool slabTest = true;
 	int gang = kGang;
 	int lightReps = 3;
 	// spatial binning of large batches (counting sort by start cell)
@@ -390,6 +392,8 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 				if (bb[3 + a] > hi[a]) hi[a] = bb[3 + a];
 			}
 		}
+		ctx->slabOK = true;
+		for (int a = 0; a < 3; a++) if (!(lo[a] > -32768.0f && hi[a] < 32768.0f)) ctx->slabOK = false;
 		BinGrid &g = ctx->grid;
 		int totalBits = 0;
 		for (int a = 0; a < 3; a++) {
@@ -441,7 +445,7 @@ int checkHandles(cmgpu_ctx *ctx, int n, const int32_t *models) {
 // nodeHi/nodeLo: CM_TraceThroughTree compares the float differences t1,t2 (widened) with the doubles
 // offset+1 and -offset-1 (cm_trace.c:483,487).  For a float t and a double x: t >= x <=> t >= RU(x) and
 // t < -x <=> t < -RD(x), RU/RD = x rounded up/down to float; so the comparison can stay in float.
-FastHull makeFastHull(const float *mins, const float *maxs, int mask) {
+FastHull makeFastHull(const float *mins, const float *maxs, int mask, bool slabOK) {
 	FastHull h{};
 	bool point = true;
 	for (int a = 0; a < 3; a++) {
@@ -461,6 +465,7 @@ FastHull makeFastHull(const float *mins, const float *maxs, int mask) {
 		h.nodeLo[a] = -dn;
 	}
 	h.mask = mask;
+	h.slabOK = slabOK ? 1 : 0;
 	return h;
 }
 
@@ -513,7 +518,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	if (blocks > resident) blocks = resident;
 	if (blocks < 1) blocks = 1;
 	if (fast) {
-		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask);
+		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
 		if (ctx->counting) traceFastKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
 		else               traceFastKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
 	} else {
@@ -657,6 +662,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "bin_cell") { if (!(value > 1.0)) return fail(ctx, CMGPU_ERR_INVALID, "bin_cell must be > 1"); ctx->binCell = (float)value; }
 	else if (k == "bin_long_len") ctx->binLongLen = (float)value;
 	else if (k == "fast") ctx->useFast = value != 0;
+	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
 	else if (k == "light_reps") ctx->lightReps = value < 1 ? 1 : (int)value;
 	else return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_set_option: unknown option '%s'", name);

@@ -41,6 +41,7 @@ struct FastHull {
 	float nodeHi[3], nodeLo[3];  // t >= offset+1  <=>  t >= nodeHi ;  t < -offset-1  <=>  t < nodeLo   (t float)
 	int   isPoint;
 	int   mask;
+	int   slabOK;                // every brush coordinate of the map is below 2^15 in magnitude
 };
 
 enum FastMode : int { FM_IDLE = 0, FM_NODE, FM_LEAF, FM_POP, FM_SPLIT, FM_BRUSH, FM_DONE, FM_PNODE, FM_PLEAF };
@@ -52,7 +53,7 @@ struct FastLane {
 	float sx, sy, sz, ex, ey, ez;        // tw.start / tw.end
 	float lox, loy, loz, hix, hiy, hiz;  // tw.bounds
 	float fraction;
-	int   solid;                         // bit0 allsolid, bit1 startsolid
+	int   solid;                         // bit0 allsolid, bit1 startsolid, bit2 slab pre-test allowed for this item
 	int   planeRef;                      // brush side whose plane / surfaceFlags the result carries, -1 none
 	int   contents, hitId;
 	int   num, sp;                       // tree cursor
@@ -70,13 +71,16 @@ __device__ __forceinline__ float rcpApprox(float x) {
 	return r;
 }
 
-// one side for the rejection pass: exact distances and flags, approximate quotient
+// one side of pass 1: exact distances and flags, approximate quotient.  The entering side with the largest
+// quotient is remembered together with the runner-up's quotient, so that a clear winner needs ONE exact division.
 struct ClipApprox {
 	bool so, go, miss, anyEnter;
-	float qe, ql;
+	float qe, q2, ql;          // largest / second largest entering quotient (clamped at 0), smallest leaving quotient (clamped at 1)
+	double bd1, bd2;           // distances of the side that owns qe
+	int bs;                    // its index
 };
 
-__device__ __forceinline__ void approxSide(ClipApprox &c, const double d1, const double d2) {
+__device__ __forceinline__ void approxSide(ClipApprox &c, const double d1, const double d2, const int s) {
 	c.go |= d2 > 0;
 	c.so |= d1 > 0;
 	c.miss |= d1 > 0 && (d2 >= kClipEps || d2 >= d1);
@@ -85,8 +89,33 @@ __device__ __forceinline__ void approxSide(ClipApprox &c, const double d1, const
 	const float numf = (float)(entering ? d1 - kClipEps : d1 + kClipEps);
 	const float denf = (float)(d1 - d2);
 	const float q = numf * rcpApprox(denf);
-	if (cross && entering) { c.anyEnter = true; c.qe = fmaxf(c.qe, fmaxf(q, 0.0f)); }
+	if (cross && entering) {
+		const float qc = fmaxf(q, 0.0f);
+		c.anyEnter = true;
+		if (qc > c.qe) { c.q2 = c.qe; c.qe = qc; c.bd1 = d1; c.bd2 = d2; c.bs = s; }
+		else c.q2 = fmaxf(c.q2, qc);
+	}
 	if (cross && !entering) c.ql = fminf(c.ql, fminf(q, 1.0f));
+}
+
+// Conservative float slab test of the sweep against a leaf entry (the brush box widened by BOUNDS_CLIP_EPSILON),
+// used to skip brushes that certainly leave the trace untouched: the start is certainly outside (so neither
+// startsolid nor allsolid) and enterFrac is certainly >= leaveFrac, or certainly >= trace.fraction
+// (cm_trace.c:352-353).  Why it is safe: the entry box widened by the hull contains the planes the reference
+// clips against (faces pushed out by the hull, then moved by SURFACE_CLIP_EPSILON = 1/8) with 1/8 to spare on every
+// side, and for |coordinates| < 2^15 all float error below (two roundings of a coordinate, rcp.approx, one
+// product) is < 0.05 units.  So the reference's enter fraction on the axis that gives tEnter is > tEnter and its
+// leave fraction on the axis that gives tLeave is < tLeave; tEnter > 0 means that side is really entered from
+// outside, tLeave < 1 means the end point really lies beyond that face.  NaNs (0 * inf on a parallel axis) drop
+// out of fminf/fmaxf and make the comparisons false: no rejection.
+__device__ __forceinline__ bool slabReject(const FastHull &h, const FastLane &L, const float4 e0, const float4 e1) {
+	const float ix = rcpApprox(L.ex - L.sx), iy = rcpApprox(L.ey - L.sy), iz = rcpApprox(L.ez - L.sz);
+	const float x0 = ((e0.x - h.p0[0]) - L.sx) * ix, x1 = ((e1.x + h.p0[0]) - L.sx) * ix;
+	const float y0 = ((e0.y - h.p0[1]) - L.sy) * iy, y1 = ((e1.y + h.p0[1]) - L.sy) * iy;
+	const float z0 = ((e0.z - h.p0[2]) - L.sz) * iz, z1 = ((e1.z + h.p0[2]) - L.sz) * iz;
+	const float tEnter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+	const float tLeave = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+	return tEnter > 0.0f && ((tEnter > tLeave && tLeave < 1.0f) || tEnter > L.fraction);
 }
 
 // CM_TraceThroughBrush (cm_trace.c:261-363) for brush b.  Returns true when the trace is over (fraction 0).
@@ -115,11 +144,12 @@ __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull 
 	// ---- pass 1: flags (exact) and quotients (approximate, used only to reject) ----
 	ClipApprox c;
 	c.so = c.go = c.miss = c.anyEnter = false;
-	c.qe = -1.0f; c.ql = 1.0f;
+	c.qe = -1.0f; c.q2 = -1.0f; c.ql = 1.0f;
+	c.bd1 = c.bd2 = 0.0; c.bs = -1;
 	int side = 0;
 	if (canonical) {
-		approxSide(c, a0, b0); approxSide(c, a1, b1); approxSide(c, a2, b2);
-		approxSide(c, a3, b3); approxSide(c, a4, b4); approxSide(c, a5, b5);
+		approxSide(c, a0, b0, 0); approxSide(c, a1, b1, 1); approxSide(c, a2, b2, 2);
+		approxSide(c, a3, b3, 3); approxSide(c, a4, b4, 4); approxSide(c, a5, b5, 5);
 		side = 6;
 		if (COUNT) L.cBrushSides += 6;
 	}
@@ -132,7 +162,7 @@ __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull 
 		const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
 		const double d1 = dotd(sx, sy, sz, pl.x, pl.y, pl.z) - dist;
 		const double d2 = dotd(ex, ey, ez, pl.x, pl.y, pl.z) - dist;
-		approxSide(c, d1, d2);
+		approxSide(c, d1, d2, side);
 	}
 	if (c.miss) return false;                       // wholly in front of one face
 	if (!c.so) {                                    // original point was inside the brush
@@ -147,20 +177,29 @@ __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull 
 		return false;
 	}
 	if (!c.anyEnter) return false;                  // enterFrac stays -1
-	{
+	float enter = -1.0f, leave = 1.0f;
+	int lead = -1;
+	bool decided = false;
+	if (c.qe >= 0.0f) {
 		// |q - f| <= 2^-21 |f| for every quotient (two conversions, rcp.approx, one product, the two roundings of
 		// the reference's own f); 2^-19 leaves a factor 4.  NaN/inf never satisfy a comparison below.
 		const float kRel = 1.9073486e-6f, kAbs = 1e-30f;
-		const float eLo = c.qe - (c.qe * kRel + kAbs);
-		const float lHi = c.ql + (fabsf(c.ql) * kRel + kAbs);
-		if (c.anyEnter && c.qe >= 0.0f) {
-			if (eLo > lHi) return false;            // enterFrac >= leaveFrac
-			if (eLo > L.fraction) return false;     // enterFrac >= trace.fraction
+		const float eLo = c.qe - (c.qe * kRel + kAbs), eHi = c.qe + (c.qe * kRel + kAbs);
+		const float lHi = c.ql + (fabsf(c.ql) * kRel + kAbs), lLo = c.ql - (fabsf(c.ql) * kRel + kAbs);
+		if (eLo > lHi) return false;                // enterFrac >= leaveFrac
+		if (eLo > L.fraction) return false;         // enterFrac >= trace.fraction
+		// a clear winner among the entering sides that clearly precedes every leaving side: one exact division
+		if (c.q2 < eLo - (c.qe * kRel + kAbs) && eHi < lLo) {
+			float f = (float)((c.bd1 - kClipEps) / (c.bd1 - c.bd2));
+			if (f < 0) f = 0.0f;
+			enter = f;
+			lead = c.bs;
+			decided = true;
+			if (COUNT) L.cCross++;
 		}
 	}
-	// ---- pass 2: the reference's own arithmetic ----
-	float enter = -1.0f, leave = 1.0f;
-	int lead = -1;
+	if (!decided) {
+	// ---- pass 2: the reference's own arithmetic for every side (ties, grazing sweeps) ----
 	auto cross = [&](const double d1, const double d2, const int s) {
 		const bool crossing = !(d1 <= 0 && d2 <= 0);
 		const bool entering = d1 > d2;
@@ -188,6 +227,7 @@ __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull 
 		const double d1 = dotd(sx, sy, sz, pl.x, pl.y, pl.z) - dist;
 		const double d2 = dotd(ex, ey, ez, pl.x, pl.y, pl.z) - dist;
 		cross(d1, d2, side);
+	}
 	}
 	if (enter < leave && enter > -1 && enter < L.fraction) {
 		if (enter < 0) enter = 0;
@@ -221,6 +261,11 @@ __device__ __forceinline__ int beginFast(const TraceBatch &q, const FastHull &h,
 	if (L.sx < L.ex) { L.lox = L.sx + h.n0[0]; L.hix = L.ex + h.p0[0]; } else { L.lox = L.ex + h.n0[0]; L.hix = L.sx + h.p0[0]; }
 	if (L.sy < L.ey) { L.loy = L.sy + h.n0[1]; L.hiy = L.ey + h.p0[1]; } else { L.loy = L.ey + h.n0[1]; L.hiy = L.sy + h.p0[1]; }
 	if (L.sz < L.ez) { L.loz = L.sz + h.n0[2]; L.hiz = L.ez + h.p0[2]; } else { L.loz = L.ez + h.n0[2]; L.hiz = L.sz + h.p0[2]; }
+	// the float slab test is only trusted for coordinates below 2^15 (see slabReject)
+	{
+		const float big = fmaxf(fmaxf(fmaxf(fabsf(L.lox), fabsf(L.loy)), fmaxf(fabsf(L.loz), fabsf(L.hix))), fmaxf(fabsf(L.hiy), fabsf(L.hiz)));
+		if (h.slabOK && big < 32768.0f) L.solid |= 4;
+	}
 	L.num = 0; L.f1 = 0.0f; L.f2 = 1.0f;
 	L.ax = L.sx; L.ay = L.sy; L.az = L.sz; L.bx = L.ex; L.by = L.ey; L.bz = L.ez;
 	if (s0x == e0x && s0y == e0y && s0z == e0z) return FM_PNODE;     // position test (cm_trace.c:641-646)
@@ -290,7 +335,7 @@ __device__ __forceinline__ int gotoChild(FastLane &L, const int c) {
 }
 
 #ifndef CMGPU_FAST_MIN_BLOCKS
-#define CMGPU_FAST_MIN_BLOCKS 5
+#define CMGPU_FAST_MIN_BLOCKS 8
 #endif
 
 template <bool COUNT>
@@ -352,7 +397,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 		// ---------------- light steps -----------------
 		#pragma unroll 1
 		for (int rep = 0; rep < q.lightReps; rep++) {
-			// one axial node of CM_TraceThroughTree, cm_trace.c:456-486
+			// ---------------- one axial node of CM_TraceThroughTree, cm_trace.c:456-486
 			if (mode == FM_NODE) {
 				const int4 nd = __ldg(&fm.nodes[L.num]);
 				if (COUNT) L.cNodes++;
@@ -367,7 +412,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (nd.z < 3 && (front || back)) mode = gotoChild<COUNT>(L, front ? nd.x : nd.y);
 				else mode = FM_SPLIT;                       // park: split (or a non-axial node) is done by a gang
 			}
-			// one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393
+			// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393
 			if (mode == FM_LEAF) {
 				const float4 e0 = __ldg(&fm.stream[2 * L.k]);
 				const float4 e1 = __ldg(&fm.stream[2 * L.k + 1]);
@@ -380,10 +425,12 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const bool want = (__float_as_int(e0.w) & h.mask) != 0 && b != L.last0 && b != L.last1;
 					const bool apart = L.hix < e0.x || L.hiy < e0.y || L.hiz < e0.z || L.lox > e1.x || L.loy > e1.y || L.loz > e1.z;
 					if (COUNT) L.cBrushBounds += want ? 1u : 0u;
-					if (want && !apart) { L.pend = b; mode = FM_BRUSH; }
+					if (want && !apart) {
+						if (!((L.solid & 4) && slabReject(h, L, e0, e1))) { L.pend = b; mode = FM_BRUSH; }
+					}
 				}
 			}
-			// return to the pending far half of a split (the returns of the reference's recursion)
+			// ---------------- return to the pending far half of a split (the returns of the reference's recursion)
 			if (mode == FM_POP) {
 				if (L.sp == 0) {
 					mode = FM_DONE;
