@@ -60,10 +60,12 @@ struct cmgpu_ctx_s {
 	bool slabOK = false;                 // all brush bounds below 2^15 in magnitude
 	bool slabTest = true;
 	int gang = kGang;
+	int gangFetch = kGang;
 	int lightReps = 3;
 	// spatial binning of large batches (counting sort by start cell)
 	BinGrid grid{};
 	bool binning = true;
+	bool binDir = false;
 	int binMinItems = 1 << 15;           // smaller batches are traced in input order
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bHist[kBinSlots];
@@ -417,7 +419,8 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 			g.inv[a] = (float)g.cells[a] / ext;
 		}
 		g.longLen2 = ctx->binLongLen * ctx->binLongLen;
-		g.numBins = kBinClasses * g.cells[0] * g.cells[1] * g.cells[2];
+		g.dirBins = ctx->binDir ? 8 : 1;
+		g.numBins = kBinClasses * g.cells[0] * g.cells[1] * g.cells[2] * g.dirBins;
 	}
 	m.numNodes = f->numNodes;
 	m.numModels = f->numModels;
@@ -508,6 +511,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	// kChunk items at a time from a cursor that must be zero at launch
 	q.cursor = ctx->dCursor + (ctx->cursorSlot++ % kCursorSlots);
 	q.gang = ctx->gang;
+	q.gangFetch = ctx->gangFetch;
 	q.lightReps = ctx->lightReps;
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
@@ -661,9 +665,11 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "bin_min_items") ctx->binMinItems = value < 1 ? 1 : (int)value;
 	else if (k == "bin_cell") { if (!(value > 1.0)) return fail(ctx, CMGPU_ERR_INVALID, "bin_cell must be > 1"); ctx->binCell = (float)value; }
 	else if (k == "bin_long_len") ctx->binLongLen = (float)value;
+	else if (k == "bin_dir") ctx->binDir = value != 0;
 	else if (k == "fast") ctx->useFast = value != 0;
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
+	else if (k == "gang_fetch") ctx->gangFetch = (int)value;
 	else if (k == "light_reps") ctx->lightReps = value < 1 ? 1 : (int)value;
 	else return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_set_option: unknown option '%s'", name);
 	return CMGPU_OK;

@@ -87,6 +87,7 @@ struct TraceBatch {
 	int *status;                         // device status word
 	int *cursor;                         // work cursor, zero at launch
 	int gang;                            // lanes that must gather before a heavy block runs
+	int gangFetch;                       // ... before finished lanes write their records and take new items (hot kernel)
 	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
 	Counters *counters;                  // only touched by the counting variant
 	const float4 *recs;                  // binned batch: [2*slot] start.xyz + item bits, [2*slot+1] end.xyz + 0; null = input order
@@ -101,7 +102,8 @@ struct BinGrid {
 	int   cells[3];                      // cells per axis (powers of two)
 	int   bits[3];
 	float longLen2;                      // sweeps longer than this form their own class
-	int   numBins;                       // classes * cells
+	int   numBins;                       // classes * cells * direction bins
+	int   dirBins;                       // 1, or 8: octant of the sweep direction
 };
 constexpr int kBinClasses = 4;           // 0 short sweep, 1 long sweep, 2 position test (start == end), 3 inline model / temp box
 
@@ -1067,7 +1069,9 @@ __device__ __forceinline__ unsigned binOf(const BinGrid &g, float sx, float sy, 
 	if (model) cls = 3;
 	else if (sx == ex && sy == ey && sz == ez) cls = 2;
 	else cls = (dx * dx + dy * dy + dz * dz > g.longLen2) ? 1 : 0;
-	return (unsigned)cls * (unsigned)(g.cells[0] * g.cells[1] * g.cells[2]) + key;
+	key += (unsigned)cls * (unsigned)(g.cells[0] * g.cells[1] * g.cells[2]);
+	if (g.dirBins == 8) key = key * 8u + ((dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u));
+	return key;
 }
 
 // pass 1: bin of every item + histogram

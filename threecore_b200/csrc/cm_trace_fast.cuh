@@ -322,15 +322,31 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 	}
 }
 
+#ifndef CMGPU_PREFETCH
+#define CMGPU_PREFETCH 0
+#endif
+#ifndef CMGPU_ORDER
+#define CMGPU_ORDER 1
+#endif
+
+// the record a lane will need at its next step, asked for one scheduler round early
+__device__ __forceinline__ void prefetchL1(const void *p) {
+#if CMGPU_PREFETCH
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#endif
+}
+
 // follow a child reference: a node, or the stream of a leaf
 template <bool COUNT>
-__device__ __forceinline__ int gotoChild(FastLane &L, const int c) {
+__device__ __forceinline__ int gotoChild(const FastMap &fm, FastLane &L, const int c) {
 	if (c < 0) {
 		L.k = -1 - c;
+		prefetchL1(&fm.stream[2 * L.k]);
 		if (COUNT) L.cLeafs++;
 		return FM_LEAF;
 	}
 	L.num = c;
+	prefetchL1(&fm.nodes[c]);
 	return FM_NODE;
 }
 
@@ -368,7 +384,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 		{
 			const int nWant = nDone + (supply ? nIdle : 0);
 			if (nIdle == 32 && !supply) break;
-			if (nWant > 0 && nWant >= gang) {
+			if (nWant > 0 && nWant >= min(q.gangFetch, nLight)) {
 				if (mode == FM_DONE) {
 					finishFast<COUNT>(fm, q, L);
 					mode = FM_IDLE;
@@ -397,25 +413,22 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 		// ---------------- light steps -----------------
 		#pragma unroll 1
 		for (int rep = 0; rep < q.lightReps; rep++) {
-			// ---------------- one axial node of CM_TraceThroughTree, cm_trace.c:456-486
+			// Every lane first ASKS for the record its step needs (node, leaf entry or pending segment -- a lane is in
+			// one mode, so the three share registers), then the steps run: the three latencies overlap instead of
+			// following each other.
+			float4 t0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t1 = t0, t2 = t0;
 			if (mode == FM_NODE) {
-				const int4 nd = __ldg(&fm.nodes[L.num]);
-				if (COUNT) L.cNodes++;
-				const bool ax0 = nd.z == 0, ax1 = nd.z == 1;
-				const float dist = __int_as_float(nd.w);
-				const float t1 = (ax0 ? L.ax : (ax1 ? L.ay : L.az)) - dist;
-				const float t2 = (ax0 ? L.bx : (ax1 ? L.by : L.bz)) - dist;
-				const float hi = ax0 ? h.nodeHi[0] : (ax1 ? h.nodeHi[1] : h.nodeHi[2]);
-				const float lo = ax0 ? h.nodeLo[0] : (ax1 ? h.nodeLo[1] : h.nodeLo[2]);
-				const bool front = t1 >= hi && t2 >= hi;
-				const bool back = t1 < lo && t2 < lo;
-				if (nd.z < 3 && (front || back)) mode = gotoChild<COUNT>(L, front ? nd.x : nd.y);
-				else mode = FM_SPLIT;                       // park: split (or a non-axial node) is done by a gang
+				t0 = __ldg(reinterpret_cast<const float4 *>(&fm.nodes[L.num]));
+			} else if (mode == FM_LEAF) {
+				t0 = __ldg(&fm.stream[2 * L.k]);
+				t1 = __ldg(&fm.stream[2 * L.k + 1]);
+			} else if (mode == FM_POP && L.sp > 0) {
+				const float4 *sp4 = reinterpret_cast<const float4 *>(&stack[L.sp - 1]);
+				t0 = sp4[0]; t1 = sp4[1]; t2 = sp4[2];
 			}
 			// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393
 			if (mode == FM_LEAF) {
-				const float4 e0 = __ldg(&fm.stream[2 * L.k]);
-				const float4 e1 = __ldg(&fm.stream[2 * L.k + 1]);
+				const float4 e0 = t0, e1 = t1;
 				L.k++;
 				const int b = __float_as_int(e1.w);
 				if (b < 0) {
@@ -431,17 +444,32 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				}
 			}
 			// ---------------- return to the pending far half of a split (the returns of the reference's recursion)
-			if (mode == FM_POP) {
+			else if (mode == FM_POP) {
 				if (L.sp == 0) {
 					mode = FM_DONE;
 				} else {
-					const FastSeg s = stack[--L.sp];
-					if (!(L.fraction <= s.f1)) {                // cm_trace.c:449: already hit something nearer
-						L.f1 = s.f1; L.f2 = s.f2;
-						L.ax = s.ax; L.ay = s.ay; L.az = s.az; L.bx = s.bx; L.by = s.by; L.bz = s.bz;
-						mode = gotoChild<COUNT>(L, s.num);
+					L.sp--;
+					if (!(L.fraction <= t0.y)) {                // cm_trace.c:449: already hit something nearer
+						L.f1 = t0.y; L.f2 = t0.z;
+						L.ax = t0.w; L.ay = t1.x; L.az = t1.y; L.bx = t1.z; L.by = t1.w; L.bz = t2.x;
+						mode = gotoChild<COUNT>(fm, L, __float_as_int(t0.x));
 					}
 				}
+			}
+			// ---------------- one axial node of CM_TraceThroughTree, cm_trace.c:456-486
+			else if (mode == FM_NODE) {
+				const int4 nd = make_int4(__float_as_int(t0.x), __float_as_int(t0.y), __float_as_int(t0.z), __float_as_int(t0.w));
+				if (COUNT) L.cNodes++;
+				const bool ax0 = nd.z == 0, ax1 = nd.z == 1;
+				const float dist = __int_as_float(nd.w);
+				const float t1v = (ax0 ? L.ax : (ax1 ? L.ay : L.az)) - dist;
+				const float t2v = (ax0 ? L.bx : (ax1 ? L.by : L.bz)) - dist;
+				const float hi = ax0 ? h.nodeHi[0] : (ax1 ? h.nodeHi[1] : h.nodeHi[2]);
+				const float lo = ax0 ? h.nodeLo[0] : (ax1 ? h.nodeLo[1] : h.nodeLo[2]);
+				const bool front = t1v >= hi && t2v >= hi;
+				const bool back = t1v < lo && t2v < lo;
+				if (nd.z < 3 && (front || back)) mode = gotoChild<COUNT>(fm, L, front ? nd.x : nd.y);
+				else mode = FM_SPLIT;                       // park: split (or a non-axial node) is done by a gang
 			}
 		}
 
@@ -462,9 +490,9 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					off = h.isPoint ? 0.0 : 2048.0;
 				}
 				if (t1 >= off + 1 && t2 >= off + 1) {
-					mode = gotoChild<COUNT>(L, nd.x);
+					mode = gotoChild<COUNT>(fm, L, nd.x);
 				} else if (t1 < -off - 1 && t2 < -off - 1) {
-					mode = gotoChild<COUNT>(L, nd.y);
+					mode = gotoChild<COUNT>(fm, L, nd.y);
 				} else {
 					// branch-free form of the three cases t1<t2, t1>t2, t1==t2
 					const bool fwd = t1 < t2, eq = !(t1 < t2) && !(t1 > t2);
@@ -495,7 +523,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					if (L.sp < kMaxDepth) stack[L.sp++] = far; else atomicOr(q.status, 1);
 					L.f2 = midf;
 					L.bx = mx; L.by = my; L.bz = mz;
-					mode = gotoChild<COUNT>(L, fwd ? nd.y : nd.x);
+					mode = gotoChild<COUNT>(fm, L, fwd ? nd.y : nd.x);
 				}
 			}
 		}
