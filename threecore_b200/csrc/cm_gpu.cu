@@ -29,7 +29,7 @@ thread_local std::string g_createError;
 
 constexpr int kCursorSlots = 64;
 constexpr int kBinSlots = 3;             // histogram tables, one per pipeline stream
-constexpr int kPipeChunks = 8;           // host batches are split so copies overlap the kernel
+constexpr int kPipeChunks = 64;          // upper bound on the pieces a host batch is cut into (copies overlap the kernels)
 constexpr size_t kMinChunkItems = 1 << 16;
 
 struct DevBuf {
@@ -57,6 +57,7 @@ struct cmgpu_ctx_s {
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	bool useFast = true;
+	int pipeChunks = 32;                 // pieces a host batch is cut into
 	bool slabOK = false;                 // all brush bounds below 2^15 in magnitude
 	bool slabTest = true;
 	int gang = kGang;
@@ -69,9 +70,12 @@ struct cmgpu_ctx_s {
 	int binMinItems = 1 << 15;           // smaller batches are traced in input order
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bHist[kBinSlots];
-	cudaEvent_t binDone = nullptr;       // the workspace above is free again once this has fired
-	cudaStream_t binStream = nullptr;    // stream of the device-pointer call that last used the workspace
-	bool binBusy = false;                // binDone has been recorded by such a call
+	DevBuf bStackArena[kBinSlots + 1];   // traversal stacks of the hot kernel: one per pipeline stream + one for device-pointer calls
+	// Device-pointer calls share one workspace (binning buffers, stack arena).  extDone fires when the last such
+	// launch has finished; a call on a different stream, or a host-pointer call, waits for it first.
+	cudaEvent_t extDone = nullptr;
+	cudaStream_t extStream = nullptr;
+	bool extBusy = false;
 	int *hStatus = nullptr;              // pinned
 	unsigned long long launches = 0;
 	cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
@@ -476,18 +480,18 @@ FastHull makeFastHull(const float *mins, const float *maxs, int mask, bool slabO
 // every chunk its own range); histSlot: which histogram table to use (one per pipeline stream).
 int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1) {
 	if (q.n <= 0) return CMGPU_OK;
+	const int arenaSlot = histSlot < 0 ? kBinSlots : histSlot;
+	const bool external = histSlot < 0;              // device-pointer call on the caller's stream
+	if (external && ctx->extBusy && ctx->extStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->extDone, 0));
 	ctx->map.noCurves = ctx->noCurves;
 	ctx->map.playerCurveClip = ctx->playerCurveClip;
 	if (ctx->binning && q.n >= ctx->binMinItems) {
 		int rc;
-		const bool external = histSlot < 0;          // device-pointer call on the caller's stream
 		if (external) {
 			histSlot = 0;
 			wsOffset = 0;
 			if ((rc = reserve(ctx, ctx->bKeys, (size_t)q.n * 4))) return rc;
 			if ((rc = reserve(ctx, ctx->bRecs, (size_t)q.n * 32))) return rc;
-			// a launch on another stream may still be reading the workspace
-			if (ctx->binBusy && ctx->binStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->binDone, 0));
 		}
 		const int numTiles = (ctx->grid.numBins + kScanTile - 1) / kScanTile;
 		if ((rc = reserve(ctx, ctx->bHist[histSlot], ((size_t)ctx->grid.numBins + (size_t)numTiles) * 4))) return rc;
@@ -504,8 +508,6 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		binScatterKernel<<<g256, 256, 0, s>>>(q.n, q.starts, q.ends, keys, hist, recs);
 		ctx->launches += 5;
 		q.recs = recs;
-		if (external) { ctx->binStream = s; ctx->binBusy = true; }
-		else ctx->binBusy = false;
 	}
 	// persistent kernel: as many CTAs as fit on the GPU (fewer for tiny batches), each warp pulls
 	// kChunk items at a time from a cursor that must be zero at launch
@@ -517,11 +519,20 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
 	const int resident = fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
-	const long long warpsWanted = ((long long)q.n + kChunk - 1) / kChunk;
+	// Items per cursor grab: kChunk for big batches; for small ones a share that spreads the batch over all
+	// resident warps (a warp works through its items 32 at a time, so a 256-item grab is ~1 ms of latency).
+	int chunk = (int)(((long long)q.n / ((long long)resident * (kBlock / 32) * 4)) / 32 * 32);
+	if (chunk < 32) chunk = 32;
+	if (chunk > kChunk) chunk = kChunk;
+	q.chunk = chunk;
+	const long long warpsWanted = ((long long)q.n + chunk - 1) / chunk;
 	long long blocks = (warpsWanted + (kBlock / 32) - 1) / (kBlock / 32);
 	if (blocks > resident) blocks = resident;
 	if (blocks < 1) blocks = 1;
 	if (fast) {
+		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * kMaxDepth * sizeof(FastSeg));
+		if (rcA) return rcA;
+		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
 		if (ctx->counting) traceFastKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
 		else               traceFastKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
@@ -531,7 +542,11 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
-	if (q.recs && ctx->binBusy) CUDA_TRY(ctx, cudaEventRecord(ctx->binDone, s));
+	if (external) {
+		CUDA_TRY(ctx, cudaEventRecord(ctx->extDone, s));
+		ctx->extStream = s;
+		ctx->extBusy = true;
+	}
 	return CMGPU_OK;
 }
 
@@ -582,7 +597,7 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 	bool ok = true;
 	for (auto &s : ctx->streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
 	for (auto &ev : ctx->evt) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
-	ok = ok && cudaEventCreateWithFlags(&ctx->binDone, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->extDone, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaMalloc(&ctx->dCounters, sizeof(Counters)) == cudaSuccess;
 	ok = ok && cudaMemset(ctx->dCounters, 0, sizeof(Counters)) == cudaSuccess;
 	ok = ok && cudaMalloc(&ctx->dStatus, sizeof(int)) == cudaSuccess;
@@ -618,8 +633,9 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	freeMap(ctx);
 	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
 	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit,
-	                  &ctx->bKeys, &ctx->bRecs, &ctx->bHist[0], &ctx->bHist[1], &ctx->bHist[2]}) releaseBuf(*b);
-	if (ctx->binDone) cudaEventDestroy(ctx->binDone);
+	                  &ctx->bKeys, &ctx->bRecs, &ctx->bHist[0], &ctx->bHist[1], &ctx->bHist[2],
+	                  &ctx->bStackArena[0], &ctx->bStackArena[1], &ctx->bStackArena[2], &ctx->bStackArena[3]}) releaseBuf(*b);
+	if (ctx->extDone) cudaEventDestroy(ctx->extDone);
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->dStatus) cudaFree(ctx->dStatus);
 	if (ctx->dCursor) cudaFree(ctx->dCursor);
@@ -667,6 +683,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "bin_long_len") ctx->binLongLen = (float)value;
 	else if (k == "bin_dir") ctx->binDir = value != 0;
 	else if (k == "fast") ctx->useFast = value != 0;
+	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
 	else if (k == "gang_fetch") ctx->gangFetch = (int)value;
@@ -840,14 +857,16 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	if (hit_ids && (rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
 	if (ctx->binning && N >= (size_t)ctx->binMinItems) {
 		if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
-		if (ctx->binBusy) CUDA_TRY(ctx, cudaEventSynchronize(ctx->binDone));   // an earlier device-pointer call
-		ctx->binBusy = false;
 		if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
 		if ((rc = reserve(ctx, ctx->bRecs, N * 32))) return rc;
 	}
 
+	if (ctx->extBusy) {                              // an earlier device-pointer call may still use the shared workspace
+		CUDA_TRY(ctx, cudaEventSynchronize(ctx->extDone));
+		ctx->extBusy = false;
+	}
 	int chunks = (int)((N + kMinChunkItems - 1) / kMinChunkItems);
-	if (chunks > kPipeChunks) chunks = kPipeChunks;
+	if (chunks > ctx->pipeChunks) chunks = ctx->pipeChunks;
 	if (chunks < 1) chunks = 1;
 	for (int c = 0; c < chunks; c++) {
 		const size_t lo = N * (size_t)c / (size_t)chunks, hi = N * (size_t)(c + 1) / (size_t)chunks;

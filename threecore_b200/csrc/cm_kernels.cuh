@@ -31,7 +31,7 @@
 namespace cmgpu {
 
 constexpr int    kBlock          = 128;     // threads per CTA of the trace kernel
-constexpr int    kChunk          = 256;     // items a warp takes from the global cursor at a time
+constexpr int    kChunk          = 256;     // most items a warp takes from the global cursor at a time (TraceBatch::chunk)
 constexpr int    kGang           = 4;       // lanes that must gather before a heavy block runs
 constexpr int    kMaxDepth       = 64;      // traversal stack entries per item (CMGPU_ERR_LIMIT beyond)
 constexpr int    kMaxPosLeafs    = 1024;    // MAX_POSITION_LEAFS, cm_trace.c:190
@@ -64,6 +64,7 @@ struct DevMap {
 	int playerCurveClip;
 };
 
+struct FastSeg;
 struct Counters {
 	unsigned long long traces, nodes, leafs, brushRefs, brushBounds, brushSides, crossings, splits,
 	                   patches, patchPlanes, facets;
@@ -86,10 +87,12 @@ struct TraceBatch {
 	int *hitIds;                         // may be null
 	int *status;                         // device status word
 	int *cursor;                         // work cursor, zero at launch
+	int chunk;                           // items a warp takes from the cursor at a time (multiple of 32)
 	int gang;                            // lanes that must gather before a heavy block runs
 	int gangFetch;                       // ... before finished lanes write their records and take new items (hot kernel)
 	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
 	Counters *counters;                  // only touched by the counting variant
+	struct FastSeg *stackArena;          // hot kernel: kMaxDepth entries per resident thread
 	const float4 *recs;                  // binned batch: [2*slot] start.xyz + item bits, [2*slot+1] end.xyz + 0; null = input order
 };
 
@@ -640,10 +643,10 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 			if (nNeed > 0 && nNeed >= min(q.gang, 32 - nNeed)) {
 				if (chunkNext >= chunkEnd && supply) {
 					int base = 0;
-					if (lane == 0) base = atomicAdd(q.cursor, kChunk);
+					if (lane == 0) base = atomicAdd(q.cursor, q.chunk);
 					base = __shfl_sync(0xffffffffu, base, 0);
 					if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
-					else { chunkNext = base; chunkEnd = min(base + kChunk, q.n); }
+					else { chunkNext = base; chunkEnd = min(base + q.chunk, q.n); }
 				}
 				if (chunkNext >= chunkEnd) {
 					if (need == 0xffffffffu) break;           // nothing in flight, nothing left

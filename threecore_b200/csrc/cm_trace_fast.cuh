@@ -359,7 +359,10 @@ __global__ void __launch_bounds__(kBlock, CMGPU_FAST_MIN_BLOCKS)
 traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned laneLt = (1u << lane) - 1u;
-	FastSeg stack[kMaxDepth];
+	// Pending far halves live in a global arena, one contiguous run of 48-byte entries per thread.  (A local array
+	// is interleaved word by word across the lanes of a warp: with a few lanes pushing at different depths every
+	// 48-byte entry cost twelve 32-byte sectors of L2 traffic; here it is two.)
+	FastSeg *const stack = q.stackArena + ((size_t)blockIdx.x * kBlock + threadIdx.x) * kMaxDepth;
 	FastLane L;
 	int mode = FM_IDLE;
 	int chunkNext = 0, chunkEnd = 0;     // warp-uniform
@@ -393,10 +396,10 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				const int nNeed = __popc(need);
 				if (chunkNext >= chunkEnd && supply) {
 					int base = 0;
-					if (lane == 0) base = atomicAdd(q.cursor, kChunk);
+					if (lane == 0) base = atomicAdd(q.cursor, q.chunk);
 					base = __shfl_sync(0xffffffffu, base, 0);
 					if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
-					else { chunkNext = base; chunkEnd = min(base + kChunk, q.n); }
+					else { chunkNext = base; chunkEnd = min(base + q.chunk, q.n); }
 				}
 				if (chunkNext < chunkEnd) {
 					if (mode == FM_IDLE) {
@@ -424,7 +427,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				t1 = __ldg(&fm.stream[2 * L.k + 1]);
 			} else if (mode == FM_POP && L.sp > 0) {
 				const float4 *sp4 = reinterpret_cast<const float4 *>(&stack[L.sp - 1]);
-				t0 = sp4[0]; t1 = sp4[1]; t2 = sp4[2];
+				t0 = __ldcg(&sp4[0]); t1 = __ldcg(&sp4[1]); t2 = __ldcg(&sp4[2]);
 			}
 			// ---------------- one brush entry of CM_TraceThroughLeaf, cm_trace.c:377-393
 			if (mode == FM_LEAF) {
@@ -515,12 +518,18 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					far.ay = L.ay + ffar * (L.by - L.ay);
 					far.az = L.az + ffar * (L.bz - L.az);
 					far.bx = L.bx; far.by = L.by; far.bz = L.bz;
-					far.pad0 = far.pad1 = far.pad2 = 0.0f;
 					const float midf = L.f1 + (L.f2 - L.f1) * fnear;
 					const float mx = L.ax + fnear * (L.bx - L.ax);
 					const float my = L.ay + fnear * (L.by - L.ay);
 					const float mz = L.az + fnear * (L.bz - L.az);
-					if (L.sp < kMaxDepth) stack[L.sp++] = far; else atomicOr(q.status, 1);
+					if (L.sp < kMaxDepth) {
+						float4 *sp4 = reinterpret_cast<float4 *>(&stack[L.sp++]);
+						__stcg(&sp4[0], make_float4(__int_as_float(far.num), far.f1, far.f2, far.ax));
+						__stcg(&sp4[1], make_float4(far.ay, far.az, far.bx, far.by));
+						__stcg(&sp4[2], make_float4(far.bz, 0.0f, 0.0f, 0.0f));
+					} else {
+						atomicOr(q.status, 1);
+					}
 					L.f2 = midf;
 					L.bx = mx; L.by = my; L.bz = mz;
 					mode = gotoChild<COUNT>(fm, L, fwd ? nd.y : nd.x);
@@ -580,7 +589,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					} else if (s == 2) {
 						L.num = nd.y;
 					} else {
-						if (L.sp < kMaxDepth) stack[L.sp++].num = nd.y; else atomicOr(q.status, 1);
+						if (L.sp < kMaxDepth) __stcg(&stack[L.sp++].num, nd.y); else atomicOr(q.status, 1);
 						L.num = nd.x;
 					}
 				}
@@ -591,7 +600,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				const int b = __float_as_int(e1.w);
 				if (b < 0) {
 					if (L.sp == 0) mode = FM_DONE;
-					else { L.num = stack[--L.sp].num; mode = FM_PNODE; }
+					else { L.num = __ldcg(&stack[--L.sp].num); mode = FM_PNODE; }
 				} else {
 					if (COUNT) L.cBrushRefs++;
 					const int contents = __float_as_int(e0.w);
