@@ -53,15 +53,14 @@ struct FastLane {
 	float sx, sy, sz, ex, ey, ez;        // tw.start / tw.end
 	float lox, loy, loz, hix, hiy, hiz;  // tw.bounds
 	float fraction;
-	int   solid;                         // bit0 allsolid, bit1 startsolid, bit2 slab pre-test allowed for this item
+	int   flags;                         // bit0 allsolid, bit1 startsolid, bit2 slab pre-test allowed for this item
 	int   planeRef;                      // brush side whose plane / surfaceFlags the result carries, -1 none
-	int   contents, hitId;
+	int   hitId;                         // brush that set the result (its contents are the result's contents), -1 none
 	int   num, sp;                       // tree cursor
 	float f1, f2, ax, ay, az, bx, by, bz;
 	int   k;                             // leaf stream cursor
-	int   pend;                          // brush waiting to be clipped
+	int   pend;                          // brush waiting to be clipped; position test: leafs seen so far
 	int   last0, last1;                  // brushes clipped most recently
-	int   found;                         // leafs seen by the position test
 	unsigned cNodes, cLeafs, cBrushRefs, cBrushBounds, cBrushSides, cCross, cSplits;
 };
 
@@ -118,6 +117,71 @@ __device__ __forceinline__ bool slabReject(const FastHull &h, const FastLane &L,
 	return tEnter > 0.0f && ((tEnter > tLeave && tLeave < 1.0f) || tEnter > L.fraction);
 }
 
+// distances of the start and end point to the two axial sides of one axis of a canonical brush:
+// side 2a   : normal -e_a, dist -mins[a], corner component size[1][a]  ->  d = -p - (size[1][a] - mins[a])
+// side 2a+1 : normal +e_a, dist  maxs[a], corner component size[0][a]  ->  d =  p - (maxs[a] - size[0][a])
+// (DotProductDP with a unit normal is exactly +-component; cm_trace.c:295-297)
+struct AxisDist { double a0, b0, a1, b1; };
+__device__ __forceinline__ AxisDist axisDist(const float s, const float e, const float mn, const float mx, const float n0, const float p0) {
+	const double dn = (double)p0 - (double)mn, dp = (double)mx - (double)n0;
+	AxisDist d;
+	d.a0 = -(double)s - dn; d.b0 = -(double)e - dn;
+	d.a1 = (double)s - dp;  d.b1 = (double)e - dp;
+	return d;
+}
+
+struct Sweep { float sx, sy, sz, ex, ey, ez; };
+struct EnterLeave { float enter, leave; int lead; };
+
+__device__ __forceinline__ void sideDist(const FastHull &h, const Sweep &L, const float4 pl, double &d1, double &d2) {
+	// tw.offsets[signbits]: the box corner that touches the plane first
+	const float cx = pl.x < 0.0f ? h.p0[0] : h.n0[0];
+	const float cy = pl.y < 0.0f ? h.p0[1] : h.n0[1];
+	const float cz = pl.z < 0.0f ? h.p0[2] : h.n0[2];
+	const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
+	d1 = dotd((double)L.sx, (double)L.sy, (double)L.sz, pl.x, pl.y, pl.z) - dist;
+	d2 = dotd((double)L.ex, (double)L.ey, (double)L.ez, pl.x, pl.y, pl.z) - dist;
+}
+
+// The reference's own arithmetic for every side of a brush that is known not to be missed and to be entered from
+// outside (cm_trace.c:291-332): enterFrac, leaveFrac and the lead side.  Rare (ties, grazing sweeps), kept out of line.
+__device__ __forceinline__ EnterLeave exactEnterLeave(const FastMap &fm, const FastHull &h, const Sweep L, const float4 r0, const float4 r1) {
+	const int firstSide = __float_as_int(r0.w);
+	const int ns = __float_as_int(r1.w) & 0xffffff;
+	const bool canonical = (__float_as_int(r1.w) >> 30) & 1;
+	float enter = -1.0f, leave = 1.0f;
+	int lead = -1;
+	auto cross = [&](const double d1, const double d2, const int s) {
+		const bool crossing = !(d1 <= 0 && d2 <= 0);
+		const bool entering = d1 > d2;
+		const double num = entering ? d1 - kClipEps : d1 + kClipEps;
+		const double den = crossing ? d1 - d2 : 1.0;
+		const float q = (float)(num / den);
+		const float fe = q < 0 ? 0.0f : q;
+		const float fl = q > 1 ? 1.0f : q;
+		if (crossing && entering && fe > enter) { enter = fe; lead = s; }
+		if (crossing && !entering && fl < leave) leave = fl;
+	};
+	int side = 0;
+	if (canonical) {
+		const AxisDist x = axisDist(L.sx, L.ex, r0.x, r1.x, h.n0[0], h.p0[0]);
+		cross(x.a0, x.b0, 0); cross(x.a1, x.b1, 1);
+		const AxisDist y = axisDist(L.sy, L.ey, r0.y, r1.y, h.n0[1], h.p0[1]);
+		cross(y.a0, y.b0, 2); cross(y.a1, y.b1, 3);
+		const AxisDist z = axisDist(L.sz, L.ez, r0.z, r1.z, h.n0[2], h.p0[2]);
+		cross(z.a0, z.b0, 4); cross(z.a1, z.b1, 5);
+		side = 6;
+	}
+	for (; side < ns; side++) {
+		double d1, d2;
+		sideDist(h, L, __ldg(&fm.sidePlanes[firstSide + side]), d1, d2);
+		cross(d1, d2, side);
+	}
+	EnterLeave r;
+	r.enter = enter; r.leave = leave; r.lead = lead;
+	return r;
+}
+
 // CM_TraceThroughBrush (cm_trace.c:261-363) for brush b.  Returns true when the trace is over (fraction 0).
 template <bool COUNT>
 __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull &h, FastLane &L, const int b) {
@@ -127,50 +191,36 @@ __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull 
 	const int ns = __float_as_int(r1.w) & 0xffffff;
 	const bool canonical = (__float_as_int(r1.w) >> 30) & 1;
 	if (ns == 0) return false;
-	const double sx = L.sx, sy = L.sy, sz = L.sz, ex = L.ex, ey = L.ey, ez = L.ez;
-	// the six axial sides straight from the bounds (canonical brushes):
-	// side 2a   : normal -e_a, dist -mins[a], corner component size[1][a]
-	// side 2a+1 : normal +e_a, dist  maxs[a], corner component size[0][a]
-	// (DotProductDP with a unit normal is exactly +-component)
-	double a0, b0, a1, b1, a2, b2, a3, b3, a4, b4, a5, b5;
-	if (canonical) {
-		const double dnx = (double)h.p0[0] - (double)r0.x, dpx = (double)r1.x - (double)h.n0[0];
-		const double dny = (double)h.p0[1] - (double)r0.y, dpy = (double)r1.y - (double)h.n0[1];
-		const double dnz = (double)h.p0[2] - (double)r0.z, dpz = (double)r1.z - (double)h.n0[2];
-		a0 = -sx - dnx; b0 = -ex - dnx; a1 = sx - dpx; b1 = ex - dpx;
-		a2 = -sy - dny; b2 = -ey - dny; a3 = sy - dpy; b3 = ey - dpy;
-		a4 = -sz - dnz; b4 = -ez - dnz; a5 = sz - dpz; b5 = ez - dpz;
-	}
-	// ---- pass 1: flags (exact) and quotients (approximate, used only to reject) ----
+	// ---- pass 1: flags (exact) and quotients (approximate: they only reject, or name a clear winner) ----
 	ClipApprox c;
 	c.so = c.go = c.miss = c.anyEnter = false;
 	c.qe = -1.0f; c.q2 = -1.0f; c.ql = 1.0f;
 	c.bd1 = c.bd2 = 0.0; c.bs = -1;
 	int side = 0;
 	if (canonical) {
-		approxSide(c, a0, b0, 0); approxSide(c, a1, b1, 1); approxSide(c, a2, b2, 2);
-		approxSide(c, a3, b3, 3); approxSide(c, a4, b4, 4); approxSide(c, a5, b5, 5);
+		const AxisDist x = axisDist(L.sx, L.ex, r0.x, r1.x, h.n0[0], h.p0[0]);
+		approxSide(c, x.a0, x.b0, 0); approxSide(c, x.a1, x.b1, 1);
+		const AxisDist y = axisDist(L.sy, L.ey, r0.y, r1.y, h.n0[1], h.p0[1]);
+		approxSide(c, y.a0, y.b0, 2); approxSide(c, y.a1, y.b1, 3);
+		const AxisDist z = axisDist(L.sz, L.ez, r0.z, r1.z, h.n0[2], h.p0[2]);
+		approxSide(c, z.a0, z.b0, 4); approxSide(c, z.a1, z.b1, 5);
 		side = 6;
 		if (COUNT) L.cBrushSides += 6;
 	}
+	Sweep sw;
+	sw.sx = L.sx; sw.sy = L.sy; sw.sz = L.sz; sw.ex = L.ex; sw.ey = L.ey; sw.ez = L.ez;
 	for (; side < ns && !c.miss; side++) {
-		const float4 pl = __ldg(&fm.sidePlanes[firstSide + side]);
+		double d1, d2;
+		sideDist(h, sw, __ldg(&fm.sidePlanes[firstSide + side]), d1, d2);
 		if (COUNT) L.cBrushSides++;
-		const float cx = pl.x < 0.0f ? h.p0[0] : h.n0[0];
-		const float cy = pl.y < 0.0f ? h.p0[1] : h.n0[1];
-		const float cz = pl.z < 0.0f ? h.p0[2] : h.n0[2];
-		const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
-		const double d1 = dotd(sx, sy, sz, pl.x, pl.y, pl.z) - dist;
-		const double d2 = dotd(ex, ey, ez, pl.x, pl.y, pl.z) - dist;
 		approxSide(c, d1, d2, side);
 	}
 	if (c.miss) return false;                       // wholly in front of one face
 	if (!c.so) {                                    // original point was inside the brush
-		L.solid |= 2;
+		L.flags |= 2;
 		if (!c.go) {
-			L.solid |= 1;
+			L.flags |= 1;
 			L.fraction = 0.0f;
-			L.contents = __ldg(&fm.brushContents[b]);
 			L.hitId = b;
 			return true;
 		}
@@ -199,41 +249,13 @@ __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull 
 		}
 	}
 	if (!decided) {
-	// ---- pass 2: the reference's own arithmetic for every side (ties, grazing sweeps) ----
-	auto cross = [&](const double d1, const double d2, const int s) {
-		const bool crossing = !(d1 <= 0 && d2 <= 0);
-		const bool entering = d1 > d2;
-		const double num = entering ? d1 - kClipEps : d1 + kClipEps;
-		const double den = crossing ? d1 - d2 : 1.0;
-		const float q = (float)(num / den);
-		if (COUNT) L.cCross += crossing ? 1u : 0u;
-		const float fe = q < 0 ? 0.0f : q;
-		const float fl = q > 1 ? 1.0f : q;
-		if (crossing && entering && fe > enter) { enter = fe; lead = s; }
-		if (crossing && !entering && fl < leave) leave = fl;
-	};
-	side = 0;
-	if (canonical) {
-		cross(a0, b0, 0); cross(a1, b1, 1); cross(a2, b2, 2);
-		cross(a3, b3, 3); cross(a4, b4, 4); cross(a5, b5, 5);
-		side = 6;
-	}
-	for (; side < ns; side++) {
-		const float4 pl = __ldg(&fm.sidePlanes[firstSide + side]);
-		const float cx = pl.x < 0.0f ? h.p0[0] : h.n0[0];
-		const float cy = pl.y < 0.0f ? h.p0[1] : h.n0[1];
-		const float cz = pl.z < 0.0f ? h.p0[2] : h.n0[2];
-		const double dist = (double)pl.w - dotd((double)cx, (double)cy, (double)cz, pl.x, pl.y, pl.z);
-		const double d1 = dotd(sx, sy, sz, pl.x, pl.y, pl.z) - dist;
-		const double d2 = dotd(ex, ey, ez, pl.x, pl.y, pl.z) - dist;
-		cross(d1, d2, side);
-	}
+		const EnterLeave r = exactEnterLeave(fm, h, sw, r0, r1);
+		enter = r.enter; leave = r.leave; lead = r.lead;
 	}
 	if (enter < leave && enter > -1 && enter < L.fraction) {
 		if (enter < 0) enter = 0;
 		L.fraction = enter;
 		if (lead >= 0) L.planeRef = firstSide + lead;
-		L.contents = __ldg(&fm.brushContents[b]);
 		L.hitId = b;
 	}
 	return L.fraction == 0.0f;
@@ -254,8 +276,8 @@ __device__ __forceinline__ int beginFast(const TraceBatch &q, const FastHull &h,
 	L.slot = slot;
 	L.sx = s0x + h.off[0]; L.sy = s0y + h.off[1]; L.sz = s0z + h.off[2];
 	L.ex = e0x + h.off[0]; L.ey = e0y + h.off[1]; L.ez = e0z + h.off[2];
-	L.solid = 0; L.fraction = 1.0f; L.planeRef = -1; L.contents = 0; L.hitId = -1;
-	L.sp = 0; L.found = 0; L.last0 = L.last1 = -1; L.pend = -1; L.k = 0;
+	L.flags = 0; L.fraction = 1.0f; L.planeRef = -1; L.hitId = -1;
+	L.sp = 0; L.last0 = L.last1 = -1; L.pend = 0; L.k = 0;
 	if (COUNT) L.cNodes = L.cLeafs = L.cBrushRefs = L.cBrushBounds = L.cBrushSides = L.cCross = L.cSplits = 0;
 	// swept bounds (cm_trace.c:628-636)
 	if (L.sx < L.ex) { L.lox = L.sx + h.n0[0]; L.hix = L.ex + h.p0[0]; } else { L.lox = L.ex + h.n0[0]; L.hix = L.sx + h.p0[0]; }
@@ -264,7 +286,7 @@ __device__ __forceinline__ int beginFast(const TraceBatch &q, const FastHull &h,
 	// the float slab test is only trusted for coordinates below 2^15 (see slabReject)
 	{
 		const float big = fmaxf(fmaxf(fmaxf(fabsf(L.lox), fabsf(L.loy)), fmaxf(fabsf(L.loz), fabsf(L.hix))), fmaxf(fabsf(L.hiy), fabsf(L.hiz)));
-		if (h.slabOK && big < 32768.0f) L.solid |= 4;
+		if (h.slabOK && big < 32768.0f) L.flags |= 4;
 	}
 	L.num = 0; L.f1 = 0.0f; L.f2 = 1.0f;
 	L.ax = L.sx; L.ay = L.sy; L.az = L.sz; L.bx = L.ex; L.by = L.ey; L.bz = L.ez;
@@ -292,6 +314,7 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 		pl = __ldg(&fm.sidePlanes[L.planeRef]);
 		meta = __ldg(&fm.sideMeta[L.planeRef]);
 	}
+	const int contents = L.hitId >= 0 ? __ldg(&fm.brushContents[L.hitId]) : 0;
 	float px, py, pz;
 	if (L.fraction == 1.0f) {
 		px = e0x; py = e0y; pz = e0z;
@@ -301,13 +324,13 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 		pz = s0z + L.fraction * (e0z - s0z);
 	}
 	uint2 *o = q.out + 7 * (size_t)i;
-	__stcs(&o[0], make_uint2((unsigned)(L.solid & 1), (unsigned)((L.solid >> 1) & 1)));
+	__stcs(&o[0], make_uint2((unsigned)(L.flags & 1), (unsigned)((L.flags >> 1) & 1)));
 	__stcs(&o[1], make_uint2(__float_as_uint(L.fraction), __float_as_uint(px)));
 	__stcs(&o[2], make_uint2(__float_as_uint(py), __float_as_uint(pz)));
 	__stcs(&o[3], make_uint2(__float_as_uint(pl.x), __float_as_uint(pl.y)));
 	__stcs(&o[4], make_uint2(__float_as_uint(pl.z), __float_as_uint(pl.w)));
 	__stcs(&o[5], make_uint2((unsigned)meta.y & 0xffffu, (unsigned)meta.x));
-	__stcs(&o[6], make_uint2((unsigned)L.contents, 0u));
+	__stcs(&o[6], make_uint2((unsigned)contents, 0u));
 	if (q.hitIds) q.hitIds[i] = L.hitId;
 	if (COUNT) {
 		Counters *c = q.counters;
@@ -442,7 +465,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const bool apart = L.hix < e0.x || L.hiy < e0.y || L.hiz < e0.z || L.lox > e1.x || L.loy > e1.y || L.loz > e1.z;
 					if (COUNT) L.cBrushBounds += want ? 1u : 0u;
 					if (want && !apart) {
-						if (!((L.solid & 4) && slabReject(h, L, e0, e1))) { L.pend = b; mode = FM_BRUSH; }
+						if (!((L.flags & 4) && slabReject(h, L, e0, e1))) { L.pend = b; mode = FM_BRUSH; }
 					}
 				}
 			}
@@ -555,10 +578,10 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			if (mode == FM_PNODE) {
 				const int c = L.num;
 				if (c < 0) {
-					if (L.found >= kMaxPosLeafs) {
+					if (L.pend >= kMaxPosLeafs) {
 						mode = FM_DONE;
 					} else {
-						L.found++;
+						L.pend++;
 						L.k = -1 - c;
 						if (COUNT) L.cLeafs++;
 						mode = FM_PLEAF;
@@ -624,9 +647,8 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 									if (d1 > 0) { inside = false; break; }
 								}
 								if (inside) {
-									L.solid = 3;
+									L.flags |= 3;
 									L.fraction = 0.0f;
-									L.contents = contents;
 									L.hitId = b;
 									mode = FM_DONE;
 								}
