@@ -348,6 +348,9 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 #ifndef CMGPU_PREFETCH
 #define CMGPU_PREFETCH 0
 #endif
+#ifndef CMGPU_PREFETCH_CHUNK
+#define CMGPU_PREFETCH_CHUNK 1
+#endif
 #ifndef CMGPU_ORDER
 #define CMGPU_ORDER 1
 #endif
@@ -422,7 +425,16 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					if (lane == 0) base = atomicAdd(q.cursor, q.chunk);
 					base = __shfl_sync(0xffffffffu, base, 0);
 					if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
-					else { chunkNext = base; chunkEnd = min(base + q.chunk, q.n); }
+					else {
+						chunkNext = base; chunkEnd = min(base + q.chunk, q.n);
+#if CMGPU_PREFETCH_CHUNK
+						// pull the chunk's ray records towards L2 while the lanes are still busy with the previous one
+						if (q.recs) {
+							for (int i = base + (int)lane * 4; i < chunkEnd; i += 128)
+								asm volatile("prefetch.global.L2 [%0];" :: "l"(&q.recs[2 * (size_t)i]));
+						}
+#endif
+					}
 				}
 				if (chunkNext < chunkEnd) {
 					if (mode == FM_IDLE) {
