@@ -213,6 +213,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count
+    eng.kernel_timing(True)                     # CUDA events around the trace kernel itself, on its launching stream
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
     evs[0].record()
@@ -223,6 +224,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     launches = eng.launch_count - launches0
+    trace_ms, trace_launches = eng.kernel_time_ms()
+    eng.kernel_timing(False)
     total_ms = evs[0].elapsed_time(evs[-1])
     kern_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -264,14 +267,16 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        kms = float(np.mean(kern_ms))
+        kms = trace_ms / max(trace_launches, 1)        # the dominant kernel alone
         achieved = BYTES_PER_TRACE * n / (kms * 1e-3) / 1e9
         tr = ncu_traffic()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                "kernel": "cmgpu::traceKernel<false>", "kernel_ms": kms,
-                "algorithmic_bytes_per_trace": BYTES_PER_TRACE,
-                "note": "irregular BSP walk: L2/latency bound by construction, HBM floor reported because the metric asks for it"}
+                "traffic": (tr or {}).get("dram_bytes_per_launch") if n == N_RAYS else None, "peak_source": peak_src,
+                "kernel": "cmgpu::traceFastKernel<false>", "kernel_ms": kms, "kernel_launches": trace_launches,
+                "step_ms": float(np.mean(kern_ms)),
+                "algorithmic_bytes_per_trace": BYTES_PER_TRACE, "traces_per_launch": n,
+                "note": "irregular BSP walk: bound by instruction issue and dependent-load latency, not by HBM; the HBM floor "
+                        "is reported because the metric asks for it (DESIGN.md 4.1)"}
         line = {"metric": METRIC, "value": value, "unit": "Mtraces/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",

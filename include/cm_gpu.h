@@ -203,6 +203,11 @@ int cmgpu_read_counters(cmgpu_ctx *ctx, cmgpu_counters *out, int reset);
 
 /* number of kernels this context has launched (for bench.py's gpu_launches) */
 unsigned long long cmgpu_launch_count(const cmgpu_ctx *ctx);
+/* CUDA-event timing of the trace kernel alone, on the stream it is launched on (the binning kernels that
+ * precede it are outside the bracket).  cmgpu_kernel_time_ms waits for the bracketed launches, returns the
+ * sum of their durations and how many there were, and starts a new measurement. */
+int cmgpu_kernel_timing(cmgpu_ctx *ctx, int enable);
+int cmgpu_kernel_time_ms(cmgpu_ctx *ctx, double *total_ms, int *launches);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus

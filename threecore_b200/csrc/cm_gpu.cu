@@ -7,6 +7,7 @@
 // code/qcommon/cm_load.c:734.
 #include "cm_kernels.cuh"
 #include "cm_trace_fast.cuh"
+#include "cm_trace_pool.cuh"
 #include "../../include/cm_gpu.h"
 
 #include <math.h>
@@ -28,6 +29,7 @@ namespace {
 thread_local std::string g_createError;
 
 constexpr int kCursorSlots = 64;
+constexpr size_t kPoolSmem = (size_t)(kBlock / 32) * PF_COUNT * CMGPU_POOL_K * 32 * sizeof(float);
 constexpr int kBinSlots = 3;             // histogram tables, one per pipeline stream
 constexpr int kPipeChunks = 64;          // upper bound on the pieces a host batch is cut into (copies overlap the kernels)
 constexpr size_t kMinChunkItems = 1 << 16;
@@ -54,10 +56,16 @@ struct cmgpu_ctx_s {
 	int cursorSlot = 0;
 	int gridPlain = 0, gridCount = 0;    // resident CTAs of the two kernel variants
 	int gridFast = 0, gridFastCount = 0;
+	int gridPool = 0, gridPoolCount = 0;
+	bool usePool = false;                // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	bool useFast = true;
 	int pipeChunks = 32;                 // pieces a host batch is cut into
+	// optional CUDA-event timing of the trace kernel alone (cmgpu_kernel_timing)
+	bool timing = false;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timingPairs;
+	size_t timingUsed = 0;
 	bool slabOK = false;                 // all brush bounds below 2^15 in magnitude
 	bool slabTest = true;
 	int gang = kGang;
@@ -518,10 +526,12 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
-	const int resident = fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
+	const bool pool = fast && ctx->usePool;
+	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
+	                   : fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
 	// Items per cursor grab: kChunk for big batches; for small ones a share that spreads the batch over all
 	// resident warps (a warp works through its items 32 at a time, so a 256-item grab is ~1 ms of latency).
-	int chunk = (int)(((long long)q.n / ((long long)resident * (kBlock / 32) * 4)) / 32 * 32);
+	int chunk = (int)(((long long)q.n / ((long long)resident * (kBlock / 32) * (pool ? CMGPU_POOL_K : 1) * 4)) / 32 * 32);
 	if (chunk < 32) chunk = 32;
 	if (chunk > kChunk) chunk = kChunk;
 	q.chunk = chunk;
@@ -529,7 +539,26 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	long long blocks = (warpsWanted + (kBlock / 32) - 1) / (kBlock / 32);
 	if (blocks > resident) blocks = resident;
 	if (blocks < 1) blocks = 1;
-	if (fast) {
+	cudaEvent_t tEnd = nullptr;
+	if (ctx->timing) {
+		if (ctx->timingUsed == ctx->timingPairs.size()) {
+			cudaEvent_t a, b;
+			CUDA_TRY(ctx, cudaEventCreate(&a));
+			CUDA_TRY(ctx, cudaEventCreate(&b));
+			ctx->timingPairs.push_back({a, b});
+		}
+		auto &pr = ctx->timingPairs[ctx->timingUsed++];
+		tEnd = pr.second;
+		CUDA_TRY(ctx, cudaEventRecord(pr.first, s));
+	}
+	if (pool) {
+		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * kPoolDepth * sizeof(FastSeg));
+		if (rcA) return rcA;
+		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
+		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
+		if (ctx->counting) tracePoolKernel<true, CMGPU_POOL_K><<<(int)blocks, kBlock, kPoolSmem, s>>>(ctx->fast, q, h);
+		else               tracePoolKernel<false, CMGPU_POOL_K><<<(int)blocks, kBlock, kPoolSmem, s>>>(ctx->fast, q, h);
+	} else if (fast) {
 		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * kMaxDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
 		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
@@ -542,6 +571,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
+	if (tEnd) CUDA_TRY(ctx, cudaEventRecord(tEnd, s));
 	if (external) {
 		CUDA_TRY(ctx, cudaEventRecord(ctx->extDone, s));
 		ctx->extStream = s;
@@ -590,6 +620,7 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 	ctx->device = device;
 	if (const char *g = getenv("CMGPU_GANG")) ctx->gang = atoi(g);   // tuning knobs
 	if (const char *g = getenv("CMGPU_LIGHT_REPS")) ctx->lightReps = atoi(g) > 0 ? atoi(g) : 1;
+	if (const char *g = getenv("CMGPU_POOL")) ctx->usePool = atoi(g) != 0;
 	if (const char *g = getenv("CMGPU_BIN")) ctx->binning = atoi(g) != 0;
 	if (const char *g = getenv("CMGPU_BIN_CELL")) ctx->binCell = atof(g) > 1.0 ? (float)atof(g) : 128.0f;
 	if (const char *g = getenv("CMGPU_BIN_LONG")) ctx->binLongLen = (float)atof(g);
@@ -616,6 +647,13 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFC, traceFastKernel<true>, kBlock, 0) == cudaSuccess && perSmFC > 0;
 		ctx->gridFast = perSmF * prop.multiProcessorCount;
 		ctx->gridFastCount = perSmFC * prop.multiProcessorCount;
+		int perSmP = 0, perSmPC = 0;
+		ok = ok && cudaFuncSetAttribute(tracePoolKernel<false, CMGPU_POOL_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
+		ok = ok && cudaFuncSetAttribute(tracePoolKernel<true, CMGPU_POOL_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmP, tracePoolKernel<false, CMGPU_POOL_K>, kBlock, kPoolSmem) == cudaSuccess && perSmP > 0;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPC, tracePoolKernel<true, CMGPU_POOL_K>, kBlock, kPoolSmem) == cudaSuccess && perSmPC > 0;
+		ctx->gridPool = perSmP * prop.multiProcessorCount;
+		ctx->gridPoolCount = perSmPC * prop.multiProcessorCount;
 	}
 	if (!ok) {
 		g_createError = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -636,6 +674,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	                  &ctx->bKeys, &ctx->bRecs, &ctx->bHist[0], &ctx->bHist[1], &ctx->bHist[2],
 	                  &ctx->bStackArena[0], &ctx->bStackArena[1], &ctx->bStackArena[2], &ctx->bStackArena[3]}) releaseBuf(*b);
 	if (ctx->extDone) cudaEventDestroy(ctx->extDone);
+	for (auto &pr : ctx->timingPairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->dStatus) cudaFree(ctx->dStatus);
 	if (ctx->dCursor) cudaFree(ctx->dCursor);
@@ -683,6 +722,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "bin_long_len") ctx->binLongLen = (float)value;
 	else if (k == "bin_dir") ctx->binDir = value != 0;
 	else if (k == "fast") ctx->useFast = value != 0;
+	else if (k == "pool") ctx->usePool = value != 0;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
@@ -741,6 +781,29 @@ int cmgpu_read_counters(cmgpu_ctx *ctx, cmgpu_counters *out, int reset) {
 }
 
 unsigned long long cmgpu_launch_count(const cmgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int cmgpu_kernel_timing(cmgpu_ctx *ctx, int enable) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	ctx->timing = enable != 0;
+	ctx->timingUsed = 0;
+	return CMGPU_OK;
+}
+
+int cmgpu_kernel_time_ms(cmgpu_ctx *ctx, double *total_ms, int *launches) {
+	if (!ctx || !total_ms) return CMGPU_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	double sum = 0.0;
+	for (size_t i = 0; i < ctx->timingUsed; i++) {
+		CUDA_TRY(ctx, cudaEventSynchronize(ctx->timingPairs[i].second));
+		float ms = 0.0f;
+		CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->timingPairs[i].first, ctx->timingPairs[i].second));
+		sum += ms;
+	}
+	*total_ms = sum;
+	if (launches) *launches = (int)ctx->timingUsed;
+	ctx->timingUsed = 0;
+	return CMGPU_OK;
+}
 
 int cmgpu_check_status(cmgpu_ctx *ctx, void *stream) {
 	if (!ctx) return CMGPU_ERR_INVALID;

@@ -1,0 +1,422 @@
+// cm_trace_pool.cuh -- the hot kernel, second cut: same steps as traceFastKernel (cm_trace_fast.cuh), other scheduling.
+//
+// traceFastKernel keeps ONE item per lane in registers; with six kinds of step in flight a block of code runs with
+// ~11 of 32 lanes on average, whatever the gang sizes (measured, and reproduced by a scheduling model over the
+// oracle's per-item step sequences).  Here every lane owns K items whose state lives in shared memory
+// (structure of arrays, [field][k][lane]: conflict-free, no cross-lane traffic, nothing shared between warps).  Each
+// round the warp votes for the step kind that the most lanes can run, and every lane that owns an item waiting for
+// that kind runs it on that item.  With K = 4 the same model gives 21-23 active lanes per instruction.
+//
+// Results are bit-identical to traceFastKernel: the step arithmetic is the same code.
+#pragma once
+
+#include "cm_trace_fast.cuh"
+
+namespace cmgpu {
+
+constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
+
+enum PoolMode : int { PM_EMPTY = 0, PM_DONE, PM_NODE, PM_LEAF, PM_POP, PM_SPLIT, PM_BRUSH, PM_PNODE, PM_PLEAF, PM_COUNT };
+
+// shared-memory fields of one item (32-bit words)
+enum PoolField : int {
+	PF_SLOT = 0, PF_SX, PF_SY, PF_SZ, PF_EX, PF_EY, PF_EZ, PF_FRACTION, PF_FLAGS /* flags | sp << 8 */, PF_PLANEREF, PF_HITID,
+	PF_CUR /* node number or leaf-stream cursor */, PF_F1, PF_F2, PF_AX, PF_AY, PF_AZ, PF_BX, PF_BY, PF_BZ,
+	PF_LAST0, PF_LAST1, PF_PEND /* brush waiting to be clipped; position test: leafs seen */, PF_COUNT
+};
+
+template <int K>
+__device__ __forceinline__ int firstInMode(const unsigned modes, const int m) {
+	int j = -1;
+	#pragma unroll
+	for (int i = K - 1; i >= 0; i--) if (((modes >> (4 * i)) & 15u) == (unsigned)m) j = i;
+	return j;
+}
+
+__device__ __forceinline__ unsigned withMode(const unsigned modes, const int j, const int m) {
+	return (modes & ~(15u << (4 * j))) | ((unsigned)m << (4 * j));
+}
+
+#ifndef CMGPU_POOL_K
+#define CMGPU_POOL_K 4
+#endif
+#ifndef CMGPU_POOL_MIN_BLOCKS
+#define CMGPU_POOL_MIN_BLOCKS 4
+#endif
+
+template <bool COUNT, int K>
+__global__ void __launch_bounds__(kBlock, CMGPU_POOL_MIN_BLOCKS)
+tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
+	extern __shared__ float poolMem[];
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned laneLt = (1u << lane) - 1u;
+	const int warpInBlock = threadIdx.x >> 5;
+	float *const P = poolMem + (size_t)warpInBlock * (PF_COUNT * K * 32) + lane;
+#define FLD(f, j) P[((f) * K + (j)) * 32]
+#define FLDI(f, j) __float_as_int(FLD(f, j))
+#define SETI(f, j, v) FLD(f, j) = __int_as_float(v)
+	const size_t globalWarp = (size_t)blockIdx.x * (kBlock / 32) + warpInBlock;
+	FastSeg *const arena = q.stackArena + ((globalWarp * K) * 32 + lane) * kPoolDepth;   // item j: + j * 32 * kPoolDepth
+#define STACK(j) (arena + (size_t)(j) * 32 * kPoolDepth)
+
+	unsigned modes = 0u;
+	#pragma unroll
+	for (int j = 0; j < K; j++) { modes |= (unsigned)PM_DONE << (4 * j); SETI(PF_SLOT, j, -1); }
+	int chunkNext = 0, chunkEnd = 0;     // warp-uniform
+	bool supply = true;                   // warp-uniform
+	unsigned cNodes = 0, cLeafs = 0, cBrushRefs = 0, cBrushBounds = 0, cBrushSides = 0, cCross = 0, cSplits = 0, cTraces = 0;
+
+	for (;;) {
+		// ---------------- vote: which kind of step can the most lanes run? ------------------
+		int bestM = 0, bestC = 0;
+		#pragma unroll
+		for (int m = 1; m < PM_COUNT; m++) {
+			const int c = __popc(__ballot_sync(0xffffffffu, firstInMode<K>(modes, m) >= 0));
+			if (c > bestC) { bestC = c; bestM = m; }
+		}
+		if (bestC == 0) break;                               // every slot empty
+
+		if (bestM == PM_DONE) {
+			// ---------------- write results, take new items (cm_trace.c:545-686) -----------------
+			const int j = firstInMode<K>(modes, PM_DONE);
+			if (j >= 0 && FLDI(PF_SLOT, j) >= 0) {
+				FastLane L;
+				L.slot = FLDI(PF_SLOT, j); L.fraction = FLD(PF_FRACTION, j); L.flags = FLDI(PF_FLAGS, j) & 0xff;
+				L.planeRef = FLDI(PF_PLANEREF, j); L.hitId = FLDI(PF_HITID, j);
+				L.cNodes = L.cLeafs = L.cBrushRefs = L.cBrushBounds = L.cBrushSides = L.cCross = L.cSplits = 0;
+				finishFast<false>(fm, q, L);
+				if (COUNT) cTraces++;
+			}
+			const unsigned need = __ballot_sync(0xffffffffu, j >= 0);
+			const int nNeed = __popc(need);
+			if (chunkNext >= chunkEnd && supply) {
+				int base = 0;
+				if (lane == 0) base = atomicAdd(q.cursor, q.chunk);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (base >= q.n) { supply = false; chunkNext = chunkEnd = 0; }
+				else {
+					chunkNext = base; chunkEnd = min(base + q.chunk, q.n);
+					if (q.recs) {
+						for (int i = base + (int)lane * 4; i < chunkEnd; i += 128)
+							asm volatile("prefetch.global.L2 [%0];" :: "l"(&q.recs[2 * (size_t)i]));
+					}
+				}
+			}
+			if (j >= 0) {
+				const int my = chunkNext + __popc(need & laneLt);
+				if (my < chunkEnd) {
+					FastLane L;
+					const int m = beginFast<false>(q, h, L, my);
+					SETI(PF_SLOT, j, L.slot);
+					FLD(PF_SX, j) = L.sx; FLD(PF_SY, j) = L.sy; FLD(PF_SZ, j) = L.sz;
+					FLD(PF_EX, j) = L.ex; FLD(PF_EY, j) = L.ey; FLD(PF_EZ, j) = L.ez;
+					FLD(PF_FRACTION, j) = 1.0f; SETI(PF_FLAGS, j, L.flags); SETI(PF_PLANEREF, j, -1); SETI(PF_HITID, j, -1);
+					SETI(PF_CUR, j, 0); FLD(PF_F1, j) = 0.0f; FLD(PF_F2, j) = 1.0f;
+					FLD(PF_AX, j) = L.sx; FLD(PF_AY, j) = L.sy; FLD(PF_AZ, j) = L.sz;
+					FLD(PF_BX, j) = L.ex; FLD(PF_BY, j) = L.ey; FLD(PF_BZ, j) = L.ez;
+					SETI(PF_LAST0, j, -1); SETI(PF_LAST1, j, -1); SETI(PF_PEND, j, 0);
+					modes = withMode(modes, j, m == FM_PNODE ? PM_PNODE : PM_NODE);
+				} else {
+					SETI(PF_SLOT, j, -1);                             // nothing to write back next time
+					if (!supply) modes = withMode(modes, j, PM_EMPTY); // else: stays PM_DONE and asks again
+				}
+			}
+			chunkNext = min(chunkNext + nNeed, chunkEnd);
+		} else if (bestM == PM_NODE) {
+			// ---------------- axial nodes of CM_TraceThroughTree, cm_trace.c:456-486 -----------------
+			#pragma unroll 1
+			for (int rep = 0; rep < q.lightReps; rep++) {
+				const int j = firstInMode<K>(modes, PM_NODE);
+				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
+				if (j >= 0) {
+					const int num = FLDI(PF_CUR, j);
+					const int4 nd = __ldg(&fm.nodes[num]);
+					if (COUNT) cNodes++;
+					const int ax = nd.z < 3 ? nd.z : 0;
+					const float dist = __int_as_float(nd.w);
+					const float t1 = FLD(PF_AX + ax, j) - dist;
+					const float t2 = FLD(PF_BX + ax, j) - dist;
+					const float hi = ax == 0 ? h.nodeHi[0] : (ax == 1 ? h.nodeHi[1] : h.nodeHi[2]);
+					const float lo = ax == 0 ? h.nodeLo[0] : (ax == 1 ? h.nodeLo[1] : h.nodeLo[2]);
+					const bool front = t1 >= hi && t2 >= hi;
+					const bool back = t1 < lo && t2 < lo;
+					if (nd.z < 3 && (front || back)) {
+						const int c = front ? nd.x : nd.y;
+						if (c < 0) { SETI(PF_CUR, j, -1 - c); modes = withMode(modes, j, PM_LEAF); if (COUNT) cLeafs++; }
+						else SETI(PF_CUR, j, c);
+					} else {
+						modes = withMode(modes, j, PM_SPLIT);
+					}
+				}
+			}
+		} else if (bestM == PM_LEAF) {
+			// ---------------- brush entries of CM_TraceThroughLeaf, cm_trace.c:377-393 -----------------
+			#pragma unroll 1
+			for (int rep = 0; rep < q.lightReps; rep++) {
+				const int j = firstInMode<K>(modes, PM_LEAF);
+				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
+				if (j >= 0) {
+					const int k = FLDI(PF_CUR, j);
+					const float4 e0 = __ldg(&fm.stream[2 * k]);
+					const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
+					SETI(PF_CUR, j, k + 1);
+					const int b = __float_as_int(e1.w);
+					if (b < 0) {
+						modes = withMode(modes, j, PM_POP);
+					} else {
+						if (COUNT) cBrushRefs++;
+						const bool want = (__float_as_int(e0.w) & h.mask) != 0 && b != FLDI(PF_LAST0, j) && b != FLDI(PF_LAST1, j);
+						if (COUNT) cBrushBounds += want ? 1u : 0u;
+						if (want) {
+							FastLane L;
+							L.sx = FLD(PF_SX, j); L.sy = FLD(PF_SY, j); L.sz = FLD(PF_SZ, j);
+							L.ex = FLD(PF_EX, j); L.ey = FLD(PF_EY, j); L.ez = FLD(PF_EZ, j);
+							// tw.bounds (cm_trace.c:628-636), recomputed instead of stored
+							const float lox = (L.sx < L.ex ? L.sx : L.ex) + h.n0[0], hix = (L.sx < L.ex ? L.ex : L.sx) + h.p0[0];
+							const float loy = (L.sy < L.ey ? L.sy : L.ey) + h.n0[1], hiy = (L.sy < L.ey ? L.ey : L.sy) + h.p0[1];
+							const float loz = (L.sz < L.ez ? L.sz : L.ez) + h.n0[2], hiz = (L.sz < L.ez ? L.ez : L.sz) + h.p0[2];
+							const bool apart = hix < e0.x || hiy < e0.y || hiz < e0.z || lox > e1.x || loy > e1.y || loz > e1.z;
+							if (!apart) {
+								L.fraction = FLD(PF_FRACTION, j);
+								if (!((FLDI(PF_FLAGS, j) & 4) && slabReject(h, L, e0, e1))) {
+									SETI(PF_PEND, j, b);
+									modes = withMode(modes, j, PM_BRUSH);
+								}
+							}
+						}
+					}
+				}
+			}
+		} else if (bestM == PM_POP) {
+			// ---------------- return to the pending far half of a split -----------------
+			const int j = firstInMode<K>(modes, PM_POP);
+			if (j >= 0) {
+				const int fl = FLDI(PF_FLAGS, j);
+				const int sp = fl >> 8;
+				if (sp == 0) {
+					modes = withMode(modes, j, PM_DONE);
+				} else {
+					const float4 *sp4 = reinterpret_cast<const float4 *>(&STACK(j)[sp - 1]);
+					const float4 t0 = __ldcg(&sp4[0]), t1 = __ldcg(&sp4[1]), t2 = __ldcg(&sp4[2]);
+					SETI(PF_FLAGS, j, fl - 256);
+					if (!(FLD(PF_FRACTION, j) <= t0.y)) {              // cm_trace.c:449: already hit something nearer
+						FLD(PF_F1, j) = t0.y; FLD(PF_F2, j) = t0.z;
+						FLD(PF_AX, j) = t0.w; FLD(PF_AY, j) = t1.x; FLD(PF_AZ, j) = t1.y;
+						FLD(PF_BX, j) = t1.z; FLD(PF_BY, j) = t1.w; FLD(PF_BZ, j) = t2.x;
+						const int c = __float_as_int(t0.x);
+						if (c < 0) { SETI(PF_CUR, j, -1 - c); modes = withMode(modes, j, PM_LEAF); if (COUNT) cLeafs++; }
+						else { SETI(PF_CUR, j, c); modes = withMode(modes, j, PM_NODE); }
+					}
+				}
+			}
+		} else if (bestM == PM_SPLIT) {
+			// ---------------- a node that is not a plain axial descent, cm_trace.c:456-537 -----------------
+			const int j = firstInMode<K>(modes, PM_SPLIT);
+			if (j >= 0) {
+				const int num = FLDI(PF_CUR, j);
+				const int4 nd = __ldg(&fm.nodes[num]);
+				const float ax_ = FLD(PF_AX, j), ay_ = FLD(PF_AY, j), az_ = FLD(PF_AZ, j);
+				const float bx_ = FLD(PF_BX, j), by_ = FLD(PF_BY, j), bz_ = FLD(PF_BZ, j);
+				const float f1 = FLD(PF_F1, j), f2 = FLD(PF_F2, j);
+				double t1, t2, off;
+				if (nd.z < 3) {
+					const float dist = __int_as_float(nd.w);
+					t1 = (double)(sel3(ax_, ay_, az_, nd.z) - dist);      // float subtract, then widened
+					t2 = (double)(sel3(bx_, by_, bz_, nd.z) - dist);
+					off = h.isPoint ? 0.0 : (double)sel3(h.p0[0], h.p0[1], h.p0[2], nd.z);
+				} else {
+					const float4 pl = __ldg(&fm.nodePlanes[num]);
+					t1 = dotd((double)pl.x, (double)pl.y, (double)pl.z, ax_, ay_, az_) - (double)pl.w;
+					t2 = dotd((double)pl.x, (double)pl.y, (double)pl.z, bx_, by_, bz_) - (double)pl.w;
+					off = h.isPoint ? 0.0 : 2048.0;
+				}
+				int c;
+				if (t1 >= off + 1 && t2 >= off + 1) {
+					c = nd.x;
+				} else if (t1 < -off - 1 && t2 < -off - 1) {
+					c = nd.y;
+				} else {
+					const bool fwd = t1 < t2, eq = !(t1 < t2) && !(t1 > t2);
+					const float inv = (float)(1.0 / (eq ? 1.0 : (t1 - t2)));
+					const double nfar = fwd ? (t1 + off + kClipEps) : (t1 - off - kClipEps);
+					const double nnear = fwd ? (t1 - off + kClipEps) : (t1 + off + kClipEps);
+					float ffar = (float)(nfar * (double)inv);
+					float fnear = (float)(nnear * (double)inv);
+					if (eq) { fnear = 1.0f; ffar = 0.0f; }
+					if (fnear < 0) fnear = 0; else if (fnear > 1) fnear = 1;
+					if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
+					if (COUNT) cSplits++;
+					const int fl = FLDI(PF_FLAGS, j);
+					const int sp = fl >> 8;
+					if (sp < kPoolDepth) {
+						float4 *sp4 = reinterpret_cast<float4 *>(&STACK(j)[sp]);
+						__stcg(&sp4[0], make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)));
+						__stcg(&sp4[1], make_float4(ay_ + ffar * (by_ - ay_), az_ + ffar * (bz_ - az_), bx_, by_));
+						__stcg(&sp4[2], make_float4(bz_, 0.0f, 0.0f, 0.0f));
+						SETI(PF_FLAGS, j, fl + 256);
+					} else {
+						atomicOr(q.status, 1);
+					}
+					FLD(PF_F2, j) = f1 + (f2 - f1) * fnear;
+					FLD(PF_BX, j) = ax_ + fnear * (bx_ - ax_);
+					FLD(PF_BY, j) = ay_ + fnear * (by_ - ay_);
+					FLD(PF_BZ, j) = az_ + fnear * (bz_ - az_);
+					c = fwd ? nd.y : nd.x;
+				}
+				if (c < 0) { SETI(PF_CUR, j, -1 - c); modes = withMode(modes, j, PM_LEAF); if (COUNT) cLeafs++; }
+				else { SETI(PF_CUR, j, c); modes = withMode(modes, j, PM_NODE); }
+			}
+		} else if (bestM == PM_BRUSH) {
+			// ---------------- CM_TraceThroughBrush for the pending brush, cm_trace.c:261-363 -----
+			const int j = firstInMode<K>(modes, PM_BRUSH);
+			if (j >= 0) {
+				FastLane L;
+				L.sx = FLD(PF_SX, j); L.sy = FLD(PF_SY, j); L.sz = FLD(PF_SZ, j);
+				L.ex = FLD(PF_EX, j); L.ey = FLD(PF_EY, j); L.ez = FLD(PF_EZ, j);
+				L.fraction = FLD(PF_FRACTION, j);
+				const int fl = FLDI(PF_FLAGS, j);
+				L.flags = fl & 0xff;
+				L.planeRef = FLDI(PF_PLANEREF, j); L.hitId = FLDI(PF_HITID, j);
+				L.cBrushSides = L.cCross = 0;
+				const int b = FLDI(PF_PEND, j);
+				const bool over = clipBrushFast<COUNT>(fm, h, L, b);
+				if (COUNT) { cBrushSides += L.cBrushSides; cCross += L.cCross; }
+				FLD(PF_FRACTION, j) = L.fraction;
+				SETI(PF_FLAGS, j, (fl & ~0xff) | L.flags);
+				SETI(PF_PLANEREF, j, L.planeRef); SETI(PF_HITID, j, L.hitId);
+				SETI(PF_LAST1, j, FLDI(PF_LAST0, j)); SETI(PF_LAST0, j, b);
+				modes = withMode(modes, j, over ? PM_DONE : PM_LEAF);
+			}
+		} else if (bestM == PM_PNODE) {
+			// ---------------- position test, tree part: CM_BoxLeafnums_r, cm_test.c:131-156 -----------------
+			#pragma unroll 1
+			for (int rep = 0; rep < q.lightReps; rep++) {
+				const int j = firstInMode<K>(modes, PM_PNODE);
+				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
+				if (j >= 0) {
+					const int c = FLDI(PF_CUR, j);
+					if (c < 0) {
+						const int found = FLDI(PF_PEND, j);
+						if (found >= kMaxPosLeafs) {
+							modes = withMode(modes, j, PM_DONE);
+						} else {
+							SETI(PF_PEND, j, found + 1);
+							SETI(PF_CUR, j, -1 - c);
+							if (COUNT) cLeafs++;
+							modes = withMode(modes, j, PM_PLEAF);
+						}
+					} else {
+						const int4 nd = __ldg(&fm.nodes[c]);
+						if (COUNT) cNodes++;
+						// start == end: tw.bounds = start + size; the listing box is one unit wider (cm_trace.c:199-205)
+						const float lox = (FLD(PF_SX, j) + h.n0[0]) - 1.0f, loy = (FLD(PF_SY, j) + h.n0[1]) - 1.0f, loz = (FLD(PF_SZ, j) + h.n0[2]) - 1.0f;
+						const float hix = (FLD(PF_SX, j) + h.p0[0]) + 1.0f, hiy = (FLD(PF_SY, j) + h.p0[1]) + 1.0f, hiz = (FLD(PF_SZ, j) + h.p0[2]) + 1.0f;
+						int s;
+						const float dist = __int_as_float(nd.w);
+						if (nd.z < 3) {                                    // BoxOnPlaneSide, q_math.c:724-758
+							if (dist <= sel3(lox, loy, loz, nd.z)) s = 1;
+							else if (dist >= sel3(hix, hiy, hiz, nd.z)) s = 2;
+							else s = 3;
+						} else {
+							const float4 pl = __ldg(&fm.nodePlanes[c]);
+							float a = 0.0f, bb = 0.0f;
+							if (pl.x < 0.0f) { bb = bb + pl.x * hix; a = a + pl.x * lox; } else { a = a + pl.x * hix; bb = bb + pl.x * lox; }
+							if (pl.y < 0.0f) { bb = bb + pl.y * hiy; a = a + pl.y * loy; } else { a = a + pl.y * hiy; bb = bb + pl.y * loy; }
+							if (pl.z < 0.0f) { bb = bb + pl.z * hiz; a = a + pl.z * loz; } else { a = a + pl.z * hiz; bb = bb + pl.z * loz; }
+							s = 0;
+							if (a >= dist) s = 1;
+							if (bb < dist) s |= 2;
+						}
+						if (s == 1) {
+							SETI(PF_CUR, j, nd.x);
+						} else if (s == 2) {
+							SETI(PF_CUR, j, nd.y);
+						} else {
+							const int fl = FLDI(PF_FLAGS, j);
+							const int sp = fl >> 8;
+							if (sp < kPoolDepth) { __stcg(&STACK(j)[sp].num, nd.y); SETI(PF_FLAGS, j, fl + 256); }
+							else atomicOr(q.status, 1);
+							SETI(PF_CUR, j, nd.x);
+						}
+					}
+				}
+			}
+		} else {
+			// ---------------- position test, leaf part: CM_TestInLeaf / CM_TestBoxInBrush, cm_trace.c:83-183 -------------
+			#pragma unroll 1
+			for (int rep = 0; rep < q.lightReps; rep++) {
+				const int j = firstInMode<K>(modes, PM_PLEAF);
+				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
+				if (j >= 0) {
+					const int k = FLDI(PF_CUR, j);
+					const float4 e0 = __ldg(&fm.stream[2 * k]);
+					const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
+					SETI(PF_CUR, j, k + 1);
+					const int b = __float_as_int(e1.w);
+					if (b < 0) {
+						const int fl = FLDI(PF_FLAGS, j);
+						const int sp = fl >> 8;
+						if (sp == 0) {
+							modes = withMode(modes, j, PM_DONE);
+						} else {
+							SETI(PF_CUR, j, __ldcg(&STACK(j)[sp - 1].num));
+							SETI(PF_FLAGS, j, fl - 256);
+							modes = withMode(modes, j, PM_PNODE);
+						}
+					} else {
+						if (COUNT) cBrushRefs++;
+						const int contents = __float_as_int(e0.w);
+						if (contents & h.mask) {
+							const float4 r0 = __ldg(&fm.brushRec[2 * b]);
+							const float4 r1 = __ldg(&fm.brushRec[2 * b + 1]);
+							const int firstSide = __float_as_int(r0.w);
+							const int ns = __float_as_int(r1.w) & 0xffffff;
+							if (ns > 0) {
+								if (COUNT) cBrushBounds++;
+								const float sx = FLD(PF_SX, j), sy = FLD(PF_SY, j), sz = FLD(PF_SZ, j);
+								const float lox = sx + h.n0[0], loy = sy + h.n0[1], loz = sz + h.n0[2];
+								const float hix = sx + h.p0[0], hiy = sy + h.p0[1], hiz = sz + h.p0[2];
+								if (!(lox > r1.x || loy > r1.y || loz > r1.z || hix < r0.x || hiy < r0.y || hiz < r0.z)) {
+									bool inside = true;
+									for (int s = 6; s < ns; s++) {
+										const float4 pl = __ldg(&fm.sidePlanes[firstSide + s]);
+										if (COUNT) cBrushSides++;
+										const float cx = pl.x < 0.0f ? h.p0[0] : h.n0[0];
+										const float cy = pl.y < 0.0f ? h.p0[1] : h.n0[1];
+										const float cz = pl.z < 0.0f ? h.p0[2] : h.n0[2];
+										const float distf = pl.w - dotf(cx, cy, cz, pl.x, pl.y, pl.z);    // all-float (cm_trace.c:111)
+										const double d1 = dotd((double)sx, (double)sy, (double)sz, pl.x, pl.y, pl.z) - (double)distf;
+										if (d1 > 0) { inside = false; break; }
+									}
+									if (inside) {
+										SETI(PF_FLAGS, j, FLDI(PF_FLAGS, j) | 3);
+										FLD(PF_FRACTION, j) = 0.0f;
+										SETI(PF_HITID, j, b);
+										modes = withMode(modes, j, PM_DONE);
+									}
+								}
+							}
+						}
+					}
+				}
+			}
+		}
+	}
+	if (COUNT) {
+		Counters *c = q.counters;
+		atomicAdd(&c->traces, (unsigned long long)cTraces);
+		atomicAdd(&c->nodes, (unsigned long long)cNodes);
+		atomicAdd(&c->leafs, (unsigned long long)cLeafs);
+		atomicAdd(&c->brushRefs, (unsigned long long)cBrushRefs);
+		atomicAdd(&c->brushBounds, (unsigned long long)cBrushBounds);
+		atomicAdd(&c->brushSides, (unsigned long long)cBrushSides);
+		atomicAdd(&c->crossings, (unsigned long long)cCross);
+		atomicAdd(&c->splits, (unsigned long long)cSplits);
+	}
+#undef FLD
+#undef FLDI
+#undef SETI
+#undef STACK
+}
+
+}  // namespace cmgpu

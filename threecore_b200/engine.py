@@ -113,6 +113,8 @@ def load_library() -> C.CDLL:
     lib.cmgpu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.cmgpu_launch_count.argtypes = [C.c_void_p]
     lib.cmgpu_launch_count.restype = C.c_ulonglong
+    lib.cmgpu_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.cmgpu_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.cmgpu_enable_counters.argtypes = [C.c_void_p, C.c_int]
     lib.cmgpu_read_counters.argtypes = [C.c_void_p, C.POINTER(_Counters), C.c_int]
     lib.cmgpu_check_status.argtypes = [C.c_void_p, C.c_void_p]
@@ -282,6 +284,16 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.cmgpu_launch_count(self.h))
+
+    def kernel_timing(self, on=True):
+        """bracket every trace-kernel launch with CUDA events on its own stream (cmgpu_kernel_timing)"""
+        self._check(self.lib.cmgpu_kernel_timing(self.h, int(bool(on))))
+
+    def kernel_time_ms(self):
+        """(sum of the bracketed trace-kernel durations in ms, number of launches) since the last call"""
+        ms, n = C.c_double(), C.c_int()
+        self._check(self.lib.cmgpu_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def enable_counters(self, on=True):
         self._check(self.lib.cmgpu_enable_counters(self.h, int(bool(on))))
