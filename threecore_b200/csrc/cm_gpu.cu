@@ -78,6 +78,7 @@ struct cmgpu_ctx_s {
 	int binMinItems = 1 << 15;           // smaller batches are traced in input order
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bHist[kBinSlots];
+	DevBuf bPoolHdr[kBinSlots + 1];
 	DevBuf bStackArena[kBinSlots + 1];   // traversal stacks of the hot kernel: one per pipeline stream + one for device-pointer calls
 	// Device-pointer calls share one workspace (binning buffers, stack arena).  extDone fires when the last such
 	// launch has finished; a call on a different stream, or a host-pointer call, waits for it first.
@@ -555,6 +556,9 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * kPoolDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
 		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
+		rcA = reserve(ctx, ctx->bPoolHdr[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * sizeof(PoolHdr));
+		if (rcA) return rcA;
+		q.poolHdr = ctx->bPoolHdr[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
 		if (ctx->counting) tracePoolKernel<true, CMGPU_POOL_K><<<(int)blocks, kBlock, kPoolSmem, s>>>(ctx->fast, q, h);
 		else               tracePoolKernel<false, CMGPU_POOL_K><<<(int)blocks, kBlock, kPoolSmem, s>>>(ctx->fast, q, h);
@@ -672,7 +676,8 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
 	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit,
 	                  &ctx->bKeys, &ctx->bRecs, &ctx->bHist[0], &ctx->bHist[1], &ctx->bHist[2],
-	                  &ctx->bStackArena[0], &ctx->bStackArena[1], &ctx->bStackArena[2], &ctx->bStackArena[3]}) releaseBuf(*b);
+	                  &ctx->bStackArena[0], &ctx->bStackArena[1], &ctx->bStackArena[2], &ctx->bStackArena[3],
+	                  &ctx->bPoolHdr[0], &ctx->bPoolHdr[1], &ctx->bPoolHdr[2], &ctx->bPoolHdr[3]}) releaseBuf(*b);
 	if (ctx->extDone) cudaEventDestroy(ctx->extDone);
 	for (auto &pr : ctx->timingPairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
 	if (ctx->dCounters) cudaFree(ctx->dCounters);

@@ -93,6 +93,7 @@ struct TraceBatch {
 	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
 	Counters *counters;                  // only touched by the counting variant
 	struct FastSeg *stackArena;          // hot kernel: kMaxDepth entries per resident thread
+	void *poolHdr;                       // pool variant: one 16-byte header per item slot
 	const float4 *recs;                  // binned batch: [2*slot] start.xyz + item bits, [2*slot+1] end.xyz + 0; null = input order
 };
 

@@ -15,33 +15,38 @@
 namespace cmgpu {
 
 constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
+constexpr int kVoteEnough = 20;          // a step kind that this many lanes can run is run without looking further
 
 enum PoolMode : int { PM_EMPTY = 0, PM_DONE, PM_NODE, PM_LEAF, PM_POP, PM_SPLIT, PM_BRUSH, PM_PNODE, PM_PLEAF, PM_COUNT };
 
 // shared-memory fields of one item (32-bit words)
 enum PoolField : int {
-	PF_SLOT = 0, PF_SX, PF_SY, PF_SZ, PF_EX, PF_EY, PF_EZ, PF_FRACTION, PF_FLAGS /* flags | sp << 8 */, PF_PLANEREF, PF_HITID,
+	PF_SX = 0, PF_SY, PF_SZ, PF_EX, PF_EY, PF_EZ, PF_FRACTION, PF_FLAGS /* flags | sp << 8 */,
 	PF_CUR /* node number or leaf-stream cursor */, PF_F1, PF_F2, PF_AX, PF_AY, PF_AZ, PF_BX, PF_BY, PF_BZ,
 	PF_LAST0, PF_LAST1, PF_PEND /* brush waiting to be clipped; position test: leafs seen */, PF_COUNT
 };
 
+// what an item only needs when its record is written lives in global memory (one 16-byte header per item slot)
+struct __align__(16) PoolHdr { int slot, planeRef, hitId, pad; };
+
+// The step kinds of a lane's K items are one-hot bytes of one register (bit m-1 of byte j: item j waits for kind m),
+// so "do I own an item of kind m" and "which" are a mask and a find-first-set.
 template <int K>
 __device__ __forceinline__ int firstInMode(const unsigned modes, const int m) {
-	int j = -1;
-	#pragma unroll
-	for (int i = K - 1; i >= 0; i--) if (((modes >> (4 * i)) & 15u) == (unsigned)m) j = i;
-	return j;
+	const unsigned t = modes & (0x01010101u << (m - 1));
+	return t ? ((__ffs((int)t) - 1) >> 3) : -1;
 }
 
 __device__ __forceinline__ unsigned withMode(const unsigned modes, const int j, const int m) {
-	return (modes & ~(15u << (4 * j))) | ((unsigned)m << (4 * j));
+	const unsigned bit = m ? (1u << (m - 1)) : 0u;
+	return (modes & ~(0xffu << (8 * j))) | (bit << (8 * j));
 }
 
 #ifndef CMGPU_POOL_K
-#define CMGPU_POOL_K 4
+#define CMGPU_POOL_K 2
 #endif
 #ifndef CMGPU_POOL_MIN_BLOCKS
-#define CMGPU_POOL_MIN_BLOCKS 4
+#define CMGPU_POOL_MIN_BLOCKS 8
 #endif
 
 template <bool COUNT, int K>
@@ -58,31 +63,44 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 	const size_t globalWarp = (size_t)blockIdx.x * (kBlock / 32) + warpInBlock;
 	FastSeg *const arena = q.stackArena + ((globalWarp * K) * 32 + lane) * kPoolDepth;   // item j: + j * 32 * kPoolDepth
 #define STACK(j) (arena + (size_t)(j) * 32 * kPoolDepth)
+	PoolHdr *const hdrs = reinterpret_cast<PoolHdr *>(q.poolHdr) + (globalWarp * K) * 32 + lane;
+#define HDR(j) hdrs[(j) * 32]
 
 	unsigned modes = 0u;
 	#pragma unroll
-	for (int j = 0; j < K; j++) { modes |= (unsigned)PM_DONE << (4 * j); SETI(PF_SLOT, j, -1); }
+	for (int j = 0; j < K; j++) { modes = withMode(modes, j, PM_DONE); HDR(j).slot = -1; }
 	int chunkNext = 0, chunkEnd = 0;     // warp-uniform
 	bool supply = true;                   // warp-uniform
 	unsigned cNodes = 0, cLeafs = 0, cBrushRefs = 0, cBrushBounds = 0, cBrushSides = 0, cCross = 0, cSplits = 0, cTraces = 0;
 
 	for (;;) {
 		// ---------------- vote: which kind of step can the most lanes run? ------------------
+		// Kinds are tried in the order of how often they win; the first one that kVoteEnough lanes can run is taken
+		// without counting the rest.
 		int bestM = 0, bestC = 0;
-		#pragma unroll
-		for (int m = 1; m < PM_COUNT; m++) {
-			const int c = __popc(__ballot_sync(0xffffffffu, firstInMode<K>(modes, m) >= 0));
-			if (c > bestC) { bestC = c; bestM = m; }
+		{
+			const unsigned present = (modes | (modes >> 8) | (modes >> 16) | (modes >> 24)) & 0xffu;
+			constexpr int order[PM_COUNT - 1] = { PM_NODE, PM_LEAF, PM_SPLIT, PM_POP, PM_BRUSH, PM_DONE, PM_PNODE, PM_PLEAF };
+			#pragma unroll
+			for (int i = 0; i < PM_COUNT - 1; i++) {
+				if (bestC < kVoteEnough) {
+					const int c = __popc(__ballot_sync(0xffffffffu, (present >> (order[i] - 1)) & 1u));
+					if (c > bestC) { bestC = c; bestM = order[i]; }
+				}
+			}
 		}
 		if (bestC == 0) break;                               // every slot empty
 
 		if (bestM == PM_DONE) {
 			// ---------------- write results, take new items (cm_trace.c:545-686) -----------------
 			const int j = firstInMode<K>(modes, PM_DONE);
-			if (j >= 0 && FLDI(PF_SLOT, j) >= 0) {
+			PoolHdr hd;
+			hd.slot = -1;
+			if (j >= 0) hd = HDR(j);
+			if (hd.slot >= 0) {
 				FastLane L;
-				L.slot = FLDI(PF_SLOT, j); L.fraction = FLD(PF_FRACTION, j); L.flags = FLDI(PF_FLAGS, j) & 0xff;
-				L.planeRef = FLDI(PF_PLANEREF, j); L.hitId = FLDI(PF_HITID, j);
+				L.slot = hd.slot; L.fraction = FLD(PF_FRACTION, j); L.flags = FLDI(PF_FLAGS, j) & 0xff;
+				L.planeRef = hd.planeRef; L.hitId = hd.hitId;
 				L.cNodes = L.cLeafs = L.cBrushRefs = L.cBrushBounds = L.cBrushSides = L.cCross = L.cSplits = 0;
 				finishFast<false>(fm, q, L);
 				if (COUNT) cTraces++;
@@ -107,17 +125,18 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (my < chunkEnd) {
 					FastLane L;
 					const int m = beginFast<false>(q, h, L, my);
-					SETI(PF_SLOT, j, L.slot);
+					hd.slot = L.slot; hd.planeRef = -1; hd.hitId = -1; hd.pad = 0;
+					HDR(j) = hd;
 					FLD(PF_SX, j) = L.sx; FLD(PF_SY, j) = L.sy; FLD(PF_SZ, j) = L.sz;
 					FLD(PF_EX, j) = L.ex; FLD(PF_EY, j) = L.ey; FLD(PF_EZ, j) = L.ez;
-					FLD(PF_FRACTION, j) = 1.0f; SETI(PF_FLAGS, j, L.flags); SETI(PF_PLANEREF, j, -1); SETI(PF_HITID, j, -1);
+					FLD(PF_FRACTION, j) = 1.0f; SETI(PF_FLAGS, j, L.flags);
 					SETI(PF_CUR, j, 0); FLD(PF_F1, j) = 0.0f; FLD(PF_F2, j) = 1.0f;
 					FLD(PF_AX, j) = L.sx; FLD(PF_AY, j) = L.sy; FLD(PF_AZ, j) = L.sz;
 					FLD(PF_BX, j) = L.ex; FLD(PF_BY, j) = L.ey; FLD(PF_BZ, j) = L.ez;
 					SETI(PF_LAST0, j, -1); SETI(PF_LAST1, j, -1); SETI(PF_PEND, j, 0);
 					modes = withMode(modes, j, m == FM_PNODE ? PM_PNODE : PM_NODE);
 				} else {
-					SETI(PF_SLOT, j, -1);                             // nothing to write back next time
+					HDR(j).slot = -1;                                 // nothing to write back next time
 					if (!supply) modes = withMode(modes, j, PM_EMPTY); // else: stays PM_DONE and asks again
 				}
 			}
@@ -276,14 +295,16 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				L.fraction = FLD(PF_FRACTION, j);
 				const int fl = FLDI(PF_FLAGS, j);
 				L.flags = fl & 0xff;
-				L.planeRef = FLDI(PF_PLANEREF, j); L.hitId = FLDI(PF_HITID, j);
+				constexpr int kUnset = (int)0x80000000;           // the header is only written when the clip changed it
+				L.planeRef = kUnset; L.hitId = kUnset;
 				L.cBrushSides = L.cCross = 0;
 				const int b = FLDI(PF_PEND, j);
 				const bool over = clipBrushFast<COUNT>(fm, h, L, b);
 				if (COUNT) { cBrushSides += L.cBrushSides; cCross += L.cCross; }
 				FLD(PF_FRACTION, j) = L.fraction;
 				SETI(PF_FLAGS, j, (fl & ~0xff) | L.flags);
-				SETI(PF_PLANEREF, j, L.planeRef); SETI(PF_HITID, j, L.hitId);
+				if (L.planeRef != kUnset) HDR(j).planeRef = L.planeRef;
+				if (L.hitId != kUnset) HDR(j).hitId = L.hitId;
 				SETI(PF_LAST1, j, FLDI(PF_LAST0, j)); SETI(PF_LAST0, j, b);
 				modes = withMode(modes, j, over ? PM_DONE : PM_LEAF);
 			}
@@ -391,7 +412,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 									if (inside) {
 										SETI(PF_FLAGS, j, FLDI(PF_FLAGS, j) | 3);
 										FLD(PF_FRACTION, j) = 0.0f;
-										SETI(PF_HITID, j, b);
+										HDR(j).hitId = b;
 										modes = withMode(modes, j, PM_DONE);
 									}
 								}
@@ -417,6 +438,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 #undef FLDI
 #undef SETI
 #undef STACK
+#undef HDR
 }
 
 }  // namespace cmgpu
