@@ -17,7 +17,9 @@ namespace cmgpu {
 constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
 constexpr int kVoteEnough = 20;          // a step kind that this many lanes can run is run without looking further
 
-enum PoolMode : int { PM_EMPTY = 0, PM_DONE, PM_NODE, PM_LEAF, PM_POP, PM_SPLIT, PM_BRUSH, PM_PNODE, PM_PLEAF, PM_COUNT };
+// step kinds an item can wait for (one-hot bit m-1 of its mode byte).  PM_POS is the position test; bit 3 of the item's
+// flags says whether it is in the tree part (CM_BoxLeafnums_r) or the leaf part (CM_TestInLeaf).
+enum PoolMode : int { PM_EMPTY = 0, PM_NODE, PM_LEAF, PM_SLAB, PM_POP, PM_SPLIT, PM_BRUSH, PM_DONE, PM_POS, PM_COUNT };
 
 // shared-memory fields of one item (32-bit words)
 enum PoolField : int {
@@ -75,23 +77,24 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 
 	for (;;) {
 		// ---------------- vote: which kind of step can the most lanes run? ------------------
-		// Kinds are tried in the order of how often they win; the first one that kVoteEnough lanes can run is taken
-		// without counting the rest.
-		int bestM = 0, bestC = 0;
+		// How many lanes own an item waiting for each kind: the presence bits of a lane are spread into byte-wide
+		// counters (4 per word) and summed over the warp with two REDUX.  Every kind that at least `thr` lanes can
+		// run (a share of the best count) is run this round.
+		int cNode, cLeaf, cSlab, cPop, cSplit, cBrush, cDone, cPos, thr;
 		{
-			const unsigned present = (modes | (modes >> 8) | (modes >> 16) | (modes >> 24)) & 0xffu;
-			constexpr int order[PM_COUNT - 1] = { PM_NODE, PM_LEAF, PM_SPLIT, PM_POP, PM_BRUSH, PM_DONE, PM_PNODE, PM_PLEAF };
-			#pragma unroll
-			for (int i = 0; i < PM_COUNT - 1; i++) {
-				if (bestC < kVoteEnough) {
-					const int c = __popc(__ballot_sync(0xffffffffu, (present >> (order[i] - 1)) & 1u));
-					if (c > bestC) { bestC = c; bestM = order[i]; }
-				}
-			}
+			unsigned present = modes | (modes >> 16);
+			present = (present | (present >> 8)) & 0xffu;
+			const unsigned ka = ((present & 0xfu) * 0x00204081u) & 0x01010101u;
+			const unsigned kb = ((present >> 4) * 0x00204081u) & 0x01010101u;
+			const unsigned ca = __reduce_add_sync(0xffffffffu, ka), cb = __reduce_add_sync(0xffffffffu, kb);
+			cNode = ca & 0xff; cLeaf = (ca >> 8) & 0xff; cSlab = (ca >> 16) & 0xff; cPop = ca >> 24;
+			cSplit = cb & 0xff; cBrush = (cb >> 8) & 0xff; cDone = (cb >> 16) & 0xff; cPos = cb >> 24;
+			const int best = max(max(max(cNode, cLeaf), max(cSlab, cPop)), max(max(cSplit, cBrush), max(cDone, cPos)));
+			if (best == 0) break;                            // every slot empty
+			thr = max(1, (best * q.gang) >> 3);
 		}
-		if (bestC == 0) break;                               // every slot empty
 
-		if (bestM == PM_DONE) {
+		if (cDone >= thr) {
 			// ---------------- write results, take new items (cm_trace.c:545-686) -----------------
 			const int j = firstInMode<K>(modes, PM_DONE);
 			PoolHdr hd;
@@ -134,19 +137,20 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					FLD(PF_AX, j) = L.sx; FLD(PF_AY, j) = L.sy; FLD(PF_AZ, j) = L.sz;
 					FLD(PF_BX, j) = L.ex; FLD(PF_BY, j) = L.ey; FLD(PF_BZ, j) = L.ez;
 					SETI(PF_LAST0, j, -1); SETI(PF_LAST1, j, -1); SETI(PF_PEND, j, 0);
-					modes = withMode(modes, j, m == FM_PNODE ? PM_PNODE : PM_NODE);
+					modes = withMode(modes, j, m == FM_PNODE ? PM_POS : PM_NODE);
 				} else {
 					HDR(j).slot = -1;                                 // nothing to write back next time
 					if (!supply) modes = withMode(modes, j, PM_EMPTY); // else: stays PM_DONE and asks again
 				}
 			}
 			chunkNext = min(chunkNext + nNeed, chunkEnd);
-		} else if (bestM == PM_NODE) {
+		}
+		if (cNode >= thr) {
 			// ---------------- axial nodes of CM_TraceThroughTree, cm_trace.c:456-486 -----------------
 			#pragma unroll 1
 			for (int rep = 0; rep < q.lightReps; rep++) {
 				const int j = firstInMode<K>(modes, PM_NODE);
-				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
+				if (!__any_sync(0xffffffffu, j >= 0)) break;
 				if (j >= 0) {
 					const int num = FLDI(PF_CUR, j);
 					const int4 nd = __ldg(&fm.nodes[num]);
@@ -168,12 +172,13 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					}
 				}
 			}
-		} else if (bestM == PM_LEAF) {
+		}
+		if (cLeaf >= thr) {
 			// ---------------- brush entries of CM_TraceThroughLeaf, cm_trace.c:377-393 -----------------
 			#pragma unroll 1
 			for (int rep = 0; rep < q.lightReps; rep++) {
 				const int j = firstInMode<K>(modes, PM_LEAF);
-				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
+				if (!__any_sync(0xffffffffu, j >= 0)) break;
 				if (j >= 0) {
 					const int k = FLDI(PF_CUR, j);
 					const float4 e0 = __ldg(&fm.stream[2 * k]);
@@ -195,18 +200,30 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 							const float loy = (L.sy < L.ey ? L.sy : L.ey) + h.n0[1], hiy = (L.sy < L.ey ? L.ey : L.sy) + h.p0[1];
 							const float loz = (L.sz < L.ez ? L.sz : L.ez) + h.n0[2], hiz = (L.sz < L.ez ? L.ez : L.sz) + h.p0[2];
 							const bool apart = hix < e0.x || hiy < e0.y || hiz < e0.z || lox > e1.x || loy > e1.y || loz > e1.z;
-							if (!apart) {
-								L.fraction = FLD(PF_FRACTION, j);
-								if (!((FLDI(PF_FLAGS, j) & 4) && slabReject(h, L, e0, e1))) {
-									SETI(PF_PEND, j, b);
-									modes = withMode(modes, j, PM_BRUSH);
-								}
+							if (!apart) {                                  // CM_BoundsIntersect passed
+								SETI(PF_PEND, j, b);
+								modes = withMode(modes, j, (FLDI(PF_FLAGS, j) & 4) ? PM_SLAB : PM_BRUSH);
 							}
 						}
 					}
 				}
 			}
-		} else if (bestM == PM_POP) {
+		}
+		if (cSlab >= thr) {
+			// ---------------- float slab pre-test of the entry that passed CM_BoundsIntersect (see slabReject) -----------------
+			const int j = firstInMode<K>(modes, PM_SLAB);
+			if (j >= 0) {
+				const int k = FLDI(PF_CUR, j) - 1;
+				const float4 e0 = __ldg(&fm.stream[2 * k]);
+				const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
+				FastLane L;
+				L.sx = FLD(PF_SX, j); L.sy = FLD(PF_SY, j); L.sz = FLD(PF_SZ, j);
+				L.ex = FLD(PF_EX, j); L.ey = FLD(PF_EY, j); L.ez = FLD(PF_EZ, j);
+				L.fraction = FLD(PF_FRACTION, j);
+				modes = withMode(modes, j, slabReject(h, L, e0, e1) ? PM_LEAF : PM_BRUSH);
+			}
+		}
+		if (cPop >= thr) {
 			// ---------------- return to the pending far half of a split -----------------
 			const int j = firstInMode<K>(modes, PM_POP);
 			if (j >= 0) {
@@ -228,7 +245,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					}
 				}
 			}
-		} else if (bestM == PM_SPLIT) {
+		}
+		if (cSplit >= thr) {
 			// ---------------- a node that is not a plain axial descent, cm_trace.c:456-537 -----------------
 			const int j = firstInMode<K>(modes, PM_SPLIT);
 			if (j >= 0) {
@@ -285,7 +303,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (c < 0) { SETI(PF_CUR, j, -1 - c); modes = withMode(modes, j, PM_LEAF); if (COUNT) cLeafs++; }
 				else { SETI(PF_CUR, j, c); modes = withMode(modes, j, PM_NODE); }
 			}
-		} else if (bestM == PM_BRUSH) {
+		}
+		if (cBrush >= thr) {
 			// ---------------- CM_TraceThroughBrush for the pending brush, cm_trace.c:261-363 -----
 			const int j = firstInMode<K>(modes, PM_BRUSH);
 			if (j >= 0) {
@@ -308,13 +327,16 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				SETI(PF_LAST1, j, FLDI(PF_LAST0, j)); SETI(PF_LAST0, j, b);
 				modes = withMode(modes, j, over ? PM_DONE : PM_LEAF);
 			}
-		} else if (bestM == PM_PNODE) {
-			// ---------------- position test, tree part: CM_BoxLeafnums_r, cm_test.c:131-156 -----------------
+		}
+		if (cPos >= thr) {
+			// ---------------- position test: CM_PositionTest / CM_BoxLeafnums_r / CM_TestInLeaf / CM_TestBoxInBrush,
+			// cm_trace.c:83-226, cm_test.c:131-156.  The reference lists <= 1024 leafs and then tests them in list order;
+			// testing each leaf when it is found is the same sequence of tests.
 			#pragma unroll 1
 			for (int rep = 0; rep < q.lightReps; rep++) {
-				const int j = firstInMode<K>(modes, PM_PNODE);
-				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
-				if (j >= 0) {
+				const int j = firstInMode<K>(modes, PM_POS);
+				if (!__any_sync(0xffffffffu, j >= 0)) break;
+				if (j >= 0 && !(FLDI(PF_FLAGS, j) & 8)) {
 					const int c = FLDI(PF_CUR, j);
 					if (c < 0) {
 						const int found = FLDI(PF_PEND, j);
@@ -324,7 +346,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 							SETI(PF_PEND, j, found + 1);
 							SETI(PF_CUR, j, -1 - c);
 							if (COUNT) cLeafs++;
-							modes = withMode(modes, j, PM_PLEAF);
+							SETI(PF_FLAGS, j, FLDI(PF_FLAGS, j) | 8);
 						}
 					} else {
 						const int4 nd = __ldg(&fm.nodes[c]);
@@ -360,15 +382,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 							SETI(PF_CUR, j, nd.x);
 						}
 					}
-				}
-			}
-		} else {
-			// ---------------- position test, leaf part: CM_TestInLeaf / CM_TestBoxInBrush, cm_trace.c:83-183 -------------
-			#pragma unroll 1
-			for (int rep = 0; rep < q.lightReps; rep++) {
-				const int j = firstInMode<K>(modes, PM_PLEAF);
-				if (rep > 0 && 2 * __popc(__ballot_sync(0xffffffffu, j >= 0)) < bestC) break;
-				if (j >= 0) {
+				} else if (j >= 0) {
 					const int k = FLDI(PF_CUR, j);
 					const float4 e0 = __ldg(&fm.stream[2 * k]);
 					const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
@@ -381,8 +395,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 							modes = withMode(modes, j, PM_DONE);
 						} else {
 							SETI(PF_CUR, j, __ldcg(&STACK(j)[sp - 1].num));
-							SETI(PF_FLAGS, j, fl - 256);
-							modes = withMode(modes, j, PM_PNODE);
+							SETI(PF_FLAGS, j, (fl - 256) & ~8);
 						}
 					} else {
 						if (COUNT) cBrushRefs++;
