@@ -133,7 +133,9 @@ int  cmgpu_set_cvars(cmgpu_ctx *ctx, int noCurves, int playerCurveClip);
 int  cmgpu_num_inline_models(const cmgpu_ctx *ctx);
 /* Tuning knobs; none of them changes results.  "bin" (0/1: trace large batches in the order of their
  * start cell), "bin_min_items", "bin_cell" (world units; takes effect at the next cmgpu_upload),
- * "bin_long_len", "gang", "light_reps".  Unknown names are CMGPU_ERR_INVALID. */
+ * "bin_long_len", "bin_dir", "gang", "gang_fetch", "light_reps", "fast" (0: always the general kernel), "pool" (0: the
+ * one-item-per-lane variant of the hot kernel), "pool_reps", "slab" (0: no float pre-test before the exact brush
+ * clip), "pipe_chunks" (pieces a host batch is cut into).  Unknown names are CMGPU_ERR_INVALID. */
 int  cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value);
 
 /* ---- batched queries, HOST pointers (copies in, kernel, copies out) -------

@@ -248,6 +248,24 @@ def test_binned_order_equals_input_order(eng, big):
     assert torch.equal(outs[0], big["out"][:n])
 
 
+@pytest.mark.parametrize("opts", [dict(pool=0), dict(pool=0, slab=0), dict(fast=0), dict(pool=1, slab=0), dict(pool=1, pool_reps=5, gang=8)])
+def test_kernel_variants_agree(eng, big, opts):
+    """the general kernel, the one-item-per-lane hot kernel and the pool kernel must return the same bytes"""
+    import torch
+    n = 1 << 20
+    try:
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        o = torch.empty((n, 56), dtype=torch.uint8, device=big["ds"].device)
+        eng.box_trace_device(big["ds"][:n], big["de"][:n], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, o)
+        torch.cuda.synchronize()
+        eng.check_status()
+    finally:
+        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=2, gang=4).items():
+            eng.set_option(k, v)
+    assert torch.equal(o, big["out"][:n])
+
+
 def test_binning_small_batches_all_query_kinds(eng):
     """force the binned path on small batches of every query kind (per-item hulls, models, temp boxes, rotations)"""
     eng.set_option("bin_min_items", 1)

@@ -57,7 +57,8 @@ struct cmgpu_ctx_s {
 	int gridPlain = 0, gridCount = 0;    // resident CTAs of the two kernel variants
 	int gridFast = 0, gridFastCount = 0;
 	int gridPool = 0, gridPoolCount = 0;
-	bool usePool = false;                // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
+	bool usePool = true;                 // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
+	int poolReps = 2;                    // its repeats of a light step per round
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	bool useFast = true;
@@ -553,6 +554,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		CUDA_TRY(ctx, cudaEventRecord(pr.first, s));
 	}
 	if (pool) {
+		q.lightReps = ctx->poolReps;
 		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * kPoolDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
 		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
@@ -728,6 +730,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "bin_dir") ctx->binDir = value != 0;
 	else if (k == "fast") ctx->useFast = value != 0;
 	else if (k == "pool") ctx->usePool = value != 0;
+	else if (k == "pool_reps") ctx->poolReps = value < 1 ? 1 : (int)value;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;

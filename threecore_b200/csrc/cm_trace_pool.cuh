@@ -163,13 +163,13 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const float lo = ax == 0 ? h.nodeLo[0] : (ax == 1 ? h.nodeLo[1] : h.nodeLo[2]);
 					const bool front = t1 >= hi && t2 >= hi;
 					const bool back = t1 < lo && t2 < lo;
-					if (nd.z < 3 && (front || back)) {
-						const int c = front ? nd.x : nd.y;
-						if (c < 0) { SETI(PF_CUR, j, -1 - c); modes = withMode(modes, j, PM_LEAF); if (COUNT) cLeafs++; }
-						else SETI(PF_CUR, j, c);
-					} else {
-						modes = withMode(modes, j, PM_SPLIT);
-					}
+					// one update of the cursor and of the step kind, no divergent tails
+					const bool go = nd.z < 3 && (front || back);          // else: split or non-axial node
+					const int c = front ? nd.x : nd.y;
+					const bool leaf = go && c < 0;
+					SETI(PF_CUR, j, go ? (c < 0 ? -1 - c : c) : num);
+					if (COUNT) cLeafs += leaf ? 1u : 0u;
+					if (!go || leaf) modes = withMode(modes, j, leaf ? PM_LEAF : PM_SPLIT);
 				}
 			}
 		}
@@ -185,27 +185,20 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
 					SETI(PF_CUR, j, k + 1);
 					const int b = __float_as_int(e1.w);
-					if (b < 0) {
-						modes = withMode(modes, j, PM_POP);
-					} else {
-						if (COUNT) cBrushRefs++;
-						const bool want = (__float_as_int(e0.w) & h.mask) != 0 && b != FLDI(PF_LAST0, j) && b != FLDI(PF_LAST1, j);
-						if (COUNT) cBrushBounds += want ? 1u : 0u;
-						if (want) {
-							FastLane L;
-							L.sx = FLD(PF_SX, j); L.sy = FLD(PF_SY, j); L.sz = FLD(PF_SZ, j);
-							L.ex = FLD(PF_EX, j); L.ey = FLD(PF_EY, j); L.ez = FLD(PF_EZ, j);
-							// tw.bounds (cm_trace.c:628-636), recomputed instead of stored
-							const float lox = (L.sx < L.ex ? L.sx : L.ex) + h.n0[0], hix = (L.sx < L.ex ? L.ex : L.sx) + h.p0[0];
-							const float loy = (L.sy < L.ey ? L.sy : L.ey) + h.n0[1], hiy = (L.sy < L.ey ? L.ey : L.sy) + h.p0[1];
-							const float loz = (L.sz < L.ez ? L.sz : L.ez) + h.n0[2], hiz = (L.sz < L.ez ? L.ez : L.sz) + h.p0[2];
-							const bool apart = hix < e0.x || hiy < e0.y || hiz < e0.z || lox > e1.x || loy > e1.y || loz > e1.z;
-							if (!apart) {                                  // CM_BoundsIntersect passed
-								SETI(PF_PEND, j, b);
-								modes = withMode(modes, j, (FLDI(PF_FLAGS, j) & 4) ? PM_SLAB : PM_BRUSH);
-							}
-						}
-					}
+					if (COUNT) cBrushRefs += b >= 0 ? 1u : 0u;
+					const bool want = b >= 0 && (__float_as_int(e0.w) & h.mask) != 0 && b != FLDI(PF_LAST0, j) && b != FLDI(PF_LAST1, j);
+					if (COUNT) cBrushBounds += want ? 1u : 0u;
+					const float sx = FLD(PF_SX, j), sy = FLD(PF_SY, j), sz = FLD(PF_SZ, j);
+					const float ex = FLD(PF_EX, j), ey = FLD(PF_EY, j), ez = FLD(PF_EZ, j);
+					// tw.bounds (cm_trace.c:628-636), recomputed instead of stored
+					const float lox = (sx < ex ? sx : ex) + h.n0[0], hix = (sx < ex ? ex : sx) + h.p0[0];
+					const float loy = (sy < ey ? sy : ey) + h.n0[1], hiy = (sy < ey ? ey : sy) + h.p0[1];
+					const float loz = (sz < ez ? sz : ez) + h.n0[2], hiz = (sz < ez ? ez : sz) + h.p0[2];
+					const bool apart = hix < e0.x || hiy < e0.y || hiz < e0.z || lox > e1.x || loy > e1.y || loz > e1.z;
+					const bool clip = want && !apart;                     // CM_BoundsIntersect passed
+					if (clip) SETI(PF_PEND, j, b);
+					if (b < 0 || clip)
+						modes = withMode(modes, j, b < 0 ? PM_POP : ((FLDI(PF_FLAGS, j) & 4) ? PM_SLAB : PM_BRUSH));
 				}
 			}
 		}
