@@ -14,5 +14,5 @@ python scripts/prof_trace.py 2097152 3 > gpurun_out/${tag}_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:trace -s 1 -c 1 -f -o gpurun_out/prof_${tag} \
     python scripts/prof_trace.py 2097152 3 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 # DRAM traffic of the dominant kernel at the bench's own launch size (16 Mi rays)
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:traceFast -s 3 -c 1 --csv \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:tracePool -s 3 -c 1 --csv \
     --log-file gpurun_out/${tag}_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"

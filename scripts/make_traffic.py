@@ -9,7 +9,7 @@ out = {"kernel": rows[0][4], "grid": rows[0][8], "block": rows[0][7],
        "dram_bytes_per_launch": d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"],
        "gpu_time_ns_under_ncu": d["gpu__time_duration.sum"], "traces_per_launch": 1 << 24,
        "command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
-                  "-k regex:traceFast -s 3 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline",
+                  "-k regex:tracePool -s 3 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline",
        "source": f"profiles/{tag}_traffic.csv"}
 json.dump(out, open("profiles/traffic.json", "w"), indent=1)
 print(out)
