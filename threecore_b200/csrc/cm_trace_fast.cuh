@@ -64,6 +64,24 @@ struct FastLane {
 	unsigned cNodes, cLeafs, cBrushRefs, cBrushBounds, cBrushSides, cCross, cSplits;
 };
 
+// The traversal stacks are a few tens of MB that every item pushes to and pops from, next to GBs of rays and
+// records that stream through L2 once: ask L2 to keep the former (evict_last) so that pops do not come from DRAM.
+__device__ __forceinline__ unsigned long long l2KeepPolicy() {
+	unsigned long long p;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ void stKeep(float4 *p, const float4 v, const unsigned long long pol) {
+	asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+	             :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ldKeep(const float4 *p, const unsigned long long pol) {
+	float4 v;
+	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+	             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+	return v;
+}
+
 __device__ __forceinline__ float rcpApprox(float x) {
 	float r;
 	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

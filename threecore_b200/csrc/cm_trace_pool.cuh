@@ -226,7 +226,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					modes = withMode(modes, j, PM_DONE);
 				} else {
 					const float4 *sp4 = reinterpret_cast<const float4 *>(&STACK(j)[sp - 1]);
-					const float4 t0 = __ldcg(&sp4[0]), t1 = __ldcg(&sp4[1]), t2 = __ldcg(&sp4[2]);
+					const unsigned long long keep = l2KeepPolicy();
+					const float4 t0 = ldKeep(&sp4[0], keep), t1 = ldKeep(&sp4[1], keep), t2 = ldKeep(&sp4[2], keep);
 					SETI(PF_FLAGS, j, fl - 256);
 					if (!(FLD(PF_FRACTION, j) <= t0.y)) {              // cm_trace.c:449: already hit something nearer
 						FLD(PF_F1, j) = t0.y; FLD(PF_F2, j) = t0.z;
@@ -280,9 +281,10 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const int sp = fl >> 8;
 					if (sp < kPoolDepth) {
 						float4 *sp4 = reinterpret_cast<float4 *>(&STACK(j)[sp]);
-						__stcg(&sp4[0], make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)));
-						__stcg(&sp4[1], make_float4(ay_ + ffar * (by_ - ay_), az_ + ffar * (bz_ - az_), bx_, by_));
-						__stcg(&sp4[2], make_float4(bz_, 0.0f, 0.0f, 0.0f));
+						const unsigned long long keep = l2KeepPolicy();
+						stKeep(&sp4[0], make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)), keep);
+						stKeep(&sp4[1], make_float4(ay_ + ffar * (by_ - ay_), az_ + ffar * (bz_ - az_), bx_, by_), keep);
+						stKeep(&sp4[2], make_float4(bz_, 0.0f, 0.0f, 0.0f), keep);
 						SETI(PF_FLAGS, j, fl + 256);
 					} else {
 						atomicOr(q.status, 1);
