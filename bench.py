@@ -187,6 +187,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: whatever native libraries print while the job runs (NCCL's version banner
+    # for one) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -290,6 +295,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "Mtraces/s", "cores": cores, "kind": kind,
                                     "sample": f"first {min(args.ref_sample, n)} rays of the same stream, one forked "
                                               f"worker per host core, {secs:.2f} s wall"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

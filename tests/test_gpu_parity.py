@@ -269,6 +269,7 @@ def test_kernel_variants_agree(eng, big, opts):
 def test_binning_small_batches_all_query_kinds(eng):
     """force the binned path on small batches of every query kind (per-item hulls, models, temp boxes, rotations)"""
     eng.set_option("bin_min_items", 1)
+    eng.set_option("pool_min_items", 1)
     try:
         for kind in ("arena_models", "patches_small"):
             m, o = load(eng, kind)
@@ -276,3 +277,4 @@ def test_binning_small_batches_all_query_kinds(eng):
                 check(eng, o, case)
     finally:
         eng.set_option("bin_min_items", 1 << 15)
+        eng.set_option("pool_min_items", 1 << 20)

@@ -59,10 +59,11 @@ struct cmgpu_ctx_s {
 	int gridPool = 0, gridPoolCount = 0;
 	bool usePool = true;                 // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
 	int poolReps = 2;                    // its repeats of a light step per round
+	int poolMinItems = 1 << 20;          // smaller launches use the one-item-per-lane variant (lower latency)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	bool useFast = true;
-	int pipeChunks = 32;                 // pieces a host batch is cut into
+	int pipeChunks = 16;                 // pieces a host batch is cut into
 	// optional CUDA-event timing of the trace kernel alone (cmgpu_kernel_timing)
 	bool timing = false;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timingPairs;
@@ -528,7 +529,8 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
-	const bool pool = fast && ctx->usePool;
+	// the pool variant pays off once every warp has several rounds of items to work through
+	const bool pool = fast && ctx->usePool && q.n >= ctx->poolMinItems;
 	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
 	                   : fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
 	// Items per cursor grab: kChunk for big batches; for small ones a share that spreads the batch over all
@@ -731,6 +733,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "fast") ctx->useFast = value != 0;
 	else if (k == "pool") ctx->usePool = value != 0;
 	else if (k == "pool_reps") ctx->poolReps = value < 1 ? 1 : (int)value;
+	else if (k == "pool_min_items") ctx->poolMinItems = value < 1 ? 1 : (int)value;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
