@@ -47,6 +47,11 @@ struct cmgpu_ctx_s {
 	bool hasMap = false;
 	DevMap map{};
 	std::vector<void *> mapAllocs;
+	std::vector<char> slabHost;          // staging of the map slab during an upload
+	std::vector<std::pair<const void **, size_t>> slabFixups;
+	void *mapSlab = nullptr;
+	size_t mapSlabBytes = 0, mapWindowBytes = 0;
+	bool l2Window = true;
 	int numModels = 0;
 	int noCurves = 0, playerCurveClip = 1;
 	bool counting = false;
@@ -59,6 +64,7 @@ struct cmgpu_ctx_s {
 	int gridPool = 0, gridPoolCount = 0;
 	bool usePool = true;                 // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
 	int poolReps = 2;                    // its repeats of a light step per round
+	int minChunk = 8;                    // fewest items a warp takes at a time in a small launch
 	int poolMinItems = 1 << 20;          // smaller launches use the one-item-per-lane variant (lower latency)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
@@ -134,21 +140,79 @@ void releaseBuf(DevBuf &b) {
 	b.cap = 0;
 }
 
+// All arrays of a map go into ONE device allocation (256-byte aligned pieces), so that a single L2 access-policy
+// window can cover the map: the kernels' L1 absorbs most hits on it, which makes the map look cold to L2's
+// replacement next to the GBs of rays and records streaming through -- without the window its lines are evicted and
+// re-read from HBM all the time.  uploadArray stages a piece and notes where its device pointer goes; commitMapSlab
+// allocates, copies and patches the pointers.
 template <typename T>
 int uploadArray(cmgpu_ctx *ctx, const std::vector<T> &host, const T **dev) {
+	const size_t bytes = (host.size() ? host.size() : 1) * sizeof(T);
+	const size_t off = (ctx->slabHost.size() + 255) & ~(size_t)255;
+	ctx->slabHost.resize(off + bytes, 0);
+	if (host.size()) memcpy(ctx->slabHost.data() + off, host.data(), host.size() * sizeof(T));
+	ctx->slabFixups.push_back({reinterpret_cast<const void **>(dev), off});
+	*dev = nullptr;
+	return CMGPU_OK;
+}
+
+int commitMapSlab(cmgpu_ctx *ctx) {
 	void *p = nullptr;
-	size_t bytes = (host.size() ? host.size() : 1) * sizeof(T);
+	const size_t bytes = ctx->slabHost.size() ? ctx->slabHost.size() : 256;
 	CUDA_TRY(ctx, cudaMalloc(&p, bytes));
 	ctx->mapAllocs.push_back(p);
-	if (host.size()) CUDA_TRY(ctx, cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
-	else CUDA_TRY(ctx, cudaMemset(p, 0, bytes));
-	*dev = (const T *)p;
+	CUDA_TRY(ctx, cudaMemcpy(p, ctx->slabHost.data(), ctx->slabHost.size(), cudaMemcpyHostToDevice));
+	for (auto &fx : ctx->slabFixups) *fx.first = (const char *)p + fx.second;
+	ctx->slabFixups.clear();
+	std::vector<char>().swap(ctx->slabHost);
+	ctx->mapSlab = p;
+	ctx->mapSlabBytes = bytes;
+	// reserve that much of L2 for persisting lines (the hardware caps both numbers)
+	cudaDeviceProp prop;
+	CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+	ctx->mapWindowBytes = 0;
+	if (ctx->l2Window && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+		size_t want = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+		if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+			ctx->mapWindowBytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+		else cudaGetLastError();
+	}
 	return CMGPU_OK;
+}
+
+// launch with the map's L2 window attached to this launch only (no stream attribute is touched: device-pointer
+// calls run on the caller's stream)
+template <typename... KArgs, typename... Args>
+cudaError_t launchOnMap(cmgpu_ctx *ctx, void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t s, Args... args) {
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)blocks);
+	cfg.blockDim = dim3((unsigned)threads);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	int nattr = 0;
+	if (ctx->mapWindowBytes) {
+		attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+		attr[0].val.accessPolicyWindow.base_ptr = ctx->mapSlab;
+		attr[0].val.accessPolicyWindow.num_bytes = ctx->mapWindowBytes;
+		attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+		attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		nattr = 1;
+	}
+	cfg.attrs = attr;
+	cfg.numAttrs = nattr;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 void freeMap(cmgpu_ctx *ctx) {
 	for (void *p : ctx->mapAllocs) cudaFree(p);
 	ctx->mapAllocs.clear();
+	if (ctx->mapWindowBytes) cudaCtxResetPersistingL2Cache();
+	ctx->mapSlab = nullptr;
+	ctx->mapSlabBytes = ctx->mapWindowBytes = 0;
+	ctx->slabFixups.clear();
+	std::vector<char>().swap(ctx->slabHost);
 	ctx->hasMap = false;
 	ctx->numModels = 0;
 	memset(&ctx->map, 0, sizeof(ctx->map));
@@ -393,12 +457,13 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		if ((rc = uploadArray(ctx, stream, &fm.stream)) != CMGPU_OK) return rc;
 		if ((rc = uploadArray(ctx, brushRec, &fm.brushRec)) != CMGPU_OK) return rc;
 		if ((rc = uploadArray(ctx, brushContents, &fm.brushContents)) != CMGPU_OK) return rc;
-		fm.nodePlanes = m.nodePlanes;
-		fm.sidePlanes = m.sidePlanes;
-		fm.sideMeta = m.sideMeta;
 		ctx->numPatches = f->numPatches;
 	}
 #undef UP
+	if ((rc = commitMapSlab(ctx)) != CMGPU_OK) return rc;
+	ctx->fast.nodePlanes = m.nodePlanes;
+	ctx->fast.sidePlanes = m.sidePlanes;
+	ctx->fast.sideMeta = m.sideMeta;
 	{	// binning grid over the bounds of the world's brushes
 		float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
 		for (int i = 0; i < f->numBrushes; i++) {
@@ -534,9 +599,15 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
 	                   : fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
 	// Items per cursor grab: kChunk for big batches; for small ones a share that spreads the batch over all
-	// resident warps (a warp works through its items 32 at a time, so a 256-item grab is ~1 ms of latency).
-	int chunk = (int)(((long long)q.n / ((long long)resident * (kBlock / 32) * (pool ? CMGPU_POOL_K : 1) * 4)) / 32 * 32);
-	if (chunk < 32) chunk = 32;
+	// resident warps -- down to 8 items per warp: a batch's latency is the walk of its slowest warp, and a warp
+	// with fewer items in flight runs fewer kinds of step per round.
+	const long long residentWarps = (long long)resident * (kBlock / 32);
+	int chunk = (int)(((long long)q.n / (residentWarps * (pool ? CMGPU_POOL_K : 1) * 4)) / 32 * 32);
+	if (chunk < 32) {
+		chunk = (int)(((long long)q.n + residentWarps - 1) / residentWarps);
+		if (chunk < ctx->minChunk) chunk = ctx->minChunk;
+		if (chunk > 32) chunk = 32;
+	}
 	if (chunk > kChunk) chunk = kChunk;
 	q.chunk = chunk;
 	const long long warpsWanted = ((long long)q.n + chunk - 1) / chunk;
@@ -564,18 +635,18 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		if (rcA) return rcA;
 		q.poolHdr = ctx->bPoolHdr[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
-		if (ctx->counting) tracePoolKernel<true, CMGPU_POOL_K><<<(int)blocks, kBlock, kPoolSmem, s>>>(ctx->fast, q, h);
-		else               tracePoolKernel<false, CMGPU_POOL_K><<<(int)blocks, kBlock, kPoolSmem, s>>>(ctx->fast, q, h);
+		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<true, CMGPU_POOL_K>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
+		else               CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 	} else if (fast) {
 		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * kMaxDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
 		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
-		if (ctx->counting) traceFastKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
-		else               traceFastKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->fast, q, h);
+		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceFastKernel<true>, (int)blocks, kBlock, 0, s, ctx->fast, q, h));
+		else               CUDA_TRY(ctx, launchOnMap(ctx, traceFastKernel<false>, (int)blocks, kBlock, 0, s, ctx->fast, q, h));
 	} else {
-		if (ctx->counting) traceKernel<true><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
-		else               traceKernel<false><<<(int)blocks, kBlock, 0, s>>>(ctx->map, q);
+		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<true>, (int)blocks, kBlock, 0, s, ctx->map, q));
+		else               CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<false>, (int)blocks, kBlock, 0, s, ctx->map, q));
 	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
@@ -731,8 +802,10 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "bin_long_len") ctx->binLongLen = (float)value;
 	else if (k == "bin_dir") ctx->binDir = value != 0;
 	else if (k == "fast") ctx->useFast = value != 0;
+	else if (k == "l2_window") ctx->l2Window = value != 0;      // takes effect at the next cmgpu_upload
 	else if (k == "pool") ctx->usePool = value != 0;
 	else if (k == "pool_reps") ctx->poolReps = value < 1 ? 1 : (int)value;
+	else if (k == "min_chunk") ctx->minChunk = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
 	else if (k == "pool_min_items") ctx->poolMinItems = value < 1 ? 1 : (int)value;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;

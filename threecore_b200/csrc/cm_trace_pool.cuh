@@ -63,8 +63,11 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 #define FLDI(f, j) __float_as_int(FLD(f, j))
 #define SETI(f, j, v) FLD(f, j) = __int_as_float(v)
 	const size_t globalWarp = (size_t)blockIdx.x * (kBlock / 32) + warpInBlock;
-	FastSeg *const arena = q.stackArena + ((globalWarp * K) * 32 + lane) * kPoolDepth;   // item j: + j * 32 * kPoolDepth
-#define STACK(j) (arena + (size_t)(j) * 32 * kPoolDepth)
+	// traversal stacks: entry d of item slot s is arena[d * slots + s] -- the entries of neighbouring slots at one depth
+	// share cache lines, so the few shallow depths that are ever used are a dense, L2-sized region
+	const size_t arenaSlots = (size_t)gridDim.x * kBlock * K;
+	FastSeg *const arena = q.stackArena + (globalWarp * K) * 32 + lane;                 // item j: + j * 32
+#define STACKAT(j, d) (arena + (size_t)(d) * arenaSlots + (size_t)(j) * 32)
 	PoolHdr *const hdrs = reinterpret_cast<PoolHdr *>(q.poolHdr) + (globalWarp * K) * 32 + lane;
 #define HDR(j) hdrs[(j) * 32]
 
@@ -99,7 +102,10 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			const int j = firstInMode<K>(modes, PM_DONE);
 			PoolHdr hd;
 			hd.slot = -1;
-			if (j >= 0) hd = HDR(j);
+			if (j >= 0) {
+				const float4 v = ldKeep(reinterpret_cast<const float4 *>(&HDR(j)), l2KeepPolicy());
+				hd.slot = __float_as_int(v.x); hd.planeRef = __float_as_int(v.y); hd.hitId = __float_as_int(v.z); hd.pad = 0;
+			}
 			if (hd.slot >= 0) {
 				FastLane L;
 				L.slot = hd.slot; L.fraction = FLD(PF_FRACTION, j); L.flags = FLDI(PF_FLAGS, j) & 0xff;
@@ -129,7 +135,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					FastLane L;
 					const int m = beginFast<false>(q, h, L, my);
 					hd.slot = L.slot; hd.planeRef = -1; hd.hitId = -1; hd.pad = 0;
-					HDR(j) = hd;
+					stKeep(reinterpret_cast<float4 *>(&HDR(j)), make_float4(__int_as_float(hd.slot), __int_as_float(-1), __int_as_float(-1), 0.0f), l2KeepPolicy());
 					FLD(PF_SX, j) = L.sx; FLD(PF_SY, j) = L.sy; FLD(PF_SZ, j) = L.sz;
 					FLD(PF_EX, j) = L.ex; FLD(PF_EY, j) = L.ey; FLD(PF_EZ, j) = L.ez;
 					FLD(PF_FRACTION, j) = 1.0f; SETI(PF_FLAGS, j, L.flags);
@@ -139,7 +145,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					SETI(PF_LAST0, j, -1); SETI(PF_LAST1, j, -1); SETI(PF_PEND, j, 0);
 					modes = withMode(modes, j, m == FM_PNODE ? PM_POS : PM_NODE);
 				} else {
-					HDR(j).slot = -1;                                 // nothing to write back next time
+					stKeep32(&HDR(j).slot, -1, l2KeepPolicy());        // nothing to write back next time
 					if (!supply) modes = withMode(modes, j, PM_EMPTY); // else: stays PM_DONE and asks again
 				}
 			}
@@ -225,7 +231,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (sp == 0) {
 					modes = withMode(modes, j, PM_DONE);
 				} else {
-					const float4 *sp4 = reinterpret_cast<const float4 *>(&STACK(j)[sp - 1]);
+					const float4 *sp4 = reinterpret_cast<const float4 *>(STACKAT(j, sp - 1));
 					const unsigned long long keep = l2KeepPolicy();
 					const float4 t0 = ldKeep(&sp4[0], keep), t1 = ldKeep(&sp4[1], keep), t2 = ldKeep(&sp4[2], keep);
 					SETI(PF_FLAGS, j, fl - 256);
@@ -280,7 +286,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const int fl = FLDI(PF_FLAGS, j);
 					const int sp = fl >> 8;
 					if (sp < kPoolDepth) {
-						float4 *sp4 = reinterpret_cast<float4 *>(&STACK(j)[sp]);
+						float4 *sp4 = reinterpret_cast<float4 *>(STACKAT(j, sp));
 						const unsigned long long keep = l2KeepPolicy();
 						stKeep(&sp4[0], make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)), keep);
 						stKeep(&sp4[1], make_float4(ay_ + ffar * (by_ - ay_), az_ + ffar * (bz_ - az_), bx_, by_), keep);
@@ -317,8 +323,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (COUNT) { cBrushSides += L.cBrushSides; cCross += L.cCross; }
 				FLD(PF_FRACTION, j) = L.fraction;
 				SETI(PF_FLAGS, j, (fl & ~0xff) | L.flags);
-				if (L.planeRef != kUnset) HDR(j).planeRef = L.planeRef;
-				if (L.hitId != kUnset) HDR(j).hitId = L.hitId;
+				if (L.planeRef != kUnset) stKeep32(&HDR(j).planeRef, L.planeRef, l2KeepPolicy());
+				if (L.hitId != kUnset) stKeep32(&HDR(j).hitId, L.hitId, l2KeepPolicy());
 				SETI(PF_LAST1, j, FLDI(PF_LAST0, j)); SETI(PF_LAST0, j, b);
 				modes = withMode(modes, j, over ? PM_DONE : PM_LEAF);
 			}
@@ -372,7 +378,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						} else {
 							const int fl = FLDI(PF_FLAGS, j);
 							const int sp = fl >> 8;
-							if (sp < kPoolDepth) { __stcg(&STACK(j)[sp].num, nd.y); SETI(PF_FLAGS, j, fl + 256); }
+							if (sp < kPoolDepth) { __stcg(&STACKAT(j, sp)->num, nd.y); SETI(PF_FLAGS, j, fl + 256); }
 							else atomicOr(q.status, 1);
 							SETI(PF_CUR, j, nd.x);
 						}
@@ -389,7 +395,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						if (sp == 0) {
 							modes = withMode(modes, j, PM_DONE);
 						} else {
-							SETI(PF_CUR, j, __ldcg(&STACK(j)[sp - 1].num));
+							SETI(PF_CUR, j, __ldcg(&STACKAT(j, sp - 1)->num));
 							SETI(PF_FLAGS, j, (fl - 256) & ~8);
 						}
 					} else {
@@ -420,7 +426,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 									if (inside) {
 										SETI(PF_FLAGS, j, FLDI(PF_FLAGS, j) | 3);
 										FLD(PF_FRACTION, j) = 0.0f;
-										HDR(j).hitId = b;
+										stKeep32(&HDR(j).hitId, b, l2KeepPolicy());
 										modes = withMode(modes, j, PM_DONE);
 									}
 								}
@@ -445,7 +451,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 #undef FLD
 #undef FLDI
 #undef SETI
-#undef STACK
+#undef STACKAT
 #undef HDR
 }
 
