@@ -34,6 +34,7 @@ constexpr int    kBlock          = 128;     // threads per CTA of the trace kern
 constexpr int    kChunk          = 256;     // most items a warp takes from the global cursor at a time (TraceBatch::chunk)
 constexpr int    kGang           = 4;       // lanes that must gather before a heavy block runs
 constexpr int    kMaxDepth       = 64;      // traversal stack entries per item (CMGPU_ERR_LIMIT beyond)
+constexpr int    kFacetSkips     = 8;       // facets a lane may skip per round before it walks the borders of one
 constexpr int    kMaxPosLeafs    = 1024;    // MAX_POSITION_LEAFS, cm_trace.c:190
 constexpr int    kBoxModelHandle = 1023;    // BOX_MODEL_HANDLE, cm_local.h:28
 constexpr double kClipEps        = 0.125;   // SURFACE_CLIP_EPSILON, cm_local.h:177
@@ -123,7 +124,7 @@ struct PointBatch {
 	int *out;
 };
 
-enum Mode : int { M_FETCH = 0, M_NODE, M_SPLIT, M_LEAF, M_BRUSH, M_SIDE, M_PATCH, M_PNODE, M_PLEAF, M_FINISH };
+enum Mode : int { M_FETCH = 0, M_NODE, M_SPLIT, M_LEAF, M_BRUSH, M_SIDE, M_PATCH, M_PNODE, M_PLEAF, M_FINISH, M_FACET };
 
 // ---- per-lane working set (registers) -----------------------------------------------------
 struct Lane {
@@ -284,101 +285,105 @@ __device__ __forceinline__ void pointPlaneRelation(const float4 pl, const Lane &
 	}
 }
 
+// The facet loops of CM_TracePointThroughPatchCollide (cm_patch.c:1264-1311) and CM_TraceThroughPatchCollide
+// (cm_patch.c:1383-1462) are cut in two so that the lanes of a warp stay together: facetSurface* decides from the
+// facet's own plane whether the facet can matter (most cannot: the reference `continue`s), facetBorders* walks the
+// border planes of one facet that can.
+struct FacetState {
+	int4 fc;                 // surfacePlane, numBorders, firstBorder
+	float4 sp;               // the surface plane
+	float t;                 // point sweep: intersection parameter of the surface plane
+	float enter, leave;      // box sweep
+	float bx, by, bz, bw;    // box sweep: best plane so far
+};
+
 template <bool COUNT>
-__device__ __forceinline__ void sweepPatchPoint(const DevMap &m, Lane &L, int firstPlane, int firstFacet, int numFacets) {
-	if (!m.playerCurveClip || !(L.flags & F_POINT)) return;
-	for (int f = 0; f < numFacets; f++) {
-		const int4 fc = __ldg(&m.facets[firstFacet + f]);
-		Cnt<COUNT>::add(L.cFacets);
-		const float4 sp = __ldg(&m.patchPlanes[firstPlane + fc.x]);
-		bool front; float t;
-		pointPlaneRelation(sp, L, front, t);
-		Cnt<COUNT>::add(L.cPatchPlanes);
-		if (!front) continue;
-		if (t < 0) continue;
-		if (t > L.fraction) continue;
-		int j;
-		for (j = 0; j < fc.y; j++) {
-			const int bd = __ldg(&m.borders[fc.z + j]);
-			const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
-			bool bfront; float bt;
-			pointPlaneRelation(bp, L, bfront, bt);
-			Cnt<COUNT>::add(L.cPatchPlanes);
-			const bool inward = bd < 0;
-			if (bfront != inward) {
-				if (bt > t) break;
-			} else {
-				if (bt < t) break;
-			}
-		}
-		if (j != fc.y) continue;
-		// hit: recompute with the 1/8 push-off, mixed widths as cm_patch.c:1300-1303
-		const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
-		const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
-		const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
-		const float off = dotf(cx, cy, cz, sp.x, sp.y, sp.z);
-		const float d1 = dotf(L.sx, L.sy, L.sz, sp.x, sp.y, sp.z) - sp.w + off;
-		const float d2 = dotf(L.ex, L.ey, L.ez, sp.x, sp.y, sp.z) - sp.w + off;
-		float fr = (float)(((double)d1 - kClipEps) / (double)(d1 - d2));
-		if (fr < 0) fr = 0;
-		L.fraction = fr;
-		L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;   // type/signbits stay stale
-	}
+__device__ __forceinline__ bool facetSurfacePoint(const DevMap &m, Lane &L, const int firstPlane, const int facet, FacetState &F) {
+	F.fc = __ldg(&m.facets[facet]);
+	Cnt<COUNT>::add(L.cFacets);
+	F.sp = __ldg(&m.patchPlanes[firstPlane + F.fc.x]);
+	bool front;
+	pointPlaneRelation(F.sp, L, front, F.t);
+	Cnt<COUNT>::add(L.cPatchPlanes);
+	return front && !(F.t < 0) && !(F.t > L.fraction);
 }
 
-// CM_TraceThroughPatchCollide, cm_patch.c:1368-1463
 template <bool COUNT>
-__device__ __forceinline__ void sweepPatch(const DevMap &m, Lane &L, int p) {
-	const float4 bmn = __ldg(&m.patchBox[2 * p]);
-	const float4 bmx = __ldg(&m.patchBox[2 * p + 1]);
-	if (L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
-	    L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps) return;
-	Cnt<COUNT>::add(L.cPatches);
-	const int4 pa = __ldg(&m.patchInfo[2 * p]);
-	const int4 pb = __ldg(&m.patchInfo[2 * p + 1]);
-	const int firstPlane = pa.z, firstFacet = pb.x, numFacets = pb.y;
-	if (L.flags & F_POINT) {
-		sweepPatchPoint<COUNT>(m, L, firstPlane, firstFacet, numFacets);
-		return;
+__device__ __forceinline__ void facetBordersPoint(const DevMap &m, Lane &L, const int firstPlane, const FacetState &F) {
+	const int4 fc = F.fc;
+	const float4 sp = F.sp;
+	const float t = F.t;
+	int j;
+	for (j = 0; j < fc.y; j++) {
+		const int bd = __ldg(&m.borders[fc.z + j]);
+		const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
+		bool bfront; float bt;
+		pointPlaneRelation(bp, L, bfront, bt);
+		Cnt<COUNT>::add(L.cPatchPlanes);
+		const bool inward = bd < 0;
+		if (bfront != inward) {
+			if (bt > t) break;
+		} else {
+			if (bt < t) break;
+		}
 	}
-	float bx = 0, by = 0, bz = 0, bw = 0;
-	for (int f = 0; f < numFacets; f++) {
-		const int4 fc = __ldg(&m.facets[firstFacet + f]);
-		Cnt<COUNT>::add(L.cFacets);
-		float enter = -1.0f, leave = 1.0f;
-		int hitnum = -1;
-		bool hit;
-		const float4 sp = __ldg(&m.patchPlanes[firstPlane + fc.x]);
-		{
-			const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
-			const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
-			const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
-			const float pw = sp.w - dotf(cx, cy, cz, sp.x, sp.y, sp.z);
-			if (!clipFacetPlane(sp.x, sp.y, sp.z, pw, L, enter, leave, hit)) continue;
-			if (hit) { bx = sp.x; by = sp.y; bz = sp.z; bw = pw; }
-		}
-		int j;
-		for (j = 0; j < fc.y; j++) {
-			const int bd = __ldg(&m.borders[fc.z + j]);
-			const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
-			Cnt<COUNT>::add(L.cPatchPlanes);
-			// corner by the ORIGINAL plane's sign bits, dotted with the possibly flipped plane
-			const float cx = bp.x < 0.0f ? L.p0x : L.n0x;
-			const float cy = bp.y < 0.0f ? L.p0y : L.n0y;
-			const float cz = bp.z < 0.0f ? L.p0z : L.n0z;
-			float px = bp.x, py = bp.y, pz = bp.z, pw = bp.w;
-			if (bd < 0) { px = -px; py = -py; pz = -pz; pw = -pw; }
-			const float off = dotf(cx, cy, cz, px, py, pz);
-			pw = pw + fabsf(off);        // double add of two floats rounded to float == float add
-			if (!clipFacetPlane(px, py, pz, pw, L, enter, leave, hit)) break;
-			if (hit) { hitnum = j; bx = px; by = py; bz = pz; bw = pw; }
-		}
-		if (j < fc.y) continue;
-		if (hitnum == fc.y - 1) continue;    // never clip against the back side
-		if (enter < leave && enter >= 0 && enter < L.fraction) {
-			L.fraction = enter;
-			L.pnx = bx; L.pny = by; L.pnz = bz; L.pd = bw;
-		}
+	if (j != fc.y) return;
+	// hit: recompute with the 1/8 push-off, mixed widths as cm_patch.c:1300-1303
+	const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
+	const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
+	const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
+	const float off = dotf(cx, cy, cz, sp.x, sp.y, sp.z);
+	const float d1 = dotf(L.sx, L.sy, L.sz, sp.x, sp.y, sp.z) - sp.w + off;
+	const float d2 = dotf(L.ex, L.ey, L.ez, sp.x, sp.y, sp.z) - sp.w + off;
+	float fr = (float)(((double)d1 - kClipEps) / (double)(d1 - d2));
+	if (fr < 0) fr = 0;
+	L.fraction = fr;
+	L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;   // type/signbits stay stale
+}
+
+template <bool COUNT>
+__device__ __forceinline__ bool facetSurfaceBox(const DevMap &m, Lane &L, const int firstPlane, const int facet, FacetState &F) {
+	F.fc = __ldg(&m.facets[facet]);
+	Cnt<COUNT>::add(L.cFacets);
+	F.enter = -1.0f; F.leave = 1.0f;
+	F.bx = F.by = F.bz = F.bw = 0.0f;
+	const float4 sp = __ldg(&m.patchPlanes[firstPlane + F.fc.x]);
+	const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
+	const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
+	const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
+	const float pw = sp.w - dotf(cx, cy, cz, sp.x, sp.y, sp.z);
+	bool hit;
+	if (!clipFacetPlane(sp.x, sp.y, sp.z, pw, L, F.enter, F.leave, hit)) return false;
+	if (hit) { F.bx = sp.x; F.by = sp.y; F.bz = sp.z; F.bw = pw; }
+	return true;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void facetBordersBox(const DevMap &m, Lane &L, const int firstPlane, FacetState &F) {
+	const int4 fc = F.fc;
+	int hitnum = -1;
+	bool hit;
+	int j;
+	for (j = 0; j < fc.y; j++) {
+		const int bd = __ldg(&m.borders[fc.z + j]);
+		const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
+		Cnt<COUNT>::add(L.cPatchPlanes);
+		// corner by the ORIGINAL plane's sign bits, dotted with the possibly flipped plane
+		const float cx = bp.x < 0.0f ? L.p0x : L.n0x;
+		const float cy = bp.y < 0.0f ? L.p0y : L.n0y;
+		const float cz = bp.z < 0.0f ? L.p0z : L.n0z;
+		float px = bp.x, py = bp.y, pz = bp.z, pw = bp.w;
+		if (bd < 0) { px = -px; py = -py; pz = -pz; pw = -pw; }
+		const float off = dotf(cx, cy, cz, px, py, pz);
+		pw = pw + fabsf(off);        // double add of two floats rounded to float == float add
+		if (!clipFacetPlane(px, py, pz, pw, L, F.enter, F.leave, hit)) break;
+		if (hit) { hitnum = j; F.bx = px; F.by = py; F.bz = pz; F.bw = pw; }
+	}
+	if (j < fc.y) return;
+	if (hitnum == fc.y - 1) return;      // never clip against the back side
+	if (F.enter < F.leave && F.enter >= 0 && F.enter < L.fraction) {
+		L.fraction = F.enter;
+		L.pnx = F.bx; L.pny = F.by; L.pnz = F.bz; L.pd = F.bw;
 	}
 }
 
@@ -603,7 +608,7 @@ __device__ __forceinline__ void finishItem(const TraceBatch &q, Lane &L) {
 // can make progress).  Running the expensive blocks with a full gang instead of whichever
 // one or two lanes happen to need them is what keeps the warp's lanes busy.
 #ifndef CMGPU_MIN_BLOCKS
-#define CMGPU_MIN_BLOCKS 1
+#define CMGPU_MIN_BLOCKS 4
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const DevMap m, const TraceBatch q) {
@@ -875,16 +880,53 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 				if (p >= 0) {
 					const int4 pa = __ldg(&m.patchInfo[2 * p]);
 					if (pa.y & L.mask) {
-						const float before = L.fraction;
-						sweepPatch<COUNT>(m, L, p);
-						if (L.fraction < before) {
-							L.surfaceFlags = pa.x;
-							L.contents = pa.y;
-							L.hitId = -2 - p;
+						// CM_TraceThroughPatchCollide starts with CM_BoundsIntersect (cm_patch.c:1376-1381)
+						const float4 bmn = __ldg(&m.patchBox[2 * p]);
+						const float4 bmx = __ldg(&m.patchBox[2 * p + 1]);
+						const bool apart = L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
+						                   L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps;
+						// a point sweep only clips against curves with cm_playerCurveClip set (cm_patch.c:1234)
+						if (!apart && !((L.flags & F_POINT) && !m.playerCurveClip)) {
+							Cnt<COUNT>::add(L.cPatches);
+							const int4 pb = __ldg(&m.patchInfo[2 * p + 1]);
+							// the facets are walked one per scheduler round (M_FACET); the brush cursor is idle meanwhile
+							L.brush = p; L.firstSide = pa.z; L.side = pb.x; L.sideEnd = pb.x + pb.y;
+							L.enter = L.fraction;                        // fraction before this patch (cm_trace.c:245)
+							mode = M_FACET;
+						} else if (!apart) {
+							Cnt<COUNT>::add(L.cPatches);
 						}
-						if (L.fraction == 0.0f) mode = M_FINISH;
 					}
 				}
+			}
+		}
+
+		// ---------------- one facet of the current patch, cm_patch.c:1264-1311 / 1383-1462 -----------------
+		// Lanes that are inside a patch run their facets together, whatever patch and facet each of them is at.
+		if (mode == M_FACET) {
+			// skip facets whose own plane already rules them out (cheap, the lanes stay together) ...
+			FacetState F;
+			bool cand = false;
+			const bool point = (L.flags & F_POINT) != 0;
+			#pragma unroll 1
+			for (int tries = 0; tries < kFacetSkips && L.side < L.sideEnd; tries++) {
+				cand = point ? facetSurfacePoint<COUNT>(m, L, L.firstSide, L.side, F) : facetSurfaceBox<COUNT>(m, L, L.firstSide, L.side, F);
+				L.side++;
+				if (cand) break;
+			}
+			// ... then walk the borders of the one that is left
+			if (cand) {
+				if (point) facetBordersPoint<COUNT>(m, L, L.firstSide, F);
+				else facetBordersBox<COUNT>(m, L, L.firstSide, F);
+			}
+			if (L.side >= L.sideEnd) {
+				if (L.fraction < L.enter) {                          // CM_TraceThroughPatch, cm_trace.c:247-252
+					const int4 pa = __ldg(&m.patchInfo[2 * L.brush]);
+					L.surfaceFlags = pa.x;
+					L.contents = pa.y;
+					L.hitId = -2 - L.brush;
+				}
+				mode = (L.fraction == 0.0f) ? M_FINISH : M_PATCH;
 			}
 		}
 
