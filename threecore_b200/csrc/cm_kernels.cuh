@@ -247,7 +247,8 @@ __device__ __forceinline__ void finishBrush(const DevMap &m, const TraceBatch &q
 
 // ---- patch facets, cm_patch.c:1220-1531 ------------------------------------------------
 
-// CM_CheckFacetPlane, cm_patch.c:1321-1360
+// CM_CheckFacetPlane, cm_patch.c:1321-1360.  One division for either kind of crossing (the numerator is selected),
+// so lanes that enter and lanes that leave a plane stay together.
 __device__ __forceinline__ bool clipFacetPlane(float px, float py, float pz, float pw, const Lane &L,
                                                float &enter, float &leave, bool &hit) {
 	hit = false;
@@ -255,12 +256,13 @@ __device__ __forceinline__ bool clipFacetPlane(float px, float py, float pz, flo
 	const float d2 = dotf(L.ex, L.ey, L.ez, px, py, pz) - pw;
 	if (d1 > 0 && (d2 >= 0.125f || d2 >= d1)) return false;
 	if (d1 <= 0 && d2 <= 0) return true;
-	if (d1 > d2) {
-		float f = (float)(((double)d1 - kClipEps) / (double)(d1 - d2));
+	const bool entering = d1 > d2;
+	const double num = entering ? (double)d1 - kClipEps : (double)d1 + kClipEps;
+	float f = (float)(num / (double)(d1 - d2));
+	if (entering) {
 		if (f < 0) f = 0;
 		if (f > enter) { enter = f; hit = true; }
 	} else {
-		float f = (float)(((double)d1 + kClipEps) / (double)(d1 - d2));
 		if (f > 1) f = 1;
 		if (f < leave) leave = f;
 	}
