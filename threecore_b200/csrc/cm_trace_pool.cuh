@@ -40,8 +40,10 @@ __device__ __forceinline__ int firstInMode(const unsigned modes, const int m) {
 }
 
 __device__ __forceinline__ unsigned withMode(const unsigned modes, const int j, const int m) {
+	// byte j of `modes` := one-hot(m): a byte permute that takes byte j from the second operand
 	const unsigned bit = m ? (1u << (m - 1)) : 0u;
-	return (modes & ~(0xffu << (8 * j))) | (bit << (8 * j));
+	const unsigned sel = 0x3210u ^ ((4u ^ (unsigned)j) << (4 * j));
+	return __byte_perm(modes, bit, sel);
 }
 
 #ifndef CMGPU_POOL_K
