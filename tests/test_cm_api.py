@@ -1,0 +1,172 @@
+"""The reference-facing layer (include/cm_public_batch.h): the CM_* names of cm_public.h and the SV_ClipMoveToEntities
+batching hook, called through ctypes exactly as the engine would bind them, against the oracle.
+
+The server-side merge (sv_world.c:497-549, 562-609) is restated below in Python -- it is a dozen lines of flag logic over
+the per-entity traces, which come from the oracle's CM_TransformedBoxTrace."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import assert_traces_equal, bspgen, cmoracle, cmref, get_map
+
+pytestmark = pytest.mark.gpu
+
+ENTITYNUM_NONE, ENTITYNUM_WORLD = 4095, 4094
+V3 = C.c_float * 3
+
+
+class Touch(C.Structure):          # cm_touch_t
+    _fields_ = [("entityNum", C.c_int), ("bmodel", C.c_int), ("modelindex", C.c_int),
+                ("mins", V3), ("maxs", V3), ("origin", V3), ("angles", V3)]
+
+
+@pytest.fixture(scope="module")
+def api():
+    from threecore_b200.engine import load_library
+    lib = load_library()
+    vp = C.c_void_p
+    lib.CM_LoadMapFromMemory.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+    lib.CM_LastError.restype = C.c_char_p
+    lib.CM_TempBoxModel.argtypes = [vp, vp]
+    lib.CM_BoxTrace.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int]
+    lib.CM_BoxTrace.restype = None
+    lib.CM_TransformedBoxTrace.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+    lib.CM_TransformedBoxTrace.restype = None
+    lib.CM_PointContents.argtypes = [vp, C.c_int]
+    lib.CM_TransformedPointContents.argtypes = [vp, C.c_int, vp, vp]
+    lib.CM_BoxTraceBatch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int]
+    lib.CM_ModelBounds.argtypes = [C.c_int, vp, vp]
+    lib.CM_ModelBounds.restype = None
+    lib.SV_ClipMovesToEntitiesBatch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    m = get_map("arena_models")
+    assert lib.CM_LoadMapFromMemory(b"maps/test.bsp", m.data, len(m.data), None) == 0, lib.CM_LastError()
+    from threecore_b200.engine import FlatMap
+    o = cmoracle.OracleCM(FlatMap.from_bsp(m.data).to_dict())
+    yield lib, m, o
+    lib.CM_ClearMap()
+
+
+def f3(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def test_single_calls_keep_the_reference_signatures(api):
+    """CM_BoxTrace / CM_TransformedBoxTrace / CM_PointContents one item at a time, as SV_Trace and trap_Trace call them"""
+    lib, m, o = api
+    n = 300
+    s, e = bspgen.make_sweeps(m, n, 21, len_short=(1.0, 300.0), len_long=(300.0, 2000.0))
+    mins, maxs = f3(bspgen.PLAYER_MINS), f3(bspgen.PLAYER_MAXS)
+    got = np.zeros(n, cmref.TRACE_DTYPE)
+    for i in range(n):
+        lib.CM_BoxTrace(got[i:i + 1].ctypes.data, s[i].ctypes.data, e[i].ctypes.data, mins.ctypes.data, maxs.ctypes.data,
+                        0, bspgen.MASK_PLAYERSOLID)
+    assert_traces_equal(got, o.box_trace(s, e, mins, maxs, mask=bspgen.MASK_PLAYERSOLID), "CM_BoxTrace")
+    # NULL mins/maxs mean a point (cm_trace.c:569-574)
+    got2 = np.zeros(n, cmref.TRACE_DTYPE)
+    for i in range(n):
+        lib.CM_BoxTrace(got2[i:i + 1].ctypes.data, s[i].ctypes.data, e[i].ctypes.data, None, None, 0, bspgen.MASK_SOLID)
+    assert_traces_equal(got2, o.box_trace(s, e, None, None, mask=bspgen.MASK_SOLID), "CM_BoxTrace NULL hull")
+    t = bspgen.make_entity_traces(m, n, 22)
+    got3 = np.zeros(n, cmref.TRACE_DTYPE)
+    pc = np.zeros(n, np.int32)
+    for i in range(n):
+        h = int(t["models"][i])
+        if h == 1023:
+            h = lib.CM_TempBoxModel(t["boxmins"][i].ctypes.data, t["boxmaxs"][i].ctypes.data)
+        lib.CM_TransformedBoxTrace(got3[i:i + 1].ctypes.data, t["starts"][i].ctypes.data, t["ends"][i].ctypes.data,
+                                   mins.ctypes.data, maxs.ctypes.data, h, bspgen.MASK_ALL,
+                                   t["origins"][i].ctypes.data, t["angles"][i].ctypes.data)
+        pc[i] = lib.CM_TransformedPointContents(t["starts"][i].ctypes.data, h, t["origins"][i].ctypes.data,
+                                                t["angles"][i].ctypes.data)
+    want3 = o.transformed_box_trace(t["starts"], t["ends"], mins, maxs, t["models"], bspgen.MASK_ALL, t["origins"], t["angles"],
+                                    t["boxmins"], t["boxmaxs"])
+    assert_traces_equal(got3, want3, "CM_TransformedBoxTrace")
+    assert np.array_equal(pc, o.point_contents(t["starts"], t["models"], t["origins"], t["angles"], t["boxmins"], t["boxmaxs"]))
+    pts = bspgen.make_points(m, n, 23)
+    c = np.array([lib.CM_PointContents(pts[i].ctypes.data, 0) for i in range(n)], np.int32)
+    assert np.array_equal(c, o.point_contents(pts))
+
+
+def _sv_trace_reference(o, s, e, mins, maxs, mask, touch_lists, ents):
+    """SV_Trace (sv_world.c:562-609) + SV_ClipMoveToEntities (:476-551) over the oracle's CM calls"""
+    n = len(s)
+    clip = o.box_trace(s, e, mins, maxs, mask=mask).copy()
+    clip["entityNum"] = np.where(clip["fraction"] != 1.0, ENTITYNUM_WORLD, ENTITYNUM_NONE)
+    # every (move, candidate) pair in one oracle batch
+    mv = np.concatenate([np.full(len(t), i) for i, t in enumerate(touch_lists)]).astype(np.int64)
+    en = np.concatenate(touch_lists).astype(np.int64)
+    tr = o.transformed_box_trace(s[mv], e[mv], mins, maxs, ents["handle"][en], mask, ents["origin"][en], ents["angles"][en],
+                                 ents["mins"][en], ents["maxs"][en])
+    k = 0
+    for i in range(n):
+        for ent in touch_lists[i]:
+            t = tr[k].copy()
+            k += 1
+            if clip[i]["allsolid"]:
+                continue
+            if t["allsolid"]:
+                clip[i]["allsolid"] = 1
+                t["entityNum"] = ents["number"][ent]
+            elif t["startsolid"]:
+                clip[i]["startsolid"] = 1
+                t["entityNum"] = ents["number"][ent]
+            if t["fraction"] < clip[i]["fraction"]:
+                old = clip[i]["startsolid"]
+                t["entityNum"] = ents["number"][ent]
+                clip[i] = t
+                clip[i]["startsolid"] |= old
+    return clip
+
+
+def test_sv_clip_moves_to_entities_batch(api):
+    """world trace, then all candidates of all moves in ONE batch, merged with the reference's rules"""
+    lib, m, o = api
+    rng = np.random.default_rng(31)
+    nm = m.num_models
+    E = 400
+    ents = dict(number=np.arange(E, dtype=np.int32) + 64,
+                bmodel=(rng.random(E) < 0.5), origin=f3(np.floor(rng.uniform(m.world_mins + 300, m.world_maxs - 300, size=(E, 3)))),
+                angles=f3(np.where(rng.random((E, 1)) < 0.5, 0.0, rng.uniform(0, 360, size=(E, 3)))),
+                mins=f3(-np.floor(rng.uniform(8, 48, size=(E, 3)))), maxs=f3(np.floor(rng.uniform(8, 64, size=(E, 3)))))
+    ents["modelindex"] = rng.integers(1, nm, size=E).astype(np.int32)
+    ents["handle"] = np.where(ents["bmodel"], ents["modelindex"], 1023).astype(np.int32)
+    ents["angles"][~ents["bmodel"]] = 0.0            # box entities do not rotate (sv_world.c:35-43 uses their bounds)
+    n = 3000
+    # moves aimed at entities so that the merge rules are exercised
+    tgt = rng.integers(0, E, size=n)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    reach = rng.uniform(40, 300, size=(n, 1))
+    s = f3(ents["origin"][tgt] + rng.uniform(-40, 40, size=(n, 3)) - d * reach)
+    e = f3(ents["origin"][tgt] + rng.uniform(-40, 40, size=(n, 3)) + d * reach * rng.uniform(-0.1, 1.0, size=(n, 1)))
+    s[:50] = ents["origin"][tgt[:50]]               # starts inside entities: startsolid / allsolid merging
+    mins, maxs = f3(bspgen.PLAYER_MINS), f3(bspgen.PLAYER_MAXS)
+    mask = bspgen.MASK_PLAYERSOLID | bspgen.CONTENTS_BODY
+    # world pass through the batched CM_BoxTrace, entityNum as SV_Trace sets it
+    clip = np.zeros(n, cmref.TRACE_DTYPE)
+    assert lib.CM_BoxTraceBatch(clip.ctypes.data, n, s.ctypes.data, e.ctypes.data, mins.ctypes.data, maxs.ctypes.data, 0, mask) == 0
+    clip["entityNum"] = np.where(clip["fraction"] != 1.0, ENTITYNUM_WORLD, ENTITYNUM_NONE)
+    # broad phase stays with the caller: the target plus a few random candidates, none for moves the world blocks at once
+    touch_lists = []
+    for i in range(n):
+        if clip[i]["fraction"] == 0:
+            touch_lists.append(np.zeros(0, np.int64))
+        else:
+            touch_lists.append(np.unique(np.concatenate([[tgt[i]], rng.integers(0, E, size=rng.integers(0, 5))])))
+    first = np.zeros(n + 1, np.int32)
+    first[1:] = np.cumsum([len(t) for t in touch_lists])
+    flat = np.concatenate(touch_lists).astype(np.int64)
+    arr = (Touch * len(flat))()
+    for k, ent in enumerate(flat):
+        arr[k].entityNum = int(ents["number"][ent]); arr[k].bmodel = int(ents["bmodel"][ent]); arr[k].modelindex = int(ents["modelindex"][ent])
+        arr[k].mins = V3(*ents["mins"][ent]); arr[k].maxs = V3(*ents["maxs"][ent])
+        arr[k].origin = V3(*ents["origin"][ent]); arr[k].angles = V3(*ents["angles"][ent])
+    masks = np.array([mask], np.int32)
+    rc = lib.SV_ClipMovesToEntitiesBatch(clip.ctypes.data, n, s.ctypes.data, e.ctypes.data, mins.ctypes.data, maxs.ctypes.data, 0,
+                                        masks.ctypes.data, 0, first.ctypes.data, C.byref(arr))
+    assert rc == 0, lib.CM_LastError()
+    want = _sv_trace_reference(o, s, e, mins, maxs, mask, touch_lists, ents)
+    assert_traces_equal(clip, want, "SV_ClipMovesToEntitiesBatch")
+    ent_hits = (clip["entityNum"] >= 64) & (clip["entityNum"] < 64 + E)
+    assert ent_hits.mean() > 0.2, "entities are not being hit"
+    assert (clip["startsolid"] == 1).sum() > 10
