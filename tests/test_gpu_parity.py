@@ -248,7 +248,8 @@ def test_binned_order_equals_input_order(eng, big):
     assert torch.equal(outs[0], big["out"][:n])
 
 
-@pytest.mark.parametrize("opts", [dict(pool=0), dict(pool=0, slab=0), dict(fast=0), dict(pool=1, slab=0), dict(pool=1, pool_reps=5, gang=8)])
+@pytest.mark.parametrize("opts", [dict(pool=0), dict(pool=0, slab=0), dict(fast=0), dict(pool=1, slab=0), dict(pool=1, pool_reps=5, gang=8),
+                                  dict(pool=0, simple_max_items=1 << 21), dict(pool=0, simple_max_items=1 << 21, bin=0, slab=0)])
 def test_kernel_variants_agree(eng, big, opts):
     """the general kernel, the one-item-per-lane hot kernel and the pool kernel must return the same bytes"""
     import torch
@@ -261,20 +262,24 @@ def test_kernel_variants_agree(eng, big, opts):
         torch.cuda.synchronize()
         eng.check_status()
     finally:
-        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=2, gang=4).items():
+        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=2, gang=4, simple_max_items=393216, bin=1).items():
             eng.set_option(k, v)
     assert torch.equal(o, big["out"][:n])
 
 
-def test_binning_small_batches_all_query_kinds(eng):
-    """force the binned path on small batches of every query kind (per-item hulls, models, temp boxes, rotations)"""
+@pytest.mark.parametrize("which", ["pool", "persistent"])
+def test_binning_small_batches_all_query_kinds(eng, which):
+    """force the binned path and the big-launch kernels on small batches of every query kind (per-item hulls, models,
+    temp boxes, rotations); by default launches this small run the thread-per-item kernel in input order"""
     eng.set_option("bin_min_items", 1)
-    eng.set_option("pool_min_items", 1)
+    eng.set_option("pool_min_items", 1 if which == "pool" else 1 << 30)
+    eng.set_option("simple_max_items", 0)
     try:
         for kind in ("arena_models", "patches_small"):
             m, o = load(eng, kind)
             for case in cases.world_cases(kind, n=5000) + cases.entity_cases(kind, n=5000):
                 check(eng, o, case)
     finally:
-        eng.set_option("bin_min_items", 1 << 15)
+        eng.set_option("bin_min_items", 98304)
         eng.set_option("pool_min_items", 1 << 20)
+        eng.set_option("simple_max_items", 393216)

@@ -8,6 +8,7 @@
 #include "cm_kernels.cuh"
 #include "cm_trace_fast.cuh"
 #include "cm_trace_pool.cuh"
+#include "cm_trace_simple.cuh"
 #include "../../include/cm_gpu.h"
 
 #include <math.h>
@@ -65,6 +66,7 @@ struct cmgpu_ctx_s {
 	bool usePool = true;                 // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
 	int poolReps = 2;                    // its repeats of a light step per round
 	int minChunk = 8;                    // fewest items a warp takes at a time in a small launch
+	int simpleMaxItems = 393216;         // launches up to this size use the thread-per-item kernel (lowest latency)
 	int poolMinItems = 1 << 20;          // smaller launches use the one-item-per-lane variant (lower latency)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
@@ -83,7 +85,7 @@ struct cmgpu_ctx_s {
 	BinGrid grid{};
 	bool binning = true;
 	bool binDir = false;
-	int binMinItems = 1 << 15;           // smaller batches are traced in input order
+	int binMinItems = 98304;             // smaller batches are traced in input order (the five binning launches cost ~50 us)
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bHist[kBinSlots];
 	DevBuf bPoolHdr[kBinSlots + 1];
@@ -626,7 +628,12 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		tEnd = pr.second;
 		CUDA_TRY(ctx, cudaEventRecord(pr.first, s));
 	}
-	if (pool) {
+	if (fast && !pool && q.n <= ctx->simpleMaxItems) {
+		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
+		const int nb = (q.n + kBlock - 1) / kBlock;
+		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<true>, nb, kBlock, 0, s, ctx->fast, q, h));
+		else               CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false>, nb, kBlock, 0, s, ctx->fast, q, h));
+	} else if (pool) {
 		q.lightReps = ctx->poolReps;
 		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * kPoolDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
@@ -806,6 +813,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "pool") ctx->usePool = value != 0;
 	else if (k == "pool_reps") ctx->poolReps = value < 1 ? 1 : (int)value;
 	else if (k == "min_chunk") ctx->minChunk = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
+	else if (k == "simple_max_items") ctx->simpleMaxItems = value < 0 ? 0 : (int)value;
 	else if (k == "pool_min_items") ctx->poolMinItems = value < 1 ? 1 : (int)value;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;

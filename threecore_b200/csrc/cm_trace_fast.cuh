@@ -701,4 +701,6 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 	}
 }
 
+#undef stackAt
+
 }  // namespace cmgpu
