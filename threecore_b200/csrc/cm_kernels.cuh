@@ -34,7 +34,7 @@ constexpr int    kBlock          = 128;     // threads per CTA of the trace kern
 constexpr int    kChunk          = 256;     // most items a warp takes from the global cursor at a time (TraceBatch::chunk)
 constexpr int    kGang           = 4;       // lanes that must gather before a heavy block runs
 constexpr int    kMaxDepth       = 64;      // traversal stack entries per item (CMGPU_ERR_LIMIT beyond)
-constexpr int    kFacetSkips     = 8;       // facets a lane may skip per round before it walks the borders of one
+constexpr int    kFacetPlaneSteps = 12;     // patch planes a lane tests per scheduler round
 constexpr int    kMaxPosLeafs    = 1024;    // MAX_POSITION_LEAFS, cm_trace.c:190
 constexpr int    kBoxModelHandle = 1023;    // BOX_MODEL_HANDLE, cm_local.h:28
 constexpr double kClipEps        = 0.125;   // SURFACE_CLIP_EPSILON, cm_local.h:177
@@ -288,105 +288,116 @@ __device__ __forceinline__ void pointPlaneRelation(const float4 pl, const Lane &
 }
 
 // The facet loops of CM_TracePointThroughPatchCollide (cm_patch.c:1264-1311) and CM_TraceThroughPatchCollide
-// (cm_patch.c:1383-1462) are cut in two so that the lanes of a warp stay together: facetSurface* decides from the
-// facet's own plane whether the facet can matter (most cannot: the reference `continue`s), facetBorders* walks the
-// border planes of one facet that can.
-struct FacetState {
-	int4 fc;                 // surfacePlane, numBorders, firstBorder
-	float4 sp;               // the surface plane
-	float t;                 // point sweep: intersection parameter of the surface plane
-	float enter, leave;      // box sweep
-	float bx, by, bz, bw;    // box sweep: best plane so far
-};
+// (cm_patch.c:1383-1462), re-cut as ONE PLANE PER STEP: the lanes of a warp that are inside patches all test one
+// plane against their sweep per step -- the surface plane of their current facet (cursor -1) or its border `cursor` --
+// whatever patch, facet and border each of them is at.  With the reference's nesting (facets, then a border loop that
+// breaks early) three of 32 lanes were active in this code.
+//
+// Per-lane facet state lives in registers that are idle while an item is inside a patch:
+//   L.side = facet, L.sideEnd, L.firstSide = first plane of the patch, L.brush = patch, L.enter = fraction before the patch
+//   L.lead = border cursor (-1: surface plane), L.bcontents = border that last raised enterFrac (-1: the surface plane,
+//   -2: none), L.leave = leaveFrac (box) / surface intersection t (point), L.kEnd = bits of enterFrac (box)
 
-template <bool COUNT>
-__device__ __forceinline__ bool facetSurfacePoint(const DevMap &m, Lane &L, const int firstPlane, const int facet, FacetState &F) {
-	F.fc = __ldg(&m.facets[facet]);
-	Cnt<COUNT>::add(L.cFacets);
-	F.sp = __ldg(&m.patchPlanes[firstPlane + F.fc.x]);
-	bool front;
-	pointPlaneRelation(F.sp, L, front, F.t);
-	Cnt<COUNT>::add(L.cPatchPlanes);
-	return front && !(F.t < 0) && !(F.t > L.fraction);
+// the plane a box sweep clips against for facet plane `which` (-1 surface, else border index): cm_patch.c:1390-1402, 1412-1426
+__device__ __forceinline__ float4 facetClipPlane(const DevMap &m, const Lane &L, const int firstPlane, const int4 fc, const int which) {
+	if (which < 0) {
+		const float4 sp = __ldg(&m.patchPlanes[firstPlane + fc.x]);
+		const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
+		const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
+		const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
+		return make_float4(sp.x, sp.y, sp.z, sp.w - dotf(cx, cy, cz, sp.x, sp.y, sp.z));
+	}
+	const int bd = __ldg(&m.borders[fc.z + which]);
+	const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
+	// corner by the ORIGINAL plane's sign bits, dotted with the possibly flipped plane
+	const float cx = bp.x < 0.0f ? L.p0x : L.n0x;
+	const float cy = bp.y < 0.0f ? L.p0y : L.n0y;
+	const float cz = bp.z < 0.0f ? L.p0z : L.n0z;
+	float px = bp.x, py = bp.y, pz = bp.z, pw = bp.w;
+	if (bd < 0) { px = -px; py = -py; pz = -pz; pw = -pw; }
+	const float off = dotf(cx, cy, cz, px, py, pz);
+	return make_float4(px, py, pz, pw + fabsf(off));     // double add of two floats rounded to float == float add
 }
 
+// one plane of a box sweep's current facet; returns true when the patch is finished
 template <bool COUNT>
-__device__ __forceinline__ void facetBordersPoint(const DevMap &m, Lane &L, const int firstPlane, const FacetState &F) {
-	const int4 fc = F.fc;
-	const float4 sp = F.sp;
-	const float t = F.t;
-	int j;
-	for (j = 0; j < fc.y; j++) {
-		const int bd = __ldg(&m.borders[fc.z + j]);
-		const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
-		bool bfront; float bt;
-		pointPlaneRelation(bp, L, bfront, bt);
+__device__ __forceinline__ bool facetPlaneStepBox(const DevMap &m, Lane &L) {
+	const int4 fc = __ldg(&m.facets[L.side]);
+	const int cur = L.lead;
+	if (cur < 0) {                                   // a new facet starts (cm_patch.c:1384-1388)
+		Cnt<COUNT>::add(L.cFacets);
+		L.kEnd = __float_as_int(-1.0f);
+		L.leave = 1.0f;
+		L.bcontents = -2;
+	} else {
 		Cnt<COUNT>::add(L.cPatchPlanes);
-		const bool inward = bd < 0;
-		if (bfront != inward) {
-			if (bt > t) break;
-		} else {
-			if (bt < t) break;
+	}
+	const float4 pl = facetClipPlane(m, L, L.firstSide, fc, cur);
+	float enter = __int_as_float(L.kEnd), leave = L.leave;
+	bool hit;
+	const bool ok = clipFacetPlane(pl.x, pl.y, pl.z, pl.w, L, enter, leave, hit);
+	bool facetDone = !ok;
+	if (ok) {
+		L.kEnd = __float_as_int(enter);
+		L.leave = leave;
+		if (hit) L.bcontents = cur;
+		L.lead = cur + 1;
+		if (L.lead >= fc.y) {                        // all borders passed (cm_patch.c:1440-1461)
+			facetDone = true;
+			const bool backSide = L.bcontents == fc.y - 1;        // never clip against the back side
+			if (!backSide && enter < leave && enter >= 0 && enter < L.fraction) {
+				L.fraction = enter;
+				const float4 best = facetClipPlane(m, L, L.firstSide, fc, L.bcontents);   // same float ops, same plane
+				L.pnx = best.x; L.pny = best.y; L.pnz = best.z; L.pd = best.w;
+			}
 		}
 	}
-	if (j != fc.y) return;
-	// hit: recompute with the 1/8 push-off, mixed widths as cm_patch.c:1300-1303
-	const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
-	const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
-	const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
-	const float off = dotf(cx, cy, cz, sp.x, sp.y, sp.z);
-	const float d1 = dotf(L.sx, L.sy, L.sz, sp.x, sp.y, sp.z) - sp.w + off;
-	const float d2 = dotf(L.ex, L.ey, L.ez, sp.x, sp.y, sp.z) - sp.w + off;
-	float fr = (float)(((double)d1 - kClipEps) / (double)(d1 - d2));
-	if (fr < 0) fr = 0;
-	L.fraction = fr;
-	L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;   // type/signbits stay stale
+	if (facetDone) { L.side++; L.lead = -1; }
+	return L.side >= L.sideEnd;
 }
 
+// one plane of a point sweep's current facet (cm_patch.c:1264-1311); returns true when the patch is finished
 template <bool COUNT>
-__device__ __forceinline__ bool facetSurfaceBox(const DevMap &m, Lane &L, const int firstPlane, const int facet, FacetState &F) {
-	F.fc = __ldg(&m.facets[facet]);
-	Cnt<COUNT>::add(L.cFacets);
-	F.enter = -1.0f; F.leave = 1.0f;
-	F.bx = F.by = F.bz = F.bw = 0.0f;
-	const float4 sp = __ldg(&m.patchPlanes[firstPlane + F.fc.x]);
-	const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
-	const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
-	const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
-	const float pw = sp.w - dotf(cx, cy, cz, sp.x, sp.y, sp.z);
-	bool hit;
-	if (!clipFacetPlane(sp.x, sp.y, sp.z, pw, L, F.enter, F.leave, hit)) return false;
-	if (hit) { F.bx = sp.x; F.by = sp.y; F.bz = sp.z; F.bw = pw; }
-	return true;
-}
-
-template <bool COUNT>
-__device__ __forceinline__ void facetBordersBox(const DevMap &m, Lane &L, const int firstPlane, FacetState &F) {
-	const int4 fc = F.fc;
-	int hitnum = -1;
-	bool hit;
-	int j;
-	for (j = 0; j < fc.y; j++) {
-		const int bd = __ldg(&m.borders[fc.z + j]);
-		const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
-		Cnt<COUNT>::add(L.cPatchPlanes);
-		// corner by the ORIGINAL plane's sign bits, dotted with the possibly flipped plane
-		const float cx = bp.x < 0.0f ? L.p0x : L.n0x;
-		const float cy = bp.y < 0.0f ? L.p0y : L.n0y;
-		const float cz = bp.z < 0.0f ? L.p0z : L.n0z;
-		float px = bp.x, py = bp.y, pz = bp.z, pw = bp.w;
-		if (bd < 0) { px = -px; py = -py; pz = -pz; pw = -pw; }
-		const float off = dotf(cx, cy, cz, px, py, pz);
-		pw = pw + fabsf(off);        // double add of two floats rounded to float == float add
-		if (!clipFacetPlane(px, py, pz, pw, L, F.enter, F.leave, hit)) break;
-		if (hit) { hitnum = j; F.bx = px; F.by = py; F.bz = pz; F.bw = pw; }
+__device__ __forceinline__ bool facetPlaneStepPoint(const DevMap &m, Lane &L) {
+	const int4 fc = __ldg(&m.facets[L.side]);
+	const int cur = L.lead;
+	Cnt<COUNT>::add(L.cPatchPlanes);
+	bool facetDone;
+	if (cur < 0) {
+		Cnt<COUNT>::add(L.cFacets);
+		const float4 sp = __ldg(&m.patchPlanes[L.firstSide + fc.x]);
+		bool front; float t;
+		pointPlaneRelation(sp, L, front, t);
+		facetDone = !front || t < 0 || t > L.fraction;
+		L.leave = t;
+	} else {
+		const int bd = __ldg(&m.borders[fc.z + cur]);
+		const float4 bp = __ldg(&m.patchPlanes[L.firstSide + (bd & 0x7fffffff)]);
+		bool bfront; float bt;
+		pointPlaneRelation(bp, L, bfront, bt);
+		const bool inward = bd < 0;
+		facetDone = (bfront != inward) ? (bt > L.leave) : (bt < L.leave);
 	}
-	if (j < fc.y) return;
-	if (hitnum == fc.y - 1) return;      // never clip against the back side
-	if (F.enter < F.leave && F.enter >= 0 && F.enter < L.fraction) {
-		L.fraction = F.enter;
-		L.pnx = F.bx; L.pny = F.by; L.pnz = F.bz; L.pd = F.bw;
+	if (!facetDone) {
+		L.lead = cur + 1;
+		if (L.lead >= fc.y) {
+			facetDone = true;
+			// hit: recompute with the 1/8 push-off, mixed widths as cm_patch.c:1300-1303
+			const float4 sp = __ldg(&m.patchPlanes[L.firstSide + fc.x]);
+			const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
+			const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
+			const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
+			const float off = dotf(cx, cy, cz, sp.x, sp.y, sp.z);
+			const float d1 = dotf(L.sx, L.sy, L.sz, sp.x, sp.y, sp.z) - sp.w + off;
+			const float d2 = dotf(L.ex, L.ey, L.ez, sp.x, sp.y, sp.z) - sp.w + off;
+			float fr = (float)(((double)d1 - kClipEps) / (double)(d1 - d2));
+			if (fr < 0) fr = 0;
+			L.fraction = fr;
+			L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;   // type/signbits stay stale
+		}
 	}
+	if (facetDone) { L.side++; L.lead = -1; }
+	return L.side >= L.sideEnd;
 }
 
 // CM_PositionTestInPatchCollide, cm_patch.c:1479-1531
@@ -633,7 +644,9 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 		const unsigned census = __reduce_add_sync(0xffffffffu, key);
 		const int nFetch = census & 63, nSplit = (census >> 6) & 63, nBrush = (census >> 12) & 63;
 		const int nSide = (census >> 18) & 63, nFinish = (census >> 24) & 63;
-		const int nLight = 32 - (nFetch + nSplit + nBrush + nSide + nFinish);
+		// lanes grinding through patch planes take many rounds per patch: parked lanes must not wait for them
+		const int nFacet = __popc(__ballot_sync(0xffffffffu, mode == M_FACET));
+		const int nLight = 32 - (nFetch + nSplit + nBrush + nSide + nFinish) - nFacet;
 		const int gang = min(q.gang, nLight);          // 0 when only parked lanes are left: run everything
 
 		// ---------------- write results, free lanes -----------------
@@ -893,6 +906,7 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 							const int4 pb = __ldg(&m.patchInfo[2 * p + 1]);
 							// the facets are walked one per scheduler round (M_FACET); the brush cursor is idle meanwhile
 							L.brush = p; L.firstSide = pa.z; L.side = pb.x; L.sideEnd = pb.x + pb.y;
+							L.lead = -1;                                 // at the surface plane of the first facet
 							L.enter = L.fraction;                        // fraction before this patch (cm_trace.c:245)
 							mode = M_FACET;
 						} else if (!apart) {
@@ -906,29 +920,23 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 		// ---------------- one facet of the current patch, cm_patch.c:1264-1311 / 1383-1462 -----------------
 		// Lanes that are inside a patch run their facets together, whatever patch and facet each of them is at.
 		if (mode == M_FACET) {
-			// skip facets whose own plane already rules them out (cheap, the lanes stay together) ...
-			FacetState F;
-			bool cand = false;
 			const bool point = (L.flags & F_POINT) != 0;
 			#pragma unroll 1
-			for (int tries = 0; tries < kFacetSkips && L.side < L.sideEnd; tries++) {
-				cand = point ? facetSurfacePoint<COUNT>(m, L, L.firstSide, L.side, F) : facetSurfaceBox<COUNT>(m, L, L.firstSide, L.side, F);
-				L.side++;
-				if (cand) break;
-			}
-			// ... then walk the borders of the one that is left
-			if (cand) {
-				if (point) facetBordersPoint<COUNT>(m, L, L.firstSide, F);
-				else facetBordersBox<COUNT>(m, L, L.firstSide, F);
-			}
-			if (L.side >= L.sideEnd) {
-				if (L.fraction < L.enter) {                          // CM_TraceThroughPatch, cm_trace.c:247-252
-					const int4 pa = __ldg(&m.patchInfo[2 * L.brush]);
-					L.surfaceFlags = pa.x;
-					L.contents = pa.y;
-					L.hitId = -2 - L.brush;
+			for (int it = 0; it < kFacetPlaneSteps; it++) {
+				bool patchDone = true;
+				if (mode == M_FACET) {
+					patchDone = (L.side >= L.sideEnd) ? true : (point ? facetPlaneStepPoint<COUNT>(m, L) : facetPlaneStepBox<COUNT>(m, L));
+					if (patchDone) {
+						if (L.fraction < L.enter) {                  // CM_TraceThroughPatch, cm_trace.c:247-252
+							const int4 pa = __ldg(&m.patchInfo[2 * L.brush]);
+							L.surfaceFlags = pa.x;
+							L.contents = pa.y;
+							L.hitId = -2 - L.brush;
+						}
+						mode = (L.fraction == 0.0f) ? M_FINISH : M_PATCH;
+					}
 				}
-				mode = (L.fraction == 0.0f) ? M_FINISH : M_PATCH;
+				if (!__any_sync(__activemask(), mode == M_FACET)) break;
 			}
 		}
 
