@@ -31,7 +31,10 @@ thread_local std::string g_createError;
 
 constexpr int kCursorSlots = 64;
 constexpr size_t kPoolSmem = (size_t)(kBlock / 32) * PF_COUNT * CMGPU_POOL_K * 32 * sizeof(float);
-constexpr int kBinSlots = 3;             // histogram tables, one per pipeline stream
+#ifndef CMGPU_PIPE_STREAMS
+#define CMGPU_PIPE_STREAMS 3
+#endif
+constexpr int kBinSlots = CMGPU_PIPE_STREAMS;   // pipeline streams of the host-pointer calls, each with its own workspaces
 constexpr int kPipeChunks = 64;          // upper bound on the pieces a host batch is cut into (copies overlap the kernels)
 constexpr size_t kMinChunkItems = 1 << 16;
 
@@ -71,7 +74,7 @@ struct cmgpu_ctx_s {
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	bool useFast = true;
-	int pipeChunks = 16;                 // pieces a host batch is cut into
+	int pipeChunks = 32;                 // pieces a host batch is cut into
 	// optional CUDA-event timing of the trace kernel alone (cmgpu_kernel_timing)
 	bool timing = false;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timingPairs;
@@ -97,7 +100,7 @@ struct cmgpu_ctx_s {
 	bool extBusy = false;
 	int *hStatus = nullptr;              // pinned
 	unsigned long long launches = 0;
-	cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+	cudaStream_t streams[kBinSlots] = {};
 	cudaEvent_t evt[kPipeChunks] = {};
 	// grow-only staging for the host-pointer entry points
 	DevBuf bStarts, bEnds, bMins, bMaxs, bModels, bMasks, bOrigins, bRot, bRotIdx, bBoxMins, bBoxMaxs, bOut, bHit;
@@ -757,9 +760,10 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	freeMap(ctx);
 	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
 	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit,
-	                  &ctx->bKeys, &ctx->bRecs, &ctx->bHist[0], &ctx->bHist[1], &ctx->bHist[2],
-	                  &ctx->bStackArena[0], &ctx->bStackArena[1], &ctx->bStackArena[2], &ctx->bStackArena[3],
-	                  &ctx->bPoolHdr[0], &ctx->bPoolHdr[1], &ctx->bPoolHdr[2], &ctx->bPoolHdr[3]}) releaseBuf(*b);
+	                  &ctx->bKeys, &ctx->bRecs}) releaseBuf(*b);
+	for (auto &b : ctx->bHist) releaseBuf(b);
+	for (auto &b : ctx->bStackArena) releaseBuf(b);
+	for (auto &b : ctx->bPoolHdr) releaseBuf(b);
 	if (ctx->extDone) cudaEventDestroy(ctx->extDone);
 	for (auto &pr : ctx->timingPairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
@@ -964,7 +968,7 @@ int cmgpu_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points
 
 // ---- host-pointer entry points -----------------------------------------------------------
 // The batch is cut into chunks; chunk c's H2D copy, kernel and D2H copy are issued on stream
-// c % 3, so the copy engines (one per direction) and the SMs work on different chunks at once.
+// c % kBinSlots, so the copy engines (one per direction) and the SMs work on different chunks at once.
 static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
                      const float *mins, const float *maxs, int hull_stride,
                      const int32_t *models, const int32_t *masks, int mask_stride,
@@ -1027,7 +1031,7 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 		const size_t lo = N * (size_t)c / (size_t)chunks, hi = N * (size_t)(c + 1) / (size_t)chunks;
 		const size_t cnt = hi - lo;
 		if (!cnt) continue;
-		cudaStream_t s = ctx->streams[c % 3];
+		cudaStream_t s = ctx->streams[c % kBinSlots];
 #define H2D(buf, src, elem) CUDA_TRY(ctx, cudaMemcpyAsync((char *)(buf).p + lo * (elem), (const char *)(src) + lo * (elem), cnt * (elem), cudaMemcpyHostToDevice, s))
 		H2D(ctx->bStarts, starts, v3);
 		H2D(ctx->bEnds, ends, v3);
@@ -1068,7 +1072,7 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 		q.hitIds = hit_ids ? (int *)ctx->bHit.p + lo : nullptr;
 		q.status = ctx->dStatus;
 		q.counters = ctx->dCounters;
-		if ((rc = launchTrace(ctx, q, s, lo, c % 3))) return rc;
+		if ((rc = launchTrace(ctx, q, s, lo, c % kBinSlots))) return rc;
 		CUDA_TRY(ctx, cudaMemcpyAsync(results + lo, (cmgpu_trace_t *)ctx->bOut.p + lo, cnt * sizeof(cmgpu_trace_t), cudaMemcpyDeviceToHost, s));
 		if (hit_ids) CUDA_TRY(ctx, cudaMemcpyAsync(hit_ids + lo, (int *)ctx->bHit.p + lo, cnt * 4, cudaMemcpyDeviceToHost, s));
 	}
