@@ -48,3 +48,25 @@ pc2 = torch.empty(n, dtype=torch.int32, device=dev)
 timed("config 4: 4Mi CM_TransformedPointContents", n,
       lambda: eng.point_contents_device(d["starts"], pc2, models=d["models"], origins=d["origins"], rotations=drot, rot_index=dridx,
                                         boxmins=d["boxmins"], boxmaxs=d["boxmaxs"]))
+
+# ---- the reference's CPU code on the same inputs (oracle/_ref, one forked worker per host core; shared hulls only,
+# so config 3 is timed as its point half and its hull half) -- a reported baseline like bench.py's cpu_baseline
+try:
+    from oracle import cmref
+    import bench as _b
+    cores = _b.host_cores()
+    if cmref.available():
+        def cpu(label, data, s, e, mins, maxs, mask, k=200000):
+            r = cmref.RefCM().load(data)
+            secs, _, _ = r.bench_box_trace(s[:k], e[:k], mins, maxs, mask, nworkers=cores, repeats=1)
+            print(f"reference, {cores} cores, {label:44s}: {min(k, len(s))/secs/1e6:8.2f} M/s", flush=True)
+        m1 = bspgen.room_map(n_brushes=500, seed=0xC0FFEE01)
+        s, e = bspgen.make_point_sweeps(m1, 1 << 20, 0xBADC0DE1)
+        cpu("config 1 point traces", m1.data, s, e, None, None, bspgen.MASK_SOLID, k=1 << 20)
+        m3 = bspgen.patch_map(n_brushes=2000, n_patches=512, seed=0xC0FFEE03)
+        s, e, mins, maxs = bspgen.make_patch_sweeps(m3, 1 << 20, 0xBADC0DE3)
+        pt = (mins == 0).all(axis=1)
+        cpu("config 3 point half", m3.data, s[pt], e[pt], None, None, bspgen.MASK_ALL, k=400000)
+        cpu("config 3 player-hull half", m3.data, s[~pt], e[~pt], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_ALL, k=400000)
+except Exception as ex:      # the reference library is optional on the GPU box
+    print("reference timing skipped:", ex)
