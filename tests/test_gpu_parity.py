@@ -262,7 +262,7 @@ def test_kernel_variants_agree(eng, big, opts):
         torch.cuda.synchronize()
         eng.check_status()
     finally:
-        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=2, gang=4, simple_max_items=393216, bin=1).items():
+        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=1, gang=4, simple_max_items=393216, bin=1).items():
             eng.set_option(k, v)
     assert torch.equal(o, big["out"][:n])
 

@@ -14,7 +14,14 @@
 
 namespace cmgpu {
 
+#ifndef CMGPU_NODE_LEVELS
+#define CMGPU_NODE_LEVELS 3
+#endif
+#ifndef CMGPU_LEAF_PAIR
+#define CMGPU_LEAF_PAIR 1
+#endif
 constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
+constexpr int kNodeLevels = CMGPU_NODE_LEVELS;   // tree levels a lane may descend per repeat of the node step
 constexpr int kVoteEnough = 20;          // a step kind that this many lanes can run is run without looking further
 
 // step kinds an item can wait for (one-hot bit m-1 of its mode byte).  PM_POS is the position test; bit 3 of the item's
@@ -155,29 +162,38 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 		}
 		if (cNode >= thr) {
 			// ---------------- axial nodes of CM_TraceThroughTree, cm_trace.c:456-486 -----------------
+			// up to kNodeLevels tree levels per repeat: a plain descent to another node goes straight on
 			#pragma unroll 1
 			for (int rep = 0; rep < q.lightReps; rep++) {
 				const int j = firstInMode<K>(modes, PM_NODE);
 				if (!__any_sync(0xffffffffu, j >= 0)) break;
 				if (j >= 0) {
-					const int num = FLDI(PF_CUR, j);
-					const int4 nd = __ldg(&fm.nodes[num]);
-					if (COUNT) cNodes++;
-					const int ax = nd.z < 3 ? nd.z : 0;
-					const float dist = __int_as_float(nd.w);
-					const float t1 = FLD(PF_AX + ax, j) - dist;
-					const float t2 = FLD(PF_BX + ax, j) - dist;
-					const float hi = ax == 0 ? h.nodeHi[0] : (ax == 1 ? h.nodeHi[1] : h.nodeHi[2]);
-					const float lo = ax == 0 ? h.nodeLo[0] : (ax == 1 ? h.nodeLo[1] : h.nodeLo[2]);
-					const bool front = t1 >= hi && t2 >= hi;
-					const bool back = t1 < lo && t2 < lo;
-					// one update of the cursor and of the step kind, no divergent tails
-					const bool go = nd.z < 3 && (front || back);          // else: split or non-axial node
-					const int c = front ? nd.x : nd.y;
-					const bool leaf = go && c < 0;
-					SETI(PF_CUR, j, go ? (c < 0 ? -1 - c : c) : num);
-					if (COUNT) cLeafs += leaf ? 1u : 0u;
-					if (!go || leaf) modes = withMode(modes, j, leaf ? PM_LEAF : PM_SPLIT);
+					int num = FLDI(PF_CUR, j);
+					int next = PM_NODE;
+					#pragma unroll
+					for (int lvl = 0; lvl < kNodeLevels; lvl++) {
+						if (next == PM_NODE) {
+							const int4 nd = __ldg(&fm.nodes[num]);
+							if (COUNT) cNodes++;
+							const int ax = nd.z < 3 ? nd.z : 0;
+							const float dist = __int_as_float(nd.w);
+							const float t1 = FLD(PF_AX + ax, j) - dist;
+							const float t2 = FLD(PF_BX + ax, j) - dist;
+							const float hi = ax == 0 ? h.nodeHi[0] : (ax == 1 ? h.nodeHi[1] : h.nodeHi[2]);
+							const float lo = ax == 0 ? h.nodeLo[0] : (ax == 1 ? h.nodeLo[1] : h.nodeLo[2]);
+							const bool front = t1 >= hi && t2 >= hi;
+							const bool back = t1 < lo && t2 < lo;
+							const bool go = nd.z < 3 && (front || back);      // else: split or non-axial node
+							const int c = front ? nd.x : nd.y;
+							const bool leaf = go && c < 0;
+							if (go) num = c < 0 ? -1 - c : c;
+							if (COUNT) cLeafs += leaf ? 1u : 0u;
+							next = !go ? PM_SPLIT : (leaf ? PM_LEAF : PM_NODE);
+						}
+					}
+					// one update of the cursor and of the step kind
+					SETI(PF_CUR, j, num);
+					if (next != PM_NODE) modes = withMode(modes, j, next);
 				}
 			}
 		}
@@ -191,19 +207,39 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const int k = FLDI(PF_CUR, j);
 					const float4 e0 = __ldg(&fm.stream[2 * k]);
 					const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
-					SETI(PF_CUR, j, k + 1);
-					const int b = __float_as_int(e1.w);
-					if (COUNT) cBrushRefs += b >= 0 ? 1u : 0u;
-					const bool want = b >= 0 && (__float_as_int(e0.w) & h.mask) != 0 && b != FLDI(PF_LAST0, j) && b != FLDI(PF_LAST1, j);
-					if (COUNT) cBrushBounds += want ? 1u : 0u;
+#if CMGPU_LEAF_PAIR
+					// two entries per repeat (the stream has a spare sentinel at its end, so the second load is always in
+					// bounds); the second one is only looked at when the first neither ends the leaf nor needs clipping
+					const float4 g0 = __ldg(&fm.stream[2 * k + 2]);
+					const float4 g1 = __ldg(&fm.stream[2 * k + 3]);
+#endif
+					const int last0 = FLDI(PF_LAST0, j), last1 = FLDI(PF_LAST1, j);
 					const float sx = FLD(PF_SX, j), sy = FLD(PF_SY, j), sz = FLD(PF_SZ, j);
 					const float ex = FLD(PF_EX, j), ey = FLD(PF_EY, j), ez = FLD(PF_EZ, j);
 					// tw.bounds (cm_trace.c:628-636), recomputed instead of stored
 					const float lox = (sx < ex ? sx : ex) + h.n0[0], hix = (sx < ex ? ex : sx) + h.p0[0];
 					const float loy = (sy < ey ? sy : ey) + h.n0[1], hiy = (sy < ey ? ey : sy) + h.p0[1];
 					const float loz = (sz < ez ? sz : ez) + h.n0[2], hiz = (sz < ez ? ez : sz) + h.p0[2];
-					const bool apart = hix < e0.x || hiy < e0.y || hiz < e0.z || lox > e1.x || loy > e1.y || loz > e1.z;
-					const bool clip = want && !apart;                     // CM_BoundsIntersect passed
+					const int b0 = __float_as_int(e1.w);
+					const bool want0 = b0 >= 0 && (__float_as_int(e0.w) & h.mask) != 0 && b0 != last0 && b0 != last1;
+					const bool apart0 = hix < e0.x || hiy < e0.y || hiz < e0.z || lox > e1.x || loy > e1.y || loz > e1.z;
+					const bool clip0 = want0 && !apart0;                               // CM_BoundsIntersect passed
+#if CMGPU_LEAF_PAIR
+					const int b1 = __float_as_int(g1.w);
+					const bool want1 = b1 >= 0 && (__float_as_int(g0.w) & h.mask) != 0 && b1 != last0 && b1 != last1;
+					const bool apart1 = hix < g0.x || hiy < g0.y || hiz < g0.z || lox > g1.x || loy > g1.y || loz > g1.z;
+					const bool clip1 = want1 && !apart1;
+					const bool stop0 = b0 < 0 || clip0;                                // the first entry decides alone
+					const int b = stop0 ? b0 : b1;
+					const bool clip = stop0 ? clip0 : clip1;
+					if (COUNT) { cBrushRefs += (b0 >= 0 ? 1u : 0u) + (!stop0 && b1 >= 0 ? 1u : 0u); cBrushBounds += (want0 ? 1u : 0u) + (!stop0 && want1 ? 1u : 0u); }
+					SETI(PF_CUR, j, k + (stop0 ? 1 : 2));
+#else
+					const int b = b0;
+					const bool clip = clip0;
+					if (COUNT) { cBrushRefs += b0 >= 0 ? 1u : 0u; cBrushBounds += want0 ? 1u : 0u; }
+					SETI(PF_CUR, j, k + 1);
+#endif
 					if (clip) SETI(PF_PEND, j, b);
 					if (b < 0 || clip)
 						modes = withMode(modes, j, b < 0 ? PM_POP : ((FLDI(PF_FLAGS, j) & 4) ? PM_SLAB : PM_BRUSH));
