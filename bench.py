@@ -277,7 +277,7 @@ def run_ours(args):
         tr = ncu_traffic()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr or {}).get("dram_bytes_per_launch") if n == N_RAYS else None, "peak_source": peak_src,
-                "kernel": "cmgpu::tracePoolKernel<false, 2>", "kernel_ms": kms, "kernel_launches": trace_launches,
+                "kernel": "cmgpu::tracePoolKernel<false, 3>", "kernel_ms": kms, "kernel_launches": trace_launches,
                 "step_ms": float(np.mean(kern_ms)),
                 "algorithmic_bytes_per_trace": BYTES_PER_TRACE, "traces_per_launch": n,
                 "note": "irregular BSP walk: bound by instruction issue and dependent-load latency, not by HBM; the HBM floor "

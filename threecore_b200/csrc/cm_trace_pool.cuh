@@ -54,10 +54,10 @@ __device__ __forceinline__ unsigned withMode(const unsigned modes, const int j, 
 }
 
 #ifndef CMGPU_POOL_K
-#define CMGPU_POOL_K 2
+#define CMGPU_POOL_K 3
 #endif
 #ifndef CMGPU_POOL_MIN_BLOCKS
-#define CMGPU_POOL_MIN_BLOCKS 8
+#define CMGPU_POOL_MIN_BLOCKS 7
 #endif
 
 template <bool COUNT, int K>
