@@ -14,6 +14,9 @@
 
 namespace cmgpu {
 
+#ifndef CMGPU_POOL_LAST2
+#define CMGPU_POOL_LAST2 0
+#endif
 #ifndef CMGPU_NODE_LEVELS
 #define CMGPU_NODE_LEVELS 3
 #endif
@@ -32,7 +35,13 @@ enum PoolMode : int { PM_EMPTY = 0, PM_NODE, PM_LEAF, PM_SLAB, PM_POP, PM_SPLIT,
 enum PoolField : int {
 	PF_SX = 0, PF_SY, PF_SZ, PF_EX, PF_EY, PF_EZ, PF_FRACTION, PF_FLAGS /* flags | sp << 8 */,
 	PF_CUR /* node number or leaf-stream cursor */, PF_F1, PF_F2, PF_AX, PF_AY, PF_AZ, PF_BX, PF_BY, PF_BZ,
-	PF_LAST0, PF_LAST1, PF_PEND /* brush waiting to be clipped; position test: leafs seen */, PF_COUNT
+	PF_LAST0,
+#if CMGPU_POOL_LAST2
+	PF_LAST1,
+#endif
+	PF_COUNT
+	// (the brush waiting to be clipped is the one of stream entry CUR-1; the position test's leaf count lives in
+	// bits 16.. of FLAGS, the stack depth in bits 8..15)
 };
 
 // what an item only needs when its record is written lives in global memory (one 16-byte header per item slot)
@@ -151,7 +160,10 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					SETI(PF_CUR, j, 0); FLD(PF_F1, j) = 0.0f; FLD(PF_F2, j) = 1.0f;
 					FLD(PF_AX, j) = L.sx; FLD(PF_AY, j) = L.sy; FLD(PF_AZ, j) = L.sz;
 					FLD(PF_BX, j) = L.ex; FLD(PF_BY, j) = L.ey; FLD(PF_BZ, j) = L.ez;
-					SETI(PF_LAST0, j, -1); SETI(PF_LAST1, j, -1); SETI(PF_PEND, j, 0);
+					SETI(PF_LAST0, j, -1);
+#if CMGPU_POOL_LAST2
+					SETI(PF_LAST1, j, -1);
+#endif
 					modes = withMode(modes, j, m == FM_PNODE ? PM_POS : PM_NODE);
 				} else {
 					stKeep32(&HDR(j).slot, -1, l2KeepPolicy());        // nothing to write back next time
@@ -213,7 +225,12 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const float4 g0 = __ldg(&fm.stream[2 * k + 2]);
 					const float4 g1 = __ldg(&fm.stream[2 * k + 3]);
 #endif
-					const int last0 = FLDI(PF_LAST0, j), last1 = FLDI(PF_LAST1, j);
+					const int last0 = FLDI(PF_LAST0, j);
+#if CMGPU_POOL_LAST2
+					const int last1 = FLDI(PF_LAST1, j);
+#else
+					const int last1 = last0;
+#endif
 					const float sx = FLD(PF_SX, j), sy = FLD(PF_SY, j), sz = FLD(PF_SZ, j);
 					const float ex = FLD(PF_EX, j), ey = FLD(PF_EY, j), ez = FLD(PF_EZ, j);
 					// tw.bounds (cm_trace.c:628-636), recomputed instead of stored
@@ -240,7 +257,6 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					if (COUNT) { cBrushRefs += b0 >= 0 ? 1u : 0u; cBrushBounds += want0 ? 1u : 0u; }
 					SETI(PF_CUR, j, k + 1);
 #endif
-					if (clip) SETI(PF_PEND, j, b);
 					if (b < 0 || clip)
 						modes = withMode(modes, j, b < 0 ? PM_POP : ((FLDI(PF_FLAGS, j) & 4) ? PM_SLAB : PM_BRUSH));
 				}
@@ -265,7 +281,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			const int j = firstInMode<K>(modes, PM_POP);
 			if (j >= 0) {
 				const int fl = FLDI(PF_FLAGS, j);
-				const int sp = fl >> 8;
+				const int sp = (fl >> 8) & 0xff;
 				if (sp == 0) {
 					modes = withMode(modes, j, PM_DONE);
 				} else {
@@ -322,7 +338,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
 					if (COUNT) cSplits++;
 					const int fl = FLDI(PF_FLAGS, j);
-					const int sp = fl >> 8;
+					const int sp = (fl >> 8) & 0xff;
 					if (sp < kPoolDepth) {
 						float4 *sp4 = reinterpret_cast<float4 *>(STACKAT(j, sp));
 						const unsigned long long keep = l2KeepPolicy();
@@ -356,14 +372,17 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				constexpr int kUnset = (int)0x80000000;           // the header is only written when the clip changed it
 				L.planeRef = kUnset; L.hitId = kUnset;
 				L.cBrushSides = L.cCross = 0;
-				const int b = FLDI(PF_PEND, j);
+				const int b = __float_as_int(__ldg(&fm.stream[2 * (FLDI(PF_CUR, j) - 1) + 1]).w);   // the entry that passed
 				const bool over = clipBrushFast<COUNT>(fm, h, L, b);
 				if (COUNT) { cBrushSides += L.cBrushSides; cCross += L.cCross; }
 				FLD(PF_FRACTION, j) = L.fraction;
 				SETI(PF_FLAGS, j, (fl & ~0xff) | L.flags);
 				if (L.planeRef != kUnset) stKeep32(&HDR(j).planeRef, L.planeRef, l2KeepPolicy());
 				if (L.hitId != kUnset) stKeep32(&HDR(j).hitId, L.hitId, l2KeepPolicy());
-				SETI(PF_LAST1, j, FLDI(PF_LAST0, j)); SETI(PF_LAST0, j, b);
+#if CMGPU_POOL_LAST2
+				SETI(PF_LAST1, j, FLDI(PF_LAST0, j));
+#endif
+				SETI(PF_LAST0, j, b);
 				modes = withMode(modes, j, over ? PM_DONE : PM_LEAF);
 			}
 		}
@@ -378,11 +397,11 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (j >= 0 && !(FLDI(PF_FLAGS, j) & 8)) {
 					const int c = FLDI(PF_CUR, j);
 					if (c < 0) {
-						const int found = FLDI(PF_PEND, j);
+						const int found = FLDI(PF_FLAGS, j) >> 16;
 						if (found >= kMaxPosLeafs) {
 							modes = withMode(modes, j, PM_DONE);
 						} else {
-							SETI(PF_PEND, j, found + 1);
+							SETI(PF_FLAGS, j, FLDI(PF_FLAGS, j) + (1 << 16));
 							SETI(PF_CUR, j, -1 - c);
 							if (COUNT) cLeafs++;
 							SETI(PF_FLAGS, j, FLDI(PF_FLAGS, j) | 8);
@@ -415,7 +434,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 							SETI(PF_CUR, j, nd.y);
 						} else {
 							const int fl = FLDI(PF_FLAGS, j);
-							const int sp = fl >> 8;
+							const int sp = (fl >> 8) & 0xff;
 							if (sp < kPoolDepth) { __stcg(&STACKAT(j, sp)->num, nd.y); SETI(PF_FLAGS, j, fl + 256); }
 							else atomicOr(q.status, 1);
 							SETI(PF_CUR, j, nd.x);
@@ -429,7 +448,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const int b = __float_as_int(e1.w);
 					if (b < 0) {
 						const int fl = FLDI(PF_FLAGS, j);
-						const int sp = fl >> 8;
+						const int sp = (fl >> 8) & 0xff;
 						if (sp == 0) {
 							modes = withMode(modes, j, PM_DONE);
 						} else {
