@@ -75,6 +75,7 @@ struct cmgpu_ctx_s {
 	int numPatches = 0;
 	bool useFast = true;
 	int pipeChunks = 32;                 // pieces a host batch is cut into
+	bool pipeRamp = true;                // ... the first ones smaller
 	// optional CUDA-event timing of the trace kernel alone (cmgpu_kernel_timing)
 	bool timing = false;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timingPairs;
@@ -822,6 +823,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "min_chunk") ctx->minChunk = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
 	else if (k == "simple_max_items") ctx->simpleMaxItems = value < 0 ? 0 : (int)value;
 	else if (k == "pool_min_items") ctx->poolMinItems = value < 1 ? 1 : (int)value;
+	else if (k == "pipe_ramp") ctx->pipeRamp = value != 0;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
@@ -1030,8 +1032,25 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	int chunks = (int)((N + kMinChunkItems - 1) / kMinChunkItems);
 	if (chunks > ctx->pipeChunks) chunks = ctx->pipeChunks;
 	if (chunks < 1) chunks = 1;
+	// Piece boundaries: equal pieces, except that the first ones grow from an eighth of a piece -- the result
+	// copies (the bottleneck on PCIe) cannot start before the first piece has been uploaded and traced, so that
+	// piece is kept small.
+	std::vector<size_t> bounds;
+	bounds.push_back(0);
+	{
+		const size_t piece = (N + (size_t)chunks - 1) / (size_t)chunks;
+		size_t first = piece / 8;
+		if (first < kMinChunkItems) first = kMinChunkItems;
+		size_t at = 0, step = first < piece && ctx->pipeRamp ? first : piece;
+		while (at < N) {
+			at = at + step < N ? at + step : N;
+			bounds.push_back(at);
+			if (step < piece) step = step * 2 < piece ? step * 2 : piece;
+		}
+	}
+	chunks = (int)bounds.size() - 1;
 	for (int c = 0; c < chunks; c++) {
-		const size_t lo = N * (size_t)c / (size_t)chunks, hi = N * (size_t)(c + 1) / (size_t)chunks;
+		const size_t lo = bounds[c], hi = bounds[c + 1];
 		const size_t cnt = hi - lo;
 		if (!cnt) continue;
 		cudaStream_t s = ctx->streams[c % kBinSlots];
