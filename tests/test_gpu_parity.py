@@ -262,7 +262,7 @@ def test_kernel_variants_agree(eng, big, opts):
         torch.cuda.synchronize()
         eng.check_status()
     finally:
-        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=1, gang=4, simple_max_items=393216, bin=1).items():
+        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=1, gang=4, simple_max_items=786432, bin=1).items():
             eng.set_option(k, v)
     assert torch.equal(o, big["out"][:n])
 
@@ -281,5 +281,5 @@ def test_binning_small_batches_all_query_kinds(eng, which):
                 check(eng, o, case)
     finally:
         eng.set_option("bin_min_items", 98304)
-        eng.set_option("pool_min_items", 1 << 20)
-        eng.set_option("simple_max_items", 393216)
+        eng.set_option("pool_min_items", 786433)
+        eng.set_option("simple_max_items", 786432)

@@ -69,8 +69,8 @@ struct cmgpu_ctx_s {
 	bool usePool = true;                 // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
 	int poolReps = 1;                    // its repeats of a light step per round (a node step is up to 3 levels, a leaf step 2 entries)
 	int minChunk = 8;                    // fewest items a warp takes at a time in a small launch
-	int simpleMaxItems = 393216;         // launches up to this size use the thread-per-item kernel (lowest latency)
-	int poolMinItems = 1 << 20;          // smaller launches use the one-item-per-lane variant (lower latency)
+	int simpleMaxItems = 786432;         // launches up to this size use the thread-per-item kernel (lowest latency)
+	int poolMinItems = 786433;           // smaller launches use the one-item-per-lane variant (lower latency)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	bool useFast = true;
@@ -442,9 +442,11 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 			stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(0)));
 			stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(-1)));
 		}
-		// a spare sentinel, so that a kernel may always read the entry after the one it is looking at
-		stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(0)));
-		stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(-1)));
+		// spare sentinels, so that a kernel may always read a few entries past the one it is looking at
+		for (int spare = 0; spare < 7; spare++) {
+			stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(0)));
+			stream.push_back(make_float4(0.0f, 0.0f, 0.0f, bitsToFloat(-1)));
+		}
 		std::vector<int4> fnodes((size_t)f->numNodes);
 		for (int i = 0; i < f->numNodes; i++) {
 			int4 nd = nodes[i];

@@ -20,10 +20,11 @@ namespace cmgpu {
 #ifndef CMGPU_NODE_LEVELS
 #define CMGPU_NODE_LEVELS 3
 #endif
-#ifndef CMGPU_LEAF_PAIR
-#define CMGPU_LEAF_PAIR 1
+#ifndef CMGPU_LEAF_ENTRIES
+#define CMGPU_LEAF_ENTRIES 3
 #endif
 constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
+constexpr int kLeafEntries = CMGPU_LEAF_ENTRIES;  // stream entries a lane looks at per repeat of the leaf step
 constexpr int kNodeLevels = CMGPU_NODE_LEVELS;   // tree levels a lane may descend per repeat of the node step
 constexpr int kVoteEnough = 20;          // a step kind that this many lanes can run is run without looking further
 
@@ -217,14 +218,14 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (!__any_sync(0xffffffffu, j >= 0)) break;
 				if (j >= 0) {
 					const int k = FLDI(PF_CUR, j);
-					const float4 e0 = __ldg(&fm.stream[2 * k]);
-					const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
-#if CMGPU_LEAF_PAIR
-					// two entries per repeat (the stream has a spare sentinel at its end, so the second load is always in
-					// bounds); the second one is only looked at when the first neither ends the leaf nor needs clipping
-					const float4 g0 = __ldg(&fm.stream[2 * k + 2]);
-					const float4 g1 = __ldg(&fm.stream[2 * k + 3]);
-#endif
+					// kLeafEntries entries per repeat (the stream has spare sentinels at its end, so the loads are always
+					// in bounds); an entry is only looked at when the ones before it neither end the leaf nor need clipping
+					float4 e0[kLeafEntries], e1[kLeafEntries];
+					#pragma unroll
+					for (int i = 0; i < kLeafEntries; i++) {
+						e0[i] = __ldg(&fm.stream[2 * (k + i)]);
+						e1[i] = __ldg(&fm.stream[2 * (k + i) + 1]);
+					}
 					const int last0 = FLDI(PF_LAST0, j);
 #if CMGPU_POOL_LAST2
 					const int last1 = FLDI(PF_LAST1, j);
@@ -237,27 +238,24 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const float lox = (sx < ex ? sx : ex) + h.n0[0], hix = (sx < ex ? ex : sx) + h.p0[0];
 					const float loy = (sy < ey ? sy : ey) + h.n0[1], hiy = (sy < ey ? ey : sy) + h.p0[1];
 					const float loz = (sz < ez ? sz : ez) + h.n0[2], hiz = (sz < ez ? ez : sz) + h.p0[2];
-					const int b0 = __float_as_int(e1.w);
-					const bool want0 = b0 >= 0 && (__float_as_int(e0.w) & h.mask) != 0 && b0 != last0 && b0 != last1;
-					const bool apart0 = hix < e0.x || hiy < e0.y || hiz < e0.z || lox > e1.x || loy > e1.y || loz > e1.z;
-					const bool clip0 = want0 && !apart0;                               // CM_BoundsIntersect passed
-#if CMGPU_LEAF_PAIR
-					const int b1 = __float_as_int(g1.w);
-					const bool want1 = b1 >= 0 && (__float_as_int(g0.w) & h.mask) != 0 && b1 != last0 && b1 != last1;
-					const bool apart1 = hix < g0.x || hiy < g0.y || hiz < g0.z || lox > g1.x || loy > g1.y || loz > g1.z;
-					const bool clip1 = want1 && !apart1;
-					const bool stop0 = b0 < 0 || clip0;                                // the first entry decides alone
-					const int b = stop0 ? b0 : b1;
-					const bool clip = stop0 ? clip0 : clip1;
-					if (COUNT) { cBrushRefs += (b0 >= 0 ? 1u : 0u) + (!stop0 && b1 >= 0 ? 1u : 0u); cBrushBounds += (want0 ? 1u : 0u) + (!stop0 && want1 ? 1u : 0u); }
-					SETI(PF_CUR, j, k + (stop0 ? 1 : 2));
-#else
-					const int b = b0;
-					const bool clip = clip0;
-					if (COUNT) { cBrushRefs += b0 >= 0 ? 1u : 0u; cBrushBounds += want0 ? 1u : 0u; }
-					SETI(PF_CUR, j, k + 1);
-#endif
-					if (b < 0 || clip)
+					int adv = 0, b = 0;
+					bool stopped = false, clip = false;
+					#pragma unroll
+					for (int i = 0; i < kLeafEntries; i++) {
+						const int bi = __float_as_int(e1[i].w);
+						const bool want = bi >= 0 && (__float_as_int(e0[i].w) & h.mask) != 0 && bi != last0 && bi != last1;
+						const bool apart = hix < e0[i].x || hiy < e0[i].y || hiz < e0[i].z || lox > e1[i].x || loy > e1[i].y || loz > e1[i].z;
+						const bool clipi = want && !apart;                             // CM_BoundsIntersect passed
+						if (!stopped) {
+							adv = i + 1;
+							b = bi;
+							clip = clipi;
+							if (COUNT) { cBrushRefs += bi >= 0 ? 1u : 0u; cBrushBounds += want ? 1u : 0u; }
+							stopped = bi < 0 || clipi;
+						}
+					}
+					SETI(PF_CUR, j, k + adv);
+					if (stopped)
 						modes = withMode(modes, j, b < 0 ? PM_POP : ((FLDI(PF_FLAGS, j) & 4) ? PM_SLAB : PM_BRUSH));
 				}
 			}
