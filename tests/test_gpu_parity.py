@@ -283,3 +283,39 @@ def test_binning_small_batches_all_query_kinds(eng, which):
         eng.set_option("bin_min_items", 98304)
         eng.set_option("pool_min_items", 786433)
         eng.set_option("simple_max_items", 786432)
+
+
+def test_pool_kernel_counters_and_hit_ids(eng, big):
+    """the pool kernel's counting variant visits what the oracle visits, and reports the brush that set each result"""
+    import torch
+    n = 1 << 20                                   # above pool_min_items: this launch runs tracePoolKernel
+    eng.load_bsp(big["m"].data)                   # earlier tests left another map in the engine
+    o = cmoracle.OracleCM(eng.map.to_dict())
+    hit = torch.empty(n, dtype=torch.int32, device=big["ds"].device)
+    out = torch.empty((n, 56), dtype=torch.uint8, device=big["ds"].device)
+    eng.enable_counters(True)
+    try:
+        eng.read_counters(reset=True)
+        eng.box_trace_device(big["ds"][:n], big["de"][:n], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, out,
+                             hit_ids=hit)
+        torch.cuda.synchronize()
+        c = eng.read_counters()
+    finally:
+        eng.enable_counters(False)
+    assert torch.equal(out, big["out"][:n])
+    idx = np.sort(np.random.default_rng(2).choice(n, size=200000, replace=False))
+    want, info = o.box_trace(big["s"][idx], big["e"][idx], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS,
+                             mask=bspgen.MASK_PLAYERSOLID, want_info=True)
+    assert np.array_equal(hit.cpu().numpy()[idx], info["hitBrush"])
+    assert c["traces"] == n
+    # totals over the whole launch against the sample's means (the oracle walks 200k of the 1Mi items)
+    for k in ("nodes", "leafs", "brushRefs", "splits"):
+        per_item = c[k] / n
+        assert abs(per_item - info[k].mean()) < 0.02 * info[k].mean() + 0.05, (k, per_item, info[k].mean())
+
+
+def test_unknown_option_is_refused(eng):
+    from threecore_b200.engine import CMGPUError
+    with pytest.raises(CMGPUError) as ex:
+        eng.set_option("no_such_knob", 1)
+    assert ex.value.code == 1

@@ -716,6 +716,7 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 	if (const char *g = getenv("CMGPU_GANG")) ctx->gang = atoi(g);   // tuning knobs
 	if (const char *g = getenv("CMGPU_LIGHT_REPS")) ctx->lightReps = atoi(g) > 0 ? atoi(g) : 1;
 	if (const char *g = getenv("CMGPU_POOL")) ctx->usePool = atoi(g) != 0;
+	if (const char *g = getenv("CMGPU_PIPE_CHUNKS")) ctx->pipeChunks = atoi(g) > 0 ? (atoi(g) > kPipeChunks ? kPipeChunks : atoi(g)) : ctx->pipeChunks;
 	if (const char *g = getenv("CMGPU_BIN")) ctx->binning = atoi(g) != 0;
 	if (const char *g = getenv("CMGPU_BIN_CELL")) ctx->binCell = atof(g) > 1.0 ? (float)atof(g) : 128.0f;
 	if (const char *g = getenv("CMGPU_BIN_LONG")) ctx->binLongLen = (float)atof(g);

@@ -370,34 +370,19 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 	}
 }
 
-#ifndef CMGPU_PREFETCH
-#define CMGPU_PREFETCH 0
-#endif
 #ifndef CMGPU_PREFETCH_CHUNK
 #define CMGPU_PREFETCH_CHUNK 1
 #endif
-#ifndef CMGPU_ORDER
-#define CMGPU_ORDER 1
-#endif
-
-// the record a lane will need at its next step, asked for one scheduler round early
-__device__ __forceinline__ void prefetchL1(const void *p) {
-#if CMGPU_PREFETCH
-	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#endif
-}
 
 // follow a child reference: a node, or the stream of a leaf
 template <bool COUNT>
 __device__ __forceinline__ int gotoChild(const FastMap &fm, FastLane &L, const int c) {
 	if (c < 0) {
 		L.k = -1 - c;
-		prefetchL1(&fm.stream[2 * L.k]);
 		if (COUNT) L.cLeafs++;
 		return FM_LEAF;
 	}
 	L.num = c;
-	prefetchL1(&fm.nodes[c]);
 	return FM_NODE;
 }
 

@@ -4,8 +4,11 @@
 // ~11 of 32 lanes on average, whatever the gang sizes (measured, and reproduced by a scheduling model over the
 // oracle's per-item step sequences).  Here every lane owns K items whose state lives in shared memory
 // (structure of arrays, [field][k][lane]: conflict-free, no cross-lane traffic, nothing shared between warps).  Each
-// round the warp votes for the step kind that the most lanes can run, and every lane that owns an item waiting for
-// that kind runs it on that item.  With K = 4 the same model gives 21-23 active lanes per instruction.
+// round the warp counts how many lanes own an item waiting for each kind of step and runs every kind that enough
+// lanes can run; a lane runs the step on its first item of that kind.  Light steps are batched: a node step descends
+// up to kNodeLevels levels, a leaf step looks at kLeafEntries stream entries.  The model gives 17 / 21 / 23 active
+// lanes per instruction for K = 2 / 3 / 4; K = 3 with 7 CTAs per SM is the measured optimum (more items per lane
+// leave too few warps and too little L1 for the same shared memory).
 //
 // Results are bit-identical to traceFastKernel: the step arithmetic is the same code.
 #pragma once
@@ -26,7 +29,6 @@ namespace cmgpu {
 constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
 constexpr int kLeafEntries = CMGPU_LEAF_ENTRIES;  // stream entries a lane looks at per repeat of the leaf step
 constexpr int kNodeLevels = CMGPU_NODE_LEVELS;   // tree levels a lane may descend per repeat of the node step
-constexpr int kVoteEnough = 20;          // a step kind that this many lanes can run is run without looking further
 
 // step kinds an item can wait for (one-hot bit m-1 of its mode byte).  PM_POS is the position test; bit 3 of the item's
 // flags says whether it is in the tree part (CM_BoxLeafnums_r) or the leaf part (CM_TestInLeaf).
@@ -35,7 +37,9 @@ enum PoolMode : int { PM_EMPTY = 0, PM_NODE, PM_LEAF, PM_SLAB, PM_POP, PM_SPLIT,
 // shared-memory fields of one item (32-bit words)
 enum PoolField : int {
 	PF_SX = 0, PF_SY, PF_SZ, PF_EX, PF_EY, PF_EZ, PF_FRACTION, PF_FLAGS /* flags | sp << 8 */,
-	PF_CUR /* node number or leaf-stream cursor */, PF_F1, PF_F2, PF_AX, PF_AY, PF_AZ, PF_BX, PF_BY, PF_BZ,
+	PF_CUR /* node number or leaf-stream cursor */,
+	PF_F1, PF_F2,
+	PF_AX, PF_AY, PF_AZ, PF_BX, PF_BY, PF_BZ,
 	PF_LAST0,
 #if CMGPU_POOL_LAST2
 	PF_LAST1,
@@ -158,7 +162,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					FLD(PF_SX, j) = L.sx; FLD(PF_SY, j) = L.sy; FLD(PF_SZ, j) = L.sz;
 					FLD(PF_EX, j) = L.ex; FLD(PF_EY, j) = L.ey; FLD(PF_EZ, j) = L.ez;
 					FLD(PF_FRACTION, j) = 1.0f; SETI(PF_FLAGS, j, L.flags);
-					SETI(PF_CUR, j, 0); FLD(PF_F1, j) = 0.0f; FLD(PF_F2, j) = 1.0f;
+					SETI(PF_CUR, j, 0);
+					FLD(PF_F1, j) = 0.0f; FLD(PF_F2, j) = 1.0f;
 					FLD(PF_AX, j) = L.sx; FLD(PF_AY, j) = L.sy; FLD(PF_AZ, j) = L.sz;
 					FLD(PF_BX, j) = L.ex; FLD(PF_BY, j) = L.ey; FLD(PF_BZ, j) = L.ez;
 					SETI(PF_LAST0, j, -1);
