@@ -311,7 +311,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS, help="rays per GPU (default: the 16 Mi of configs[1])")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--ref-sample", type=int, default=1 << 22, help="rays per reference/cpu_baseline step")
+    ap.add_argument("--ref-sample", type=int, default=1 << 24,
+                    help="rays per reference/cpu_baseline step (default: the whole 16 Mi workload, ~17 s of CPU work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
