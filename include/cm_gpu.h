@@ -211,6 +211,17 @@ unsigned long long cmgpu_launch_count(const cmgpu_ctx *ctx);
 int cmgpu_kernel_timing(cmgpu_ctx *ctx, int enable);
 int cmgpu_kernel_time_ms(cmgpu_ctx *ctx, double *total_ms, int *launches);
 
+/* ---- multi-GPU: a result buffer shared by the processes of one node ------------
+ * One process per GPU.  The rank that wants all records allocates the buffer (cmgpu_ipc_alloc) and
+ * passes the 64-byte handle to the others by whatever control plane it has; they open it (cmgpu_ipc_open) and give
+ * `pointer + 56 * first_item_of_my_range` as `results` to the device-pointer entry points: their kernels store the
+ * records into the owner's HBM over NVLink as they finish items, so there is no gather pass.  A barrier after each
+ * rank's stream synchronisation makes the records visible to the owner.                                           */
+int cmgpu_ipc_alloc(cmgpu_ctx *ctx, size_t bytes, void **devptr, unsigned char handle[64]);
+int cmgpu_ipc_open(cmgpu_ctx *ctx, const unsigned char handle[64], void **devptr);
+int cmgpu_ipc_close(cmgpu_ctx *ctx, void *devptr);
+int cmgpu_ipc_free(cmgpu_ctx *ctx, void *devptr);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

@@ -1,0 +1,62 @@
+"""Multi-GPU result gather fused into the trace kernels' stores (sharding.PeerResults, cmgpu_ipc_*): needs two GPUs.
+The round's single-GPU run skips it; `gpurun --gpus 2 -- python -m pytest tests/test_peer_results.py -m gpu` runs it."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ROOT, bspgen
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from threecore_b200.engine import Engine
+        from threecore_b200.sharding import PeerResults
+        m = bspgen.arena_map(n_brushes=2500, seed=0xC0FFEE12, size_xy=4096.0, size_z=2048.0)
+        s, e = bspgen.make_sweeps(m, n, 77)
+        eng = Engine(rank)
+        eng.load_bsp(m.data)
+        dev = torch.device("cuda", rank)
+        pr = PeerResults(eng, n)
+        lo, hi = pr.local_range()
+        ds, de = torch.from_numpy(s[lo:hi]).to(dev), torch.from_numpy(e[lo:hi]).to(dev)
+        eng.box_trace_device(ds, de, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, pr.pointer(lo))
+        pr.finish()
+        eng.check_status()
+        if rank == 0:
+            got = pr.records().cpu().numpy()
+            # the same batch traced by this rank alone
+            one = torch.empty((n, 56), dtype=torch.uint8, device=dev)
+            eng.box_trace_device(torch.from_numpy(s).to(dev), torch.from_numpy(e).to(dev), bspgen.PLAYER_MINS,
+                                 bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, one)
+            torch.cuda.synchronize()
+            q.put(bool(np.array_equal(got, one.cpu().numpy())))
+        pr.close()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_results_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, n = 2, 1_500_001
+    procs = [ctx.Process(target=_worker, args=(r, world, 29641, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

@@ -886,6 +886,52 @@ int cmgpu_read_counters(cmgpu_ctx *ctx, cmgpu_counters *out, int reset) {
 
 unsigned long long cmgpu_launch_count(const cmgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// ---- result buffers shared between the processes of one node (one process per GPU) ------------------
+// Rank A allocates, the others open A's buffer and hand (pointer + their offset) to the device-pointer entry points:
+// their trace kernels then store their 56-byte records straight into A's memory over NVLink while they run -- the
+// result gather is the kernels' own stores, not a pass after them.
+int cmgpu_ipc_alloc(cmgpu_ctx *ctx, size_t bytes, void **devptr, unsigned char handle[64]) {
+	if (!ctx || !devptr || !handle || !bytes) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_ipc_alloc: bad argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	void *p = nullptr;
+	CUDA_TRY(ctx, cudaMalloc(&p, bytes));
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) {
+		cudaFree(p);
+		return fail(ctx, CMGPU_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+	}
+	memcpy(handle, &h, 64);
+	*devptr = p;
+	return CMGPU_OK;
+}
+
+int cmgpu_ipc_open(cmgpu_ctx *ctx, const unsigned char handle[64], void **devptr) {
+	if (!ctx || !devptr || !handle) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_ipc_open: bad argument");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	CUDA_TRY(ctx, cudaIpcOpenMemHandle(devptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return CMGPU_OK;
+}
+
+int cmgpu_ipc_close(cmgpu_ctx *ctx, void *devptr) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaDeviceSynchronize());
+	CUDA_TRY(ctx, cudaIpcCloseMemHandle(devptr));
+	return CMGPU_OK;
+}
+
+int cmgpu_ipc_free(cmgpu_ctx *ctx, void *devptr) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaDeviceSynchronize());
+	CUDA_TRY(ctx, cudaFree(devptr));
+	return CMGPU_OK;
+}
+
 int cmgpu_kernel_timing(cmgpu_ctx *ctx, int enable) {
 	if (!ctx) return CMGPU_ERR_INVALID;
 	ctx->timing = enable != 0;

@@ -113,6 +113,10 @@ def load_library() -> C.CDLL:
     lib.cmgpu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.cmgpu_launch_count.argtypes = [C.c_void_p]
     lib.cmgpu_launch_count.restype = C.c_ulonglong
+    lib.cmgpu_ipc_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.cmgpu_ipc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.cmgpu_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cmgpu_ipc_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     lib.cmgpu_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.cmgpu_enable_counters.argtypes = [C.c_void_p, C.c_int]
@@ -285,6 +289,25 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.cmgpu_launch_count(self.h))
 
+    # ---- result buffers shared between the ranks of one node (cmgpu_ipc_*) ----------------
+    def ipc_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte handle) of a buffer other processes of this node can open"""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        self._check(self.lib.cmgpu_ipc_alloc(self.h, int(nbytes), C.byref(p), h))
+        return int(p.value), h.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.cmgpu_ipc_open(self.h, handle, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self.lib.cmgpu_ipc_close(self.h, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr: int):
+        self._check(self.lib.cmgpu_ipc_free(self.h, C.c_void_p(ptr)))
+
     def kernel_timing(self, on=True):
         """bracket every trace-kernel launch with CUDA events on its own stream (cmgpu_kernel_timing)"""
         self._check(self.lib.cmgpu_kernel_timing(self.h, int(bool(on))))
@@ -380,13 +403,13 @@ class Engine:
 
         starts/ends float32 [n,3] CUDA tensors.  mins/maxs: a shared hull as 3 host floats (numpy / list /
         None) or per-item CUDA tensors [n,3].  mask: a shared int or a per-item int32 CUDA tensor [n].
-        out uint8 [n,56].  Uses torch's current stream unless `stream` (a cudaStream_t int) is given.
+        out uint8 [n,56] (a CUDA tensor, or a raw device pointer such as PeerResults.pointer()).  Uses torch's current stream unless `stream` (a cudaStream_t int) is given.
         """
         import torch
         n = starts.shape[0]
         if stream is None:
             stream = torch.cuda.current_stream(starts.device).cuda_stream
-        ptr = lambda t: None if t is None else t.data_ptr()
+        ptr = lambda t: None if t is None else (int(t) if isinstance(t, int) else t.data_ptr())
         keep = []
         if mins is None or not isinstance(mins, torch.Tensor):
             hs = 0

@@ -66,3 +66,65 @@ class ShardedTracer:
         if gather and self.world > 1:
             return gather_records(local, n, self.group)
         return local
+
+
+class _DevicePointer:
+    """wraps a raw device pointer for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class PeerResults:
+    """All ranks' trace_t records in ONE buffer in the root rank's HBM, filled by the other ranks' trace kernels
+    themselves: every rank passes `pointer(lo)` as the result pointer of its launches, so its records travel over
+    NVLink while its kernel runs (cmgpu_ipc_* in cm_gpu.h).  There is no gather pass; `finish()` is the stream
+    synchronisation plus a barrier that makes the records visible to the root.
+
+    The control plane (handle broadcast, barrier) is torch.distributed on whatever backend the job uses.
+    """
+
+    def __init__(self, engine, n_total: int, root: int = 0, group=None):
+        self.eng = engine
+        self.n = int(n_total)
+        self.root = root
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        nbytes = max(self.n, 1) * 56
+        box = [None]
+        if self.rank == root:
+            self.base, handle = engine.ipc_alloc(nbytes)
+            box[0] = handle
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=root, group=group)
+        if self.rank != root:
+            self.base = engine.ipc_open(box[0])
+        self.nbytes = nbytes
+
+    def local_range(self):
+        return shard_range(self.n, self.rank, self.world)
+
+    def pointer(self, first_item: int) -> int:
+        return self.base + 56 * int(first_item)
+
+    def finish(self):
+        torch.cuda.synchronize(self.eng.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def records(self) -> torch.Tensor:
+        """root only: the [n,56] uint8 view of the shared buffer"""
+        if self.rank != self.root:
+            raise RuntimeError("the records live on the root rank")
+        t = torch.as_tensor(_DevicePointer(self.base, self.nbytes), device=torch.device("cuda", self.eng.device))
+        return t[: self.n * 56].view(self.n, 56)
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.rank == self.root:
+            self.eng.ipc_free(self.base)
+        else:
+            self.eng.ipc_close(self.base)
+        self.base = 0
