@@ -511,7 +511,7 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		}
 		g.longLen2 = ctx->binLongLen * ctx->binLongLen;
 		g.dirBins = ctx->binDir ? 8 : 1;
-		g.numBins = kBinClasses * g.cells[0] * g.cells[1] * g.cells[2] * g.dirBins;
+		g.numBins = 2 * kBinClasses * g.cells[0] * g.cells[1] * g.cells[2] * g.dirBins;   // x2: point hulls / box hulls of per-item batches
 	}
 	m.numNodes = f->numNodes;
 	m.numModels = f->numModels;
@@ -587,7 +587,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		unsigned *hist = (unsigned *)ctx->bHist[histSlot].p;
 		CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, (size_t)ctx->grid.numBins * 4, s));
 		const int g256 = (q.n + 255) / 256;
-		binCountKernel<<<g256, 256, 0, s>>>(ctx->grid, q.n, q.starts, q.ends, q.models, keys, hist);
+		binCountKernel<<<g256, 256, 0, s>>>(ctx->grid, q.n, q.starts, q.ends, q.models, q.mins, q.maxs, keys, hist);
 		unsigned *tileSums = hist + ctx->grid.numBins;
 		binTileSumKernel<<<numTiles, 256, 0, s>>>(hist, ctx->grid.numBins, tileSums);
 		binTileScanKernel<<<1, 256, 0, s>>>(tileSums, numTiles);

@@ -1107,7 +1107,8 @@ __global__ void __launch_bounds__(128) pointContentsKernel(const DevMap m, const
 }
 
 // ---- binning kernels ------------------------------------------------------------------------
-__device__ __forceinline__ unsigned binOf(const BinGrid &g, float sx, float sy, float sz, float ex, float ey, float ez, int model) {
+__device__ __forceinline__ unsigned binOf(const BinGrid &g, float sx, float sy, float sz, float ex, float ey, float ez, int model,
+                                          bool pointHull = false) {
 	const int qx = (int)fminf(fmaxf((sx - g.lo[0]) * g.inv[0], 0.0f), (float)(g.cells[0] - 1));
 	const int qy = (int)fminf(fmaxf((sy - g.lo[1]) * g.inv[1], 0.0f), (float)(g.cells[1] - 1));
 	const int qz = (int)fminf(fmaxf((sz - g.lo[2]) * g.inv[2], 0.0f), (float)(g.cells[2] - 1));
@@ -1127,16 +1128,23 @@ __device__ __forceinline__ unsigned binOf(const BinGrid &g, float sx, float sy, 
 	else cls = (dx * dx + dy * dy + dz * dz > g.longLen2) ? 1 : 0;
 	key += (unsigned)cls * (unsigned)(g.cells[0] * g.cells[1] * g.cells[2]);
 	if (g.dirBins == 8) key = key * 8u + ((dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u));
+	// batches with per-item hulls: point sweeps and box sweeps take different code in the patch tests, keep them apart
+	// (the upper half of the bins; numBins has room for both halves)
+	if (pointHull) key += (unsigned)(g.numBins >> 1);
 	return key;
 }
 
 // pass 1: bin of every item + histogram
 __global__ void __launch_bounds__(256) binCountKernel(const BinGrid g, int n, const float *starts, const float *ends,
-                                                      const int *models, unsigned *keys, unsigned *hist) {
+                                                      const int *models, const float *mins, const float *maxs,
+                                                      unsigned *keys, unsigned *hist) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const size_t o = 3 * (size_t)i;
-	const unsigned k = binOf(g, starts[o], starts[o + 1], starts[o + 2], ends[o], ends[o + 1], ends[o + 2], models ? models[i] : 0);
+	bool pointHull = false;
+	if (mins) pointHull = mins[o] == maxs[o] && mins[o + 1] == maxs[o + 1] && mins[o + 2] == maxs[o + 2];
+	const unsigned k = binOf(g, starts[o], starts[o + 1], starts[o + 2], ends[o], ends[o + 1], ends[o + 2], models ? models[i] : 0,
+	                         pointHull);
 	keys[i] = k;
 	atomicAdd(&hist[k], 1u);
 }
