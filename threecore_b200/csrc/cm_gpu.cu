@@ -308,6 +308,7 @@ int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 			const int32_t *fc = f->facets + 3 * (size_t)(p[4] + k);
 			NEED(fc[0] >= 0 && fc[0] < p[3], "patch %d facet %d: bad surface plane", i, k);
 			NEED(fc[1] >= 0 && fc[2] >= 0 && (long long)fc[2] + fc[1] <= f->numBorders, "patch %d facet %d: bad borders", i, k);
+			NEED(fc[1] <= 26, "patch %d facet %d: %d borders (the reference's facet_t holds 4 + 6 + 16)", i, k, fc[1]);
 			for (int j = 0; j < fc[1]; j++) {
 				int bp = f->borders[2 * (size_t)(fc[2] + j)];
 				NEED(bp >= 0 && bp < p[3], "patch %d facet %d border %d: bad plane", i, k, j);
@@ -416,6 +417,29 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 	for (int i = 0; i < f->numBorders; i++) {
 		borders[i] = f->borders[2 * (size_t)i] | (f->borders[2 * (size_t)i + 1] ? (int)0x80000000u : 0);
 	}
+	// Sweeps walk a facet's planes one per step: every facet gets its planes as one contiguous run (surface plane,
+	// then the borders in order) so that a step is ONE dependent load instead of facet -> border -> plane.
+	// facetRuns[f] = first plane of the run, numBorders, borderInward bits (validate() caps numBorders at 26), 0
+	std::vector<int4> facetRuns((size_t)f->numFacets);
+	std::vector<float4> facetPlanes;
+	for (int p = 0; p < f->numPatches; p++) {
+		const int32_t *pt = f->patches + 6 * (size_t)p;
+		for (int k = 0; k < pt[5]; k++) {
+			const int fi = pt[4] + k;
+			const int32_t *fc = f->facets + 3 * (size_t)fi;
+			unsigned inward = 0;
+			const int start = (int)facetPlanes.size();
+			const float *sp = f->patchPlanes + 4 * (size_t)(pt[2] + fc[0]);
+			facetPlanes.push_back(make_float4(sp[0], sp[1], sp[2], sp[3]));
+			for (int j = 0; j < fc[1]; j++) {
+				const int32_t *bd = f->borders + 2 * (size_t)(fc[2] + j);
+				const float *bp = f->patchPlanes + 4 * (size_t)(pt[2] + bd[0]);
+				facetPlanes.push_back(make_float4(bp[0], bp[1], bp[2], bp[3]));
+				if (bd[1]) inward |= 1u << j;
+			}
+			facetRuns[fi] = make_int4(start, fc[1], (int)inward, 0);
+		}
+	}
 
 	int rc = CMGPU_OK;
 #define UP(vec, field) if ((rc = uploadArray(ctx, vec, &m.field)) != CMGPU_OK) return rc
@@ -423,7 +447,7 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 	UP(leafsurfaces, leafsurfaces); UP(brushInfo, brushInfo);
 	UP(sidePlanes, sidePlanes); UP(sideMeta, sideMeta); UP(modelLeafs, modelLeafs); UP(surf2patch, surf2patch);
 	UP(patchInfo, patchInfo); UP(patchBox, patchBox); UP(patchPlanes, patchPlanes); UP(facets, facets);
-	UP(borders, borders);
+	UP(borders, borders); UP(facetRuns, facetRuns); UP(facetPlanes, facetPlanes);
 	{	// ---- layout of the hot kernel: leafs as sentinel-terminated streams of widened brush boxes ----
 		std::vector<int> streamStart((size_t)f->numLeafs);
 		std::vector<float4> stream;

@@ -57,6 +57,8 @@ struct DevMap {
 	const float4 *patchPlanes;
 	const int4   *facets;       // surfacePlane, numBorders, firstBorder, 0
 	const int    *borders;      // plane | inward << 31
+	const int4   *facetRuns;    // per facet: first plane of its run in facetPlanes, numBorders, borderInward bits, 0
+	const float4 *facetPlanes;  // per facet: surface plane, then its border planes in order (copies of patchPlanes)
 	int numNodes;
 	int numModels;
 	int boxBrush;
@@ -294,45 +296,48 @@ __device__ __forceinline__ void pointPlaneRelation(const float4 pl, const Lane &
 // breaks early) three of 32 lanes were active in this code.
 //
 // Per-lane facet state lives in registers that are idle while an item is inside a patch:
-//   L.side = facet, L.sideEnd, L.firstSide = first plane of the patch, L.brush = patch, L.enter = fraction before the patch
+//   L.side = facet, L.sideEnd, L.brush = patch, L.enter = fraction before the patch
+//   L.firstSide = first plane of the current facet's run, L.found = numBorders | borderInward bits << 5
 //   L.lead = border cursor (-1: surface plane), L.bcontents = border that last raised enterFrac (-1: the surface plane,
 //   -2: none), L.leave = leaveFrac (box) / surface intersection t (point), L.kEnd = bits of enterFrac (box)
 
-// the plane a box sweep clips against for facet plane `which` (-1 surface, else border index): cm_patch.c:1390-1402, 1412-1426
-__device__ __forceinline__ float4 facetClipPlane(const DevMap &m, const Lane &L, const int firstPlane, const int4 fc, const int which) {
-	if (which < 0) {
-		const float4 sp = __ldg(&m.patchPlanes[firstPlane + fc.x]);
-		const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
-		const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
-		const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
-		return make_float4(sp.x, sp.y, sp.z, sp.w - dotf(cx, cy, cz, sp.x, sp.y, sp.z));
-	}
-	const int bd = __ldg(&m.borders[fc.z + which]);
-	const float4 bp = __ldg(&m.patchPlanes[firstPlane + (bd & 0x7fffffff)]);
+// the plane a box sweep clips against for plane `which` of the current facet (-1 surface, else border index):
+// cm_patch.c:1390-1402, 1412-1426
+__device__ __forceinline__ float4 facetClipPlane(const DevMap &m, const Lane &L, const int which) {
+	const float4 bp = __ldg(&m.facetPlanes[L.firstSide + 1 + which]);
 	// corner by the ORIGINAL plane's sign bits, dotted with the possibly flipped plane
 	const float cx = bp.x < 0.0f ? L.p0x : L.n0x;
 	const float cy = bp.y < 0.0f ? L.p0y : L.n0y;
 	const float cz = bp.z < 0.0f ? L.p0z : L.n0z;
+	if (which < 0) return make_float4(bp.x, bp.y, bp.z, bp.w - dotf(cx, cy, cz, bp.x, bp.y, bp.z));
 	float px = bp.x, py = bp.y, pz = bp.z, pw = bp.w;
-	if (bd < 0) { px = -px; py = -py; pz = -pz; pw = -pw; }
+	if ((L.found >> (5 + which)) & 1) { px = -px; py = -py; pz = -pz; pw = -pw; }
 	const float off = dotf(cx, cy, cz, px, py, pz);
 	return make_float4(px, py, pz, pw + fabsf(off));     // double add of two floats rounded to float == float add
+}
+
+// a new facet starts: fetch where its planes are
+__device__ __forceinline__ void facetBegin(const DevMap &m, Lane &L) {
+	const int4 fr = __ldg(&m.facetRuns[L.side]);
+	L.firstSide = fr.x;
+	L.found = fr.y | (fr.z << 5);
 }
 
 // one plane of a box sweep's current facet; returns true when the patch is finished
 template <bool COUNT>
 __device__ __forceinline__ bool facetPlaneStepBox(const DevMap &m, Lane &L) {
-	const int4 fc = __ldg(&m.facets[L.side]);
 	const int cur = L.lead;
 	if (cur < 0) {                                   // a new facet starts (cm_patch.c:1384-1388)
 		Cnt<COUNT>::add(L.cFacets);
+		facetBegin(m, L);
 		L.kEnd = __float_as_int(-1.0f);
 		L.leave = 1.0f;
 		L.bcontents = -2;
 	} else {
 		Cnt<COUNT>::add(L.cPatchPlanes);
 	}
-	const float4 pl = facetClipPlane(m, L, L.firstSide, fc, cur);
+	const int numBorders = L.found & 31;
+	const float4 pl = facetClipPlane(m, L, cur);
 	float enter = __int_as_float(L.kEnd), leave = L.leave;
 	bool hit;
 	const bool ok = clipFacetPlane(pl.x, pl.y, pl.z, pl.w, L, enter, leave, hit);
@@ -342,12 +347,12 @@ __device__ __forceinline__ bool facetPlaneStepBox(const DevMap &m, Lane &L) {
 		L.leave = leave;
 		if (hit) L.bcontents = cur;
 		L.lead = cur + 1;
-		if (L.lead >= fc.y) {                        // all borders passed (cm_patch.c:1440-1461)
+		if (L.lead >= numBorders) {                  // all borders passed (cm_patch.c:1440-1461)
 			facetDone = true;
-			const bool backSide = L.bcontents == fc.y - 1;        // never clip against the back side
+			const bool backSide = L.bcontents == numBorders - 1;  // never clip against the back side
 			if (!backSide && enter < leave && enter >= 0 && enter < L.fraction) {
 				L.fraction = enter;
-				const float4 best = facetClipPlane(m, L, L.firstSide, fc, L.bcontents);   // same float ops, same plane
+				const float4 best = facetClipPlane(m, L, L.bcontents);   // same float ops, same plane
 				L.pnx = best.x; L.pny = best.y; L.pnz = best.z; L.pd = best.w;
 			}
 		}
@@ -359,31 +364,29 @@ __device__ __forceinline__ bool facetPlaneStepBox(const DevMap &m, Lane &L) {
 // one plane of a point sweep's current facet (cm_patch.c:1264-1311); returns true when the patch is finished
 template <bool COUNT>
 __device__ __forceinline__ bool facetPlaneStepPoint(const DevMap &m, Lane &L) {
-	const int4 fc = __ldg(&m.facets[L.side]);
 	const int cur = L.lead;
 	Cnt<COUNT>::add(L.cPatchPlanes);
-	bool facetDone;
 	if (cur < 0) {
 		Cnt<COUNT>::add(L.cFacets);
-		const float4 sp = __ldg(&m.patchPlanes[L.firstSide + fc.x]);
-		bool front; float t;
-		pointPlaneRelation(sp, L, front, t);
+		facetBegin(m, L);
+	}
+	const float4 pl = __ldg(&m.facetPlanes[L.firstSide + 1 + cur]);
+	bool front; float t;
+	pointPlaneRelation(pl, L, front, t);
+	bool facetDone;
+	if (cur < 0) {
 		facetDone = !front || t < 0 || t > L.fraction;
 		L.leave = t;
 	} else {
-		const int bd = __ldg(&m.borders[fc.z + cur]);
-		const float4 bp = __ldg(&m.patchPlanes[L.firstSide + (bd & 0x7fffffff)]);
-		bool bfront; float bt;
-		pointPlaneRelation(bp, L, bfront, bt);
-		const bool inward = bd < 0;
-		facetDone = (bfront != inward) ? (bt > L.leave) : (bt < L.leave);
+		const bool inward = (L.found >> (5 + cur)) & 1;
+		facetDone = (front != inward) ? (t > L.leave) : (t < L.leave);
 	}
 	if (!facetDone) {
 		L.lead = cur + 1;
-		if (L.lead >= fc.y) {
+		if (L.lead >= (L.found & 31)) {
 			facetDone = true;
 			// hit: recompute with the 1/8 push-off, mixed widths as cm_patch.c:1300-1303
-			const float4 sp = __ldg(&m.patchPlanes[L.firstSide + fc.x]);
+			const float4 sp = __ldg(&m.facetPlanes[L.firstSide]);
 			const float cx = sp.x < 0.0f ? L.p0x : L.n0x;
 			const float cy = sp.y < 0.0f ? L.p0y : L.n0y;
 			const float cz = sp.z < 0.0f ? L.p0z : L.n0z;
@@ -905,7 +908,7 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 							Cnt<COUNT>::add(L.cPatches);
 							const int4 pb = __ldg(&m.patchInfo[2 * p + 1]);
 							// the facets are walked one per scheduler round (M_FACET); the brush cursor is idle meanwhile
-							L.brush = p; L.firstSide = pa.z; L.side = pb.x; L.sideEnd = pb.x + pb.y;
+							L.brush = p; L.side = pb.x; L.sideEnd = pb.x + pb.y;
 							L.lead = -1;                                 // at the surface plane of the first facet
 							L.enter = L.fraction;                        // fraction before this patch (cm_trace.c:245)
 							mode = M_FACET;
