@@ -15,7 +15,7 @@ ds, de, dmn, dmx = T(s), T(e), T(mins), T(maxs); out = torch.empty((n, 56), dtyp
 pt = (mins == 0).all(axis=1)
 dsp, dep = T(s[pt]), T(e[pt]); dsh, deh = T(s[~pt]), T(e[~pt])
 ref = None
-for opts in [dict(), dict(gang=1, gang_fetch=1), dict(gang=2, gang_fetch=2), dict(gang=8), dict(light_reps=1), dict(light_reps=6), dict(bin=0), dict(bin_cell=128)]:
+for opts in [dict(), dict(facet_steps=2), dict(facet_steps=4), dict(facet_steps=6), dict(facet_steps=24), dict(facet_steps=4, light_reps=6), dict(facet_steps=6, light_reps=8), dict(facet_steps=24, light_reps=12)]:
     for k, v in opts.items(): eng.set_option(k, v)
     if "bin_cell" in opts: eng.load_bsp(m.data)
     def run(a, b, mn, mx, o):
@@ -31,5 +31,5 @@ for opts in [dict(), dict(gang=1, gang_fetch=1), dict(gang=2, gang_fetch=2), dic
     msp = run(dsp, dep, None, None, out[: dsp.shape[0]])
     msh = run(dsh, deh, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, out[: dsh.shape[0]])
     print(f"{str(opts):32s} mixed {n/ms/1e3:7.1f} M/s same={same}   points alone {dsp.shape[0]/msp/1e3:7.1f}   hulls alone {dsh.shape[0]/msh/1e3:7.1f}", flush=True)
-    for k, v in dict(gang=4, gang_fetch=4, light_reps=3, bin=1, bin_cell=256).items(): eng.set_option(k, v)
+    for k, v in dict(gang=4, gang_fetch=4, light_reps=3, bin=1, bin_cell=256, facet_steps=12).items(): eng.set_option(k, v)
     if "bin_cell" in opts: eng.load_bsp(m.data)

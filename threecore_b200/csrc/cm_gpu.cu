@@ -85,6 +85,7 @@ struct cmgpu_ctx_s {
 	int gang = kGang;
 	int gangFetch = kGang;
 	int lightReps = 3;
+	int facetSteps = kFacetPlaneSteps;
 	// spatial binning of large batches (counting sort by start cell)
 	BinGrid grid{};
 	bool binning = true;
@@ -626,6 +627,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	q.gang = ctx->gang;
 	q.gangFetch = ctx->gangFetch;
 	q.lightReps = ctx->lightReps;
+	q.facetSteps = ctx->facetSteps;
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
@@ -855,6 +857,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
 	else if (k == "gang_fetch") ctx->gangFetch = (int)value;
+	else if (k == "facet_steps") ctx->facetSteps = value < 1 ? 1 : (int)value;
 	else if (k == "light_reps") ctx->lightReps = value < 1 ? 1 : (int)value;
 	else return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_set_option: unknown option '%s'", name);
 	return CMGPU_OK;

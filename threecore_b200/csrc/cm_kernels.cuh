@@ -94,6 +94,7 @@ struct TraceBatch {
 	int gang;                            // lanes that must gather before a heavy block runs
 	int gangFetch;                       // ... before finished lanes write their records and take new items (hot kernel)
 	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
+	int facetSteps;                      // patch planes a lane tests per scheduler iteration (general kernel)
 	Counters *counters;                  // only touched by the counting variant
 	struct FastSeg *stackArena;          // hot kernel: kMaxDepth entries per resident thread
 	void *poolHdr;                       // pool variant: one 16-byte header per item slot
@@ -925,7 +926,7 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 		if (mode == M_FACET) {
 			const bool point = (L.flags & F_POINT) != 0;
 			#pragma unroll 1
-			for (int it = 0; it < kFacetPlaneSteps; it++) {
+			for (int it = 0; it < q.facetSteps; it++) {
 				bool patchDone = true;
 				if (mode == M_FACET) {
 					patchDone = (L.side >= L.sideEnd) ? true : (point ? facetPlaneStepPoint<COUNT>(m, L) : facetPlaneStepBox<COUNT>(m, L));
