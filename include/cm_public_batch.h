@@ -109,6 +109,10 @@ int SV_ClipMovesToEntitiesBatch(trace_t *clipTraces, int numMoves, const float *
                                 const int *contentmasks, int mask_stride,
                                 const int *touchFirst, const cm_touch_t *touch);
 
+/* SV_PointContents (server/sv_world.c:616-647) for many points: point m owns touch[touchFirst[m] .. touchFirst[m+1])
+ * (the caller's SV_AreaEntities result minus passEntityNum); contents[m] = world contents | every candidate's. */
+int SV_PointContentsBatch(int *contents, int numPoints, const float *points, const int *touchFirst, const cm_touch_t *touch);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

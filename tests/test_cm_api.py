@@ -39,6 +39,7 @@ def api():
     lib.CM_ModelBounds.argtypes = [C.c_int, vp, vp]
     lib.CM_ModelBounds.restype = None
     lib.SV_ClipMovesToEntitiesBatch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.SV_PointContentsBatch.argtypes = [vp, C.c_int, vp, vp, vp]
     m = get_map("arena_models")
     assert lib.CM_LoadMapFromMemory(b"maps/test.bsp", m.data, len(m.data), None) == 0, lib.CM_LastError()
     from threecore_b200.engine import FlatMap
@@ -170,3 +171,35 @@ def test_sv_clip_moves_to_entities_batch(api):
     ent_hits = (clip["entityNum"] >= 64) & (clip["entityNum"] < 64 + E)
     assert ent_hits.mean() > 0.2, "entities are not being hit"
     assert (clip["startsolid"] == 1).sum() > 10
+
+
+def test_sv_point_contents_batch(api):
+    """SV_PointContents: world contents OR-ed with CM_TransformedPointContents of every candidate entity"""
+    lib, m, o = api
+    rng = np.random.default_rng(41)
+    nm = m.num_models
+    E, n = 200, 5000
+    bmodel = rng.random(E) < 0.6
+    origin = f3(np.floor(rng.uniform(m.world_mins + 300, m.world_maxs - 300, size=(E, 3))))
+    angles = f3(np.where(rng.random((E, 1)) < 0.5, 0.0, rng.uniform(0, 360, size=(E, 3))))
+    angles[~bmodel] = 0.0
+    emins, emaxs = f3(-np.floor(rng.uniform(8, 48, size=(E, 3)))), f3(np.floor(rng.uniform(8, 64, size=(E, 3))))
+    modelindex = rng.integers(1, nm, size=E).astype(np.int32)
+    handle = np.where(bmodel, modelindex, 1023).astype(np.int32)
+    tgt = rng.integers(0, E, size=n)
+    pts = f3(origin[tgt] + rng.uniform(-60, 60, size=(n, 3)))
+    lists = [np.unique(np.concatenate([[tgt[i]], rng.integers(0, E, size=rng.integers(0, 4))])) for i in range(n)]
+    first = np.zeros(n + 1, np.int32); first[1:] = np.cumsum([len(t) for t in lists])
+    flat = np.concatenate(lists).astype(np.int64)
+    arr = (Touch * len(flat))()
+    for k, ent in enumerate(flat):
+        arr[k].entityNum = int(ent); arr[k].bmodel = int(bmodel[ent]); arr[k].modelindex = int(modelindex[ent])
+        arr[k].mins = V3(*emins[ent]); arr[k].maxs = V3(*emaxs[ent]); arr[k].origin = V3(*origin[ent]); arr[k].angles = V3(*angles[ent])
+    got = np.zeros(n, np.int32)
+    assert lib.SV_PointContentsBatch(got.ctypes.data, n, pts.ctypes.data, first.ctypes.data, C.byref(arr)) == 0, lib.CM_LastError()
+    want = o.point_contents(pts).copy()
+    mv = np.concatenate([np.full(len(t), i) for i, t in enumerate(lists)])
+    c2 = o.point_contents(pts[mv], handle[flat], origin[flat], angles[flat], emins[flat], emaxs[flat])
+    np.bitwise_or.at(want, mv, c2)
+    assert np.array_equal(got, want)
+    assert (got != o.point_contents(pts)).mean() > 0.05, "entities do not contribute"

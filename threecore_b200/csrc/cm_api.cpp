@@ -271,6 +271,35 @@ int SV_ClipMovesToEntitiesBatch(trace_t *clipTraces, int numMoves, const float *
 	return CMGPU_OK;
 }
 
+// SV_PointContents (sv_world.c:616-647) for many points: the world's contents of every point and the contents of
+// every (point, candidate entity) pair in two batches, OR-ed per point.
+int SV_PointContentsBatch(int *contents, int numPoints, const float *points, const int *touchFirst, const cm_touch_t *touch) {
+	if (numPoints <= 0) return CMGPU_OK;
+	int rc = CM_PointContentsBatch(contents, numPoints, points, nullptr, nullptr, nullptr, nullptr, nullptr);
+	if (rc) return rc;
+	const int total = touchFirst[numPoints];
+	if (total <= 0) return CMGPU_OK;
+	const size_t T = (size_t)total;
+	std::vector<float> p(3 * T), org(3 * T), ang(3 * T), bmn(3 * T), bmx(3 * T);
+	std::vector<int> models(T), c2(T);
+	for (int m = 0; m < numPoints; m++) {
+		for (int t = touchFirst[m]; t < touchFirst[m + 1]; t++) {
+			const cm_touch_t &tc = touch[t];
+			memcpy(&p[3 * (size_t)t], points + 3 * (size_t)m, 12);
+			memcpy(&org[3 * (size_t)t], tc.origin, 12);
+			memcpy(&ang[3 * (size_t)t], tc.angles, 12);
+			memcpy(&bmn[3 * (size_t)t], tc.mins, 12);
+			memcpy(&bmx[3 * (size_t)t], tc.maxs, 12);
+			models[t] = tc.bmodel ? CM_InlineModel(tc.modelindex) : CMGPU_BOX_MODEL_HANDLE;   // SV_ClipHandleForEntity
+		}
+	}
+	rc = CM_PointContentsBatch(c2.data(), total, p.data(), models.data(), org.data(), ang.data(), bmn.data(), bmx.data());
+	if (rc) return rc;
+	for (int m = 0; m < numPoints; m++)
+		for (int t = touchFirst[m]; t < touchFirst[m + 1]; t++) contents[m] |= c2[t];
+	return CMGPU_OK;
+}
+
 int SV_ClipMoveToEntitiesBatch(trace_t *clipTrace, const vec3_t start, const vec3_t end,
                                const vec3_t mins, const vec3_t maxs, int contentmask,
                                int numTouch, const cm_touch_t *touch) {
