@@ -1,7 +1,12 @@
-// cm_trace_fast.cuh -- the hot kernel: CM_BoxTrace against the WORLD with a hull and a mask shared by
+// cm_trace_fast.cuh -- the hot path: CM_BoxTrace against the WORLD with a hull and a mask shared by
 // the whole batch (BASELINE configs 1, 2 and 5), on maps without patches (or with cm_noCurves set).
 // Everything else (inline models, temp boxes, rotations, per-item hulls, patches) runs traceKernel
 // in cm_kernels.cuh.
+//
+// This header holds the data layout (FastMap, FastHull) and the STEPS of the hot path -- beginFast, slabReject,
+// clipBrushFast, finishFast -- plus traceFastKernel, the one-item-per-lane persistent scheduler over them.  The other
+// two schedulers over the same steps are tracePoolKernel (cm_trace_pool.cuh: K items per lane in shared memory, the
+// kernel of big launches) and traceSimpleKernel (cm_trace_simple.cuh: one thread per item, small launches).
 //
 // Same persistent flat-state-machine scheduling as traceKernel (see there), re-cut so that every
 // step is a handful of instructions:
@@ -10,7 +15,7 @@
 //   * the entries carry the brush bounds already widened by BOUNDS_CLIP_EPSILON (the float ops
 //     of cm_test.c:481-494 done once at upload), so CM_BoundsIntersect is six compares;
 //   * an axial node compares the FLOAT differences t1,t2 with float images of offset+1 and
-//     -offset-1 computed once per batch (exact, see nodeThresholds in cm_gpu.cu);
+//     -offset-1 computed once per batch (exact, see makeFastHull in cm_gpu.cu);
 //   * the running result is (fraction, reference to the clip side, contents); the plane and surface
 //     flags are fetched when the record is written;
 //   * the brush clip first runs with float quotients that are only used to REJECT (enterFrac
