@@ -194,6 +194,52 @@ void cmgpu_rotation_matrices(int n, const float *angles, float *matrices, int32_
 /* Device status word of the last launches: 0, or CMGPU_ERR_LIMIT if any item overflowed its stack. */
 int cmgpu_check_status(cmgpu_ctx *ctx, void *stream);
 
+/* ---- whole SV_Trace / SV_PointContents on the device (server/sv_world.c:330-647) -----
+ * The world pass, the broad phase over the linked entities (SV_AreaEntities, :330-394), the pass / owner /
+ * contents filters (:496-516), one CM_TransformedBoxTrace per surviving entity (:518-528) and the merge
+ * (:532-549) all run on the GPU; results carry entityNum as SV_Trace sets it (:577, :534-546).
+ *
+ * cmgpu_sv_set_entities snapshots the LINKED entities (call it after the frame's SV_LinkEntity calls).  `ents`
+ * should be in the order SV_AreaEntities returns for a box that holds the whole world: ties between entities a
+ * move hits at the same fraction go to the first one in that order.  (Entities are re-bucketed by sector node
+ * here, so only the relative order of entities of the same node is taken from the caller.)  ownerNums[g] is
+ * r.ownerNum of gentity g for g < numGentities (the pass entity's owner, :484-488, need not be linked);
+ * it may be NULL when no move passes an entity.  A bmodel entity whose modelindex is not an inline model of
+ * the uploaded map is CMGPU_ERR_BAD_HANDLE (CM_InlineModel's ERR_DROP, cm_load.c:792-795).                   */
+typedef struct cmgpu_sv_entity_s {
+	int32_t number;                  /* touch->s.number */
+	int32_t ownerNum;                /* touch->r.ownerNum */
+	int32_t contents;                /* touch->r.contents */
+	int32_t bmodel;                  /* touch->r.bmodel: inline model, else the box r.mins/r.maxs (sv_world.c:34-42) */
+	int32_t modelindex;              /* touch->s.modelindex (bmodel only) */
+	float   mins[3], maxs[3];        /* touch->r.mins / r.maxs */
+	float   absmin[3], absmax[3];    /* touch->r.absmin / r.absmax as SV_LinkEntity left them (:243-264) */
+	float   origin[3], angles[3];    /* touch->r.currentOrigin / currentAngles */
+} cmgpu_sv_entity;
+
+int cmgpu_sv_set_entities(cmgpu_ctx *ctx, int n, const cmgpu_sv_entity *ents, const int32_t *ownerNums, int numGentities);
+
+/* n calls of SV_Trace.  HOST pointers; hull_stride / pass_stride / mask_stride 0 = one shared value. */
+int cmgpu_sv_trace_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                         const float *mins, const float *maxs, int hull_stride,
+                         const int32_t *passEntityNums, int pass_stride,
+                         const int32_t *contentmasks, int mask_stride, cmgpu_trace_t *results);
+/* DEVICE pointers for the per-move arrays; shared values (stride 0) are host pointers read at call time.
+ * Enqueues the world pass and the broad phase on `stream`, waits for the candidate count (one 4-byte read),
+ * then enqueues the entity pass and the merge. */
+int cmgpu_sv_trace_batch_device(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                         const float *mins, const float *maxs, int hull_stride,
+                         const int32_t *passEntityNums, int pass_stride,
+                         const int32_t *contentmasks, int mask_stride, cmgpu_trace_t *results, void *stream);
+/* n calls of SV_PointContents (:616-647): world contents | CM_TransformedPointContents of every linked entity
+ * whose box holds the point, except passEntityNum. */
+int cmgpu_sv_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
+                         const int32_t *passEntityNums, int pass_stride, int32_t *contents);
+int cmgpu_sv_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points,
+                         const int32_t *passEntityNums, int pass_stride, int32_t *contents, void *stream);
+/* candidates (entity clips) the last cmgpu_sv_* call generated */
+unsigned long long cmgpu_sv_last_candidates(const cmgpu_ctx *ctx);
+
 /* ---- instrumentation (successor of c_traces/c_brush_traces, cm_load.c:60-61) */
 typedef struct cmgpu_counters_s {
 	unsigned long long traces, nodes, leafs, brushRefs, brushBounds, brushSides, crossings, splits,

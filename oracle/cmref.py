@@ -1,7 +1,8 @@
 """ctypes front-end for oracle/_ref/libcmref.so -- TEST INFRASTRUCTURE.
 
 libcmref.so is the UNMODIFIED reference clip-map code (code/qcommon/cm_*.c,
-q_math.c, q_shared.c) built by oracle/Makefile plus oracle/ref_shim.c.  It is
+q_math.c, q_shared.c, and code/server/sv_world.c) built by oracle/Makefile plus
+oracle/ref_shim.c and oracle/sv_shim.c.  It is
 the checker for parity tests and the timed subject of ``bench.py --impl
 reference`` / the ``cpu_baseline`` leg.  Product code never imports this.
 """
@@ -195,6 +196,59 @@ class RefCM:
             self.lib.cmref_shared_free(C.c_void_p(shared), nbytes)
         self._check(rc, "bench")
         return secs.value, wsecs[:nworkers], out
+
+    # ---- the reference's server world (server/sv_world.c, compiled verbatim; oracle/sv_shim.c) ------------
+    def sv_clear_world(self):
+        """SV_ClearWorld after zeroing all MAX_GENTITIES (4096) gentities (ownerNum = ENTITYNUM_NONE)"""
+        self.lib.svref_clear_world()
+
+    def sv_link_entity(self, num, bmodel, modelindex, mins, maxs, origin, angles, contents, owner=4095):
+        """set the fields the game owns, then SV_LinkEntity; returns r.linked"""
+        mins, maxs, origin, angles = _f(mins), _f(maxs), _f(origin), _f(angles)
+        return self.lib.svref_link_entity(int(num), int(bool(bmodel)), int(modelindex), _p(mins), _p(maxs), _p(origin),
+                                          _p(angles), int(contents), int(owner))
+
+    def sv_set_owner(self, num, owner):
+        self.lib.svref_set_owner(int(num), int(owner))
+
+    def sv_unlink_entity(self, num):
+        self.lib.svref_unlink_entity(int(num))
+
+    def sv_entity_bounds(self, num):
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        linked = self.lib.svref_entity_bounds(int(num), _p(a), _p(b))
+        return a, b, linked
+
+    def sv_area_entities(self, mins, maxs, maxcount=4096):
+        mins, maxs = _f(mins), _f(maxs)
+        lst = np.zeros(maxcount, np.int32)
+        n = self.lib.svref_area_entities(_p(mins), _p(maxs), _p(lst), int(maxcount))
+        return lst[:n].copy()
+
+    def sv_trace(self, starts, ends, mins, maxs, pass_ents, masks):
+        """SV_Trace per item (sv_world.c:562-609)"""
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        mins, maxs, hs = self._hull(n, mins, maxs)
+        pe = np.asarray(pass_ents)
+        pe, ps = (_i(pe.reshape(1)), 0) if pe.ndim == 0 else (_i(pe), 1)
+        m, ms = self._mask(n, masks)
+        out = np.zeros(n, dtype=TRACE_DTYPE)
+        self.lib.svref_trace_batch(_p(out), n, _p(starts), _p(ends), _p(mins), _p(maxs), hs, _p(pe), ps, _p(m), ms)
+        return out
+
+    def sv_point_contents(self, pts, pass_ents):
+        pts = _f(pts)
+        pe = np.asarray(pass_ents)
+        pe, ps = (_i(pe.reshape(1)), 0) if pe.ndim == 0 else (_i(pe), 1)
+        out = np.zeros(pts.shape[0], np.int32)
+        self.lib.svref_point_contents_batch(_p(out), pts.shape[0], _p(pts), _p(pe), ps)
+        return out
+
+    def sv_time_traces(self, starts, ends, mins, maxs, pass_ents, mask):
+        starts, ends, mins, maxs, pe = _f(starts), _f(ends), _f(mins), _f(maxs), _i(pass_ents)
+        self.lib.svref_time_traces.restype = C.c_double
+        return self.lib.svref_time_traces(starts.shape[0], _p(starts), _p(ends), _p(mins), _p(maxs), _p(pe), int(mask))
 
     # ---- dumps of the loaded clipMap_t -----------------------------------
     COUNT_NAMES = ["planes", "nodes", "leafs", "leafbrushes", "leafsurfaces", "brushes", "brushsides",

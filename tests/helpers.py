@@ -94,3 +94,13 @@ def load_golden(name: str):
 
 
 GOLDEN_SETS = ["tiny_world", "room_world", "models_world", "models_entities", "patches_world", "patches_entities"]
+
+
+def load_golden_sv():
+    """tests/golden/sv_world.npz: moves and points against the scene of sv_scene.make_entities(arena_models, 300, 71),
+    answered by the reference's SV_Trace / SV_PointContents (tests/golden/make_golden_sv.py)"""
+    z = np.load(os.path.join(GOLDEN, "sv_world.npz"), allow_pickle=False)
+    g = {k: np.ascontiguousarray(z[k]) for k in z.files}
+    g["traces"] = g["traces"].view(cmref.TRACE_DTYPE).reshape(-1)
+    g["bsp_len"] = int(g["bsp_len"])
+    return g

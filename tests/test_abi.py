@@ -10,7 +10,7 @@ import pytest
 from helpers import ROOT, cmoracle, cmref, get_map, have_ref
 from threecore_b200 import engine
 
-HEADERS = [os.path.join(ROOT, "include", "cm_gpu.h"), os.path.join(ROOT, "include", "cm_public_batch.h")]
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("cm_gpu.h", "cm_public_batch.h", "sv_world_batch.h")]
 
 
 def declared_functions():

@@ -9,6 +9,7 @@
 #include "cm_trace_fast.cuh"
 #include "cm_trace_pool.cuh"
 #include "cm_trace_simple.cuh"
+#include "cm_sv_world.cuh"
 #include "../../include/cm_gpu.h"
 
 #include <math.h>
@@ -108,6 +109,13 @@ struct cmgpu_ctx_s {
 	DevBuf bStarts, bEnds, bMins, bMaxs, bModels, bMasks, bOrigins, bRot, bRotIdx, bBoxMins, bBoxMaxs, bOut, bHit;
 	std::vector<float> hostRot;
 	std::vector<int32_t> hostRotIdx;
+	// SV_Trace on the device (cm_sv_world.cuh): the linked entities in sector order, and the workspaces of a batch
+	float worldBounds[6] = {};           // CM_ModelBounds(0): what SV_ClearWorld builds the sector tree from
+	SvWorld sv{};
+	bool hasSvWorld = false;
+	DevBuf bSvWorld, bSvOffsets, bSvTiles, bSvItems, bSvCand, bSvPass;
+	unsigned *hSvTotal = nullptr;        // pinned
+	unsigned long long svCandidates = 0;
 };
 
 namespace {
@@ -793,7 +801,9 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	freeMap(ctx);
 	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
 	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit,
-	                  &ctx->bKeys, &ctx->bRecs}) releaseBuf(*b);
+	                  &ctx->bKeys, &ctx->bRecs, &ctx->bSvWorld, &ctx->bSvOffsets, &ctx->bSvTiles, &ctx->bSvItems, &ctx->bSvCand,
+	                  &ctx->bSvPass}) releaseBuf(*b);
+	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
 	for (auto &b : ctx->bHist) releaseBuf(b);
 	for (auto &b : ctx->bStackArena) releaseBuf(b);
 	for (auto &b : ctx->bPoolHdr) releaseBuf(b);
@@ -815,8 +825,10 @@ int cmgpu_upload(cmgpu_ctx *ctx, const cmgpu_flatmap *map) {
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaDeviceSynchronize());
 	freeMap(ctx);
+	ctx->hasSvWorld = false;                     // entity snapshots refer to the inline models of the map they were made for
 	rc = packAndUpload(ctx, map);
 	if (rc) freeMap(ctx);
+	else memcpy(ctx->worldBounds, map->modelBounds, sizeof(ctx->worldBounds));
 	return rc;
 }
 
@@ -1247,6 +1259,352 @@ int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
 	                                       boxmins ? (const float *)ctx->bBoxMins.p : nullptr,
 	                                       boxmins ? (const float *)ctx->bBoxMaxs.p : nullptr,
 	                                       (int32_t *)ctx->bHit.p, s);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(contents, ctx->bHit.p, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return CMGPU_OK;
+}
+
+}  // extern "C"
+
+// ---- SV_Trace / SV_PointContents on the device (cm_sv_world.cuh) ---------------------------
+
+namespace {
+
+struct SectorNode { int axis; float dist; int child[2]; int parent, side, end; };
+
+// SV_CreateworldSector (sv_world.c:81-113): depth 4, split the longer of x and y at its middle; children[0] is the
+// upper half.  Nodes are numbered in creation order, which is depth first with children[0] before children[1].
+int buildSectors(std::vector<SectorNode> &nodes, int depth, const float *mins, const float *maxs, int parent, int side) {
+	const int me = (int)nodes.size();
+	nodes.push_back(SectorNode{-1, 0.0f, {-1, -1}, parent, side, 0});
+	if (depth < 4) {
+		const float sx = maxs[0] - mins[0], sy = maxs[1] - mins[1];
+		const int axis = sx > sy ? 0 : 1;
+		const float dist = (float)(0.5 * (double)(maxs[axis] + mins[axis]));
+		nodes[me].axis = axis;
+		nodes[me].dist = dist;
+		float mins1[3], maxs1[3], mins2[3], maxs2[3];
+		memcpy(mins1, mins, 12); memcpy(mins2, mins, 12); memcpy(maxs1, maxs, 12); memcpy(maxs2, maxs, 12);
+		maxs1[axis] = mins2[axis] = dist;
+		const int c0 = buildSectors(nodes, depth + 1, mins2, maxs2, me, 0);
+		const int c1 = buildSectors(nodes, depth + 1, mins1, maxs1, me, 1);
+		nodes[me].child[0] = c0;
+		nodes[me].child[1] = c1;
+	}
+	nodes[me].end = (int)nodes.size();
+	return me;
+}
+
+template <typename T>
+T *carve(std::vector<char> &host, size_t count, size_t &offset) {
+	offset = (host.size() + 255) & ~(size_t)255;
+	host.resize(offset + count * sizeof(T));
+	return reinterpret_cast<T *>(host.data() + offset);
+}
+
+// exclusive prefix sum of counts[0..m) in place (the binning scan kernels)
+int scanOffsets(cmgpu_ctx *ctx, unsigned *counts, int m, cudaStream_t s) {
+	const int tiles = (m + kScanTile - 1) / kScanTile;
+	int rc = reserve(ctx, ctx->bSvTiles, (size_t)tiles * 4);
+	if (rc) return rc;
+	unsigned *tileSums = (unsigned *)ctx->bSvTiles.p;
+	binTileSumKernel<<<tiles, 256, 0, s>>>(counts, m, tileSums);
+	binTileScanKernel<<<1, 256, 0, s>>>(tileSums, tiles);
+	binScanKernel<<<tiles, 256, 0, s>>>(counts, m, tileSums);
+	ctx->launches += 3;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int readTotal(cmgpu_ctx *ctx, const unsigned *offsets, int n, cudaStream_t s, unsigned *total) {
+	if (!ctx->hSvTotal) CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->hSvTotal, sizeof(unsigned)));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hSvTotal, offsets + n, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	*total = *ctx->hSvTotal;
+	if (*total > 0x7fffff00u) return fail(ctx, CMGPU_ERR_LIMIT, "SV batch: %u entity clips do not fit one launch", *total);
+	return CMGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmgpu_sv_set_entities(cmgpu_ctx *ctx, int n, const cmgpu_sv_entity *ents, const int32_t *ownerNums, int numGentities) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && !ents) || numGentities < 0 || (numGentities > 0 && !ownerNums))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_sv_set_entities: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	for (int i = 0; i < n; i++) {
+		if (ents[i].bmodel && (ents[i].modelindex < 0 || ents[i].modelindex >= ctx->numModels))
+			return fail(ctx, CMGPU_ERR_BAD_HANDLE, "CM_InlineModel: bad number %i (entity %d)", ents[i].modelindex, ents[i].number);
+	}
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	std::vector<SectorNode> nodes;
+	buildSectors(nodes, 0, ctx->worldBounds, ctx->worldBounds + 3, -1, -1);
+	// SV_LinkEntity's descent (sv_world.c:308-320): the first node whose plane the box straddles, or a leaf
+	std::vector<int> nodeOf((size_t)n), order((size_t)n);
+	std::vector<int> perNode(nodes.size() + 1, 0);
+	for (int i = 0; i < n; i++) {
+		int k = 0;
+		while (nodes[k].axis != -1) {
+			if (ents[i].absmin[nodes[k].axis] > nodes[k].dist) k = nodes[k].child[0];
+			else if (ents[i].absmax[nodes[k].axis] < nodes[k].dist) k = nodes[k].child[1];
+			else break;
+		}
+		nodeOf[i] = k;
+		perNode[k + 1]++;
+	}
+	for (size_t k = 0; k < nodes.size(); k++) perNode[k + 1] += perNode[k];
+	{
+		std::vector<int> next(perNode.begin(), perNode.end() - 1);
+		for (int i = 0; i < n; i++) order[next[nodeOf[i]]++] = i;          // stable: the caller's order inside a node
+	}
+	const size_t E = (size_t)n, G = (size_t)numGentities;
+	std::vector<char> host;
+	size_t oNodes, oLo, oHi, oInfo, oOrg, oMins, oMaxs, oRot, oOwner;
+	carve<int4>(host, 2 * nodes.size(), oNodes);
+	carve<float4>(host, E + 1, oLo);
+	carve<float4>(host, E + 1, oHi);
+	carve<int4>(host, E + 1, oInfo);
+	carve<float>(host, 3 * E + 3, oOrg);
+	carve<float>(host, 3 * E + 3, oMins);
+	carve<float>(host, 3 * E + 3, oMaxs);
+	carve<float>(host, 9 * E + 9, oRot);
+	carve<int>(host, G + 1, oOwner);
+	int4 *hNodes = reinterpret_cast<int4 *>(host.data() + oNodes);
+	for (size_t k = 0; k < nodes.size(); k++) {
+		const SectorNode &nd = nodes[k];
+		int axis = 0, distBits = 0;
+		if (nd.parent >= 0) { axis = nodes[nd.parent].axis; memcpy(&distBits, &nodes[nd.parent].dist, 4); }
+		hNodes[2 * k] = make_int4(axis, distBits, nd.side, nd.end);
+		hNodes[2 * k + 1] = make_int4(perNode[k], perNode[k + 1], 0, 0);
+	}
+	std::vector<float> angles(3 * E + 3, 0.0f);
+	std::vector<int32_t> rotIdx(E + 1, -1);
+	for (size_t j = 0; j < E; j++) {
+		const cmgpu_sv_entity &e = ents[order[j]];
+		float4 lo = make_float4(e.absmin[0], e.absmin[1], e.absmin[2], 0.0f), hi = make_float4(e.absmax[0], e.absmax[1], e.absmax[2], 0.0f);
+		memcpy(&lo.w, &e.ownerNum, 4);
+		memcpy(&hi.w, &e.contents, 4);
+		reinterpret_cast<float4 *>(host.data() + oLo)[j] = lo;
+		reinterpret_cast<float4 *>(host.data() + oHi)[j] = hi;
+		memcpy(host.data() + oOrg + 12 * j, e.origin, 12);
+		memcpy(host.data() + oMins + 12 * j, e.mins, 12);
+		memcpy(host.data() + oMaxs + 12 * j, e.maxs, 12);
+		memcpy(&angles[3 * j], e.angles, 12);
+	}
+	// rotation matrices with the host's libm, as for every transformed trace (cm_trace.c:776-779)
+	cmgpu_rotation_matrices(n, angles.data(), reinterpret_cast<float *>(host.data() + oRot), rotIdx.data());
+	for (size_t j = 0; j < E; j++) {
+		const cmgpu_sv_entity &e = ents[order[j]];
+		// SV_ClipHandleForEntity (sv_world.c:34-42)
+		reinterpret_cast<int4 *>(host.data() + oInfo)[j] = make_int4(e.number, e.bmodel ? e.modelindex : CMGPU_BOX_MODEL_HANDLE, rotIdx[j], 0);
+	}
+	if (G) memcpy(host.data() + oOwner, ownerNums, 4 * G);
+	CUDA_TRY(ctx, cudaDeviceSynchronize());                                 // nothing may still be reading the old snapshot
+	int rc = reserve(ctx, ctx->bSvWorld, host.size());
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpy(ctx->bSvWorld.p, host.data(), host.size(), cudaMemcpyHostToDevice));
+	const char *base = (const char *)ctx->bSvWorld.p;
+	SvWorld &w = ctx->sv;
+	w.nodes = (const int4 *)(base + oNodes);
+	w.entLo = (const float4 *)(base + oLo);
+	w.entHi = (const float4 *)(base + oHi);
+	w.entInfo = (const int4 *)(base + oInfo);
+	w.entOrigin = (const float *)(base + oOrg);
+	w.entMins = (const float *)(base + oMins);
+	w.entMaxs = (const float *)(base + oMaxs);
+	w.entRot = (const float *)(base + oRot);
+	w.ownerByNum = (const int *)(base + oOwner);
+	w.numNodes = (int)nodes.size();
+	w.numEnts = n;
+	w.numGentities = numGentities;
+	ctx->hasSvWorld = true;
+	return CMGPU_OK;
+}
+
+unsigned long long cmgpu_sv_last_candidates(const cmgpu_ctx *ctx) { return ctx ? ctx->svCandidates : 0; }
+
+int cmgpu_sv_trace_batch_device(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                                const float *mins, const float *maxs, int hull_stride,
+                                const int32_t *passEntityNums, int pass_stride,
+                                const int32_t *contentmasks, int mask_stride, cmgpu_trace_t *results, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!starts || !ends || !passEntityNums || !contentmasks || !results)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_sv_trace_batch_device: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (!ctx->hasSvWorld) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_sv_set_entities has not been called for this map");
+	if ((mins == nullptr) != (maxs == nullptr)) return fail(ctx, CMGPU_ERR_INVALID, "mins and maxs must both be given or both be NULL");
+	if (hull_stride && !mins) hull_stride = 0;
+	ctx->svCandidates = 0;
+	if (n == 0) return CMGPU_OK;
+	cudaStream_t s = (cudaStream_t)stream;
+	// 1. clip to world (sv_world.c:576)
+	int rc = cmgpu_box_trace_batch_device(ctx, n, starts, ends, mins, maxs, hull_stride, nullptr, contentmasks, mask_stride,
+	                                      nullptr, nullptr, nullptr, nullptr, nullptr, results, nullptr, stream);
+	if (rc) return rc;
+	// 2. count the entities every move has to be clipped against
+	if ((rc = reserve(ctx, ctx->bSvOffsets, ((size_t)n + 1) * 4))) return rc;
+	SvMoves q{};
+	q.n = n; q.starts = starts; q.ends = ends;
+	if (hull_stride) { q.mins = mins; q.maxs = maxs; }
+	else if (mins) { memcpy(q.sharedMins, mins, 12); memcpy(q.sharedMaxs, maxs, 12); }
+	if (pass_stride) q.passEnts = passEntityNums; else q.sharedPass = passEntityNums[0];
+	if (mask_stride) q.masks = contentmasks; else q.sharedMask = contentmasks[0];
+	q.results = reinterpret_cast<uint2 *>(results);
+	q.offsets = (unsigned *)ctx->bSvOffsets.p;
+	const int grid = (n + 127) / 128;
+	CUDA_TRY(ctx, cudaMemsetAsync(q.offsets + n, 0, 4, s));
+	svGatherKernel<false><<<grid, 128, 0, s>>>(ctx->sv, q, SvItems{});
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	if ((rc = scanOffsets(ctx, q.offsets, n + 1, s))) return rc;
+	unsigned total = 0;
+	if ((rc = readTotal(ctx, q.offsets, n, s, &total))) return rc;
+	ctx->svCandidates = total;
+	if (total == 0) return CMGPU_OK;
+	// 3. one transformed-trace item per (move, entity)
+	const size_t T = total, v3 = 12;
+	const size_t perItem = 5 * v3 + (hull_stride ? 2 * v3 : 0) + 4 /*model*/ + (mask_stride ? 4 : 0) + 4 /*rot*/ + 4 /*number*/;
+	if ((rc = reserve(ctx, ctx->bSvItems, T * perItem + 16 * 256))) return rc;
+	if ((rc = reserve(ctx, ctx->bSvCand, T * sizeof(cmgpu_trace_t)))) return rc;
+	char *p = (char *)ctx->bSvItems.p;
+	auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+	SvItems it{};
+	it.starts = (float *)take(T * v3); it.ends = (float *)take(T * v3);
+	if (hull_stride) { it.mins = (float *)take(T * v3); it.maxs = (float *)take(T * v3); }
+	it.models = (int *)take(T * 4);
+	if (mask_stride) it.masks = (int *)take(T * 4);
+	it.origins = (float *)take(T * v3);
+	it.rotIndex = (int *)take(T * 4);
+	it.boxmins = (float *)take(T * v3); it.boxmaxs = (float *)take(T * v3);
+	it.entNumber = (int *)take(T * 4);
+	svGatherKernel<true><<<grid, 128, 0, s>>>(ctx->sv, q, it);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	// 4. clip to the entities (sv_world.c:526-528), all moves in one launch
+	const int32_t sharedMask = mask_stride ? 0 : contentmasks[0];
+	rc = cmgpu_box_trace_batch_device(ctx, (int)total, it.starts, it.ends,
+	                                  hull_stride ? it.mins : mins, hull_stride ? it.maxs : maxs, hull_stride,
+	                                  it.models, mask_stride ? it.masks : &sharedMask, mask_stride,
+	                                  it.origins, ctx->sv.entRot, it.rotIndex, it.boxmins, it.boxmaxs,
+	                                  (cmgpu_trace_t *)ctx->bSvCand.p, nullptr, stream);
+	if (rc) return rc;
+	// 5. merge in list order
+	svMergeKernel<<<grid, 128, 0, s>>>(n, q.results, q.offsets, (const uint2 *)ctx->bSvCand.p, it.entNumber);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_sv_trace_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                         const float *mins, const float *maxs, int hull_stride,
+                         const int32_t *passEntityNums, int pass_stride,
+                         const int32_t *contentmasks, int mask_stride, cmgpu_trace_t *results) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!starts || !ends || !passEntityNums || !contentmasks || !results)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_sv_trace_batch: bad argument");
+	if (n == 0) return CMGPU_OK;
+	if (hull_stride && !mins) hull_stride = 0;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n, v3 = 12;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
+	if ((rc = reserve(ctx, ctx->bEnds, N * v3))) return rc;
+	if (hull_stride) {
+		if ((rc = reserve(ctx, ctx->bMins, N * v3))) return rc;
+		if ((rc = reserve(ctx, ctx->bMaxs, N * v3))) return rc;
+	}
+	if (mask_stride && (rc = reserve(ctx, ctx->bMasks, N * 4))) return rc;
+	if (pass_stride && (rc = reserve(ctx, ctx->bSvPass, N * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bOut, N * sizeof(cmgpu_trace_t)))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, starts, N * v3, cudaMemcpyHostToDevice, s));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bEnds.p, ends, N * v3, cudaMemcpyHostToDevice, s));
+	if (hull_stride) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMins.p, mins, N * v3, cudaMemcpyHostToDevice, s));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMaxs.p, maxs, N * v3, cudaMemcpyHostToDevice, s));
+	}
+	if (mask_stride) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMasks.p, contentmasks, N * 4, cudaMemcpyHostToDevice, s));
+	if (pass_stride) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bSvPass.p, passEntityNums, N * 4, cudaMemcpyHostToDevice, s));
+	rc = cmgpu_sv_trace_batch_device(ctx, n, (const float *)ctx->bStarts.p, (const float *)ctx->bEnds.p,
+	                                 hull_stride ? (const float *)ctx->bMins.p : mins, hull_stride ? (const float *)ctx->bMaxs.p : maxs, hull_stride,
+	                                 pass_stride ? (const int32_t *)ctx->bSvPass.p : passEntityNums, pass_stride,
+	                                 mask_stride ? (const int32_t *)ctx->bMasks.p : contentmasks, mask_stride,
+	                                 (cmgpu_trace_t *)ctx->bOut.p, s);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->bOut.p, N * sizeof(cmgpu_trace_t), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return cmgpu_check_status(ctx, s);
+}
+
+int cmgpu_sv_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points,
+                                         const int32_t *passEntityNums, int pass_stride, int32_t *contents, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !passEntityNums || !contents)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_sv_point_contents_batch_device: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (!ctx->hasSvWorld) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_sv_set_entities has not been called for this map");
+	ctx->svCandidates = 0;
+	if (n == 0) return CMGPU_OK;
+	cudaStream_t s = (cudaStream_t)stream;
+	// base contents from the world (sv_world.c:625)
+	int rc = cmgpu_point_contents_batch_device(ctx, n, points, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, contents, stream);
+	if (rc) return rc;
+	if ((rc = reserve(ctx, ctx->bSvOffsets, ((size_t)n + 1) * 4))) return rc;
+	unsigned *offsets = (unsigned *)ctx->bSvOffsets.p;
+	const int grid = (n + 127) / 128;
+	const int *passDev = pass_stride ? passEntityNums : nullptr;
+	const int sharedPass = pass_stride ? 0 : passEntityNums[0];
+	CUDA_TRY(ctx, cudaMemsetAsync(offsets + n, 0, 4, s));
+	svPointGatherKernel<false><<<grid, 128, 0, s>>>(ctx->sv, n, points, passDev, sharedPass, offsets, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	if ((rc = scanOffsets(ctx, offsets, n + 1, s))) return rc;
+	unsigned total = 0;
+	if ((rc = readTotal(ctx, offsets, n, s, &total))) return rc;
+	ctx->svCandidates = total;
+	if (total == 0) return CMGPU_OK;
+	const size_t T = total, v3 = 12;
+	if ((rc = reserve(ctx, ctx->bSvItems, T * (4 * v3 + 8) + 8 * 256))) return rc;
+	if ((rc = reserve(ctx, ctx->bSvCand, T * 4))) return rc;
+	char *p = (char *)ctx->bSvItems.p;
+	auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+	float *itPoints = (float *)take(T * v3), *itOrigins = (float *)take(T * v3);
+	float *itBoxMins = (float *)take(T * v3), *itBoxMaxs = (float *)take(T * v3);
+	int *itModels = (int *)take(T * 4), *itRot = (int *)take(T * 4);
+	svPointGatherKernel<true><<<grid, 128, 0, s>>>(ctx->sv, n, points, passDev, sharedPass, offsets, itPoints, itModels, itOrigins, itRot, itBoxMins, itBoxMaxs);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	// CM_TransformedPointContents of every candidate (sv_world.c:641)
+	rc = cmgpu_point_contents_batch_device(ctx, (int)total, itPoints, itModels, itOrigins, ctx->sv.entRot, itRot, itBoxMins, itBoxMaxs,
+	                                       (int32_t *)ctx->bSvCand.p, stream);
+	if (rc) return rc;
+	svPointMergeKernel<<<grid, 128, 0, s>>>(n, contents, offsets, (const int *)ctx->bSvCand.p);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_sv_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
+                                  const int32_t *passEntityNums, int pass_stride, int32_t *contents) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !passEntityNums || !contents)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_sv_point_contents_batch: bad argument");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, N * 12))) return rc;
+	if (pass_stride && (rc = reserve(ctx, ctx->bSvPass, N * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, points, N * 12, cudaMemcpyHostToDevice, s));
+	if (pass_stride) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bSvPass.p, passEntityNums, N * 4, cudaMemcpyHostToDevice, s));
+	rc = cmgpu_sv_point_contents_batch_device(ctx, n, (const float *)ctx->bStarts.p,
+	                                          pass_stride ? (const int32_t *)ctx->bSvPass.p : passEntityNums, pass_stride,
+	                                          (int32_t *)ctx->bHit.p, s);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(contents, ctx->bHit.p, N * 4, cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(ctx, cudaStreamSynchronize(s));

@@ -88,6 +88,13 @@ _SCALARS = [("box_brush", "boxBrush"), ("box_first_plane", "boxFirstPlane"), ("b
 _lib = None
 
 
+# cmgpu_sv_entity (include/cm_gpu.h): one linked entity as SV_ClipMoveToEntities reads it
+SV_ENTITY_DTYPE = np.dtype([("number", "<i4"), ("ownerNum", "<i4"), ("contents", "<i4"), ("bmodel", "<i4"), ("modelindex", "<i4"),
+                            ("mins", "<f4", (3,)), ("maxs", "<f4", (3,)), ("absmin", "<f4", (3,)), ("absmax", "<f4", (3,)),
+                            ("origin", "<f4", (3,)), ("angles", "<f4", (3,))])
+assert SV_ENTITY_DTYPE.itemsize == 92
+
+
 def load_library() -> C.CDLL:
     """Load libcmgpu.so; loud failure when it has not been built (no fallback exists)."""
     global _lib
@@ -131,6 +138,13 @@ def load_library() -> C.CDLL:
                                                  vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cmgpu_point_contents_batch_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cmgpu_rotation_matrices.argtypes = [C.c_int, vp, vp, vp]
+    lib.cmgpu_sv_set_entities.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+    lib.cmgpu_sv_trace_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]
+    lib.cmgpu_sv_trace_batch_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.cmgpu_sv_point_contents_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
+    lib.cmgpu_sv_point_contents_batch_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.cmgpu_sv_last_candidates.argtypes = [vp]
+    lib.cmgpu_sv_last_candidates.restype = C.c_ulonglong
     lib.cmgpu_rotation_matrices.restype = None
     if lib.cmgpu_abi_version() != 1:
         raise ImportError("libcmgpu.so ABI version mismatch")
@@ -442,6 +456,63 @@ class Engine:
         self._check(self.lib.cmgpu_point_contents_batch_device(
             self.h, n, ptr(points), ptr(models), ptr(origins), ptr(rotations), ptr(rot_index),
             ptr(boxmins), ptr(boxmaxs), ptr(out), C.c_void_p(stream)))
+
+    # ---- whole SV_Trace on the device (server/sv_world.c:562-609) -----------------
+    def sv_set_entities(self, ents: np.ndarray, owner_nums=None):
+        """ents: structured array of SV_ENTITY_DTYPE (the linked entities, in SV_AreaEntities order);
+        owner_nums: r.ownerNum of every gentity by number (for the pass entity's owner), or None"""
+        ents = np.ascontiguousarray(ents, dtype=SV_ENTITY_DTYPE)
+        own = None if owner_nums is None else _i(owner_nums)
+        self._check(self.lib.cmgpu_sv_set_entities(self.h, len(ents), _p(ents), _p(own), 0 if own is None else len(own)))
+
+    def sv_trace(self, starts, ends, mins, maxs, pass_ents, masks):
+        """host arrays in, structured trace_t array out; hull / pass entity / mask shared (1-d, scalar) or per move"""
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        mins, maxs, hs = self._hull(n, mins, maxs)
+        pe = np.asarray(pass_ents)
+        pe, ps = (_i(pe.reshape(1)), 0) if pe.ndim == 0 else (_i(pe), 1)
+        m, ms = self._mask(n, masks)
+        out = np.zeros(n, dtype=TRACE_DTYPE)
+        self._check(self.lib.cmgpu_sv_trace_batch(self.h, n, _p(starts), _p(ends), _p(mins), _p(maxs), hs, _p(pe), ps,
+                                                  _p(m), ms, _p(out)))
+        return out
+
+    def sv_trace_device(self, starts, ends, mins, maxs, pass_ent, mask, out, stream=None):
+        """resident moves (CUDA tensors [n,3]); shared hull (3 host floats each), pass entity and mask (ints),
+        or per-move CUDA tensors for any of them"""
+        import torch
+        n = starts.shape[0]
+        if stream is None:
+            stream = torch.cuda.current_stream(starts.device).cuda_stream
+        keep = []
+
+        def shared_or_tensor(v, dtype):
+            if isinstance(v, torch.Tensor):
+                return v.data_ptr(), 1
+            if v is None:
+                return None, 0
+            h = np.ascontiguousarray(np.asarray(v).reshape(-1), dtype=dtype)
+            keep.append(h)
+            return h.ctypes.data, 0
+        pmins, hs = shared_or_tensor(mins, np.float32)
+        pmaxs, _ = shared_or_tensor(maxs, np.float32)
+        ppass, ps = shared_or_tensor(np.int64(pass_ent).astype(np.int32) if not isinstance(pass_ent, torch.Tensor) else pass_ent, np.int32)
+        pmask, ms = shared_or_tensor(np.int64(mask).astype(np.int32) if not isinstance(mask, torch.Tensor) else mask, np.int32)
+        self._check(self.lib.cmgpu_sv_trace_batch_device(self.h, n, starts.data_ptr(), ends.data_ptr(), pmins, pmaxs, hs,
+                                                         ppass, ps, pmask, ms, out.data_ptr(), C.c_void_p(stream)))
+
+    def sv_point_contents(self, pts, pass_ents):
+        pts = _f(pts)
+        pe = np.asarray(pass_ents)
+        pe, ps = (_i(pe.reshape(1)), 0) if pe.ndim == 0 else (_i(pe), 1)
+        out = np.zeros(pts.shape[0], np.int32)
+        self._check(self.lib.cmgpu_sv_point_contents_batch(self.h, pts.shape[0], _p(pts), _p(pe), ps, _p(out)))
+        return out
+
+    @property
+    def sv_last_candidates(self) -> int:
+        return int(self.lib.cmgpu_sv_last_candidates(self.h))
 
     def check_status(self, stream=None):
         import torch
