@@ -147,6 +147,17 @@ def cpu_reference_run(data, starts, ends, sample, repeats=1):
     return sample / secs / 1e6, 1, "port", secs
 
 
+def single_core_run(data, starts, ends, sample):
+    """the same reference code on ONE core (SURVEY 8d asks for both figures)"""
+    from oracle import cmref
+    if not cmref.available():
+        return None
+    r = cmref.RefCM().load(data)
+    secs, _, _ = r.bench_box_trace(starts[:sample], ends[:sample], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS,
+                                   bspgen.MASK_PLAYERSOLID, nworkers=1, repeats=1)
+    return sample / secs / 1e6
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -270,16 +281,47 @@ def run_ours(args):
     # the e2e results must be the same records the resident arm produced
     same = bool(torch.equal(h_out[: 1 << 16], d_out[: 1 << 16].cpu()))
 
+    # ---- L2 working-set roofline: visit counts of this very batch from the counting kernel variant (untimed),
+    # priced with the reference's own record sizes, against an L2-resident copy measured here
+    l2 = None
+    if rank == 0:
+        eng.enable_counters(True)
+        eng.read_counters(reset=True)
+        step()
+        torch.cuda.synchronize()
+        c = eng.read_counters(reset=True)
+        eng.enable_counters(False)
+        l2_bytes = (36 * c["nodes"] + 24 * c["leafs"] + 4 * c["brushRefs"] + 56 * c["brushBounds"] + 36 * c["brushSides"]
+                    + 20 * c["patchPlanes"] + 320 * c["facets"])
+        nb = 24 << 20                                   # two 24 MiB buffers: resident in the 126 MB L2
+        a = torch.empty(nb, dtype=torch.uint8, device=dev)
+        b = torch.empty(nb, dtype=torch.uint8, device=dev)
+        best = 1e9
+        for _ in range(30):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            b.copy_(a)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        l2_peak = 2 * nb / (best * 1e-3) / 1e9
+        del a, b
+        l2 = {"bytes_per_trace": l2_bytes / max(c["traces"], 1), "peak": l2_peak, "unit": "GB/s",
+              "peak_source": "measured here: copy of a 24 MiB buffer that stays in L2, read+write bytes, best of 30",
+              "visits_per_trace": {k: c[k] / max(c["traces"], 1) for k in ("nodes", "leafs", "brushRefs", "brushBounds", "brushSides", "splits")}}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         kms = trace_ms / max(trace_launches, 1)        # the dominant kernel alone
+        l2["achieved"] = l2["bytes_per_trace"] * n / (kms * 1e-3) / 1e9
+        l2["frac"] = l2["achieved"] / l2["peak"]
         achieved = BYTES_PER_TRACE * n / (kms * 1e-3) / 1e9
         tr = ncu_traffic()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr or {}).get("dram_bytes_per_launch") if n == N_RAYS else None, "peak_source": peak_src,
                 "kernel": "cmgpu::tracePoolKernel<false, 3>", "kernel_ms": kms, "kernel_launches": trace_launches,
                 "step_ms": float(np.mean(kern_ms)),
-                "algorithmic_bytes_per_trace": BYTES_PER_TRACE, "traces_per_launch": n,
+                "algorithmic_bytes_per_trace": BYTES_PER_TRACE, "traces_per_launch": n, "l2": l2,
                 "note": "irregular BSP walk: bound by instruction issue and dependent-load latency, not by HBM; the HBM floor "
                         "is reported because the metric asks for it (DESIGN.md 4.1)"}
         line = {"metric": METRIC, "value": value, "unit": "Mtraces/s", "n_gpus": world, "steps": args.steps,
@@ -292,7 +334,8 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks, "hit_fraction": hits}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, kind, secs = cpu_reference_run(m.data, starts, ends, min(args.ref_sample, n))
-            line["cpu_baseline"] = {"value": v, "unit": "Mtraces/s", "cores": cores, "kind": kind,
+            one = single_core_run(m.data, starts, ends, min(1 << 18, n))
+            line["cpu_baseline"] = {"value": v, "unit": "Mtraces/s", "cores": cores, "kind": kind, "single_core": one,
                                     "sample": f"first {min(args.ref_sample, n)} rays of the same stream, one forked "
                                               f"worker per host core, {secs:.2f} s wall"}
         sys.stdout.flush()

@@ -102,5 +102,5 @@ def load_golden_sv():
     z = np.load(os.path.join(GOLDEN, "sv_world.npz"), allow_pickle=False)
     g = {k: np.ascontiguousarray(z[k]) for k in z.files}
     g["traces"] = g["traces"].view(cmref.TRACE_DTYPE).reshape(-1)
-    g["bsp_len"] = int(g["bsp_len"])
+    g["bsp_len"] = int(g["bsp_len"].reshape(-1)[0])
     return g

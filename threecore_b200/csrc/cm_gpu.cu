@@ -1362,7 +1362,39 @@ int cmgpu_sv_set_entities(cmgpu_ctx *ctx, int n, const cmgpu_sv_entity *ents, co
 	}
 	const size_t E = (size_t)n, G = (size_t)numGentities;
 	std::vector<char> host;
-	size_t oNodes, oLo, oHi, oInfo, oOrg, oMins, oMaxs, oRot, oOwner;
+	// the two grids (cm_sv_world.cuh): per cell, the entities whose box reaches it
+	const int gridCells[2] = {32, 8};
+	float gridLo[2], gridInv[2][2];
+	std::vector<int> cellStart[2], cellEnts[2];
+	std::vector<int> firstCell((size_t)n, 0);
+	for (int a = 0; a < 2; a++) gridLo[a] = ctx->worldBounds[a];
+	for (int l = 0; l < 2; l++) {
+		const int G = gridCells[l];
+		for (int a = 0; a < 2; a++) {
+			const float size = ctx->worldBounds[3 + a] - ctx->worldBounds[a];
+			gridInv[l][a] = size > 0.0f ? (float)G / size : 0.0f;
+		}
+		std::vector<int> count((size_t)G * G + 1, 0);
+		auto range = [&](const cmgpu_sv_entity &e, int *r) {
+			r[0] = svCellOf(e.absmin[0], gridLo[0], gridInv[l][0], G); r[1] = svCellOf(e.absmax[0], gridLo[0], gridInv[l][0], G);
+			r[2] = svCellOf(e.absmin[1], gridLo[1], gridInv[l][1], G); r[3] = svCellOf(e.absmax[1], gridLo[1], gridInv[l][1], G);
+		};
+		int r[4];
+		for (int j = 0; j < n; j++) {
+			range(ents[order[j]], r);
+			for (int y = r[2]; y <= r[3]; y++) for (int x = r[0]; x <= r[1]; x++) count[(size_t)y * G + x + 1]++;
+		}
+		for (size_t c = 0; c < (size_t)G * G; c++) count[c + 1] += count[c];
+		cellStart[l] = count;
+		cellEnts[l].assign((size_t)count.back() + 1, 0);
+		std::vector<int> next(count.begin(), count.end() - 1);
+		for (int j = 0; j < n; j++) {
+			range(ents[order[j]], r);
+			firstCell[j] |= (r[0] | r[2] << 8) << (16 * l);
+			for (int y = r[2]; y <= r[3]; y++) for (int x = r[0]; x <= r[1]; x++) cellEnts[l][next[(size_t)y * G + x]++] = j;
+		}
+	}
+	size_t oNodes, oLo, oHi, oInfo, oOrg, oMins, oMaxs, oRot, oOwner, oCellStart[2], oCellEnts[2];
 	carve<int4>(host, 2 * nodes.size(), oNodes);
 	carve<float4>(host, E + 1, oLo);
 	carve<float4>(host, E + 1, oHi);
@@ -1372,6 +1404,12 @@ int cmgpu_sv_set_entities(cmgpu_ctx *ctx, int n, const cmgpu_sv_entity *ents, co
 	carve<float>(host, 3 * E + 3, oMaxs);
 	carve<float>(host, 9 * E + 9, oRot);
 	carve<int>(host, G + 1, oOwner);
+	for (int l = 0; l < 2; l++) {
+		int *p0 = carve<int>(host, cellStart[l].size(), oCellStart[l]);
+		memcpy(p0, cellStart[l].data(), 4 * cellStart[l].size());
+		int *p1 = carve<int>(host, cellEnts[l].size(), oCellEnts[l]);
+		memcpy(p1, cellEnts[l].data(), 4 * cellEnts[l].size());
+	}
 	int4 *hNodes = reinterpret_cast<int4 *>(host.data() + oNodes);
 	for (size_t k = 0; k < nodes.size(); k++) {
 		const SectorNode &nd = nodes[k];
@@ -1399,7 +1437,7 @@ int cmgpu_sv_set_entities(cmgpu_ctx *ctx, int n, const cmgpu_sv_entity *ents, co
 	for (size_t j = 0; j < E; j++) {
 		const cmgpu_sv_entity &e = ents[order[j]];
 		// SV_ClipHandleForEntity (sv_world.c:34-42)
-		reinterpret_cast<int4 *>(host.data() + oInfo)[j] = make_int4(e.number, e.bmodel ? e.modelindex : CMGPU_BOX_MODEL_HANDLE, rotIdx[j], 0);
+		reinterpret_cast<int4 *>(host.data() + oInfo)[j] = make_int4(e.number, e.bmodel ? e.modelindex : CMGPU_BOX_MODEL_HANDLE, rotIdx[j], firstCell[j]);
 	}
 	if (G) memcpy(host.data() + oOwner, ownerNums, 4 * G);
 	CUDA_TRY(ctx, cudaDeviceSynchronize());                                 // nothing may still be reading the old snapshot
@@ -1420,6 +1458,13 @@ int cmgpu_sv_set_entities(cmgpu_ctx *ctx, int n, const cmgpu_sv_entity *ents, co
 	w.numNodes = (int)nodes.size();
 	w.numEnts = n;
 	w.numGentities = numGentities;
+	for (int l = 0; l < 2; l++) {
+		w.cellStart[l] = (const int *)(base + oCellStart[l]);
+		w.cellEnts[l] = (const int *)(base + oCellEnts[l]);
+		w.gridCells[l] = gridCells[l];
+		w.gridInv[l][0] = gridInv[l][0]; w.gridInv[l][1] = gridInv[l][1];
+	}
+	w.gridLo[0] = gridLo[0]; w.gridLo[1] = gridLo[1];
 	ctx->hasSvWorld = true;
 	return CMGPU_OK;
 }
@@ -1445,7 +1490,8 @@ int cmgpu_sv_trace_batch_device(cmgpu_ctx *ctx, int n, const float *starts, cons
 	                                      nullptr, nullptr, nullptr, nullptr, nullptr, results, nullptr, stream);
 	if (rc) return rc;
 	// 2. count the entities every move has to be clipped against
-	if ((rc = reserve(ctx, ctx->bSvOffsets, ((size_t)n + 1) * 4))) return rc;
+	const size_t offBytes = (((size_t)n + 1) * 4 + 255) & ~(size_t)255;
+	if ((rc = reserve(ctx, ctx->bSvOffsets, offBytes + (size_t)n * sizeof(int4)))) return rc;
 	SvMoves q{};
 	q.n = n; q.starts = starts; q.ends = ends;
 	if (hull_stride) { q.mins = mins; q.maxs = maxs; }
@@ -1454,6 +1500,7 @@ int cmgpu_sv_trace_batch_device(cmgpu_ctx *ctx, int n, const float *starts, cons
 	if (mask_stride) q.masks = contentmasks; else q.sharedMask = contentmasks[0];
 	q.results = reinterpret_cast<uint2 *>(results);
 	q.offsets = (unsigned *)ctx->bSvOffsets.p;
+	q.firstCands = (int4 *)((char *)ctx->bSvOffsets.p + offBytes);
 	const int grid = (n + 127) / 128;
 	CUDA_TRY(ctx, cudaMemsetAsync(q.offsets + n, 0, 4, s));
 	svGatherKernel<false><<<grid, 128, 0, s>>>(ctx->sv, q, SvItems{});
@@ -1479,7 +1526,7 @@ int cmgpu_sv_trace_batch_device(cmgpu_ctx *ctx, int n, const float *starts, cons
 	it.origins = (float *)take(T * v3);
 	it.rotIndex = (int *)take(T * 4);
 	it.boxmins = (float *)take(T * v3); it.boxmaxs = (float *)take(T * v3);
-	it.entNumber = (int *)take(T * 4);
+	it.entIndex = (int *)take(T * 4);
 	svGatherKernel<true><<<grid, 128, 0, s>>>(ctx->sv, q, it);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
@@ -1492,7 +1539,7 @@ int cmgpu_sv_trace_batch_device(cmgpu_ctx *ctx, int n, const float *starts, cons
 	                                  (cmgpu_trace_t *)ctx->bSvCand.p, nullptr, stream);
 	if (rc) return rc;
 	// 5. merge in list order
-	svMergeKernel<<<grid, 128, 0, s>>>(n, q.results, q.offsets, (const uint2 *)ctx->bSvCand.p, it.entNumber);
+	svMergeKernel<<<grid, 128, 0, s>>>(n, q.results, q.offsets, (const uint2 *)ctx->bSvCand.p, it.entIndex, ctx->sv.entInfo);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return CMGPU_OK;

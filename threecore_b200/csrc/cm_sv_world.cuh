@@ -17,6 +17,10 @@
 // child 1, so every query sees a subsequence of ONE global order (the order a query with an infinite box returns).
 // The host stores the entities in that order, node by node, and the nodes in depth-first order; a node is entered
 // if its parent was and the parent's plane test passes (sv_world.c:370-375), else its whole subtree is skipped.
+// An entity in a subtree the query does not enter fails the box test anyway (it was linked there because its box
+// lies beyond that plane), so the candidates are simply "the entities whose box touches, in global order" -- which
+// lets the common case skip the tree: two uniform grids hold, per cell, the ascending indices of the entities that
+// reach the cell, and a move merges the lists of the few cells its box covers.
 #pragma once
 
 #include "cm_kernels.cuh"
@@ -31,14 +35,22 @@ struct SvWorld {
 	                           // [2i+1] first entity, end entity, 0, 0
 	const float4 *entLo;       // absmin.xyz, ownerNum bits
 	const float4 *entHi;       // absmax.xyz, contents bits
-	const int4   *entInfo;     // number, clip handle (inline model or 1023), rotation index (-1: angles are zero), 0
+	const int4   *entInfo;     // number, clip handle (inline model or 1023), rotation index (-1: angles are zero),
+	                           // first cell of the entity's box: x | y << 8 at the fine level, the same << 16 at the coarse level
 	const float  *entOrigin;   // [e][3]
 	const float  *entMins;     // [e][3]  r.mins / r.maxs: the CM_TempBoxModel box
 	const float  *entMaxs;
 	const float  *entRot;      // [e][9]
 	const int    *ownerByNum;  // r.ownerNum of every gentity
 	int numNodes, numEnts, numGentities;
+	// two uniform x/y grids over the world (fine, coarse): per cell the entities whose box reaches it, ascending
+	const int    *cellStart[2];
+	const int    *cellEnts[2];
+	float gridLo[2];
+	float gridInv[2][2];
+	int gridCells[2];          // cells per axis
 };
+constexpr int kSvMaxCells = 16;
 
 struct SvMoves {
 	int n;
@@ -51,6 +63,7 @@ struct SvMoves {
 	int sharedMask;
 	uint2 *results;                      // world traces in, merged traces out
 	unsigned *offsets;                   // [n+1]: counts, then (after the scan) first candidate of every move
+	int4 *firstCands;                    // [n]: the first four candidates the counting pass found (saves the second walk)
 };
 
 struct SvItems {                         // the entity pass's batch, one item per candidate
@@ -59,18 +72,81 @@ struct SvItems {                         // the entity pass's batch, one item pe
 	float *origins;
 	int *rotIndex;
 	float *boxmins, *boxmaxs;
-	int *entNumber;                      // touch->s.number of the candidate
+	int *entIndex;                       // the candidate's place in SV_AreaEntities order (its index in the snapshot)
 };
 
-// the walk of SV_AreaEntities_r + the filters of SV_ClipMoveToEntities; f(e) is called per survivor, in list order
+// pass entity, its missiles, its owner's other missiles, unwanted contents (sv_world.c:496-516)
+struct SvFilter {
+	int passEnt, passOwner, mask;
+	bool on;
+};
+
+__device__ __forceinline__ SvFilter svMakeFilter(const SvWorld &w, int passEnt, int mask, bool on) {
+	SvFilter f{passEnt, -1, mask, on};
+	if (on && passEnt != kEntityNumNone) {                                     // :484-493
+		f.passOwner = (passEnt >= 0 && passEnt < w.numGentities) ? __ldg(&w.ownerByNum[passEnt]) : kEntityNumNone;
+		if (f.passOwner == kEntityNumNone) f.passOwner = -1;
+	}
+	return f;
+}
+
+__device__ __forceinline__ bool svTouches(const SvWorld &w, int e, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                          const SvFilter &f) {
+	const float4 lo = __ldg(&w.entLo[e]);
+	const float4 hi = __ldg(&w.entHi[e]);
+	if (lo.x > hix || lo.y > hiy || lo.z > hiz || hi.x < lox || hi.y < loy || hi.z < loz) return false;   // sv_world.c:349-356
+	if (f.on) {
+		const int owner = __float_as_int(lo.w);
+		if (f.passEnt != kEntityNumNone) {                                     // :500-510
+			if (__ldg(&w.entInfo[e]).x == f.passEnt) return false;
+			if (owner == f.passEnt) return false;
+			if (owner == f.passOwner) return false;
+		}
+		if (!(f.mask & __float_as_int(hi.w))) return false;                    // :514-516
+	}
+	return true;
+}
+
+// cell of a coordinate on one axis of a grid level: monotone in x, and the SAME float ops as the host uses for the
+// entities' cell ranges (svCellOf in cm_gpu.cu), so overlapping boxes always share a cell
+__host__ __device__ __forceinline__ int svCellOf(float x, float lo, float inv, int cells) {
+	const float t = (x - lo) * inv;
+	if (!(t > 0.0f)) return 0;
+	if (t >= (float)cells) return cells - 1;
+	return (int)t;
+}
+
+// The candidates of one move, each once, in no particular order: the entities listed in the cells that the move's
+// box covers, at the finer of the two levels where those are at most kSvMaxCells cells; a larger box walks the
+// sector tree.  Entity indices ARE the order SV_AreaEntities lists them in, so the merge kernel can restore it.
 template <typename F>
 __device__ __forceinline__ void svForEachCandidate(const SvWorld &w, float lox, float loy, float loz, float hix, float hiy, float hiz,
                                                    int passEnt, int mask, bool wantFilters, F f) {
-	int passOwner = -1;
-	if (wantFilters && passEnt != kEntityNumNone) {
-		passOwner = (passEnt >= 0 && passEnt < w.numGentities) ? __ldg(&w.ownerByNum[passEnt]) : kEntityNumNone;
-		if (passOwner == kEntityNumNone) passOwner = -1;
+	const SvFilter flt = svMakeFilter(w, passEnt, mask, wantFilters);
+	#pragma unroll 1
+	for (int level = 0; level < 2; level++) {
+		const int G = w.gridCells[level];
+		const int cx0 = svCellOf(lox, w.gridLo[0], w.gridInv[level][0], G), cx1 = svCellOf(hix, w.gridLo[0], w.gridInv[level][0], G);
+		const int cy0 = svCellOf(loy, w.gridLo[1], w.gridInv[level][1], G), cy1 = svCellOf(hiy, w.gridLo[1], w.gridInv[level][1], G);
+		const int nx = cx1 - cx0 + 1, nc = nx * (cy1 - cy0 + 1);
+		if (nc > kSvMaxCells) continue;
+		const int *cellStart = w.cellStart[level], *cellEnts = w.cellEnts[level];
+		for (int cy = cy0; cy <= cy1; cy++) {
+			for (int cx = cx0; cx <= cx1; cx++) {
+				const int cell = cy * G + cx;
+				const int p1 = __ldg(&cellStart[cell + 1]);
+				for (int p = __ldg(&cellStart[cell]); p < p1; p++) {
+					const int e = __ldg(&cellEnts[p]);
+					// an entity that reaches several of the covered cells is taken in the first of them
+					const int first = __ldg(&w.entInfo[e]).w >> (16 * level);
+					if (max(first & 0xff, cx0) != cx || max((first >> 8) & 0xff, cy0) != cy) continue;
+					if (svTouches(w, e, lox, loy, loz, hix, hiy, hiz, flt)) f(e);
+				}
+			}
+		}
+		return;
 	}
+	// the walk of SV_AreaEntities_r (sv_world.c:344-377) over the depth-first node array
 	int i = 0;
 	while (i < w.numNodes) {
 		const int4 a = __ldg(&w.nodes[2 * i]);
@@ -82,20 +158,7 @@ __device__ __forceinline__ void svForEachCandidate(const SvWorld &w, float lox, 
 		}
 		const int4 b = __ldg(&w.nodes[2 * i + 1]);
 		for (int e = b.x; e < b.y; e++) {
-			const float4 lo = __ldg(&w.entLo[e]);
-			const float4 hi = __ldg(&w.entHi[e]);
-			if (lo.x > hix || lo.y > hiy || lo.z > hiz || hi.x < lox || hi.y < loy || hi.z < loz) continue;   // sv_world.c:349-356
-			if (wantFilters) {
-				const int number = __ldg(&w.entInfo[e]).x;
-				const int owner = __float_as_int(lo.w);
-				if (passEnt != kEntityNumNone) {                       // sv_world.c:500-510
-					if (number == passEnt) continue;
-					if (owner == passEnt) continue;
-					if (owner == passOwner) continue;
-				}
-				if (!(mask & __float_as_int(hi.w))) continue;          // sv_world.c:514-516
-			}
-			f(e);
+			if (svTouches(w, e, lox, loy, loz, hix, hiy, hiz, flt)) f(e);
 		}
 		i++;
 	}
@@ -132,12 +195,18 @@ __global__ void __launch_bounds__(128) svGatherKernel(const SvWorld w, const SvM
 	const int mask = q.masks ? q.masks[m] : q.sharedMask;
 	if (!FILL) {
 		unsigned count = 0;
-		svForEachCandidate(w, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], passEnt, mask, true, [&](int) { count++; });
+		int4 c4 = make_int4(0, 0, 0, 0);
+		svForEachCandidate(w, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], passEnt, mask, true, [&](int e) {
+			if (count == 0) c4.x = e; else if (count == 1) c4.y = e; else if (count == 2) c4.z = e; else if (count == 3) c4.w = e;
+			count++;
+		});
 		q.offsets[m] = count;
+		if (count) q.firstCands[m] = c4;
 	} else {
 		size_t k = q.offsets[m];
-		if (k == q.offsets[m + 1]) return;
-		svForEachCandidate(w, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], passEnt, mask, true, [&](int e) {
+		const unsigned count = q.offsets[m + 1] - (unsigned)k;
+		if (count == 0) return;
+		auto emit = [&](int e) {
 			const size_t k3 = 3 * k, e3o = 3 * (size_t)e;
 			const int4 info = __ldg(&w.entInfo[e]);
 			#pragma unroll
@@ -155,14 +224,26 @@ __global__ void __launch_bounds__(128) svGatherKernel(const SvWorld w, const SvM
 			if (q.masks) it.masks[k] = mask;
 			it.models[k] = info.y;
 			it.rotIndex[k] = info.z;
-			it.entNumber[k] = info.x;
+			it.entIndex[k] = e;
 			k++;
-		});
+		};
+		if (count <= 4) {
+			const int4 c4 = q.firstCands[m];
+			emit(c4.x);
+			if (count > 1) emit(c4.y);
+			if (count > 2) emit(c4.z);
+			if (count > 3) emit(c4.w);
+		} else {
+			svForEachCandidate(w, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], passEnt, mask, true, emit);
+		}
 	}
 }
 
-// SV_ClipMoveToEntities' loop body after the clip (sv_world.c:490-549), over the candidates of one move
-__global__ void __launch_bounds__(128) svMergeKernel(int n, uint2 *results, const unsigned *offsets, const uint2 *cand, const int *entNumber) {
+// SV_ClipMoveToEntities' loop body after the clip (sv_world.c:490-549), over the candidates of one move IN LIST
+// ORDER: the gather emits them in cell order, so each round takes the candidate with the smallest entity index
+// that has not been taken yet (a move has a handful of candidates)
+__global__ void __launch_bounds__(128) svMergeKernel(int n, uint2 *results, const unsigned *offsets, const uint2 *cand, const int *entIndex,
+                                                     const int4 *entInfo) {
 	const int m = blockIdx.x * blockDim.x + threadIdx.x;
 	if (m >= n) return;
 	const unsigned k0 = offsets[m], k1 = offsets[m + 1];
@@ -172,13 +253,21 @@ __global__ void __launch_bounds__(128) svMergeKernel(int n, uint2 *results, cons
 	#pragma unroll
 	for (int j = 0; j < 7; j++) clip[j] = dst[j];
 	// words: 0 allsolid, 1 startsolid, 2 fraction, ..., 13 entityNum  ->  clip[0] = (allsolid, startsolid), clip[1].x = fraction, clip[6].y = entityNum
-	for (unsigned k = k0; k < k1; k++) {
+	int last = -1;
+	for (unsigned round = k0; round < k1; round++) {
 		if (clip[0].x) break;                                          // :491-493
+		unsigned k = k0;
+		int e = 0x7fffffff;
+		for (unsigned j = k0; j < k1; j++) {
+			const int ej = entIndex[j];
+			if (ej > last && ej < e) { e = ej; k = j; }
+		}
+		last = e;
 		const uint2 *src = cand + 7 * (size_t)k;
 		uint2 t[7];
 		#pragma unroll
 		for (int j = 0; j < 7; j++) t[j] = src[j];
-		const unsigned num = (unsigned)entNumber[k];
+		const unsigned num = (unsigned)__ldg(&entInfo[e]).x;           // touch->s.number
 		if (t[0].x) { clip[0].x = 1; t[6].y = num; }                   // :532-534
 		else if (t[0].y) { clip[0].y = 1; t[6].y = num; }              // :535-538
 		if (__uint_as_float(t[1].x) < __uint_as_float(clip[1].x)) {    // :540-549
