@@ -42,7 +42,7 @@ extern "C" {
 #endif
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 
-#define CMGPU_ABI_VERSION 1
+#define CMGPU_ABI_VERSION 2
 
 #define CMGPU_BOX_MODEL_HANDLE 1023   /* BOX_MODEL_HANDLE, cm_local.h:28 */
 #define CMGPU_MAX_SUBMODELS    1024   /* MAX_SUBMODELS,   cm_local.h:27 */
@@ -107,6 +107,12 @@ typedef struct cmgpu_flatmap_s {
 	int32_t boxFirstPlane;   /* = numPlanes-12 */
 	int32_t boxFirstSide;    /* = numBrushSides-6 */
 	int32_t boxLeafBrush;    /* leafbrushes[] slot holding boxBrush */
+	/* visibility and areas (cm_load.c:313-320,495-515) -- only the leaf / PVS queries below read them */
+	int32_t numClusters;     /* max leaf cluster + 1, or the vis lump's own count when vised */
+	int32_t numAreas;        /* max leaf area + 1 */
+	int32_t vised;           /* 0: no vis lump, every cluster sees every cluster (visibility may be NULL) */
+	int32_t clusterBytes;    /* bytes per row of visibility[] */
+	const uint8_t *visibility;                                /* [numClusters][clusterBytes] bit c of row r: r sees c */
 } cmgpu_flatmap;
 
 typedef struct cmgpu_ctx_s cmgpu_ctx;
@@ -239,6 +245,54 @@ int cmgpu_sv_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *poi
                          const int32_t *passEntityNums, int pass_stride, int32_t *contents, void *stream);
 /* candidates (entity clips) the last cmgpu_sv_* call generated */
 unsigned long long cmgpu_sv_last_candidates(const cmgpu_ctx *ctx);
+
+/* ---- leaf queries (cm_test.c:31-61, 131-181): the tree lookups behind entity linking and PVS culling --------
+ * cmgpu_point_leafnum_batch: CM_PointLeafnum per point.  cmgpu_box_leafnums_batch: CM_BoxLeafnums per box --
+ * lists[i*listsize ..] receives the leafs the box touches in the reference's order (children[0] first), counts[i]
+ * how many were stored (<= listsize), lastLeafs[i] the last touched leaf that has a cluster, counted even when
+ * the list is full (cm_test.c:78-81).  The _device variants take device pointers and only enqueue work.     */
+int cmgpu_point_leafnum_batch(cmgpu_ctx *ctx, int n, const float *points, int32_t *leafnums);
+int cmgpu_box_leafnums_batch(cmgpu_ctx *ctx, int n, const float *mins, const float *maxs, int listsize,
+                             int32_t *lists, int32_t *counts, int32_t *lastLeafs);
+int cmgpu_point_leafnum_batch_device(cmgpu_ctx *ctx, int n, const float *points, int32_t *leafnums, void *stream);
+int cmgpu_box_leafnums_batch_device(cmgpu_ctx *ctx, int n, const float *mins, const float *maxs, int listsize,
+                             int32_t *lists, int32_t *counts, int32_t *lastLeafs, void *stream);
+
+/* ---- entity linking, PVS part, and snapshot culling (server/sv_world.c:255-303, sv_snapshot.c:316-355) ----
+ * What SV_LinkEntity stores in the svEntity_t (server.h:42-45) for the box absmin..absmax, computed in ONE tree
+ * walk per entity (the 128-leaf list of sv_world.c:178-181 never leaves the thread). */
+#define CMGPU_MAX_AREAS          256     /* limit of this library (the q3map tools stop at 0x100 areas) */
+#define CMGPU_MAX_ENT_CLUSTERS   16      /* server.h:35 */
+#define CMGPU_MAX_ENT_LEAFS      128     /* MAX_TOTAL_ENT_LEAFS, sv_world.c:178 */
+typedef struct cmgpu_entity_clusters_s {
+	int32_t numLeafs;                    /* leafs CM_BoxLeafnums stored (<= 128); 0 = outside the world, not linked */
+	int32_t areanum, areanum2;
+	int32_t numClusters;
+	int32_t lastCluster;                 /* set when the clusters did not fit (sv_world.c:300-303) */
+	int32_t clusternums[CMGPU_MAX_ENT_CLUSTERS];   /* entries >= numClusters are 0 */
+} cmgpu_entity_clusters_t;               /* 84 bytes */
+int cmgpu_entity_clusters_batch(cmgpu_ctx *ctx, int n, const float *absmins, const float *absmaxs,
+                                cmgpu_entity_clusters_t *out);
+int cmgpu_entity_clusters_batch_device(cmgpu_ctx *ctx, int n, const float *absmins, const float *absmaxs,
+                                cmgpu_entity_clusters_t *out, void *stream);
+
+/* Area portals (cm_test.c:322-424).  The context keeps the reference counts and the flood numbers;
+ * cmgpu_upload resets them like CM_LoadMap does (all closed, cm_load.c:734). */
+int cmgpu_adjust_area_portal_state(cmgpu_ctx *ctx, int area1, int area2, int open);
+int cmgpu_areas_connected(cmgpu_ctx *ctx, int area1, int area2);          /* 1 / 0, < 0: error code */
+/* CM_WriteAreaBits (cm_test.c:441-470): ORs into buffer, returns the byte count (< 0: error code) */
+int cmgpu_write_area_bits(cmgpu_ctx *ctx, uint8_t *buffer, int area);
+/* cm_noAreas (cm_load.c:640): when set every pair of areas counts as connected */
+int cmgpu_set_no_areas(cmgpu_ctx *ctx, int noAreas);
+
+/* The PVS stage of SV_AddEntitiesVisibleFromPoint (sv_snapshot.c:316-355) for every (viewpoint, entity) pair:
+ * bit e%32 of visible[v * ((nEnts+31)/32) + e/32] is set when entity e passes the area and cluster tests seen
+ * from origins[v].  viewLeafs (may be NULL) receives CM_PointLeafnum(origins[v]).  ents are records made by
+ * cmgpu_entity_clusters_batch. */
+int cmgpu_visible_from_points_batch(cmgpu_ctx *ctx, int nViews, const float *origins, int nEnts,
+                                    const cmgpu_entity_clusters_t *ents, uint32_t *visible, int32_t *viewLeafs);
+int cmgpu_visible_from_points_batch_device(cmgpu_ctx *ctx, int nViews, const float *origins, int nEnts,
+                                    const cmgpu_entity_clusters_t *ents, uint32_t *visible, int32_t *viewLeafs, void *stream);
 
 /* ---- instrumentation (successor of c_traces/c_brush_traces, cm_load.c:60-61) */
 typedef struct cmgpu_counters_s {

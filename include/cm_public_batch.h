@@ -31,6 +31,7 @@ typedef float vec_t;
 typedef vec_t vec3_t[3];           /* q_shared.h:369 */
 typedef int clipHandle_t;          /* q_shared.h:228 */
 typedef int qboolean;
+typedef unsigned char byte;       /* q_shared.h */
 typedef cmgpu_trace_t trace_t;     /* q_shared.h:976-986, same 56 bytes */
 
 #define ENTITYNUM_NONE   4095      /* q_shared.h: MAX_GENTITIES-1 */
@@ -83,6 +84,36 @@ int CM_TransformedBoxTraceBatch(trace_t *results, int n, const float *starts, co
 int CM_PointContentsBatch(int *contents, int n, const float *points, const clipHandle_t *models,
                           const float *origins, const float *angles,
                           const float *boxmins, const float *boxmaxs);
+
+/* ---- leaf queries (cm_public.h:54-62), single and batched ------------------------------------
+ * What SV_LinkEntity asks per entity (sv_world.c:266-303) and the snapshot code per client. */
+int CM_PointLeafnum(const vec3_t p);
+int CM_BoxLeafnums(const vec3_t mins, const vec3_t maxs, int *list, int listsize, int *lastLeaf);
+int CM_LeafCluster(int leafnum);
+int CM_LeafArea(int leafnum);
+int CM_PointLeafnumBatch(int *leafnums, int n, const float *points);
+/* lists is [n][listsize]; counts[i] leafs were stored for box i, lastLeafs[i] as CM_BoxLeafnums' *lastLeaf */
+int CM_BoxLeafnumsBatch(int n, const float *mins, const float *maxs, int listsize, int *lists, int *counts, int *lastLeafs);
+
+/* ---- visibility and area portals (cm_public.h:56-69) -----------------------------------------
+ * Table lookups on the loaded map (no tree work): served from the host copy of the map.  The batched,
+ * device-side consumers of the same tables are SV_EntityClustersBatch / SV_VisibleFromPointsBatch below. */
+int   CM_NumClusters(void);
+byte *CM_ClusterPVS(int cluster);                        /* row of the visibility matrix; all ones when not vised */
+void  CM_AdjustAreaPortalState(int area1, int area2, qboolean open);
+qboolean CM_AreasConnected(int area1, int area2);
+int   CM_WriteAreaBits(byte *buffer, int area);
+
+/* ---- server: entity linking (PVS part) and snapshot culling ----------------------------------
+ * SV_EntityClustersBatch: what SV_LinkEntity (server/sv_world.c:255-303) stores in svEntity_t.{numClusters,
+ * clusternums, lastCluster, areanum, areanum2} for n boxes absmin..absmax, one device thread per entity.
+ * SV_VisibleFromPointsBatch: the PVS stage of SV_AddEntitiesVisibleFromPoint (server/sv_snapshot.c:316-355) for
+ * every (viewpoint, entity) pair; bit e%32 of visible[v*((nEnts+31)/32) + e/32].  SVF_BROADCAST, singleClient,
+ * draw distance and the anti-cheat traces stay with the caller (they need game state; the traces are SV_TraceBatch). */
+typedef cmgpu_entity_clusters_t sv_entity_clusters_t;
+int SV_EntityClustersBatch(int n, const float *absmins, const float *absmaxs, sv_entity_clusters_t *out);
+int SV_VisibleFromPointsBatch(int nViews, const float *origins, int nEnts, const sv_entity_clusters_t *ents,
+                              unsigned int *visible, int *viewLeafs);
 
 /* ---- server hook: SV_ClipMoveToEntities (server/sv_world.c:476-551) ----------
  * The caller keeps the broad phase and the pass/owner/contents filters

@@ -883,3 +883,140 @@ void cmo_point_contents_batch(const cmo_map_t *m, int n, const float *pts, const
 		}
 	}
 }
+
+/* ---------------------------------------------------------------------- */
+/* leaf queries, entity linking (PVS part), areas and visibility            */
+/* ---------------------------------------------------------------------- */
+
+/* CM_BoxLeafnums, cm_test.c:163-181 with CM_BoxLeafnums_r :131-156 and CM_StoreLeafs :73-88.
+ * leafClusterArea is [numLeafs][2] (cluster, area) or NULL (then no leaf has a cluster). */
+int cmo_box_leafnums(const cmo_map_t *m, const int *leafClusterArea, const float *mins, const float *maxs,
+                     int *list, int listsize, int *lastLeaf) {
+	int stack[STACK_MAX];
+	int sp = 0, count = 0, last = 0, num = 0;
+	for (;;) {
+		while (num >= 0) {
+			const int *nd = m->nodes + 3 * (size_t)num;
+			int s = box_plane_side(mins, maxs, m->planes + 4 * (size_t)nd[0], m->planeType[nd[0]], m->planeSignbits[nd[0]]);
+			if (s == 1) {
+				num = nd[1];
+			} else if (s == 2) {
+				num = nd[2];
+			} else {
+				if (sp < STACK_MAX) stack[sp++] = nd[2];   /* children[1] waits while children[0] is walked */
+				num = nd[1];
+			}
+		}
+		int leaf = -1 - num;
+		if (leafClusterArea && leafClusterArea[2 * (size_t)leaf] != -1) last = leaf;   /* even when the list is full */
+		if (count < listsize) list[count++] = leaf;
+		if (!sp) break;
+		num = stack[--sp];
+	}
+	if (lastLeaf) *lastLeaf = last;
+	return count;
+}
+
+void cmo_box_leafnums_batch(const cmo_map_t *m, const int *leafClusterArea, int n, const float *mins, const float *maxs,
+                            int listsize, int *lists, int *counts, int *lastLeafs) {
+	for (int i = 0; i < n; i++) {
+		counts[i] = cmo_box_leafnums(m, leafClusterArea, mins + 3 * (size_t)i, maxs + 3 * (size_t)i,
+		                             lists + (size_t)i * listsize, listsize, &lastLeafs[i]);
+	}
+}
+
+/* The PVS part of SV_LinkEntity, server/sv_world.c:255-303: the clusters and areas the box absmin..absmax touches.
+ * out: numLeafs, areanum, areanum2, numClusters, lastCluster, clusternums[16]  (CMO_ENT_CLUSTER_INTS ints) */
+void cmo_entity_clusters(const cmo_map_t *m, const int *leafClusterArea, const float *absmin, const float *absmax, int *out) {
+	int leafs[128];                                    /* MAX_TOTAL_ENT_LEAFS, sv_world.c:178 */
+	int lastLeaf = 0;
+	int numLeafs = cmo_box_leafnums(m, leafClusterArea, absmin, absmax, leafs, 128, &lastLeaf);
+	int areanum = -1, areanum2 = -1, numClusters = 0, lastCluster = 0, i;
+	int *clusters = out + 5;
+	for (i = 0; i < 16; i++) clusters[i] = 0;
+	for (i = 0; i < numLeafs; i++) {
+		int area = leafClusterArea ? leafClusterArea[2 * (size_t)leafs[i] + 1] : -1;
+		if (area != -1) {
+			if (areanum != -1 && areanum != area) areanum2 = area;   /* doors may straddle two areas */
+			else areanum = area;
+		}
+	}
+	for (i = 0; i < numLeafs; i++) {
+		int cluster = leafClusterArea ? leafClusterArea[2 * (size_t)leafs[i]] : -1;
+		if (cluster != -1) {
+			clusters[numClusters++] = cluster;
+			if (numClusters == 16) break;                /* MAX_ENT_CLUSTERS, server.h:35 */
+		}
+	}
+	if (i != numLeafs) lastCluster = leafClusterArea ? leafClusterArea[2 * (size_t)lastLeaf] : -1;
+	out[0] = numLeafs; out[1] = areanum; out[2] = areanum2; out[3] = numClusters; out[4] = lastCluster;
+}
+
+void cmo_entity_clusters_batch(const cmo_map_t *m, const int *leafClusterArea, int n, const float *absmins,
+                               const float *absmaxs, int *out) {
+	for (int i = 0; i < n; i++) {
+		cmo_entity_clusters(m, leafClusterArea, absmins + 3 * (size_t)i, absmaxs + 3 * (size_t)i,
+		                    out + (size_t)i * CMO_ENT_CLUSTER_INTS);
+	}
+}
+
+/* CM_FloodAreaConnections, cm_test.c:348-365 with CM_FloodArea_r :322-342: floodnum[area] from the reference
+ * counts areaPortals[numAreas][numAreas].  Depth-first in index order like the recursion. */
+void cmo_flood_areas(int numAreas, const int *areaPortals, int *floodnum) {
+	int floodvalid[256];
+	int stack[256], iter[256];
+	int next = 0;
+	if (numAreas > 256) numAreas = 256;                /* the product refuses maps with more areas */
+	for (int i = 0; i < numAreas; i++) { floodvalid[i] = 0; floodnum[i] = 0; }
+	for (int i = 0; i < numAreas; i++) {
+		if (floodvalid[i]) continue;
+		next++;
+		int sp = 0;
+		stack[0] = i; iter[0] = 0;
+		floodnum[i] = next; floodvalid[i] = 1;
+		while (sp >= 0) {
+			int a = stack[sp];
+			if (iter[sp] >= numAreas) { sp--; continue; }
+			int j = iter[sp]++;
+			if (areaPortals[(size_t)a * numAreas + j] > 0 && !floodvalid[j]) {
+				floodnum[j] = next; floodvalid[j] = 1;
+				sp++;
+				stack[sp] = j; iter[sp] = 0;
+			}
+		}
+	}
+}
+
+/* The PVS stage of SV_AddEntitiesVisibleFromPoint, server/sv_snapshot.c:327-355, for one (viewpoint, entity) pair:
+ * area connection (CM_AreasConnected, cm_test.c:404-424, cm_noAreas = 0), then the entity's clusters against the
+ * viewpoint cluster's row of the visibility matrix (CM_ClusterPVS, cm_test.c:306-312), then the overflow range.
+ * vis == NULL: not vised, every bit set.  ent = the CMO_ENT_CLUSTER_INTS ints of cmo_entity_clusters. */
+int cmo_entity_visible(int numAreas, const int *floodnum, int numClusters, int clusterBytes, const uint8_t *vis,
+                       int clientArea, int clientCluster, const int *ent) {
+	int areanum = ent[1], areanum2 = ent[2], n = ent[3], lastCluster = ent[4];
+	const int *clusters = ent + 5;
+	int connected = 0;
+	(void)numAreas;
+	if (clientArea >= 0 && areanum >= 0 && floodnum[clientArea] == floodnum[areanum]) connected = 1;
+	if (!connected && clientArea >= 0 && areanum2 >= 0 && floodnum[clientArea] == floodnum[areanum2]) connected = 1;
+	if (!connected) return 0;
+	if (!n) return 0;
+	const uint8_t *row = NULL;                          /* NULL: all ones */
+	if (vis) row = (clientCluster < 0 || clientCluster >= numClusters) ? vis : vis + (size_t)clientCluster * clusterBytes;
+	int i, l = 0;
+	for (i = 0; i < n; i++) {
+		l = clusters[i];
+		if (!row || (row[l >> 3] & (1 << (l & 7)))) break;
+	}
+	if (i == n) {
+		if (lastCluster) {
+			for (; l <= lastCluster; l++) {
+				if (!row || (row[l >> 3] & (1 << (l & 7)))) break;
+			}
+			if (l == lastCluster) return 0;             /* sv_snapshot.c:352, kept as written */
+		} else {
+			return 0;
+		}
+	}
+	return 1;
+}

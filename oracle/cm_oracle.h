@@ -99,6 +99,19 @@ int cmo_transformed_point_contents(const cmo_map_t *m, const float *p, int model
                                    const float *boxmins, const float *boxmaxs);
 int cmo_point_leafnum(const cmo_map_t *m, const float *p);
 
+/* leaf lists, entity linking (PVS part), areas, visibility -- see cm_oracle.c */
+#define CMO_ENT_CLUSTER_INTS 21     /* numLeafs, areanum, areanum2, numClusters, lastCluster, clusternums[16] */
+int  cmo_box_leafnums(const cmo_map_t *m, const int *leafClusterArea, const float *mins, const float *maxs,
+                      int *list, int listsize, int *lastLeaf);
+void cmo_box_leafnums_batch(const cmo_map_t *m, const int *leafClusterArea, int n, const float *mins, const float *maxs,
+                            int listsize, int *lists, int *counts, int *lastLeafs);
+void cmo_entity_clusters(const cmo_map_t *m, const int *leafClusterArea, const float *absmin, const float *absmax, int *out);
+void cmo_entity_clusters_batch(const cmo_map_t *m, const int *leafClusterArea, int n, const float *absmins,
+                               const float *absmaxs, int *out);
+void cmo_flood_areas(int numAreas, const int *areaPortals, int *floodnum);
+int  cmo_entity_visible(int numAreas, const int *floodnum, int numClusters, int clusterBytes, const uint8_t *vis,
+                        int clientArea, int clientCluster, const int *ent);
+
 /* batch wrappers (hull_stride / mask_stride: 0 shared, 1 per item) */
 void cmo_box_trace_batch(const cmo_map_t *m, int n, const float *starts, const float *ends,
                          const float *mins, const float *maxs, int hull_stride,

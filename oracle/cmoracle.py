@@ -226,6 +226,57 @@ class OracleCM:
         return np.array([self.lib.cmo_point_leafnum(C.byref(self._m), _p(pts[i])) for i in range(pts.shape[0])],
                         dtype=np.int32)
 
+    # ---- leaf lists, entity clusters, areas, visibility (restated in cm_oracle.c) ----
+    def _lca(self):
+        a = self.flat.get("leaf_cluster_area")
+        if a is None:
+            return None
+        if not hasattr(self, "_lca_arr"):
+            self._lca_arr = np.ascontiguousarray(a, np.int32)
+        return self._lca_arr
+
+    def box_leafnums(self, mins, maxs, listsize=64):
+        mins, maxs = _f(mins).reshape(-1, 3), _f(maxs).reshape(-1, 3)
+        n = mins.shape[0]
+        lists = np.full((n, listsize), -1, np.int32)
+        counts, last = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lca = self._lca()
+        self.lib.cmo_box_leafnums_batch(C.byref(self._m), _p(lca), n, _p(mins), _p(maxs), int(listsize),
+                                        _p(lists), _p(counts), _p(last))
+        return lists, counts, last
+
+    def entity_clusters(self, absmins, absmaxs):
+        """-> int32 [n][21]: numLeafs, areanum, areanum2, numClusters, lastCluster, clusternums[16]"""
+        absmins, absmaxs = _f(absmins).reshape(-1, 3), _f(absmaxs).reshape(-1, 3)
+        out = np.zeros((absmins.shape[0], 21), np.int32)
+        lca = self._lca()
+        self.lib.cmo_entity_clusters_batch(C.byref(self._m), _p(lca), absmins.shape[0], _p(absmins), _p(absmaxs), _p(out))
+        return out
+
+    def flood_areas(self, area_portals):
+        ap = np.ascontiguousarray(area_portals, np.int32)
+        n = ap.shape[0]
+        out = np.zeros(max(n, 1), np.int32)
+        self.lib.cmo_flood_areas(n, _p(ap), _p(out))
+        return out[:n]
+
+    def visible_from_points(self, origins, ents, floodnum, num_clusters, cluster_bytes, vis):
+        """ents: int32 [n][21] from entity_clusters; vis: uint8 matrix or None -> bool [nViews][nEnts]"""
+        origins = _f(origins).reshape(-1, 3)
+        ents = np.ascontiguousarray(ents, np.int32)
+        floodnum = np.ascontiguousarray(floodnum, np.int32)
+        lca = self._lca()
+        leafs = self.point_leafnum(origins)
+        visb = np.ascontiguousarray(vis, np.uint8) if vis is not None and np.size(vis) else None
+        out = np.zeros((origins.shape[0], ents.shape[0]), bool)
+        self.lib.cmo_entity_visible.restype = C.c_int
+        for v in range(origins.shape[0]):
+            cl, ar = int(lca[leafs[v], 0]), int(lca[leafs[v], 1])
+            for e in range(ents.shape[0]):
+                out[v, e] = bool(self.lib.cmo_entity_visible(floodnum.shape[0], _p(floodnum), int(num_clusters), int(cluster_bytes),
+                                                             _p(visb), ar, cl, _p(np.ascontiguousarray(ents[e]))))
+        return out
+
     def angle_vectors(self, angles):
         a = _f(angles)
         f = np.zeros(3, np.float32); r = np.zeros(3, np.float32); u = np.zeros(3, np.float32)

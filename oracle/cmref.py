@@ -250,6 +250,48 @@ class RefCM:
         self.lib.svref_time_traces.restype = C.c_double
         return self.lib.svref_time_traces(starts.shape[0], _p(starts), _p(ends), _p(mins), _p(maxs), _p(pe), int(mask))
 
+    # ---- clusters, areas, visibility (cm_load.c:838-860, cm_test.c:306-470) and what uses them ---------------
+    def leaf_cluster_area(self, leafs):
+        leafs = _i(leafs)
+        c, a = np.zeros(leafs.shape[0], np.int32), np.zeros(leafs.shape[0], np.int32)
+        self._check(self.lib.cmref_leaf_cluster_area(leafs.shape[0], _p(leafs), _p(c), _p(a)), "CM_LeafCluster")
+        return c, a
+
+    def num_clusters(self):
+        return int(self.lib.cmref_num_clusters())
+
+    def cluster_pvs(self, cluster, nbytes):
+        out = np.zeros(nbytes, np.uint8)
+        self._check(self.lib.cmref_cluster_pvs(int(cluster), int(nbytes), _p(out)), "CM_ClusterPVS")
+        return out
+
+    def adjust_area_portal_state(self, a1, a2, open_):
+        self._check(self.lib.cmref_adjust_area_portal(int(a1), int(a2), int(bool(open_))), "CM_AdjustAreaPortalState")
+
+    def areas_connected(self, a1, a2):
+        a1, a2 = _i(a1), _i(a2)
+        out = np.zeros(a1.shape[0], np.int32)
+        self._check(self.lib.cmref_areas_connected(a1.shape[0], _p(a1), _p(a2), _p(out)), "CM_AreasConnected")
+        return out
+
+    def write_area_bits(self, area, nbytes=32):
+        buf = np.zeros(nbytes, np.uint8)
+        n = C.c_int(0)
+        self._check(self.lib.cmref_write_area_bits(int(area), _p(buf), C.byref(n)), "CM_WriteAreaBits")
+        return bytes(buf[:n.value])
+
+    def sv_entity_clusters(self, num):
+        """-> (areanum, areanum2, numClusters, lastCluster, clusternums[16]) of the linked entity's svEntity_t"""
+        out = np.zeros(20, np.int32)
+        linked = self.lib.svref_entity_clusters(int(num), _p(out))
+        return out, linked
+
+    def sv_visible_from_points(self, origins, nums):
+        origins, nums = _f(origins).reshape(-1, 3), _i(nums)
+        vis = np.zeros((origins.shape[0], nums.shape[0]), np.uint8)
+        self.lib.svref_visible_from_points(origins.shape[0], _p(origins), nums.shape[0], _p(nums), _p(vis))
+        return vis.astype(bool)
+
     # ---- dumps of the loaded clipMap_t -----------------------------------
     COUNT_NAMES = ["planes", "nodes", "leafs", "leafbrushes", "leafsurfaces", "brushes", "brushsides",
                    "models", "surfaces", "shaders", "patches", "patchplanes", "facets", "borders"]

@@ -289,6 +289,49 @@ API int cmref_box_leafnums_batch(int n, const float *mins, const float *maxs, in
 	return 0;
 }
 
+/* ---- clusters, areas, visibility (cm_load.c:838-860, cm_test.c:306-470) ---- */
+API int cmref_leaf_cluster_area(int n, const int *leafs, int *cluster, int *area) {
+	GUARD_BEGIN();
+	for (int i = 0; i < n; i++) {
+		cluster[i] = CM_LeafCluster(leafs[i]);
+		area[i] = CM_LeafArea(leafs[i]);
+	}
+	GUARD_END();
+	return 0;
+}
+
+API int cmref_num_clusters(void) { return CM_NumClusters(); }
+
+/* the row CM_ClusterPVS(cluster) points at, (numClusters+7)/8 bytes of it (the engine's users index it by cluster) */
+API int cmref_cluster_pvs(int cluster, int nbytes, unsigned char *out) {
+	GUARD_BEGIN();
+	memcpy(out, CM_ClusterPVS(cluster), (size_t)nbytes);
+	GUARD_END();
+	return 0;
+}
+
+API int cmref_adjust_area_portal(int area1, int area2, int open) {
+	GUARD_BEGIN();
+	CM_AdjustAreaPortalState(area1, area2, open ? qtrue : qfalse);
+	GUARD_END();
+	return 0;
+}
+
+API int cmref_areas_connected(int n, const int *a1, const int *a2, int *out) {
+	GUARD_BEGIN();
+	for (int i = 0; i < n; i++) out[i] = CM_AreasConnected(a1[i], a2[i]);
+	GUARD_END();
+	return 0;
+}
+
+/* CM_WriteAreaBits into a zeroed buffer; returns the byte count in *bytes */
+API int cmref_write_area_bits(int area, unsigned char *buffer, int *bytes) {
+	GUARD_BEGIN();
+	*bytes = CM_WriteAreaBits(buffer, area);
+	GUARD_END();
+	return 0;
+}
+
 API void cmref_angle_vectors(const float *angles, float *fwd, float *right, float *up) {
 	AngleVectors(angles, fwd, right, up);
 }

@@ -97,6 +97,58 @@ API int svref_entity_bounds(int num, float *absmin, float *absmax) {
 	return e->r.linked;
 }
 
+/* what the PVS part of SV_LinkEntity (sv_world.c:255-303) left in the svEntity_t:
+ * out[0..3] = areanum, areanum2, numClusters, lastCluster; out[4..19] = clusternums[16] */
+API int svref_entity_clusters(int num, int *out) {
+	const svEntity_t *se;
+	int i;
+	if (num < 0 || num >= MAX_GENTITIES || !s_gents) return -1;
+	se = &sv.svEntities[num];
+	out[0] = se->areanum; out[1] = se->areanum2; out[2] = se->numClusters; out[3] = se->lastCluster;
+	for (i = 0; i < MAX_ENT_CLUSTERS; i++) out[4 + i] = se->clusternums[i];
+	return s_gents[num].r.linked;
+}
+
+/* The PVS stage of SV_AddEntitiesVisibleFromPoint (sv_snapshot.c:316-355; that function is static and walks
+ * svs.currFrame, so its culling lines are REPEATED here over the svEntity_t the reference's SV_LinkEntity filled,
+ * calling the reference's own CM_PointLeafnum / CM_LeafArea / CM_LeafCluster / CM_ClusterPVS / CM_AreasConnected).
+ * visible[v * nEnts + e] = 1 when entity nums[e] passes for viewpoint v. */
+API void svref_visible_from_points(int nViews, const float *origins, int nEnts, const int *nums, unsigned char *visible) {
+	int v, e, i, l;
+	for (v = 0; v < nViews; v++) {
+		int leafnum = CM_PointLeafnum(origins + 3 * (size_t)v);
+		int clientarea = CM_LeafArea(leafnum);
+		int clientcluster = CM_LeafCluster(leafnum);
+		byte *clientpvs = CM_ClusterPVS(clientcluster);
+		for (e = 0; e < nEnts; e++) {
+			const svEntity_t *svEnt = &sv.svEntities[nums[e]];
+			byte *bitvector = clientpvs;
+			unsigned char *out = &visible[(size_t)v * nEnts + e];
+			*out = 0;
+			if (!CM_AreasConnected(clientarea, svEnt->areanum)) {
+				if (!CM_AreasConnected(clientarea, svEnt->areanum2)) continue;
+			}
+			if (!svEnt->numClusters) continue;
+			l = 0;
+			for (i = 0; i < svEnt->numClusters; i++) {
+				l = svEnt->clusternums[i];
+				if (bitvector[l >> 3] & (1 << (l & 7))) break;
+			}
+			if (i == svEnt->numClusters) {
+				if (svEnt->lastCluster) {
+					for (; l <= svEnt->lastCluster; l++) {
+						if (bitvector[l >> 3] & (1 << (l & 7))) break;
+					}
+					if (l == svEnt->lastCluster) continue;
+				} else {
+					continue;
+				}
+			}
+			*out = 1;
+		}
+	}
+}
+
 API int svref_area_entities(const float *mins, const float *maxs, int *list, int maxcount) {
 	return SV_AreaEntities(mins, maxs, list, maxcount);
 }

@@ -712,6 +712,46 @@ def tiny_map(seed=1) -> SynthMap:
     return mb.finish(seed=seed, leaf_max=2, nonaxial_node_prob=0.5)
 
 
+def with_visibility(m: SynthMap, seed=0x715, n_areas=5, solid_frac=0.3, density=0.25, vised=True) -> SynthMap:
+    """The same map with clusters, areas and a visibility lump (finish() gives every leaf its own cluster,
+    area 0 and no lump).  A fraction of the leafs becomes "solid" (cluster -1, area -1, as q3map marks leafs inside
+    brushes), the others get consecutive clusters and one of n_areas areas; the matrix is random with the given
+    density plus the diagonal.  Nothing here is spatially meaningful -- it feeds CM_BoxLeafnums' lastLeaf rule,
+    SV_LinkEntity's cluster/area bookkeeping and the PVS test (cm_test.c:73-88, sv_world.c:255-303,
+    sv_snapshot.c:316-355), none of which looks at geometry."""
+    rng = np.random.default_rng(seed)
+    data = bytearray(m.data)
+    lofs, llen = struct.unpack_from("<ii", data, 8 + 8 * LUMP_LEAFS)
+    lf = np.frombuffer(bytes(data[lofs:lofs + llen]), dtype="<i4").reshape(-1, 12).copy()
+    n = lf.shape[0]
+    solid = rng.random(n) < solid_frac
+    solid[0] = False
+    open_ = np.flatnonzero(~solid)
+    lf[:, 0] = -1
+    lf[:, 1] = -1
+    lf[open_, 0] = np.arange(open_.size)
+    # areas in runs of leaf numbers, so that boxes usually touch one or two and sometimes three or more
+    run = max(1, open_.size // max(4 * n_areas, 1))
+    lf[open_, 1] = (np.arange(open_.size) // run) % n_areas
+    data[lofs:lofs + llen] = lf.astype("<i4").tobytes()
+    if vised:
+        nc = int(open_.size)
+        cb = ((nc + 63) & ~63) >> 3
+        bits = rng.random((nc, cb * 8)) < density
+        bits[np.arange(nc), np.arange(nc)] = True
+        bits[:, nc:] = False
+        vis = np.packbits(bits, axis=1, bitorder="little")
+        lump = struct.pack("<ii", nc, cb) + vis.tobytes()
+        pad = (-len(data)) % 4
+        data += b"\x00" * pad
+        struct.pack_into("<ii", data, 8 + 8 * LUMP_VISIBILITY, len(data), len(lump))
+        data += lump
+    out = SynthMap(**{k: getattr(m, k) for k in m.__dataclass_fields__})
+    out.data = bytes(data)
+    out.stats = dict(m.stats, clusters=int(open_.size), areas=n_areas, vised=bool(vised))
+    return out
+
+
 # ----------------------------------------------------------------------------
 # trace streams
 # ----------------------------------------------------------------------------

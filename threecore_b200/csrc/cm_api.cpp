@@ -210,6 +210,96 @@ int CM_TransformedPointContents(const vec3_t p, clipHandle_t model, const vec3_t
 	return c;
 }
 
+// ---- leaf queries (cm_public.h:54-62) --------------------------------------------------------
+int CM_PointLeafnumBatch(int *leafnums, int n, const float *points) {
+	if (!g_map) {                                  // map not loaded: leaf 0 (cm_test.c:57-59)
+		for (int i = 0; i < n; i++) leafnums[i] = 0;
+		return CMGPU_OK;
+	}
+	int rc = cmgpu_point_leafnum_batch(g_ctx, n, points, leafnums);
+	dropOn(rc, "CM_PointLeafnum");
+	return rc;
+}
+
+int CM_BoxLeafnumsBatch(int n, const float *mins, const float *maxs, int listsize, int *lists, int *counts, int *lastLeafs) {
+	if (!g_map) { raise("CM_BoxLeafnums: no map loaded"); return CMGPU_ERR_NO_MAP; }
+	int rc = cmgpu_box_leafnums_batch(g_ctx, n, mins, maxs, listsize, lists, counts, lastLeafs);
+	dropOn(rc, "CM_BoxLeafnums");
+	return rc;
+}
+
+int CM_PointLeafnum(const vec3_t p) {
+	int leaf = 0;
+	CM_PointLeafnumBatch(&leaf, 1, p);
+	return leaf;
+}
+
+int CM_BoxLeafnums(const vec3_t mins, const vec3_t maxs, int *list, int listsize, int *lastLeaf) {
+	int count = 0, last = 0;
+	CM_BoxLeafnumsBatch(1, mins, maxs, listsize, list, &count, &last);
+	if (lastLeaf) *lastLeaf = last;
+	return count;
+}
+
+int CM_LeafCluster(int leafnum) {                  // cm_load.c: ERR_DROP on a bad number
+	if (!g_map || leafnum < 0 || leafnum >= g_map->numLeafs) { raise("CM_LeafCluster: bad number"); return -1; }
+	return g_map->leafClusterArea ? g_map->leafClusterArea[2 * (size_t)leafnum] : -1;
+}
+
+int CM_LeafArea(int leafnum) {
+	if (!g_map || leafnum < 0 || leafnum >= g_map->numLeafs) { raise("CM_LeafArea: bad number"); return -1; }
+	return g_map->leafClusterArea ? g_map->leafClusterArea[2 * (size_t)leafnum + 1] : -1;
+}
+
+// ---- visibility and area portals (cm_test.c:306-470): table lookups on the host copy of the map ----
+int CM_NumClusters(void) { return g_map ? g_map->numClusters : 0; }
+
+byte *CM_ClusterPVS(int cluster) {
+	static std::vector<byte> allOnes;
+	if (!g_map) return nullptr;
+	if (!g_map->vised) {                                   // cm_load.c:503-505: a single row of 0xff
+		if (allOnes.size() < (size_t)g_map->clusterBytes + 1) allOnes.assign((size_t)g_map->clusterBytes + 1, 255);
+		return allOnes.data();
+	}
+	byte *vis = const_cast<byte *>(g_map->visibility);
+	if (cluster < 0 || cluster >= g_map->numClusters) return vis;
+	return vis + (size_t)cluster * (size_t)g_map->clusterBytes;
+}
+
+void CM_AdjustAreaPortalState(int area1, int area2, qboolean open) {
+	if (!g_ctx || !g_map) return;
+	if (cmgpu_adjust_area_portal_state(g_ctx, area1, area2, open ? 1 : 0)) raise("%s", cmgpu_last_error(g_ctx));
+}
+
+qboolean CM_AreasConnected(int area1, int area2) {
+	if (!g_ctx || !g_map) return 0;
+	int r = cmgpu_areas_connected(g_ctx, area1, area2);
+	if (r < 0) { raise("%s", cmgpu_last_error(g_ctx)); return 0; }
+	return r ? 1 : 0;
+}
+
+int CM_WriteAreaBits(byte *buffer, int area) {
+	if (!g_ctx || !g_map) return 0;
+	int r = cmgpu_write_area_bits(g_ctx, buffer, area);
+	if (r < 0) { raise("%s", cmgpu_last_error(g_ctx)); return 0; }
+	return r;
+}
+
+int SV_EntityClustersBatch(int n, const float *absmins, const float *absmaxs, sv_entity_clusters_t *out) {
+	if (!g_map) { raise("SV_LinkEntity: no map loaded"); return CMGPU_ERR_NO_MAP; }
+	int rc = cmgpu_entity_clusters_batch(g_ctx, n, absmins, absmaxs, out);
+	dropOn(rc, "SV_LinkEntity");
+	return rc;
+}
+
+int SV_VisibleFromPointsBatch(int nViews, const float *origins, int nEnts, const sv_entity_clusters_t *ents,
+                              unsigned int *visible, int *viewLeafs) {
+	if (!g_map) { raise("SV_AddEntitiesVisibleFromPoint: no map loaded"); return CMGPU_ERR_NO_MAP; }
+	int rc = cmgpu_visible_from_points_batch(g_ctx, nViews, origins, nEnts, ents, visible, viewLeafs);
+	dropOn(rc, "SV_AddEntitiesVisibleFromPoint");
+	return rc;
+}
+
 // ---- SV_ClipMoveToEntities, batched ---------------------------------------------------------
 // merge rules of sv_world.c:497-549 applied to already computed per-entity traces
 static void mergeEntityTraces(trace_t *clip, int numTouch, const cm_touch_t *touch, const trace_t *traces) {

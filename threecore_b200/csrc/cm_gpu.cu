@@ -10,6 +10,7 @@
 #include "cm_trace_pool.cuh"
 #include "cm_trace_simple.cuh"
 #include "cm_sv_world.cuh"
+#include "cm_leaf_queries.cuh"
 #include "../../include/cm_gpu.h"
 
 #include <math.h>
@@ -114,6 +115,13 @@ struct cmgpu_ctx_s {
 	SvWorld sv{};
 	bool hasSvWorld = false;
 	DevBuf bSvWorld, bSvOffsets, bSvTiles, bSvItems, bSvCand, bSvPass;
+	const int *leafCluster = nullptr;    // [numLeafs][2] cluster, area (cm_leaf_queries.cuh); part of the map slab
+	DevBuf bLeafLists, bLeafCounts;
+	// visibility and areas (cm_leaf_queries.cuh).  The matrix can be tens of MB: its own allocation, not the map slab
+	DevBuf bVis, bFlood, bEntRecs, bVisible;
+	bool vised = false;
+	int numClusters = 0, clusterBytes = 0, numAreas = 0, noAreas = 0;
+	std::vector<int> areaPortals, floodnum;          // host copies: [numAreas][numAreas] reference counts, [numAreas]
 	unsigned *hSvTotal = nullptr;        // pinned
 	unsigned long long svCandidates = 0;
 };
@@ -233,6 +241,40 @@ void freeMap(cmgpu_ctx *ctx) {
 	memset(&ctx->map, 0, sizeof(ctx->map));
 	memset(&ctx->fast, 0, sizeof(ctx->fast));
 	ctx->numPatches = 0;
+	ctx->leafCluster = nullptr;
+	ctx->vised = false;
+	ctx->numClusters = ctx->clusterBytes = ctx->numAreas = 0;
+	ctx->areaPortals.clear();
+	ctx->floodnum.clear();
+}
+
+// CM_FloodAreaConnections (cm_test.c:322-365): flood numbers from the portal reference counts, then to the device.
+// Areas are numbered by the lowest area of their connected set, in index order, like the reference's recursion.
+int floodAreas(cmgpu_ctx *ctx) {
+	const int n = ctx->numAreas;
+	ctx->floodnum.assign((size_t)n, 0);
+	std::vector<int> work;
+	int next = 0;
+	for (int i = 0; i < n; i++) {
+		if (ctx->floodnum[i]) continue;
+		ctx->floodnum[i] = ++next;
+		work.assign(1, i);
+		while (!work.empty()) {
+			const int a = work.back();
+			work.pop_back();
+			for (int j = 0; j < n; j++) {
+				if (ctx->areaPortals[(size_t)a * n + j] > 0 && !ctx->floodnum[j]) {
+					ctx->floodnum[j] = next;
+					work.push_back(j);
+				}
+			}
+		}
+	}
+	if (n == 0) return CMGPU_OK;
+	int rc = reserve(ctx, ctx->bFlood, (size_t)n * sizeof(int));
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpy(ctx->bFlood.p, ctx->floodnum.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+	return CMGPU_OK;
 }
 
 inline int signbitsOf(const float *n) {
@@ -255,6 +297,16 @@ int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 	NEED(f->boxFirstPlane >= 0 && f->boxFirstPlane + 12 <= f->numPlanes, "bad boxFirstPlane");
 	NEED(f->leafbrushes[f->boxLeafBrush] == f->boxBrush, "boxLeafBrush does not name boxBrush");
 	NEED(f->brushes[3 * (size_t)f->boxBrush + 2] == 6, "box brush must have 6 sides");
+	NEED(f->numClusters >= 0 && f->numAreas >= 0 && f->numAreas <= CMGPU_MAX_AREAS, "bad cluster / area counts");
+	NEED(!f->vised || (f->visibility && f->clusterBytes > 0), "vised map without a visibility matrix");
+	if (f->leafClusterArea) {
+		for (int i = 0; i < f->numLeafs; i++) {
+			const int c = f->leafClusterArea[2 * (size_t)i], a = f->leafClusterArea[2 * (size_t)i + 1];
+			NEED(c >= -1 && (c == -1 || c < f->numClusters || !f->vised), "leaf %i: bad cluster %i", i, c);
+			NEED(a >= -1 && (a == -1 || a < f->numAreas), "leaf %i: bad area %i", i, a);
+			NEED(!f->vised || c < 8 * f->clusterBytes, "leaf %i: cluster %i beyond the visibility rows", i, c);
+		}
+	}
 
 	for (int i = 0; i < f->numNodes; i++) {
 		const int32_t *nd = f->nodes + 3 * (size_t)i;
@@ -457,6 +509,11 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 	UP(sidePlanes, sidePlanes); UP(sideMeta, sideMeta); UP(modelLeafs, modelLeafs); UP(surf2patch, surf2patch);
 	UP(patchInfo, patchInfo); UP(patchBox, patchBox); UP(patchPlanes, patchPlanes); UP(facets, facets);
 	UP(borders, borders); UP(facetRuns, facetRuns); UP(facetPlanes, facetPlanes);
+	ctx->leafCluster = nullptr;
+	if (f->leafClusterArea) {
+		std::vector<int> lca(f->leafClusterArea, f->leafClusterArea + 2 * (size_t)f->numLeafs);
+		if ((rc = uploadArray(ctx, lca, &ctx->leafCluster)) != CMGPU_OK) return rc;
+	}
 	{	// ---- layout of the hot kernel: leafs as sentinel-terminated streams of widened brush boxes ----
 		std::vector<int> streamStart((size_t)f->numLeafs);
 		std::vector<float4> stream;
@@ -553,6 +610,18 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 	m.noCurves = ctx->noCurves;
 	m.playerCurveClip = ctx->playerCurveClip;
 	ctx->numModels = f->numModels;
+	// visibility matrix and areas; every portal starts closed (cm_load.c:320,734)
+	ctx->vised = f->vised != 0;
+	ctx->numClusters = f->numClusters;
+	ctx->clusterBytes = f->clusterBytes;
+	ctx->numAreas = f->leafClusterArea ? f->numAreas : 0;
+	if (ctx->vised) {
+		const size_t bytes = (size_t)f->numClusters * (size_t)f->clusterBytes;
+		if ((rc = reserve(ctx, ctx->bVis, bytes + 1))) return rc;
+		CUDA_TRY(ctx, cudaMemcpy(ctx->bVis.p, f->visibility, bytes, cudaMemcpyHostToDevice));
+	}
+	ctx->areaPortals.assign((size_t)ctx->numAreas * ctx->numAreas, 0);
+	if ((rc = floodAreas(ctx))) return rc;
 	ctx->hasMap = true;
 	return CMGPU_OK;
 }
@@ -802,7 +871,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
 	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit,
 	                  &ctx->bKeys, &ctx->bRecs, &ctx->bSvWorld, &ctx->bSvOffsets, &ctx->bSvTiles, &ctx->bSvItems, &ctx->bSvCand,
-	                  &ctx->bSvPass}) releaseBuf(*b);
+	                  &ctx->bSvPass, &ctx->bLeafLists, &ctx->bLeafCounts, &ctx->bVis, &ctx->bFlood, &ctx->bEntRecs, &ctx->bVisible}) releaseBuf(*b);
 	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
 	for (auto &b : ctx->bHist) releaseBuf(b);
 	for (auto &b : ctx->bStackArena) releaseBuf(b);
@@ -1654,6 +1723,223 @@ int cmgpu_sv_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
 	                                          (int32_t *)ctx->bHit.p, s);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(contents, ctx->bHit.p, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return CMGPU_OK;
+}
+
+// ---- leaf queries (cm_leaf_queries.cuh) ------------------------------------------------------
+int cmgpu_point_leafnum_batch_device(cmgpu_ctx *ctx, int n, const float *points, int32_t *leafnums, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !leafnums))) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_point_leafnum_batch_device: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	pointLeafnumKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, n, points, leafnums);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_box_leafnums_batch_device(cmgpu_ctx *ctx, int n, const float *mins, const float *maxs, int listsize,
+                                    int32_t *lists, int32_t *counts, int32_t *lastLeafs, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || listsize < 0 || (n > 0 && (!mins || !maxs || !counts || !lastLeafs || (listsize > 0 && !lists))))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_box_leafnums_batch_device: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	LeafListBatch q{n, mins, maxs, listsize, lists, counts, lastLeafs, ctx->leafCluster, ctx->dStatus};
+	boxLeafnumsKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_point_leafnum_batch(cmgpu_ctx *ctx, int n, const float *points, int32_t *leafnums) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !leafnums))) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_point_leafnum_batch: bad argument");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, N * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, points, N * 12, cudaMemcpyHostToDevice, s));
+	if ((rc = cmgpu_point_leafnum_batch_device(ctx, n, (const float *)ctx->bStarts.p, (int32_t *)ctx->bHit.p, s))) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(leafnums, ctx->bHit.p, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return CMGPU_OK;
+}
+
+int cmgpu_box_leafnums_batch(cmgpu_ctx *ctx, int n, const float *mins, const float *maxs, int listsize,
+                             int32_t *lists, int32_t *counts, int32_t *lastLeafs) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || listsize < 0 || (n > 0 && (!mins || !maxs || !counts || !lastLeafs || (listsize > 0 && !lists))))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_box_leafnums_batch: bad argument");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n, L = N * (size_t)listsize * 4;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, N * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bEnds, N * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bLeafLists, L + 16))) return rc;
+	if ((rc = reserve(ctx, ctx->bLeafCounts, 2 * N * 4))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, mins, N * 12, cudaMemcpyHostToDevice, s));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bEnds.p, maxs, N * 12, cudaMemcpyHostToDevice, s));
+	if (L) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bLeafLists.p, lists, L, cudaMemcpyHostToDevice, s));    // entries past a count stay the caller's
+	int32_t *dCounts = (int32_t *)ctx->bLeafCounts.p, *dLast = dCounts + N;
+	if ((rc = cmgpu_box_leafnums_batch_device(ctx, n, (const float *)ctx->bStarts.p, (const float *)ctx->bEnds.p, listsize,
+	                                          (int32_t *)ctx->bLeafLists.p, dCounts, dLast, s))) return rc;
+	if (L) CUDA_TRY(ctx, cudaMemcpyAsync(lists, ctx->bLeafLists.p, L, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaMemcpyAsync(counts, dCounts, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaMemcpyAsync(lastLeafs, dLast, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return cmgpu_check_status(ctx, s);
+}
+
+// ---- entity linking (PVS part), areas, snapshot culling (cm_leaf_queries.cuh) --------------------------------
+int cmgpu_entity_clusters_batch_device(cmgpu_ctx *ctx, int n, const float *absmins, const float *absmaxs,
+                                       cmgpu_entity_clusters_t *out, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!absmins || !absmaxs || !out))) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_entity_clusters_batch_device: bad argument");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	static_assert(sizeof(EntClusters) == sizeof(cmgpu_entity_clusters_t), "record layout");
+	EntClusterBatch q{n, absmins, absmaxs, reinterpret_cast<EntClusters *>(out), ctx->leafCluster, ctx->dStatus};
+	entityClustersKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_entity_clusters_batch(cmgpu_ctx *ctx, int n, const float *absmins, const float *absmaxs,
+                                cmgpu_entity_clusters_t *out) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!absmins || !absmaxs || !out))) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_entity_clusters_batch: bad argument");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, N * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bEnds, N * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bEntRecs, N * sizeof(cmgpu_entity_clusters_t)))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, absmins, N * 12, cudaMemcpyHostToDevice, s));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bEnds.p, absmaxs, N * 12, cudaMemcpyHostToDevice, s));
+	if ((rc = cmgpu_entity_clusters_batch_device(ctx, n, (const float *)ctx->bStarts.p, (const float *)ctx->bEnds.p,
+	                                             (cmgpu_entity_clusters_t *)ctx->bEntRecs.p, s))) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->bEntRecs.p, N * sizeof(cmgpu_entity_clusters_t), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return cmgpu_check_status(ctx, s);
+}
+
+int cmgpu_adjust_area_portal_state(cmgpu_ctx *ctx, int area1, int area2, int open) {      // cm_test.c:373-396
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (area1 < 0 || area2 < 0) return CMGPU_OK;
+	const int n = ctx->numAreas;
+	if (area1 >= n || area2 >= n) return fail(ctx, CMGPU_ERR_INVALID, "CM_ChangeAreaPortalState: bad area number");
+	int &a = ctx->areaPortals[(size_t)area1 * n + area2], &b = ctx->areaPortals[(size_t)area2 * n + area1];
+	if (open) {
+		a++;
+		if (&a != &b) b++; else a++;                     // area1 == area2: the reference increments the same cell twice
+	} else {
+		a--;
+		if (&a != &b) b--; else a--;
+		if (b < 0) return fail(ctx, CMGPU_ERR_INVALID, "CM_AdjustAreaPortalState: negative reference count");
+	}
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	return floodAreas(ctx);
+}
+
+int cmgpu_areas_connected(cmgpu_ctx *ctx, int area1, int area2) {                         // cm_test.c:404-424
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (ctx->noAreas) return 1;
+	if (area1 < 0 || area2 < 0) return 0;
+	if (area1 >= ctx->numAreas || area2 >= ctx->numAreas) return fail(ctx, CMGPU_ERR_INVALID, "area >= cm.numAreas");
+	return ctx->floodnum[area1] == ctx->floodnum[area2] ? 1 : 0;
+}
+
+int cmgpu_write_area_bits(cmgpu_ctx *ctx, uint8_t *buffer, int area) {                   // cm_test.c:441-470
+	if (!ctx || !buffer) return CMGPU_ERR_INVALID;
+	const int n = ctx->numAreas, bytes = (n + 7) >> 3;
+	if (ctx->noAreas || area == -1) {
+		memset(buffer, 255, (size_t)bytes);
+	} else {
+		if (area < 0 || area >= n) return fail(ctx, CMGPU_ERR_INVALID, "CM_WriteAreaBits: bad area number");
+		const int fl = ctx->floodnum[area];
+		for (int i = 0; i < n; i++) {
+			if (ctx->floodnum[i] == fl) buffer[i >> 3] |= (uint8_t)(1 << (i & 7));
+		}
+	}
+	return bytes;
+}
+
+int cmgpu_set_no_areas(cmgpu_ctx *ctx, int noAreas) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	ctx->noAreas = noAreas ? 1 : 0;
+	return CMGPU_OK;
+}
+
+int cmgpu_visible_from_points_batch_device(cmgpu_ctx *ctx, int nViews, const float *origins, int nEnts,
+                                           const cmgpu_entity_clusters_t *ents, uint32_t *visible, int32_t *viewLeafs, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (nViews < 0 || nEnts < 0 || (nViews > 0 && !origins) || (nViews > 0 && nEnts > 0 && (!ents || !visible)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_visible_from_points_batch_device: bad argument");
+	if (nViews > 65535) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_visible_from_points_batch_device: more than 65535 viewpoints in one call");
+	if (!ctx->hasMap) return fail(ctx, CMGPU_ERR_NO_MAP, "no map uploaded");
+	if (nViews == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = (cudaStream_t)stream;
+	int rc;
+	if (!viewLeafs) {
+		if ((rc = reserve(ctx, ctx->bLeafCounts, (size_t)nViews * 4))) return rc;
+		viewLeafs = (int32_t *)ctx->bLeafCounts.p;
+	}
+	if ((rc = cmgpu_point_leafnum_batch_device(ctx, nViews, origins, viewLeafs, stream))) return rc;
+	if (nEnts == 0) return CMGPU_OK;
+	VisBatch q{};
+	q.nViews = nViews; q.nEnts = nEnts;
+	q.viewLeafs = viewLeafs;
+	q.ents = reinterpret_cast<const EntClusters *>(ents);
+	q.visible = visible;
+	q.leafCluster = ctx->leafCluster;
+	q.floodnum = ctx->noAreas ? nullptr : (const int *)ctx->bFlood.p;
+	q.numAreas = ctx->noAreas ? 0 : ctx->numAreas;
+	if (!ctx->noAreas && ctx->numAreas == 0) { q.floodnum = (const int *)ctx->dStatus; q.numAreas = 0; }   // no areas: nothing is connected
+	q.vis = ctx->vised ? (const unsigned char *)ctx->bVis.p : nullptr;
+	q.numClusters = ctx->numClusters; q.clusterBytes = ctx->clusterBytes;
+	dim3 grid((unsigned)((nEnts + 127) / 128), (unsigned)nViews);
+	visibleFromPointsKernel<<<grid, 128, 0, s>>>(q);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_visible_from_points_batch(cmgpu_ctx *ctx, int nViews, const float *origins, int nEnts,
+                                    const cmgpu_entity_clusters_t *ents, uint32_t *visible, int32_t *viewLeafs) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (nViews < 0 || nEnts < 0 || (nViews > 0 && !origins) || (nViews > 0 && nEnts > 0 && (!ents || !visible)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_visible_from_points_batch: bad argument");
+	if (nViews == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t V = (size_t)nViews, E = (size_t)nEnts, words = (E + 31) / 32;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, V * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bHit, V * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bEntRecs, E * sizeof(cmgpu_entity_clusters_t) + 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bVisible, V * words * 4 + 4))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, origins, V * 12, cudaMemcpyHostToDevice, s));
+	if (E) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bEntRecs.p, ents, E * sizeof(cmgpu_entity_clusters_t), cudaMemcpyHostToDevice, s));
+	if ((rc = cmgpu_visible_from_points_batch_device(ctx, nViews, (const float *)ctx->bStarts.p, nEnts,
+	                                                 (const cmgpu_entity_clusters_t *)ctx->bEntRecs.p, (uint32_t *)ctx->bVisible.p,
+	                                                 (int32_t *)ctx->bHit.p, s))) return rc;
+	if (E) CUDA_TRY(ctx, cudaMemcpyAsync(visible, ctx->bVisible.p, V * words * 4, cudaMemcpyDeviceToHost, s));
+	if (viewLeafs) CUDA_TRY(ctx, cudaMemcpyAsync(viewLeafs, ctx->bHit.p, V * 4, cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(ctx, cudaStreamSynchronize(s));
 	return CMGPU_OK;
 }

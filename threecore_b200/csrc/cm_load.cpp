@@ -56,6 +56,7 @@ struct OwnedMap {
 	std::vector<int32_t> nodes, leafs, leafClusterArea, leafbrushes, leafsurfaces, brushes, brushsides, modelLeafs,
 	                     surf2patch, patches, patchPlaneSignbits, facets, borders;
 	std::vector<float> brushBounds, modelBounds, patchBounds, patchPlanes;
+	std::vector<uint8_t> visibility;
 };
 
 struct Fail {
@@ -176,6 +177,28 @@ extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap
 		m->leafs[4 * (size_t)i + 3] = dleafs[i].numLeafSurfaces;
 		m->leafClusterArea[2 * (size_t)i] = dleafs[i].cluster;
 		m->leafClusterArea[2 * (size_t)i + 1] = dleafs[i].area;
+		if (dleafs[i].cluster >= m->c.numClusters) m->c.numClusters = dleafs[i].cluster + 1;   // cm_load.c:313-316
+		if (dleafs[i].area >= m->c.numAreas) m->c.numAreas = dleafs[i].area + 1;
+	}
+	if (m->c.numAreas > CMGPU_MAX_AREAS) return fail("CMod_LoadLeafs: more than %i areas", CMGPU_MAX_AREAS);
+
+	// visibility, CMod_LoadVisibility cm_load.c:495-515.  Without a lump every cluster sees every cluster
+	// (a single row of 0xff, :503-505), which the device expresses as vised = 0.
+	{
+		const Lump &vl = h.lumps[LUMP_VISIBILITY];
+		if (vl.len) {
+			if (vl.len < 8) return fail("CMod_LoadVisibility: truncated lump");
+			int32_t hdr[2];
+			memcpy(hdr, base + vl.ofs, 8);
+			if (hdr[0] < 0 || hdr[1] < 0 || (int64_t)hdr[0] * hdr[1] > (int64_t)vl.len - 8)
+				return fail("CMod_LoadVisibility: %i clusters of %i bytes do not fit the lump", hdr[0], hdr[1]);
+			m->c.vised = 1;
+			m->c.numClusters = hdr[0];
+			m->c.clusterBytes = hdr[1];
+			m->visibility.assign(base + vl.ofs + 8, base + vl.ofs + vl.len);
+		} else {
+			m->c.clusterBytes = (m->c.numClusters + 31) & ~31;
+		}
 	}
 
 	// leafbrushes (+1 box entry, then the submodel lists), cm_load.c:373-395 and CMod_CheckLeafBrushes :428-440
@@ -277,6 +300,7 @@ extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap
 	c.patchPlaneSignbits = m->patchPlaneSignbits.data();
 	c.numFacets = (int32_t)(m->facets.size() / 3); c.facets = m->facets.data();
 	c.numBorders = (int32_t)(m->borders.size() / 2); c.borders = m->borders.data();
+	c.visibility = m->visibility.empty() ? nullptr : m->visibility.data();
 	c.boxBrush = nBrushes; c.boxFirstPlane = nPlanes; c.boxFirstSide = nSides; c.boxLeafBrush = nLeafBrushes;
 
 	guard.p = nullptr;

@@ -51,6 +51,8 @@ class _FlatMap(C.Structure):
         ("numBorders", C.c_int32), ("borders", C.c_void_p),
         ("leafClusterArea", C.c_void_p),
         ("boxBrush", C.c_int32), ("boxFirstPlane", C.c_int32), ("boxFirstSide", C.c_int32), ("boxLeafBrush", C.c_int32),
+        ("numClusters", C.c_int32), ("numAreas", C.c_int32), ("vised", C.c_int32), ("clusterBytes", C.c_int32),
+        ("visibility", C.c_void_p),
     ]
 
 
@@ -93,6 +95,10 @@ SV_ENTITY_DTYPE = np.dtype([("number", "<i4"), ("ownerNum", "<i4"), ("contents",
                             ("mins", "<f4", (3,)), ("maxs", "<f4", (3,)), ("absmin", "<f4", (3,)), ("absmax", "<f4", (3,)),
                             ("origin", "<f4", (3,)), ("angles", "<f4", (3,))])
 assert SV_ENTITY_DTYPE.itemsize == 92
+# cmgpu_entity_clusters_t: what the PVS part of SV_LinkEntity stores (server.h:42-45)
+ENT_CLUSTERS_DTYPE = np.dtype([("numLeafs", "<i4"), ("areanum", "<i4"), ("areanum2", "<i4"), ("numClusters", "<i4"),
+                               ("lastCluster", "<i4"), ("clusternums", "<i4", (16,))])
+assert ENT_CLUSTERS_DTYPE.itemsize == 84
 
 
 def load_library() -> C.CDLL:
@@ -146,7 +152,19 @@ def load_library() -> C.CDLL:
     lib.cmgpu_sv_last_candidates.argtypes = [vp]
     lib.cmgpu_sv_last_candidates.restype = C.c_ulonglong
     lib.cmgpu_rotation_matrices.restype = None
-    if lib.cmgpu_abi_version() != 1:
+    lib.cmgpu_point_leafnum_batch.argtypes = [vp, C.c_int, vp, vp]
+    lib.cmgpu_box_leafnums_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
+    lib.cmgpu_point_leafnum_batch_device.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.cmgpu_box_leafnums_batch_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.cmgpu_entity_clusters_batch.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.cmgpu_entity_clusters_batch_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    lib.cmgpu_adjust_area_portal_state.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.cmgpu_areas_connected.argtypes = [vp, C.c_int, C.c_int]
+    lib.cmgpu_write_area_bits.argtypes = [vp, vp, C.c_int]
+    lib.cmgpu_set_no_areas.argtypes = [vp, C.c_int]
+    lib.cmgpu_visible_from_points_batch.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    lib.cmgpu_visible_from_points_batch_device.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
+    if lib.cmgpu_abi_version() != 2:
         raise ImportError("libcmgpu.so ABI version mismatch")
     _lib = lib
     return lib
@@ -192,6 +210,20 @@ class FlatMap:
             setattr(s, ptr, a.ctypes.data)
         for key, fld in _SCALARS:
             setattr(s, fld, int(d[key]))
+        # clusters, areas, visibility matrix (optional; derived like cm_load.c:313-316,503-505 when absent)
+        lca = d.get("leaf_cluster_area")
+        s.numClusters = int(d.get("num_clusters", (int(np.max(lca[:, 0])) + 1) if lca is not None and len(lca) else 0))
+        s.numAreas = int(d.get("num_areas", (int(np.max(lca[:, 1])) + 1) if lca is not None and len(lca) else 0))
+        vis = d.get("visibility")
+        if vis is not None and np.size(vis):
+            v = np.ascontiguousarray(vis, dtype=np.uint8)
+            self._keep.append(v)
+            s.vised = 1
+            s.clusterBytes = int(d["cluster_bytes"])
+            s.visibility = v.ctypes.data
+        else:
+            s.vised = 0
+            s.clusterBytes = (s.numClusters + 31) & ~31
         self._struct = s
         return self
 
@@ -217,6 +249,12 @@ class FlatMap:
             d[key] = np.frombuffer(buf, dtype=dtype).reshape(shape).copy()
         for key, fld in _SCALARS:
             d[key] = int(getattr(s, fld))
+        d["num_clusters"], d["num_areas"], d["cluster_bytes"] = int(s.numClusters), int(s.numAreas), int(s.clusterBytes)
+        if s.vised and s.visibility:
+            nbytes = int(s.numClusters) * int(s.clusterBytes)
+            d["visibility"] = np.frombuffer((C.c_char * nbytes).from_address(s.visibility), dtype=np.uint8).copy()
+        else:
+            d["visibility"] = np.zeros(0, np.uint8)
         return d
 
     def __del__(self):
@@ -511,6 +549,61 @@ class Engine:
         return out
 
     @property
+    # ---- leaf queries, entity clusters, visibility (cm_test.c, sv_world.c:255-303, sv_snapshot.c:316-355) ----
+    def point_leafnum(self, pts):
+        pts = _f(pts).reshape(-1, 3)
+        out = np.zeros(pts.shape[0], np.int32)
+        self._check(self.lib.cmgpu_point_leafnum_batch(self.h, pts.shape[0], _p(pts), _p(out)))
+        return out
+
+    def box_leafnums(self, mins, maxs, listsize=64):
+        mins, maxs = _f(mins).reshape(-1, 3), _f(maxs).reshape(-1, 3)
+        n = mins.shape[0]
+        lists = np.full((n, max(listsize, 0)), -1, np.int32)
+        counts = np.zeros(n, np.int32)
+        last = np.zeros(n, np.int32)
+        self._check(self.lib.cmgpu_box_leafnums_batch(self.h, n, _p(mins), _p(maxs), listsize, _p(lists) if lists.size else None,
+                                                      _p(counts), _p(last)))
+        return lists, counts, last
+
+    def entity_clusters(self, absmins, absmaxs) -> np.ndarray:
+        absmins, absmaxs = _f(absmins).reshape(-1, 3), _f(absmaxs).reshape(-1, 3)
+        out = np.zeros(absmins.shape[0], ENT_CLUSTERS_DTYPE)
+        self._check(self.lib.cmgpu_entity_clusters_batch(self.h, absmins.shape[0], _p(absmins), _p(absmaxs), _p(out)))
+        return out
+
+    def adjust_area_portal_state(self, area1, area2, open_):
+        self._check(self.lib.cmgpu_adjust_area_portal_state(self.h, int(area1), int(area2), int(bool(open_))))
+
+    def areas_connected(self, area1, area2) -> bool:
+        r = self.lib.cmgpu_areas_connected(self.h, int(area1), int(area2))
+        if r < 0:
+            self._check(r)
+        return bool(r)
+
+    def write_area_bits(self, area, nbytes=32) -> bytes:
+        buf = np.zeros(nbytes, np.uint8)
+        r = self.lib.cmgpu_write_area_bits(self.h, _p(buf), int(area))
+        if r < 0:
+            self._check(r)
+        return bytes(buf[:r])
+
+    def set_no_areas(self, on):
+        self._check(self.lib.cmgpu_set_no_areas(self.h, int(bool(on))))
+
+    def visible_from_points(self, origins, ents: np.ndarray):
+        """-> (bool [nViews][nEnts], view leafs) : the PVS stage of SV_AddEntitiesVisibleFromPoint per pair"""
+        origins = _f(origins).reshape(-1, 3)
+        ents = np.ascontiguousarray(ents, ENT_CLUSTERS_DTYPE)
+        nv, ne = origins.shape[0], ents.shape[0]
+        words = (ne + 31) // 32
+        bits = np.zeros((nv, max(words, 1)), np.uint32)
+        leafs = np.zeros(nv, np.int32)
+        self._check(self.lib.cmgpu_visible_from_points_batch(self.h, nv, _p(origins), ne, _p(ents) if ne else None,
+                                                             _p(bits), _p(leafs)))
+        vis = np.unpackbits(bits.view(np.uint8).reshape(nv, -1), axis=1, bitorder="little")[:, :ne].astype(bool)
+        return vis, leafs
+
     def sv_last_candidates(self) -> int:
         return int(self.lib.cmgpu_sv_last_candidates(self.h))
 
