@@ -548,7 +548,6 @@ class Engine:
         self._check(self.lib.cmgpu_sv_point_contents_batch(self.h, pts.shape[0], _p(pts), _p(pe), ps, _p(out)))
         return out
 
-    @property
     # ---- leaf queries, entity clusters, visibility (cm_test.c, sv_world.c:255-303, sv_snapshot.c:316-355) ----
     def point_leafnum(self, pts):
         pts = _f(pts).reshape(-1, 3)
@@ -604,6 +603,7 @@ class Engine:
         vis = np.unpackbits(bits.view(np.uint8).reshape(nv, -1), axis=1, bitorder="little")[:, :ne].astype(bool)
         return vis, leafs
 
+    @property
     def sv_last_candidates(self) -> int:
         return int(self.lib.cmgpu_sv_last_candidates(self.h))
 
