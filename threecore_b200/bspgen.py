@@ -737,10 +737,13 @@ def with_visibility(m: SynthMap, seed=0x715, n_areas=5, solid_frac=0.3, density=
     if vised:
         nc = int(open_.size)
         cb = ((nc + 63) & ~63) >> 3
-        bits = rng.random((nc, cb * 8)) < density
-        bits[np.arange(nc), np.arange(nc)] = True
-        bits[:, nc:] = False
-        vis = np.packbits(bits, axis=1, bitorder="little")
+        vis = np.zeros((nc, cb), np.uint8)
+        for r0 in range(0, nc, 512):                  # in slabs of rows: the matrix of a 20 k-brush arena is ~50 MB
+            r1 = min(nc, r0 + 512)
+            bits = rng.random((r1 - r0, cb * 8), dtype=np.float32) < density
+            bits[np.arange(r1 - r0), np.arange(r0, r1)] = True
+            bits[:, nc:] = False
+            vis[r0:r1] = np.packbits(bits, axis=1, bitorder="little")
         lump = struct.pack("<ii", nc, cb) + vis.tobytes()
         pad = (-len(data)) % 4
         data += b"\x00" * pad

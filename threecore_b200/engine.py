@@ -603,6 +603,31 @@ class Engine:
         vis = np.unpackbits(bits.view(np.uint8).reshape(nv, -1), axis=1, bitorder="little")[:, :ne].astype(bool)
         return vis, leafs
 
+    # resident variants: CUDA tensors in and out, work only enqueued on the tensors' current stream
+    def _stream(self, t, stream):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream if stream is None else stream)
+
+    def point_leafnum_device(self, points, out, stream=None):
+        self._check(self.lib.cmgpu_point_leafnum_batch_device(self.h, points.shape[0], points.data_ptr(), out.data_ptr(),
+                                                              self._stream(points, stream)))
+
+    def box_leafnums_device(self, mins, maxs, listsize, lists, counts, last_leafs, stream=None):
+        self._check(self.lib.cmgpu_box_leafnums_batch_device(self.h, mins.shape[0], mins.data_ptr(), maxs.data_ptr(), int(listsize),
+                                                             lists.data_ptr(), counts.data_ptr(), last_leafs.data_ptr(),
+                                                             self._stream(mins, stream)))
+
+    def entity_clusters_device(self, absmins, absmaxs, out, stream=None):
+        """out: uint8/int32 CUDA tensor of n * 84 bytes (cmgpu_entity_clusters_t records)"""
+        self._check(self.lib.cmgpu_entity_clusters_batch_device(self.h, absmins.shape[0], absmins.data_ptr(), absmaxs.data_ptr(),
+                                                                out.data_ptr(), self._stream(absmins, stream)))
+
+    def visible_from_points_device(self, origins, n_ents, ents, visible, view_leafs=None, stream=None):
+        """visible: int32 CUDA tensor [nViews][(n_ents+31)//32]"""
+        self._check(self.lib.cmgpu_visible_from_points_batch_device(
+            self.h, origins.shape[0], origins.data_ptr(), int(n_ents), ents.data_ptr(), visible.data_ptr(),
+            None if view_leafs is None else view_leafs.data_ptr(), self._stream(origins, stream)))
+
     @property
     def sv_last_candidates(self) -> int:
         return int(self.lib.cmgpu_sv_last_candidates(self.h))
