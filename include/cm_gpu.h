@@ -141,7 +141,9 @@ int  cmgpu_num_inline_models(const cmgpu_ctx *ctx);
  * start cell), "bin_min_items", "bin_cell" (world units; takes effect at the next cmgpu_upload),
  * "bin_long_len", "bin_dir", "gang", "gang_fetch", "light_reps", "fast" (0: always the general kernel), "pool" (0: the
  * one-item-per-lane variant of the hot kernel), "pool_reps", "slab" (0: no float pre-test before the exact brush
- * clip), "pipe_chunks" (pieces a host batch is cut into).  Unknown names are CMGPU_ERR_INVALID. */
+ * clip), "two_phase" (0: binned hot launches store 56-byte records by item number from the walk itself instead of
+ * 16-byte results by slot plus an expansion pass), "pipe_chunks" (pieces a host batch is cut into).  Unknown names
+ * are CMGPU_ERR_INVALID. */
 int  cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value);
 
 /* ---- batched queries, HOST pointers (copies in, kernel, copies out) -------

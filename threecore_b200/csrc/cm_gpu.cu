@@ -94,7 +94,8 @@ struct cmgpu_ctx_s {
 	bool binDir = false;
 	int binMinItems = 98304;             // smaller batches are traced in input order (the five binning launches cost ~50 us)
 	float binCell = 256.0f, binLongLen = 512.0f;
-	DevBuf bKeys, bRecs, bHist[kBinSlots];
+	DevBuf bKeys, bRecs, bCompact, bHist[kBinSlots];
+	bool twoPhase = true;                // binned hot launches: 16-byte results by slot + expandRecordsKernel
 	DevBuf bPoolHdr[kBinSlots + 1];
 	DevBuf bStackArena[kBinSlots + 1];   // traversal stacks of the hot kernel: one per pipeline stream + one for device-pointer calls
 	// Device-pointer calls share one workspace (binning buffers, stack arena).  extDone fires when the last such
@@ -669,6 +670,8 @@ FastHull makeFastHull(const float *mins, const float *maxs, int mask, bool slabO
 // every chunk its own range); histSlot: which histogram table to use (one per pipeline stream).
 int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1) {
 	if (q.n <= 0) return CMGPU_OK;
+	const unsigned *slotOf = nullptr;
+	q.compact = nullptr;
 	const int arenaSlot = histSlot < 0 ? kBinSlots : histSlot;
 	const bool external = histSlot < 0;              // device-pointer call on the caller's stream
 	if (external && ctx->extBusy && ctx->extStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->extDone, 0));
@@ -681,6 +684,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 			wsOffset = 0;
 			if ((rc = reserve(ctx, ctx->bKeys, (size_t)q.n * 4))) return rc;
 			if ((rc = reserve(ctx, ctx->bRecs, (size_t)q.n * 32))) return rc;
+			if ((rc = reserve(ctx, ctx->bCompact, (size_t)q.n * 16))) return rc;
 		}
 		const int numTiles = (ctx->grid.numBins + kScanTile - 1) / kScanTile;
 		if ((rc = reserve(ctx, ctx->bHist[histSlot], ((size_t)ctx->grid.numBins + (size_t)numTiles) * 4))) return rc;
@@ -697,6 +701,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		binScatterKernel<<<g256, 256, 0, s>>>(q.n, q.starts, q.ends, keys, hist, recs);
 		ctx->launches += 5;
 		q.recs = recs;
+		slotOf = keys;
 	}
 	// persistent kernel: as many CTAs as fit on the GPU (fewer for tiny batches), each warp pulls
 	// kChunk items at a time from a cursor that must be zero at launch
@@ -710,6 +715,9 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
 	// the pool variant pays off once every warp has several rounds of items to work through
 	const bool pool = fast && ctx->usePool && q.n >= ctx->poolMinItems;
+	// out must be 16-byte aligned for the expand pass's stores (any cudaMalloc'ed or record-aligned pointer is)
+	if (fast && slotOf && ctx->twoPhase && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
+		q.compact = (uint4 *)ctx->bCompact.p + wsOffset;
 	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
 	                   : fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
 	// Items per cursor grab: kChunk for big batches; for small ones a share that spreads the batch over all
@@ -769,7 +777,13 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
-	if (tEnd) CUDA_TRY(ctx, cudaEventRecord(tEnd, s));
+	if (q.compact) {
+		expandRecordsKernel<<<(q.n + kExpandBlock - 1) / kExpandBlock, kExpandBlock, 0, s>>>(ctx->fast, q.n, slotOf, q.compact, q.starts,
+		                                                                                   q.ends, q.out, q.hitIds);
+		ctx->launches++;
+		CUDA_TRY(ctx, cudaGetLastError());
+	}
+	if (tEnd) CUDA_TRY(ctx, cudaEventRecord(tEnd, s));     // the bracket covers both phases: walk + record expansion
 	if (external) {
 		CUDA_TRY(ctx, cudaEventRecord(ctx->extDone, s));
 		ctx->extStream = s;
@@ -870,7 +884,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	freeMap(ctx);
 	for (DevBuf *b : {&ctx->bStarts, &ctx->bEnds, &ctx->bMins, &ctx->bMaxs, &ctx->bModels, &ctx->bMasks, &ctx->bOrigins,
 	                  &ctx->bRot, &ctx->bRotIdx, &ctx->bBoxMins, &ctx->bBoxMaxs, &ctx->bOut, &ctx->bHit,
-	                  &ctx->bKeys, &ctx->bRecs, &ctx->bSvWorld, &ctx->bSvOffsets, &ctx->bSvTiles, &ctx->bSvItems, &ctx->bSvCand,
+	                  &ctx->bKeys, &ctx->bRecs, &ctx->bCompact, &ctx->bSvWorld, &ctx->bSvOffsets, &ctx->bSvTiles, &ctx->bSvItems, &ctx->bSvCand,
 	                  &ctx->bSvPass, &ctx->bLeafLists, &ctx->bLeafCounts, &ctx->bVis, &ctx->bFlood, &ctx->bEntRecs, &ctx->bVisible}) releaseBuf(*b);
 	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
 	for (auto &b : ctx->bHist) releaseBuf(b);
@@ -936,6 +950,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "pipe_ramp") ctx->pipeRamp = value != 0;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
+	else if (k == "two_phase") ctx->twoPhase = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
 	else if (k == "gang_fetch") ctx->gangFetch = (int)value;
 	else if (k == "facet_steps") ctx->facetSteps = value < 1 ? 1 : (int)value;
@@ -1178,8 +1193,8 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	if (hit_ids && (rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
 	if (ctx->binning && N >= (size_t)ctx->binMinItems) {
 		if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
-		if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
 		if ((rc = reserve(ctx, ctx->bRecs, N * 32))) return rc;
+		if ((rc = reserve(ctx, ctx->bCompact, N * 16))) return rc;
 	}
 
 	if (ctx->extBusy) {                              // an earlier device-pointer call may still use the shared workspace
@@ -1200,7 +1215,7 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 		if (first < kMinChunkItems) first = kMinChunkItems;
 		size_t at = 0, step = first < piece && ctx->pipeRamp ? first : piece;
 		while (at < N) {
-			at = at + step < N ? at + step : N;
+			at = at + step < N ? ((at + step) & ~(size_t)1) : N;   // even: a piece's first record stays 16-byte aligned
 			bounds.push_back(at);
 			if (step < piece) step = step * 2 < piece ? step * 2 : piece;
 		}

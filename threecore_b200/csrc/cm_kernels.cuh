@@ -99,6 +99,8 @@ struct TraceBatch {
 	struct FastSeg *stackArena;          // hot kernel: kMaxDepth entries per resident thread
 	void *poolHdr;                       // pool variant: one 16-byte header per item slot
 	const float4 *recs;                  // binned batch: [2*slot] start.xyz + item bits, [2*slot+1] end.xyz + 0; null = input order
+	uint4 *compact;                      // binned hot kernels: results leave as 16 bytes per SLOT (fraction, flags, clip side,
+	                                     // hit brush); expandRecordsKernel writes the 56-byte records in item order.  null: direct
 };
 
 // ---- spatial binning of a batch (counting sort by start cell) -------------------------------
@@ -1224,12 +1226,14 @@ __global__ void __launch_bounds__(256) binScanKernel(unsigned *hist, int numBins
 }
 
 // pass 3: every item takes the next slot of its bin and leaves its ray there
-__global__ void __launch_bounds__(256) binScatterKernel(int n, const float *starts, const float *ends, const unsigned *keys,
+// (keys[i] becomes the item's slot: what expandRecordsKernel needs to find the item's result again)
+__global__ void __launch_bounds__(256) binScatterKernel(int n, const float *starts, const float *ends, unsigned *keys,
                                                         unsigned *hist, float4 *recs) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const size_t o = 3 * (size_t)i;
 	const unsigned slot = atomicAdd(&hist[keys[i]], 1u);
+	keys[i] = slot;
 	recs[2 * (size_t)slot] = make_float4(starts[o], starts[o + 1], starts[o + 2], __int_as_float(i));
 	recs[2 * (size_t)slot + 1] = make_float4(ends[o], ends[o + 1], ends[o + 2], 0.0f);
 }

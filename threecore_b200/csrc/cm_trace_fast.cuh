@@ -325,6 +325,12 @@ __device__ __forceinline__ int beginFast(const TraceBatch &q, const FastHull &h,
 template <bool COUNT>
 __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &q, FastLane &L) {
 	int i = L.slot;
+	if (q.compact) {
+		// Two-phase results: neighbouring slots finish in the same warp at about the same time, so these 16-byte
+		// stores fill their sectors while they are in L2 -- unlike 56-byte records scattered by item number.
+		q.compact[i] = make_uint4(__float_as_uint(L.fraction), (unsigned)(L.flags & 3), (unsigned)L.planeRef, (unsigned)L.hitId);
+		return;
+	}
 	float s0x, s0y, s0z, e0x, e0y, e0z;
 	if (q.recs) {
 		const float4 a = __ldcs(&q.recs[2 * (size_t)i]), b = __ldcs(&q.recs[2 * (size_t)i + 1]);
@@ -373,6 +379,58 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 		atomicAdd(&c->crossings, (unsigned long long)L.cCross);
 		atomicAdd(&c->splits, (unsigned long long)L.cSplits);
 	}
+}
+
+// Second phase of a binned hot launch: one thread per ITEM.  Finds the item's 16-byte result by its slot, reads the
+// item's own start and end (input arrays, coalesced), fetches the clip plane / surface flags / contents from the map
+// (L2-resident) and builds the trace_t (cm_trace.c:671-686).  The block's records are put together in shared
+// memory and leave as fully coalesced 16-byte stores: every sector of the output is written exactly once, whole.
+constexpr int kExpandBlock = 256;
+__global__ void __launch_bounds__(kExpandBlock) expandRecordsKernel(const FastMap fm, int n, const unsigned *slotOf, const uint4 *compact,
+                                                                    const float *starts, const float *ends, uint2 *out, int *hitIds) {
+	__shared__ uint2 rec[kExpandBlock * 7];
+	const int base = blockIdx.x * kExpandBlock;
+	const int i = base + threadIdx.x;
+	if (i < n) {
+		const uint4 c = __ldcs(&compact[slotOf[i]]);
+		const size_t o = 3 * (size_t)i;
+		const float s0x = __ldcs(&starts[o]), s0y = __ldcs(&starts[o + 1]), s0z = __ldcs(&starts[o + 2]);
+		const float e0x = __ldcs(&ends[o]), e0y = __ldcs(&ends[o + 1]), e0z = __ldcs(&ends[o + 2]);
+		const float fraction = __uint_as_float(c.x);
+		const int planeRef = (int)c.z, hitId = (int)c.w;
+		float4 pl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		int2 meta = make_int2(0, 0);
+		if (planeRef >= 0) {
+			pl = __ldg(&fm.sidePlanes[planeRef]);
+			meta = __ldg(&fm.sideMeta[planeRef]);
+		}
+		const int contents = hitId >= 0 ? __ldg(&fm.brushContents[hitId]) : 0;
+		float px, py, pz;
+		if (fraction == 1.0f) {
+			px = e0x; py = e0y; pz = e0z;
+		} else {
+			px = s0x + fraction * (e0x - s0x);
+			py = s0y + fraction * (e0y - s0y);
+			pz = s0z + fraction * (e0z - s0z);
+		}
+		uint2 *r = rec + 7 * threadIdx.x;
+		r[0] = make_uint2(c.y & 1u, (c.y >> 1) & 1u);
+		r[1] = make_uint2(__float_as_uint(fraction), __float_as_uint(px));
+		r[2] = make_uint2(__float_as_uint(py), __float_as_uint(pz));
+		r[3] = make_uint2(__float_as_uint(pl.x), __float_as_uint(pl.y));
+		r[4] = make_uint2(__float_as_uint(pl.z), __float_as_uint(pl.w));
+		r[5] = make_uint2((unsigned)meta.y & 0xffffu, (unsigned)meta.x);
+		r[6] = make_uint2((unsigned)contents, 0u);
+		if (hitIds) hitIds[i] = hitId;
+	}
+	__syncthreads();
+	// kExpandBlock * 56 bytes = 896 16-byte pieces; the block's first record is 16-byte aligned (base * 56)
+	const int items = min(kExpandBlock, n - base);
+	const int pieces = (items * 7) >> 1, oddTail = (items * 7) & 1;
+	uint4 *dst = reinterpret_cast<uint4 *>(out + 7 * (size_t)base);
+	const uint4 *src = reinterpret_cast<const uint4 *>(rec);
+	for (int k = threadIdx.x; k < pieces; k += kExpandBlock) __stcs(&dst[k], src[k]);
+	if (oddTail && threadIdx.x == 0) __stcs(&out[7 * (size_t)base + 2 * pieces], rec[2 * pieces]);
 }
 
 #ifndef CMGPU_PREFETCH_CHUNK
