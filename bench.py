@@ -312,14 +312,16 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        kms = trace_ms / max(trace_launches, 1)        # the dominant kernel alone
+        kms = trace_ms / max(trace_launches, 1)        # the trace launch alone (walk + record expansion), without the binning passes
         l2["achieved"] = l2["bytes_per_trace"] * n / (kms * 1e-3) / 1e9
         l2["frac"] = l2["achieved"] / l2["peak"]
         achieved = BYTES_PER_TRACE * n / (kms * 1e-3) / 1e9
         tr = ncu_traffic()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr or {}).get("dram_bytes_per_launch") if n == N_RAYS else None, "peak_source": peak_src,
-                "kernel": "cmgpu::tracePoolKernel<false, 3>", "kernel_ms": kms, "kernel_launches": trace_launches,
+                "kernel": "cmgpu::tracePoolKernel<false, 3> + cmgpu::expandRecordsKernel (the two phases of one trace launch: "
+                          "the walk stores 16 B per item, the expansion writes the 56-byte records; kernel_ms and traffic cover both)",
+                "kernel_ms": kms, "kernel_launches": trace_launches,
                 "step_ms": float(np.mean(kern_ms)),
                 "algorithmic_bytes_per_trace": BYTES_PER_TRACE, "traces_per_launch": n, "l2": l2,
                 "note": "irregular BSP walk: bound by instruction issue and dependent-load latency, not by HBM; the HBM floor "

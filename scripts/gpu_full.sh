@@ -10,9 +10,9 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_o
 cat gpurun_out/${tag}_bench.json | cut -c1-400
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_list.log 2>&1; echo "ncu list rc=$?"
-python scripts/prof_trace.py 2097152 3 > gpurun_out/${tag}_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:trace -s 1 -c 1 -f -o gpurun_out/prof_${tag} \
-    python scripts/prof_trace.py 2097152 3 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+python scripts/prof_trace.py 4194304 3 > gpurun_out/${tag}_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tracePool -s 1 -c 1 -f -o gpurun_out/prof_${tag} \
+    python scripts/prof_trace.py 4194304 3 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 # DRAM traffic of the dominant kernel at the bench's own launch size (16 Mi rays)
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:tracePool -s 3 -c 1 --csv \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'tracePool|expandRecords' -s 6 -c 2 --csv \
     --log-file gpurun_out/${tag}_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"

@@ -86,6 +86,7 @@ struct cmgpu_ctx_s {
 	bool slabTest = true;
 	int gang = kGang;
 	int gangFetch = kGang;
+	int gangBrush = kGang;
 	int lightReps = 3;
 	int facetSteps = kFacetPlaneSteps;
 	// spatial binning of large batches (counting sort by start cell)
@@ -708,6 +709,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	q.cursor = ctx->dCursor + (ctx->cursorSlot++ % kCursorSlots);
 	q.gang = ctx->gang;
 	q.gangFetch = ctx->gangFetch;
+	q.gangBrush = ctx->gangBrush;
 	q.lightReps = ctx->lightReps;
 	q.facetSteps = ctx->facetSteps;
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
@@ -953,6 +955,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "two_phase") ctx->twoPhase = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
 	else if (k == "gang_fetch") ctx->gangFetch = (int)value;
+	else if (k == "gang_brush") ctx->gangBrush = (int)value;
 	else if (k == "facet_steps") ctx->facetSteps = value < 1 ? 1 : (int)value;
 	else if (k == "light_reps") ctx->lightReps = value < 1 ? 1 : (int)value;
 	else return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_set_option: unknown option '%s'", name);

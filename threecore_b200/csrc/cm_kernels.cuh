@@ -93,6 +93,7 @@ struct TraceBatch {
 	int chunk;                           // items a warp takes from the cursor at a time (multiple of 32)
 	int gang;                            // lanes that must gather before a heavy block runs
 	int gangFetch;                       // ... before finished lanes write their records and take new items (hot kernel)
+	int gangBrush;                       // ... before the pool kernel runs its brush clip (the heaviest, least populated step)
 	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
 	int facetSteps;                      // patch planes a lane tests per scheduler iteration (general kernel)
 	Counters *counters;                  // only touched by the counting variant

@@ -106,7 +106,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 		// How many lanes own an item waiting for each kind: the presence bits of a lane are spread into byte-wide
 		// counters (4 per word) and summed over the warp with two REDUX.  Every kind that at least `thr` lanes can
 		// run (a share of the best count) is run this round.
-		int cNode, cLeaf, cSlab, cPop, cSplit, cBrush, cDone, cPos, thr;
+		int cNode, cLeaf, cSlab, cPop, cSplit, cBrush, cDone, cPos, thr, thrBrush, thrDone;
 		{
 			unsigned present = modes | (modes >> 16);
 			present = (present | (present >> 8)) & 0xffu;
@@ -118,9 +118,11 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			const int best = max(max(max(cNode, cLeaf), max(cSlab, cPop)), max(max(cSplit, cBrush), max(cDone, cPos)));
 			if (best == 0) break;                            // every slot empty
 			thr = max(1, (best * q.gang) >> 3);
+			thrBrush = max(1, (best * q.gangBrush) >> 3);
+			thrDone = max(1, (best * q.gangFetch) >> 3);
 		}
 
-		if (cDone >= thr) {
+		if (cDone >= thrDone) {
 			// ---------------- write results, take new items (cm_trace.c:545-686) -----------------
 			const int j = firstInMode<K>(modes, PM_DONE);
 			PoolHdr hd;
@@ -362,7 +364,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				else { SETI(PF_CUR, j, c); modes = withMode(modes, j, PM_NODE); }
 			}
 		}
-		if (cBrush >= thr) {
+		if (cBrush >= thrBrush) {
 			// ---------------- CM_TraceThroughBrush for the pending brush, cm_trace.c:261-363 -----
 			const int j = firstInMode<K>(modes, PM_BRUSH);
 			if (j >= 0) {
