@@ -142,7 +142,9 @@ int  cmgpu_num_inline_models(const cmgpu_ctx *ctx);
  * "bin_long_len", "bin_dir", "gang", "gang_fetch", "light_reps", "fast" (0: always the general kernel), "pool" (0: the
  * one-item-per-lane variant of the hot kernel), "pool_reps", "slab" (0: no float pre-test before the exact brush
  * clip), "two_phase" (0: binned hot launches store 56-byte records by item number from the walk itself instead of
- * 16-byte results by slot plus an expansion pass), "pipe_chunks" (pieces a host batch is cut into).  Unknown names
+ * 16-byte results by slot plus an expansion pass), "compact_by_item" (0: the pool kernel stores those results by slot and
+ * the expansion gathers them), "node_thresholds" (0: the pool kernel's node step subtracts and compares instead of using
+ * the per-hull threshold table), "gang_brush", "pipe_chunks" (pieces a host batch is cut into).  Unknown names
  * are CMGPU_ERR_INVALID. */
 int  cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value);
 

@@ -30,18 +30,19 @@ for kind in ("arena_small", "room", "arena_models"):
             outs = {}
             for label, opts in (("general", dict(fast=0)), ("pool", dict(fast=1, pool=1, pool_min_items=1, simple_max_items=0)),
                                 ("persistent", dict(fast=1, pool=0, simple_max_items=0)), ("simple", dict(fast=1, pool=0, simple_max_items=1 << 30)),
-                                ("pool-unbinned", dict(fast=1, pool=1, pool_min_items=1, simple_max_items=0, bin=0))):
+                                ("pool-unbinned", dict(fast=1, pool=1, pool_min_items=1, simple_max_items=0, bin=0)),
+                                ("pool-plain", dict(fast=1, pool=1, pool_min_items=1, simple_max_items=0, node_thresholds=0, two_phase=0))):
                 for k, v in opts.items(): eng.set_option(k, v)
                 o = torch.empty((n, 56), dtype=torch.uint8, device=dev)
                 eng.box_trace_device(ds, de, hull[0], hull[1], bspgen.MASK_ALL, o)
                 torch.cuda.synchronize(); eng.check_status()
                 outs[label] = o
-                for k, v in dict(fast=1, pool=1, pool_min_items=786433, simple_max_items=786432, bin=1).items(): eng.set_option(k, v)
+                for k, v in dict(fast=1, pool=1, pool_min_items=786433, simple_max_items=786432, bin=1, node_thresholds=1, two_phase=1).items(): eng.set_option(k, v)
             for label, o in outs.items():
                 if label == "general": continue
                 bad = int((o != outs["general"]).any(dim=1).sum())
                 bad_total += bad
                 if bad: print("MISMATCH", kind, seed, None if hull[0] is None else hull[0].tolist(), label, bad, flush=True)
             hits = float((outs["general"][:, 8:12].view(torch.float32) < 1).float().mean())
-        print(f"{kind} seed {seed}: {n} sweeps x 4 hulls x 4 variants ok so far (bad={bad_total}), hit fraction {hits:.2f}", flush=True)
+        print(f"{kind} seed {seed}: {n} sweeps x 4 hulls x 5 variants ok so far (bad={bad_total}), hit fraction {hits:.2f}", flush=True)
 print("TOTAL MISMATCHES", bad_total)

@@ -12,6 +12,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 m, starts, ends = bench.make_workload(n)
 eng = Engine(0)
 eng.load_bsp(m.data)
+for kv in (sys.argv[3].split(',') if len(sys.argv) > 3 else []):
+    eng.set_option(kv.split('=')[0], float(kv.split('=')[1]))
 dev = torch.device("cuda", 0)
 d_starts = torch.from_numpy(starts).to(dev); d_ends = torch.from_numpy(ends).to(dev)
 d_mins = bspgen.PLAYER_MINS; d_maxs = bspgen.PLAYER_MAXS

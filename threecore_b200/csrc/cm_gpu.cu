@@ -96,7 +96,11 @@ struct cmgpu_ctx_s {
 	int binMinItems = 98304;             // smaller batches are traced in input order (the five binning launches cost ~50 us)
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bCompact, bHist[kBinSlots];
-	bool twoPhase = true;                // binned hot launches: 16-byte results by slot + expandRecordsKernel
+	bool twoPhase = true, compactByItem = true;
+	// pool kernel: per-hull node threshold tables (nodeThresholdKernel), built on first use, dropped with the map
+	struct HullTable { NodeHull key; DevBuf buf; bool usable; };
+	std::vector<HullTable> hullTables;
+	bool nodeThresholds = true;                // binned hot launches: 16-byte results by slot + expandRecordsKernel
 	DevBuf bPoolHdr[kBinSlots + 1];
 	DevBuf bStackArena[kBinSlots + 1];   // traversal stacks of the hot kernel: one per pipeline stream + one for device-pointer calls
 	// Device-pointer calls share one workspace (binning buffers, stack arena).  extDone fires when the last such
@@ -243,6 +247,8 @@ void freeMap(cmgpu_ctx *ctx) {
 	memset(&ctx->map, 0, sizeof(ctx->map));
 	memset(&ctx->fast, 0, sizeof(ctx->fast));
 	ctx->numPatches = 0;
+	for (auto &t : ctx->hullTables) releaseBuf(t.buf);
+	ctx->hullTables.clear();
 	ctx->leafCluster = nullptr;
 	ctx->vised = false;
 	ctx->numClusters = ctx->clusterBytes = ctx->numAreas = 0;
@@ -667,6 +673,40 @@ FastHull makeFastHull(const float *mins, const float *maxs, int mask, bool slabO
 	return h;
 }
 
+// The node table of a hull (cm_trace_pool.cuh, nodeThresholdKernel): looked up by the bits of the six thresholds, built
+// on first use.  Building synchronises the stream once per (map, hull); a table whose boundaries could not be verified
+// on the device is marked unusable and the launch takes the plain node step.
+const int4 *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStream_t s) {
+	NodeHull key;
+	for (int a = 0; a < 3; a++) { key.hi[a] = h.nodeHi[a]; key.lo[a] = h.nodeLo[a]; }
+	for (auto &t : ctx->hullTables) {
+		if (!memcmp(&t.key, &key, sizeof(key))) return t.usable ? (const int4 *)t.buf.p : nullptr;
+	}
+	if (ctx->hullTables.size() >= 8) {                    // a ninth hull: start over (nothing may still read the old tables)
+		cudaDeviceSynchronize();
+		for (auto &t : ctx->hullTables) releaseBuf(t.buf);
+		ctx->hullTables.clear();
+	}
+	cmgpu_ctx::HullTable t{};
+	t.key = key;
+	t.usable = false;
+	const int n = ctx->map.numNodes;
+	const size_t bytes = (size_t)n * sizeof(int4);
+	if (reserve(ctx, t.buf, bytes + 16) == CMGPU_OK) {
+		int *flag = (int *)((char *)t.buf.p + bytes);
+		int hostFlag = -1;
+		bool ok = cudaMemsetAsync(flag, 0, sizeof(int), s) == cudaSuccess;
+		if (ok) nodeThresholdKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->fast.nodes, n, key, (int4 *)t.buf.p, flag);
+		ok = ok && cudaGetLastError() == cudaSuccess;
+		ok = ok && cudaMemcpyAsync(&hostFlag, flag, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+		ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+		t.usable = ok && hostFlag == 0;
+		ctx->launches++;
+	}
+	ctx->hullTables.push_back(t);
+	return t.usable ? (const int4 *)t.buf.p : nullptr;
+}
+
 // wsOffset: first item of this launch inside the context's binning workspace (the host pipeline gives
 // every chunk its own range); histSlot: which histogram table to use (one per pipeline stream).
 int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1) {
@@ -720,6 +760,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	// out must be 16-byte aligned for the expand pass's stores (any cudaMalloc'ed or record-aligned pointer is)
 	if (fast && slotOf && ctx->twoPhase && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
 		q.compact = (uint4 *)ctx->bCompact.p + wsOffset;
+	q.compactByItem = q.compact && pool && ctx->compactByItem ? 1 : 0;
 	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
 	                   : fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
 	// Items per cursor grab: kChunk for big batches; for small ones a share that spreads the batch over all
@@ -764,8 +805,10 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		if (rcA) return rcA;
 		q.poolHdr = ctx->bPoolHdr[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
-		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<true, CMGPU_POOL_K>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
-		else               CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
+		q.tnodes = (ctx->nodeThresholds && !ctx->counting) ? hullTable(ctx, h, s) : nullptr;
+		if (ctx->counting)  CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<true, CMGPU_POOL_K, false>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
+		else if (q.tnodes)  CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, true>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
+		else                CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, false>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 	} else if (fast) {
 		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * kMaxDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
@@ -780,7 +823,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
 	if (q.compact) {
-		expandRecordsKernel<<<(q.n + kExpandBlock - 1) / kExpandBlock, kExpandBlock, 0, s>>>(ctx->fast, q.n, slotOf, q.compact, q.starts,
+		expandRecordsKernel<<<(q.n + kExpandBlock - 1) / kExpandBlock, kExpandBlock, 0, s>>>(ctx->fast, q.n, q.compactByItem ? nullptr : slotOf, q.compact, q.starts,
 		                                                                                   q.ends, q.out, q.hitIds);
 		ctx->launches++;
 		CUDA_TRY(ctx, cudaGetLastError());
@@ -863,10 +906,14 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 		ctx->gridFast = perSmF * prop.multiProcessorCount;
 		ctx->gridFastCount = perSmFC * prop.multiProcessorCount;
 		int perSmP = 0, perSmPC = 0;
-		ok = ok && cudaFuncSetAttribute(tracePoolKernel<false, CMGPU_POOL_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
-		ok = ok && cudaFuncSetAttribute(tracePoolKernel<true, CMGPU_POOL_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
-		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmP, tracePoolKernel<false, CMGPU_POOL_K>, kBlock, kPoolSmem) == cudaSuccess && perSmP > 0;
-		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPC, tracePoolKernel<true, CMGPU_POOL_K>, kBlock, kPoolSmem) == cudaSuccess && perSmPC > 0;
+		ok = ok && cudaFuncSetAttribute(tracePoolKernel<false, CMGPU_POOL_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
+		ok = ok && cudaFuncSetAttribute(tracePoolKernel<false, CMGPU_POOL_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
+		ok = ok && cudaFuncSetAttribute(tracePoolKernel<true, CMGPU_POOL_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
+		int perSmPT = 0;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmP, tracePoolKernel<false, CMGPU_POOL_K, false>, kBlock, kPoolSmem) == cudaSuccess && perSmP > 0;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPT, tracePoolKernel<false, CMGPU_POOL_K, true>, kBlock, kPoolSmem) == cudaSuccess && perSmPT > 0;
+		if (perSmPT < perSmP) perSmP = perSmPT;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPC, tracePoolKernel<true, CMGPU_POOL_K, false>, kBlock, kPoolSmem) == cudaSuccess && perSmPC > 0;
 		ctx->gridPool = perSmP * prop.multiProcessorCount;
 		ctx->gridPoolCount = perSmPC * prop.multiProcessorCount;
 	}
@@ -953,6 +1000,8 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "two_phase") ctx->twoPhase = value != 0;
+	else if (k == "compact_by_item") ctx->compactByItem = value != 0;
+	else if (k == "node_thresholds") ctx->nodeThresholds = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
 	else if (k == "gang_fetch") ctx->gangFetch = (int)value;
 	else if (k == "gang_brush") ctx->gangBrush = (int)value;

@@ -102,6 +102,8 @@ struct TraceBatch {
 	const float4 *recs;                  // binned batch: [2*slot] start.xyz + item bits, [2*slot+1] end.xyz + 0; null = input order
 	uint4 *compact;                      // binned hot kernels: results leave as 16 bytes per SLOT (fraction, flags, clip side,
 	                                     // hit brush); expandRecordsKernel writes the 56-byte records in item order.  null: direct
+	const int4 *tnodes;                  // pool kernel: nodes with this batch's hull folded into two thresholds (nodeThresholdKernel); may be null
+	int compactByItem;                   // pool kernel: compact[] is indexed by item number (a 16-byte scatter), not by slot
 };
 
 // ---- spatial binning of a batch (counting sort by start cell) -------------------------------

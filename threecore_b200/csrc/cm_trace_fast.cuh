@@ -55,6 +55,7 @@ struct __align__(16) FastSeg { int num; float f1, f2, ax; float ay, az, bx, by; 
 
 struct FastLane {
 	int   slot;                          // position in the (binned) batch
+	int   item;                          // its number in the caller's arrays (== slot when the batch is not binned)
 	float sx, sy, sz, ex, ey, ez;        // tw.start / tw.end
 	float lox, loy, loz, hix, hiy, hiz;  // tw.bounds
 	float fraction;
@@ -295,10 +296,12 @@ __device__ __forceinline__ int beginFast(const TraceBatch &q, const FastHull &h,
 	if (q.recs) {
 		const float4 a = __ldcs(&q.recs[2 * (size_t)slot]), b = __ldcs(&q.recs[2 * (size_t)slot + 1]);
 		s0x = a.x; s0y = a.y; s0z = a.z; e0x = b.x; e0y = b.y; e0z = b.z;
+		L.item = __float_as_int(a.w);
 	} else {
 		const size_t o = 3 * (size_t)slot;
 		s0x = q.starts[o]; s0y = q.starts[o + 1]; s0z = q.starts[o + 2];
 		e0x = q.ends[o]; e0y = q.ends[o + 1]; e0z = q.ends[o + 2];
+		L.item = slot;
 	}
 	L.slot = slot;
 	L.sx = s0x + h.off[0]; L.sy = s0y + h.off[1]; L.sz = s0z + h.off[2];
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(kExpandBlock) expandRecordsKernel(const FastMa
 	const int base = blockIdx.x * kExpandBlock;
 	const int i = base + threadIdx.x;
 	if (i < n) {
-		const uint4 c = __ldcs(&compact[slotOf[i]]);
+		const uint4 c = __ldcs(&compact[slotOf ? slotOf[i] : (unsigned)i]);
 		const size_t o = 3 * (size_t)i;
 		const float s0x = __ldcs(&starts[o]), s0y = __ldcs(&starts[o + 1]), s0z = __ldcs(&starts[o + 2]);
 		const float e0x = __ldcs(&ends[o]), e0y = __ldcs(&ends[o + 1]), e0z = __ldcs(&ends[o + 2]);

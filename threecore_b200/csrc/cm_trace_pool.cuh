@@ -74,7 +74,55 @@ __device__ __forceinline__ unsigned withMode(const unsigned modes, const int j, 
 #define CMGPU_POOL_MIN_BLOCKS 7
 #endif
 
-template <bool COUNT, int K>
+// ---- the batch's hull folded into the nodes --------------------------------------------------------------------
+// An axial node asks whether fl(p - dist) >= hi (both ends: in front) or fl(p - dist) < lo (both ends: behind), with
+// hi / lo the float images of offset+1 / -offset-1 for the node's axis (makeFastHull).  Float subtraction is monotone
+// in p, so each question is a threshold on p itself: p >= tHi with tHi the SMALLEST float whose difference reaches
+// hi, and p < tLo with tLo the smallest float whose difference reaches lo.  The table holds, per node,
+// {child0 << 2 | type, child1, tHi, tLo}; a non-axial node gets (+inf, -inf) and so never passes as a plain descent.
+// Built once per (map, hull) -- 16 bytes per node -- and saves the node step its two subtractions and the per-axis
+// selection of hi and lo.
+// (bisection over the floats in their numeric order: near dist = -want the answer lies astronomically many
+// representable values away from want + dist, so stepping with nextafterf does not get there)
+__device__ __forceinline__ unsigned floatOrderKey(const float f) {
+	const unsigned u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float floatFromOrderKey(const unsigned k) {
+	return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ float smallestReaching(const float dist, const float want) {
+	unsigned lo = floatOrderKey(-3.0e38f), hi = floatOrderKey(3.0e38f);   // predicate false at lo, true at hi
+	while (hi - lo > 1u) {
+		const unsigned mid = lo + ((hi - lo) >> 1);
+		if ((floatFromOrderKey(mid) - dist) >= want) hi = mid; else lo = mid;
+	}
+	return floatFromOrderKey(hi);
+}
+
+struct NodeHull { float hi[3], lo[3]; };
+
+__global__ void __launch_bounds__(256) nodeThresholdKernel(const int4 *nodes, const int n, const NodeHull h, int4 *out, int *status) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int4 nd = nodes[i];
+	float tHi = INFINITY, tLo = -INFINITY;
+	if (nd.z < 3) {
+		const float dist = __int_as_float(nd.w);
+		const float hi = nd.z == 0 ? h.hi[0] : (nd.z == 1 ? h.hi[1] : h.hi[2]);
+		const float lo = nd.z == 0 ? h.lo[0] : (nd.z == 1 ? h.lo[1] : h.lo[2]);
+		tHi = smallestReaching(dist, hi);
+		tLo = smallestReaching(dist, lo);
+		// the boundary must be exact: the float just below fails, the threshold itself passes (else: no table for this map)
+		const bool okHi = (tHi - dist) >= hi && !((nextafterf(tHi, -INFINITY) - dist) >= hi) && fabsf(tHi) < 1.0e38f;
+		const bool okLo = (tLo - dist) >= lo && !((nextafterf(tLo, -INFINITY) - dist) >= lo) && fabsf(tLo) < 1.0e38f;
+		if (!okHi || !okLo) atomicOr(status, 2);
+	}
+	if (nd.x >= (1 << 29) || nd.x < -(1 << 29)) atomicOr(status, 2);
+	out[i] = make_int4((int)(((unsigned)nd.x << 2) | (unsigned)(nd.z & 3)), nd.y, __float_as_int(tHi), __float_as_int(tLo));
+}
+
+template <bool COUNT, int K, bool THR>
 __global__ void __launch_bounds__(kBlock, CMGPU_POOL_MIN_BLOCKS)
 tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 	extern __shared__ float poolMem[];
@@ -129,11 +177,11 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			hd.slot = -1;
 			if (j >= 0) {
 				const float4 v = ldKeep(reinterpret_cast<const float4 *>(&HDR(j)), l2KeepPolicy());
-				hd.slot = __float_as_int(v.x); hd.planeRef = __float_as_int(v.y); hd.hitId = __float_as_int(v.z); hd.pad = 0;
+				hd.slot = __float_as_int(v.x); hd.planeRef = __float_as_int(v.y); hd.hitId = __float_as_int(v.z); hd.pad = __float_as_int(v.w);
 			}
 			if (hd.slot >= 0) {
 				FastLane L;
-				L.slot = hd.slot; L.fraction = FLD(PF_FRACTION, j); L.flags = FLDI(PF_FLAGS, j) & 0xff;
+				L.slot = q.compactByItem ? hd.pad : hd.slot; L.fraction = FLD(PF_FRACTION, j); L.flags = FLDI(PF_FLAGS, j) & 0xff;
 				L.planeRef = hd.planeRef; L.hitId = hd.hitId;
 				L.cNodes = L.cLeafs = L.cBrushRefs = L.cBrushBounds = L.cBrushSides = L.cCross = L.cSplits = 0;
 				finishFast<false>(fm, q, L);
@@ -160,7 +208,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					FastLane L;
 					const int m = beginFast<false>(q, h, L, my);
 					hd.slot = L.slot; hd.planeRef = -1; hd.hitId = -1; hd.pad = 0;
-					stKeep(reinterpret_cast<float4 *>(&HDR(j)), make_float4(__int_as_float(hd.slot), __int_as_float(-1), __int_as_float(-1), 0.0f), l2KeepPolicy());
+					stKeep(reinterpret_cast<float4 *>(&HDR(j)), make_float4(__int_as_float(hd.slot), __int_as_float(-1), __int_as_float(-1), __int_as_float(L.item)), l2KeepPolicy());
 					FLD(PF_SX, j) = L.sx; FLD(PF_SY, j) = L.sy; FLD(PF_SZ, j) = L.sz;
 					FLD(PF_EX, j) = L.ex; FLD(PF_EY, j) = L.ey; FLD(PF_EZ, j) = L.ez;
 					FLD(PF_FRACTION, j) = 1.0f; SETI(PF_FLAGS, j, L.flags);
@@ -193,18 +241,33 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					#pragma unroll
 					for (int lvl = 0; lvl < kNodeLevels; lvl++) {
 						if (next == PM_NODE) {
-							const int4 nd = __ldg(&fm.nodes[num]);
+							bool go, front;
+							int c0, c1;
+							if (THR) {
+								// thresholds on the coordinates themselves (nodeThresholdKernel); type 3 reads the field
+								// after the axis triple and compares it with +-inf: never a plain descent
+								const int4 nd = __ldg(&q.tnodes[num]);
+								const int ax = nd.x & 3;
+								const float tHi = __int_as_float(nd.z), tLo = __int_as_float(nd.w);
+								const float a = FLD(PF_AX + ax, j), b = FLD(PF_BX + ax, j);
+								front = a >= tHi && b >= tHi;
+								go = front || (a < tLo && b < tLo);
+								c0 = nd.x >> 2; c1 = nd.y;
+							} else {
+								const int4 nd = __ldg(&fm.nodes[num]);
+								const int ax = nd.z < 3 ? nd.z : 0;
+								const float dist = __int_as_float(nd.w);
+								const float t1 = FLD(PF_AX + ax, j) - dist;
+								const float t2 = FLD(PF_BX + ax, j) - dist;
+								const float hi = ax == 0 ? h.nodeHi[0] : (ax == 1 ? h.nodeHi[1] : h.nodeHi[2]);
+								const float lo = ax == 0 ? h.nodeLo[0] : (ax == 1 ? h.nodeLo[1] : h.nodeLo[2]);
+								front = t1 >= hi && t2 >= hi;
+								const bool back = t1 < lo && t2 < lo;
+								go = nd.z < 3 && (front || back);      // else: split or non-axial node
+								c0 = nd.x; c1 = nd.y;
+							}
 							if (COUNT) cNodes++;
-							const int ax = nd.z < 3 ? nd.z : 0;
-							const float dist = __int_as_float(nd.w);
-							const float t1 = FLD(PF_AX + ax, j) - dist;
-							const float t2 = FLD(PF_BX + ax, j) - dist;
-							const float hi = ax == 0 ? h.nodeHi[0] : (ax == 1 ? h.nodeHi[1] : h.nodeHi[2]);
-							const float lo = ax == 0 ? h.nodeLo[0] : (ax == 1 ? h.nodeLo[1] : h.nodeLo[2]);
-							const bool front = t1 >= hi && t2 >= hi;
-							const bool back = t1 < lo && t2 < lo;
-							const bool go = nd.z < 3 && (front || back);      // else: split or non-axial node
-							const int c = front ? nd.x : nd.y;
+							const int c = front ? c0 : c1;
 							const bool leaf = go && c < 0;
 							if (go) num = c < 0 ? -1 - c : c;
 							if (COUNT) cLeafs += leaf ? 1u : 0u;
