@@ -203,3 +203,102 @@ def test_sv_point_contents_batch(api):
     np.bitwise_or.at(want, mv, c2)
     assert np.array_equal(got, want)
     assert (got != o.point_contents(pts)).mean() > 0.05, "entities do not contribute"
+
+
+# ---- leaf queries, visibility and area portals under their cm_public.h names (cm_public.h:54-69) --------------------
+@pytest.fixture(scope="module")
+def vis_api(api):
+    """the same library with a map that has clusters, areas and a visibility lump; the arena map is put back afterwards"""
+    import leaf_cases as lc
+    lib, m0, _ = api
+    vp = C.c_void_p
+    lib.CM_PointLeafnum.argtypes = [vp]
+    lib.CM_BoxLeafnums.argtypes = [vp, vp, vp, C.c_int, vp]
+    lib.CM_LeafCluster.argtypes = [C.c_int]
+    lib.CM_LeafArea.argtypes = [C.c_int]
+    lib.CM_PointLeafnumBatch.argtypes = [vp, C.c_int, vp]
+    lib.CM_BoxLeafnumsBatch.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp]
+    lib.CM_ClusterPVS.argtypes = [C.c_int]
+    lib.CM_ClusterPVS.restype = C.POINTER(C.c_ubyte)
+    lib.CM_AdjustAreaPortalState.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.CM_AdjustAreaPortalState.restype = None
+    lib.CM_AreasConnected.argtypes = [C.c_int, C.c_int]
+    lib.CM_WriteAreaBits.argtypes = [vp, C.c_int]
+    lib.SV_EntityClustersBatch.argtypes = [C.c_int, vp, vp, vp]
+    lib.SV_VisibleFromPointsBatch.argtypes = [C.c_int, vp, C.c_int, vp, vp, vp]
+    m = lc.vis_map("arena_small_vis")
+    assert lib.CM_LoadMapFromMemory(b"maps/vis.bsp", m.data, len(m.data), None) == 0, lib.CM_LastError()
+    from threecore_b200.engine import FlatMap
+    o = cmoracle.OracleCM(FlatMap.from_bsp(m.data).to_dict())
+    yield lib, m, o, lc
+    assert lib.CM_LoadMapFromMemory(b"maps/test.bsp", m0.data, len(m0.data), None) == 0, lib.CM_LastError()
+
+
+def test_leaf_queries_keep_the_reference_signatures(vis_api):
+    lib, m, o, lc = vis_api
+    lca = o.flat["leaf_cluster_area"]
+    pts = lc.viewpoints(m, 200, 61)
+    want = o.point_leafnum(pts)
+    got = np.array([lib.CM_PointLeafnum(pts[i].ctypes.data) for i in range(len(pts))], np.int32)
+    assert np.array_equal(got, want)
+    assert [lib.CM_LeafCluster(int(l)) for l in want[:50]] == lca[want[:50], 0].tolist()
+    assert [lib.CM_LeafArea(int(l)) for l in want[:50]] == lca[want[:50], 1].tolist()
+    batch = np.zeros(len(pts), np.int32)
+    assert lib.CM_PointLeafnumBatch(batch.ctypes.data, len(pts), pts.ctypes.data) == 0
+    assert np.array_equal(batch, want)
+    mins, maxs = lc.query_boxes(m, 200, 62)
+    wl, wc, wlast = o.box_leafnums(mins, maxs, 32)
+    for i in range(len(mins)):
+        lst = np.full(32, -1, np.int32)
+        last = C.c_int(-5)
+        n = lib.CM_BoxLeafnums(mins[i].ctypes.data, maxs[i].ctypes.data, lst.ctypes.data, 32, C.byref(last))
+        assert n == wc[i] and last.value == wlast[i] and np.array_equal(lst, wl[i]), f"box {i}"
+    # lastLeaf may be NULL (cm_public.h:58 callers that do not care)
+    lst = np.zeros(4, np.int32)
+    assert lib.CM_BoxLeafnums(mins[0].ctypes.data, maxs[0].ctypes.data, lst.ctypes.data, 4, None) == min(4, o.box_leafnums(mins[:1], maxs[:1], 4)[1][0])
+    lists, counts, lasts = np.full((len(mins), 32), -1, np.int32), np.zeros(len(mins), np.int32), np.zeros(len(mins), np.int32)
+    assert lib.CM_BoxLeafnumsBatch(len(mins), mins.ctypes.data, maxs.ctypes.data, 32, lists.ctypes.data, counts.ctypes.data, lasts.ctypes.data) == 0
+    assert np.array_equal(lists, wl) and np.array_equal(counts, wc) and np.array_equal(lasts, wlast)
+
+
+def test_visibility_and_area_portals_keep_the_reference_signatures(vis_api):
+    lib, m, o, lc = vis_api
+    nc, cb, vis = lc.vis_lump(m.data)
+    nA = m.stats["areas"]
+    assert lib.CM_NumClusters() == nc
+    for cl in (0, 5, nc - 1):
+        row = np.ctypeslib.as_array(lib.CM_ClusterPVS(cl), shape=(cb,))
+        assert np.array_equal(row, vis[cl * cb:(cl + 1) * cb])
+    row = np.ctypeslib.as_array(lib.CM_ClusterPVS(-1), shape=(cb,))          # out of range: row 0 (cm_test.c:307-309)
+    assert np.array_equal(row, vis[:cb])
+    portals = np.zeros((nA, nA), np.int32)
+    mins, maxs = lc.query_boxes(m, 120, 63)
+    ents21 = o.entity_clusters(mins, maxs)
+    ents = np.zeros((len(mins), 21), np.int32)
+    assert lib.SV_EntityClustersBatch(len(mins), mins.ctypes.data, maxs.ctypes.data, ents.ctypes.data) == 0
+    assert np.array_equal(ents, ents21)
+    views = lc.viewpoints(m, 40, 64)
+    words = (len(mins) + 31) // 32
+    for step, (p, q, open_) in enumerate(lc.portal_script(nA, 65, steps=6)):
+        lib.CM_AdjustAreaPortalState(p, q, int(open_))
+        d = 1 if open_ else -1
+        portals[p, q] += d
+        portals[q, p] += d
+        flood = o.flood_areas(portals)
+        for a in range(nA):
+            assert [bool(lib.CM_AreasConnected(a, b)) for b in range(nA)] == (flood == flood[a]).tolist()
+            buf = np.zeros(8, np.uint8)
+            assert lib.CM_WriteAreaBits(buf.ctypes.data, a) == (nA + 7) // 8
+            assert np.array_equal(np.unpackbits(buf, bitorder="little")[:nA].astype(bool), flood == flood[a])
+        assert not lib.CM_AreasConnected(-1, 0)
+        bits = np.zeros((len(views), words), np.uint32)
+        leafs = np.zeros(len(views), np.int32)
+        assert lib.SV_VisibleFromPointsBatch(len(views), views.ctypes.data, len(mins), ents.ctypes.data, bits.ctypes.data, leafs.ctypes.data) == 0
+        got = np.unpackbits(bits.view(np.uint8).reshape(len(views), -1), axis=1, bitorder="little")[:, :len(mins)].astype(bool)
+        assert np.array_equal(leafs, o.point_leafnum(views))
+        assert np.array_equal(got, o.visible_from_points(views, ents21, flood, nc, cb, vis)), f"step {step}"
+    # close what the script left open so that the module's other tests see a map with all portals closed
+    for a in range(nA):
+        for b in range(a, nA):
+            for _ in range(int(portals[a, b]) // (2 if a == b else 1)):
+                lib.CM_AdjustAreaPortalState(a, b, 0)
