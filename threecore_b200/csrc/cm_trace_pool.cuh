@@ -52,19 +52,18 @@ enum PoolField : int {
 // what an item only needs when its record is written lives in global memory (one 16-byte header per item slot)
 struct __align__(16) PoolHdr { int slot, planeRef, hitId, pad; };
 
-// The step kinds of a lane's K items are one-hot bytes of one register (bit m-1 of byte j: item j waits for kind m),
-// so "do I own an item of kind m" and "which" are a mask and a find-first-set.
+// The step kinds of a lane's K (<= 4) items live in one register, kind-major: nibble m-1 holds one bit per item that
+// waits for kind m.  "Do I own an item of kind m, and which" is a shift, a mask and a find-first-set; moving item j
+// to another kind clears bit j of every nibble and sets one bit.
 template <int K>
 __device__ __forceinline__ int firstInMode(const unsigned modes, const int m) {
-	const unsigned t = modes & (0x01010101u << (m - 1));
-	return t ? ((__ffs((int)t) - 1) >> 3) : -1;
+	return __ffs((int)((modes >> (4 * (m - 1))) & 0xfu)) - 1;
 }
 
 __device__ __forceinline__ unsigned withMode(const unsigned modes, const int j, const int m) {
-	// byte j of `modes` := one-hot(m): a byte permute that takes byte j from the second operand
-	const unsigned bit = m ? (1u << (m - 1)) : 0u;
-	const unsigned sel = 0x3210u ^ ((4u ^ (unsigned)j) << (4 * j));
-	return __byte_perm(modes, bit, sel);
+	const unsigned clr = 0x11111111u << j;
+	const unsigned set = m ? ((1u << (4 * (m - 1))) << j) : 0u;
+	return (modes & ~clr) | set;
 }
 
 #ifndef CMGPU_POOL_K
@@ -156,13 +155,15 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 		// run (a share of the best count) is run this round.
 		int cNode, cLeaf, cSlab, cPop, cSplit, cBrush, cDone, cPos, thr, thrBrush, thrDone;
 		{
-			unsigned present = modes | (modes >> 16);
-			present = (present | (present >> 8)) & 0xffu;
-			const unsigned ka = ((present & 0xfu) * 0x00204081u) & 0x01010101u;
-			const unsigned kb = ((present >> 4) * 0x00204081u) & 0x01010101u;
+			// bit 4k of p: nibble k is not empty.  (x | x << 12) & 0x01010101 puts kinds 0, 2, 1, 3 of a half into bytes 0..3
+			unsigned p = modes | (modes >> 1);
+			p = (p | (p >> 2)) & 0x11111111u;
+			const unsigned xa = p & 0xffffu, xb = p >> 16;
+			const unsigned ka = (xa | (xa << 12)) & 0x01010101u;
+			const unsigned kb = (xb | (xb << 12)) & 0x01010101u;
 			const unsigned ca = __reduce_add_sync(0xffffffffu, ka), cb = __reduce_add_sync(0xffffffffu, kb);
-			cNode = ca & 0xff; cLeaf = (ca >> 8) & 0xff; cSlab = (ca >> 16) & 0xff; cPop = ca >> 24;
-			cSplit = cb & 0xff; cBrush = (cb >> 8) & 0xff; cDone = (cb >> 16) & 0xff; cPos = cb >> 24;
+			cNode = ca & 0xff; cSlab = (ca >> 8) & 0xff; cLeaf = (ca >> 16) & 0xff; cPop = ca >> 24;
+			cSplit = cb & 0xff; cDone = (cb >> 8) & 0xff; cBrush = (cb >> 16) & 0xff; cPos = cb >> 24;
 			const int best = max(max(max(cNode, cLeaf), max(cSlab, cPop)), max(max(cSplit, cBrush), max(cDone, cPos)));
 			if (best == 0) break;                            // every slot empty
 			thr = max(1, (best * q.gang) >> 3);
