@@ -250,7 +250,7 @@ def test_binned_order_equals_input_order(eng, big):
 
 @pytest.mark.parametrize("opts", [dict(pool=0), dict(pool=0, slab=0), dict(fast=0), dict(pool=1, slab=0), dict(pool=1, pool_reps=5, gang=8),
                                   dict(pool=0, simple_max_items=1 << 21), dict(pool=0, simple_max_items=1 << 21, bin=0, slab=0),
-                                  dict(two_phase=0), dict(node_thresholds=0), dict(node_thresholds=0, compact_by_item=0), dict(two_phase=0, pool=0), dict(two_phase=0, pool=0, simple_max_items=1 << 21)])
+                                  dict(two_phase=0), dict(node_thresholds=0), dict(node_thresholds=0, compact_by_item=0), dict(two_phase=0, pool=0), dict(two_phase_small=1, pool=0), dict(two_phase_small=1, pool=0, simple_max_items=1 << 21)])
 def test_kernel_variants_agree(eng, big, opts):
     """the general kernel, the one-item-per-lane hot kernel and the pool kernel must return the same bytes"""
     import torch
@@ -263,12 +263,12 @@ def test_kernel_variants_agree(eng, big, opts):
         torch.cuda.synchronize()
         eng.check_status()
     finally:
-        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=1, gang=4, simple_max_items=786432, bin=1, two_phase=1, node_thresholds=1, compact_by_item=1).items():
+        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=1, gang=4, simple_max_items=786432, bin=1, two_phase=1, two_phase_small=0, node_thresholds=1, compact_by_item=1).items():
             eng.set_option(k, v)
     assert torch.equal(o, big["out"][:n])
 
 
-@pytest.mark.parametrize("n,shift", [((1 << 20) + 37, 0), ((1 << 20) - 255, 1), (131073, 3)])
+@pytest.mark.parametrize("n,shift", [((1 << 20) + 37, 0), ((1 << 20) - 255, 1), ((1 << 20) + 1, 3)])
 def test_two_phase_results_odd_sizes_and_unaligned_output(eng, big, n, shift):
     """binned hot launches write 16-byte results by slot and expand them to records in a second pass: item counts that
     are no multiple of the pass's block, hit ids, and an output pointer the pass cannot take (8 mod 16: direct stores)"""

@@ -96,7 +96,7 @@ struct cmgpu_ctx_s {
 	int binMinItems = 98304;             // smaller batches are traced in input order (the five binning launches cost ~50 us)
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bCompact, bHist[kBinSlots];
-	bool twoPhase = true, twoPhaseHost = false, compactByItem = true;
+	bool twoPhase = true, twoPhaseHost = false, twoPhaseSmall = false, compactByItem = true;
 	// pool kernel: per-hull node threshold tables (nodeThresholdKernel), built on first use, dropped with the map
 	struct HullTable { NodeHull key; DevBuf buf; bool usable; };
 	std::vector<HullTable> hullTables;
@@ -760,7 +760,9 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	// out must be 16-byte aligned for the expand pass's stores (any cudaMalloc'ed or record-aligned pointer is)
 	// (not in the host pipeline: its pieces are small, their records leave over PCIe anyway, and the extra launch per
 	//  piece costs the call 8 % -- measured 764 against 826 Mtraces/s end to end)
-	if (fast && slotOf && ctx->twoPhase && (external || ctx->twoPhaseHost) && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
+	// and not for the smaller launches of the one-item-per-lane kernels either (a rollout phase, a game tick: one more
+	// launch is 5 % of their latency; "two_phase_small" turns it on for them)
+	if (fast && (pool || ctx->twoPhaseSmall) && slotOf && ctx->twoPhase && (external || ctx->twoPhaseHost) && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
 		q.compact = (uint4 *)ctx->bCompact.p + wsOffset;
 	q.compactByItem = q.compact && pool && ctx->compactByItem ? 1 : 0;
 	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
@@ -1003,6 +1005,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "slab") ctx->slabTest = value != 0;
 	else if (k == "two_phase") ctx->twoPhase = value != 0;
 	else if (k == "two_phase_host") ctx->twoPhaseHost = value != 0;
+	else if (k == "two_phase_small") ctx->twoPhaseSmall = value != 0;
 	else if (k == "compact_by_item") ctx->compactByItem = value != 0;
 	else if (k == "node_thresholds") ctx->nodeThresholds = value != 0;
 	else if (k == "gang") ctx->gang = (int)value;
