@@ -64,6 +64,9 @@ class Rollout:
         self.out = torch.empty((3 * self.n, 56), dtype=torch.uint8, device=self.dev)
         self.traces = 0
         self.launches = 0
+        # constants of a tick, made once (torch.tensor(..., device=...) is a synchronous copy every time it is called)
+        c = lambda *xyz: torch.tensor(list(xyz), dtype=torch.float32, device=self.dev)
+        self._down, self._eye, self._flat, self._up = c(0.0, 0.0, -1.0), c(0.0, 0.0, 26.0), c(1.0, 1.0, 0.0), c(0.0, 0.0, STEP_HEIGHT)
 
     def _trace(self, starts: torch.Tensor, ends: torch.Tensor) -> torch.Tensor:
         starts = starts.contiguous()
@@ -80,15 +83,15 @@ class Rollout:
     def tick(self):
         n, dt = self.n, self.dt
         o, v = self.origin, self.velocity
-        down = torch.tensor([0.0, 0.0, -1.0], device=self.dev)
+        down = self._down
         # ---- ground trace + the two probes: independent of each other, one launch of 3n traces
-        eye = o + torch.tensor([0.0, 0.0, 26.0], device=self.dev)
+        eye = o + self._eye
         starts = torch.cat([o, o, eye])
         ends = torch.cat([o + down * GROUND_DIST, o + down * 2.0, eye + v * (dt * 0.25)])
         rec = self._trace(starts, ends)
         gf, _, gn, _ = _fields(rec[:n])
         on_ground = (gf < 1.0) & (gn[:, 2] > 0.7)
-        v = torch.where(on_ground[:, None], v * torch.tensor([1.0, 1.0, 0.0], device=self.dev), v + down * (800.0 * dt))
+        v = torch.where(on_ground[:, None], v * self._flat, v + down * (800.0 * dt))
         # ---- slide move: 4 bumps, every agent traces every bump (a finished agent sweeps zero distance: position test)
         time_left = torch.full((n,), dt, device=self.dev)
         for _ in range(4):
@@ -102,11 +105,11 @@ class Rollout:
             back = torch.where(back < 0, back * OVERCLIP, back / OVERCLIP)
             v = torch.where(hit[:, None], v - nrm * back[:, None], v)
         # ---- step: up, forward, down
-        up = torch.tensor([0.0, 0.0, STEP_HEIGHT], device=self.dev)
+        up = self._up
         rec = self._trace(o, o + up)
         _, top, _, _ = _fields(rec)
         top = top.clone()
-        fwd = v * torch.tensor([1.0, 1.0, 0.0], device=self.dev) * dt
+        fwd = v * self._flat * dt
         rec = self._trace(top, top + fwd)
         _, ahead, _, _ = _fields(rec)
         ahead = ahead.clone()
