@@ -88,6 +88,12 @@ __device__ __forceinline__ float4 ldKeep(const float4 *p, const unsigned long lo
 	return v;
 }
 
+__device__ __forceinline__ float ldKeepF(const float *p, const unsigned long long pol) {
+	float v;
+	asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
+	return v;
+}
+
 __device__ __forceinline__ void stKeep32(int *p, const int v, const unsigned long long pol) {
 	asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
 }

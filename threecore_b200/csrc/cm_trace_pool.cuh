@@ -133,11 +133,16 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 #define FLDI(f, j) __float_as_int(FLD(f, j))
 #define SETI(f, j, v) FLD(f, j) = __int_as_float(v)
 	const size_t globalWarp = (size_t)blockIdx.x * (kBlock / 32) + warpInBlock;
-	// traversal stacks: entry d of item slot s is arena[d * slots + s] -- the entries of neighbouring slots at one depth
-	// share cache lines, so the few shallow depths that are ever used are a dense, L2-sized region
+	// traversal stacks, depth-major: the entries of neighbouring slots at one depth share cache lines, so the few shallow
+	// depths that are ever used are a dense, L2-sized region.  An entry is 36 bytes; its first eight words are one whole
+	// 32-byte sector of arena32[d][slot] (child, f1, f2, a.xyz, b.xy -- never a partial-sector write), the ninth (b.z)
+	// lives in arenaZ[d][slot], where the lanes of a warp are neighbours.
 	const size_t arenaSlots = (size_t)gridDim.x * kBlock * K;
-	FastSeg *const arena = q.stackArena + (globalWarp * K) * 32 + lane;                 // item j: + j * 32
-#define STACKAT(j, d) (arena + (size_t)(d) * arenaSlots + (size_t)(j) * 32)
+	float4 *const arena32 = reinterpret_cast<float4 *>(q.stackArena) + 2 * ((globalWarp * K) * 32 + lane);      // item j: + 2 * j * 32
+	float *const arenaZ = reinterpret_cast<float *>(reinterpret_cast<float4 *>(q.stackArena) + 2 * (size_t)kPoolDepth * arenaSlots)
+	                      + (globalWarp * K) * 32 + lane;
+#define STACKAT(j, d) (arena32 + 2 * ((size_t)(d) * arenaSlots + (size_t)(j) * 32))
+#define STACKZ(j, d) (arenaZ + (size_t)(d) * arenaSlots + (size_t)(j) * 32)
 	PoolHdr *const hdrs = reinterpret_cast<PoolHdr *>(q.poolHdr) + (globalWarp * K) * 32 + lane;
 #define HDR(j) hdrs[(j) * 32]
 
@@ -354,14 +359,15 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (sp == 0) {
 					modes = withMode(modes, j, PM_DONE);
 				} else {
-					const float4 *sp4 = reinterpret_cast<const float4 *>(STACKAT(j, sp - 1));
+					const float4 *sp4 = STACKAT(j, sp - 1);
 					const unsigned long long keep = l2KeepPolicy();
-					const float4 t0 = ldKeep(&sp4[0], keep), t1 = ldKeep(&sp4[1], keep), t2 = ldKeep(&sp4[2], keep);
+					const float4 t0 = ldKeep(&sp4[0], keep), t1 = ldKeep(&sp4[1], keep);
+					const float t2x = ldKeepF(STACKZ(j, sp - 1), keep);
 					SETI(PF_FLAGS, j, fl - 256);
 					if (!(FLD(PF_FRACTION, j) <= t0.y)) {              // cm_trace.c:449: already hit something nearer
 						FLD(PF_F1, j) = t0.y; FLD(PF_F2, j) = t0.z;
 						FLD(PF_AX, j) = t0.w; FLD(PF_AY, j) = t1.x; FLD(PF_AZ, j) = t1.y;
-						FLD(PF_BX, j) = t1.z; FLD(PF_BY, j) = t1.w; FLD(PF_BZ, j) = t2.x;
+						FLD(PF_BX, j) = t1.z; FLD(PF_BY, j) = t1.w; FLD(PF_BZ, j) = t2x;
 						const int c = __float_as_int(t0.x);
 						if (c < 0) { SETI(PF_CUR, j, -1 - c); modes = withMode(modes, j, PM_LEAF); if (COUNT) cLeafs++; }
 						else { SETI(PF_CUR, j, c); modes = withMode(modes, j, PM_NODE); }
@@ -409,11 +415,11 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const int fl = FLDI(PF_FLAGS, j);
 					const int sp = (fl >> 8) & 0xff;
 					if (sp < kPoolDepth) {
-						float4 *sp4 = reinterpret_cast<float4 *>(STACKAT(j, sp));
+						float4 *sp4 = STACKAT(j, sp);
 						const unsigned long long keep = l2KeepPolicy();
 						stKeep(&sp4[0], make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)), keep);
 						stKeep(&sp4[1], make_float4(ay_ + ffar * (by_ - ay_), az_ + ffar * (bz_ - az_), bx_, by_), keep);
-						stKeep(&sp4[2], make_float4(bz_, 0.0f, 0.0f, 0.0f), keep);
+						stKeep32(reinterpret_cast<int *>(STACKZ(j, sp)), __float_as_int(bz_), keep);
 						SETI(PF_FLAGS, j, fl + 256);
 					} else {
 						atomicOr(q.status, 1);
@@ -504,7 +510,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						} else {
 							const int fl = FLDI(PF_FLAGS, j);
 							const int sp = (fl >> 8) & 0xff;
-							if (sp < kPoolDepth) { __stcg(&STACKAT(j, sp)->num, nd.y); SETI(PF_FLAGS, j, fl + 256); }
+							if (sp < kPoolDepth) { __stcg(reinterpret_cast<int *>(STACKAT(j, sp)), nd.y); SETI(PF_FLAGS, j, fl + 256); }
 							else atomicOr(q.status, 1);
 							SETI(PF_CUR, j, nd.x);
 						}
@@ -521,7 +527,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						if (sp == 0) {
 							modes = withMode(modes, j, PM_DONE);
 						} else {
-							SETI(PF_CUR, j, __ldcg(&STACKAT(j, sp - 1)->num));
+							SETI(PF_CUR, j, __ldcg(reinterpret_cast<const int *>(STACKAT(j, sp - 1))));
 							SETI(PF_FLAGS, j, (fl - 256) & ~8);
 						}
 					} else {
@@ -578,6 +584,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 #undef FLDI
 #undef SETI
 #undef STACKAT
+#undef STACKZ
 #undef HDR
 }
 
