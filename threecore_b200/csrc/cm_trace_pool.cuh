@@ -153,6 +153,27 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 	bool supply = true;                   // warp-uniform
 	unsigned cNodes = 0, cLeafs = 0, cBrushRefs = 0, cBrushBounds = 0, cBrushSides = 0, cCross = 0, cSplits = 0, cTraces = 0;
 
+	// Return to the pending far half of a split (cm_trace.c:449, 516-537): the new step kind of item j.  PM_POP again
+	// when the half is already behind the nearest hit -- the next one is tried in a later round.
+	auto popHalf = [&](const int j) -> int {
+		const int fl = FLDI(PF_FLAGS, j);
+		const int sp = (fl >> 8) & 0xff;
+		if (sp == 0) return PM_DONE;
+		const float4 *sp4 = STACKAT(j, sp - 1);
+		const unsigned long long keep = l2KeepPolicy();
+		const float4 t0 = ldKeep(&sp4[0], keep), t1 = ldKeep(&sp4[1], keep);
+		const float t2x = ldKeepF(STACKZ(j, sp - 1), keep);
+		SETI(PF_FLAGS, j, fl - 256);
+		if (FLD(PF_FRACTION, j) <= t0.y) return PM_POP;            // cm_trace.c:449: already hit something nearer
+		FLD(PF_F1, j) = t0.y; FLD(PF_F2, j) = t0.z;
+		FLD(PF_AX, j) = t0.w; FLD(PF_AY, j) = t1.x; FLD(PF_AZ, j) = t1.y;
+		FLD(PF_BX, j) = t1.z; FLD(PF_BY, j) = t1.w; FLD(PF_BZ, j) = t2x;
+		const int c = __float_as_int(t0.x);
+		if (c < 0) { SETI(PF_CUR, j, -1 - c); if (COUNT) cLeafs++; return PM_LEAF; }
+		SETI(PF_CUR, j, c);
+		return PM_NODE;
+	};
+
 	for (;;) {
 		// ---------------- vote: which kind of step can the most lanes run? ------------------
 		// How many lanes own an item waiting for each kind: the presence bits of a lane are spread into byte-wide
@@ -354,25 +375,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			// ---------------- return to the pending far half of a split -----------------
 			const int j = firstInMode<K>(modes, PM_POP);
 			if (j >= 0) {
-				const int fl = FLDI(PF_FLAGS, j);
-				const int sp = (fl >> 8) & 0xff;
-				if (sp == 0) {
-					modes = withMode(modes, j, PM_DONE);
-				} else {
-					const float4 *sp4 = STACKAT(j, sp - 1);
-					const unsigned long long keep = l2KeepPolicy();
-					const float4 t0 = ldKeep(&sp4[0], keep), t1 = ldKeep(&sp4[1], keep);
-					const float t2x = ldKeepF(STACKZ(j, sp - 1), keep);
-					SETI(PF_FLAGS, j, fl - 256);
-					if (!(FLD(PF_FRACTION, j) <= t0.y)) {              // cm_trace.c:449: already hit something nearer
-						FLD(PF_F1, j) = t0.y; FLD(PF_F2, j) = t0.z;
-						FLD(PF_AX, j) = t0.w; FLD(PF_AY, j) = t1.x; FLD(PF_AZ, j) = t1.y;
-						FLD(PF_BX, j) = t1.z; FLD(PF_BY, j) = t1.w; FLD(PF_BZ, j) = t2x;
-						const int c = __float_as_int(t0.x);
-						if (c < 0) { SETI(PF_CUR, j, -1 - c); modes = withMode(modes, j, PM_LEAF); if (COUNT) cLeafs++; }
-						else { SETI(PF_CUR, j, c); modes = withMode(modes, j, PM_NODE); }
-					}
-				}
+				const int m = popHalf(j);
+				if (m != PM_POP) modes = withMode(modes, j, m);
 			}
 		}
 		if (cSplit >= thr) {
