@@ -345,3 +345,48 @@ def test_unknown_option_is_refused(eng):
     with pytest.raises(CMGPUError) as ex:
         eng.set_option("no_such_knob", 1)
     assert ex.value.code == 1
+
+
+def test_node_tables_per_hull_and_per_map(eng, big):
+    """the pool kernel keeps one node threshold table per (map, hull): more hulls than the cache holds, the first hull
+    again after it was dropped, a hull with a zero extent, and another map in between -- always the general kernel's bytes"""
+    import torch
+    n = 1 << 20
+    dev = big["ds"].device
+    eng.load_bsp(big["m"].data)
+    rng = np.random.default_rng(77)
+    hulls = [(bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS), (None, None),
+             (np.array([-8, -8, 0], np.float32), np.array([8, 8, 0], np.float32))]
+    hulls += [(-rng.uniform(1, 40, 3).astype(np.float32), rng.uniform(1, 40, 3).astype(np.float32)) for _ in range(8)]
+    hulls.append(hulls[0])
+
+    def run(h, **opts):
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        o = torch.empty((n, 56), dtype=torch.uint8, device=dev)
+        eng.box_trace_device(big["ds"][:n], big["de"][:n], h[0], h[1], bspgen.MASK_PLAYERSOLID, o)
+        torch.cuda.synchronize()
+        eng.check_status()
+        return o
+
+    try:
+        for i, h in enumerate(hulls):
+            got = run(h, fast=1)
+            want = run(h, fast=0)
+            assert torch.equal(got, want), f"hull {i}"
+            if i == 5:                                   # another map, then back: the tables of the first load are gone
+                m2 = get_map("arena_small")
+                eng.load_bsp(m2.data)
+                s2, e2 = bspgen.make_sweeps(m2, n, 5)
+                a, b = torch.from_numpy(s2).to(dev), torch.from_numpy(e2).to(dev)
+                o1 = torch.empty((n, 56), dtype=torch.uint8, device=dev)
+                o2 = torch.empty((n, 56), dtype=torch.uint8, device=dev)
+                eng.set_option("fast", 1)
+                eng.box_trace_device(a, b, h[0], h[1], bspgen.MASK_PLAYERSOLID, o1)
+                eng.set_option("fast", 0)
+                eng.box_trace_device(a, b, h[0], h[1], bspgen.MASK_PLAYERSOLID, o2)
+                torch.cuda.synchronize()
+                assert torch.equal(o1, o2), "second map"
+                eng.load_bsp(big["m"].data)
+    finally:
+        eng.set_option("fast", 1)
