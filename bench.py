@@ -304,10 +304,13 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        l2_peak = 2 * nb / (best * 1e-3) / 1e9
+        l2_copy = 2 * nb / (best * 1e-3) / 1e9
         del a, b
+        l2_peak = eng.measure_l2_read(nb, 50)           # the walk reads: its ceiling is the rate at which SMs read L2
         l2 = {"bytes_per_trace": l2_bytes / max(c["traces"], 1), "peak": l2_peak, "unit": "GB/s",
-              "peak_source": "measured here: copy of a 24 MiB buffer that stays in L2, read+write bytes, best of 30",
+              "peak_source": "measured here: cmgpu_measure_l2_read, 50 sweeps of 16-byte loads over a 24 MiB buffer that stays in L2, "
+                             "best of 4 timed launches",
+              "l2_copy_gbs": l2_copy,   # a torch copy of the same buffer, read+write bytes (the earlier denominator)
               "visits_per_trace": {k: c[k] / max(c["traces"], 1) for k in ("nodes", "leafs", "brushRefs", "brushBounds", "brushSides", "splits")}}
 
     if rank == 0:

@@ -314,6 +314,9 @@ unsigned long long cmgpu_launch_count(const cmgpu_ctx *ctx);
  * sum of their durations and how many there were, and starts a new measurement. */
 int cmgpu_kernel_timing(cmgpu_ctx *ctx, int enable);
 int cmgpu_kernel_time_ms(cmgpu_ctx *ctx, double *total_ms, int *launches);
+/* The denominator of the L2 working-set roofline: GB/s at which this GPU's SMs can READ a buffer of `bytes` that stays in
+ * L2 (16-byte loads, `passes` sweeps inside one kernel, CUDA-event timed).  bytes <= 64 MiB. */
+int cmgpu_measure_l2_read(cmgpu_ctx *ctx, size_t bytes, int passes, double *gbs);
 
 /* ---- multi-GPU: a result buffer shared by the processes of one node ------------
  * One process per GPU.  The rank that wants all records allocates the buffer (cmgpu_ipc_alloc) and

@@ -2017,4 +2017,40 @@ int cmgpu_visible_from_points_batch(cmgpu_ctx *ctx, int nViews, const float *ori
 	return CMGPU_OK;
 }
 
+int cmgpu_measure_l2_read(cmgpu_ctx *ctx, size_t bytes, int passes, double *gbs) {
+	if (!ctx || !gbs || bytes < 4096 || bytes > ((size_t)64 << 20) || passes < 1) return ctx ? fail(ctx, CMGPU_ERR_INVALID, "cmgpu_measure_l2_read: bad argument") : CMGPU_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	void *buf = nullptr;
+	CUDA_TRY(ctx, cudaMalloc(&buf, bytes + 16));
+	cudaEvent_t a = nullptr, b = nullptr;
+	cudaDeviceProp prop;
+	bool ok = cudaMemset(buf, 0, bytes + 16) == cudaSuccess && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess &&
+	          cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess;
+	float best = 0.0f;
+	if (ok) {
+		const size_t n16 = bytes / 16;
+		uint4 *sink = (uint4 *)((char *)buf + n16 * 16);
+		const int grid = prop.multiProcessorCount * 8;
+		cudaStream_t s = ctx->streams[0];
+		for (int rep = 0; rep < 6 && ok; rep++) {            // the first repetitions also bring the buffer into L2
+			ok = cudaEventRecord(a, s) == cudaSuccess;
+			l2ReadKernel<<<grid, 256, 0, s>>>((const uint4 *)buf, n16, passes, sink);
+			ok = ok && cudaEventRecord(b, s) == cudaSuccess && cudaEventSynchronize(b) == cudaSuccess;
+			float ms = 0.0f;
+			ok = ok && cudaEventElapsedTime(&ms, a, b) == cudaSuccess;
+			if (ok && rep >= 2 && ms > 0.0f) {
+				const float rate = (float)((double)n16 * 16.0 * passes / (ms * 1e-3) / 1e9);
+				if (rate > best) best = rate;
+			}
+		}
+		ctx->launches += 6;
+	}
+	if (a) cudaEventDestroy(a);
+	if (b) cudaEventDestroy(b);
+	cudaFree(buf);
+	if (!ok) return fail(ctx, CMGPU_ERR_CUDA, "cmgpu_measure_l2_read: %s", cudaGetErrorString(cudaGetLastError()));
+	*gbs = best;
+	return CMGPU_OK;
+}
+
 }  // extern "C"

@@ -1228,6 +1228,20 @@ __global__ void __launch_bounds__(256) binScanKernel(unsigned *hist, int numBins
 	}
 }
 
+// ---- L2 read rate (the denominator of the L2 working-set roofline) --------------------------------------------
+// every thread sweeps the buffer `passes` times with 16-byte loads, grid-strided; the xor keeps the loads alive
+__global__ void __launch_bounds__(256) l2ReadKernel(const uint4 *buf, size_t n16, int passes, uint4 *sink) {
+	uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (int p = 0; p < passes; p++) {
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+			const uint4 v = __ldcg(&buf[i]);
+			acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+		}
+	}
+	if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = acc;      // never true for a zeroed buffer; defeats dead-code removal
+}
+
 // pass 3: every item takes the next slot of its bin and leaves its ray there
 // (keys[i] becomes the item's slot: what expandRecordsKernel needs to find the item's result again)
 __global__ void __launch_bounds__(256) binScatterKernel(int n, const float *starts, const float *ends, unsigned *keys,

@@ -152,6 +152,7 @@ def load_library() -> C.CDLL:
     lib.cmgpu_sv_last_candidates.argtypes = [vp]
     lib.cmgpu_sv_last_candidates.restype = C.c_ulonglong
     lib.cmgpu_rotation_matrices.restype = None
+    lib.cmgpu_measure_l2_read.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     lib.cmgpu_point_leafnum_batch.argtypes = [vp, C.c_int, vp, vp]
     lib.cmgpu_box_leafnums_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
     lib.cmgpu_point_leafnum_batch_device.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -369,6 +370,12 @@ class Engine:
         ms, n = C.c_double(), C.c_int()
         self._check(self.lib.cmgpu_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def measure_l2_read(self, nbytes=24 << 20, passes=50) -> float:
+        """GB/s at which the SMs read an L2-resident buffer (denominator of bench.py's roofline.l2)"""
+        g = C.c_double()
+        self._check(self.lib.cmgpu_measure_l2_read(self.h, int(nbytes), int(passes), C.byref(g)))
+        return float(g.value)
 
     def enable_counters(self, on=True):
         self._check(self.lib.cmgpu_enable_counters(self.h, int(bool(on))))
