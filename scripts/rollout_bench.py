@@ -1,7 +1,8 @@
 """BASELINE config 5 numbers: 65,536 agents x 10 traces/tick on a 50k-brush arena.
 
     python scripts/rollout_bench.py [agents] [ticks]                                   one GPU
-    torchrun --nproc-per-node N ... scripts/rollout_bench.py [agents] [ticks] [weak]   agents sharded by id over N GPUs
+    torchrun --nproc-per-node N ... scripts/rollout_bench.py [agents] [ticks] [weak] [graph]   agents sharded by id over N GPUs;
+                                                                                       graph: the tick replayed as a CUDA graph
                                                                                        (weak: `agents` per GPU)
 The BSP is replicated, every rank steps its own agents (Rollout(first_agent=...)), there is no exchange inside a tick;
 the time of a run is the slowest rank's (CUDA events, max over ranks)."""
@@ -16,7 +17,8 @@ from threecore_b200.sharding import shard_range
 
 agents = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-weak = len(sys.argv) > 3 and sys.argv[3] == "weak"
+weak = "weak" in sys.argv[3:]
+graph = "graph" in sys.argv[3:]
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 if world > 1:
     import torch.distributed as dist
@@ -31,6 +33,8 @@ if rank == 0:
 eng = Engine(local); eng.load_bsp(m.data)
 r = Rollout(eng, hi - lo, m.world_mins, m.world_maxs, seed=5, first_agent=lo)
 r.run(5); torch.cuda.synchronize()
+if graph:
+    r.capture()
 if world > 1:
     dist.barrier()
 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
@@ -44,7 +48,7 @@ if world > 1:
     dist.all_reduce(n, op=dist.ReduceOp.SUM)
 ms, n = float(ms.item()), float(n.item())
 if rank == 0:
-    print(f"agents {total} on {world} GPU(s) ({'weak' if weak else 'strong'} scaling), ticks {ticks}: {ms/ticks:.3f} ms/tick, "
+    print(f"agents {total} on {world} GPU(s) ({'weak' if weak else 'strong'} scaling{', CUDA graph' if graph else ''}), ticks {ticks}: {ms/ticks:.3f} ms/tick, "
           f"{n/ms/1e3:.1f} Mtraces/s, {(r.launches-l0)/ticks:.0f} launches/tick ({TRACES_PER_TICK} traces per agent and tick)", flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -96,6 +96,7 @@ struct cmgpu_ctx_s {
 	int binMinItems = 98304;             // smaller batches are traced in input order (the five binning launches cost ~50 us)
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bCompact, bHist[kBinSlots];
+	bool capturing = false;              // the stream of the current device-pointer call is being captured into a CUDA graph
 	bool twoPhase = true, twoPhaseHost = false, twoPhaseSmall = false, compactByItem = true;
 	// pool kernel: per-hull node threshold tables (nodeThresholdKernel), built on first use, dropped with the map
 	struct HullTable { NodeHull key; DevBuf buf; bool usable; };
@@ -154,6 +155,8 @@ int fail(cmgpu_ctx *ctx, int code, const char *fmt, ...) {
 
 int reserve(cmgpu_ctx *ctx, DevBuf &b, size_t bytes) {
 	if (bytes <= b.cap) return CMGPU_OK;
+	if (ctx->capturing)                              // cudaFree / cudaMalloc are not allowed while a stream is being captured
+		return fail(ctx, CMGPU_ERR_INVALID, "a workspace would have to grow during stream capture: run the same call once before capturing it");
 	if (b.p) cudaFree(b.p);                      // cudaFree synchronises the device: nothing is still reading the old block
 	b.p = nullptr;
 	b.cap = 0;
@@ -682,6 +685,7 @@ const int4 *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStream_t s) {
 	for (auto &t : ctx->hullTables) {
 		if (!memcmp(&t.key, &key, sizeof(key))) return t.usable ? (const int4 *)t.buf.p : nullptr;
 	}
+	if (ctx->capturing) return nullptr;                   // building synchronises: not inside a capture (plain node step instead)
 	if (ctx->hullTables.size() >= 8) {                    // a ninth hull: start over (nothing may still read the old tables)
 		cudaDeviceSynchronize();
 		for (auto &t : ctx->hullTables) releaseBuf(t.buf);
@@ -715,7 +719,17 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	q.compact = nullptr;
 	const int arenaSlot = histSlot < 0 ? kBinSlots : histSlot;
 	const bool external = histSlot < 0;              // device-pointer call on the caller's stream
-	if (external && ctx->extBusy && ctx->extStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->extDone, 0));
+	// A call on a stream that is being captured (CUDA graph of a rollout tick, a server frame) only records work:
+	// no allocation, no event bookkeeping with the host-pointer calls, no timing.  The captured launches use the
+	// workspaces as they are, so the caller keeps graph replays and other calls on this context in stream order.
+	struct CaptureScope { cmgpu_ctx *c; ~CaptureScope() { c->capturing = false; } } captureScope{ctx};
+	{
+		cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+		if (external && cudaStreamIsCapturing(s, &st) == cudaSuccess) ctx->capturing = st != cudaStreamCaptureStatusNone;
+		else cudaGetLastError();
+	}
+	const bool capturing = ctx->capturing;
+	if (external && !capturing && ctx->extBusy && ctx->extStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->extDone, 0));
 	ctx->map.noCurves = ctx->noCurves;
 	ctx->map.playerCurveClip = ctx->playerCurveClip;
 	if (ctx->binning && q.n >= ctx->binMinItems) {
@@ -784,7 +798,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	if (blocks > resident) blocks = resident;
 	if (blocks < 1) blocks = 1;
 	cudaEvent_t tEnd = nullptr;
-	if (ctx->timing) {
+	if (ctx->timing && !capturing) {
 		if (ctx->timingUsed == ctx->timingPairs.size()) {
 			cudaEvent_t a, b;
 			CUDA_TRY(ctx, cudaEventCreate(&a));
@@ -833,7 +847,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		CUDA_TRY(ctx, cudaGetLastError());
 	}
 	if (tEnd) CUDA_TRY(ctx, cudaEventRecord(tEnd, s));     // the bracket covers both phases: walk + record expansion
-	if (external) {
+	if (external && !capturing) {
 		CUDA_TRY(ctx, cudaEventRecord(ctx->extDone, s));
 		ctx->extStream = s;
 		ctx->extBusy = true;

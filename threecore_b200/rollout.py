@@ -117,9 +117,40 @@ class Rollout:
         f, landed, nrm, ss = _fields(rec)
         take = (f < 1.0) & (nrm[:, 2] > 0.7) & (ss == 0) & on_ground
         o = torch.where(take[:, None], landed, o)
-        self.origin, self.velocity = o.contiguous(), v.contiguous()
+        # in place: origin and velocity are the static tensors a captured tick (capture()) reads and writes
+        self.origin.copy_(o)
+        self.velocity.copy_(v)
+
+    def capture(self, warmup: int = 3):
+        """Record one tick -- its eight trace launches and the kinematics between them, some seventy kernels -- as a CUDA
+        graph; run() then replays it.  A tick is a chain of small dependent launches, so issued one by one it is bound
+        by launch latency, not by the GPU.  `warmup` eager ticks come first (they size the engine's workspaces: nothing
+        may be allocated while the stream is being captured) and advance the agents like any other tick."""
+        assert self.record is None, "recording needs the eager path"
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.tick()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        t0, l0 = self.traces, self.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.tick()
+        self._tick_counts = (self.traces - t0, self.launches - l0)
+        self.traces, self.launches = t0, l0              # capturing executed nothing
+        self._graph = g
+        return self
 
     def run(self, ticks: int):
+        g = getattr(self, "_graph", None)
         for _ in range(ticks):
-            self.tick()
+            if g is None:
+                self.tick()
+            else:
+                g.replay()
+                self.traces += self._tick_counts[0]
+                self.launches += self._tick_counts[1]
         return self
