@@ -183,7 +183,8 @@ int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
  * (NULL = default stream).  The call only enqueues work.  rotations: [n][9] row-major rotation matrices
  * (CreateRotationMatrix, cm_trace.c:65-68) with rot_index[i] == -1 for an
  * unrotated item; build them with cmgpu_rotation_matrices on the host.      * The _device calls may be issued on a stream that is being captured into a CUDA graph: they then allocate nothing
- * (a workspace that would have to grow is CMGPU_ERR_INVALID: run the call once before capturing it) and record no events.
+ * (a workspace that would have to grow is CMGPU_ERR_INVALID: run the call once before capturing it) and record no events.  (Not cmgpu_sv_trace_batch_device / cmgpu_sv_point_contents_batch_device: they read a count back between
+ * their passes.)
  */
 int cmgpu_box_trace_batch_device(cmgpu_ctx *ctx, int n,
                           const float *starts, const float *ends,
