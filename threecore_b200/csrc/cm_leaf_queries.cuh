@@ -173,16 +173,20 @@ __global__ void __launch_bounds__(128) visibleFromPointsKernel(const VisBatch q)
 			// CM_ClusterPVS, cm_test.c:306-312: a cluster out of range reads row 0
 			const unsigned char *row = nullptr;
 			if (q.vis) row = q.vis + ((ca.x < 0 || ca.x >= q.numClusters) ? (size_t)0 : (size_t)ca.x * q.clusterBytes);
+			// (the records come from the caller: a cluster number beyond the row reads as "not set" instead of reading past it)
+			const unsigned rowBits = 8u * (unsigned)q.clusterBytes;
+			const int nn = n < kMaxEntClusters ? n : kMaxEntClusters;
 			int k, l = 0;
-			for (k = 0; k < n; k++) {
+			for (k = 0; k < nn; k++) {
 				l = __ldg(ent + 5 + k);
-				if (!row || (__ldg(&row[l >> 3]) & (1 << (l & 7)))) break;
+				if (!row || ((unsigned)l < rowBits && (__ldg(&row[l >> 3]) & (1 << (l & 7))))) break;
 			}
 			visible = true;
-			if (k == n) {
+			if (k == nn) {
 				if (lastCluster) {                           // the overflow range, sv_snapshot.c:347-353 as written
-					for (; l <= lastCluster; l++) {
-						if (!row || (__ldg(&row[l >> 3]) & (1 << (l & 7)))) break;
+					const int lastScan = (unsigned)lastCluster < rowBits ? lastCluster : (int)rowBits;   // nothing is set beyond the row
+					for (; l <= lastScan; l++) {
+						if (!row || ((unsigned)l < rowBits && (__ldg(&row[l >> 3]) & (1 << (l & 7))))) break;
 					}
 					if (l == lastCluster) visible = false;
 				} else {

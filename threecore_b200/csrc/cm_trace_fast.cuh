@@ -397,7 +397,7 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 constexpr int kExpandBlock = 256;
 __global__ void __launch_bounds__(kExpandBlock) expandRecordsKernel(const FastMap fm, int n, const unsigned *slotOf, const uint4 *compact,
                                                                     const float *starts, const float *ends, uint2 *out, int *hitIds) {
-	__shared__ uint2 rec[kExpandBlock * 7];
+	__shared__ __align__(16) uint2 rec[kExpandBlock * 7];       // read back as uint4
 	const int base = blockIdx.x * kExpandBlock;
 	const int i = base + threadIdx.x;
 	if (i < n) {
