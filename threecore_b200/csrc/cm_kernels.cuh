@@ -1251,8 +1251,10 @@ __global__ void __launch_bounds__(256) binScatterKernel(int n, const float *star
 	const size_t o = 3 * (size_t)i;
 	const unsigned slot = atomicAdd(&hist[keys[i]], 1u);
 	keys[i] = slot;
-	recs[2 * (size_t)slot] = make_float4(starts[o], starts[o + 1], starts[o + 2], __int_as_float(i));
-	recs[2 * (size_t)slot + 1] = make_float4(ends[o], ends[o + 1], ends[o + 2], 0.0f);
+	// the 32-byte record in one store: a whole sector at once
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+	             :: "l"(&recs[2 * (size_t)slot]), "f"(starts[o]), "f"(starts[o + 1]), "f"(starts[o + 2]), "f"(__int_as_float(i)),
+	                "f"(ends[o]), "f"(ends[o + 1]), "f"(ends[o + 2]), "f"(0.0f) : "memory");
 }
 
 }  // namespace cmgpu

@@ -88,6 +88,33 @@ __device__ __forceinline__ float4 ldKeep(const float4 *p, const unsigned long lo
 	return v;
 }
 
+// ---- 32-byte records in ONE access (sm_100 has 256-bit global loads and stores: LDG/STG.E.ENL2.256) ----------------
+// Leaf-stream entries, brush records, binned rays and stack entries are 32 bytes on 32-byte boundaries; two 16-byte
+// accesses touch the same sector twice, and a divergent warp pays for every sector it touches.
+struct Pair4 { float4 a, b; };
+__device__ __forceinline__ Pair4 ldg32(const float4 *p) {              // read-only path
+	Pair4 r;
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ Pair4 ldcs32(const float4 *p) {             // streaming (evict first)
+	Pair4 r;
+	asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ Pair4 ldKeep32B(const float4 *p, const unsigned long long pol) {
+	Pair4 r;
+	asm volatile("ld.global.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p), "l"(pol) : "memory");
+	return r;
+}
+__device__ __forceinline__ void stKeep32B(float4 *p, const float4 a, const float4 b, const unsigned long long pol) {
+	asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+	             :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ float ldKeepF(const float *p, const unsigned long long pol) {
 	float v;
 	asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
@@ -219,8 +246,8 @@ __device__ __forceinline__ EnterLeave exactEnterLeave(const FastMap &fm, const F
 // CM_TraceThroughBrush (cm_trace.c:261-363) for brush b.  Returns true when the trace is over (fraction 0).
 template <bool COUNT>
 __device__ __forceinline__ bool clipBrushFast(const FastMap &fm, const FastHull &h, FastLane &L, const int b) {
-	const float4 r0 = __ldg(&fm.brushRec[2 * b]);
-	const float4 r1 = __ldg(&fm.brushRec[2 * b + 1]);
+	const Pair4 rr = ldg32(&fm.brushRec[2 * b]);
+	const float4 r0 = rr.a, r1 = rr.b;
 	const int firstSide = __float_as_int(r0.w);
 	const int ns = __float_as_int(r1.w) & 0xffffff;
 	const bool canonical = (__float_as_int(r1.w) >> 30) & 1;
@@ -300,7 +327,8 @@ template <bool COUNT>
 __device__ __forceinline__ int beginFast(const TraceBatch &q, const FastHull &h, FastLane &L, const int slot) {
 	float s0x, s0y, s0z, e0x, e0y, e0z;
 	if (q.recs) {
-		const float4 a = __ldcs(&q.recs[2 * (size_t)slot]), b = __ldcs(&q.recs[2 * (size_t)slot + 1]);
+		const Pair4 ab = ldcs32(&q.recs[2 * (size_t)slot]);
+		const float4 a = ab.a, b = ab.b;
 		s0x = a.x; s0y = a.y; s0z = a.z; e0x = b.x; e0y = b.y; e0z = b.z;
 		L.item = __float_as_int(a.w);
 	} else {
@@ -342,7 +370,8 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 	}
 	float s0x, s0y, s0z, e0x, e0y, e0z;
 	if (q.recs) {
-		const float4 a = __ldcs(&q.recs[2 * (size_t)i]), b = __ldcs(&q.recs[2 * (size_t)i + 1]);
+		const Pair4 ab = ldcs32(&q.recs[2 * (size_t)i]);
+		const float4 a = ab.a, b = ab.b;
 		s0x = a.x; s0y = a.y; s0z = a.z; e0x = b.x; e0y = b.y; e0z = b.z;
 		i = __float_as_int(a.w);
 	} else {
@@ -543,8 +572,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			if (mode == FM_NODE) {
 				t0 = __ldg(reinterpret_cast<const float4 *>(&fm.nodes[L.num]));
 			} else if (mode == FM_LEAF) {
-				t0 = __ldg(&fm.stream[2 * L.k]);
-				t1 = __ldg(&fm.stream[2 * L.k + 1]);
+				{ const Pair4 ee = ldg32(&fm.stream[2 * L.k]); t0 = ee.a; t1 = ee.b; }
 			} else if (mode == FM_POP && L.sp > 0) {
 				const float4 *sp4 = reinterpret_cast<const float4 *>(stackAt(L.sp - 1));
 				t0 = __ldcg(&sp4[0]); t1 = __ldcg(&sp4[1]); t2 = __ldcg(&sp4[2]);
@@ -714,8 +742,8 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					}
 				}
 			} else if (mode == FM_PLEAF) {
-				const float4 e0 = __ldg(&fm.stream[2 * L.k]);
-				const float4 e1 = __ldg(&fm.stream[2 * L.k + 1]);
+				const Pair4 ee = ldg32(&fm.stream[2 * L.k]);
+				const float4 e0 = ee.a, e1 = ee.b;
 				L.k++;
 				const int b = __float_as_int(e1.w);
 				if (b < 0) {
@@ -725,8 +753,8 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					if (COUNT) L.cBrushRefs++;
 					const int contents = __float_as_int(e0.w);
 					if (contents & h.mask) {
-						const float4 r0 = __ldg(&fm.brushRec[2 * b]);
-						const float4 r1 = __ldg(&fm.brushRec[2 * b + 1]);
+						const Pair4 rr = ldg32(&fm.brushRec[2 * b]);
+						const float4 r0 = rr.a, r1 = rr.b;
 						const int firstSide = __float_as_int(r0.w);
 						const int ns = __float_as_int(r1.w) & 0xffffff;
 						if (ns > 0) {

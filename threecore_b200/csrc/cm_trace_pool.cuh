@@ -161,7 +161,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 		if (sp == 0) return PM_DONE;
 		const float4 *sp4 = STACKAT(j, sp - 1);
 		const unsigned long long keep = l2KeepPolicy();
-		const float4 t0 = ldKeep(&sp4[0], keep), t1 = ldKeep(&sp4[1], keep);
+		const Pair4 tt = ldKeep32B(sp4, keep);
+		const float4 t0 = tt.a, t1 = tt.b;
 		const float t2x = ldKeepF(STACKZ(j, sp - 1), keep);
 		SETI(PF_FLAGS, j, fl - 256);
 		if (FLD(PF_FRACTION, j) <= t0.y) return PM_POP;            // cm_trace.c:449: already hit something nearer
@@ -320,8 +321,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					float4 e0[kLeafEntries], e1[kLeafEntries];
 					#pragma unroll
 					for (int i = 0; i < kLeafEntries; i++) {
-						e0[i] = __ldg(&fm.stream[2 * (k + i)]);
-						e1[i] = __ldg(&fm.stream[2 * (k + i) + 1]);
+						const Pair4 ee = ldg32(&fm.stream[2 * (k + i)]);
+						e0[i] = ee.a; e1[i] = ee.b;
 					}
 					const int last0 = FLDI(PF_LAST0, j);
 #if CMGPU_POOL_LAST2
@@ -362,8 +363,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			const int j = firstInMode<K>(modes, PM_SLAB);
 			if (j >= 0) {
 				const int k = FLDI(PF_CUR, j) - 1;
-				const float4 e0 = __ldg(&fm.stream[2 * k]);
-				const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
+				const Pair4 ee = ldg32(&fm.stream[2 * k]);
+				const float4 e0 = ee.a, e1 = ee.b;
 				FastLane L;
 				L.sx = FLD(PF_SX, j); L.sy = FLD(PF_SY, j); L.sz = FLD(PF_SZ, j);
 				L.ex = FLD(PF_EX, j); L.ey = FLD(PF_EY, j); L.ez = FLD(PF_EZ, j);
@@ -421,8 +422,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					if (sp < kPoolDepth) {
 						float4 *sp4 = STACKAT(j, sp);
 						const unsigned long long keep = l2KeepPolicy();
-						stKeep(&sp4[0], make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)), keep);
-						stKeep(&sp4[1], make_float4(ay_ + ffar * (by_ - ay_), az_ + ffar * (bz_ - az_), bx_, by_), keep);
+						stKeep32B(sp4, make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)),
+						          make_float4(ay_ + ffar * (by_ - ay_), az_ + ffar * (bz_ - az_), bx_, by_), keep);
 						stKeep32(reinterpret_cast<int *>(STACKZ(j, sp)), __float_as_int(bz_), keep);
 						SETI(PF_FLAGS, j, fl + 256);
 					} else {
@@ -521,8 +522,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					}
 				} else if (j >= 0) {
 					const int k = FLDI(PF_CUR, j);
-					const float4 e0 = __ldg(&fm.stream[2 * k]);
-					const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
+					const Pair4 ee = ldg32(&fm.stream[2 * k]);
+					const float4 e0 = ee.a, e1 = ee.b;
 					SETI(PF_CUR, j, k + 1);
 					const int b = __float_as_int(e1.w);
 					if (b < 0) {
@@ -538,8 +539,8 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						if (COUNT) cBrushRefs++;
 						const int contents = __float_as_int(e0.w);
 						if (contents & h.mask) {
-							const float4 r0 = __ldg(&fm.brushRec[2 * b]);
-							const float4 r1 = __ldg(&fm.brushRec[2 * b + 1]);
+							const Pair4 rr = ldg32(&fm.brushRec[2 * b]);
+							const float4 r0 = rr.a, r1 = rr.b;
 							const int firstSide = __float_as_int(r0.w);
 							const int ns = __float_as_int(r1.w) & 0xffffff;
 							if (ns > 0) {

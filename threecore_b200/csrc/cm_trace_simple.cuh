@@ -59,14 +59,14 @@ traceSimpleKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			found++;
 			if (COUNT) L.cLeafs++;
 			for (int k = -1 - c; ; k++) {
-				const float4 e0 = __ldg(&fm.stream[2 * k]);
-				const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
+				const Pair4 ee = ldg32(&fm.stream[2 * k]);
+				const float4 e0 = ee.a, e1 = ee.b;
 				const int b = __float_as_int(e1.w);
 				if (b < 0) break;
 				if (COUNT) L.cBrushRefs++;
 				if (!(__float_as_int(e0.w) & h.mask)) continue;
-				const float4 r0 = __ldg(&fm.brushRec[2 * b]);
-				const float4 r1 = __ldg(&fm.brushRec[2 * b + 1]);
+				const Pair4 rr = ldg32(&fm.brushRec[2 * b]);
+				const float4 r0 = rr.a, r1 = rr.b;
 				const int firstSide = __float_as_int(r0.w);
 				const int ns = __float_as_int(r1.w) & 0xffffff;
 				if (ns == 0) continue;
@@ -151,8 +151,8 @@ traceSimpleKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 			if (COUNT) L.cLeafs++;
 			bool over = false;
 			for (int k = -1 - c; ; k++) {
-				const float4 e0 = __ldg(&fm.stream[2 * k]);
-				const float4 e1 = __ldg(&fm.stream[2 * k + 1]);
+				const Pair4 ee = ldg32(&fm.stream[2 * k]);
+				const float4 e0 = ee.a, e1 = ee.b;
 				const int b = __float_as_int(e1.w);
 				if (b < 0) break;
 				if (COUNT) L.cBrushRefs++;
