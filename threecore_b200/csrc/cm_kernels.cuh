@@ -74,6 +74,33 @@ struct Counters {
 };
 
 // ---- one batch ----------------------------------------------------------------
+// ---- 32-byte records in ONE access (sm_100 has 256-bit global loads and stores: LDG/STG.E.ENL2.256) ----------------
+// Leaf-stream entries, brush records, binned rays and stack entries are 32 bytes on 32-byte boundaries; two 16-byte
+// accesses touch the same sector twice, and a divergent warp pays for every sector it touches.
+struct Pair4 { float4 a, b; };
+__device__ __forceinline__ Pair4 ldg32(const float4 *p) {              // read-only path
+	Pair4 r;
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ Pair4 ldcs32(const float4 *p) {             // streaming (evict first)
+	Pair4 r;
+	asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ Pair4 ldKeep32B(const float4 *p, const unsigned long long pol) {
+	Pair4 r;
+	asm volatile("ld.global.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p), "l"(pol) : "memory");
+	return r;
+}
+__device__ __forceinline__ void stKeep32B(float4 *p, const float4 a, const float4 b, const unsigned long long pol) {
+	asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+	             :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
+}
+
 struct TraceBatch {
 	int n;
 	const float *starts, *ends;          // [n][3]
@@ -488,7 +515,8 @@ __device__ __forceinline__ int beginItem(const DevMap &m, const TraceBatch &q, L
 	int i = slot;
 	float s0x, s0y, s0z, e0x, e0y, e0z;
 	if (q.recs) {
-		const float4 a = __ldcs(&q.recs[2 * (size_t)slot]), b = __ldcs(&q.recs[2 * (size_t)slot + 1]);
+		const Pair4 ab = ldcs32(&q.recs[2 * (size_t)slot]);
+		const float4 a = ab.a, b = ab.b;
 		s0x = a.x; s0y = a.y; s0z = a.z; e0x = b.x; e0y = b.y; e0z = b.z;
 		i = __float_as_int(a.w);
 	} else {
@@ -731,8 +759,8 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 				if (L.k >= L.kEnd) {
 					mode = (L.ps < L.psEnd && !m.noCurves) ? M_PATCH : popSegment(L, stack);
 				} else {
-					const float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
-					const float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
+					const Pair4 bb = ldg32(&m.leafBrushBox[2 * L.k]);
+					const float4 bmn = bb.a, bmx = bb.b;
 					L.k++;
 					Cnt<COUNT>::add(L.cBrushRefs);
 					if (__float_as_int(bmn.w) & L.mask) {
@@ -802,8 +830,8 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 		// ---------------- clip against the brush at entry k-1: CM_TraceThroughBrush, cm_trace.c:261-363 (heavy) -----
 		if (nBrush > 0 && nBrush >= gang) {
 			if (mode == M_BRUSH) {
-				float4 bmn = __ldg(&m.leafBrushBox[2 * (L.k - 1)]);
-				float4 bmx = __ldg(&m.leafBrushBox[2 * (L.k - 1) + 1]);
+				const Pair4 bb = ldg32(&m.leafBrushBox[2 * (L.k - 1)]);
+				float4 bmn = bb.a, bmx = bb.b;
 				const int contents = __float_as_int(bmn.w);
 				const int b = __float_as_int(bmx.w);
 				const bool boxBrush = (L.flags & F_BOX) && b == m.boxBrush;
@@ -905,8 +933,8 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 					const int4 pa = __ldg(&m.patchInfo[2 * p]);
 					if (pa.y & L.mask) {
 						// CM_TraceThroughPatchCollide starts with CM_BoundsIntersect (cm_patch.c:1376-1381)
-						const float4 bmn = __ldg(&m.patchBox[2 * p]);
-						const float4 bmx = __ldg(&m.patchBox[2 * p + 1]);
+						const Pair4 bb = ldg32(&m.patchBox[2 * p]);
+						const float4 bmn = bb.a, bmx = bb.b;
 						const bool apart = L.hix < bmn.x - kBoundsEps || L.hiy < bmn.y - kBoundsEps || L.hiz < bmn.z - kBoundsEps ||
 						                   L.lox > bmx.x + kBoundsEps || L.loy > bmx.y + kBoundsEps || L.loz > bmx.z + kBoundsEps;
 						// a point sweep only clips against curves with cm_playerCurveClip set (cm_patch.c:1234)
@@ -981,8 +1009,8 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 		// ---------------- CM_TestInLeaf / CM_TestBoxInBrush, cm_trace.c:130-183, 83-123 -----------------
 		if (mode == M_PLEAF) {
 			if (L.k < L.kEnd) {
-				float4 bmn = __ldg(&m.leafBrushBox[2 * L.k]);
-				float4 bmx = __ldg(&m.leafBrushBox[2 * L.k + 1]);
+				const Pair4 bb = ldg32(&m.leafBrushBox[2 * L.k]);
+				float4 bmn = bb.a, bmx = bb.b;
 				L.k++;
 				Cnt<COUNT>::add(L.cBrushRefs);
 				const int contents = __float_as_int(bmn.w);
@@ -1089,8 +1117,8 @@ __global__ void __launch_bounds__(128) pointContentsKernel(const DevMap m, const
 	}
 	int contents = 0;
 	for (int k = 0; k < leaf.y; k++) {
-		float4 bmn = __ldg(&m.leafBrushBox[2 * (leaf.x + k)]);
-		float4 bmx = __ldg(&m.leafBrushBox[2 * (leaf.x + k) + 1]);
+		const Pair4 bb = ldg32(&m.leafBrushBox[2 * (leaf.x + k)]);
+		float4 bmn = bb.a, bmx = bb.b;
 		const int b = __float_as_int(bmx.w);
 		const bool boxBrush = isBox && b == m.boxBrush;
 		if (boxBrush) {

@@ -88,33 +88,6 @@ __device__ __forceinline__ float4 ldKeep(const float4 *p, const unsigned long lo
 	return v;
 }
 
-// ---- 32-byte records in ONE access (sm_100 has 256-bit global loads and stores: LDG/STG.E.ENL2.256) ----------------
-// Leaf-stream entries, brush records, binned rays and stack entries are 32 bytes on 32-byte boundaries; two 16-byte
-// accesses touch the same sector twice, and a divergent warp pays for every sector it touches.
-struct Pair4 { float4 a, b; };
-__device__ __forceinline__ Pair4 ldg32(const float4 *p) {              // read-only path
-	Pair4 r;
-	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	    : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
-	return r;
-}
-__device__ __forceinline__ Pair4 ldcs32(const float4 *p) {             // streaming (evict first)
-	Pair4 r;
-	asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p) : "memory");
-	return r;
-}
-__device__ __forceinline__ Pair4 ldKeep32B(const float4 *p, const unsigned long long pol) {
-	Pair4 r;
-	asm volatile("ld.global.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p), "l"(pol) : "memory");
-	return r;
-}
-__device__ __forceinline__ void stKeep32B(float4 *p, const float4 a, const float4 b, const unsigned long long pol) {
-	asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
-	             :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
-}
-
 __device__ __forceinline__ float ldKeepF(const float *p, const unsigned long long pol) {
 	float v;
 	asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
