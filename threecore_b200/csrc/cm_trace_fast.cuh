@@ -399,7 +399,7 @@ __device__ __forceinline__ void finishFast(const FastMap &fm, const TraceBatch &
 constexpr int kExpandBlock = 256;
 __global__ void __launch_bounds__(kExpandBlock) expandRecordsKernel(const FastMap fm, int n, const unsigned *slotOf, const uint4 *compact,
                                                                     const float *starts, const float *ends, uint2 *out, int *hitIds) {
-	__shared__ __align__(16) uint2 rec[kExpandBlock * 7];       // read back as uint4
+	__shared__ __align__(32) uint2 rec[kExpandBlock * 7];       // read back in 32-byte pieces
 	const int base = blockIdx.x * kExpandBlock;
 	const int i = base + threadIdx.x;
 	if (i < n) {
@@ -436,12 +436,22 @@ __global__ void __launch_bounds__(kExpandBlock) expandRecordsKernel(const FastMa
 	}
 	__syncthreads();
 	// kExpandBlock * 56 bytes = 896 16-byte pieces; the block's first record is 16-byte aligned (base * 56)
+	// kExpandBlock * 56 bytes = 448 32-byte pieces when the block is full; the block's first record is 32-byte aligned
+	// when `out` is (base * 56 = blockIdx * 14336), otherwise -- and for the last, partial block -- 8-byte stores
 	const int items = min(kExpandBlock, n - base);
-	const int pieces = (items * 7) >> 1, oddTail = (items * 7) & 1;
-	uint4 *dst = reinterpret_cast<uint4 *>(out + 7 * (size_t)base);
-	const uint4 *src = reinterpret_cast<const uint4 *>(rec);
-	for (int k = threadIdx.x; k < pieces; k += kExpandBlock) __stcs(&dst[k], src[k]);
-	if (oddTail && threadIdx.x == 0) __stcs(&out[7 * (size_t)base + 2 * pieces], rec[2 * pieces]);
+	const int words = items * 7;                                 // 8-byte words
+	uint2 *dst = out + 7 * (size_t)base;
+	int done = 0;
+	if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+		const int pieces = words >> 2;
+		for (int k = threadIdx.x; k < pieces; k += kExpandBlock) {
+			const uint4 a = reinterpret_cast<const uint4 *>(rec)[2 * k], b = reinterpret_cast<const uint4 *>(rec)[2 * k + 1];
+			asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+			             :: "l"(dst + 4 * k), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+		}
+		done = pieces << 2;
+	}
+	for (int k = done + threadIdx.x; k < words; k += kExpandBlock) __stcs(&dst[k], rec[k]);
 }
 
 #ifndef CMGPU_PREFETCH_CHUNK
