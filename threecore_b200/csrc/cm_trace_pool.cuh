@@ -24,7 +24,7 @@ namespace cmgpu {
 #define CMGPU_NODE_LEVELS 3
 #endif
 #ifndef CMGPU_LEAF_ENTRIES
-#define CMGPU_LEAF_ENTRIES 3
+#define CMGPU_LEAF_ENTRIES 4
 #endif
 constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
 constexpr int kLeafEntries = CMGPU_LEAF_ENTRIES;  // stream entries a lane looks at per repeat of the leaf step
