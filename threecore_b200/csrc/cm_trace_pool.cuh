@@ -23,6 +23,9 @@ namespace cmgpu {
 #ifndef CMGPU_NODE_LEVELS
 #define CMGPU_NODE_LEVELS 3
 #endif
+#ifndef CMGPU_INLINE_SLAB
+#define CMGPU_INLINE_SLAB 1
+#endif
 #ifndef CMGPU_LEAF_ENTRIES
 #define CMGPU_LEAF_ENTRIES 4
 #endif
@@ -338,12 +341,25 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const float loz = (sz < ez ? sz : ez) + h.n0[2], hiz = (sz < ez ? ez : sz) + h.p0[2];
 					int adv = 0, b = 0;
 					bool stopped = false, clip = false;
+#if CMGPU_INLINE_SLAB
+					// the float slab pre-test (slabReject) right here, on the entry that is in registers anyway: an entry it
+					// rejects is a certain no-op and the scan goes on, instead of two more rounds (SLAB, then LEAF again)
+					FastLane S;
+					S.sx = sx; S.sy = sy; S.sz = sz; S.ex = ex; S.ey = ey; S.ez = ez;
+					S.fraction = FLD(PF_FRACTION, j);
+					const bool slabOn = (FLDI(PF_FLAGS, j) & 4) != 0;
+#endif
 					#pragma unroll
 					for (int i = 0; i < kLeafEntries; i++) {
 						const int bi = __float_as_int(e1[i].w);
 						const bool want = bi >= 0 && (__float_as_int(e0[i].w) & h.mask) != 0 && bi != last0 && bi != last1;
 						const bool apart = hix < e0[i].x || hiy < e0[i].y || hiz < e0[i].z || lox > e1[i].x || loy > e1[i].y || loz > e1[i].z;
+#if CMGPU_INLINE_SLAB
+						bool clipi = want && !apart;                                   // CM_BoundsIntersect passed
+						if (!stopped && clipi && slabOn && slabReject(h, S, e0[i], e1[i])) clipi = false;
+#else
 						const bool clipi = want && !apart;                             // CM_BoundsIntersect passed
+#endif
 						if (!stopped) {
 							adv = i + 1;
 							b = bi;
@@ -354,7 +370,11 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					}
 					SETI(PF_CUR, j, k + adv);
 					if (stopped)
+#if CMGPU_INLINE_SLAB
+						modes = withMode(modes, j, b < 0 ? PM_POP : PM_BRUSH);
+#else
 						modes = withMode(modes, j, b < 0 ? PM_POP : ((FLDI(PF_FLAGS, j) & 4) ? PM_SLAB : PM_BRUSH));
+#endif
 				}
 			}
 		}
