@@ -6,7 +6,9 @@
 // (structure of arrays, [field][k][lane]: conflict-free, no cross-lane traffic, nothing shared between warps).  Each
 // round the warp counts how many lanes own an item waiting for each kind of step and runs every kind that enough
 // lanes can run; a lane runs the step on its first item of that kind.  Light steps are batched: a node step descends
-// up to kNodeLevels levels, a leaf step looks at kLeafEntries stream entries.  The model gives 17 / 21 / 23 active
+// up to kNodeLevels levels through a per-hull table of thresholds on the coordinates (nodeThresholdKernel), a leaf step
+// looks at kLeafEntries stream entries and runs the float slab pre-test on the ones that pass the bounds test, so that
+// only brushes that need the exact clip cost a round of their own.  The model gives 17 / 21 / 23 active
 // lanes per instruction for K = 2 / 3 / 4; K = 3 with 7 CTAs per SM is the measured optimum (more items per lane
 // leave too few warps and too little L1 for the same shared memory).
 //
@@ -378,6 +380,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				}
 			}
 		}
+#if !CMGPU_INLINE_SLAB
 		if (cSlab >= thr) {
 			// ---------------- float slab pre-test of the entry that passed CM_BoundsIntersect (see slabReject) -----------------
 			const int j = firstInMode<K>(modes, PM_SLAB);
@@ -392,6 +395,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				modes = withMode(modes, j, slabReject(h, L, e0, e1) ? PM_LEAF : PM_BRUSH);
 			}
 		}
+#endif
 		if (cPop >= thr) {
 			// ---------------- return to the pending far half of a split -----------------
 			const int j = firstInMode<K>(modes, PM_POP);
