@@ -56,7 +56,8 @@ enum {
 	CMGPU_ERR_BAD_HANDLE = 5,   /* CM_ClipHandleToModel: bad handle, cm_load.c:768-798 */
 	CMGPU_ERR_BAD_MAP = 6,      /* malformed lump / index out of range (the reference's ERR_DROPs in cm_load.c) */
 	CMGPU_ERR_NOMEM = 7,
-	CMGPU_ERR_LIMIT = 8         /* traversal stack overflow (tree deeper than CMGPU_MAX_DEPTH) */
+	CMGPU_ERR_LIMIT = 8         /* cmgpu_upload: the BSP is more than 255 levels deep (the traversal stacks are sized by
+	                               the depth of the uploaded tree; the reference recurses without a limit) */
 };
 
 /* trace_t, q_shared.h:976-986: 56 bytes, layout is ABI (QVM memory, botlib copies). */
@@ -182,9 +183,20 @@ int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
  * time, like the by-value arguments of CM_BoxTrace.  `stream` is a cudaStream_t
  * (NULL = default stream).  The call only enqueues work.  rotations: [n][9] row-major rotation matrices
  * (CreateRotationMatrix, cm_trace.c:65-68) with rot_index[i] == -1 for an
- * unrotated item; build them with cmgpu_rotation_matrices on the host.      * The _device calls may be issued on a stream that is being captured into a CUDA graph: they then allocate nothing
- * (a workspace that would have to grow is CMGPU_ERR_INVALID: run the call once before capturing it) and record no events.  (Not cmgpu_sv_trace_batch_device / cmgpu_sv_point_contents_batch_device: they read a count back between
- * their passes.)
+ * unrotated item; build them with cmgpu_rotation_matrices on the host.
+ *
+ * Model handles in a device array cannot be checked before the launch.  The kernels check them: an item whose handle
+ * is neither a loaded inline model nor 1023 touches no map data, is traced against nothing (fraction 1, contents 0),
+ * and the next cmgpu_check_status returns CMGPU_ERR_BAD_HANDLE (the reference drops the frame, cm_load.c:768-798).
+ *
+ * CUDA graphs.  The _device calls may be issued on a stream that is being captured: they then allocate nothing (a
+ * workspace that would have to grow is CMGPU_ERR_INVALID: run the same call once before capturing it) and record no
+ * events.  The captured launches name the context's workspaces by address; from the first capture on, a workspace
+ * that later has to grow (or a hull table that has to make room) is retired, not freed, so replays stay valid until
+ * the map is replaced (cmgpu_upload / cmgpu_clear) or the context destroyed -- a graph must not be replayed after
+ * that.  Replays and other calls on the same context share those workspaces: keep them in stream order.
+ * (Not capturable: cmgpu_sv_trace_batch_device / cmgpu_sv_point_contents_batch_device, which read a count back
+ * between their passes.)
  */
 int cmgpu_box_trace_batch_device(cmgpu_ctx *ctx, int n,
                           const float *starts, const float *ends,
@@ -204,7 +216,9 @@ int cmgpu_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points
  * matrices [n][9]; rot_index[i] = i if any angle is non-zero, else -1. */
 void cmgpu_rotation_matrices(int n, const float *angles, float *matrices, int32_t *rot_index);
 
-/* Device status word of the last launches: 0, or CMGPU_ERR_LIMIT if any item overflowed its stack. */
+/* Device status word of the launches since the last check (cleared by the call): CMGPU_OK, CMGPU_ERR_BAD_HANDLE if a
+ * device-side model handle was out of range, CMGPU_ERR_LIMIT if a traversal stack overflowed (cannot happen on a map
+ * that passed cmgpu_upload; kept as a tripwire).  Synchronises `stream`. */
 int cmgpu_check_status(cmgpu_ctx *ctx, void *stream);
 
 /* ---- whole SV_Trace / SV_PointContents on the device (server/sv_world.c:330-647) -----

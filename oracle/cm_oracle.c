@@ -35,7 +35,7 @@
 #define CLIP_EPS        0.125      /* SURFACE_CLIP_EPSILON, cm_local.h:177 (a double constant) */
 #define BOUNDS_EPS      0.25f      /* BOUNDS_CLIP_EPSILON, cm_test.c:474 */
 #define MAX_POS_LEAFS   1024       /* MAX_POSITION_LEAFS, cm_trace.c:190 */
-#define STACK_MAX       256
+#define STACK_MAX 4096          /* far above any tree the tests build; the reference recurses without a limit */
 
 typedef struct {
 	float start[3], end[3];        /* symmetrised sweep endpoints */

@@ -35,6 +35,47 @@ def build(quiet=True) -> bool:
     return r.returncode == 0 and available()
 
 
+def fork_map(n: int, out_dtype, work, nworkers: int | None = None) -> np.ndarray:
+    """Run ``work(lo, hi) -> array[hi - lo]`` over contiguous slices of range(n) in fork()ed children, one per host
+    core, and return the concatenated result.  The reference's CM layer is not re-entrant (global checkcount, shared temp
+    box: cm_trace.c:553, cm_load.c:927-949), so parallel checking needs processes, not threads; a child inherits the map
+    the parent loaded.  Results come back through an anonymous shared mapping."""
+    import mmap
+    import traceback
+    out_dtype = np.dtype(out_dtype)
+    if nworkers is None:
+        try:
+            nworkers = len(os.sched_getaffinity(0))
+        except Exception:
+            nworkers = os.cpu_count() or 1
+    nworkers = max(1, min(int(nworkers), (n + 4095) // 4096))
+    if nworkers == 1 or n == 0:
+        return np.asarray(work(0, n), dtype=out_dtype).reshape(n)
+    buf = mmap.mmap(-1, n * out_dtype.itemsize)
+    out = np.frombuffer(buf, dtype=out_dtype, count=n)
+    pids = []
+    for w in range(nworkers):
+        lo, hi = n * w // nworkers, n * (w + 1) // nworkers
+        pid = os.fork()
+        if pid == 0:
+            rc = 1
+            try:
+                out[lo:hi] = np.asarray(work(lo, hi), dtype=out_dtype).reshape(hi - lo)
+                rc = 0
+            except BaseException:
+                traceback.print_exc()
+            finally:
+                os._exit(rc)
+        pids.append(pid)
+    bad = [p for p in pids if os.waitpid(p, 0)[1] != 0]
+    res = out.copy()
+    del out
+    buf.close()
+    if bad:
+        raise RuntimeError(f"fork_map: {len(bad)} of {nworkers} workers failed")
+    return res
+
+
 _f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
 _i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
 _p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None

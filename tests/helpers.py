@@ -40,6 +40,17 @@ def get_map(kind: str):
     raise KeyError(kind)
 
 
+def comb_map(slabs):
+    """`slabs` thin brushes in a row, split off one at a time: a comb-shaped BSP about as deep as there are slabs"""
+    mb = bspgen.MapBuilder()
+    half = 50.0 * slabs + 192.0
+    bspgen._room_walls(mb, [-half, -64, -64], [half, 64, 64])
+    for i in range(slabs):
+        x = -50.0 * slabs + 100.0 * i
+        mb.box_brush([x, -32, -32], [x + 8, 32, 32], 0)
+    return mb.finish(seed=1, leaf_max=1, comb=True, max_depth=4 * slabs + 64), half
+
+
 def oracle_for(flat: dict, **cvars) -> "cmoracle.OracleCM":
     return cmoracle.OracleCM(flat, **cvars)
 

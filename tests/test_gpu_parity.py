@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import cases
-from helpers import (GOLDEN_SETS, assert_traces_equal, bspgen, cmoracle, flat_for, get_map, load_golden)
+from helpers import (GOLDEN_SETS, assert_traces_equal, bspgen, cmoracle, comb_map, flat_for, get_map, load_golden)
 
 pytestmark = pytest.mark.gpu
 
@@ -143,26 +143,105 @@ def test_error_codes(eng):
     e2.close()
 
 
-def test_deep_tree_reports_limit(eng):
-    """a degenerate BSP deeper than the traversal stack must be refused loudly, not traced wrongly"""
-    from threecore_b200.engine import CMGPUError, Engine
-    mb = bspgen.MapBuilder()
-    bspgen._room_walls(mb, [-4096, -64, -64], [4096, 64, 64])
-    for i in range(100):                                               # 100 thin slabs in a row: a comb tree
-        mb.box_brush([-4000 + 80 * i, -32, -32], [-4000 + 80 * i + 8, 32, 32], 0)
-    m = mb.finish(seed=1, leaf_max=1)
+@pytest.mark.parametrize("slabs", [50, 150])
+def test_deep_unbalanced_trees(eng, slabs):
+    """The reference recurses without a limit (cm_trace.c:516-537); here every traversal stack is sized by the depth of
+    the uploaded tree.  A comb of 50 slabs is deeper than the 32 pending halves the pool kernel once held, one of 150
+    deeper than the 64 entries of the kernels with local-memory stacks (they have a 256-entry variant).  Sweeps along
+    the comb in both directions keep a pending half per level; every kernel variant must return the reference's bytes."""
+    import torch
+    from helpers import cmref
+    from threecore_b200.engine import Engine
+    m, half = comb_map(slabs)
+    assert m.stats["max_depth"] > (64 if slabs > 100 else 32)
     e2 = Engine(0)
-    e2.load_bsp(m.data)
-    s = np.array([[-4050, 0, 0]], np.float32).repeat(64, 0)
-    en = np.array([[4050, 0, 0]], np.float32).repeat(64, 0)
-    o = cmoracle.OracleCM(e2.map.to_dict())
-    want, info = o.box_trace(s, en, want_info=True)
     try:
-        got = e2.box_trace(s, en)
-        assert_traces_equal(got, want, "deep tree within the stack limit")
-    except CMGPUError as ex:
-        assert ex.code == 8
-    e2.close()
+        e2.load_bsp(m.data)
+        o = cmoracle.OracleCM(e2.map.to_dict())
+        rng = np.random.default_rng(slabs)
+        n = 1 << 20                                       # big enough for the binned pool kernel
+        s = np.stack([rng.uniform(-half + 70, half - 70, n), rng.uniform(-20, 20, n), rng.uniform(-20, 20, n)], 1).astype(np.float32)
+        en = s.copy()
+        en[:, 0] = np.where(rng.random(n) < 0.5, half - 70, -half + 70).astype(np.float32)      # to either end of the comb
+        en[: n // 8] = s[: n // 8]                         # position tests
+        idx = rng.choice(n, 4000, replace=False)
+        # masks: solid (stops at the first slab) and one that no brush has (the sweep crosses the whole comb: deepest stacks)
+        for mask in (bspgen.MASK_PLAYERSOLID, 0x40000000):
+            for mins, maxs in ((bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS), (None, None)):
+                want = o.box_trace(s[idx], en[idx], mins, maxs, mask=mask)
+                if cmref.available():
+                    assert_traces_equal(cmref.RefCM().load(m.data).box_trace(s[idx], en[idx], mins, maxs, mask=mask), want, "oracle vs reference")
+                for opts in (dict(), dict(pool=0), dict(fast=0)):
+                    try:
+                        for k, v in opts.items():
+                            e2.set_option(k, v)
+                        got = e2.box_trace(s[idx], en[idx], mins, maxs, mask=mask)             # small launch
+                        assert_traces_equal(got, want, f"{slabs} slabs, small launch, {opts}, mask {mask:#x}")
+                        dev = torch.device("cuda", 0)
+                        out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
+                        e2.box_trace_device(torch.from_numpy(s).to(dev), torch.from_numpy(en).to(dev), mins, maxs, mask, out)
+                        torch.cuda.synchronize()
+                        e2.check_status()
+                        from threecore_b200.engine import traces_from_tensor
+                        assert_traces_equal(traces_from_tensor(out)[idx], want, f"{slabs} slabs, 1 Mi launch, {opts}, mask {mask:#x}")
+                    finally:
+                        for k in opts:
+                            e2.set_option(k, 1)
+        # a box over the whole comb: CM_BoxLeafnums_r keeps a pending child per level too (cm_test.c:131-156)
+        lists, counts, last = e2.box_leafnums(np.array([[-half, -40, -40]], np.float32), np.array([[half, 40, 40]], np.float32), 1024)
+        wl, wc, wlast = o.box_leafnums(np.array([[-half, -40, -40]], np.float32), np.array([[half, 40, 40]], np.float32), 1024)
+        assert counts[0] == wc[0] and np.array_equal(lists[0][: counts[0]], wl[0][: wc[0]]) and last[0] == wlast[0]
+        assert counts[0] > slabs
+    finally:
+        e2.close()
+
+
+def test_tree_deeper_than_the_stacks_is_refused_at_upload():
+    """256+ levels: cmgpu_upload says so (CMGPU_ERR_LIMIT) instead of tracing with stacks that could overflow"""
+    from threecore_b200.engine import CMGPUError, Engine
+    m, _ = comb_map(300)
+    assert m.stats["max_depth"] >= 256
+    e2 = Engine(0)
+    try:
+        with pytest.raises(CMGPUError) as ex:
+            e2.load_bsp(m.data)
+        assert ex.value.code == 8 and "levels deep" in str(ex.value)
+    finally:
+        e2.close()
+
+
+def test_bad_model_handle_in_a_device_array_is_reported(eng):
+    """CM_ClipHandleToModel drops the frame on a bad handle (cm_load.c:768-798); the host-pointer calls check before they
+    launch, a device array is checked by the kernels: no out-of-range read, the item hits nothing, check_status says why"""
+    import torch
+    from threecore_b200.engine import CMGPUError, traces_from_tensor
+    m, o = load(eng, "arena_models")
+    n = 4096
+    s, e = bspgen.make_sweeps(m, n, 21)
+    dev = torch.device("cuda", 0)
+    models = np.zeros(n, np.int32)
+    models[5], models[77], models[4000] = 999, -3, 1 << 30
+    ds, de = torch.from_numpy(s).to(dev), torch.from_numpy(e).to(dev)
+    out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
+    eng.box_trace_device(ds, de, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, out,
+                         models=torch.from_numpy(models).to(dev))
+    torch.cuda.synchronize()
+    with pytest.raises(CMGPUError) as ex:
+        eng.check_status()
+    assert ex.value.code == 5
+    got = traces_from_tensor(out)
+    ok = np.ones(n, bool)
+    ok[[5, 77, 4000]] = False
+    want = o.box_trace(s[ok], e[ok], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID)
+    assert_traces_equal(got[ok], want, "items next to bad handles")
+    assert (got["fraction"][~ok] == 1.0).all() and (got["contents"][~ok] == 0).all()
+    eng.check_status()                                    # the status word was cleared
+    pc = torch.empty(n, dtype=torch.int32, device=dev)
+    eng.point_contents_device(ds, pc, models=torch.from_numpy(models).to(dev))
+    torch.cuda.synchronize()
+    with pytest.raises(CMGPUError) as ex:
+        eng.check_status()
+    assert ex.value.code == 5 and (pc.cpu().numpy()[~ok] == 0).all()
 
 
 # ---- full-size properties (BASELINE.json sizes; the oracle only checks a sample) -----------------

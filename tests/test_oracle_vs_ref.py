@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import cases
-from helpers import assert_traces_equal, cmoracle, cmref, get_map, have_ref
+from helpers import assert_traces_equal, bspgen, cmoracle, cmref, get_map, have_ref
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libcmref.so not built (no reference tree here)")
 
@@ -95,3 +95,23 @@ def test_repeat_visits_do_not_change_results():
     b, info = o.box_trace(s, e, cases.bspgen.PLAYER_MINS, cases.bspgen.PLAYER_MAXS, mask=-1, want_info=True)
     assert_traces_equal(b, a, "long sweeps")
     assert info["leafs"].max() > 8
+
+
+def test_deep_comb_tree_restatement_matches_reference():
+    """a BSP 155 levels deep: the reference recurses, the restatement keeps explicit stacks"""
+    from helpers import comb_map
+    m, half = comb_map(150)
+    r = cmref.RefCM().load(m.data)
+    o = cmoracle.OracleCM(cmoracle.flat_from_ref_dump(r.dump()))
+    rng = np.random.default_rng(5)
+    n = 3000
+    s = np.stack([rng.uniform(-half + 70, half - 70, n), rng.uniform(-20, 20, n), rng.uniform(-20, 20, n)], 1).astype(np.float32)
+    e = s.copy()
+    e[:, 0] = np.where(rng.random(n) < 0.5, half - 70, -half + 70).astype(np.float32)
+    e[: n // 8] = s[: n // 8]
+    for mask in (bspgen.MASK_PLAYERSOLID, 0x40000000):
+        for mins, maxs in ((bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS), (None, None)):
+            assert_traces_equal(o.box_trace(s, e, mins, maxs, mask=mask), r.box_trace(s, e, mins, maxs, mask=mask), f"comb {mask:#x}")
+    lo, hi = np.array([[-half, -40, -40]], np.float32), np.array([[half, 40, 40]], np.float32)
+    a, b = o.box_leafnums(lo, hi, 1024), r.box_leafnums(lo, hi, 1024)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and a[1][0] > 150

@@ -236,8 +236,9 @@ class MapBuilder:
 
     # -- finalisation -------------------------------------------------------
     def finish(self, seed=0, leaf_max=4, nonaxial_node_prob=0.0, max_depth=48,
-               planar_every=0) -> SynthMap:
-        """Build the BSP over the world brushes/patches and serialise all lumps."""
+               planar_every=0, comb=False) -> SynthMap:
+        """Build the BSP over the world brushes/patches and serialise all lumps.  comb=True peels one item per split
+        (the lowest usable plane on the longest axis): a degenerate tree about as deep as the map has brushes."""
         rng = np.random.default_rng(seed ^ 0x5EED)
         n_world_brushes = self.models[0]["first_brush"] if self.models else len(self.brushes)
         n_world_patches = self.models[0]["first_patch"] if self.models else len(self.patches)
@@ -309,6 +310,13 @@ class MapBuilder:
                 if cand.size == 0:
                     continue
                 cand = np.unique(cand)
+                if comb:
+                    for c in cand:
+                        nf = int(np.count_nonzero(mx[:, a] > c))
+                        nb = int(np.count_nonzero(mn[:, a] < c))
+                        if max(nf, nb) < n:
+                            return (0.0, int(a), float(c))
+                    continue
                 centre = np.median(0.5 * (mn[:, a] + mx[:, a]))
                 # a handful of candidates around the median
                 pos = np.searchsorted(cand, centre)

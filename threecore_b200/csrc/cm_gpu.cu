@@ -64,7 +64,7 @@ struct cmgpu_ctx_s {
 	Counters *dCounters = nullptr;
 	int *dStatus = nullptr;
 	int *dCursor = nullptr;              // work cursors of the persistent kernel, one per launch slot
-	int cursorSlot = 0;
+	unsigned cursorSlot = 0;
 	int gridPlain = 0, gridCount = 0;    // resident CTAs of the two kernel variants
 	int gridFast = 0, gridFastCount = 0;
 	int gridPool = 0, gridPoolCount = 0;
@@ -75,6 +75,7 @@ struct cmgpu_ctx_s {
 	int poolMinItems = 786433;           // smaller launches use the one-item-per-lane variant (lower latency)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
+	int treeDepth = 1;                   // levels of the world BSP (validate()): the size of every traversal stack
 	bool useFast = true;
 	int pipeChunks = 32;                 // pieces a host batch is cut into
 	bool pipeRamp = true;                // ... the first ones smaller
@@ -98,6 +99,12 @@ struct cmgpu_ctx_s {
 	float binCell = 256.0f, binLongLen = 512.0f;
 	DevBuf bKeys, bRecs, bCompact, bHist[kBinSlots];
 	bool capturing = false;              // the stream of the current device-pointer call is being captured into a CUDA graph
+	// A captured launch bakes the addresses of the workspaces it used (binning buffers, stack arena, pool headers, hull
+	// tables) into the graph.  Once a capture has used this context, a workspace that has to grow -- or a hull table that
+	// has to make room -- is RETIRED instead of freed: replays keep reading and writing their own, still valid blocks.
+	// Retired blocks are released with the map (a graph does not outlive the map it was recorded on) or the context.
+	bool graphPinned = false;
+	std::vector<void *> retired;
 	bool twoPhase = true, twoPhaseHost = false, twoPhaseSmall = false, compactByItem = true;
 	// pool kernel: per-hull node threshold tables (nodeThresholdKernel), built on first use, dropped with the map
 	struct HullTable { NodeHull key; DevBuf buf; bool usable; };
@@ -158,7 +165,8 @@ int reserve(cmgpu_ctx *ctx, DevBuf &b, size_t bytes) {
 	if (bytes <= b.cap) return CMGPU_OK;
 	if (ctx->capturing)                              // cudaFree / cudaMalloc are not allowed while a stream is being captured
 		return fail(ctx, CMGPU_ERR_INVALID, "a workspace would have to grow during stream capture: run the same call once before capturing it");
-	if (b.p) cudaFree(b.p);                      // cudaFree synchronises the device: nothing is still reading the old block
+	if (b.p && ctx->graphPinned) ctx->retired.push_back(b.p);   // a recorded graph may still name it (see graphPinned)
+	else if (b.p) cudaFree(b.p);                 // cudaFree synchronises the device: nothing is still reading the old block
 	b.p = nullptr;
 	b.cap = 0;
 	size_t want = bytes + bytes / 4 + 256;
@@ -253,6 +261,9 @@ void freeMap(cmgpu_ctx *ctx) {
 	ctx->numPatches = 0;
 	for (auto &t : ctx->hullTables) releaseBuf(t.buf);
 	ctx->hullTables.clear();
+	for (void *p : ctx->retired) cudaFree(p);
+	ctx->retired.clear();
+	ctx->graphPinned = false;
 	ctx->leafCluster = nullptr;
 	ctx->vised = false;
 	ctx->numClusters = ctx->clusterBytes = ctx->numAreas = 0;
@@ -295,7 +306,7 @@ inline int signbitsOf(const float *n) {
 
 // Everything the kernels index is range-checked here so that a malformed map is
 // a CMGPU_ERR_BAD_MAP on the host instead of an out-of-bounds access on the GPU.
-int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
+int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f, int *treeLevels) {
 #define NEED(cond, ...) do { if (!(cond)) return fail(ctx, CMGPU_ERR_BAD_MAP, __VA_ARGS__); } while (0)
 	NEED(f->numPlanes >= 12 && f->planes && f->planeType && f->planeSignbits, "map with no planes");
 	NEED(f->numNodes >= 1 && f->nodes, "map has no nodes");
@@ -329,19 +340,27 @@ int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		}
 	}
 	{   // the node graph must be a tree: a cycle would never terminate on the device
+		// ... and its depth bounds the traversal stacks: the pending far halves of a sweep (cm_trace.c:516-537) and the
+		// pending children[1] of a box query (cm_test.c:131-156) each belong to a different node on the path from the
+		// root, so a walk never holds more of them than the tree has levels.  The reference recurses without a limit.
 		std::vector<unsigned char> seen((size_t)f->numNodes, 0);
-		std::vector<int> st;
-		st.push_back(0);
+		std::vector<std::pair<int, int>> st;
+		st.push_back({0, 1});
+		int levels = 0;
 		while (!st.empty()) {
-			int n = st.back();
+			const int n = st.back().first, d = st.back().second;
 			st.pop_back();
 			NEED(!seen[n], "node %d reachable twice: BSP is not a tree", n);
 			seen[n] = 1;
+			if (d > levels) levels = d;
 			for (int c = 1; c <= 2; c++) {
 				int ch = f->nodes[3 * (size_t)n + c];
-				if (ch >= 0) st.push_back(ch);
+				if (ch >= 0) st.push_back({ch, d + 1});
 			}
 		}
+		if (levels > kDeepDepth - 1)
+			return fail(ctx, CMGPU_ERR_LIMIT, "the map's BSP is %d levels deep; the traversal stacks hold %d pending halves", levels, kDeepDepth - 1);
+		*treeLevels = levels;
 	}
 	auto checkLeaf = [&](const int32_t *lf, const char *what, int i) -> int {
 		NEED(lf[1] >= 0 && lf[0] >= 0 && (long long)lf[0] + lf[1] <= f->numLeafBrushes, "%s %d: bad leafbrush range", what, i);
@@ -689,7 +708,10 @@ const int4 *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStream_t s) {
 	if (ctx->capturing) return nullptr;                   // building synchronises: not inside a capture (plain node step instead)
 	if (ctx->hullTables.size() >= 8) {                    // a ninth hull: start over (nothing may still read the old tables)
 		cudaDeviceSynchronize();
-		for (auto &t : ctx->hullTables) releaseBuf(t.buf);
+		for (auto &t : ctx->hullTables) {
+			if (ctx->graphPinned && t.buf.p) { ctx->retired.push_back(t.buf.p); t.buf = DevBuf{}; }
+			else releaseBuf(t.buf);
+		}
 		ctx->hullTables.clear();
 	}
 	cmgpu_ctx::HullTable t{};
@@ -712,6 +734,23 @@ const int4 *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStream_t s) {
 	return t.usable ? (const int4 *)t.buf.p : nullptr;
 }
 
+// Device-pointer calls share the context's workspaces.  Whatever such a call leaves running on its stream, the next
+// one on ANOTHER stream (or a host-pointer call) must wait for: extDone is recorded after the last kernel that reads or
+// writes a shared workspace, and waited for at entry.
+int extWait(cmgpu_ctx *ctx, cudaStream_t s) {
+	if (ctx->extBusy && ctx->extStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->extDone, 0));
+	return CMGPU_OK;
+}
+int extRecord(cmgpu_ctx *ctx, cudaStream_t s) {
+	cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+	if (cudaStreamIsCapturing(s, &st) != cudaSuccess) cudaGetLastError();
+	if (st != cudaStreamCaptureStatusNone) return CMGPU_OK;          // captured work: the caller orders replays
+	CUDA_TRY(ctx, cudaEventRecord(ctx->extDone, s));
+	ctx->extStream = s;
+	ctx->extBusy = true;
+	return CMGPU_OK;
+}
+
 // wsOffset: first item of this launch inside the context's binning workspace (the host pipeline gives
 // every chunk its own range); histSlot: which histogram table to use (one per pipeline stream).
 int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1) {
@@ -728,6 +767,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
 		if (external && cudaStreamIsCapturing(s, &st) == cudaSuccess) ctx->capturing = st != cudaStreamCaptureStatusNone;
 		else cudaGetLastError();
+		if (ctx->capturing) ctx->graphPinned = true;
 	}
 	const bool capturing = ctx->capturing;
 	if (external && !capturing && ctx->extBusy && ctx->extStream != s) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->extDone, 0));
@@ -767,6 +807,8 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	q.gangBrush = ctx->gangBrush;
 	q.lightReps = ctx->lightReps;
 	q.facetSteps = ctx->facetSteps;
+	q.stackDepth = ctx->treeDepth;
+	const bool deep = ctx->treeDepth > kMaxDepth;   // the kernels with local-memory stacks have a variant for such maps
 	CUDA_TRY(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(int), s));
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
@@ -813,12 +855,13 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	if (fast && !pool && q.n <= ctx->simpleMaxItems) {
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
 		const int nb = (q.n + kBlock - 1) / kBlock;
-		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<true>, nb, kBlock, 0, s, ctx->fast, q, h));
-		else               CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false>, nb, kBlock, 0, s, ctx->fast, q, h));
+		if (deep)               CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false, kDeepDepth>, nb, kBlock, 0, s, ctx->fast, q, h));
+		else if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<true>, nb, kBlock, 0, s, ctx->fast, q, h));
+		else                    CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false>, nb, kBlock, 0, s, ctx->fast, q, h));
 	} else if (pool) {
 		q.lightReps = ctx->poolReps;
 		q.gangFetch = ctx->gangFetchPool;
-		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * kPoolDepth * sizeof(FastSeg));
+		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * q.stackDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
 		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
 		rcA = reserve(ctx, ctx->bPoolHdr[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * sizeof(PoolHdr));
@@ -830,15 +873,16 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		else if (q.tnodes)  CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, true>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 		else                CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, false>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 	} else if (fast) {
-		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * kMaxDepth * sizeof(FastSeg));
+		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * q.stackDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
 		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
 		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceFastKernel<true>, (int)blocks, kBlock, 0, s, ctx->fast, q, h));
 		else               CUDA_TRY(ctx, launchOnMap(ctx, traceFastKernel<false>, (int)blocks, kBlock, 0, s, ctx->fast, q, h));
 	} else {
-		if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<true>, (int)blocks, kBlock, 0, s, ctx->map, q));
-		else               CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<false>, (int)blocks, kBlock, 0, s, ctx->map, q));
+		if (deep)               CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<false, kDeepDepth>, (int)blocks, kBlock, 0, s, ctx->map, q));
+		else if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<true>, (int)blocks, kBlock, 0, s, ctx->map, q));
+		else                    CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<false>, (int)blocks, kBlock, 0, s, ctx->map, q));
 	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
@@ -973,10 +1017,12 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 int cmgpu_upload(cmgpu_ctx *ctx, const cmgpu_flatmap *map) {
 	if (!ctx || !map) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_upload: NULL argument");
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-	int rc = validate(ctx, map);
+	int levels = 1;
+	int rc = validate(ctx, map, &levels);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaDeviceSynchronize());
 	freeMap(ctx);
+	ctx->treeDepth = levels;
 	ctx->hasSvWorld = false;                     // entity snapshots refer to the inline models of the map they were made for
 	rc = packAndUpload(ctx, map);
 	if (rc) freeMap(ctx);
@@ -1157,9 +1203,13 @@ int cmgpu_check_status(cmgpu_ctx *ctx, void *stream) {
 	cudaStream_t s = (cudaStream_t)stream;
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hStatus, ctx->dStatus, sizeof(int), cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(ctx, cudaStreamSynchronize(s));
-	if (*ctx->hStatus) {
+	if (const int st = *ctx->hStatus) {
 		CUDA_TRY(ctx, cudaMemsetAsync(ctx->dStatus, 0, sizeof(int), s));
-		return fail(ctx, CMGPU_ERR_LIMIT, "traversal stack overflow: BSP deeper than %d pending splits", kMaxDepth);
+		if (st & 2)
+			return fail(ctx, CMGPU_ERR_BAD_HANDLE, "CM_ClipHandleToModel: a device-side model handle was neither a loaded inline model (0..%d) nor %d; "
+			            "those items were traced against nothing", ctx->numModels - 1, CMGPU_BOX_MODEL_HANDLE);
+		// cannot happen on a validated map (stacks are sized by the tree's depth, %d levels here); kept as a tripwire
+		return fail(ctx, CMGPU_ERR_LIMIT, "traversal stack overflow: more than %d pending halves on a BSP of %d levels", ctx->treeDepth > kMaxDepth ? kDeepDepth : ctx->treeDepth, ctx->treeDepth);
 	}
 	return CMGPU_OK;
 }
@@ -1210,6 +1260,7 @@ int cmgpu_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points
 	q.boxmins = boxmins; q.boxmaxs = boxmins ? boxmaxs : nullptr;
 	if (!q.boxmaxs) q.boxmins = nullptr;
 	q.out = contents;
+	q.status = ctx->dStatus;
 	const int grid = (n + 127) / 128;
 	pointContentsKernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
 	ctx->launches++;
@@ -1701,7 +1752,7 @@ int cmgpu_sv_trace_batch_device(cmgpu_ctx *ctx, int n, const float *starts, cons
 	svMergeKernel<<<grid, 128, 0, s>>>(n, q.results, q.offsets, (const uint2 *)ctx->bSvCand.p, it.entIndex, ctx->sv.entInfo);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
-	return CMGPU_OK;
+	return extRecord(ctx, s);                    // the merge still reads the offsets and the candidates' records
 }
 
 int cmgpu_sv_trace_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
@@ -1755,8 +1806,10 @@ int cmgpu_sv_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *poi
 	ctx->svCandidates = 0;
 	if (n == 0) return CMGPU_OK;
 	cudaStream_t s = (cudaStream_t)stream;
+	int rc = extWait(ctx, s);
+	if (rc) return rc;
 	// base contents from the world (sv_world.c:625)
-	int rc = cmgpu_point_contents_batch_device(ctx, n, points, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, contents, stream);
+	rc = cmgpu_point_contents_batch_device(ctx, n, points, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, contents, stream);
 	if (rc) return rc;
 	if ((rc = reserve(ctx, ctx->bSvOffsets, ((size_t)n + 1) * 4))) return rc;
 	unsigned *offsets = (unsigned *)ctx->bSvOffsets.p;
@@ -1790,7 +1843,7 @@ int cmgpu_sv_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *poi
 	svPointMergeKernel<<<grid, 128, 0, s>>>(n, contents, offsets, (const int *)ctx->bSvCand.p);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
-	return CMGPU_OK;
+	return extRecord(ctx, s);
 }
 
 int cmgpu_sv_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
@@ -1839,7 +1892,8 @@ int cmgpu_box_leafnums_batch_device(cmgpu_ctx *ctx, int n, const float *mins, co
 	if (n == 0) return CMGPU_OK;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	LeafListBatch q{n, mins, maxs, listsize, lists, counts, lastLeafs, ctx->leafCluster, ctx->dStatus};
-	boxLeafnumsKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	if (ctx->treeDepth > kMaxDepth) boxLeafnumsKernel<kDeepDepth><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	else boxLeafnumsKernel<kMaxDepth><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return CMGPU_OK;
@@ -1899,7 +1953,8 @@ int cmgpu_entity_clusters_batch_device(cmgpu_ctx *ctx, int n, const float *absmi
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	static_assert(sizeof(EntClusters) == sizeof(cmgpu_entity_clusters_t), "record layout");
 	EntClusterBatch q{n, absmins, absmaxs, reinterpret_cast<EntClusters *>(out), ctx->leafCluster, ctx->dStatus};
-	entityClustersKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	if (ctx->treeDepth > kMaxDepth) entityClustersKernel<kDeepDepth><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
+	else entityClustersKernel<kMaxDepth><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->map, q);
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
 	return CMGPU_OK;

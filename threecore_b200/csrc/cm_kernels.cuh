@@ -33,7 +33,9 @@ namespace cmgpu {
 constexpr int    kBlock          = 128;     // threads per CTA of the trace kernel
 constexpr int    kChunk          = 256;     // most items a warp takes from the global cursor at a time (TraceBatch::chunk)
 constexpr int    kGang           = 4;       // lanes that must gather before a heavy block runs
-constexpr int    kMaxDepth       = 64;      // traversal stack entries per item (CMGPU_ERR_LIMIT beyond)
+constexpr int    kMaxDepth       = 64;      // traversal stack entries per item of the kernels that keep their stack in local memory ...
+constexpr int    kDeepDepth      = 256;     // ... and of their variants for maps whose BSP is deeper than that (cmgpu_upload refuses trees
+                                            // deeper than kDeepDepth - 1; pending far halves never outnumber the levels of the tree)
 constexpr int    kFacetPlaneSteps = 12;     // patch planes a lane tests per scheduler round
 constexpr int    kMaxPosLeafs    = 1024;    // MAX_POSITION_LEAFS, cm_trace.c:190
 constexpr int    kBoxModelHandle = 1023;    // BOX_MODEL_HANDLE, cm_local.h:28
@@ -124,7 +126,8 @@ struct TraceBatch {
 	int lightReps;                       // light (node / brush-box) steps per scheduler iteration
 	int facetSteps;                      // patch planes a lane tests per scheduler iteration (general kernel)
 	Counters *counters;                  // only touched by the counting variant
-	struct FastSeg *stackArena;          // hot kernel: kMaxDepth entries per resident thread
+	struct FastSeg *stackArena;          // hot kernels: stackDepth entries per resident item slot
+	int stackDepth;                      // = levels of the map's BSP (pending far halves never outnumber them), <= 255
 	void *poolHdr;                       // pool variant: one 16-byte header per item slot
 	const float4 *recs;                  // binned batch: [2*slot] start.xyz + item bits, [2*slot+1] end.xyz + 0; null = input order
 	uint4 *compact;                      // binned hot kernels: results leave as 16 bytes per SLOT (fraction, flags, clip side,
@@ -157,6 +160,7 @@ struct PointBatch {
 	const int *rotIndex;
 	const float *boxmins, *boxmaxs;
 	int *out;
+	int *status;                         // device status word (bit 1: a bad model handle)
 };
 
 enum Mode : int { M_FETCH = 0, M_NODE, M_SPLIT, M_LEAF, M_BRUSH, M_SIDE, M_PATCH, M_PNODE, M_PLEAF, M_FINISH, M_FACET };
@@ -532,7 +536,11 @@ __device__ __forceinline__ int beginItem(const DevMap &m, const TraceBatch &q, L
 		mnx = q.sharedMins[0]; mny = q.sharedMins[1]; mnz = q.sharedMins[2];
 		mxx = q.sharedMaxs[0]; mxy = q.sharedMaxs[1]; mxz = q.sharedMaxs[2];
 	}
-	const int model = q.models ? q.models[i] : 0;
+	int model = q.models ? q.models[i] : 0;
+	// CM_ClipHandleToModel (cm_load.c:768-798) drops the frame on a handle that is neither a loaded model nor 1023.
+	// The host-pointer calls check that before anything is launched; a device array can only be checked here: the
+	// item is traced against nothing, and bit 1 of the status word makes cmgpu_check_status report CMGPU_ERR_BAD_HANDLE.
+	if (model != kBoxModelHandle && (unsigned)model >= (unsigned)m.numModels) { atomicOr(q.status, 2); model = kBoxModelHandle + 1; }
 	L.mask = q.masks ? q.masks[i] : q.sharedMask;
 	L.flags = (model == kBoxModelHandle) ? F_BOX : 0;
 
@@ -582,7 +590,7 @@ __device__ __forceinline__ int beginItem(const DevMap &m, const TraceBatch &q, L
 	if (L.sz < L.ez) { L.loz = L.sz + L.n0z; L.hiz = L.ez + L.p0z; } else { L.loz = L.ez + L.n0z; L.hiz = L.sz + L.p0z; }
 
 	int4 mleaf = make_int4(0, 0, 0, 0);
-	if (model) mleaf = (L.flags & F_BOX) ? make_int4(m.boxLeafBrush, 1, 0, 0) : __ldg(&m.modelLeafs[model]);
+	if (model) mleaf = (L.flags & F_BOX) ? make_int4(m.boxLeafBrush, 1, 0, 0) : (model > kBoxModelHandle ? make_int4(0, 0, 0, 0) : __ldg(&m.modelLeafs[model]));
 
 	if (ts0x == te0x && ts0y == te0y && ts0z == te0z) {
 		// position test: isPoint stays false and extents zero here (cm_trace.c:641-646)
@@ -660,11 +668,11 @@ __device__ __forceinline__ void finishItem(const TraceBatch &q, Lane &L) {
 #ifndef CMGPU_MIN_BLOCKS
 #define CMGPU_MIN_BLOCKS 4
 #endif
-template <bool COUNT>
+template <bool COUNT, int DEPTH = kMaxDepth>
 __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const DevMap m, const TraceBatch q) {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned laneLt = (1u << lane) - 1u;
-	Seg stack[kMaxDepth];
+	Seg stack[DEPTH];
 	Lane L;
 	int mode = M_FETCH;
 	int chunkNext = 0, chunkEnd = 0;     // warp-uniform
@@ -819,7 +827,7 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 				const float mx = L.ax + fnear * (L.bx - L.ax);
 				const float my = L.ay + fnear * (L.by - L.ay);
 				const float mz = L.az + fnear * (L.bz - L.az);
-				if (L.sp < kMaxDepth) stack[L.sp++] = far; else atomicOr(q.status, 1);
+				if (L.sp < DEPTH) stack[L.sp++] = far; else atomicOr(q.status, 1);
 				L.num = side ? nd.y : nd.x;
 				L.f2 = midf;
 				L.bx = mx; L.by = my; L.bz = mz;
@@ -1000,7 +1008,7 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 				} else if (s == 2) {
 					L.num = nd.y;
 				} else {
-					if (L.sp < kMaxDepth) stack[L.sp++].num = nd.y; else atomicOr(q.status, 1);
+					if (L.sp < DEPTH) stack[L.sp++].num = nd.y; else atomicOr(q.status, 1);
 					L.num = nd.x;
 				}
 			}
@@ -1098,6 +1106,10 @@ __global__ void __launch_bounds__(128) pointContentsKernel(const DevMap m, const
 	}
 	int4 leaf;
 	if (model) {
+		if (!isBox && (unsigned)model >= (unsigned)m.numModels) {      // bad handle (see beginItem): an empty leaf, and say so
+			atomicOr(q.status, 2);
+			leaf = make_int4(0, 0, 0, 0);
+		} else
 		leaf = isBox ? make_int4(m.boxLeafBrush, 1, 0, 0) : __ldg(&m.modelLeafs[model]);
 	} else {
 		// CM_PointLeafnum_r, cm_test.c:31-54

@@ -38,6 +38,7 @@ struct LeafListBatch {
 	int *status;
 };
 
+template <int DEPTH>
 __global__ void __launch_bounds__(128) boxLeafnumsKernel(const DevMap m, const LeafListBatch q) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.n) return;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(128) boxLeafnumsKernel(const DevMap m, const L
 	const float lox = q.mins[o], loy = q.mins[o + 1], loz = q.mins[o + 2];
 	const float hix = q.maxs[o], hiy = q.maxs[o + 1], hiz = q.maxs[o + 2];
 	int *list = q.lists + (size_t)i * q.listsize;
-	int stack[kMaxDepth];
+	int stack[DEPTH];
 	int sp = 0, count = 0, lastLeaf = 0, num = 0;
 	for (;;) {
 		while (num >= 0) {                                       // CM_BoxLeafnums_r, cm_test.c:131-156
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(128) boxLeafnumsKernel(const DevMap m, const L
 			if (s == 1) num = nd.x;
 			else if (s == 2) num = nd.y;
 			else {
-				if (sp < kMaxDepth) stack[sp++] = nd.y; else atomicOr(q.status, 1);
+				if (sp < DEPTH) stack[sp++] = nd.y; else atomicOr(q.status, 1);
 				num = nd.x;
 			}
 		}
@@ -87,13 +88,14 @@ struct EntClusterBatch {
 	int *status;
 };
 
+template <int DEPTH>
 __global__ void __launch_bounds__(128) entityClustersKernel(const DevMap m, const EntClusterBatch q) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.n) return;
 	const size_t o = 3 * (size_t)i;
 	const float lox = q.absmins[o], loy = q.absmins[o + 1], loz = q.absmins[o + 2];
 	const float hix = q.absmaxs[o], hiy = q.absmaxs[o + 1], hiz = q.absmaxs[o + 2];
-	int stack[kMaxDepth];
+	int stack[DEPTH];
 	int sp = 0, count = 0, lastLeaf = 0, num = 0;
 	int areanum = -1, areanum2 = -1, numClusters = 0;
 	bool full = false;                                       // the cluster loop hit its break (sv_world.c:294-296)
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(128) entityClustersKernel(const DevMap m, cons
 			if (s == 1) num = nd.x;
 			else if (s == 2) num = nd.y;
 			else {
-				if (sp < kMaxDepth) stack[sp++] = nd.y; else atomicOr(q.status, 1);
+				if (sp < DEPTH) stack[sp++] = nd.y; else atomicOr(q.status, 1);
 				num = nd.x;
 			}
 		}

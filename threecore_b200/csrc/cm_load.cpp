@@ -15,6 +15,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <new>
+#include <stdexcept>
+#include <stdint.h>
 #include <vector>
 
 namespace {
@@ -83,7 +86,7 @@ int lumpView(const uint8_t *base, const Lump &l, const char *what, const Fail &f
 
 }  // namespace
 
-extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen) {
+static int flatmapFromBsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen) {
 	Fail fail{err, errlen};
 	if (err && errlen) err[0] = 0;
 	if (!out) return CMGPU_ERR_INVALID;
@@ -97,6 +100,9 @@ extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap
 	for (int i = 0; i < HEADER_LUMPS; i++) {
 		const int64_t o = h.lumps[i].ofs, l = h.lumps[i].len;
 		if (o < 0 || l < 0 || o + l > (int64_t)len) return fail("CM_LoadMap: wrong lump[%i] size/offset", i);
+		// the records are read in place as 4-byte words (the reference casts the same way, cm_load.c:104-580, and the
+		// tools that write .bsp files pad every lump to 4 bytes)
+		if (l > 0 && ((o & 3) || (reinterpret_cast<uintptr_t>(base) & 3))) return fail("CM_LoadMap: lump[%i] is not 4-byte aligned", i);
 	}
 
 	const DShader *shaders = nullptr; const DLeaf *dleafs = nullptr; const int32_t *dleafbrushes = nullptr, *dleafsurfaces = nullptr; const DPlane *dplanes = nullptr;
@@ -220,6 +226,10 @@ extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap
 		}
 		if (i == 0) continue;
 		if (dm.numBrushes < 0 || dm.numSurfaces < 0) return fail("CMod_LoadSubmodels: model %i: negative count", i);
+		if (dm.firstBrush < 0 || (int64_t)dm.firstBrush + dm.numBrushes > nBrushes)
+			return fail("CMod_LoadSubmodels: model %i: brushes %i..+%i outside the map's %i", i, dm.firstBrush, dm.numBrushes, nBrushes);
+		if (dm.firstSurface < 0 || (int64_t)dm.firstSurface + dm.numSurfaces > nSurfs)
+			return fail("CMod_LoadSubmodels: model %i: surfaces %i..+%i outside the map's %i", i, dm.firstSurface, dm.numSurfaces, nSurfs);
 		m->modelLeafs[4 * (size_t)i] = (int32_t)m->leafbrushes.size();
 		m->modelLeafs[4 * (size_t)i + 1] = dm.numBrushes;
 		for (int j = 0; j < dm.numBrushes; j++) m->leafbrushes.push_back(dm.firstBrush + j);
@@ -306,6 +316,21 @@ extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap
 	guard.p = nullptr;
 	*out = &m->c;
 	return CMGPU_OK;
+}
+
+// nothing may leave an extern "C" function by exception: a corrupt file that asks for absurd sizes is an error code
+extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen) {
+	try {
+		return flatmapFromBsp(bsp, len, out, err, errlen);
+	} catch (const std::bad_alloc &) {
+		if (out) *out = nullptr;
+		if (err && errlen) snprintf(err, errlen, "CM_LoadMap: out of memory");
+		return CMGPU_ERR_NOMEM;
+	} catch (const std::exception &e) {
+		if (out) *out = nullptr;
+		if (err && errlen) snprintf(err, errlen, "CM_LoadMap: %s", e.what());
+		return CMGPU_ERR_BAD_MAP;
+	}
 }
 
 extern "C" void cmgpu_flatmap_free(cmgpu_flatmap *map) {

@@ -653,7 +653,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					const float mx = L.ax + fnear * (L.bx - L.ax);
 					const float my = L.ay + fnear * (L.by - L.ay);
 					const float mz = L.az + fnear * (L.bz - L.az);
-					if (L.sp < kMaxDepth) {
+					if (L.sp < q.stackDepth) {
 						float4 *sp4 = reinterpret_cast<float4 *>(stackAt(L.sp++));
 						__stcg(&sp4[0], make_float4(__int_as_float(far.num), far.f1, far.f2, far.ax));
 						__stcg(&sp4[1], make_float4(far.ay, far.az, far.bx, far.by));
@@ -720,7 +720,7 @@ traceFastKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					} else if (s == 2) {
 						L.num = nd.y;
 					} else {
-						if (L.sp < kMaxDepth) __stcg(&stackAt(L.sp++)->num, nd.y); else atomicOr(q.status, 1);
+						if (L.sp < q.stackDepth) __stcg(&stackAt(L.sp++)->num, nd.y); else atomicOr(q.status, 1);
 						L.num = nd.x;
 					}
 				}

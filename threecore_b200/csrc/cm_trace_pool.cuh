@@ -31,7 +31,6 @@ namespace cmgpu {
 #ifndef CMGPU_LEAF_ENTRIES
 #define CMGPU_LEAF_ENTRIES 4
 #endif
-constexpr int kPoolDepth = 32;           // pending far halves per item (CMGPU_ERR_LIMIT beyond)
 constexpr int kLeafEntries = CMGPU_LEAF_ENTRIES;  // stream entries a lane looks at per repeat of the leaf step
 constexpr int kNodeLevels = CMGPU_NODE_LEVELS;   // tree levels a lane may descend per repeat of the node step
 
@@ -144,7 +143,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 	// lives in arenaZ[d][slot], where the lanes of a warp are neighbours.
 	const size_t arenaSlots = (size_t)gridDim.x * kBlock * K;
 	float4 *const arena32 = reinterpret_cast<float4 *>(q.stackArena) + 2 * ((globalWarp * K) * 32 + lane);      // item j: + 2 * j * 32
-	float *const arenaZ = reinterpret_cast<float *>(reinterpret_cast<float4 *>(q.stackArena) + 2 * (size_t)kPoolDepth * arenaSlots)
+	float *const arenaZ = reinterpret_cast<float *>(reinterpret_cast<float4 *>(q.stackArena) + 2 * (size_t)q.stackDepth * arenaSlots)
 	                      + (globalWarp * K) * 32 + lane;
 #define STACKAT(j, d) (arena32 + 2 * ((size_t)(d) * arenaSlots + (size_t)(j) * 32))
 #define STACKZ(j, d) (arenaZ + (size_t)(d) * arenaSlots + (size_t)(j) * 32)
@@ -443,7 +442,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					if (COUNT) cSplits++;
 					const int fl = FLDI(PF_FLAGS, j);
 					const int sp = (fl >> 8) & 0xff;
-					if (sp < kPoolDepth) {
+					if (sp < q.stackDepth) {
 						float4 *sp4 = STACKAT(j, sp);
 						const unsigned long long keep = l2KeepPolicy();
 						stKeep32B(sp4, make_float4(__int_as_float(fwd ? nd.x : nd.y), f1 + (f2 - f1) * ffar, f2, ax_ + ffar * (bx_ - ax_)),
@@ -539,7 +538,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						} else {
 							const int fl = FLDI(PF_FLAGS, j);
 							const int sp = (fl >> 8) & 0xff;
-							if (sp < kPoolDepth) { __stcg(reinterpret_cast<int *>(STACKAT(j, sp)), nd.y); SETI(PF_FLAGS, j, fl + 256); }
+							if (sp < q.stackDepth) { __stcg(reinterpret_cast<int *>(STACKAT(j, sp)), nd.y); SETI(PF_FLAGS, j, fl + 256); }
 							else atomicOr(q.status, 1);
 							SETI(PF_CUR, j, nd.x);
 						}

@@ -11,12 +11,12 @@
 
 namespace cmgpu {
 
-template <bool COUNT>
+template <bool COUNT, int DEPTH = kMaxDepth>
 __global__ void __launch_bounds__(kBlock)
 traceSimpleKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 	const int slot = blockIdx.x * kBlock + threadIdx.x;
 	if (slot >= q.n) return;
-	FastSeg stack[kMaxDepth];            // local memory: per resident thread, not per item (small launches)
+	FastSeg stack[DEPTH];            // local memory: per resident thread, not per item (small launches)
 #define stackAt(d) (&stack[d])
 	FastLane L;
 	const int kind = beginFast<COUNT>(q, h, L, slot);
@@ -51,7 +51,7 @@ traceSimpleKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (s == 1) c = nd.x;
 				else if (s == 2) c = nd.y;
 				else {
-					if (L.sp < kMaxDepth) stackAt(L.sp++)->num = nd.y; else atomicOr(q.status, 1);
+					if (L.sp < DEPTH) stackAt(L.sp++)->num = nd.y; else atomicOr(q.status, 1);
 					c = nd.x;
 				}
 			}
@@ -133,7 +133,7 @@ traceSimpleKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 				if (fnear < 0) fnear = 0; else if (fnear > 1) fnear = 1;
 				if (ffar < 0) ffar = 0; else if (ffar > 1) ffar = 1;
 				if (COUNT) L.cSplits++;
-				if (L.sp < kMaxDepth) {
+				if (L.sp < DEPTH) {
 					float4 *sp4 = reinterpret_cast<float4 *>(stackAt(L.sp++));
 					sp4[0] = make_float4(__int_as_float(fwd ? nd.x : nd.y), L.f1 + (L.f2 - L.f1) * ffar, L.f2, L.ax + ffar * (L.bx - L.ax));
 					sp4[1] = make_float4(L.ay + ffar * (L.by - L.ay), L.az + ffar * (L.bz - L.az), L.bx, L.by);
