@@ -42,11 +42,11 @@ BYTES_PER_TRACE = 24 + 56          # ray record (start,end) + trace_t, shared hu
 METRIC = "Mtraces/s batched CM_BoxTrace"
 
 
-def workload_config(n_rays, parallelism):
+def workload_config(n_rays, gpus):
     return {"workload": "configs[1]: 16Mi player-hull box traces (mins -15,-15,-24 maxs 15,15,32, MASK_PLAYERSOLID) "
                         "on a synthetic 20k-brush arena BSP",
             "rays_per_gpu": n_rays, "brushes": N_BRUSHES, "map_seed": hex(MAP_SEED), "ray_seed": hex(RAY_SEED),
-            "parallelism": parallelism,
+            "parallelism": f"BSP replicated per GPU, rays sharded x{gpus} (the reference arm runs the same rays on the host cores)",
             "l2_policy": "inputs (384 MiB of rays + 896 MiB of results per step) are larger than the 126 MB L2; no flush needed"}
 
 
@@ -63,6 +63,32 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def parity_gate(eng, data, starts, ends, d_out, sample, seed):
+    """no timing is accepted before the records agree with the reference.  A random sample of this rank's
+    batch, traced by the unmodified reference (oracle/_ref, forked workers) or, when that library was not shipped, by
+    the oracle port; all 56 bytes of every sampled record must be equal."""
+    import torch
+    from oracle import cmref
+    n = len(starts)
+    idx = np.sort(np.random.default_rng(seed).choice(n, size=min(sample, n), replace=False))
+    got = d_out[torch.from_numpy(idx).to(d_out.device)].cpu().numpy()
+    s, e = np.ascontiguousarray(starts[idx]), np.ascontiguousarray(ends[idx])
+    if cmref.available():
+        _, _, want = cmref.RefCM().load(data).bench_box_trace(s, e, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID,
+                                                              nworkers=host_cores(), want_results=True)
+        against = "reference (oracle/_ref/libcmref.so)"
+    else:
+        from oracle import cmoracle
+        from threecore_b200.engine import FlatMap
+        want = cmoracle.OracleCM(FlatMap.from_bsp(data).to_dict()).box_trace(s, e, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS,
+                                                                             mask=bspgen.MASK_PLAYERSOLID)
+        against = "oracle port (oracle/cm_oracle.c)"
+    w = np.ascontiguousarray(want).view(np.uint8).reshape(-1, 56)
+    bad = int((got != w).any(axis=1).sum())
+    return {"checked": int(len(idx)), "mismatches": bad, "against": against,
+            "what": "all 56 bytes of trace_t, random sample of the timed batch, before timing"}
 
 
 def ncu_traffic():
@@ -178,7 +204,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mtraces/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": workload_config(N_RAYS, "cpu"),
+            "config": workload_config(N_RAYS, args.gpus),
             "cpu_baseline": {"value": value, "unit": "Mtraces/s", "cores": cores, "kind": kind, "sample": sample_txt},
             "e2e": {"value": value, "unit": "Mtraces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -223,6 +249,10 @@ def run_ours(args):
         step()
     eng.check_status()
     torch.cuda.synchronize()
+    # parity gate before any timing: rank 0 checks a large sample, the other ranks (same host cores) a small one
+    parity = parity_gate(eng, m.data, starts, ends, d_out, args.parity_sample if rank == 0 else 1 << 14, 77 + rank)
+    if parity["mismatches"]:
+        raise SystemExit(f"bench.py: parity gate failed on rank {rank}: {parity}")
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -321,7 +351,15 @@ def run_ours(args):
         achieved = BYTES_PER_TRACE * n / (kms * 1e-3) / 1e9
         tr = ncu_traffic()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (tr or {}).get("dram_bytes_per_launch") if n == N_RAYS else None, "peak_source": peak_src,
+                "traffic": (tr or {}).get("dram_bytes_per_launch") if n == N_RAYS else None,
+                "traffic_source": ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from the "
+                                   f"committed ncu capture {tr.get('source')} ({tr.get('captured', 'date not recorded')}), same command at 16 Mi rays")
+                                  if tr and n == N_RAYS else None,
+                "warp_efficiency": ({"lanes_per_instruction": tr.get("lanes_per_instruction"), "of": 32,
+                                     "issue_active_pct": tr.get("issue_active_pct"),
+                                     "source": f"smsp__thread_inst_executed_per_inst_executed.ratio of the walk kernel, committed ncu --set full capture {tr.get('full_source')}"}
+                                    if tr and tr.get("lanes_per_instruction") else None),
+                "peak_source": peak_src,
                 "kernel": "cmgpu::tracePoolKernel<false, 3> + cmgpu::expandRecordsKernel (the two phases of one trace launch: "
                           "the walk stores 16 B per item, the expansion writes the 56-byte records; kernel_ms and traffic cover both)",
                 "kernel_ms": kms, "kernel_launches": trace_launches,
@@ -332,7 +370,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": "Mtraces/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-                "config": workload_config(n, f"replicated BSP, rays sharded x{world}"),
+                "config": workload_config(n, world),
+                "parity": parity,
                 "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": "Mtraces/s", "h2d_bytes_per_step": int(24 * n),
                         "d2h_bytes_per_step": int(56 * n), "steps": e2e_steps, "matches_resident": same},
@@ -362,6 +401,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1 << 24,
                     help="rays per reference/cpu_baseline step (default: the whole 16 Mi workload, ~17 s of CPU work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-sample", type=int, default=1 << 21, help="records checked against the reference before timing")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
