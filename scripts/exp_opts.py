@@ -21,6 +21,8 @@ for spec in ["base"] + sys.argv[1:] + ["base"]:
     opts = {} if spec == "base" else {kv.split("=")[0]: float(kv.split("=")[1]) for kv in spec.split(",")}
     for k, v in opts.items():
         eng.set_option(k, v)
+    if "entry_cell" in opts or "l2_window" in opts:      # options that take effect at upload
+        eng.load_bsp(m.data)
     fn = lambda: eng.box_trace_device(ds, de, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, out)
     for _ in range(2): fn()
     eng.kernel_timing(True)

@@ -329,7 +329,7 @@ def test_binned_order_equals_input_order(eng, big):
 
 @pytest.mark.parametrize("opts", [dict(pool=0), dict(pool=0, slab=0), dict(fast=0), dict(pool=1, slab=0), dict(pool=1, pool_reps=5, gang=8),
                                   dict(pool=0, simple_max_items=1 << 21), dict(pool=0, simple_max_items=1 << 21, bin=0, slab=0),
-                                  dict(two_phase=0), dict(node_thresholds=0), dict(node_thresholds=0, compact_by_item=0), dict(two_phase=0, pool=0), dict(two_phase_small=1, pool=0), dict(two_phase_small=1, pool=0, simple_max_items=1 << 21)])
+                                  dict(two_phase=0), dict(entry_grid=0), dict(node_thresholds=0), dict(node_thresholds=0, compact_by_item=0), dict(two_phase=0, pool=0), dict(two_phase_small=1, pool=0), dict(two_phase_small=1, pool=0, simple_max_items=1 << 21)])
 def test_kernel_variants_agree(eng, big, opts):
     """the general kernel, the one-item-per-lane hot kernel and the pool kernel must return the same bytes"""
     import torch
@@ -342,7 +342,7 @@ def test_kernel_variants_agree(eng, big, opts):
         torch.cuda.synchronize()
         eng.check_status()
     finally:
-        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=1, gang=4, simple_max_items=786432, bin=1, two_phase=1, two_phase_small=0, node_thresholds=1, compact_by_item=1).items():
+        for k, v in dict(pool=1, fast=1, slab=1, pool_reps=1, gang=4, gang_pool=3, simple_max_items=786432, bin=1, two_phase=1, two_phase_small=0, node_thresholds=1, compact_by_item=1, entry_grid=1).items():
             eng.set_option(k, v)
     assert torch.equal(o, big["out"][:n])
 

@@ -86,6 +86,7 @@ struct cmgpu_ctx_s {
 	bool slabOK = false;                 // all brush bounds below 2^15 in magnitude
 	bool slabTest = true;
 	int gang = kGang;
+	int gangPool = 3;                    // pool kernel: eighths of the most popular kind's lane count a kind needs to run (measured: 3 beats 4 by 1 %)
 	int gangFetch = kGang;
 	int gangBrush = 5;                   // pool kernel: eighths of the most popular kind's lane count that must wait for a brush clip ...
 	int gangFetchPool = 6;               // ... and for the fetch step, before it runs (measured: +0.7 % over 4 / 4)
@@ -107,7 +108,10 @@ struct cmgpu_ctx_s {
 	std::vector<void *> retired;
 	bool twoPhase = true, twoPhaseHost = false, twoPhaseSmall = false, compactByItem = true;
 	// pool kernel: per-hull node threshold tables (nodeThresholdKernel), built on first use, dropped with the map
-	struct HullTable { NodeHull key; DevBuf buf; bool usable; };
+	struct HullTable { NodeHull key; DevBuf buf; bool usable; DevBuf cells; bool gridUsable; };
+	EntryGrid entry{};                   // geometry of the entry grid and the heap of the top levels (cellRec is per hull: HullTable::cells)
+	bool entryGrid = true;
+	float entryCell = 128.0f;            // target cell size of the entry grid, world units
 	std::vector<HullTable> hullTables;
 	bool nodeThresholds = true;                // binned hot launches: 16-byte results by slot + expandRecordsKernel
 	DevBuf bPoolHdr[kBinSlots + 1];
@@ -259,7 +263,7 @@ void freeMap(cmgpu_ctx *ctx) {
 	memset(&ctx->map, 0, sizeof(ctx->map));
 	memset(&ctx->fast, 0, sizeof(ctx->fast));
 	ctx->numPatches = 0;
-	for (auto &t : ctx->hullTables) releaseBuf(t.buf);
+	for (auto &t : ctx->hullTables) { releaseBuf(t.buf); releaseBuf(t.cells); }
 	ctx->hullTables.clear();
 	for (void *p : ctx->retired) cudaFree(p);
 	ctx->retired.clear();
@@ -575,6 +579,23 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 			if (nd.y < 0) nd.y = -1 - streamStart[-1 - nd.y];
 			fnodes[i] = nd;
 		}
+		// the first kEntryLevels levels of the tree in heap order (EntryGrid::top): entry (1 << L) - 1 + path is where the L
+		// decisions `path` (first decision = most significant bit, 1 = children[0]) lead; positions below a leaf stay 0
+		std::vector<int> top(((size_t)2 << kEntryLevels), 0);
+		{
+			struct T { int ref, level; unsigned path; };
+			std::vector<T> st;
+			st.push_back({0, 0, 0u});
+			while (!st.empty()) {
+				const T t = st.back();
+				st.pop_back();
+				top[((size_t)1 << t.level) - 1 + t.path] = t.ref;
+				if (t.ref < 0 || t.level == kEntryLevels) continue;
+				st.push_back({fnodes[t.ref].x, t.level + 1, (t.path << 1) | 1u});
+				st.push_back({fnodes[t.ref].y, t.level + 1, t.path << 1});
+			}
+		}
+		if ((rc = uploadArray(ctx, top, &ctx->entry.top)) != CMGPU_OK) return rc;
 		std::vector<float4> brushRec(2 * (size_t)f->numBrushes);
 		std::vector<int> brushContents((size_t)f->numBrushes);
 		for (int i = 0; i < f->numBrushes; i++) {
@@ -633,6 +654,39 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		g.longLen2 = ctx->binLongLen * ctx->binLongLen;
 		g.dirBins = ctx->binDir ? 8 : 1;
 		g.numBins = 2 * kBinClasses * g.cells[0] * g.cells[1] * g.cells[2] * g.dirBins;   // x2: point hulls / box hulls of per-item batches
+	}
+	{	// entry grid (EntryGrid): cells of about entryCell units over the bounds of the world's brushes, at most 2^20 of them
+		float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+		for (int i = 0; i < f->numBrushes; i++) {
+			if (i == f->boxBrush) continue;
+			const float *bb = f->brushBounds + 6 * (size_t)i;
+			for (int a = 0; a < 3; a++) {
+				if (bb[a] < lo[a]) lo[a] = bb[a];
+				if (bb[3 + a] > hi[a]) hi[a] = bb[3 + a];
+			}
+		}
+		EntryGrid &e = ctx->entry;
+		int bits[3], total = 0;
+		for (int a = 0; a < 3; a++) {
+			float ext = hi[a] - lo[a];
+			if (!(ext > 1.0f) || !(ext < 1e9f)) ext = 1.0f;
+			bits[a] = 0;
+			while (bits[a] < 10 && ext / (float)(1 << bits[a]) > ctx->entryCell) bits[a]++;
+			total += bits[a];
+		}
+		while (total > 20) {
+			const int a = bits[0] >= bits[1] ? (bits[0] >= bits[2] ? 0 : 2) : (bits[1] >= bits[2] ? 1 : 2);
+			bits[a]--;
+			total--;
+		}
+		for (int a = 0; a < 3; a++) {
+			float ext = hi[a] - lo[a];
+			if (!(ext > 1.0f) || !(ext < 1e9f)) ext = 1.0f;
+			e.cells[a] = 1 << bits[a];
+			e.lo[a] = lo[a];
+			e.inv[a] = (float)e.cells[a] / ext;
+		}
+		e.cellRec = nullptr;
 	}
 	m.numNodes = f->numNodes;
 	m.numModels = f->numModels;
@@ -699,24 +753,28 @@ FastHull makeFastHull(const float *mins, const float *maxs, int mask, bool slabO
 // The node table of a hull (cm_trace_pool.cuh, nodeThresholdKernel): looked up by the bits of the six thresholds, built
 // on first use.  Building synchronises the stream once per (map, hull); a table whose boundaries could not be verified
 // on the device is marked unusable and the launch takes the plain node step.
-const int4 *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStream_t s) {
+const cmgpu_ctx::HullTable *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStream_t s) {
 	NodeHull key;
 	for (int a = 0; a < 3; a++) { key.hi[a] = h.nodeHi[a]; key.lo[a] = h.nodeLo[a]; }
 	for (auto &t : ctx->hullTables) {
-		if (!memcmp(&t.key, &key, sizeof(key))) return t.usable ? (const int4 *)t.buf.p : nullptr;
+		if (!memcmp(&t.key, &key, sizeof(key))) return t.usable ? &t : nullptr;
 	}
 	if (ctx->capturing) return nullptr;                   // building synchronises: not inside a capture (plain node step instead)
 	if (ctx->hullTables.size() >= 8) {                    // a ninth hull: start over (nothing may still read the old tables)
 		cudaDeviceSynchronize();
 		for (auto &t : ctx->hullTables) {
-			if (ctx->graphPinned && t.buf.p) { ctx->retired.push_back(t.buf.p); t.buf = DevBuf{}; }
-			else releaseBuf(t.buf);
+			if (ctx->graphPinned) {
+				if (t.buf.p) ctx->retired.push_back(t.buf.p);
+				if (t.cells.p) ctx->retired.push_back(t.cells.p);
+				t.buf = DevBuf{}; t.cells = DevBuf{};
+			} else { releaseBuf(t.buf); releaseBuf(t.cells); }
 		}
 		ctx->hullTables.clear();
 	}
 	cmgpu_ctx::HullTable t{};
 	t.key = key;
 	t.usable = false;
+	t.gridUsable = false;
 	const int n = ctx->map.numNodes;
 	const size_t bytes = (size_t)n * sizeof(int4);
 	if (reserve(ctx, t.buf, bytes + 16) == CMGPU_OK) {
@@ -729,9 +787,22 @@ const int4 *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStream_t s) {
 		ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
 		t.usable = ok && hostFlag == 0;
 		ctx->launches++;
+		// the entry grid of this hull (entryGridKernel): built from the table just made, verified on the device like it
+		const EntryGrid &e = ctx->entry;
+		const int cells = e.cells[0] * e.cells[1] * e.cells[2];
+		if (t.usable && ctx->entryGrid && e.top && cells > 1 && reserve(ctx, t.cells, (size_t)cells * sizeof(uint2)) == CMGPU_OK) {
+			hostFlag = -1;
+			ok = cudaMemsetAsync(flag, 0, sizeof(int), s) == cudaSuccess;
+			if (ok) entryGridKernel<<<(cells + 255) / 256, 256, 0, s>>>((const int4 *)t.buf.p, e, (uint2 *)t.cells.p, flag);
+			ok = ok && cudaGetLastError() == cudaSuccess;
+			ok = ok && cudaMemcpyAsync(&hostFlag, flag, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+			ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+			t.gridUsable = ok && hostFlag == 0;
+			ctx->launches++;
+		}
 	}
 	ctx->hullTables.push_back(t);
-	return t.usable ? (const int4 *)t.buf.p : nullptr;
+	return t.usable ? &ctx->hullTables.back() : nullptr;
 }
 
 // Device-pointer calls share the context's workspaces.  Whatever such a call leaves running on its stream, the next
@@ -861,6 +932,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	} else if (pool) {
 		q.lightReps = ctx->poolReps;
 		q.gangFetch = ctx->gangFetchPool;
+		q.gang = ctx->gangPool;
 		int rcA = reserve(ctx, ctx->bStackArena[arenaSlot], (size_t)resident * kBlock * CMGPU_POOL_K * q.stackDepth * sizeof(FastSeg));
 		if (rcA) return rcA;
 		q.stackArena = (FastSeg *)ctx->bStackArena[arenaSlot].p;
@@ -868,7 +940,10 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		if (rcA) return rcA;
 		q.poolHdr = ctx->bPoolHdr[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
-		q.tnodes = (ctx->nodeThresholds && !ctx->counting) ? hullTable(ctx, h, s) : nullptr;
+		const cmgpu_ctx::HullTable *ht = (ctx->nodeThresholds && !ctx->counting) ? hullTable(ctx, h, s) : nullptr;
+		q.tnodes = ht ? (const int4 *)ht->buf.p : nullptr;
+		q.entry = ctx->entry;
+		q.entry.cellRec = (ht && ht->gridUsable && ctx->entryGrid) ? (const uint2 *)ht->cells.p : nullptr;
 		if (ctx->counting)  CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<true, CMGPU_POOL_K, false>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 		else if (q.tnodes)  CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, true>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 		else                CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, false>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
@@ -1070,7 +1145,10 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "two_phase_small") ctx->twoPhaseSmall = value != 0;
 	else if (k == "compact_by_item") ctx->compactByItem = value != 0;
 	else if (k == "node_thresholds") ctx->nodeThresholds = value != 0;
-	else if (k == "gang") ctx->gang = (int)value;
+	else if (k == "entry_grid") ctx->entryGrid = value != 0;
+	else if (k == "entry_cell") { if (!(value >= 8.0)) return fail(ctx, CMGPU_ERR_INVALID, "entry_cell must be >= 8"); ctx->entryCell = (float)value; }   // takes effect at the next cmgpu_upload
+	else if (k == "gang") ctx->gang = ctx->gangPool = (int)value;
+	else if (k == "gang_pool") ctx->gangPool = (int)value;
 	else if (k == "gang_fetch") ctx->gangFetch = ctx->gangFetchPool = (int)value;
 	else if (k == "gang_brush") ctx->gangBrush = (int)value;
 	else if (k == "facet_steps") ctx->facetSteps = value < 1 ? 1 : (int)value;

@@ -103,6 +103,23 @@ __device__ __forceinline__ void stKeep32B(float4 *p, const float4 a, const float
 	             :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
 }
 
+// ---- entry grid of the pool kernel (cm_trace_pool.cuh): where the plain descent of a sweep ends ------------------
+// The first thing CM_TraceThroughTree does with a sweep is walk down from the root while both end points lie on the
+// same side of every plane by more than the hull (cm_trace.c:483-490).  With the hull folded into thresholds on the
+// coordinates (nodeThresholdKernel) that part of the walk depends on nothing but WHERE the two points are, so it is
+// tabulated: a uniform grid over the world; per cell the path (one bit per level) and the node that every point of the
+// cell reaches by plain descents alone.  The sweep starts at the deepest common ancestor of its two cells' nodes, found
+// from the two paths with a few bit operations and, when neither cell's node is that ancestor, one lookup in `top`, the
+// first `levels` levels of the tree in heap order.
+constexpr int kEntryLevels = 14;         // levels the table may skip (path bits of a cell record)
+constexpr float kEntryMaxCoord = 32768.0f;   // items with a coordinate beyond this take the walk from the root
+struct EntryGrid {
+	float lo[3], inv[3];                 // cell along an axis = clamp((int)((p - lo) * inv), 0, cells - 1): monotone in p
+	int   cells[3];
+	const uint2 *cellRec;                // [z][y][x] {path | depth << 16, node or leaf-stream reference}; null: no grid
+	const int   *top;                    // [(1 << L) - 1 + path]: the node (or leaf) `path` leads to after L levels
+};
+
 struct TraceBatch {
 	int n;
 	const float *starts, *ends;          // [n][3]
@@ -134,6 +151,7 @@ struct TraceBatch {
 	                                     // hit brush); expandRecordsKernel writes the 56-byte records in item order.  null: direct
 	const int4 *tnodes;                  // pool kernel: nodes with this batch's hull folded into two thresholds (nodeThresholdKernel); may be null
 	int compactByItem;                   // pool kernel: compact[] is indexed by item number (a 16-byte scatter), not by slot
+	EntryGrid entry;                     // pool kernel with tnodes: where an item's walk starts (cellRec null: at the root)
 };
 
 // ---- spatial binning of a batch (counting sort by start cell) -------------------------------

@@ -31,6 +31,9 @@ namespace cmgpu {
 #ifndef CMGPU_LEAF_ENTRIES
 #define CMGPU_LEAF_ENTRIES 4
 #endif
+#ifndef CMGPU_SLAB_HOIST
+#define CMGPU_SLAB_HOIST 1
+#endif
 constexpr int kLeafEntries = CMGPU_LEAF_ENTRIES;  // stream entries a lane looks at per repeat of the leaf step
 constexpr int kNodeLevels = CMGPU_NODE_LEVELS;   // tree levels a lane may descend per repeat of the node step
 
@@ -123,6 +126,91 @@ __global__ void __launch_bounds__(256) nodeThresholdKernel(const int4 *nodes, co
 	}
 	if (nd.x >= (1 << 29) || nd.x < -(1 << 29)) atomicOr(status, 2);
 	out[i] = make_int4((int)(((unsigned)nd.x << 2) | (unsigned)(nd.z & 3)), nd.y, __float_as_int(tHi), __float_as_int(tLo));
+}
+
+// ---- entry grid (EntryGrid, cm_kernels.cuh) ----------------------------------------------------------------------
+__device__ __forceinline__ int entryCellAxis(const float p, const float lo, const float inv, const int cells) {
+	const float t = (p - lo) * inv;                    // two separately rounded operations: monotone in p
+	const int c = (int)t;                              // truncation: monotone too
+	return min(max(c, 0), cells - 1);
+}
+
+// smallest float in [-kEntryMaxCoord, kEntryMaxCoord] whose cell along the axis is >= want (kEntryMaxCoord's
+// successor when there is none): bisection over the floats in numeric order, like smallestReaching
+__device__ __forceinline__ float entryCellStart(const float glo, const float ginv, const int cells, const int want) {
+	if (entryCellAxis(-kEntryMaxCoord, glo, ginv, cells) >= want) return -kEntryMaxCoord;
+	if (entryCellAxis(kEntryMaxCoord, glo, ginv, cells) < want) return nextafterf(kEntryMaxCoord, INFINITY);
+	unsigned lo = floatOrderKey(-kEntryMaxCoord), hi = floatOrderKey(kEntryMaxCoord);   // predicate false at lo, true at hi
+	while (hi - lo > 1u) {
+		const unsigned mid = lo + ((hi - lo) >> 1);
+		if (entryCellAxis(floatFromOrderKey(mid), glo, ginv, cells) >= want) hi = mid; else lo = mid;
+	}
+	return floatFromOrderKey(hi);
+}
+
+// One thread per cell.  The cell's points along an axis are the floats [first, last] (within +-kEntryMaxCoord; items
+// beyond that do not use the grid); a node is passed by a plain descent of EVERY point of the cell when first >= tHi
+// (front) or last < tLo (back) -- the very comparisons the node step makes.  The walk stops at the first node that
+// some point of the cell does not pass that way, at a leaf, or after kEntryLevels levels.
+__global__ void __launch_bounds__(256) entryGridKernel(const int4 *tnodes, const EntryGrid g, uint2 *out, int *status) {
+	const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+	const int total = g.cells[0] * g.cells[1] * g.cells[2];
+	if (cell >= total) return;
+	const int ix = cell % g.cells[0], iy = (cell / g.cells[0]) % g.cells[1], iz = cell / (g.cells[0] * g.cells[1]);
+	float first[3], last[3];
+	const int idx[3] = {ix, iy, iz};
+	bool ok = true;
+	#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		first[a] = entryCellStart(g.lo[a], g.inv[a], g.cells[a], idx[a]);
+		const float next = entryCellStart(g.lo[a], g.inv[a], g.cells[a], idx[a] + 1);
+		last[a] = nextafterf(next, -INFINITY);
+		// the boundaries must be exact (else: no grid for this map): both ends map to this cell, their outer neighbours do not
+		if (first[a] <= last[a]) {
+			ok = ok && entryCellAxis(first[a], g.lo[a], g.inv[a], g.cells[a]) == idx[a] && entryCellAxis(last[a], g.lo[a], g.inv[a], g.cells[a]) == idx[a];
+			if (first[a] > -kEntryMaxCoord) ok = ok && entryCellAxis(nextafterf(first[a], -INFINITY), g.lo[a], g.inv[a], g.cells[a]) < idx[a];
+			if (last[a] < kEntryMaxCoord) ok = ok && entryCellAxis(next, g.lo[a], g.inv[a], g.cells[a]) > idx[a];
+		}
+	}
+	if (!ok) atomicOr(status, 2);
+	int node = 0, depth = 0;
+	unsigned path = 0u;
+	const bool empty = first[0] > last[0] || first[1] > last[1] || first[2] > last[2];    // no float maps here: never looked up
+	while (!empty && node >= 0 && depth < kEntryLevels) {
+		const int4 nd = tnodes[node];
+		const int ax = nd.x & 3;
+		if (ax == 3) break;
+		const float tHi = __int_as_float(nd.z), tLo = __int_as_float(nd.w);
+		const float f = ax == 0 ? first[0] : (ax == 1 ? first[1] : first[2]);
+		const float l = ax == 0 ? last[0] : (ax == 1 ? last[1] : last[2]);
+		int next;
+		if (f >= tHi) { next = nd.x >> 2; path = (path << 1) | 1u; }
+		else if (l < tLo) { next = nd.y; path = path << 1; }
+		else break;
+		node = next;
+		depth++;
+	}
+	out[cell] = make_uint2(path | ((unsigned)depth << 16), (unsigned)node);
+}
+
+// where the walk of the sweep a -> b starts (a node, or a leaf-stream reference < 0)
+__device__ __forceinline__ int entryLookup(const EntryGrid &g, const float ax, const float ay, const float az,
+                                           const float bx, const float by, const float bz) {
+	const int ca = (entryCellAxis(az, g.lo[2], g.inv[2], g.cells[2]) * g.cells[1] + entryCellAxis(ay, g.lo[1], g.inv[1], g.cells[1])) * g.cells[0]
+	               + entryCellAxis(ax, g.lo[0], g.inv[0], g.cells[0]);
+	const int cb = (entryCellAxis(bz, g.lo[2], g.inv[2], g.cells[2]) * g.cells[1] + entryCellAxis(by, g.lo[1], g.inv[1], g.cells[1])) * g.cells[0]
+	               + entryCellAxis(bx, g.lo[0], g.inv[0], g.cells[0]);
+	const uint2 ra = __ldg(&g.cellRec[ca]);
+	const uint2 rb = __ldg(&g.cellRec[cb]);
+	const int da = (int)(ra.x >> 16), db = (int)(rb.x >> 16);
+	const unsigned pa = ra.x & 0xffffu, pb = rb.x & 0xffffu;
+	const int m = min(da, db);
+	const unsigned xa = pa >> (da - m), xb = pb >> (db - m);
+	const unsigned x = xa ^ xb;
+	const int L = x ? m - (32 - __clz((int)x)) : m;      // levels the two paths share
+	if (L == da) return (int)ra.y;                        // a's node is b's node or one of its ancestors
+	if (L == db) return (int)rb.y;
+	return __ldg(&g.top[(1 << L) - 1 + (int)(xa >> (m - L))]);
 }
 
 template <bool COUNT, int K, bool THR>
@@ -244,7 +332,18 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 					FLD(PF_SX, j) = L.sx; FLD(PF_SY, j) = L.sy; FLD(PF_SZ, j) = L.sz;
 					FLD(PF_EX, j) = L.ex; FLD(PF_EY, j) = L.ey; FLD(PF_EZ, j) = L.ez;
 					FLD(PF_FRACTION, j) = 1.0f; SETI(PF_FLAGS, j, L.flags);
-					SETI(PF_CUR, j, 0);
+					int cur0 = 0;
+					int m0 = m == FM_PNODE ? PM_POS : PM_NODE;
+					if (THR && !COUNT && q.entry.cellRec && m != FM_PNODE) {
+						// skip the plain descents at the top of the tree (EntryGrid); NaNs fail the comparisons
+						const bool inGrid = fabsf(L.sx) <= kEntryMaxCoord && fabsf(L.sy) <= kEntryMaxCoord && fabsf(L.sz) <= kEntryMaxCoord &&
+						                    fabsf(L.ex) <= kEntryMaxCoord && fabsf(L.ey) <= kEntryMaxCoord && fabsf(L.ez) <= kEntryMaxCoord;
+						if (inGrid) {
+							const int c = entryLookup(q.entry, L.sx, L.sy, L.sz, L.ex, L.ey, L.ez);
+							if (c < 0) { cur0 = -1 - c; m0 = PM_LEAF; } else cur0 = c;
+						}
+					}
+					SETI(PF_CUR, j, cur0);
 					FLD(PF_F1, j) = 0.0f; FLD(PF_F2, j) = 1.0f;
 					FLD(PF_AX, j) = L.sx; FLD(PF_AY, j) = L.sy; FLD(PF_AZ, j) = L.sz;
 					FLD(PF_BX, j) = L.ex; FLD(PF_BY, j) = L.ey; FLD(PF_BZ, j) = L.ez;
@@ -252,7 +351,7 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 #if CMGPU_POOL_LAST2
 					SETI(PF_LAST1, j, -1);
 #endif
-					modes = withMode(modes, j, m == FM_PNODE ? PM_POS : PM_NODE);
+					modes = withMode(modes, j, m0);
 				} else {
 					stKeep32(&HDR(j).slot, -1, l2KeepPolicy());        // nothing to write back next time
 					if (!supply) modes = withMode(modes, j, PM_EMPTY); // else: stays PM_DONE and asks again
@@ -345,9 +444,13 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 #if CMGPU_INLINE_SLAB
 					// the float slab pre-test (slabReject) right here, on the entry that is in registers anyway: an entry it
 					// rejects is a certain no-op and the scan goes on, instead of two more rounds (SLAB, then LEAF again)
+#if CMGPU_SLAB_HOIST
+					const SlabItem S = slabItem(h, sx, sy, sz, ex, ey, ez, FLD(PF_FRACTION, j));
+#else
 					FastLane S;
 					S.sx = sx; S.sy = sy; S.sz = sz; S.ex = ex; S.ey = ey; S.ez = ez;
 					S.fraction = FLD(PF_FRACTION, j);
+#endif
 					const bool slabOn = (FLDI(PF_FLAGS, j) & 4) != 0;
 #endif
 					#pragma unroll
@@ -357,7 +460,11 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						const bool apart = hix < e0[i].x || hiy < e0[i].y || hiz < e0[i].z || lox > e1[i].x || loy > e1[i].y || loz > e1[i].z;
 #if CMGPU_INLINE_SLAB
 						bool clipi = want && !apart;                                   // CM_BoundsIntersect passed
+#if CMGPU_SLAB_HOIST
+						if (!stopped && clipi && slabOn && slabRejectPre(S, e0[i], e1[i])) clipi = false;
+#else
 						if (!stopped && clipi && slabOn && slabReject(h, S, e0[i], e1[i])) clipi = false;
+#endif
 #else
 						const bool clipi = want && !apart;                             // CM_BoundsIntersect passed
 #endif
