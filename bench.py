@@ -211,6 +211,182 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---- the other arms of the line (the multi-GPU data path, the host copy ceiling, pageable callers) ----
+def _max_over_ranks(x, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+
+def arm_host_copy_ceiling(dev, world, n, h_starts, h_ends, h_out, d_starts, d_ends, d_out, reps=3):
+    """What the box's PCIe path gives this job with NO kernel in the way: every rank copies one step's rays host->device
+    and one step's records device->host at the same time (pinned memory, two streams), all ranks together.  The end to
+    end arm cannot beat n / that time."""
+    import torch
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def once():
+        with torch.cuda.stream(s_in):
+            d_starts.copy_(h_starts, non_blocking=True)
+            d_ends.copy_(h_ends, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+    once()
+    _barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    secs = _max_over_ranks(time.perf_counter() - t0, dev, world) / reps
+    return {"secs_per_step": secs, "gbs": world * 80.0 * n / secs / 1e9, "copy_bound_mtraces": world * n / secs / 1e6,
+            "what": f"{world} rank(s) at once, each: 24 B/trace host->device + 56 B/trace device->host, pinned, concurrent, no kernels"}
+
+
+def arm_e2e_pageable(eng, dev, world, n, starts, ends, steps=2):
+    """The host-pointer call on plain malloc'ed arrays (what a caller that never heard of CUDA passes): as they are (the
+    driver stages every copy and blocks, nothing overlaps), and after cmgpu_host_register of the same three arrays."""
+    out = np.empty((n, 56), np.uint8)
+
+    def step():
+        eng.box_trace_hostptr(n, starts.ctypes.data, ends.ctypes.data, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS,
+                              bspgen.MASK_PLAYERSOLID, out.ctypes.data)
+
+    def timed(k):
+        step()
+        _barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            step()
+        return world * n * k / _max_over_ranks(time.perf_counter() - t0, dev, world) / 1e6
+    res = {"unit": "Mtraces/s", "unregistered": timed(1)}
+    t0 = time.perf_counter()
+    for a in (starts, ends, out):
+        eng.host_register(a.ctypes.data, a.nbytes)
+    res["register_ms_once"] = 1e3 * (time.perf_counter() - t0)
+    res["registered"] = timed(steps)
+    for a in (starts, ends, out):
+        eng.host_unregister(a.ctypes.data)
+    res["what"] = ("cmgpu_box_trace_batch on numpy (pageable) arrays: `unregistered` = as they are, `registered` = after "
+                   "cmgpu_host_register of rays and results (one-time cost register_ms_once)")
+    return res, out
+
+
+def arm_gathered(eng, dev, world, rank, n, d_starts, d_ends, d_out, steps):
+    """north_star's data path: every rank traces its shard and its kernels store the records straight into rank 0's HBM
+    over NVLink (sharding.PeerResults); the timed region ends when all records have landed."""
+    import torch
+    import torch.distributed as dist
+    from threecore_b200.sharding import PeerResults
+    pr = PeerResults(eng, n * world)
+    lo = rank * n
+
+    def step():
+        eng.box_trace_device(d_starts, d_ends, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, pr.pointer(lo))
+    for _ in range(2):
+        step()
+    _barrier(world)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    _barrier(world)
+    ms = _max_over_ranks(a.elapsed_time(b), dev, world) / steps
+    eng.check_status()
+    # every rank's shard in rank 0's buffer must be the records that rank holds locally (64-bit word sums)
+    mine = d_out.view(torch.int64).sum().reshape(1)
+    sums = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(sums, mine)
+    else:
+        sums = [mine]
+    ok = None
+    if rank == 0:
+        rec = pr.records()
+        ok = all(int(rec[r * n:(r + 1) * n].view(torch.int64).sum().item()) == int(sums[r].item()) for r in range(world))
+    pr.close()
+    return {"value": world * n / ms / 1e3, "unit": "Mtraces/s", "ms_per_step": ms, "verified": ok,
+            "rank0_ingress_gbs": (world - 1) * n * 56 / ms / 1e6,
+            "what": f"{world} x {n} rays, all {world * n} trace_t records landing in rank 0's HBM inside the timed region "
+                    "(peer stores of the trace kernels over NVLink, no gather pass)"}
+
+
+def arm_strong(eng, dev, world, rank, n, starts, ends, d_out_rank0_full, steps):
+    """Strong scaling: BASELINE's 16 Mi batch (rank 0's stream) split into `world` contiguous ranges, records kept on the
+    ranks (`value`) and gathered into rank 0's HBM (`gathered`)."""
+    import torch
+    from threecore_b200.sharding import PeerResults, shard_range
+    if rank != 0:
+        _, starts, ends = make_workload(n, 0)          # the one global batch; rank 0 already holds it
+    lo, hi = shard_range(n, rank, world)
+    ds, de = torch.from_numpy(starts[lo:hi]).to(dev), torch.from_numpy(ends[lo:hi]).to(dev)
+    local = torch.empty((hi - lo, 56), dtype=torch.uint8, device=dev)
+    pr = PeerResults(eng, n)
+
+    def timed(target):
+        for _ in range(2):
+            eng.box_trace_device(ds, de, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, target)
+        _barrier(world)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            eng.box_trace_device(ds, de, bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, target)
+        b.record()
+        _barrier(world)
+        return _max_over_ranks(a.elapsed_time(b), dev, world) / steps
+    ms_local = timed(local)
+    ms_gath = timed(pr.pointer(lo))
+    eng.check_status()
+    ok = bool(torch.equal(pr.records(), d_out_rank0_full)) if rank == 0 else None
+    pr.close()
+    return {"value": n / ms_local / 1e3, "unit": "Mtraces/s", "ms_per_step": ms_local, "rays_total": n, "rays_per_gpu": hi - lo,
+            "gathered": {"value": n / ms_gath / 1e3, "ms_per_step": ms_gath, "equals_single_gpu_records": ok,
+                         "rank0_ingress_gbs": (n - (n // world)) * 56 / ms_gath / 1e6},
+            "limiter": "a launch of n/N rays still pays the five binning launches, the expansion launch and the walk of its slowest warp "
+                       "(the per-launch floor is ~0.3 ms; see DESIGN.md 5)"}
+
+
+def arm_rollout(local, dev, world, rank, ticks=40):
+    """BASELINE config 5: 65 536 Pmove-shaped agents x 10 traces per tick on the 50k-brush arena, agents sharded by id,
+    the tick replayed as a CUDA graph (threecore_b200/rollout.py)."""
+    import torch
+    from threecore_b200.engine import Engine
+    from threecore_b200.rollout import Rollout, TRACES_PER_TICK
+    from threecore_b200.sharding import shard_range
+    agents = 65536
+    m = bspgen.arena_map(n_brushes=50000, seed=0xC0FFEE05)
+    e2 = Engine(local)
+    try:
+        e2.load_bsp(m.data)
+        lo, hi = shard_range(agents, rank, world)
+        ro = Rollout(e2, hi - lo, m.world_mins, m.world_maxs, seed=9, first_agent=lo).capture(warmup=3)
+        ro.run(3)
+        _barrier(world)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ro.run(ticks)
+        b.record()
+        _barrier(world)
+        ms = _max_over_ranks(a.elapsed_time(b), dev, world) / ticks
+        e2.check_status()
+    finally:
+        e2.close()
+    return {"value": agents * TRACES_PER_TICK / ms / 1e3, "unit": "Mtraces/s", "ms_per_tick": ms, "agents": agents,
+            "agents_per_gpu": hi - lo, "brushes": 50000, "scaling": "strong (agents sharded by id)",
+            "limiter": "a tick is eight DEPENDENT trace launches; each waits for its slowest walk"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -310,6 +486,26 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     # the e2e results must be the same records the resident arm produced
     same = bool(torch.equal(h_out[: 1 << 16], d_out[: 1 << 16].cpu()))
+    extra = {}
+    if not args.no_extra_arms:
+        def attempt(name, fn):
+            try:
+                extra[name] = fn()
+            except Exception as ex:                       # an extra arm never takes the headline down with it
+                extra[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                torch.cuda.synchronize()
+        attempt("host_copy", lambda: arm_host_copy_ceiling(dev, world, n, h_starts, h_ends, h_out, d_starts, d_ends, d_out))
+    if not args.no_extra_arms:
+        def pageable():
+            res, out = arm_e2e_pageable(eng, dev, world, n, starts, ends)
+            res["matches_resident"] = bool(np.array_equal(out[: 1 << 16], d_out[: 1 << 16].cpu().numpy()))
+            return res
+        attempt("e2e_pageable", pageable)
+        del h_starts, h_ends, h_out
+        if world > 1:
+            attempt("gathered", lambda: arm_gathered(eng, dev, world, rank, n, d_starts, d_ends, d_out, max(2, min(args.steps, 5))))
+        attempt("strong", lambda: arm_strong(eng, dev, world, rank, n, starts, ends, d_out, max(2, min(args.steps, 5))))
+        attempt("rollout", lambda: arm_rollout(local, dev, world, rank))
 
     # ---- L2 working-set roofline: visit counts of this very batch from the counting kernel variant (untimed),
     # priced with the reference's own record sizes, against an L2-resident copy measured here
@@ -374,7 +570,14 @@ def run_ours(args):
                 "parity": parity,
                 "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": "Mtraces/s", "h2d_bytes_per_step": int(24 * n),
-                        "d2h_bytes_per_step": int(56 * n), "steps": e2e_steps, "matches_resident": same},
+                        "d2h_bytes_per_step": int(56 * n), "steps": e2e_steps, "matches_resident": same,
+                        "host_copy_ceiling_gbs": (extra.get("host_copy") or {}).get("gbs"),
+                        "copy_bound_mtraces": (extra.get("host_copy") or {}).get("copy_bound_mtraces"),
+                        "frac_of_copy_bound": (e2e_value / extra["host_copy"]["copy_bound_mtraces"]
+                                               if (extra.get("host_copy") or {}).get("copy_bound_mtraces") else None),
+                        "host_copy": extra.get("host_copy")},
+                "e2e_pageable": extra.get("e2e_pageable"), "gathered": extra.get("gathered"), "strong": extra.get("strong"),
+                "rollout": extra.get("rollout"),
                 "gpu_launches": int(launches), "clocks": clocks, "hit_fraction": hits}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, kind, secs = cpu_reference_run(m.data, starts, ends, min(args.ref_sample, n))
@@ -401,6 +604,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1 << 24,
                     help="rays per reference/cpu_baseline step (default: the whole 16 Mi workload, ~17 s of CPU work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-arms", action="store_true", help="only value / e2e / roofline: skip host-copy ceiling, pageable, gathered, strong-scaling and rollout arms")
     ap.add_argument("--parity-sample", type=int, default=1 << 21, help="records checked against the reference before timing")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

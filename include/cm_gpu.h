@@ -176,6 +176,21 @@ int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
                                const int32_t *models, const float *origins, const float *angles,
                                const float *boxmins, const float *boxmaxs, int32_t *contents);
 
+/* ---- pinned host memory ----------------------------------------------------
+ * The host-pointer calls cut a batch into pieces and overlap copy-in, tracing and copy-out.  That only works from
+ * page-locked memory: copies from or to pageable memory are staged by the driver and block the caller, so the pieces
+ * run one after the other (measured in bench.py: `e2e_pageable`).  The engine's callers own long-lived arenas -- the
+ * game VM's data segment that trap_Trace results are written into (server/sv_game.c:198, VMA(1)), a bot library's
+ * result arrays: register such a region ONCE, unregister it before it is freed.  Regions may overlap earlier ones (they
+ * are merged); a region somebody else already pinned is accepted as it is.
+ *
+ * cmgpu_set_option("auto_register", 1) makes the host-pointer calls register any pageable starts / ends / results array
+ * of 1 MiB or more on first sight.  Only safe when such arrays live until cmgpu_destroy or are released with
+ * cmgpu_host_unregister first: memory that is freed while registered and handed out again by the allocator would be
+ * copied through stale page mappings.  Off by default. */
+int cmgpu_host_register(cmgpu_ctx *ctx, const void *ptr, size_t bytes);
+int cmgpu_host_unregister(cmgpu_ctx *ctx, const void *ptr);
+
 /* ---- batched queries, DEVICE pointers (inputs resident in HBM) -----------
  * Same meaning as above; per-item arrays are device pointers on the context's
  * GPU.  A SHARED hull (hull_stride == 0: mins/maxs, 3 floats each, may be NULL)

@@ -1,5 +1,5 @@
-"""Multi-GPU result gather fused into the trace kernels' stores (sharding.PeerResults, cmgpu_ipc_*): needs two GPUs.
-The round's single-GPU run skips it; `gpurun --gpus 2 -- python -m pytest tests/test_peer_results.py -m gpu` runs it."""
+"""Multi-GPU result gather fused into the trace kernels' stores (sharding.PeerResults, cmgpu_ipc_*): 2, 4 and 8 ranks,
+each case skipped where the box has fewer GPUs (`gpurun --gpus N -- python -m pytest tests/test_peer_results.py -m gpu`)."""
 import os
 import sys
 
@@ -48,12 +48,15 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_peer_results_two_ranks():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_results(world):
+    """world ranks (one GPU each) trace their ranges; rank 0's buffer must hold exactly the records of a single-rank run"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    world, n = 2, 1_500_001
-    procs = [ctx.Process(target=_worker, args=(r, world, 29641, n, q)) for r in range(world)]
+    n = 1_500_001
+    procs = [ctx.Process(target=_worker, args=(r, world, 29641 + world, n, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

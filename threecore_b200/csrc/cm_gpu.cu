@@ -142,6 +142,9 @@ struct cmgpu_ctx_s {
 	int numClusters = 0, clusterBytes = 0, numAreas = 0, noAreas = 0;
 	std::vector<int> areaPortals, floodnum;          // host copies: [numAreas][numAreas] reference counts, [numAreas]
 	unsigned *hSvTotal = nullptr;        // pinned
+	// host regions pinned through this context (cmgpu_host_register, or "auto_register"): page-aligned [lo, hi)
+	std::vector<std::pair<uintptr_t, uintptr_t>> hostRegs;
+	bool autoRegister = false;
 	unsigned long long svCandidates = 0;
 };
 
@@ -978,6 +981,48 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 
 }  // namespace
 
+// ---- pinned host memory for the host-pointer calls --------------------------------------------------------------
+// cudaMemcpyAsync from or to pageable memory is staged by the driver and blocks the calling thread, so the pieces of a
+// host batch stop overlapping (copy in, trace, copy out run one after the other).  The engine's callers hand over
+// long-lived memory -- the QVM's data segment (sv_game.c:198, VMA(1)), a results arena -- which can be pinned ONCE.
+static int registerRange(cmgpu_ctx *ctx, const void *ptr, size_t bytes) {
+	if (!ptr || !bytes) return CMGPU_OK;
+	uintptr_t lo = (uintptr_t)ptr & ~(uintptr_t)4095, hi = ((uintptr_t)ptr + bytes + 4095) & ~(uintptr_t)4095;
+	// regions of ours that the new one touches are merged into it (a registration cannot overlap another)
+	for (size_t i = 0; i < ctx->hostRegs.size();) {
+		auto &r = ctx->hostRegs[i];
+		if (r.first <= lo && hi <= r.second) return CMGPU_OK;
+		if (r.first < hi && lo < r.second) {
+			cudaHostUnregister((void *)r.first);
+			if (r.first < lo) lo = r.first;
+			if (r.second > hi) hi = r.second;
+			ctx->hostRegs.erase(ctx->hostRegs.begin() + (long)i);
+		} else i++;
+	}
+	cudaError_t e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault);
+	if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return CMGPU_OK; }   // pinned by its owner: nothing to do
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(ctx, CMGPU_ERR_CUDA, "cudaHostRegister(%p, %zu bytes): %s", (void *)lo, (size_t)(hi - lo), cudaGetErrorString(e));
+	}
+	ctx->hostRegs.push_back({lo, hi});
+	return CMGPU_OK;
+}
+
+static bool isPageable(const void *p) {
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+	return a.type == cudaMemoryTypeUnregistered;
+}
+
+// "auto_register": pin the big arrays of a host batch on first sight (see cm_gpu.h for when that is safe)
+static void autoRegister(cmgpu_ctx *ctx, const void *ptr, size_t bytes) {
+	if (!ctx->autoRegister || !ptr || bytes < ((size_t)1 << 20)) return;
+	if (!isPageable(ptr) && !isPageable((const char *)ptr + bytes - 1)) return;
+	if (registerRange(ctx, ptr, bytes) != CMGPU_OK) ctx->err.clear();      // not fatal: the copies are merely staged
+}
+
+
 // =====================================================================================
 // C ABI
 // =====================================================================================
@@ -1075,6 +1120,8 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	                  &ctx->bKeys, &ctx->bRecs, &ctx->bCompact, &ctx->bSvWorld, &ctx->bSvOffsets, &ctx->bSvTiles, &ctx->bSvItems, &ctx->bSvCand,
 	                  &ctx->bSvPass, &ctx->bLeafLists, &ctx->bLeafCounts, &ctx->bVis, &ctx->bFlood, &ctx->bEntRecs, &ctx->bVisible}) releaseBuf(*b);
 	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
+	for (auto &r : ctx->hostRegs) cudaHostUnregister((void *)r.first);
+	ctx->hostRegs.clear();
 	for (auto &b : ctx->bHist) releaseBuf(b);
 	for (auto &b : ctx->bStackArena) releaseBuf(b);
 	for (auto &b : ctx->bPoolHdr) releaseBuf(b);
@@ -1146,6 +1193,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "compact_by_item") ctx->compactByItem = value != 0;
 	else if (k == "node_thresholds") ctx->nodeThresholds = value != 0;
 	else if (k == "entry_grid") ctx->entryGrid = value != 0;
+	else if (k == "auto_register") ctx->autoRegister = value != 0;
 	else if (k == "entry_cell") { if (!(value >= 8.0)) return fail(ctx, CMGPU_ERR_INVALID, "entry_cell must be >= 8"); ctx->entryCell = (float)value; }   // takes effect at the next cmgpu_upload
 	else if (k == "gang") ctx->gang = ctx->gangPool = (int)value;
 	else if (k == "gang_pool") ctx->gangPool = (int)value;
@@ -1251,6 +1299,29 @@ int cmgpu_ipc_free(cmgpu_ctx *ctx, void *devptr) {
 	CUDA_TRY(ctx, cudaDeviceSynchronize());
 	CUDA_TRY(ctx, cudaFree(devptr));
 	return CMGPU_OK;
+}
+
+int cmgpu_host_register(cmgpu_ctx *ctx, const void *ptr, size_t bytes) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (!ptr || !bytes) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_host_register: empty region");
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	return registerRange(ctx, ptr, bytes);
+}
+
+int cmgpu_host_unregister(cmgpu_ctx *ctx, const void *ptr) {
+	if (!ctx || !ptr) return CMGPU_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaDeviceSynchronize());          // nothing may still copy from or to it
+	const uintptr_t p = (uintptr_t)ptr;
+	for (size_t i = 0; i < ctx->hostRegs.size(); i++) {
+		if (ctx->hostRegs[i].first <= p && p < ctx->hostRegs[i].second) {
+			cudaHostUnregister((void *)ctx->hostRegs[i].first);
+			cudaGetLastError();
+			ctx->hostRegs.erase(ctx->hostRegs.begin() + (long)i);
+			return CMGPU_OK;
+		}
+	}
+	return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_host_unregister: %p is not inside a region registered through this context", ptr);
 }
 
 int cmgpu_kernel_timing(cmgpu_ctx *ctx, int enable) {
@@ -1404,6 +1475,9 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 		CUDA_TRY(ctx, cudaEventSynchronize(ctx->extDone));
 		ctx->extBusy = false;
 	}
+	autoRegister(ctx, starts, N * v3);
+	autoRegister(ctx, ends, N * v3);
+	autoRegister(ctx, results, N * sizeof(cmgpu_trace_t));
 	int chunks = (int)((N + kMinChunkItems - 1) / kMinChunkItems);
 	if (chunks > ctx->pipeChunks) chunks = ctx->pipeChunks;
 	if (chunks < 1) chunks = 1;

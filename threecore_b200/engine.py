@@ -130,6 +130,8 @@ def load_library() -> C.CDLL:
     lib.cmgpu_ipc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.cmgpu_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_ipc_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cmgpu_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.cmgpu_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     lib.cmgpu_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.cmgpu_enable_counters.argtypes = [C.c_void_p, C.c_int]
@@ -360,6 +362,13 @@ class Engine:
 
     def ipc_free(self, ptr: int):
         self._check(self.lib.cmgpu_ipc_free(self.h, C.c_void_p(ptr)))
+
+    def host_register(self, ptr: int, nbytes: int):
+        """pin a long-lived host region (cmgpu_host_register) so that the host-pointer calls copy straight from / to it"""
+        self._check(self.lib.cmgpu_host_register(self.h, C.c_void_p(ptr), int(nbytes)))
+
+    def host_unregister(self, ptr: int):
+        self._check(self.lib.cmgpu_host_unregister(self.h, C.c_void_p(ptr)))
 
     def kernel_timing(self, on=True):
         """bracket every trace-kernel launch with CUDA events on its own stream (cmgpu_kernel_timing)"""
