@@ -34,7 +34,10 @@ def timed(target, label):
     if rank == 0:
         print(f"{label:48s}: {t.item():7.2f} ms/step  {world * per / t.item() / 1e3:8.1f} Mtraces/s (all ranks)", flush=True)
 timed(out, "records stay on each rank")
-timed(pr.pointer(lo), "records stored into rank 0 (NVLink, fused)")
+for spec in ["remote_pipeline=0"] + sys.argv[2:]:
+    for kv in spec.split(","):
+        eng.set_option(kv.split("=")[0], float(kv.split("=")[1]))
+    timed(pr.pointer(lo), f"records into rank 0 over NVLink [{spec}]")
 pr.finish()
 if rank == 0:
     rec = pr.records()

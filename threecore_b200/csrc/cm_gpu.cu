@@ -13,6 +13,7 @@
 #include "cm_leaf_queries.cuh"
 #include "../../include/cm_gpu.h"
 
+#include <cuda.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -104,6 +105,14 @@ struct cmgpu_ctx_s {
 	// tables) into the graph.  Once a capture has used this context, a workspace that has to grow -- or a hull table that
 	// has to make room -- is RETIRED instead of freed: replays keep reading and writing their own, still valid blocks.
 	// Retired blocks are released with the map (a graph does not outlive the map it was recorded on) or the context.
+	// records that leave this GPU (a peer's HBM over NVLink, sharding.PeerResults): the batch is traced in pieces and the
+	// expansion of piece p -- the only kernel that writes records -- runs on a side stream with a few CTAs, next to the
+	// walk of piece p + 1: the transfer hides behind the walks instead of following them (tracePieces)
+	cudaStream_t sideStream = nullptr;
+	cudaEvent_t evWalked = nullptr, evSideDone = nullptr;
+	int remotePieces = 4, remoteExpandCtas = 64;
+	std::vector<std::pair<uintptr_t, uintptr_t>> peerRanges;   // peer buffers opened with cmgpu_ipc_open: [base, end)
+	bool remotePipeline = false;         // measured on 2 B200s: the per-piece launches cost more than the overlap saves; "remote_pipeline" turns it on
 	bool graphPinned = false;
 	std::vector<void *> retired;
 	bool twoPhase = true, twoPhaseHost = false, twoPhaseSmall = false, compactByItem = true;
@@ -827,7 +836,7 @@ int extRecord(cmgpu_ctx *ctx, cudaStream_t s) {
 
 // wsOffset: first item of this launch inside the context's binning workspace (the host pipeline gives
 // every chunk its own range); histSlot: which histogram table to use (one per pipeline stream).
-int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1) {
+int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1, bool sideExpand = false) {
 	if (q.n <= 0) return CMGPU_OK;
 	const unsigned *slotOf = nullptr;
 	q.compact = nullptr;
@@ -893,7 +902,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	//  piece costs the call 8 % -- measured 764 against 826 Mtraces/s end to end)
 	// and not for the smaller launches of the one-item-per-lane kernels either (a rollout phase, a game tick: one more
 	// launch is 5 % of their latency; "two_phase_small" turns it on for them)
-	if (fast && (pool || ctx->twoPhaseSmall) && slotOf && ctx->twoPhase && (external || ctx->twoPhaseHost) && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
+	if (fast && (pool || ctx->twoPhaseSmall) && slotOf && ctx->twoPhase && (external || ctx->twoPhaseHost || sideExpand) && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
 		q.compact = (uint4 *)ctx->bCompact.p + wsOffset;
 	q.compactByItem = q.compact && pool && ctx->compactByItem ? 1 : 0;
 	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
@@ -964,7 +973,16 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
-	if (q.compact) {
+	if (q.compact && sideExpand) {
+		int ctas = (q.n + kExpandBlock - 1) / kExpandBlock;
+		if (ctas > ctx->remoteExpandCtas) ctas = ctx->remoteExpandCtas;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->evWalked, s));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->sideStream, ctx->evWalked, 0));
+		expandRecordsKernel<<<ctas, kExpandBlock, 0, ctx->sideStream>>>(ctx->fast, q.n, q.compactByItem ? nullptr : slotOf, q.compact, q.starts,
+		                                                                 q.ends, q.out, q.hitIds);
+		ctx->launches++;
+		CUDA_TRY(ctx, cudaGetLastError());
+	} else if (q.compact) {
 		expandRecordsKernel<<<(q.n + kExpandBlock - 1) / kExpandBlock, kExpandBlock, 0, s>>>(ctx->fast, q.n, q.compactByItem ? nullptr : slotOf, q.compact, q.starts,
 		                                                                                   q.ends, q.out, q.hitIds);
 		ctx->launches++;
@@ -1022,6 +1040,54 @@ static void autoRegister(cmgpu_ctx *ctx, const void *ptr, size_t bytes) {
 	if (registerRange(ctx, ptr, bytes) != CMGPU_OK) ctx->err.clear();      // not fatal: the copies are merely staged
 }
 
+
+// ---- records that land in another GPU's memory ---------------------------------------------------------------------
+constexpr int CMGPU_ERR_UNSUPPORTED_INTERNAL = -1000;    // tracePieces: not a batch it handles, take the plain launch
+
+bool isRemote(cmgpu_ctx *ctx, const void *p) {
+	for (auto &r : ctx->peerRanges) {
+		if (r.first <= (uintptr_t)p && (uintptr_t)p < r.second) return true;
+	}
+	return false;
+}
+
+// A big hot-path batch whose records go to a peer: pieces of >= poolMinItems items are binned and walked one after the
+// other on the caller's stream; each piece's expansion -- narrow, NVLink-bound -- runs on the side stream while the next
+// piece is walked.  The caller's stream waits for the last expansion before the call's work counts as done.
+int tracePieces(cmgpu_ctx *ctx, const TraceBatch &q0, cudaStream_t s) {
+	const bool hot = ctx->useFast && ctx->usePool && ctx->twoPhase && ctx->binning && !ctx->counting && !q0.mins && !q0.masks && !q0.models && !q0.origins &&
+	                 (ctx->numPatches == 0 || ctx->noCurves) && ((uintptr_t)q0.out & 15) == 0;
+	int pieces = ctx->remotePieces;
+	if (pieces > q0.n / ctx->poolMinItems) pieces = q0.n / ctx->poolMinItems;
+	if (!hot || pieces < 2) return CMGPU_ERR_UNSUPPORTED_INTERNAL;
+	cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+	if (cudaStreamIsCapturing(s, &st) != cudaSuccess) cudaGetLastError();
+	if (st != cudaStreamCaptureStatusNone) return CMGPU_ERR_UNSUPPORTED_INTERNAL;
+	if (!ctx->sideStream) {
+		CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking));
+		CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evWalked, cudaEventDisableTiming));
+		CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evSideDone, cudaEventDisableTiming));
+	}
+	int rc;
+	if ((rc = extWait(ctx, s))) return rc;
+	const size_t N = (size_t)q0.n;
+	if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bRecs, N * 32))) return rc;
+	if ((rc = reserve(ctx, ctx->bCompact, N * 16))) return rc;
+	for (int p = 0; p < pieces; p++) {
+		const size_t lo = ((N * (size_t)p / (size_t)pieces) & ~(size_t)255), hi = p + 1 == pieces ? N : ((N * (size_t)(p + 1) / (size_t)pieces) & ~(size_t)255);
+		TraceBatch q = q0;
+		q.n = (int)(hi - lo);
+		q.starts = q0.starts + 3 * lo;
+		q.ends = q0.ends + 3 * lo;
+		q.out = q0.out + 7 * lo;
+		q.hitIds = q0.hitIds ? q0.hitIds + lo : nullptr;
+		if ((rc = launchTrace(ctx, q, s, lo, kBinSlots - 1, true))) return rc;
+	}
+	CUDA_TRY(ctx, cudaEventRecord(ctx->evSideDone, ctx->sideStream));
+	CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->evSideDone, 0));
+	return extRecord(ctx, s);
+}
 
 // =====================================================================================
 // C ABI
@@ -1126,6 +1192,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	for (auto &b : ctx->bStackArena) releaseBuf(b);
 	for (auto &b : ctx->bPoolHdr) releaseBuf(b);
 	if (ctx->extDone) cudaEventDestroy(ctx->extDone);
+	if (ctx->sideStream) { cudaStreamDestroy(ctx->sideStream); cudaEventDestroy(ctx->evWalked); cudaEventDestroy(ctx->evSideDone); }
 	for (auto &pr : ctx->timingPairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
 	if (ctx->dCounters) cudaFree(ctx->dCounters);
 	if (ctx->dStatus) cudaFree(ctx->dStatus);
@@ -1194,6 +1261,9 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "node_thresholds") ctx->nodeThresholds = value != 0;
 	else if (k == "entry_grid") ctx->entryGrid = value != 0;
 	else if (k == "auto_register") ctx->autoRegister = value != 0;
+	else if (k == "remote_pipeline") ctx->remotePipeline = value != 0;
+	else if (k == "remote_pieces") ctx->remotePieces = value < 1 ? 1 : (int)value;
+	else if (k == "remote_expand_ctas") ctx->remoteExpandCtas = value < 1 ? 1 : (int)value;
 	else if (k == "entry_cell") { if (!(value >= 8.0)) return fail(ctx, CMGPU_ERR_INVALID, "entry_cell must be >= 8"); ctx->entryCell = (float)value; }   // takes effect at the next cmgpu_upload
 	else if (k == "gang") ctx->gang = ctx->gangPool = (int)value;
 	else if (k == "gang_pool") ctx->gangPool = (int)value;
@@ -1282,6 +1352,20 @@ int cmgpu_ipc_open(cmgpu_ctx *ctx, const unsigned char handle[64], void **devptr
 	cudaIpcMemHandle_t h;
 	memcpy(&h, handle, 64);
 	CUDA_TRY(ctx, cudaIpcOpenMemHandle(devptr, h, cudaIpcMemLazyEnablePeerAccess));
+	// remember the mapping: records stored into it travel over NVLink, and big batches are streamed there (tracePieces)
+	CUdeviceptr base = (CUdeviceptr)*devptr;
+	size_t size = 1;
+	{	// the driver call through the runtime's entry-point lookup: libcmgpu.so does not link libcuda
+		typedef CUresult (*RangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult qr;
+		if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
+			CUdeviceptr b = 0;
+			size_t sz = 0;
+			if (((RangeFn)fn)(&b, &sz, (CUdeviceptr)*devptr) == CUDA_SUCCESS && sz) { base = b; size = sz; }
+		} else cudaGetLastError();
+	}
+	ctx->peerRanges.push_back({(uintptr_t)base, (uintptr_t)base + size});
 	return CMGPU_OK;
 }
 
@@ -1290,6 +1374,9 @@ int cmgpu_ipc_close(cmgpu_ctx *ctx, void *devptr) {
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	CUDA_TRY(ctx, cudaDeviceSynchronize());
 	CUDA_TRY(ctx, cudaIpcCloseMemHandle(devptr));
+	for (size_t i = 0; i < ctx->peerRanges.size(); i++) {
+		if (ctx->peerRanges[i].first <= (uintptr_t)devptr && (uintptr_t)devptr < ctx->peerRanges[i].second) { ctx->peerRanges.erase(ctx->peerRanges.begin() + (long)i); break; }
+	}
 	return CMGPU_OK;
 }
 
@@ -1390,6 +1477,10 @@ int cmgpu_box_trace_batch_device(cmgpu_ctx *ctx, int n,
 	if (!q.boxmaxs) q.boxmins = nullptr;
 	q.out = reinterpret_cast<uint2 *>(results); q.hitIds = hit_ids;
 	q.status = ctx->dStatus; q.counters = ctx->dCounters;
+	if (ctx->remotePipeline && isRemote(ctx, results)) {
+		const int rc = tracePieces(ctx, q, (cudaStream_t)stream);
+		if (rc != CMGPU_ERR_UNSUPPORTED_INTERNAL) return rc;
+	}
 	return launchTrace(ctx, q, (cudaStream_t)stream);
 }
 

@@ -422,7 +422,9 @@ constexpr int kExpandBlock = 256;
 __global__ void __launch_bounds__(kExpandBlock) expandRecordsKernel(const FastMap fm, int n, const unsigned *slotOf, const uint4 *compact,
                                                                     const float *starts, const float *ends, uint2 *out, int *hitIds) {
 	__shared__ __align__(32) uint2 rec[kExpandBlock * 7];       // read back in 32-byte pieces
-	const int base = blockIdx.x * kExpandBlock;
+	// one block of kExpandBlock items per CTA; a launch with fewer CTAs than blocks strides over them (the narrow launch
+	// that streams records into a peer's HBM next to the walk of the following piece, cm_gpu.cu: tracePieces)
+	for (int base = blockIdx.x * kExpandBlock; base < n; base += gridDim.x * kExpandBlock) {
 	const int i = base + threadIdx.x;
 	if (i < n) {
 		const uint4 c = __ldcs(&compact[slotOf ? slotOf[i] : (unsigned)i]);
@@ -474,6 +476,8 @@ __global__ void __launch_bounds__(kExpandBlock) expandRecordsKernel(const FastMa
 		done = pieces << 2;
 	}
 	for (int k = done + threadIdx.x; k < words; k += kExpandBlock) __stcs(&dst[k], rec[k]);
+	__syncthreads();                                             // rec is reused by the next block of items
+	}
 }
 
 #ifndef CMGPU_PREFETCH_CHUNK
