@@ -100,6 +100,11 @@ class PeerResults:
             dist.broadcast_object_list(box, src=root, group=group)
         if self.rank != root:
             self.base = engine.ipc_open(box[0])
+            # With three or more ranks the root's NVLink ingress is what limits a gathered step (7 x 0.94 GB per 16 Mi-ray
+            # step at 8 ranks): the engine then traces in pieces and streams each piece's records while the next is walked
+            # (cm_gpu.cu: tracePieces).  Measured: 8 ranks 14.2 -> 9.9 ms per step; 2 ranks 7.3 -> 7.6 ms, so not there.
+            engine.set_option("remote_pipeline", 1 if self.world >= 3 else 0)
+            engine.set_option("remote_expand_ctas", 148)
         self.nbytes = nbytes
 
     def local_range(self):
