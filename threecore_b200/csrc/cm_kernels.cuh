@@ -458,6 +458,134 @@ __device__ __forceinline__ bool facetPlaneStepPoint(const DevMap &m, Lane &L) {
 	return L.side >= L.sideEnd;
 }
 
+// ---- a patch as WARP work ---------------------------------------------------------------------------------------
+// The reference tests a sweep against every facet of a patch whose box it touches (cm_patch.c:1264-1311, 1383-1462):
+// facets x (surface plane + borders), nearly all of which fail at their first or second plane.  One plane per scheduler
+// round (facetPlaneStep*) keeps the lanes of a warp together but costs a round per plane -- ~190 rounds per trace on
+// BASELINE config 3.  Here the warp takes ONE item's patch at a time: the owner's sweep is broadcast, every lane tests a
+// facet of its own (32 facets per pass), and the passes' survivors are merged in facet order.  That is the reference's
+// result because a facet's own test never looks at the running fraction except to compare with it at the very end
+// (box: `enterFrac < tw->trace.fraction`, strict, so the first facet with the smallest enterFrac wins) or at the very
+// start (point: `intersect > tw->trace.fraction` skips the facet; the survivors of a pass are replayed in order against
+// the fraction as it falls).  The counting kernel variant keeps the plane-per-round walk: its visit counts are the
+// reference's, which depend on that order.
+struct FacetBox { bool ok; float enter; int which; };
+
+// one facet against a box sweep: CM_TraceThroughPatchCollide's loop body (cm_patch.c:1384-1446) up to the final comparison
+__device__ __forceinline__ FacetBox facetBoxWhole(const DevMap &m, Lane &T, const int f) {
+	const int4 fr = __ldg(&m.facetRuns[f]);
+	T.firstSide = fr.x;
+	T.found = fr.y | (fr.z << 5);
+	const int numBorders = fr.y;
+	float enter = -1.0f, leave = 1.0f;
+	int which = -2;
+	FacetBox r;
+	r.ok = false; r.enter = -1.0f; r.which = -2;
+	for (int cur = -1; cur < numBorders; cur++) {
+		const float4 pl = facetClipPlane(m, T, cur);
+		bool hit;
+		if (!clipFacetPlane(pl.x, pl.y, pl.z, pl.w, T, enter, leave, hit)) return r;
+		if (hit) which = cur;
+	}
+	if (which == numBorders - 1) return r;                    // never clip against the back side (cm_patch.c:1437-1439)
+	r.ok = enter < leave && enter >= 0;
+	r.enter = enter;
+	r.which = which;
+	return r;
+}
+
+// one facet against a point sweep (cm_patch.c:1264-1299): does the sweep pass through the facet, where (t), and the
+// fraction it would record.  `cur`: the running fraction when the pass started (facets beyond it cannot be taken).
+struct FacetPoint { bool pass; float t, fraction; };
+__device__ __forceinline__ FacetPoint facetPointWhole(const DevMap &m, const Lane &T, const int f, const float cur) {
+	const int4 fr = __ldg(&m.facetRuns[f]);
+	FacetPoint r;
+	r.pass = false; r.t = 0.0f; r.fraction = 0.0f;
+	const float4 sp = __ldg(&m.facetPlanes[fr.x]);
+	bool front; float t;
+	pointPlaneRelation(sp, T, front, t);
+	if (!front || t < 0 || t > cur) return r;
+	for (int b = 0; b < fr.y; b++) {
+		const float4 pl = __ldg(&m.facetPlanes[fr.x + 1 + b]);
+		bool fb; float tb;
+		pointPlaneRelation(pl, T, fb, tb);
+		const bool inward = (fr.z >> b) & 1;
+		if ((fb != inward) ? (tb > t) : (tb < t)) return r;
+	}
+	// hit: the fraction with the 1/8 push-off, mixed widths as cm_patch.c:1300-1303
+	const float cx = sp.x < 0.0f ? T.p0x : T.n0x;
+	const float cy = sp.y < 0.0f ? T.p0y : T.n0y;
+	const float cz = sp.z < 0.0f ? T.p0z : T.n0z;
+	const float off = dotf(cx, cy, cz, sp.x, sp.y, sp.z);
+	const float d1 = dotf(T.sx, T.sy, T.sz, sp.x, sp.y, sp.z) - sp.w + off;
+	const float d2 = dotf(T.ex, T.ey, T.ez, sp.x, sp.y, sp.z) - sp.w + off;
+	float fr2 = (float)(((double)d1 - kClipEps) / (double)(d1 - d2));
+	if (fr2 < 0) fr2 = 0;
+	r.pass = true; r.t = t; r.fraction = fr2;
+	return r;
+}
+
+// The warp clips the sweep of lane `owner` (in M_FACET: L.side .. L.sideEnd are the patch's facets) against the patch.
+// Every lane calls this; only the owner's L is changed (fraction and clip plane).
+__device__ __forceinline__ void patchByWarp(const DevMap &m, Lane &L, const int owner, const unsigned lane) {
+	const unsigned full = 0xffffffffu;
+	Lane T;
+	T.sx = __shfl_sync(full, L.sx, owner); T.sy = __shfl_sync(full, L.sy, owner); T.sz = __shfl_sync(full, L.sz, owner);
+	T.ex = __shfl_sync(full, L.ex, owner); T.ey = __shfl_sync(full, L.ey, owner); T.ez = __shfl_sync(full, L.ez, owner);
+	T.n0x = __shfl_sync(full, L.n0x, owner); T.n0y = __shfl_sync(full, L.n0y, owner); T.n0z = __shfl_sync(full, L.n0z, owner);
+	T.p0x = __shfl_sync(full, L.p0x, owner); T.p0y = __shfl_sync(full, L.p0y, owner); T.p0z = __shfl_sync(full, L.p0z, owner);
+	const int first = __shfl_sync(full, L.side, owner), end = __shfl_sync(full, L.sideEnd, owner);
+	const bool point = (__shfl_sync(full, L.flags, owner) & F_POINT) != 0;
+	float cur = __shfl_sync(full, L.fraction, owner);
+	bool any = false;
+	float4 best = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	if (point) {
+		int bestFacet = -1;
+		for (int base = first; base < end; base += 32) {
+			const int f = base + (int)lane;
+			FacetPoint r;
+			r.pass = false; r.t = 0.0f; r.fraction = 0.0f;
+			if (f < end) r = facetPointWhole(m, T, f, cur);
+			unsigned cand = __ballot_sync(full, r.pass);
+			while (cand) {                                        // the survivors in facet order (cm_patch.c:1271)
+				const int w = __ffs((int)cand) - 1;
+				cand &= cand - 1u;
+				const float tw = __shfl_sync(full, r.t, w), fw = __shfl_sync(full, r.fraction, w);
+				if (!(tw > cur)) { cur = fw; bestFacet = base + w; }
+			}
+		}
+		if (bestFacet >= 0 && lane == (unsigned)owner) {
+			const float4 sp = __ldg(&m.facetPlanes[__ldg(&m.facetRuns[bestFacet]).x]);
+			L.fraction = cur;
+			L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;       // type/signbits stay stale (cm_patch.c:1309-1310)
+		}
+		return;
+	}
+	for (int base = first; base < end; base += 32) {
+		const int f = base + (int)lane;
+		FacetBox r;
+		r.ok = false; r.enter = -1.0f; r.which = -2;
+		if (f < end) r = facetBoxWhole(m, T, f);
+		const bool accept = r.ok && r.enter < cur;
+		// enter is >= 0 here (or -0.0, which orders like +0.0: strict `<` lets the first facet keep a tie)
+		const unsigned key = accept ? (__float_as_uint(r.enter) & 0x7fffffffu) : 0xffffffffu;
+		const unsigned mn = __reduce_min_sync(full, key);
+		if (mn != 0xffffffffu) {
+			const int w = __ffs((int)__ballot_sync(full, key == mn)) - 1;
+			float4 pl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if ((int)lane == w) pl = facetClipPlane(m, T, r.which);   // same float ops, same plane (T still holds this facet's run)
+			cur = __shfl_sync(full, r.enter, w);
+			best.x = __shfl_sync(full, pl.x, w); best.y = __shfl_sync(full, pl.y, w);
+			best.z = __shfl_sync(full, pl.z, w); best.w = __shfl_sync(full, pl.w, w);
+			any = true;
+		}
+	}
+	if (any && lane == (unsigned)owner) {
+		L.fraction = cur;
+		L.pnx = best.x; L.pny = best.y; L.pnz = best.z; L.pd = best.w;
+	}
+}
+
 // CM_PositionTestInPatchCollide, cm_patch.c:1479-1531
 template <bool COUNT>
 __device__ __forceinline__ bool boxInPatch(const DevMap &m, Lane &L, int p) {
@@ -982,7 +1110,25 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 
 		// ---------------- one facet of the current patch, cm_patch.c:1264-1311 / 1383-1462 -----------------
 		// Lanes that are inside a patch run their facets together, whatever patch and facet each of them is at.
-		if (mode == M_FACET) {
+		if (!COUNT) {
+			// the warp takes the patches its lanes have reached one at a time (patchByWarp)
+			unsigned pend = __ballot_sync(0xffffffffu, mode == M_FACET);
+			while (pend) {
+				const int owner = __ffs((int)pend) - 1;
+				pend &= pend - 1u;
+				patchByWarp(m, L, owner, lane);
+				if ((int)lane == owner) {
+					if (L.fraction < L.enter) {                      // CM_TraceThroughPatch, cm_trace.c:247-252
+						const int4 pa = __ldg(&m.patchInfo[2 * L.brush]);
+						L.surfaceFlags = pa.x;
+						L.contents = pa.y;
+						L.hitId = -2 - L.brush;
+					}
+					mode = (L.fraction == 0.0f) ? M_FINISH : M_PATCH;
+				}
+			}
+		}
+		if (COUNT && mode == M_FACET) {
 			const bool point = (L.flags & F_POINT) != 0;
 			#pragma unroll 1
 			for (int it = 0; it < q.facetSteps; it++) {
