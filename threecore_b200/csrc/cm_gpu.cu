@@ -507,7 +507,7 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		const int32_t *p = f->patches + 6 * (size_t)i;
 		const float *pb = f->patchBounds + 6 * (size_t)i;
 		patchInfo[2 * (size_t)i] = make_int4(p[0], p[1], p[2], p[3]);
-		patchInfo[2 * (size_t)i + 1] = make_int4(p[4], p[5], 0, 0);
+		patchInfo[2 * (size_t)i + 1] = make_int4(p[4], p[5], 0, 0);     // .z: first chunk of 32 facets, set below
 		patchBox[2 * (size_t)i] = make_float4(pb[0], pb[1], pb[2], 0.0f);
 		patchBox[2 * (size_t)i + 1] = make_float4(pb[3], pb[4], pb[5], 0.0f);
 	}
@@ -549,6 +549,41 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		}
 	}
 
+	// the axial borders of every facet, and their maxima over the chunks of 32 facets a warp takes per pass (DevMap::facetAxial)
+	std::vector<float4> facetAxial(2 * (size_t)f->numFacets), facetChunkAxial;
+	for (int p = 0; p < f->numPatches; p++) {
+		const int32_t *pt = f->patches + 6 * (size_t)p;
+		patchInfo[2 * (size_t)p + 1].z = (int)(facetChunkAxial.size() / 2);
+		for (int k0 = 0; k0 < pt[5]; k0 += 32) {
+			float cmax[6];
+			for (int d = 0; d < 6; d++) cmax[d] = -INFINITY;
+			for (int k = k0; k < pt[5] && k < k0 + 32; k++) {
+				const int fi = pt[4] + k;
+				const int32_t *fc = f->facets + 3 * (size_t)fi;
+				float D[6];
+				for (int d = 0; d < 6; d++) D[d] = INFINITY;
+				for (int j = 0; j < fc[1]; j++) {
+					const int32_t *bd = f->borders + 2 * (size_t)(fc[2] + j);
+					const float *bp = f->patchPlanes + 4 * (size_t)(pt[2] + bd[0]);
+					float n[3] = {bp[0], bp[1], bp[2]}, w = bp[3];
+					if (bd[1]) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; w = -w; }      // borderInward: the plane is flipped (cm_patch.c:1413-1417)
+					for (int a = 0; a < 3; a++) {
+						const int b = (a + 1) % 3, c = (a + 2) % 3;
+						if (n[b] == 0.0f && n[c] == 0.0f && (n[a] == 1.0f || n[a] == -1.0f)) {
+							const int d = 2 * a + (n[a] < 0.0f ? 1 : 0);
+							if (w < D[d]) D[d] = w;
+						}
+					}
+				}
+				facetAxial[2 * (size_t)fi] = make_float4(D[0], D[1], D[2], D[3]);
+				facetAxial[2 * (size_t)fi + 1] = make_float4(D[4], D[5], 0.0f, 0.0f);
+				for (int d = 0; d < 6; d++) if (D[d] > cmax[d]) cmax[d] = D[d];
+			}
+			facetChunkAxial.push_back(make_float4(cmax[0], cmax[1], cmax[2], cmax[3]));
+			facetChunkAxial.push_back(make_float4(cmax[4], cmax[5], 0.0f, 0.0f));
+		}
+	}
+
 	int rc = CMGPU_OK;
 #define UP(vec, field) if ((rc = uploadArray(ctx, vec, &m.field)) != CMGPU_OK) return rc
 	UP(nodes, nodes); UP(nodePlanes, nodePlanes); UP(leafs, leafs); UP(leafBrushBox, leafBrushBox);
@@ -556,6 +591,7 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 	UP(sidePlanes, sidePlanes); UP(sideMeta, sideMeta); UP(modelLeafs, modelLeafs); UP(surf2patch, surf2patch);
 	UP(patchInfo, patchInfo); UP(patchBox, patchBox); UP(patchPlanes, patchPlanes); UP(facets, facets);
 	UP(borders, borders); UP(facetRuns, facetRuns); UP(facetPlanes, facetPlanes);
+	UP(facetAxial, facetAxial); UP(facetChunkAxial, facetChunkAxial);
 	ctx->leafCluster = nullptr;
 	if (f->leafClusterArea) {
 		std::vector<int> lca(f->leafClusterArea, f->leafClusterArea + 2 * (size_t)f->numLeafs);

@@ -61,6 +61,14 @@ struct DevMap {
 	const int    *borders;      // plane | inward << 31
 	const int4   *facetRuns;    // per facet: first plane of its run in facetPlanes, numBorders, borderInward bits, 0
 	const float4 *facetPlanes;  // per facet: surface plane, then its border planes in order (copies of patchPlanes)
+	// Axial borders of a facet (the bevels of CM_AddFacetBevels, cm_patch.c:780-960, and any border that happens to be
+	// axial), as six distances: [2f] = +x, -x, +y, -y ; [2f+1] = +z, -z, -, - ; +inf where the facet has no such border.
+	// A sweep that one of these planes rejects (CM_CheckFacetPlane's first test) is rejected by the facet whatever its other
+	// planes say, so a box sweep tests them first -- six subtractions from one 32-byte record -- and the same six numbers,
+	// maximised over 32 consecutive facets (facetChunkAxial, [2c], [2c+1]; patchInfo[2p+1].z = the patch's first chunk),
+	// let a whole pass of patchByWarp be skipped.
+	const float4 *facetAxial;
+	const float4 *facetChunkAxial;
 	int numNodes;
 	int numModels;
 	int boxBrush;
@@ -469,7 +477,41 @@ __device__ __forceinline__ bool facetPlaneStepPoint(const DevMap &m, Lane &L) {
 // start (point: `intersect > tw->trace.fraction` skips the facet; the survivors of a pass are replayed in order against
 // the fraction as it falls).  The counting kernel variant keeps the plane-per-round walk: its visit counts are the
 // reference's, which depend on that order.
+__device__ __forceinline__ float rcpApproxFtz(float x) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
 struct FacetBox { bool ok; float enter; int which; };
+
+// Do the axial border planes of the facet (or of every facet of the chunk) alone reject the sweep?  Two ways:
+//  * CM_CheckFacetPlane's first test on one of them -- start in front of the plane and the end at least 1/8 in front of
+//    it too (cm_patch.c:1329-1331).  The arithmetic is the reference's own for such a plane (cm_patch.c:1412-1426,
+//    1326-1327) with a hull whose two halves are equal: the plane is pushed out by the hull's extent on its axis
+//    (dist + |offset|, offset = +-extent exactly), d = +-p - dist exactly as DotProduct gives it for a unit axis normal.
+//    `whole` adds the `d2 >= d1` half of that test, which holds for a facet but not for a chunk's maximum.
+//  * the slab test: these planes are a box around the facet; where the sweep enters the last of them (enterFrac can
+//    only be later) and leaves the first (leaveFrac can only be earlier) is computed with float quotients
+//    (rcp.approx; relative error < 2^-21 against the reference's rounded double quotient), and a facet whose box the
+//    sweep leaves before it has entered it -- by a margin of 2^-18 -- fails `enterFrac < leaveFrac` (cm_patch.c:1441).
+// Both hold for a chunk's maxima: a larger distance makes every d smaller, entering quotients smaller, leaving ones
+// larger, and a plane the sweep does not cross at the larger distance simply drops out of the test.
+__device__ __forceinline__ bool axialBordersReject(const float4 a, const float4 b, const Lane &T, const bool whole) {
+	bool rej = false;
+	float enter = -1.0f, leave = 1.0f;
+#define CMGPU_AX(D, s, e, ext) { const float dd = (D) + (ext); const float d1 = (s) - dd, d2 = (e) - dd; \
+                                 rej |= d1 > 0 && (d2 >= 0.125f || (whole && d2 >= d1)); \
+                                 const float inv = rcpApproxFtz(d1 - d2); \
+                                 if (d1 > d2 && d1 > 0) enter = fmaxf(enter, (d1 - 0.125f) * inv); \
+                                 if (d1 < d2 && d2 > 0) leave = fminf(leave, (d1 + 0.125f) * inv); }
+	CMGPU_AX(a.x, T.sx, T.ex, T.p0x) CMGPU_AX(a.y, -T.sx, -T.ex, T.p0x)
+	CMGPU_AX(a.z, T.sy, T.ey, T.p0y) CMGPU_AX(a.w, -T.sy, -T.ey, T.p0y)
+	CMGPU_AX(b.x, T.sz, T.ez, T.p0z) CMGPU_AX(b.y, -T.sz, -T.ez, T.p0z)
+#undef CMGPU_AX
+	// NaN (inf - inf for a missing plane) fails every comparison: no rejection from it
+	return rej || enter > leave + (fabsf(enter) + fabsf(leave)) * 3.8146973e-6f + 1e-30f;
+}
 
 // one facet against a box sweep: CM_TraceThroughPatchCollide's loop body (cm_patch.c:1384-1446) up to the final comparison
 __device__ __forceinline__ FacetBox facetBoxWhole(const DevMap &m, Lane &T, const int f) {
@@ -535,6 +577,7 @@ __device__ __forceinline__ void patchByWarp(const DevMap &m, Lane &L, const int 
 	T.n0x = __shfl_sync(full, L.n0x, owner); T.n0y = __shfl_sync(full, L.n0y, owner); T.n0z = __shfl_sync(full, L.n0z, owner);
 	T.p0x = __shfl_sync(full, L.p0x, owner); T.p0y = __shfl_sync(full, L.p0y, owner); T.p0z = __shfl_sync(full, L.p0z, owner);
 	const int first = __shfl_sync(full, L.side, owner), end = __shfl_sync(full, L.sideEnd, owner);
+	const int firstChunk = __shfl_sync(full, L.firstSide, owner);     // set when the item entered the patch (M_PATCH)
 	const bool point = (__shfl_sync(full, L.flags, owner) & F_POINT) != 0;
 	float cur = __shfl_sync(full, L.fraction, owner);
 	bool any = false;
@@ -561,11 +604,23 @@ __device__ __forceinline__ void patchByWarp(const DevMap &m, Lane &L, const int 
 		}
 		return;
 	}
-	for (int base = first; base < end; base += 32) {
+	// the axial pre-tests need the reference's |offset| to be the same number for both halves of the hull
+	const bool cull = T.n0x == -T.p0x && T.n0y == -T.p0y && T.n0z == -T.p0z;
+	unsigned chunks = 0xffffffffu;                                    // passes that cannot be skipped
+	const bool chunkCull = cull && end - first <= 1024;               // one chunk per lane (MAX_FACETS is 1024, cm_patch.h:23)
+	if (chunkCull) {
+		const int c = firstChunk + (int)lane;
+		bool live = false;
+		if (first + 32 * (int)lane < end) live = !axialBordersReject(__ldg(&m.facetChunkAxial[2 * c]), __ldg(&m.facetChunkAxial[2 * c + 1]), T, false);
+		chunks = __ballot_sync(full, live);
+	}
+	for (int base = first, ci = 0; base < end; base += 32, ci++) {
+		if (chunkCull && !((chunks >> ci) & 1u)) continue;
 		const int f = base + (int)lane;
 		FacetBox r;
 		r.ok = false; r.enter = -1.0f; r.which = -2;
-		if (f < end) r = facetBoxWhole(m, T, f);
+		if (f < end && !(cull && axialBordersReject(__ldg(&m.facetAxial[2 * f]), __ldg(&m.facetAxial[2 * f + 1]), T, true)))
+			r = facetBoxWhole(m, T, f);
 		const bool accept = r.ok && r.enter < cur;
 		// enter is >= 0 here (or -0.0, which orders like +0.0: strict `<` lets the first facet keep a tie)
 		const unsigned key = accept ? (__float_as_uint(r.enter) & 0x7fffffffu) : 0xffffffffu;
@@ -1097,6 +1152,7 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 							const int4 pb = __ldg(&m.patchInfo[2 * p + 1]);
 							// the facets are walked one per scheduler round (M_FACET); the brush cursor is idle meanwhile
 							L.brush = p; L.side = pb.x; L.sideEnd = pb.x + pb.y;
+							L.firstSide = pb.z;                          // patchByWarp: the patch's first chunk of 32 facets
 							L.lead = -1;                                 // at the surface plane of the first facet
 							L.enter = L.fraction;                        // fraction before this patch (cm_trace.c:245)
 							mode = M_FACET;
