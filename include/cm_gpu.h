@@ -361,6 +361,36 @@ int cmgpu_ipc_open(cmgpu_ctx *ctx, const unsigned char handle[64], void **devptr
 int cmgpu_ipc_close(cmgpu_ctx *ctx, void *devptr);
 int cmgpu_ipc_free(cmgpu_ctx *ctx, void *devptr);
 
+/* ---- botlib's AAS tracer -----------------------------------
+ * AAS_TraceClientBBox (code/botlib/be_aas_sample.c:399-665) and AAS_PointAreaNum (:212-258), batched: the line traces a
+ * bot's movement prediction issues (be_aas_move.c:644,772,923) against the AAS file's own tree.  The world is handed
+ * over as the three arrays the tracer reads of aas_t (be_aas_def.h): planes [numplanes][5] floats (normal, dist, type;
+ * stored in opposite pairs, plane n ^ 1 is plane n flipped), nodes [numnodes][3] ints (planenum, children[0],
+ * children[1]; node 0 is the dummy, the root is node 1; child > 0 a node, 0 a solid leaf, < 0 minus an area number) and
+ * areasettings[].presencetype per area (area 0 is the dummy).  Entity collisions (passent >= 0, :472-487) are server
+ * traces -- cmgpu_sv_trace_batch -- and not part of this call: it is AAS_TraceClientBBox(start, end, presencetype, -1).
+ * Results are aas_trace_t records (be_aas.h:84-93), byte for byte.  Independent of the clip map: cmgpu_upload /
+ * cmgpu_clear do not touch it. */
+typedef struct {
+	int32_t startsolid;
+	float   fraction;
+	float   endpos[3];
+	int32_t ent;
+	int32_t lastarea;
+	int32_t area;
+	int32_t planenum;
+} cmgpu_aas_trace_t;                 /* 36 bytes */
+
+int cmgpu_aas_upload(cmgpu_ctx *ctx, int numplanes, const float *planes, int numnodes, const int32_t *nodes, int numareas,
+                     const int32_t *presencetypes);
+/* presencetypes: one per item (presence_stride 1) or one for the batch (stride 0: a HOST pointer, also for the _device call) */
+int cmgpu_aas_trace_client_bbox_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                                      const int32_t *presencetypes, int presence_stride, cmgpu_aas_trace_t *results);
+int cmgpu_aas_trace_client_bbox_batch_device(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                                             const int32_t *presencetypes, int presence_stride, cmgpu_aas_trace_t *results, void *stream);
+int cmgpu_aas_point_area_num_batch(cmgpu_ctx *ctx, int n, const float *points, int32_t *areas);
+int cmgpu_aas_point_area_num_batch_device(cmgpu_ctx *ctx, int n, const float *points, int32_t *areas, void *stream);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

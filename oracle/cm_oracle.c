@@ -1020,3 +1020,131 @@ int cmo_entity_visible(int numAreas, const int *floodnum, int numClusters, int c
 	}
 	return 1;
 }
+
+/* ================================================================================================================
+ * botlib's AAS tracer: AAS_TraceClientBBox (code/botlib/be_aas_sample.c:399-665) and AAS_PointAreaNum (:212-258),
+ * restated over plain arrays.  planes [n][5] (normal, dist, type), nodes [n][3] (planenum, children[0], children[1];
+ * node 0 is the dummy, the root is node 1), presence[area].  Entity collisions (passent >= 0, :472-487) are the
+ * server's SV_Trace and not part of this path: passent is -1.  All arithmetic is float except the two places the
+ * reference's literals make double: (front +- 0.125) / (front - back) (:624-625) and VectorMA(.., -0.125, ..) (:459,518).
+ * Pinned to the unmodified reference by tests/test_aas.py.
+ * ================================================================================================================ */
+typedef struct { int startsolid; float fraction; float endpos[3]; int ent, lastarea, area, planenum; } cmo_aas_trace_t;
+
+static float aas_dot(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+static void aas_blocked(cmo_aas_trace_t *tr, const float *planes, const float *start, const float *end, float *segStart,
+                        int planenum, int area) {
+	float v1[3], v2[3];
+	int i;
+	if (segStart[0] == start[0] && segStart[1] == start[1] && segStart[2] == start[2]) {   /* :444-451 */
+		tr->startsolid = 1;
+		tr->fraction = 0.0f;
+		v1[0] = v1[1] = v1[2] = 0.0f;
+	} else {
+		float len2, length, ilength, l2;
+		tr->startsolid = 0;
+		for (i = 0; i < 3; i++) { v1[i] = end[i] - start[i]; v2[i] = segStart[i] - start[i]; }
+		l2 = sqrtf(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);                           /* VectorLength, q_shared.h:558 */
+		len2 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];                               /* VectorNormalize, q_math.c:857-874 */
+		length = len2;
+		if (len2) {
+			ilength = 1 / (float)sqrt(len2);
+			length = len2 * ilength;
+			v1[0] *= ilength; v1[1] *= ilength; v1[2] *= ilength;
+		}
+		tr->fraction = l2 / length;
+		for (i = 0; i < 3; i++) segStart[i] = (float)(segStart[i] + v1[i] * (-0.125));     /* VectorMA with a double scale */
+	}
+	for (i = 0; i < 3; i++) tr->endpos[i] = segStart[i];
+	tr->ent = 0;
+	tr->area = area;
+	tr->planenum = planenum;
+	if (aas_dot(v1, planes + 5 * (size_t)planenum) > 0) tr->planenum ^= 1;                  /* :468-469 */
+}
+
+void cmo_aas_trace_client_bbox(const float *planes, const int *nodes, const int *presence, const float *start, const float *end,
+                               int presencetype, cmo_aas_trace_t *out) {
+	struct { float start[3], end[3]; int planenum, nodenum; } stack[127], *sp = stack;
+	cmo_aas_trace_t tr;
+	int i;
+	memset(&tr, 0, sizeof(tr));
+	for (i = 0; i < 3; i++) { sp->start[i] = start[i]; sp->end[i] = end[i]; }
+	sp->planenum = 0;
+	sp->nodenum = 1;
+	sp++;
+	for (;;) {
+		sp--;
+		if (sp < stack) {                                          /* nothing was hit, :421-434 */
+			tr.startsolid = 0;
+			tr.fraction = 1.0f;
+			for (i = 0; i < 3; i++) tr.endpos[i] = end[i];
+			tr.ent = 0; tr.area = 0; tr.planenum = 0;
+			break;
+		}
+		const int nodenum = sp->nodenum;
+		if (nodenum < 0) {                                         /* an area, :438-490 */
+			if (!(presence[-nodenum] & presencetype)) { aas_blocked(&tr, planes, start, end, sp->start, sp->planenum, -nodenum); break; }
+			tr.lastarea = -nodenum;
+			continue;
+		}
+		if (!nodenum) { aas_blocked(&tr, planes, start, end, sp->start, sp->planenum, 0); break; }   /* solid leaf, :492-528 */
+		const int *nd = nodes + 3 * (size_t)nodenum;
+		const float *pl = planes + 5 * (size_t)nd[0];
+		float cs[3], ce[3];
+		for (i = 0; i < 3; i++) { cs[i] = sp->start[i]; ce[i] = sp->end[i]; }
+		float front = aas_dot(cs, pl) - pl[3], back = aas_dot(ce, pl) - pl[3];
+		if (front >= 0 && back >= 0) {                             /* ON_EPSILON is 0, :590-603 */
+			sp->nodenum = nd[1];
+			sp++;
+			if (sp >= &stack[127]) break;                          /* "stack overflow": the trace as it stands */
+		} else if (front < 0 && back < 0) {
+			sp->nodenum = nd[2];
+			sp++;
+			if (sp >= &stack[127]) break;
+		} else {
+			const int tmpplanenum = sp->planenum;
+			float frac, mid[3];
+			if (front == back) front -= 0.001f;
+			if (front < 0) frac = (float)((front + 0.125) / (front - back));
+			else frac = (float)((front - 0.125) / (front - back));
+			if (frac < 0) frac = 0.001f;
+			else if (frac > 1) frac = 0.999f;
+			for (i = 0; i < 3; i++) mid[i] = cs[i] + (ce[i] - cs[i]) * frac;
+			const int side = front < 0;
+			for (i = 0; i < 3; i++) sp->start[i] = mid[i];          /* the far part keeps its end */
+			sp->planenum = nd[0];
+			sp->nodenum = nd[1 + !side];
+			sp++;
+			if (sp >= &stack[127]) break;
+			for (i = 0; i < 3; i++) { sp->start[i] = cs[i]; sp->end[i] = mid[i]; }
+			sp->planenum = tmpplanenum;
+			sp->nodenum = nd[1 + side];
+			sp++;
+			if (sp >= &stack[127]) break;
+		}
+	}
+	*out = tr;
+}
+
+void cmo_aas_trace_client_bbox_batch(const float *planes, const int *nodes, const int *presence, int n, const float *starts,
+                                     const float *ends, const int *presencetypes, int presence_stride, cmo_aas_trace_t *out) {
+	int i;
+	for (i = 0; i < n; i++)
+		cmo_aas_trace_client_bbox(planes, nodes, presence, starts + 3 * (size_t)i, ends + 3 * (size_t)i,
+		                          presencetypes[presence_stride ? i : 0], out + i);
+}
+
+void cmo_aas_point_area_num_batch(const float *planes, const int *nodes, int n, const float *points, int *out) {
+	int i;
+	for (i = 0; i < n; i++) {
+		int nodenum = 1;
+		while (nodenum > 0) {
+			const int *nd = nodes + 3 * (size_t)nodenum;
+			const float *pl = planes + 5 * (size_t)nd[0];
+			const float dist = aas_dot(points + 3 * (size_t)i, pl) - pl[3];
+			nodenum = dist > 0 ? nd[1] : nd[2];
+		}
+		out[i] = nodenum ? -nodenum : 0;
+	}
+}

@@ -282,3 +282,30 @@ class OracleCM:
         f = np.zeros(3, np.float32); r = np.zeros(3, np.float32); u = np.zeros(3, np.float32)
         self.lib.cmo_angle_vectors(_p(a), _p(f), _p(r), _p(u))
         return f, r, u
+
+
+class OracleAAS:
+    """The restated AAS tracer of cm_oracle.c (AAS_TraceClientBBox / AAS_PointAreaNum) over an aasgen.AasWorld."""
+
+    def __init__(self, world):
+        if not available() and not build():
+            raise RuntimeError("oracle/libcmoracle.so missing and could not be built")
+        self.lib = C.CDLL(LIB_PATH)
+        self.planes, self.nodes, self.presence = _f(world.planes), _i(world.nodes), _i(world.presence)
+
+    def trace_client_bbox(self, starts, ends, presencetype):
+        from .cmref import AAS_TRACE_DTYPE
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        pt = np.asarray(presencetype)
+        pt, ps = (_i(pt.reshape(1)), 0) if pt.ndim == 0 else (_i(pt), 1)
+        out = np.zeros(n, dtype=AAS_TRACE_DTYPE)
+        self.lib.cmo_aas_trace_client_bbox_batch(_p(self.planes), _p(self.nodes), _p(self.presence), n, _p(starts), _p(ends),
+                                                 _p(pt), ps, _p(out))
+        return out
+
+    def point_area_num(self, points):
+        points = _f(points)
+        out = np.zeros(points.shape[0], np.int32)
+        self.lib.cmo_aas_point_area_num_batch(_p(self.planes), _p(self.nodes), points.shape[0], _p(points), _p(out))
+        return out

@@ -23,6 +23,11 @@ TRACE_DTYPE = np.dtype([
     ("surfaceFlags", "<i4"), ("contents", "<i4"), ("entityNum", "<i4")])
 assert TRACE_DTYPE.itemsize == 56     # q_shared.h:976-986
 
+# aas_trace_t, botlib/be_aas.h:84-93
+AAS_TRACE_DTYPE = np.dtype([("startsolid", "<i4"), ("fraction", "<f4"), ("endpos", "<f4", (3,)), ("ent", "<i4"),
+                            ("lastarea", "<i4"), ("area", "<i4"), ("planenum", "<i4")])
+assert AAS_TRACE_DTYPE.itemsize == 36
+
 
 def available() -> bool:
     return os.path.exists(LIB_PATH)
@@ -332,6 +337,30 @@ class RefCM:
         vis = np.zeros((origins.shape[0], nums.shape[0]), np.uint8)
         self.lib.svref_visible_from_points(origins.shape[0], _p(origins), nums.shape[0], _p(nums), _p(vis))
         return vis.astype(bool)
+
+    # ---- botlib's AAS sampling (botlib/be_aas_sample.c, compiled verbatim; oracle/aas_shim.c) ---------------------
+    def aas_load(self, world):
+        """world: threecore_b200.aasgen.AasWorld (planes [n,5], nodes [n,3], presence [n])"""
+        planes, nodes, pres = _f(world.planes), _i(world.nodes), _i(world.presence)
+        assert self.lib.aasref_sizeof_trace() == AAS_TRACE_DTYPE.itemsize
+        self._check(self.lib.aasref_load(planes.shape[0], _p(planes), nodes.shape[0], _p(nodes), pres.shape[0], _p(pres)), "aas load")
+        return self
+
+    def aas_trace_client_bbox(self, starts, ends, presencetype):
+        """n x AAS_TraceClientBBox(start, end, presencetype, passent = -1) (be_aas_sample.c:399-665)"""
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        pt = np.asarray(presencetype)
+        pt, ps = (_i(pt.reshape(1)), 0) if pt.ndim == 0 else (_i(pt), 1)
+        out = np.zeros(n, dtype=AAS_TRACE_DTYPE)
+        self.lib.aasref_trace_client_bbox_batch(n, _p(starts), _p(ends), _p(pt), ps, _p(out))
+        return out
+
+    def aas_point_area_num(self, points):
+        points = _f(points)
+        out = np.zeros(points.shape[0], np.int32)
+        self.lib.aasref_point_area_num_batch(points.shape[0], _p(points), _p(out))
+        return out
 
     # ---- dumps of the loaded clipMap_t -----------------------------------
     COUNT_NAMES = ["planes", "nodes", "leafs", "leafbrushes", "leafsurfaces", "brushes", "brushsides",

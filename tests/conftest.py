@@ -12,7 +12,7 @@ for _p in (ROOT, os.path.join(ROOT, 'tests')):
 # the ANCHOR of every GPU parity claim, so they run in both invocations the driver uses: `-m "not gpu"` (they carry no
 # gpu mark) and `-m gpu` (the hook below adds the mark for that run), and the GPU box's record shows the anchor green
 # next to the kernels it vouches for.
-ANCHOR_MODULES = {"test_oracle_vs_ref.py", "test_golden.py", "test_loader.py", "test_abi.py", "test_leaf_queries.py",
+ANCHOR_MODULES = {"test_oracle_vs_ref.py", "test_golden.py", "test_loader.py", "test_abi.py", "test_leaf_queries.py", "test_aas.py",
                   "test_sv_world.py"}
 
 

@@ -11,6 +11,7 @@
 #include "cm_trace_simple.cuh"
 #include "cm_sv_world.cuh"
 #include "cm_leaf_queries.cuh"
+#include "cm_aas.cuh"
 #include "../../include/cm_gpu.h"
 
 #include <cuda.h>
@@ -151,6 +152,10 @@ struct cmgpu_ctx_s {
 	int numClusters = 0, clusterBytes = 0, numAreas = 0, noAreas = 0;
 	std::vector<int> areaPortals, floodnum;          // host copies: [numAreas][numAreas] reference counts, [numAreas]
 	unsigned *hSvTotal = nullptr;        // pinned
+	// botlib's AAS world (cm_aas.cuh): its own tree, independent of the clip map
+	AasMap aas{};
+	DevBuf bAas;
+	bool hasAas = false;
 	// host regions pinned through this context (cmgpu_host_register, or "auto_register"): page-aligned [lo, hi)
 	std::vector<std::pair<uintptr_t, uintptr_t>> hostRegs;
 	bool autoRegister = false;
@@ -1222,6 +1227,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	                  &ctx->bKeys, &ctx->bRecs, &ctx->bCompact, &ctx->bSvWorld, &ctx->bSvOffsets, &ctx->bSvTiles, &ctx->bSvItems, &ctx->bSvCand,
 	                  &ctx->bSvPass, &ctx->bLeafLists, &ctx->bLeafCounts, &ctx->bVis, &ctx->bFlood, &ctx->bEntRecs, &ctx->bVisible}) releaseBuf(*b);
 	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
+	releaseBuf(ctx->bAas);
 	for (auto &r : ctx->hostRegs) cudaHostUnregister((void *)r.first);
 	ctx->hostRegs.clear();
 	for (auto &b : ctx->bHist) releaseBuf(b);
@@ -2401,6 +2407,146 @@ int cmgpu_measure_l2_read(cmgpu_ctx *ctx, size_t bytes, int passes, double *gbs)
 	cudaFree(buf);
 	if (!ok) return fail(ctx, CMGPU_ERR_CUDA, "cmgpu_measure_l2_read: %s", cudaGetErrorString(cudaGetLastError()));
 	*gbs = best;
+	return CMGPU_OK;
+}
+
+}  // extern "C"
+
+
+// =====================================================================================
+// botlib's AAS tracer (cm_aas.cuh; code/botlib/be_aas_sample.c)
+// =====================================================================================
+extern "C" {
+
+int cmgpu_aas_upload(cmgpu_ctx *ctx, int numplanes, const float *planes, int numnodes, const int32_t *nodes, int numareas,
+                     const int32_t *presencetypes) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (numplanes < 2 || !planes || numnodes < 2 || !nodes || numareas < 1 || !presencetypes)
+		return fail(ctx, CMGPU_ERR_BAD_MAP, "cmgpu_aas_upload: an AAS world has planes, a dummy node 0 and a root node 1, and a dummy area 0");
+	// every index the kernels follow is checked here; the node graph must be a tree (a cycle would never end on the device)
+	for (int i = 1; i < numnodes; i++) {
+		const int32_t *nd = nodes + 3 * (size_t)i;
+		if (nd[0] < 0 || nd[0] >= numplanes) return fail(ctx, CMGPU_ERR_BAD_MAP, "aas node %d: bad plane %d", i, nd[0]);
+		for (int c = 1; c <= 2; c++) {
+			if (nd[c] > 0 && nd[c] >= numnodes) return fail(ctx, CMGPU_ERR_BAD_MAP, "aas node %d: bad child %d", i, nd[c]);
+			if (nd[c] < 0 && -(long long)nd[c] >= numareas) return fail(ctx, CMGPU_ERR_BAD_MAP, "aas node %d: bad area %d", i, -nd[c]);
+		}
+	}
+	{
+		std::vector<unsigned char> seen((size_t)numnodes, 0);
+		std::vector<int> st;
+		st.push_back(1);
+		while (!st.empty()) {
+			const int n = st.back();
+			st.pop_back();
+			if (seen[n]) return fail(ctx, CMGPU_ERR_BAD_MAP, "aas node %d reachable twice: not a tree", n);
+			seen[n] = 1;
+			for (int c = 1; c <= 2; c++) if (nodes[3 * (size_t)n + c] > 0) st.push_back(nodes[3 * (size_t)n + c]);
+		}
+	}
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaDeviceSynchronize());
+	const size_t nNodes = (size_t)numnodes, nPlanes = (size_t)numplanes, nAreas = (size_t)numareas;
+	std::vector<float4> nodePlane(nNodes), pl(nPlanes);
+	std::vector<int4> nodeInfo(nNodes);
+	for (size_t i = 0; i < nPlanes; i++) pl[i] = make_float4(planes[5 * i], planes[5 * i + 1], planes[5 * i + 2], planes[5 * i + 3]);
+	nodePlane[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	nodeInfo[0] = make_int4(0, 0, 0, 0);
+	for (size_t i = 1; i < nNodes; i++) {
+		nodePlane[i] = pl[(size_t)nodes[3 * i]];
+		nodeInfo[i] = make_int4(nodes[3 * i], nodes[3 * i + 1], nodes[3 * i + 2], 0);
+	}
+	const size_t offInfo = nNodes * 16, offPlanes = offInfo + nNodes * 16, offPres = offPlanes + nPlanes * 16, total = offPres + nAreas * 4;
+	ctx->hasAas = false;
+	int rc = reserve(ctx, ctx->bAas, total);
+	if (rc) return rc;
+	char *base = (char *)ctx->bAas.p;
+	CUDA_TRY(ctx, cudaMemcpy(base, nodePlane.data(), nNodes * 16, cudaMemcpyHostToDevice));
+	CUDA_TRY(ctx, cudaMemcpy(base + offInfo, nodeInfo.data(), nNodes * 16, cudaMemcpyHostToDevice));
+	CUDA_TRY(ctx, cudaMemcpy(base + offPlanes, pl.data(), nPlanes * 16, cudaMemcpyHostToDevice));
+	CUDA_TRY(ctx, cudaMemcpy(base + offPres, presencetypes, nAreas * 4, cudaMemcpyHostToDevice));
+	ctx->aas.nodePlane = (const float4 *)base;
+	ctx->aas.nodeInfo = (const int4 *)(base + offInfo);
+	ctx->aas.planes = (const float4 *)(base + offPlanes);
+	ctx->aas.presence = (const int *)(base + offPres);
+	ctx->aas.numNodes = numnodes; ctx->aas.numPlanes = numplanes; ctx->aas.numAreas = numareas;
+	ctx->hasAas = true;
+	return CMGPU_OK;
+}
+
+int cmgpu_aas_trace_client_bbox_batch_device(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                                             const int32_t *presencetypes, int presence_stride, cmgpu_aas_trace_t *results, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!starts || !ends || !presencetypes || !results)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_aas_trace_client_bbox_batch_device: bad argument");
+	if (!ctx->hasAas) return fail(ctx, CMGPU_ERR_NO_MAP, "no AAS world uploaded (the reference returns a zeroed trace, be_aas_sample.c:414)");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	AasTraceBatch q{};
+	q.n = n; q.starts = starts; q.ends = ends;
+	if (presence_stride) q.presencetypes = presencetypes; else q.sharedPresence = presencetypes[0];     // host [1], by value
+	q.out = reinterpret_cast<int *>(results);
+	aasTraceClientBBoxKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->aas, q);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_aas_point_area_num_batch_device(cmgpu_ctx *ctx, int n, const float *points, int32_t *areas, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !areas))) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_aas_point_area_num_batch_device: bad argument");
+	if (!ctx->hasAas) return fail(ctx, CMGPU_ERR_NO_MAP, "no AAS world uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	aasPointAreaNumKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->aas, n, points, areas);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_aas_trace_client_bbox_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
+                                      const int32_t *presencetypes, int presence_stride, cmgpu_aas_trace_t *results) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!starts || !ends || !presencetypes || !results)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_aas_trace_client_bbox_batch: bad argument");
+	if (!ctx->hasAas) return fail(ctx, CMGPU_ERR_NO_MAP, "no AAS world uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, N * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bEnds, N * 12))) return rc;
+	if (presence_stride && (rc = reserve(ctx, ctx->bMasks, N * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bOut, N * sizeof(cmgpu_aas_trace_t)))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, starts, N * 12, cudaMemcpyHostToDevice, s));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bEnds.p, ends, N * 12, cudaMemcpyHostToDevice, s));
+	if (presence_stride) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bMasks.p, presencetypes, N * 4, cudaMemcpyHostToDevice, s));
+	rc = cmgpu_aas_trace_client_bbox_batch_device(ctx, n, (const float *)ctx->bStarts.p, (const float *)ctx->bEnds.p,
+	                                              presence_stride ? (const int32_t *)ctx->bMasks.p : presencetypes, presence_stride,
+	                                              (cmgpu_aas_trace_t *)ctx->bOut.p, s);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(results, ctx->bOut.p, N * sizeof(cmgpu_aas_trace_t), cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return CMGPU_OK;
+}
+
+int cmgpu_aas_point_area_num_batch(cmgpu_ctx *ctx, int n, const float *points, int32_t *areas) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || (n > 0 && (!points || !areas))) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_aas_point_area_num_batch: bad argument");
+	if (!ctx->hasAas) return fail(ctx, CMGPU_ERR_NO_MAP, "no AAS world uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n;
+	int rc;
+	if ((rc = reserve(ctx, ctx->bStarts, N * 12))) return rc;
+	if ((rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bStarts.p, points, N * 12, cudaMemcpyHostToDevice, s));
+	rc = cmgpu_aas_point_area_num_batch_device(ctx, n, (const float *)ctx->bStarts.p, (int32_t *)ctx->bHit.p, s);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(areas, ctx->bHit.p, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
 	return CMGPU_OK;
 }
 

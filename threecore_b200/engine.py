@@ -96,6 +96,9 @@ SV_ENTITY_DTYPE = np.dtype([("number", "<i4"), ("ownerNum", "<i4"), ("contents",
                             ("origin", "<f4", (3,)), ("angles", "<f4", (3,))])
 assert SV_ENTITY_DTYPE.itemsize == 92
 # cmgpu_entity_clusters_t: what the PVS part of SV_LinkEntity stores (server.h:42-45)
+# aas_trace_t (botlib/be_aas.h:84-93) == cmgpu_aas_trace_t
+AAS_TRACE_DTYPE = np.dtype([("startsolid", "<i4"), ("fraction", "<f4"), ("endpos", "<f4", (3,)), ("ent", "<i4"),
+                            ("lastarea", "<i4"), ("area", "<i4"), ("planenum", "<i4")])
 ENT_CLUSTERS_DTYPE = np.dtype([("numLeafs", "<i4"), ("areanum", "<i4"), ("areanum2", "<i4"), ("numClusters", "<i4"),
                                ("lastCluster", "<i4"), ("clusternums", "<i4", (16,))])
 assert ENT_CLUSTERS_DTYPE.itemsize == 84
@@ -131,6 +134,11 @@ def load_library() -> C.CDLL:
     lib.cmgpu_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_ipc_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.cmgpu_aas_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.cmgpu_aas_trace_client_bbox_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.cmgpu_aas_trace_client_bbox_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cmgpu_aas_point_area_num_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cmgpu_aas_point_area_num_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cmgpu_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     lib.cmgpu_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -510,6 +518,42 @@ class Engine:
         self._check(self.lib.cmgpu_point_contents_batch_device(
             self.h, n, ptr(points), ptr(models), ptr(origins), ptr(rotations), ptr(rot_index),
             ptr(boxmins), ptr(boxmaxs), ptr(out), C.c_void_p(stream)))
+
+    # ---- botlib's AAS tracer (botlib/be_aas_sample.c:212-258, 399-665) -----------------
+    def aas_upload(self, world):
+        """world: planes [n,5] float32, nodes [n,3] int32, presence [numareas] int32 (aasgen.AasWorld or the like)"""
+        planes, nodes, pres = _f(world.planes), _i(world.nodes), _i(world.presence)
+        self._check(self.lib.cmgpu_aas_upload(self.h, planes.shape[0], _p(planes), nodes.shape[0], _p(nodes), pres.shape[0], _p(pres)))
+
+    def aas_trace_client_bbox(self, starts, ends, presencetype) -> np.ndarray:
+        """n x AAS_TraceClientBBox(start, end, presencetype, -1) on host arrays -> aas_trace_t records"""
+        starts, ends = _f(starts), _f(ends)
+        n = starts.shape[0]
+        pt = np.asarray(presencetype)
+        pt, ps = (_i(pt.reshape(1)), 0) if pt.ndim == 0 else (_i(pt), 1)
+        out = np.zeros(n, dtype=AAS_TRACE_DTYPE)
+        self._check(self.lib.cmgpu_aas_trace_client_bbox_batch(self.h, n, _p(starts), _p(ends), _p(pt), ps, _p(out)))
+        return out
+
+    def aas_trace_client_bbox_device(self, starts, ends, presencetype, out, stream=None):
+        """CUDA tensors; presencetype: an int (shared) or an int32 CUDA tensor [n]; out: uint8 [n,36]"""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(starts.device).cuda_stream
+        if isinstance(presencetype, int):
+            pt = np.array([presencetype], np.int32)
+            ptr, ps, keep = pt.ctypes.data, 0, pt
+        else:
+            ptr, ps, keep = presencetype.data_ptr(), 1, presencetype
+        self._check(self.lib.cmgpu_aas_trace_client_bbox_batch_device(self.h, starts.shape[0], starts.data_ptr(), ends.data_ptr(), ptr, ps,
+                                                                      out.data_ptr(), C.c_void_p(stream)))
+        del keep
+
+    def aas_point_area_num(self, points) -> np.ndarray:
+        points = _f(points)
+        out = np.zeros(points.shape[0], np.int32)
+        self._check(self.lib.cmgpu_aas_point_area_num_batch(self.h, points.shape[0], _p(points), _p(out)))
+        return out
 
     # ---- whole SV_Trace on the device (server/sv_world.c:562-609) -----------------
     def sv_set_entities(self, ents: np.ndarray, owner_nums=None):
