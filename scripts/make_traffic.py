@@ -17,5 +17,15 @@ out = {"kernels": per, "dram_bytes_read": tot_r, "dram_bytes_write": tot_w, "dra
        "command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
                   "-k regex:'tracePool|expandRecords' -s 6 -c 2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline",
        "source": f"profiles/{tag}_traffic.csv"}
+# warp execution efficiency and issue utilisation of the walk kernel from the same set's ncu --set full capture
+try:
+    import datetime
+    k = json.load(open(f"profiles/{tag}_trace_kernel_ncu.json"))["kernels"][0]
+    out["lanes_per_instruction"] = float(k["smsp__thread_inst_executed_per_inst_executed.ratio"]["value"])
+    out["issue_active_pct"] = float(k["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"])
+    out["full_source"] = f"profiles/{tag}_trace_kernel_ncu.json"
+    out["captured"] = f"{datetime.date.today().isoformat()} (set {tag})"
+except Exception as ex:
+    print("no full capture for this set:", ex)
 json.dump(out, open("profiles/traffic.json", "w"), indent=1)
 print(out)
