@@ -130,6 +130,10 @@ const char *cmgpu_last_error(const cmgpu_ctx *ctx);   /* ctx may be NULL: last e
  * inline models, box hull; patches are tessellated on the host as
  * CM_GeneratePatchCollide does).  Free with cmgpu_flatmap_free. */
 int  cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen);
+/* The same, with the Bezier patches tessellated ON THE GPU: one thread per MST_PATCH surface runs CM_GeneratePatchCollide
+ * (cm_patch.c:1137-1203; the code the host loader runs, csrc/cm_patchgen_core.h) in a fixed scratch block; planes and
+ * facets come out in the same order with the same float bits.  `device`: CUDA device ordinal. */
+int  cmgpu_flatmap_from_bsp_device(int device, const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen);
 void cmgpu_flatmap_free(cmgpu_flatmap *map);
 
 /* Validate, pack into the device layout and copy to the context's GPU. Replaces any previous map. */

@@ -68,3 +68,23 @@ def test_generator_is_deterministic():
     s1, e1 = bspgen.make_sweeps(get_map("tiny"), 1000, 3)
     s2, e2 = bspgen.make_sweeps(get_map("tiny"), 1000, 3)
     assert s1.tobytes() == s2.tobytes() and e1.tobytes() == e2.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["patches_small", "config3"])
+def test_gpu_tessellation_equals_host_and_reference(kind):
+    """CM_GeneratePatchCollide as one GPU thread per patch (cmgpu_flatmap_from_bsp_device) -- every
+    array of the flattened map, patch planes and facets included, must be the bytes the host loader makes, which
+    test_flatmap_equals_reference_clipmap pins to the reference's own loaded clipMap_t"""
+    m = get_map("patches_small") if kind == "patches_small" else bspgen.patch_map(n_brushes=2000, n_patches=512, seed=0xC0FFEE03)
+    host = FlatMap.from_bsp(m.data).to_dict()
+    dev = FlatMap.from_bsp(m.data, tess_device=0).to_dict()
+    assert host.keys() == dev.keys()
+    for k in host:
+        a, b = np.asarray(host[k]), np.asarray(dev[k])
+        assert a.shape == b.shape and a.tobytes() == b.tobytes(), f"{kind}: `{k}` differs between host and GPU tessellation"
+    assert len(host["patches"]) > 10 and len(host["facets"]) > 100
+    if have_ref():
+        ref = cmoracle.flat_from_ref_dump(cmref.RefCM().load(m.data).dump())
+        for k in ("patch_planes", "patch_plane_signbits", "facets", "borders", "patch_bounds", "patches"):
+            assert np.asarray(ref[k]).tobytes() == np.asarray(dev[k]).tobytes(), f"{kind}: `{k}` differs from the reference's clipMap_t"

@@ -13,6 +13,8 @@
 #include "cm_leaf_queries.cuh"
 #include "cm_aas.cuh"
 #include "../../include/cm_gpu.h"
+#include "cm_patchgen.h"
+#include "cm_patchgen_core.h"
 
 #include <cuda.h>
 #include <math.h>
@@ -21,6 +23,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <memory>
+#include <new>
+#include <stddef.h>
 #include <string>
 #include <vector>
 
@@ -2551,3 +2557,69 @@ int cmgpu_aas_point_area_num_batch(cmgpu_ctx *ctx, int n, const float *points, i
 }
 
 }  // extern "C"
+
+
+// =====================================================================================
+// Bezier patches -> collision facets on the device (CM_GeneratePatchCollide, cm_patch.c:1137-1203)
+// =====================================================================================
+// One thread per patch runs the builder of cm_patchgen_core.h -- the code the host loader runs -- in its own scratch
+// block in global memory.  The work of a patch is one long dependent chain (every new plane is compared with all the
+// planes found so far, facets are validated against them in order), so there is nothing to spread over a warp without
+// changing the order in which planes are numbered; patches are independent, and a map has hundreds.
+namespace cmgpu {
+
+__global__ void __launch_bounds__(32) patchCollideKernel(int n, const int *widths, const int *heights, const int *firstPoint,
+                                                         const float *points, pg::PatchScratch *scratch) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	pg::Builder(scratch[i]).run(widths[i], heights[i], points + 3 * (size_t)firstPoint[i]);
+}
+
+bool generatePatchCollidesOnDevice(int device, int n, const int *widths, const int *heights, const int *firstPoint,
+                                   const float *points, size_t numPoints, PatchCollide *out, char *err, size_t errlen) {
+	auto failWith = [&](const char *what, cudaError_t e) {
+		if (err && errlen) snprintf(err, errlen, "%s: %s", what, cudaGetErrorString(e));
+		return false;
+	};
+	if (n <= 0) return true;
+	cudaError_t e = cudaSetDevice(device);
+	if (e != cudaSuccess) return failWith("cudaSetDevice", e);
+	int *dMeta = nullptr;
+	float *dPoints = nullptr;
+	pg::PatchScratch *dScratch = nullptr;
+	// patches are built in waves so that the scratch stays within 1 GiB whatever the map
+	const int wave = (int)std::min<size_t>((size_t)n, ((size_t)1 << 30) / sizeof(pg::PatchScratch));
+	bool ok = true;
+	std::vector<int> meta(3 * (size_t)n);
+	for (int i = 0; i < n; i++) { meta[(size_t)i] = widths[i]; meta[(size_t)n + i] = heights[i]; meta[2 * (size_t)n + i] = firstPoint[i]; }
+	std::unique_ptr<pg::PatchScratch> host(new (std::nothrow) pg::PatchScratch);
+	if (!host) { if (err && errlen) snprintf(err, errlen, "out of memory"); return false; }
+	if ((e = cudaMalloc(&dMeta, meta.size() * sizeof(int))) != cudaSuccess) ok = failWith("cudaMalloc", e);
+	if (ok && (e = cudaMalloc(&dPoints, (numPoints ? numPoints : 1) * 12)) != cudaSuccess) ok = failWith("cudaMalloc", e);
+	if (ok && (e = cudaMalloc(&dScratch, (size_t)wave * sizeof(pg::PatchScratch))) != cudaSuccess) ok = failWith("cudaMalloc (patch scratch)", e);
+	if (ok && (e = cudaMemcpy(dMeta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) ok = failWith("cudaMemcpy", e);
+	if (ok && (e = cudaMemcpy(dPoints, points, numPoints * 12, cudaMemcpyHostToDevice)) != cudaSuccess) ok = failWith("cudaMemcpy", e);
+	for (int base = 0; ok && base < n; base += wave) {
+		const int cnt = std::min(wave, n - base);
+		patchCollideKernel<<<(cnt + 31) / 32, 32>>>(cnt, dMeta + base, dMeta + n + base, dMeta + 2 * (size_t)n + base, dPoints, dScratch);
+		if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) { ok = failWith("patchCollideKernel", e); break; }
+		for (int i = 0; i < cnt && ok; i++) {
+			// results only: the tail of the block (planes, facets, bounds, counts, error), not the 330 KB of grid scratch
+			const size_t off = offsetof(pg::PatchScratch, planes);
+			if ((e = cudaMemcpy((char *)host.get() + off, (const char *)(dScratch + i) + off, sizeof(pg::PatchScratch) - off, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+				ok = failWith("cudaMemcpy (patch results)", e);
+				break;
+			}
+			if (host->error) {
+				if (err && errlen) snprintf(err, errlen, "%s", pg::errorText(host->error));
+				ok = false;
+				break;
+			}
+			patchCollideFromScratch(*host, &out[base + i]);
+		}
+	}
+	cudaFree(dMeta); cudaFree(dPoints); cudaFree(dScratch);
+	return ok;
+}
+
+}  // namespace cmgpu

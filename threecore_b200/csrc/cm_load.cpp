@@ -86,7 +86,7 @@ int lumpView(const uint8_t *base, const Lump &l, const char *what, const Fail &f
 
 }  // namespace
 
-static int flatmapFromBsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen) {
+static int flatmapFromBsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen, int tessDevice) {
 	Fail fail{err, errlen};
 	if (err && errlen) err[0] = 0;
 	if (!out) return CMGPU_ERR_INVALID;
@@ -246,8 +246,11 @@ static int flatmapFromBsp(const void *bsp, size_t len, cmgpu_flatmap **out, char
 		m->nodes[3 * (size_t)i + 2] = dnodes[i].children[1];
 	}
 
-	// patches, CMod_LoadPatches cm_load.c:514-580
+	// patches, CMod_LoadPatches cm_load.c:514-580.  The facets of every MST_PATCH surface are generated on the host, one
+	// patch after the other, or -- tessDevice >= 0 -- on that CUDA device, one thread per patch (cm_gpu.cu); either way by
+	// the builder of cm_patchgen_core.h, and appended in surface order.
 	m->surf2patch.assign((size_t)nSurfs, -1);
+	std::vector<int> patchSurf, pw, ph, pfirst;
 	for (int i = 0; i < nSurfs; i++) {
 		const DSurface &s = dsurfs[i];
 		if (s.surfaceType != MST_PATCH) continue;
@@ -256,11 +259,28 @@ static int flatmapFromBsp(const void *bsp, size_t len, cmgpu_flatmap **out, char
 		if (c > kMaxPatchVerts) return fail("CMod_LoadPatches: MAX_PATCH_VERTS");
 		if (w < 0 || hgt < 0 || s.firstVert < 0 || (int64_t)s.firstVert + c > nVerts) return fail("CMod_LoadPatches: surface %i: bad vertex range", i);
 		if (s.shader < 0 || s.shader >= nShaders) return fail("CMod_LoadPatches: bad shaderNum: %i", s.shader);
-		std::vector<float> pts(3 * (size_t)c);
-		for (int64_t j = 0; j < c; j++) memcpy(&pts[3 * (size_t)j], dverts[s.firstVert + j].xyz, 12);
-		cmgpu::PatchCollide pc;
-		char perr[256];
-		if (!cmgpu::generatePatchCollide(w, hgt, pts.data(), &pc, perr, sizeof(perr))) return fail("%s", perr);
+		patchSurf.push_back(i); pw.push_back(w); ph.push_back(hgt); pfirst.push_back(s.firstVert);
+	}
+	std::vector<cmgpu::PatchCollide> pcs(patchSurf.size());
+	char perr[256];
+	if (tessDevice >= 0 && !patchSurf.empty()) {
+		// the parameter checks of CM_GeneratePatchCollide come first, in surface order, like on the host
+		std::vector<float> allPts(3 * (size_t)nVerts);
+		for (int v = 0; v < nVerts; v++) memcpy(&allPts[3 * (size_t)v], dverts[v].xyz, 12);
+		if (!cmgpu::generatePatchCollidesOnDevice(tessDevice, (int)patchSurf.size(), pw.data(), ph.data(), pfirst.data(), allPts.data(),
+		                                          (size_t)nVerts, pcs.data(), perr, sizeof(perr))) return fail("%s", perr);
+	} else {
+		for (size_t k = 0; k < patchSurf.size(); k++) {
+			const int64_t c = (int64_t)pw[k] * ph[k];
+			std::vector<float> pts(3 * (size_t)c);
+			for (int64_t j = 0; j < c; j++) memcpy(&pts[3 * (size_t)j], dverts[pfirst[k] + j].xyz, 12);
+			if (!cmgpu::generatePatchCollide(pw[k], ph[k], pts.data(), &pcs[k], perr, sizeof(perr))) return fail("%s", perr);
+		}
+	}
+	for (size_t k = 0; k < patchSurf.size(); k++) {
+		const int i = patchSurf[k];
+		const DSurface &s = dsurfs[i];
+		const cmgpu::PatchCollide &pc = pcs[k];
 		const int ord = (int)(m->patches.size() / 6);
 		m->surf2patch[i] = ord;
 		const int firstPlane = (int)(m->patchPlanes.size() / 4), firstFacet = (int)(m->facets.size() / 3);
@@ -319,9 +339,9 @@ static int flatmapFromBsp(const void *bsp, size_t len, cmgpu_flatmap **out, char
 }
 
 // nothing may leave an extern "C" function by exception: a corrupt file that asks for absurd sizes is an error code
-extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen) {
+static int flatmapFromBspGuarded(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen, int tessDevice) {
 	try {
-		return flatmapFromBsp(bsp, len, out, err, errlen);
+		return flatmapFromBsp(bsp, len, out, err, errlen, tessDevice);
 	} catch (const std::bad_alloc &) {
 		if (out) *out = nullptr;
 		if (err && errlen) snprintf(err, errlen, "CM_LoadMap: out of memory");
@@ -331,6 +351,18 @@ extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap
 		if (err && errlen) snprintf(err, errlen, "CM_LoadMap: %s", e.what());
 		return CMGPU_ERR_BAD_MAP;
 	}
+}
+
+extern "C" int cmgpu_flatmap_from_bsp(const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen) {
+	return flatmapFromBspGuarded(bsp, len, out, err, errlen, -1);
+}
+
+extern "C" int cmgpu_flatmap_from_bsp_device(int device, const void *bsp, size_t len, cmgpu_flatmap **out, char *err, size_t errlen) {
+	if (device < 0) {
+		if (err && errlen) snprintf(err, errlen, "cmgpu_flatmap_from_bsp_device: bad device");
+		return CMGPU_ERR_INVALID;
+	}
+	return flatmapFromBspGuarded(bsp, len, out, err, errlen, device);
 }
 
 extern "C" void cmgpu_flatmap_free(cmgpu_flatmap *map) {

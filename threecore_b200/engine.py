@@ -120,6 +120,7 @@ def load_library() -> C.CDLL:
     lib.cmgpu_destroy.argtypes = [C.c_void_p]
     lib.cmgpu_destroy.restype = None
     lib.cmgpu_flatmap_from_bsp.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(_FlatMap)), C.c_char_p, C.c_size_t]
+    lib.cmgpu_flatmap_from_bsp_device.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(_FlatMap)), C.c_char_p, C.c_size_t]
     lib.cmgpu_flatmap_free.argtypes = [C.POINTER(_FlatMap)]
     lib.cmgpu_flatmap_free.restype = None
     lib.cmgpu_upload.argtypes = [C.c_void_p, C.POINTER(_FlatMap)]
@@ -190,12 +191,16 @@ class FlatMap:
         self._keep = []
 
     @classmethod
-    def from_bsp(cls, data: bytes) -> "FlatMap":
+    def from_bsp(cls, data: bytes, tess_device: int | None = None) -> "FlatMap":
+        """tess_device: CUDA device that tessellates the Bezier patches (cmgpu_flatmap_from_bsp_device); None: the host does"""
         lib = load_library()
         self = cls()
         out = C.POINTER(_FlatMap)()
         err = C.create_string_buffer(512)
-        rc = lib.cmgpu_flatmap_from_bsp(bytes(data), len(data), C.byref(out), err, len(err))
+        if tess_device is None:
+            rc = lib.cmgpu_flatmap_from_bsp(bytes(data), len(data), C.byref(out), err, len(err))
+        else:
+            rc = lib.cmgpu_flatmap_from_bsp_device(int(tess_device), bytes(data), len(data), C.byref(out), err, len(err))
         if rc:
             raise CMGPUError(rc, err.value.decode(errors="replace"))
         self._ptr = out
@@ -325,8 +330,9 @@ class Engine:
             raise CMGPUError(rc, self.lib.cmgpu_last_error(self.h).decode(errors="replace"))
 
     # ---- map ---------------------------------------------------------------
-    def load_bsp(self, data: bytes) -> FlatMap:
-        fm = FlatMap.from_bsp(data)
+    def load_bsp(self, data: bytes, gpu_patches: bool = False) -> FlatMap:
+        """parse the .bsp image (CM_LoadMap) and upload it; gpu_patches: tessellate the Bezier patches on this GPU"""
+        fm = FlatMap.from_bsp(data, self.device if gpu_patches else None)
         self.upload(fm)
         return fm
 
