@@ -48,6 +48,17 @@ constexpr int kBinSlots = CMGPU_PIPE_STREAMS;   // pipeline streams of the host-
 constexpr int kPipeChunks = 64;          // upper bound on the pieces a host batch is cut into (copies overlap the kernels)
 constexpr size_t kMinChunkItems = 1 << 16;
 
+// calls of a few items (traceHostTiny): where their arguments and results live in the context's mapped pinned block
+constexpr int kTinyMax = 128;
+struct TinyLayout {
+	static constexpr size_t v3 = 12 * (size_t)kTinyMax, i4 = 4 * (size_t)kTinyMax;
+	static constexpr size_t starts = 0, ends = starts + v3, mins = ends + v3, maxs = mins + v3, models = maxs + v3, masks = models + i4,
+	                        origins = masks + i4, rot = origins + v3, rotIdx = rot + 36 * (size_t)kTinyMax, boxmins = rotIdx + i4,
+	                        boxmaxs = boxmins + v3, out = boxmaxs + v3, hit = out + sizeof(cmgpu_trace_t) * (size_t)kTinyMax,
+	                        status = hit + i4, cursor = status + 64, total = cursor + 64;
+};
+
+
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
@@ -158,6 +169,11 @@ struct cmgpu_ctx_s {
 	int numClusters = 0, clusterBytes = 0, numAreas = 0, noAreas = 0;
 	std::vector<int> areaPortals, floodnum;          // host copies: [numAreas][numAreas] reference counts, [numAreas]
 	unsigned *hSvTotal = nullptr;        // pinned
+	// A call of a few items (the drop-in CM_BoxTrace is a batch of one) is all latency: its arguments and results live
+	// in one block of MAPPED pinned memory that the kernel reads and writes over PCIe itself -- one launch, one
+	// synchronisation, no copy calls, the status word included (traceHostTiny).
+	char *tinyHost = nullptr, *tinyDev = nullptr;
+	bool tinyCalls = true;
 	// botlib's AAS world (cm_aas.cuh): its own tree, independent of the clip map
 	AasMap aas{};
 	DevBuf bAas;
@@ -1189,6 +1205,9 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 	ok = ok && cudaMalloc(&ctx->dStatus, sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMemset(ctx->dStatus, 0, sizeof(int)) == cudaSuccess;
 	ok = ok && cudaMallocHost(&ctx->hStatus, sizeof(int)) == cudaSuccess;
+	if (ok && cudaHostAlloc((void **)&ctx->tinyHost, TinyLayout::total, cudaHostAllocMapped) == cudaSuccess) {
+		if (cudaHostGetDevicePointer((void **)&ctx->tinyDev, ctx->tinyHost, 0) != cudaSuccess) { cudaFreeHost(ctx->tinyHost); ctx->tinyHost = nullptr; cudaGetLastError(); }
+	} else if (ok) { ctx->tinyHost = nullptr; cudaGetLastError(); }
 	ok = ok && cudaMalloc(&ctx->dCursor, kCursorSlots * sizeof(int)) == cudaSuccess;
 	if (ok) {
 		int perSm = 0;
@@ -1233,6 +1252,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	                  &ctx->bKeys, &ctx->bRecs, &ctx->bCompact, &ctx->bSvWorld, &ctx->bSvOffsets, &ctx->bSvTiles, &ctx->bSvItems, &ctx->bSvCand,
 	                  &ctx->bSvPass, &ctx->bLeafLists, &ctx->bLeafCounts, &ctx->bVis, &ctx->bFlood, &ctx->bEntRecs, &ctx->bVisible}) releaseBuf(*b);
 	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
+	if (ctx->tinyHost) cudaFreeHost(ctx->tinyHost);
 	releaseBuf(ctx->bAas);
 	for (auto &r : ctx->hostRegs) cudaHostUnregister((void *)r.first);
 	ctx->hostRegs.clear();
@@ -1309,6 +1329,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "node_thresholds") ctx->nodeThresholds = value != 0;
 	else if (k == "entry_grid") ctx->entryGrid = value != 0;
 	else if (k == "auto_register") ctx->autoRegister = value != 0;
+	else if (k == "tiny_calls") ctx->tinyCalls = value != 0;
 	else if (k == "remote_pipeline") ctx->remotePipeline = value != 0;
 	else if (k == "remote_pieces") ctx->remotePieces = value < 1 ? 1 : (int)value;
 	else if (k == "remote_expand_ctas") ctx->remoteExpandCtas = value < 1 ? 1 : (int)value;
@@ -1559,6 +1580,80 @@ int cmgpu_point_contents_batch_device(cmgpu_ctx *ctx, int n, const float *points
 // ---- host-pointer entry points -----------------------------------------------------------
 // The batch is cut into chunks; chunk c's H2D copy, kernel and D2H copy are issued on stream
 // c % kBinSlots, so the copy engines (one per direction) and the SMs work on different chunks at once.
+// ---- calls of a few items ------------------------------------------------------------------------------------------
+static int traceHostTiny(cmgpu_ctx *ctx, int n, const float *starts, const float *ends, const float *mins, const float *maxs, int hull_stride,
+                         const int32_t *models, const int32_t *masks, int mask_stride, const float *origins, const float *angles,
+                         const float *boxmins, const float *boxmaxs, cmgpu_trace_t *results, int32_t *hit_ids) {
+	typedef TinyLayout T;
+	char *h = ctx->tinyHost, *d = ctx->tinyDev;
+	const size_t N = (size_t)n;
+	cudaStream_t s = ctx->streams[0];
+	if (ctx->extBusy) {                              // an earlier device-pointer call may still use the status word
+		CUDA_TRY(ctx, cudaEventSynchronize(ctx->extDone));
+		ctx->extBusy = false;
+	}
+	memcpy(h + T::starts, starts, N * 12);
+	memcpy(h + T::ends, ends, N * 12);
+	TraceBatch q{};
+	q.n = n;
+	q.starts = (const float *)(d + T::starts);
+	q.ends = (const float *)(d + T::ends);
+	if (hull_stride) {
+		memcpy(h + T::mins, mins, N * 12); memcpy(h + T::maxs, maxs, N * 12);
+		q.mins = (const float *)(d + T::mins); q.maxs = (const float *)(d + T::maxs);
+	} else if (mins) {
+		memcpy(q.sharedMins, mins, 12); memcpy(q.sharedMaxs, maxs, 12);
+	}
+	if (models) { memcpy(h + T::models, models, N * 4); q.models = (const int *)(d + T::models); }
+	if (mask_stride) { memcpy(h + T::masks, masks, N * 4); q.masks = (const int *)(d + T::masks); } else q.sharedMask = masks[0];
+	if (origins) {
+		memcpy(h + T::origins, origins, N * 12);
+		cmgpu_rotation_matrices(n, angles, (float *)(h + T::rot), (int32_t *)(h + T::rotIdx));
+		q.origins = (const float *)(d + T::origins);
+		q.rotations = (const float *)(d + T::rot);
+		q.rotIndex = (const int *)(d + T::rotIdx);
+	}
+	if (boxmins) {
+		memcpy(h + T::boxmins, boxmins, N * 12); memcpy(h + T::boxmaxs, boxmaxs, N * 12);
+		q.boxmins = (const float *)(d + T::boxmins); q.boxmaxs = (const float *)(d + T::boxmaxs);
+	}
+	q.out = reinterpret_cast<uint2 *>(d + T::out);
+	q.hitIds = hit_ids ? (int *)(d + T::hit) : nullptr;
+	q.status = (int *)(d + T::status);
+	q.cursor = (int *)(d + T::cursor);
+	*(volatile int *)(h + T::status) = 0;
+	*(volatile int *)(h + T::cursor) = 0;
+	q.counters = ctx->dCounters;
+	q.gang = ctx->gang; q.gangFetch = ctx->gangFetch; q.gangBrush = ctx->gangBrush; q.lightReps = ctx->lightReps;
+	q.facetSteps = ctx->facetSteps;
+	q.stackDepth = ctx->treeDepth;
+	q.chunk = ctx->minChunk;
+	ctx->map.noCurves = ctx->noCurves;
+	ctx->map.playerCurveClip = ctx->playerCurveClip;
+	const bool deep = ctx->treeDepth > kMaxDepth;
+	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
+	if (fast) {
+		const FastHull fh = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
+		const int nb = (n + kBlock - 1) / kBlock;
+		if (deep) CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false, kDeepDepth>, nb, kBlock, 0, s, ctx->fast, q, fh));
+		else      CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false>, nb, kBlock, 0, s, ctx->fast, q, fh));
+	} else {
+		const int warps = (n + q.chunk - 1) / q.chunk;
+		const int nb = (warps + kBlock / 32 - 1) / (kBlock / 32);
+		if (deep) CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<false, kDeepDepth>, nb, kBlock, 0, s, ctx->map, q));
+		else      CUDA_TRY(ctx, launchOnMap(ctx, traceKernel<false>, nb, kBlock, 0, s, ctx->map, q));
+	}
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	memcpy(results, h + T::out, N * sizeof(cmgpu_trace_t));
+	if (hit_ids) memcpy(hit_ids, h + T::hit, N * 4);
+	if (const int st = *(volatile int *)(h + T::status)) {
+		if (st & 2) return fail(ctx, CMGPU_ERR_BAD_HANDLE, "CM_ClipHandleToModel: bad handle");
+		return fail(ctx, CMGPU_ERR_LIMIT, "traversal stack overflow on a BSP of %d levels", ctx->treeDepth);
+	}
+	return CMGPU_OK;
+}
+
 static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
                      const float *mins, const float *maxs, int hull_stride,
                      const int32_t *models, const int32_t *masks, int mask_stride,
@@ -1578,6 +1673,10 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	hull_stride = hull_stride ? 1 : 0;
 	mask_stride = mask_stride ? 1 : 0;
 	if (!boxmins || !boxmaxs) boxmins = boxmaxs = nullptr;
+	if (!mins) hull_stride = 0;
+	if (n <= kTinyMax && ctx->tinyCalls && ctx->tinyHost && !ctx->counting)
+		return traceHostTiny(ctx, n, starts, ends, mins, maxs, hull_stride, models, masks, mask_stride, origins, angles, boxmins, boxmaxs,
+		                     results, hit_ids);
 
 	const size_t N = (size_t)n;
 	const size_t v3 = 3 * sizeof(float);
