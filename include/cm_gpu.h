@@ -385,8 +385,9 @@ typedef struct {
 	int32_t planenum;
 } cmgpu_aas_trace_t;                 /* 36 bytes */
 
+/* areacontents: areasettings[].contents per area (AREACONTENTS_*, aasfile.h:73-89), or NULL for none */
 int cmgpu_aas_upload(cmgpu_ctx *ctx, int numplanes, const float *planes, int numnodes, const int32_t *nodes, int numareas,
-                     const int32_t *presencetypes);
+                     const int32_t *presencetypes, const int32_t *areacontents);
 /* presencetypes: one per item (presence_stride 1) or one for the batch (stride 0: a HOST pointer, also for the _device call) */
 int cmgpu_aas_trace_client_bbox_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
                                       const int32_t *presencetypes, int presence_stride, cmgpu_aas_trace_t *results);
@@ -394,6 +395,42 @@ int cmgpu_aas_trace_client_bbox_batch_device(cmgpu_ctx *ctx, int n, const float 
                                              const int32_t *presencetypes, int presence_stride, cmgpu_aas_trace_t *results, void *stream);
 int cmgpu_aas_point_area_num_batch(cmgpu_ctx *ctx, int n, const float *points, int32_t *areas);
 int cmgpu_aas_point_area_num_batch_device(cmgpu_ctx *ctx, int n, const float *points, int32_t *areas, void *stream);
+
+/* AAS_PredictClientMovement (code/botlib/be_aas_move.c:495-979), batched: one bot's movement predicted up to maxframes frames
+ * ahead -- gravity, friction, acceleration by the command, a slide along the AAS with step-ups -- until one of the events in
+ * stopevent happens (SE_*, be_aas.h:163-176; SE_HITBOUNDINGBOX tests the fixed 8-unit box of :973-974).  It is the call
+ * AAS_PredictClientMovement(&move, -1, origin, presencetype, onground, velocity, cmdmove, cmdframes, maxframes, frametime,
+ * stopevent, stopareanum, qfalse): entnum -1, i.e. no entity collisions (those are server traces).  The contents of the world
+ * (AAS_PointContents -> botimport.PointContents, be_aas_bspq3.c:138) are CM_PointContents of the clip map uploaded to the same
+ * context (0 everywhere when there is none).  moves: aas_clientmove_t records (be_aas.h:178-189), byte for byte; results: the
+ * function's return value per item (0 only when the slide loop gives up, :875), may be NULL. */
+typedef struct {
+	float phys_friction, phys_stopspeed, phys_gravity, phys_waterfriction, phys_watergravity, phys_maxwalkvelocity, phys_maxcrouchvelocity,
+	      phys_maxswimvelocity, phys_walkaccelerate, phys_airaccelerate, phys_swimaccelerate, phys_maxstep, phys_maxsteepness, phys_maxbarrier,
+	      phys_jumpvel;
+} cmgpu_aas_settings;                /* the fields of aas_settings_t (be_aas_def.h:86-104) the predictor reads */
+void cmgpu_aas_default_settings(cmgpu_aas_settings *settings);            /* AAS_InitSettings' defaults, be_aas_move.c:74-92 */
+int  cmgpu_aas_set_settings(cmgpu_ctx *ctx, const cmgpu_aas_settings *settings);
+
+typedef struct {
+	const float   *origins, *velocities, *cmdmoves;      /* [n][3] */
+	const float   *frametimes;                           /* [n] */
+	const int32_t *presencetypes, *ongrounds, *cmdframes, *maxframes, *stopevents, *stopareanums;   /* [n] */
+} cmgpu_aas_moves;
+
+typedef struct {
+	float   endpos[3];
+	int32_t endarea;
+	float   velocity[3];
+	cmgpu_aas_trace_t trace;
+	int32_t presencetype, stopevent, endcontents;
+	float   time;
+	int32_t frames;
+} cmgpu_aas_clientmove_t;            /* 84 bytes */
+
+int cmgpu_aas_predict_client_movement_batch(cmgpu_ctx *ctx, int n, const cmgpu_aas_moves *in, cmgpu_aas_clientmove_t *moves, int32_t *results);
+int cmgpu_aas_predict_client_movement_batch_device(cmgpu_ctx *ctx, int n, const cmgpu_aas_moves *in, cmgpu_aas_clientmove_t *moves,
+                                                   int32_t *results, void *stream);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus

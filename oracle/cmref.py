@@ -27,6 +27,10 @@ assert TRACE_DTYPE.itemsize == 56     # q_shared.h:976-986
 AAS_TRACE_DTYPE = np.dtype([("startsolid", "<i4"), ("fraction", "<f4"), ("endpos", "<f4", (3,)), ("ent", "<i4"),
                             ("lastarea", "<i4"), ("area", "<i4"), ("planenum", "<i4")])
 assert AAS_TRACE_DTYPE.itemsize == 36
+# aas_clientmove_t, botlib/be_aas.h:178-189
+AAS_MOVE_DTYPE = np.dtype([("endpos", "<f4", (3,)), ("endarea", "<i4"), ("velocity", "<f4", (3,)), ("trace", AAS_TRACE_DTYPE),
+                           ("presencetype", "<i4"), ("stopevent", "<i4"), ("endcontents", "<i4"), ("time", "<f4"), ("frames", "<i4")])
+assert AAS_MOVE_DTYPE.itemsize == 84
 
 
 def available() -> bool:
@@ -342,9 +346,24 @@ class RefCM:
     def aas_load(self, world):
         """world: threecore_b200.aasgen.AasWorld (planes [n,5], nodes [n,3], presence [n])"""
         planes, nodes, pres = _f(world.planes), _i(world.nodes), _i(world.presence)
+        contents = _i(getattr(world, "contents", None)) if getattr(world, "contents", None) is not None else None
         assert self.lib.aasref_sizeof_trace() == AAS_TRACE_DTYPE.itemsize
-        self._check(self.lib.aasref_load(planes.shape[0], _p(planes), nodes.shape[0], _p(nodes), pres.shape[0], _p(pres)), "aas load")
+        assert self.lib.aasref_sizeof_clientmove() == AAS_MOVE_DTYPE.itemsize
+        self._check(self.lib.aasref_load(planes.shape[0], _p(planes), nodes.shape[0], _p(nodes), pres.shape[0], _p(pres), _p(contents)),
+                    "aas load")
         return self
+
+    def aas_predict_client_movement(self, p):
+        """n x AAS_PredictClientMovement(&move, -1, ...) (be_aas_move.c:965-979); p: dict of arrays as aasgen.make_moves returns.
+        The world's contents (AAS_PointContents) come from the clip map loaded with load(), if any.  -> (moves, return values)"""
+        n = len(p["origins"])
+        moves = np.zeros(n, dtype=AAS_MOVE_DTYPE)
+        res = np.zeros(n, np.int32)
+        a = {k: (_f(v) if k in ("origins", "velocities", "cmdmoves", "frametimes") else _i(v)) for k, v in p.items()}
+        self.lib.aasref_predict_client_movement_batch(n, _p(a["origins"]), _p(a["presencetypes"]), _p(a["ongrounds"]), _p(a["velocities"]),
+                                                      _p(a["cmdmoves"]), _p(a["cmdframes"]), _p(a["maxframes"]), _p(a["frametimes"]),
+                                                      _p(a["stopevents"]), _p(a["stopareanums"]), _p(moves), _p(res))
+        return moves, res
 
     def aas_trace_client_bbox(self, starts, ends, presencetype):
         """n x AAS_TraceClientBBox(start, end, presencetype, passent = -1) (be_aas_sample.c:399-665)"""

@@ -15,8 +15,16 @@ from threecore_b200 import aasgen
 
 def _golden():
     z = np.load(os.path.join(GOLDEN, "aas_trace.npz"))
-    w = SimpleNamespace(planes=z["planes"], nodes=z["nodes"], presence=z["presence"])
+    w = SimpleNamespace(planes=z["planes"], nodes=z["nodes"], presence=z["presence"], contents=z["contents"])
     return w, z
+
+
+def _same_moves(a, b, ra, rb, what):
+    a8 = np.ascontiguousarray(a).view(np.uint8).reshape(-1, 84)
+    b8 = np.ascontiguousarray(b).view(np.uint8).reshape(-1, 84)
+    bad = (a8 != b8).any(axis=1) | (np.asarray(ra) != np.asarray(rb))
+    assert not bad.any(), (f"{what}: {int(bad.sum())} of {len(a8)} aas_clientmove_t records differ, first at {int(np.flatnonzero(bad)[0])}:\n"
+                           f" got  {a[bad][0]} ret {np.asarray(ra)[bad][0]}\n want {b[bad][0]} ret {np.asarray(rb)[bad][0]}")
 
 
 def _comb_world(n):
@@ -148,3 +156,52 @@ def test_gpu_stack_overflow_like_the_reference(eng):
     w, s, e = _comb_world(200)
     eng.aas_upload(w)
     _same(eng.aas_trace_client_bbox(s, e, 2), cmoracle.OracleAAS(w).trace_client_bbox(s, e, 2), "overflow")
+
+
+# ---- AAS_PredictClientMovement (be_aas_move.c:495-979) ------------------------------------------------------------
+def _move_world():
+    from threecore_b200 import bspgen
+    w = aasgen.make_world(n_boxes=300, seed=0xAA5003, extent=3072.0, height=768.0)
+    m = bspgen.arena_map(n_brushes=1200, seed=0xC0FFEE22, size_xy=3072.0, size_z=768.0)     # the world whose contents the predictor asks for
+    return w, m
+
+
+@pytest.mark.gpu
+def test_gpu_movement_prediction_equals_the_reference(eng):
+    """every stop event, both presence types, swimming, jumping, crouching, steps, gaps: all 84 bytes of every aas_clientmove_t
+    and the return value, against the unmodified be_aas_move.c"""
+    if not have_ref():
+        pytest.skip("oracle/_ref/libcmref.so not shipped")
+    w, m = _move_world()
+    eng.load_bsp(m.data)
+    eng.aas_upload(w)
+    r = cmref.RefCM().load(m.data)
+    r.aas_load(w)
+    n = 400000
+    p = aasgen.make_moves(w, n, 21)
+    got, gres = eng.aas_predict_client_movement(p)
+    want = cmref.fork_map(n, cmref.AAS_MOVE_DTYPE, lambda lo, hi: r.aas_predict_client_movement({k: v[lo:hi] for k, v in p.items()})[0])
+    wres = cmref.fork_map(n, np.int32, lambda lo, hi: r.aas_predict_client_movement({k: v[lo:hi] for k, v in p.items()})[1])
+    _same_moves(got, want, gres, wres, "movement prediction")
+    seen = set(np.unique(want["stopevent"]).tolist())
+    assert {0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 2048, 4096} <= seen, f"stop events exercised: {sorted(seen)}"
+    assert (wres == 0).any() and (want["endcontents"] != 0).any() and (want["frames"] > 10).any()
+
+
+@pytest.mark.gpu
+def test_gpu_movement_prediction_golden_and_device_pointers(eng):
+    import torch
+    from threecore_b200.engine import AAS_MOVE_DTYPE
+    w, z = _golden()
+    eng.load_bsp(z["bsp"].tobytes())
+    eng.aas_upload(w)
+    p = {k[3:]: z[k] for k in z.files if k.startswith("mv_")}
+    got, res = eng.aas_predict_client_movement(p)
+    _same_moves(got, z["moves"].view(AAS_MOVE_DTYPE).reshape(-1), res, z["move_results"], "golden moves")
+    dev = torch.device("cuda", 0)
+    dp = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in p.items()}
+    out = torch.empty((len(got), 84), dtype=torch.uint8, device=dev)
+    dres = torch.empty(len(got), dtype=torch.int32, device=dev)
+    eng.aas_predict_client_movement_device(dp, out, dres)
+    torch.cuda.synchronize()
+    _same_moves(out.cpu().numpy().view(AAS_MOVE_DTYPE).reshape(-1), got, dres.cpu().numpy(), res, "device pointers")

@@ -25,6 +25,7 @@ class AasWorld:
     planes: np.ndarray          # [n,5] float32: normal, dist, type
     nodes: np.ndarray           # [n,3] int32: planenum, children[0], children[1]
     presence: np.ndarray        # [numareasettings] int32 (area 0 unused)
+    contents: np.ndarray        # [numareasettings] int32 AREACONTENTS_* (aasfile.h:73-89)
     mins: np.ndarray
     maxs: np.ndarray
     stats: dict
@@ -127,8 +128,12 @@ def make_world(n_boxes=400, seed=0xAA5001, extent=4096.0, height=1024.0, leaf_de
         sys.setrecursionlimit(old)
     assert root == 1, "the root must be node 1"
     stats.update(nodes=len(nodes), planes=len(planes), areas=len(presence) - 1)
+    # a few areas are liquids, jump pads, teleporters and cluster portals: what the movement predictor's stop events look at
+    crng = np.random.default_rng(seed ^ 0xC0)
+    contents = crng.choice([0, 1, 2, 4, 8, 64, 128], size=len(presence), p=[0.82, 0.05, 0.02, 0.02, 0.03, 0.03, 0.03]).astype(np.int32)
+    contents[0] = 0
     return AasWorld(np.asarray(planes, np.float32).reshape(-1, 5), np.asarray(nodes, np.int32).reshape(-1, 3),
-                    np.asarray(presence, np.int32), lo.astype(np.float32), hi.astype(np.float32), stats)
+                    np.asarray(presence, np.int32), contents, lo.astype(np.float32), hi.astype(np.float32), stats)
 
 
 def make_lines(w: AasWorld, n, seed, length=(8.0, 1200.0), zero_frac=0.02):
@@ -144,3 +149,53 @@ def make_lines(w: AasWorld, n, seed, length=(8.0, 1200.0), zero_frac=0.02):
     z = rng.random(n) < zero_frac
     e[z] = s[z]
     return s.astype(np.float32), e.astype(np.float32)
+
+
+SE_ALL = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
+
+
+def make_moves(w: AasWorld, n, seed, maxframes=(1, 40)):
+    """inputs of n calls of AAS_PredictClientMovement (be_aas_move.c:965): where the bot is, how it moves, what the command is,
+    and which events stop the prediction -- the combinations be_ai_move.c and be_aas_reach.c use, and random ones"""
+    rng = np.random.default_rng(seed)
+    org = rng.uniform(w.mins + 32, w.maxs - 32, size=(n, 3))
+    low = rng.random(n) < 0.6                                          # most bots are near the floor
+    org[low, 2] = rng.uniform(w.mins[2] + 24, w.mins[2] + 96, size=int(low.sum()))
+    yaw = rng.uniform(0, 2 * np.pi, n)
+    speed = rng.choice([0.0, 100.0, 320.0, 400.0, 600.0], size=n)
+    vel = np.stack([np.cos(yaw) * speed, np.sin(yaw) * speed, rng.choice([0.0, -60.0, 270.0, -400.0], size=n)], 1)
+    cyaw = yaw + rng.normal(0, 0.5, n)
+    cmd = np.stack([np.cos(cyaw) * 400.0, np.sin(cyaw) * 400.0, rng.choice([0.0, 0.0, 400.0, -400.0], size=n)], 1)
+    cmd[rng.random(n) < 0.1] = 0.0
+    typical = [1 | 32 | 4 | 8 | 16 | 64, 4 | 8 | 16 | 32 | 64, 128 | 1024, 512 | 1 | 32, 1 | 2, 2048 | 1, 4096 | 256 | 1, 0]
+    stop = np.where(rng.random(n) < 0.6, rng.choice(typical, size=n),
+                    [int(sum(rng.choice(SE_ALL, size=rng.integers(1, 5), replace=False))) for _ in range(n)])
+    # make the rarer stop events reachable: some bots head for the area a few frames ahead of them (SE_ENTERAREA,
+    # SE_HITGROUNDAREA), some pass the 8-unit box around the world origin that SE_HITBOUNDINGBOX tests (be_aas_move.c:973)
+    stoparea = rng.integers(0, len(w.presence), n)
+    ahead = rng.random(n) < 0.25
+    stoparea[ahead] = point_area_num(w, (org + vel * 0.3)[ahead])
+    box = rng.random(n) < 0.05
+    org[box] = rng.uniform(-40, 40, size=(int(box.sum()), 3)) + [0, 0, 0]
+    vel[box] = -org[box] * rng.uniform(1.0, 6.0, size=(int(box.sum()), 1))
+    stop = np.asarray(stop, np.int64)
+    stop[box] |= 2048
+    return dict(origins=org.astype(np.float32), presencetypes=rng.choice([PRESENCE_NORMAL, PRESENCE_NORMAL, PRESENCE_CROUCH], size=n).astype(np.int32),
+                ongrounds=rng.integers(0, 2, n).astype(np.int32), velocities=vel.astype(np.float32), cmdmoves=cmd.astype(np.float32),
+                cmdframes=rng.integers(0, 12, n).astype(np.int32), maxframes=rng.integers(maxframes[0], maxframes[1], n).astype(np.int32),
+                frametimes=rng.choice([0.1, 0.1, 0.05, 0.0], size=n).astype(np.float32), stopevents=np.asarray(stop, np.int32),
+                stopareanums=stoparea.astype(np.int32))
+
+
+def point_area_num(w: AasWorld, pts) -> np.ndarray:
+    """AAS_PointAreaNum for generator purposes (float64 here: only used to pick interesting targets)"""
+    pts = np.asarray(pts, np.float64)
+    node = np.ones(len(pts), np.int64)
+    live = node > 0
+    while live.any():
+        nd = w.nodes[node[live]]
+        pl = w.planes[nd[:, 0]].astype(np.float64)
+        d = (pts[live] * pl[:, :3]).sum(1) - pl[:, 3]
+        node[live] = np.where(d > 0, nd[:, 1], nd[:, 2])
+        live = node > 0
+    return np.where(node < 0, -node, 0)

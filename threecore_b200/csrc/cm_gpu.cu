@@ -176,7 +176,8 @@ struct cmgpu_ctx_s {
 	bool tinyCalls = true;
 	// botlib's AAS world (cm_aas.cuh): its own tree, independent of the clip map
 	AasMap aas{};
-	DevBuf bAas;
+	AasPhysics aasPhys{6.0f, 100.0f, 800.0f, 1.0f, 400.0f, 320.0f, 100.0f, 150.0f, 10.0f, 1.0f, 4.0f, 19.0f, 0.7f, 33.0f, 270.0f};   // AAS_InitSettings, be_aas_move.c:74-92
+	DevBuf bAas, bAasIn, bAasOut;
 	bool hasAas = false;
 	// host regions pinned through this context (cmgpu_host_register, or "auto_register"): page-aligned [lo, hi)
 	std::vector<std::pair<uintptr_t, uintptr_t>> hostRegs;
@@ -1253,7 +1254,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	                  &ctx->bSvPass, &ctx->bLeafLists, &ctx->bLeafCounts, &ctx->bVis, &ctx->bFlood, &ctx->bEntRecs, &ctx->bVisible}) releaseBuf(*b);
 	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
 	if (ctx->tinyHost) cudaFreeHost(ctx->tinyHost);
-	releaseBuf(ctx->bAas);
+	releaseBuf(ctx->bAas); releaseBuf(ctx->bAasIn); releaseBuf(ctx->bAasOut);
 	for (auto &r : ctx->hostRegs) cudaHostUnregister((void *)r.first);
 	ctx->hostRegs.clear();
 	for (auto &b : ctx->bHist) releaseBuf(b);
@@ -2524,7 +2525,7 @@ int cmgpu_measure_l2_read(cmgpu_ctx *ctx, size_t bytes, int passes, double *gbs)
 extern "C" {
 
 int cmgpu_aas_upload(cmgpu_ctx *ctx, int numplanes, const float *planes, int numnodes, const int32_t *nodes, int numareas,
-                     const int32_t *presencetypes) {
+                     const int32_t *presencetypes, const int32_t *areacontents) {
 	if (!ctx) return CMGPU_ERR_INVALID;
 	if (numplanes < 2 || !planes || numnodes < 2 || !nodes || numareas < 1 || !presencetypes)
 		return fail(ctx, CMGPU_ERR_BAD_MAP, "cmgpu_aas_upload: an AAS world has planes, a dummy node 0 and a root node 1, and a dummy area 0");
@@ -2561,7 +2562,8 @@ int cmgpu_aas_upload(cmgpu_ctx *ctx, int numplanes, const float *planes, int num
 		nodePlane[i] = pl[(size_t)nodes[3 * i]];
 		nodeInfo[i] = make_int4(nodes[3 * i], nodes[3 * i + 1], nodes[3 * i + 2], 0);
 	}
-	const size_t offInfo = nNodes * 16, offPlanes = offInfo + nNodes * 16, offPres = offPlanes + nPlanes * 16, total = offPres + nAreas * 4;
+	const size_t offInfo = nNodes * 16, offPlanes = offInfo + nNodes * 16, offPres = offPlanes + nPlanes * 16, offCont = offPres + nAreas * 4,
+	             total = offCont + nAreas * 4;
 	ctx->hasAas = false;
 	int rc = reserve(ctx, ctx->bAas, total);
 	if (rc) return rc;
@@ -2570,10 +2572,13 @@ int cmgpu_aas_upload(cmgpu_ctx *ctx, int numplanes, const float *planes, int num
 	CUDA_TRY(ctx, cudaMemcpy(base + offInfo, nodeInfo.data(), nNodes * 16, cudaMemcpyHostToDevice));
 	CUDA_TRY(ctx, cudaMemcpy(base + offPlanes, pl.data(), nPlanes * 16, cudaMemcpyHostToDevice));
 	CUDA_TRY(ctx, cudaMemcpy(base + offPres, presencetypes, nAreas * 4, cudaMemcpyHostToDevice));
+	if (areacontents) CUDA_TRY(ctx, cudaMemcpy(base + offCont, areacontents, nAreas * 4, cudaMemcpyHostToDevice));
+	else CUDA_TRY(ctx, cudaMemset(base + offCont, 0, nAreas * 4));
 	ctx->aas.nodePlane = (const float4 *)base;
 	ctx->aas.nodeInfo = (const int4 *)(base + offInfo);
 	ctx->aas.planes = (const float4 *)(base + offPlanes);
 	ctx->aas.presence = (const int *)(base + offPres);
+	ctx->aas.areaContents = (const int *)(base + offCont);
 	ctx->aas.numNodes = numnodes; ctx->aas.numPlanes = numplanes; ctx->aas.numAreas = numareas;
 	ctx->hasAas = true;
 	return CMGPU_OK;
@@ -2651,6 +2656,89 @@ int cmgpu_aas_point_area_num_batch(cmgpu_ctx *ctx, int n, const float *points, i
 	rc = cmgpu_aas_point_area_num_batch_device(ctx, n, (const float *)ctx->bStarts.p, (int32_t *)ctx->bHit.p, s);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(areas, ctx->bHit.p, N * 4, cudaMemcpyDeviceToHost, s));
+	CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	return CMGPU_OK;
+}
+
+void cmgpu_aas_default_settings(cmgpu_aas_settings *st) {          // AAS_InitSettings, be_aas_move.c:74-92 (the libvars' defaults)
+	if (!st) return;
+	const cmgpu_aas_settings d = {6.0f, 100.0f, 800.0f, 1.0f, 400.0f, 320.0f, 100.0f, 150.0f, 10.0f, 1.0f, 4.0f, 19.0f, 0.7f, 33.0f, 270.0f};
+	*st = d;
+}
+
+int cmgpu_aas_set_settings(cmgpu_ctx *ctx, const cmgpu_aas_settings *st) {
+	if (!ctx || !st) return CMGPU_ERR_INVALID;
+	static_assert(sizeof(cmgpu_aas_settings) == sizeof(AasPhysics), "the two are the same fifteen floats");
+	memcpy(&ctx->aasPhys, st, sizeof(AasPhysics));
+	return CMGPU_OK;
+}
+
+int cmgpu_aas_predict_client_movement_batch_device(cmgpu_ctx *ctx, int n, const cmgpu_aas_moves *in, cmgpu_aas_clientmove_t *moves,
+                                                   int32_t *results, void *stream) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || !in || (n > 0 && (!in->origins || !in->velocities || !in->cmdmoves || !in->frametimes || !in->presencetypes || !in->ongrounds ||
+	                               !in->cmdframes || !in->maxframes || !in->stopevents || !in->stopareanums || !moves)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_aas_predict_client_movement_batch_device: bad argument");
+	if (!ctx->hasAas) return fail(ctx, CMGPU_ERR_NO_MAP, "no AAS world uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	AasMoveBatch q{};
+	q.n = n;
+	q.origins = in->origins; q.velocities = in->velocities; q.cmdmoves = in->cmdmoves; q.frametimes = in->frametimes;
+	q.presencetypes = in->presencetypes; q.ongrounds = in->ongrounds; q.cmdframes = in->cmdframes; q.maxframes = in->maxframes;
+	q.stopevents = in->stopevents; q.stopareanums = in->stopareanums;
+	q.out = reinterpret_cast<int *>(moves);
+	q.results = results;
+	ctx->map.noCurves = ctx->noCurves;
+	ctx->map.playerCurveClip = ctx->playerCurveClip;
+	// the world's contents (AAS_PointContents) come from the clip map of this context, when one is uploaded
+	aasPredictClientMovementKernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ctx->aas, ctx->map, ctx->hasMap ? 1 : 0, ctx->aasPhys, q);
+	ctx->launches++;
+	CUDA_TRY(ctx, cudaGetLastError());
+	return CMGPU_OK;
+}
+
+int cmgpu_aas_predict_client_movement_batch(cmgpu_ctx *ctx, int n, const cmgpu_aas_moves *in, cmgpu_aas_clientmove_t *moves, int32_t *results) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (n < 0 || !in || (n > 0 && (!in->origins || !in->velocities || !in->cmdmoves || !in->frametimes || !in->presencetypes || !in->ongrounds ||
+	                               !in->cmdframes || !in->maxframes || !in->stopevents || !in->stopareanums || !moves)))
+		return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_aas_predict_client_movement_batch: bad argument");
+	if (!ctx->hasAas) return fail(ctx, CMGPU_ERR_NO_MAP, "no AAS world uploaded");
+	if (n == 0) return CMGPU_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t)n;
+	// one staging block: three [n][3] float arrays, then seven [n] arrays of 4-byte values
+	const size_t bytesIn = N * (3 * 12 + 7 * 4);
+	int rc;
+	if ((rc = reserve(ctx, ctx->bAasIn, bytesIn))) return rc;
+	if ((rc = reserve(ctx, ctx->bAasOut, N * (sizeof(cmgpu_aas_clientmove_t) + 4)))) return rc;
+	cudaStream_t s = ctx->streams[0];
+	char *d = (char *)ctx->bAasIn.p;
+	cmgpu_aas_moves dv{};
+	size_t off = 0;
+	auto put = [&](const void *src, size_t bytes) -> const void * {
+		const void *at = d + off;
+		if (cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) rc = CMGPU_ERR_CUDA;
+		off += bytes;
+		return at;
+	};
+	dv.origins = (const float *)put(in->origins, N * 12);
+	dv.velocities = (const float *)put(in->velocities, N * 12);
+	dv.cmdmoves = (const float *)put(in->cmdmoves, N * 12);
+	dv.frametimes = (const float *)put(in->frametimes, N * 4);
+	dv.presencetypes = (const int32_t *)put(in->presencetypes, N * 4);
+	dv.ongrounds = (const int32_t *)put(in->ongrounds, N * 4);
+	dv.cmdframes = (const int32_t *)put(in->cmdframes, N * 4);
+	dv.maxframes = (const int32_t *)put(in->maxframes, N * 4);
+	dv.stopevents = (const int32_t *)put(in->stopevents, N * 4);
+	dv.stopareanums = (const int32_t *)put(in->stopareanums, N * 4);
+	if (rc) return fail(ctx, CMGPU_ERR_CUDA, "cudaMemcpyAsync (AAS moves): %s", cudaGetErrorString(cudaGetLastError()));
+	cmgpu_aas_clientmove_t *dMoves = (cmgpu_aas_clientmove_t *)ctx->bAasOut.p;
+	int32_t *dRes = (int32_t *)((char *)ctx->bAasOut.p + N * sizeof(cmgpu_aas_clientmove_t));
+	rc = cmgpu_aas_predict_client_movement_batch_device(ctx, n, &dv, dMoves, dRes, s);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(moves, dMoves, N * sizeof(cmgpu_aas_clientmove_t), cudaMemcpyDeviceToHost, s));
+	if (results) CUDA_TRY(ctx, cudaMemcpyAsync(results, dRes, N * 4, cudaMemcpyDeviceToHost, s));
 	CUDA_TRY(ctx, cudaStreamSynchronize(s));
 	return CMGPU_OK;
 }

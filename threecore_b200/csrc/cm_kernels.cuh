@@ -1300,6 +1300,40 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 }
 
 // ---- CM_PointContents / CM_TransformedPointContents, cm_test.c:217-294 -----------------------------
+// CM_PointContents(p, 0) (cm_test.c:217-264) for one point of the world, as a device function: what botlib's
+// AAS_PointContents resolves to on a server without entities in the way (be_aas_bspq3.c:138, sv_bot.c BotImport_PointContents)
+__device__ __forceinline__ int pointContentsWorld(const DevMap &m, const float px, const float py, const float pz) {
+	int num = 0;
+	while (num >= 0) {                                           // CM_PointLeafnum_r, cm_test.c:31-54
+		const int4 nd = __ldg(&m.nodes[num]);
+		float d;
+		if (nd.z < 3) {
+			d = sel3(px, py, pz, nd.z) - __int_as_float(nd.w);
+		} else {
+			const float4 pl = __ldg(&m.nodePlanes[num]);
+			d = dotf(pl.x, pl.y, pl.z, px, py, pz) - pl.w;
+		}
+		num = (d < 0) ? nd.y : nd.x;
+	}
+	const int4 leaf = __ldg(&m.leafs[-1 - num]);
+	int contents = 0;
+	for (int k = 0; k < leaf.y; k++) {
+		const Pair4 bb = ldg32(&m.leafBrushBox[2 * (leaf.x + k)]);
+		const float4 bmn = bb.a, bmx = bb.b;
+		const int b = __float_as_int(bmx.w);
+		if (bmx.x < px - kBoundsEps || bmx.y < py - kBoundsEps || bmx.z < pz - kBoundsEps ||
+		    bmn.x > px + kBoundsEps || bmn.y > py + kBoundsEps || bmn.z > pz + kBoundsEps) continue;
+		const int4 bi = __ldg(&m.brushInfo[b]);
+		int s;
+		for (s = 0; s < bi.y; s++) {
+			const float4 pl = __ldg(&m.sidePlanes[bi.x + s]);
+			if (dotf(px, py, pz, pl.x, pl.y, pl.z) > pl.w) break;
+		}
+		if (s == bi.y) contents |= __float_as_int(bmn.w);
+	}
+	return contents;
+}
+
 __global__ void __launch_bounds__(128) pointContentsKernel(const DevMap m, const PointBatch q) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= q.n) return;

@@ -99,6 +99,16 @@ assert SV_ENTITY_DTYPE.itemsize == 92
 # aas_trace_t (botlib/be_aas.h:84-93) == cmgpu_aas_trace_t
 AAS_TRACE_DTYPE = np.dtype([("startsolid", "<i4"), ("fraction", "<f4"), ("endpos", "<f4", (3,)), ("ent", "<i4"),
                             ("lastarea", "<i4"), ("area", "<i4"), ("planenum", "<i4")])
+# aas_clientmove_t (botlib/be_aas.h:178-189) == cmgpu_aas_clientmove_t
+AAS_MOVE_DTYPE = np.dtype([("endpos", "<f4", (3,)), ("endarea", "<i4"), ("velocity", "<f4", (3,)), ("trace", AAS_TRACE_DTYPE),
+                           ("presencetype", "<i4"), ("stopevent", "<i4"), ("endcontents", "<i4"), ("time", "<f4"), ("frames", "<i4")])
+
+
+class _AasMoves(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("origins", "velocities", "cmdmoves", "frametimes", "presencetypes", "ongrounds", "cmdframes",
+                                          "maxframes", "stopevents", "stopareanums")]
+
+
 ENT_CLUSTERS_DTYPE = np.dtype([("numLeafs", "<i4"), ("areanum", "<i4"), ("areanum2", "<i4"), ("numClusters", "<i4"),
                                ("lastCluster", "<i4"), ("clusternums", "<i4", (16,))])
 assert ENT_CLUSTERS_DTYPE.itemsize == 84
@@ -135,7 +145,12 @@ def load_library() -> C.CDLL:
     lib.cmgpu_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_ipc_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
-    lib.cmgpu_aas_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.cmgpu_aas_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cmgpu_aas_predict_client_movement_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_AasMoves), C.c_void_p, C.c_void_p]
+    lib.cmgpu_aas_predict_client_movement_batch_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(_AasMoves), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cmgpu_aas_set_settings.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cmgpu_aas_default_settings.argtypes = [C.c_void_p]
+    lib.cmgpu_aas_default_settings.restype = None
     lib.cmgpu_aas_trace_client_bbox_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.cmgpu_aas_trace_client_bbox_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.cmgpu_aas_point_area_num_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -529,7 +544,31 @@ class Engine:
     def aas_upload(self, world):
         """world: planes [n,5] float32, nodes [n,3] int32, presence [numareas] int32 (aasgen.AasWorld or the like)"""
         planes, nodes, pres = _f(world.planes), _i(world.nodes), _i(world.presence)
-        self._check(self.lib.cmgpu_aas_upload(self.h, planes.shape[0], _p(planes), nodes.shape[0], _p(nodes), pres.shape[0], _p(pres)))
+        cont = getattr(world, "contents", None)
+        cont = _i(cont) if cont is not None else None
+        self._check(self.lib.cmgpu_aas_upload(self.h, planes.shape[0], _p(planes), nodes.shape[0], _p(nodes), pres.shape[0], _p(pres), _p(cont)))
+
+    AAS_MOVE_KEYS = ("origins", "velocities", "cmdmoves", "frametimes", "presencetypes", "ongrounds", "cmdframes", "maxframes",
+                     "stopevents", "stopareanums")
+
+    def aas_predict_client_movement(self, p):
+        """n x AAS_PredictClientMovement(&move, -1, ...) on host arrays; p: dict with AAS_MOVE_KEYS -> (aas_clientmove_t records, return values)"""
+        a = {k: (_f(p[k]) if k in ("origins", "velocities", "cmdmoves", "frametimes") else _i(p[k])) for k in self.AAS_MOVE_KEYS}
+        n = a["origins"].shape[0]
+        m = _AasMoves(*[a[k].ctypes.data for k in self.AAS_MOVE_KEYS])
+        moves = np.zeros(n, dtype=AAS_MOVE_DTYPE)
+        res = np.zeros(n, np.int32)
+        self._check(self.lib.cmgpu_aas_predict_client_movement_batch(self.h, n, C.byref(m), _p(moves), _p(res)))
+        return moves, res
+
+    def aas_predict_client_movement_device(self, p, moves, results=None, stream=None):
+        """p: dict of CUDA tensors with AAS_MOVE_KEYS; moves: uint8 [n,84]; results: int32 [n] or None"""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(moves.device).cuda_stream
+        m = _AasMoves(*[p[k].data_ptr() for k in self.AAS_MOVE_KEYS])
+        self._check(self.lib.cmgpu_aas_predict_client_movement_batch_device(self.h, p["origins"].shape[0], C.byref(m), moves.data_ptr(),
+                                                                           None if results is None else results.data_ptr(), C.c_void_p(stream)))
 
     def aas_trace_client_bbox(self, starts, ends, presencetype) -> np.ndarray:
         """n x AAS_TraceClientBBox(start, end, presencetype, -1) on host arrays -> aas_trace_t records"""
