@@ -387,6 +387,101 @@ def arm_rollout(local, dev, world, rank, ticks=40):
             "limiter": "a tick is eight DEPENDENT trace launches; each waits for its slowest walk"}
 
 
+def arm_other_configs(local, dev):
+    """The other BASELINE configs and the botlib tracer on the driver's record (rank 0, one GPU): resident throughput, each
+    with a sample of its records compared with the reference (oracle/_ref) when that library was shipped."""
+    import torch
+    from oracle import cmref
+    from threecore_b200 import aasgen
+    from threecore_b200.engine import Engine, rotation_matrices
+    have = cmref.available()
+    e2 = Engine(local)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    res = {}
+
+    def timed(fn, n, reps=5):
+        for _ in range(2):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        e2.check_status()
+        ms = a.elapsed_time(b) / reps
+        return {"value": n / ms / 1e3, "unit": "M items/s", "ms": ms, "items": n}
+
+    def sample_equal(got_u8, want):
+        return bool(np.array_equal(got_u8, np.ascontiguousarray(want).view(np.uint8).reshape(got_u8.shape)))
+    try:
+        idx = np.arange(0, 1 << 20, 16)
+        # config 1: 1 Mi point traces, 500-brush room
+        m = bspgen.room_map(n_brushes=500, seed=0xC0FFEE01)
+        e2.load_bsp(m.data)
+        n = 1 << 20
+        s, e = bspgen.make_point_sweeps(m, n, 0xBADC0DE1)
+        ds, de, out = T(s), T(e), torch.empty((n, 56), dtype=torch.uint8, device=dev)
+        res["config1_point_traces"] = timed(lambda: e2.box_trace_device(ds, de, None, None, bspgen.MASK_SOLID, out), n)
+        if have:
+            res["config1_point_traces"]["sample_equals_reference"] = sample_equal(
+                out.cpu().numpy()[idx], cmref.RefCM().load(m.data).box_trace(s[idx], e[idx], None, None, mask=bspgen.MASK_SOLID))
+        # config 3: 4 Mi point + hull traces, 2k brushes + 512 Bezier patches
+        m = bspgen.patch_map(n_brushes=2000, n_patches=512, seed=0xC0FFEE03)
+        e2.load_bsp(m.data)
+        n = 1 << 22
+        s, e, mins, maxs = bspgen.make_patch_sweeps(m, n, 0xBADC0DE3)
+        ds, de, dmn, dmx, out = T(s), T(e), T(mins), T(maxs), torch.empty((n, 56), dtype=torch.uint8, device=dev)
+        res["config3_patches"] = timed(lambda: e2.box_trace_device(ds, de, dmn, dmx, bspgen.MASK_ALL, out), n)
+        if have:
+            res["config3_patches"]["sample_equals_reference"] = sample_equal(
+                out.cpu().numpy()[idx], cmref.RefCM().load(m.data).box_trace(s[idx], e[idx], mins[idx], maxs[idx], mask=bspgen.MASK_ALL))
+        # config 4: transformed traces against 256 inline models, point contents
+        m = bspgen.arena_map(n_brushes=N_BRUSHES, seed=MAP_SEED, n_models=256)
+        e2.load_bsp(m.data)
+        t = bspgen.make_entity_traces(m, n, 0xBADC0DE4)
+        rot, ridx = rotation_matrices(t["angles"])
+        d = {k: T(v) for k, v in t.items() if k != "angles"}
+        drot, dridx = T(rot), T(ridx)
+        res["config4_transformed_traces"] = timed(lambda: e2.box_trace_device(
+            d["starts"], d["ends"], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_ALL, out, models=d["models"], origins=d["origins"],
+            rotations=drot, rot_index=dridx, boxmins=d["boxmins"], boxmaxs=d["boxmaxs"]), n)
+        if have:
+            r = cmref.RefCM().load(m.data)
+            res["config4_transformed_traces"]["sample_equals_reference"] = sample_equal(out.cpu().numpy()[idx], r.transformed_box_trace(
+                t["starts"][idx], t["ends"][idx], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, t["models"][idx], bspgen.MASK_ALL, t["origins"][idx],
+                t["angles"][idx], t["boxmins"][idx], t["boxmaxs"][idx]))
+        npts = 1 << 24
+        pts = bspgen.make_points(m, npts, 0xBADC0DE5)
+        dp, pc = T(pts), torch.empty(npts, dtype=torch.int32, device=dev)
+        res["config4_point_contents"] = timed(lambda: e2.point_contents_device(dp, pc), npts)
+        if have:
+            res["config4_point_contents"]["sample_equals_reference"] = bool(np.array_equal(pc.cpu().numpy()[idx], r.point_contents(pts[idx])))
+        del ds, de, dmn, dmx, out, dp, pc, d
+        # botlib: AAS_TraceClientBBox and AAS_PredictClientMovement (SURVEY 8f rank 4) on a generated AAS world
+        w = aasgen.make_world(n_boxes=2000, seed=0xAA5004, extent=8192.0, height=1024.0)
+        e2.aas_upload(w)
+        n = 1 << 24
+        s, e = aasgen.make_lines(w, n, 11)
+        ds, de, out = T(s), T(e), torch.empty((n, 36), dtype=torch.uint8, device=dev)
+        res["aas_trace_client_bbox"] = timed(lambda: e2.aas_trace_client_bbox_device(ds, de, aasgen.PRESENCE_NORMAL, out), n)
+        nm = 1 << 20
+        p = aasgen.make_moves(w, nm, 13)
+        dpm = {k: T(v) for k, v in p.items()}
+        mo = torch.empty((nm, 84), dtype=torch.uint8, device=dev)
+        res["aas_predict_client_movement"] = timed(lambda: e2.aas_predict_client_movement_device(dpm, mo), nm, reps=3)
+        if have:
+            r.aas_load(w)
+            res["aas_trace_client_bbox"]["sample_equals_reference"] = sample_equal(
+                out.cpu().numpy()[idx], r.aas_trace_client_bbox(s[idx], e[idx], aasgen.PRESENCE_NORMAL))
+            k = idx[:16384]
+            res["aas_predict_client_movement"]["sample_equals_reference"] = sample_equal(
+                mo.cpu().numpy()[k], r.aas_predict_client_movement({kk: v[k] for kk, v in p.items()})[0])
+    finally:
+        e2.close()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -506,6 +601,8 @@ def run_ours(args):
             attempt("gathered", lambda: arm_gathered(eng, dev, world, rank, n, d_starts, d_ends, d_out, max(2, min(args.steps, 5))))
         attempt("strong", lambda: arm_strong(eng, dev, world, rank, n, starts, ends, d_out, max(2, min(args.steps, 5))))
         attempt("rollout", lambda: arm_rollout(local, dev, world, rank))
+        if world == 1:
+            attempt("other_configs", lambda: arm_other_configs(local, dev))
 
     # ---- L2 working-set roofline: visit counts of this very batch from the counting kernel variant (untimed),
     # priced with the reference's own record sizes, against an L2-resident copy measured here
@@ -577,7 +674,7 @@ def run_ours(args):
                                                if (extra.get("host_copy") or {}).get("copy_bound_mtraces") else None),
                         "host_copy": extra.get("host_copy")},
                 "e2e_pageable": extra.get("e2e_pageable"), "gathered": extra.get("gathered"), "strong": extra.get("strong"),
-                "rollout": extra.get("rollout"),
+                "rollout": extra.get("rollout"), "other_configs": extra.get("other_configs"),
                 "gpu_launches": int(launches), "clocks": clocks, "hit_fraction": hits}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, kind, secs = cpu_reference_run(m.data, starts, ends, min(args.ref_sample, n))
