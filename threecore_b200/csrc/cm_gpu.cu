@@ -110,7 +110,7 @@ struct cmgpu_ctx_s {
 	int gangBrush = 5;                   // pool kernel: eighths of the most popular kind's lane count that must wait for a brush clip ...
 	int gangFetchPool = 6;               // ... and for the fetch step, before it runs (measured: +0.7 % over 4 / 4)
 	int lightReps = 3;
-	int facetSteps = kFacetPlaneSteps;
+	int facetSteps = 8;                  // lanes that must have reached a patch before the warp takes the patches together (counting variant: planes per round)
 	// spatial binning of large batches (counting sort by start cell)
 	BinGrid grid{};
 	bool binning = true;
@@ -440,6 +440,7 @@ int validate(cmgpu_ctx *ctx, const cmgpu_flatmap *f, int *treeLevels) {
 		const int32_t *p = f->patches + 6 * (size_t)i;
 		NEED(p[2] >= 0 && p[3] >= 0 && (long long)p[2] + p[3] <= f->numPatchPlanes, "patch %d: bad plane range", i);
 		NEED(p[4] >= 0 && p[5] >= 0 && (long long)p[4] + p[5] <= f->numFacets, "patch %d: bad facet range", i);
+		NEED(p[5] <= 65535, "patch %d: %d facets (the reference stops at MAX_FACETS = 1024, cm_patch.h:23; the kernels index a patch's facets with 16 bits)", i, p[5]);
 		for (int k = 0; k < p[5]; k++) {
 			const int32_t *fc = f->facets + 3 * (size_t)(p[4] + k);
 			NEED(fc[0] >= 0 && fc[0] < p[3], "patch %d facet %d: bad surface plane", i, k);

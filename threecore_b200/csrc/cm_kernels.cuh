@@ -483,6 +483,7 @@ __device__ __forceinline__ float rcpApproxFtz(float x) {
 	return r;
 }
 
+constexpr int pgMaxFacetsPerPatch = 1024;   // MAX_FACETS, cm_patch.h:23
 struct FacetBox { bool ok; float enter; int which; };
 
 // Do the axial border planes of the facet (or of every facet of the chunk) alone reject the sweep?  Two ways:
@@ -567,78 +568,125 @@ __device__ __forceinline__ FacetPoint facetPointWhole(const DevMap &m, const Lan
 	return r;
 }
 
-// The warp clips the sweep of lane `owner` (in M_FACET: L.side .. L.sideEnd are the patch's facets) against the patch.
+__device__ __forceinline__ void broadcastSweep(Lane &T, const Lane &L, const int src) {
+	const unsigned full = 0xffffffffu;
+	T.sx = __shfl_sync(full, L.sx, src); T.sy = __shfl_sync(full, L.sy, src); T.sz = __shfl_sync(full, L.sz, src);
+	T.ex = __shfl_sync(full, L.ex, src); T.ey = __shfl_sync(full, L.ey, src); T.ez = __shfl_sync(full, L.ez, src);
+	T.n0x = __shfl_sync(full, L.n0x, src); T.n0y = __shfl_sync(full, L.n0y, src); T.n0z = __shfl_sync(full, L.n0z, src);
+	T.p0x = __shfl_sync(full, L.p0x, src); T.p0y = __shfl_sync(full, L.p0y, src); T.p0z = __shfl_sync(full, L.p0z, src);
+}
+
+// The warp clips the POINT sweep of lane `owner` (in M_FACET: L.side .. L.sideEnd are the patch's facets) against the patch.
 // Every lane calls this; only the owner's L is changed (fraction and clip plane).
-__device__ __forceinline__ void patchByWarp(const DevMap &m, Lane &L, const int owner, const unsigned lane) {
+__device__ __forceinline__ void patchPointByWarp(const DevMap &m, Lane &L, const int owner, const unsigned lane) {
 	const unsigned full = 0xffffffffu;
 	Lane T;
-	T.sx = __shfl_sync(full, L.sx, owner); T.sy = __shfl_sync(full, L.sy, owner); T.sz = __shfl_sync(full, L.sz, owner);
-	T.ex = __shfl_sync(full, L.ex, owner); T.ey = __shfl_sync(full, L.ey, owner); T.ez = __shfl_sync(full, L.ez, owner);
-	T.n0x = __shfl_sync(full, L.n0x, owner); T.n0y = __shfl_sync(full, L.n0y, owner); T.n0z = __shfl_sync(full, L.n0z, owner);
-	T.p0x = __shfl_sync(full, L.p0x, owner); T.p0y = __shfl_sync(full, L.p0y, owner); T.p0z = __shfl_sync(full, L.p0z, owner);
+	broadcastSweep(T, L, owner);
 	const int first = __shfl_sync(full, L.side, owner), end = __shfl_sync(full, L.sideEnd, owner);
-	const int firstChunk = __shfl_sync(full, L.firstSide, owner);     // set when the item entered the patch (M_PATCH)
-	const bool point = (__shfl_sync(full, L.flags, owner) & F_POINT) != 0;
 	float cur = __shfl_sync(full, L.fraction, owner);
-	bool any = false;
-	float4 best = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	if (point) {
-		int bestFacet = -1;
-		for (int base = first; base < end; base += 32) {
-			const int f = base + (int)lane;
-			FacetPoint r;
-			r.pass = false; r.t = 0.0f; r.fraction = 0.0f;
-			if (f < end) r = facetPointWhole(m, T, f, cur);
-			unsigned cand = __ballot_sync(full, r.pass);
-			while (cand) {                                        // the survivors in facet order (cm_patch.c:1271)
-				const int w = __ffs((int)cand) - 1;
-				cand &= cand - 1u;
-				const float tw = __shfl_sync(full, r.t, w), fw = __shfl_sync(full, r.fraction, w);
-				if (!(tw > cur)) { cur = fw; bestFacet = base + w; }
+	int bestFacet = -1;
+	for (int base = first; base < end; base += 32) {
+		const int f = base + (int)lane;
+		FacetPoint r;
+		r.pass = false; r.t = 0.0f; r.fraction = 0.0f;
+		if (f < end) r = facetPointWhole(m, T, f, cur);
+		unsigned cand = __ballot_sync(full, r.pass);
+		while (cand) {                                        // the survivors in facet order (cm_patch.c:1271)
+			const int w = __ffs((int)cand) - 1;
+			cand &= cand - 1u;
+			const float tw = __shfl_sync(full, r.t, w), fw = __shfl_sync(full, r.fraction, w);
+			if (!(tw > cur)) { cur = fw; bestFacet = base + w; }
+		}
+	}
+	if (bestFacet >= 0 && lane == (unsigned)owner) {
+		const float4 sp = __ldg(&m.facetPlanes[__ldg(&m.facetRuns[bestFacet]).x]);
+		L.fraction = cur;
+		L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;       // type/signbits stay stale (cm_patch.c:1309-1310)
+	}
+}
+
+// The warp clips the BOX sweeps of all lanes in `owners` against the patches they have reached.
+//  Pass 1, owner by owner: the owner's sweep is broadcast and every lane pre-tests a facet of its own (the chunk's and the
+//    facet's axial borders, axialBordersReject); the survivors -- a handful out of hundreds -- are queued as (owner, facet),
+//    owners in lane order, facets in facet order.
+//  Pass 2, 32 queue entries at a time, whatever owners they belong to: each lane fetches ITS owner's sweep (shuffles with a
+//    per-lane source), walks its facet's planes (facetBoxWhole), and the results are merged owner by owner against the
+//    owner's running fraction: smallest enterFrac, lowest queue position among equals -- the first facet in the reference's
+//    order, because an owner's entries are queued in that order and batches are taken in order.
+// Walking survivors of several owners together is what fills the warp: one owner rarely has more than a few.
+constexpr int kPatchQueue = 256;
+__device__ __forceinline__ void patchBoxesByWarp(const DevMap &m, Lane &L, unsigned owners, const unsigned lane) {
+	const unsigned full = 0xffffffffu;
+	const unsigned laneLt = (1u << lane) - 1u;
+	__shared__ unsigned queue[kBlock / 32][kPatchQueue];
+	unsigned *const sq = queue[threadIdx.x >> 5];
+	int count = 0;
+
+	auto flush = [&]() {
+		__syncwarp();
+		for (int base = 0; base < count; base += 32) {
+			const int k = base + (int)lane;
+			const bool valid = k < count;
+			const unsigned entry = valid ? sq[k] : 0u;
+			const int myOwner = valid ? (int)(entry >> 16) : (int)lane;
+			Lane T;
+			broadcastSweep(T, L, myOwner);
+			const int first = __shfl_sync(full, L.side, myOwner);
+			FacetBox r;
+			r.ok = false; r.enter = -1.0f; r.which = -2;
+			if (valid) r = facetBoxWhole(m, T, first + (int)(entry & 0xffffu));
+			unsigned remaining = __ballot_sync(full, valid && r.ok);
+			while (remaining) {
+				const int o = __shfl_sync(full, myOwner, __ffs((int)remaining) - 1);
+				const float cur = __shfl_sync(full, L.fraction, o);
+				const bool mine = valid && r.ok && myOwner == o;
+				remaining &= ~__ballot_sync(full, mine);
+				// enter is >= 0 here (or -0.0, which orders like +0.0: strict `<` lets the first facet keep a tie)
+				const unsigned key = (mine && r.enter < cur) ? (__float_as_uint(r.enter) & 0x7fffffffu) : 0xffffffffu;
+				const unsigned mn = __reduce_min_sync(full, key);
+				if (mn != 0xffffffffu) {
+					const int w = __ffs((int)__ballot_sync(full, key == mn)) - 1;
+					float4 pl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+					if ((int)lane == w) pl = facetClipPlane(m, T, r.which);   // same float ops, same plane (T still holds this facet's run)
+					const float e = __shfl_sync(full, r.enter, w);
+					const float bx = __shfl_sync(full, pl.x, w), by = __shfl_sync(full, pl.y, w), bz = __shfl_sync(full, pl.z, w), bw = __shfl_sync(full, pl.w, w);
+					if ((int)lane == o) { L.fraction = e; L.pnx = bx; L.pny = by; L.pnz = bz; L.pd = bw; }
+				}
 			}
 		}
-		if (bestFacet >= 0 && lane == (unsigned)owner) {
-			const float4 sp = __ldg(&m.facetPlanes[__ldg(&m.facetRuns[bestFacet]).x]);
-			L.fraction = cur;
-			L.pnx = sp.x; L.pny = sp.y; L.pnz = sp.z; L.pd = sp.w;       // type/signbits stay stale (cm_patch.c:1309-1310)
+		__syncwarp();
+		count = 0;
+	};
+
+	while (owners) {
+		const int owner = __ffs((int)owners) - 1;
+		owners &= owners - 1u;
+		Lane T;
+		broadcastSweep(T, L, owner);
+		const int first = __shfl_sync(full, L.side, owner), end = __shfl_sync(full, L.sideEnd, owner);
+		const int firstChunk = __shfl_sync(full, L.firstSide, owner);     // set when the item entered the patch (M_PATCH)
+		// the axial pre-tests need the reference's |offset| to be the same number for both halves of the hull
+		const bool cull = T.n0x == -T.p0x && T.n0y == -T.p0y && T.n0z == -T.p0z;
+		unsigned chunks = 0xffffffffu;                                    // passes that cannot be skipped
+		const bool chunkCull = cull && end - first <= 1024;               // one chunk per lane (MAX_FACETS is 1024, cm_patch.h:23)
+		if (chunkCull) {
+			const int c = firstChunk + (int)lane;
+			bool live = false;
+			if (first + 32 * (int)lane < end) live = !axialBordersReject(__ldg(&m.facetChunkAxial[2 * c]), __ldg(&m.facetChunkAxial[2 * c + 1]), T, false);
+			chunks = __ballot_sync(full, live);
 		}
-		return;
-	}
-	// the axial pre-tests need the reference's |offset| to be the same number for both halves of the hull
-	const bool cull = T.n0x == -T.p0x && T.n0y == -T.p0y && T.n0z == -T.p0z;
-	unsigned chunks = 0xffffffffu;                                    // passes that cannot be skipped
-	const bool chunkCull = cull && end - first <= 1024;               // one chunk per lane (MAX_FACETS is 1024, cm_patch.h:23)
-	if (chunkCull) {
-		const int c = firstChunk + (int)lane;
-		bool live = false;
-		if (first + 32 * (int)lane < end) live = !axialBordersReject(__ldg(&m.facetChunkAxial[2 * c]), __ldg(&m.facetChunkAxial[2 * c + 1]), T, false);
-		chunks = __ballot_sync(full, live);
-	}
-	for (int base = first, ci = 0; base < end; base += 32, ci++) {
-		if (chunkCull && !((chunks >> ci) & 1u)) continue;
-		const int f = base + (int)lane;
-		FacetBox r;
-		r.ok = false; r.enter = -1.0f; r.which = -2;
-		if (f < end && !(cull && axialBordersReject(__ldg(&m.facetAxial[2 * f]), __ldg(&m.facetAxial[2 * f + 1]), T, true)))
-			r = facetBoxWhole(m, T, f);
-		const bool accept = r.ok && r.enter < cur;
-		// enter is >= 0 here (or -0.0, which orders like +0.0: strict `<` lets the first facet keep a tie)
-		const unsigned key = accept ? (__float_as_uint(r.enter) & 0x7fffffffu) : 0xffffffffu;
-		const unsigned mn = __reduce_min_sync(full, key);
-		if (mn != 0xffffffffu) {
-			const int w = __ffs((int)__ballot_sync(full, key == mn)) - 1;
-			float4 pl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-			if ((int)lane == w) pl = facetClipPlane(m, T, r.which);   // same float ops, same plane (T still holds this facet's run)
-			cur = __shfl_sync(full, r.enter, w);
-			best.x = __shfl_sync(full, pl.x, w); best.y = __shfl_sync(full, pl.y, w);
-			best.z = __shfl_sync(full, pl.z, w); best.w = __shfl_sync(full, pl.w, w);
-			any = true;
+		for (int base = first, ci = 0; base < end; base += 32, ci++) {
+			if (chunkCull && !((chunks >> ci) & 1u)) continue;
+			const int f = base + (int)lane;
+			const bool live = f < end && f - first < 65536 &&
+			                  !(cull && axialBordersReject(__ldg(&m.facetAxial[2 * f]), __ldg(&m.facetAxial[2 * f + 1]), T, true));
+			const unsigned mask = __ballot_sync(full, live);
+			if (count + __popc(mask) > kPatchQueue) flush();
+			if (live) sq[count + __popc(mask & laneLt)] = ((unsigned)owner << 16) | (unsigned)(f - first);
+			count += __popc(mask);
 		}
 	}
-	if (any && lane == (unsigned)owner) {
-		L.fraction = cur;
-		L.pnx = best.x; L.pny = best.y; L.pnz = best.z; L.pd = best.w;
-	}
+	if (count) flush();
 }
 
 // CM_PositionTestInPatchCollide, cm_patch.c:1479-1531
@@ -1167,13 +1215,19 @@ __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const De
 		// ---------------- one facet of the current patch, cm_patch.c:1264-1311 / 1383-1462 -----------------
 		// Lanes that are inside a patch run their facets together, whatever patch and facet each of them is at.
 		if (!COUNT) {
-			// the warp takes the patches its lanes have reached one at a time (patchByWarp)
-			unsigned pend = __ballot_sync(0xffffffffu, mode == M_FACET);
-			while (pend) {
-				const int owner = __ffs((int)pend) - 1;
-				pend &= pend - 1u;
-				patchByWarp(m, L, owner, lane);
-				if ((int)lane == owner) {
+			// the warp takes the patches its lanes have reached: point sweeps one owner at a time, box sweeps all together
+			// (like the other heavy steps, once a gang of lanes has gathered -- q.facetSteps of them -- or nothing else can move)
+			const unsigned pend = __ballot_sync(0xffffffffu, mode == M_FACET);
+			if (pend && __popc(pend) >= min(q.facetSteps, nLight)) {
+				unsigned points = pend & __ballot_sync(0xffffffffu, (L.flags & F_POINT) != 0);
+				const unsigned boxes = pend & ~points;
+				while (points) {
+					const int owner = __ffs((int)points) - 1;
+					points &= points - 1u;
+					patchPointByWarp(m, L, owner, lane);
+				}
+				if (boxes) patchBoxesByWarp(m, L, boxes, lane);
+				if (mode == M_FACET) {
 					if (L.fraction < L.enter) {                      // CM_TraceThroughPatch, cm_trace.c:247-252
 						const int4 pa = __ldg(&m.patchInfo[2 * L.brush]);
 						L.surfaceFlags = pa.x;
