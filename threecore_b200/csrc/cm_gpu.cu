@@ -2530,6 +2530,7 @@ int cmgpu_aas_upload(cmgpu_ctx *ctx, int numplanes, const float *planes, int num
 	if (!ctx) return CMGPU_ERR_INVALID;
 	if (numplanes < 2 || !planes || numnodes < 2 || !nodes || numareas < 1 || !presencetypes)
 		return fail(ctx, CMGPU_ERR_BAD_MAP, "cmgpu_aas_upload: an AAS world has planes, a dummy node 0 and a root node 1, and a dummy area 0");
+	if (numplanes & 1) return fail(ctx, CMGPU_ERR_BAD_MAP, "cmgpu_aas_upload: %d planes -- AAS planes come in opposite pairs (plane n ^ 1 is plane n flipped, be_aas_sample.c:469)", numplanes);
 	// every index the kernels follow is checked here; the node graph must be a tree (a cycle would never end on the device)
 	for (int i = 1; i < numnodes; i++) {
 		const int32_t *nd = nodes + 3 * (size_t)i;
