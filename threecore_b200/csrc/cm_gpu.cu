@@ -47,6 +47,7 @@ constexpr size_t kPoolSmem = (size_t)(kBlock / 32) * PF_COUNT * CMGPU_POOL_K * 3
 constexpr int kBinSlots = CMGPU_PIPE_STREAMS;   // pipeline streams of the host-pointer calls, each with its own workspaces
 constexpr int kPipeChunks = 64;          // upper bound on the pieces a host batch is cut into (copies overlap the kernels)
 constexpr size_t kMinChunkItems = 1 << 16;
+constexpr int kHullTables = 8;            // hulls whose node tables and entry grids are kept per map
 
 // calls of a few items (traceHostTiny): where their arguments and results live in the context's mapped pinned block
 constexpr int kTinyMax = 128;
@@ -76,6 +77,11 @@ struct cmgpu_ctx_s {
 	std::vector<std::pair<const void **, size_t>> slabFixups;
 	void *mapSlab = nullptr;
 	size_t mapSlabBytes = 0, mapWindowBytes = 0;
+	// per-hull tables live right behind the map in the same allocation (kHullTables slots of hullArenaPer bytes): one L2
+	// access-policy window per launch is all CUDA gives, and without it their lines count as streaming data
+	size_t hullArenaPer = 0, hullArenaOff = 0;
+	int hullSlotsUsed = 0;
+	bool hullWindow = true;              // "hull_window" 0: the window covers the map only (as in round 1)
 	bool l2Window = true;
 	int numModels = 0;
 	int noCurves = 0, playerCurveClip = 1;
@@ -135,7 +141,7 @@ struct cmgpu_ctx_s {
 	std::vector<void *> retired;
 	bool twoPhase = true, twoPhaseHost = false, twoPhaseSmall = false, compactByItem = true;
 	// pool kernel: per-hull node threshold tables (nodeThresholdKernel), built on first use, dropped with the map
-	struct HullTable { NodeHull key; DevBuf buf; bool usable; DevBuf cells; bool gridUsable; };
+	struct HullTable { NodeHull key; int4 *nodes; uint2 *cells; bool usable, gridUsable; };   // slots of the arena behind the map
 	EntryGrid entry{};                   // geometry of the entry grid and the heap of the top levels (cellRec is per hull: HullTable::cells)
 	bool entryGrid = true;
 	float entryCell = 128.0f;            // target cell size of the entry grid, world units
@@ -243,7 +249,10 @@ int uploadArray(cmgpu_ctx *ctx, const std::vector<T> &host, const T **dev) {
 
 int commitMapSlab(cmgpu_ctx *ctx) {
 	void *p = nullptr;
-	const size_t bytes = ctx->slabHost.size() ? ctx->slabHost.size() : 256;
+	const size_t mapBytes = ((ctx->slabHost.size() ? ctx->slabHost.size() : 256) + 255) & ~(size_t)255;
+	const size_t bytes = mapBytes + (size_t)kHullTables * ctx->hullArenaPer;
+	ctx->hullArenaOff = mapBytes;
+	ctx->hullSlotsUsed = 0;
 	CUDA_TRY(ctx, cudaMalloc(&p, bytes));
 	ctx->mapAllocs.push_back(p);
 	CUDA_TRY(ctx, cudaMemcpy(p, ctx->slabHost.data(), ctx->slabHost.size(), cudaMemcpyHostToDevice));
@@ -257,7 +266,9 @@ int commitMapSlab(cmgpu_ctx *ctx) {
 	CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
 	ctx->mapWindowBytes = 0;
 	if (ctx->l2Window && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
-		size_t want = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+		// set aside room for the map and two hulls' tables; the window of a launch covers the map and the slots in use
+		const size_t aside = mapBytes + 2 * ctx->hullArenaPer;
+		size_t want = aside < (size_t)prop.persistingL2CacheMaxSize ? aside : (size_t)prop.persistingL2CacheMaxSize;
 		if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
 			ctx->mapWindowBytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
 		else cudaGetLastError();
@@ -279,7 +290,9 @@ cudaError_t launchOnMap(cmgpu_ctx *ctx, void (*kernel)(KArgs...), int blocks, in
 	if (ctx->mapWindowBytes) {
 		attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
 		attr[0].val.accessPolicyWindow.base_ptr = ctx->mapSlab;
-		attr[0].val.accessPolicyWindow.num_bytes = ctx->mapWindowBytes;
+		size_t inUse = ctx->hullArenaOff + ctx->hullTables.size() * ctx->hullArenaPer;
+		if (inUse > ctx->mapWindowBytes || !ctx->hullWindow) inUse = ctx->hullWindow ? ctx->mapWindowBytes : (ctx->hullArenaOff < ctx->mapWindowBytes ? ctx->hullArenaOff : ctx->mapWindowBytes);
+		attr[0].val.accessPolicyWindow.num_bytes = inUse;
 		attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
 		attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
 		attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
@@ -303,7 +316,6 @@ void freeMap(cmgpu_ctx *ctx) {
 	memset(&ctx->map, 0, sizeof(ctx->map));
 	memset(&ctx->fast, 0, sizeof(ctx->fast));
 	ctx->numPatches = 0;
-	for (auto &t : ctx->hullTables) { releaseBuf(t.buf); releaseBuf(t.cells); }
 	ctx->hullTables.clear();
 	for (void *p : ctx->retired) cudaFree(p);
 	ctx->retired.clear();
@@ -690,6 +702,42 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		ctx->numPatches = f->numPatches;
 	}
 #undef UP
+	{	// entry grid (EntryGrid): cells of about entryCell units over the bounds of the world's brushes, at most 2^20 of them
+		float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+		for (int i = 0; i < f->numBrushes; i++) {
+			if (i == f->boxBrush) continue;
+			const float *bb = f->brushBounds + 6 * (size_t)i;
+			for (int a = 0; a < 3; a++) {
+				if (bb[a] < lo[a]) lo[a] = bb[a];
+				if (bb[3 + a] > hi[a]) hi[a] = bb[3 + a];
+			}
+		}
+		EntryGrid &e = ctx->entry;
+		int bits[3], total = 0;
+		for (int a = 0; a < 3; a++) {
+			float ext = hi[a] - lo[a];
+			if (!(ext > 1.0f) || !(ext < 1e9f)) ext = 1.0f;
+			bits[a] = 0;
+			while (bits[a] < 10 && ext / (float)(1 << bits[a]) > ctx->entryCell) bits[a]++;
+			total += bits[a];
+		}
+		while (total > 20) {
+			const int a = bits[0] >= bits[1] ? (bits[0] >= bits[2] ? 0 : 2) : (bits[1] >= bits[2] ? 1 : 2);
+			bits[a]--;
+			total--;
+		}
+		for (int a = 0; a < 3; a++) {
+			float ext = hi[a] - lo[a];
+			if (!(ext > 1.0f) || !(ext < 1e9f)) ext = 1.0f;
+			e.cells[a] = 1 << bits[a];
+			e.lo[a] = lo[a];
+			e.inv[a] = (float)e.cells[a] / ext;
+		}
+		e.cellRec = nullptr;
+	}
+	// room behind the map for the per-hull tables (node thresholds + entry grid), so that the map's L2 window covers them too
+	ctx->hullArenaPer = (((size_t)f->numNodes * sizeof(int4) + 16 + 255) & ~(size_t)255) +
+	                    (((size_t)ctx->entry.cells[0] * ctx->entry.cells[1] * ctx->entry.cells[2] * sizeof(uint2) + 255) & ~(size_t)255);
 	if ((rc = commitMapSlab(ctx)) != CMGPU_OK) return rc;
 	ctx->fast.nodePlanes = m.nodePlanes;
 	ctx->fast.sidePlanes = m.sidePlanes;
@@ -731,39 +779,6 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		g.longLen2 = ctx->binLongLen * ctx->binLongLen;
 		g.dirBins = ctx->binDir ? 8 : 1;
 		g.numBins = 2 * kBinClasses * g.cells[0] * g.cells[1] * g.cells[2] * g.dirBins;   // x2: point hulls / box hulls of per-item batches
-	}
-	{	// entry grid (EntryGrid): cells of about entryCell units over the bounds of the world's brushes, at most 2^20 of them
-		float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-		for (int i = 0; i < f->numBrushes; i++) {
-			if (i == f->boxBrush) continue;
-			const float *bb = f->brushBounds + 6 * (size_t)i;
-			for (int a = 0; a < 3; a++) {
-				if (bb[a] < lo[a]) lo[a] = bb[a];
-				if (bb[3 + a] > hi[a]) hi[a] = bb[3 + a];
-			}
-		}
-		EntryGrid &e = ctx->entry;
-		int bits[3], total = 0;
-		for (int a = 0; a < 3; a++) {
-			float ext = hi[a] - lo[a];
-			if (!(ext > 1.0f) || !(ext < 1e9f)) ext = 1.0f;
-			bits[a] = 0;
-			while (bits[a] < 10 && ext / (float)(1 << bits[a]) > ctx->entryCell) bits[a]++;
-			total += bits[a];
-		}
-		while (total > 20) {
-			const int a = bits[0] >= bits[1] ? (bits[0] >= bits[2] ? 0 : 2) : (bits[1] >= bits[2] ? 1 : 2);
-			bits[a]--;
-			total--;
-		}
-		for (int a = 0; a < 3; a++) {
-			float ext = hi[a] - lo[a];
-			if (!(ext > 1.0f) || !(ext < 1e9f)) ext = 1.0f;
-			e.cells[a] = 1 << bits[a];
-			e.lo[a] = lo[a];
-			e.inv[a] = (float)e.cells[a] / ext;
-		}
-		e.cellRec = nullptr;
 	}
 	m.numNodes = f->numNodes;
 	m.numModels = f->numModels;
@@ -837,15 +852,11 @@ const cmgpu_ctx::HullTable *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStr
 		if (!memcmp(&t.key, &key, sizeof(key))) return t.usable ? &t : nullptr;
 	}
 	if (ctx->capturing) return nullptr;                   // building synchronises: not inside a capture (plain node step instead)
-	if (ctx->hullTables.size() >= 8) {                    // a ninth hull: start over (nothing may still read the old tables)
-		cudaDeviceSynchronize();
-		for (auto &t : ctx->hullTables) {
-			if (ctx->graphPinned) {
-				if (t.buf.p) ctx->retired.push_back(t.buf.p);
-				if (t.cells.p) ctx->retired.push_back(t.cells.p);
-				t.buf = DevBuf{}; t.cells = DevBuf{};
-			} else { releaseBuf(t.buf); releaseBuf(t.cells); }
-		}
+	if ((int)ctx->hullTables.size() >= kHullTables) {
+		// every slot behind the map is taken.  Start over -- unless a recorded graph may name a slot: then this hull simply
+		// gets no table (the plain node step, same results)
+		if (ctx->graphPinned) return nullptr;
+		cudaDeviceSynchronize();                          // nothing may still read the old tables
 		ctx->hullTables.clear();
 	}
 	cmgpu_ctx::HullTable t{};
@@ -854,11 +865,15 @@ const cmgpu_ctx::HullTable *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStr
 	t.gridUsable = false;
 	const int n = ctx->map.numNodes;
 	const size_t bytes = (size_t)n * sizeof(int4);
-	if (reserve(ctx, t.buf, bytes + 16) == CMGPU_OK) {
-		int *flag = (int *)((char *)t.buf.p + bytes);
+	const size_t nodesRoom = (bytes + 16 + 255) & ~(size_t)255;
+	char *slot = (char *)ctx->mapSlab + ctx->hullArenaOff + ctx->hullTables.size() * ctx->hullArenaPer;
+	if (ctx->mapSlab && ctx->hullArenaPer >= nodesRoom) {
+		t.nodes = (int4 *)slot;
+		t.cells = (uint2 *)(slot + nodesRoom);
+		int *flag = (int *)(slot + bytes);
 		int hostFlag = -1;
 		bool ok = cudaMemsetAsync(flag, 0, sizeof(int), s) == cudaSuccess;
-		if (ok) nodeThresholdKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->fast.nodes, n, key, (int4 *)t.buf.p, flag);
+		if (ok) nodeThresholdKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->fast.nodes, n, key, t.nodes, flag);
 		ok = ok && cudaGetLastError() == cudaSuccess;
 		ok = ok && cudaMemcpyAsync(&hostFlag, flag, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess;
 		ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
@@ -867,10 +882,10 @@ const cmgpu_ctx::HullTable *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStr
 		// the entry grid of this hull (entryGridKernel): built from the table just made, verified on the device like it
 		const EntryGrid &e = ctx->entry;
 		const int cells = e.cells[0] * e.cells[1] * e.cells[2];
-		if (t.usable && ctx->entryGrid && e.top && cells > 1 && reserve(ctx, t.cells, (size_t)cells * sizeof(uint2)) == CMGPU_OK) {
+		if (t.usable && ctx->entryGrid && e.top && cells > 1 && ctx->hullArenaPer >= nodesRoom + (size_t)cells * sizeof(uint2)) {
 			hostFlag = -1;
 			ok = cudaMemsetAsync(flag, 0, sizeof(int), s) == cudaSuccess;
-			if (ok) entryGridKernel<<<(cells + 255) / 256, 256, 0, s>>>((const int4 *)t.buf.p, e, (uint2 *)t.cells.p, flag);
+			if (ok) entryGridKernel<<<(cells + 255) / 256, 256, 0, s>>>(t.nodes, e, t.cells, flag);
 			ok = ok && cudaGetLastError() == cudaSuccess;
 			ok = ok && cudaMemcpyAsync(&hostFlag, flag, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess;
 			ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
@@ -1018,9 +1033,9 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 		q.poolHdr = ctx->bPoolHdr[arenaSlot].p;
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
 		const cmgpu_ctx::HullTable *ht = (ctx->nodeThresholds && !ctx->counting) ? hullTable(ctx, h, s) : nullptr;
-		q.tnodes = ht ? (const int4 *)ht->buf.p : nullptr;
+		q.tnodes = ht ? ht->nodes : nullptr;
 		q.entry = ctx->entry;
-		q.entry.cellRec = (ht && ht->gridUsable && ctx->entryGrid) ? (const uint2 *)ht->cells.p : nullptr;
+		q.entry.cellRec = (ht && ht->gridUsable && ctx->entryGrid) ? ht->cells : nullptr;
 		if (ctx->counting)  CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<true, CMGPU_POOL_K, false>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 		else if (q.tnodes)  CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, true>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
 		else                CUDA_TRY(ctx, launchOnMap(ctx, tracePoolKernel<false, CMGPU_POOL_K, false>, (int)blocks, kBlock, kPoolSmem, s, ctx->fast, q, h));
@@ -1330,6 +1345,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "compact_by_item") ctx->compactByItem = value != 0;
 	else if (k == "node_thresholds") ctx->nodeThresholds = value != 0;
 	else if (k == "entry_grid") ctx->entryGrid = value != 0;
+	else if (k == "hull_window") ctx->hullWindow = value != 0;
 	else if (k == "auto_register") ctx->autoRegister = value != 0;
 	else if (k == "tiny_calls") ctx->tinyCalls = value != 0;
 	else if (k == "remote_pipeline") ctx->remotePipeline = value != 0;
