@@ -915,7 +915,7 @@ __device__ __forceinline__ void finishItem(const TraceBatch &q, Lane &L) {
 // can make progress).  Running the expensive blocks with a full gang instead of whichever
 // one or two lanes happen to need them is what keeps the warp's lanes busy.
 #ifndef CMGPU_MIN_BLOCKS
-#define CMGPU_MIN_BLOCKS 4
+#define CMGPU_MIN_BLOCKS 6   // 80 registers with a few spills beat 124 without: 24 warps per SM instead of 16 (config 4 1600 -> 1700, config 3 280 -> 303 Mtraces/s)
 #endif
 template <bool COUNT, int DEPTH = kMaxDepth>
 __global__ void __launch_bounds__(kBlock, CMGPU_MIN_BLOCKS) traceKernel(const DevMap m, const TraceBatch q) {
