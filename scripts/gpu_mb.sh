@@ -1,2 +1,2 @@
 #!/bin/bash
-for v in mb6 mb7 mb8; do echo "== $v"; CMGPU_LIB=build/variants/$v.so timeout 300 python scripts/config_bench.py 2>&1 | grep "config 3\|config 4: 4Mi transformed"; done
+for sm in 0 14000 18000 28000 37000 56000 75000 113000; do echo "== smem $sm"; CMGPU_AAS_SMEM=$sm timeout 300 python scripts/aas_bench.py 4194304 2>&1 | grep "TraceClientBBox x"; done
