@@ -96,6 +96,8 @@ struct cmgpu_ctx_s {
 	bool usePool = true;                 // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
 	int poolReps = 1;                    // its repeats of a light step per round (a node step is up to 3 levels, a leaf step 2 entries)
 	int minChunk = 8;                    // fewest items a warp takes at a time in a small launch
+	int simpleSpread = -1;               // thread-per-item kernel: log2 of the lanes per item; -1 = as many as fill the GPU's warp slots once
+	int gridSimple = 0;                  // resident CTAs of the thread-per-item kernel
 	int simpleMaxItems = 786432;         // launches up to this size use the thread-per-item kernel (lowest latency)
 	int poolMinItems = 786433;           // smaller launches use the one-item-per-lane variant (lower latency)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
@@ -897,6 +899,16 @@ const cmgpu_ctx::HullTable *hullTable(cmgpu_ctx *ctx, const FastHull &h, cudaStr
 	return t.usable ? &ctx->hullTables.back() : nullptr;
 }
 
+// Lanes per item of the thread-per-item kernel (log2): the largest spread that still fits the launch into the GPU's
+// resident warps at once.
+static int simpleSpread(const cmgpu_ctx *ctx, const int n) {
+	if (ctx->simpleSpread >= 0) return ctx->simpleSpread;
+	const long long slots = (long long)ctx->gridSimple * kBlock;      // resident threads
+	int lg = 0;
+	while (lg < 5 && ((long long)n << (lg + 1)) <= slots) lg++;
+	return lg;
+}
+
 // Device-pointer calls share the context's workspaces.  Whatever such a call leaves running on its stream, the next
 // one on ANOTHER stream (or a host-pointer call) must wait for: extDone is recorded after the last kernel that reads or
 // writes a shared workspace, and waited for at entry.
@@ -1017,7 +1029,8 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	}
 	if (fast && !pool && q.n <= ctx->simpleMaxItems) {
 		const FastHull h = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
-		const int nb = (q.n + kBlock - 1) / kBlock;
+		q.spreadLog2 = simpleSpread(ctx, q.n);
+		const int nb = (int)((((long long)q.n << q.spreadLog2) + kBlock - 1) / kBlock);
 		if (deep)               CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false, kDeepDepth>, nb, kBlock, 0, s, ctx->fast, q, h));
 		else if (ctx->counting) CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<true>, nb, kBlock, 0, s, ctx->fast, q, h));
 		else                    CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false>, nb, kBlock, 0, s, ctx->fast, q, h));
@@ -1238,6 +1251,9 @@ int cmgpu_create(cmgpu_ctx **out, int device) {
 		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmFC, traceFastKernel<true>, kBlock, 0) == cudaSuccess && perSmFC > 0;
 		ctx->gridFast = perSmF * prop.multiProcessorCount;
 		ctx->gridFastCount = perSmFC * prop.multiProcessorCount;
+		int perSmS = 0;
+		ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmS, traceSimpleKernel<false>, kBlock, 0) == cudaSuccess && perSmS > 0;
+		ctx->gridSimple = perSmS * prop.multiProcessorCount;
 		int perSmP = 0, perSmPC = 0;
 		ok = ok && cudaFuncSetAttribute(tracePoolKernel<false, CMGPU_POOL_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
 		ok = ok && cudaFuncSetAttribute(tracePoolKernel<false, CMGPU_POOL_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem) == cudaSuccess;
@@ -1358,6 +1374,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "gang_brush") ctx->gangBrush = (int)value;
 	else if (k == "facet_steps") ctx->facetSteps = value < 1 ? 1 : (int)value;
 	else if (k == "light_reps") ctx->lightReps = value < 1 ? 1 : (int)value;
+	else if (k == "simple_spread") ctx->simpleSpread = value < 0 ? -1 : (value > 5 ? 5 : (int)value);
 	else return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_set_option: unknown option '%s'", name);
 	return CMGPU_OK;
 }
@@ -1652,7 +1669,8 @@ static int traceHostTiny(cmgpu_ctx *ctx, int n, const float *starts, const float
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
 	if (fast) {
 		const FastHull fh = makeFastHull(q.sharedMins, q.sharedMaxs, q.sharedMask, ctx->slabOK && ctx->slabTest);
-		const int nb = (n + kBlock - 1) / kBlock;
+		q.spreadLog2 = simpleSpread(ctx, n);               // a handful of items: a warp each
+		const int nb = ((n << q.spreadLog2) + kBlock - 1) / kBlock;
 		if (deep) CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false, kDeepDepth>, nb, kBlock, 0, s, ctx->fast, q, fh));
 		else      CUDA_TRY(ctx, launchOnMap(ctx, traceSimpleKernel<false>, nb, kBlock, 0, s, ctx->fast, q, fh));
 	} else {

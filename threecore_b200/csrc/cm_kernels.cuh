@@ -160,6 +160,7 @@ struct TraceBatch {
 	const int4 *tnodes;                  // pool kernel: nodes with this batch's hull folded into two thresholds (nodeThresholdKernel); may be null
 	int compactByItem;                   // pool kernel: compact[] is indexed by item number (a 16-byte scatter), not by slot
 	EntryGrid entry;                     // pool kernel with tnodes: where an item's walk starts (cellRec null: at the root)
+	int spreadLog2;                      // thread-per-item kernel: only every (1 << spreadLog2)-th lane takes an item (small launches)
 };
 
 // ---- spatial binning of a batch (counting sort by start cell) -------------------------------
