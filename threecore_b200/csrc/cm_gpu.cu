@@ -95,7 +95,7 @@ struct cmgpu_ctx_s {
 	int gridPool = 0, gridPoolCount = 0;
 	bool usePool = true;                 // hot kernel variant with K items per lane in shared memory (cm_trace_pool.cuh)
 	int poolReps = 1;                    // its repeats of a light step per round (a node step is up to 3 levels, a leaf step 2 entries)
-	int minChunk = 8;                    // fewest items a warp takes at a time in a small launch
+	int minChunk = 4;                    // fewest items a warp takes at a time in a small launch
 	int simpleSpread = -1;               // thread-per-item kernel: log2 of the lanes per item; -1 = as many as fill the GPU's warp slots once
 	int gridSimple = 0;                  // resident CTAs of the thread-per-item kernel
 	int simpleMaxItems = 786432;         // launches up to this size use the thread-per-item kernel (lowest latency)
