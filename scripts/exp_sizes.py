@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 ds = torch.from_numpy(starts).to(dev); de = torch.from_numpy(ends).to(dev)
 d_out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
 eng = Engine(0); eng.load_bsp(m.data)
-for k in (65536, 131072, 262144, 393216, 524288, 786432, 1 << 20, 1 << 21, 1 << 22):
+for k in (65536, 81920, 98304, 114688, 131072, 163840, 196608):
     row = []
     for label, opts in (("simple", dict(simple_max_items=1 << 30, pool=0)), ("persistent", dict(simple_max_items=0, pool=0)), ("pool", dict(simple_max_items=0, pool=1, pool_min_items=1))):
         for kk, v in opts.items(): eng.set_option(kk, v)
@@ -23,5 +23,5 @@ for k in (65536, 131072, 262144, 393216, 524288, 786432, 1 << 20, 1 << 21, 1 << 
         for _ in range(10): eng.box_trace_device(ds[:k], de[:k], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, o)
         b.record(); torch.cuda.synchronize()
         row.append(f"{label} {a.elapsed_time(b)*100:.0f} us")
-        for kk, v in dict(pool=1, pool_min_items=1 << 20, simple_max_items=393216).items(): eng.set_option(kk, v)
+        for kk, v in dict(pool=1, pool_min_items=196609, simple_max_items=786432).items(): eng.set_option(kk, v)
     print(f"n={k:8d}: " + "   ".join(row), flush=True)

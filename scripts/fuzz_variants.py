@@ -37,7 +37,7 @@ for kind in ("arena_small", "room", "arena_models"):
                 eng.box_trace_device(ds, de, hull[0], hull[1], bspgen.MASK_ALL, o)
                 torch.cuda.synchronize(); eng.check_status()
                 outs[label] = o
-                for k, v in dict(fast=1, pool=1, pool_min_items=786433, simple_max_items=786432, bin=1, node_thresholds=1, two_phase=1).items(): eng.set_option(k, v)
+                for k, v in dict(fast=1, pool=1, pool_min_items=196609, simple_max_items=786432, bin=1, node_thresholds=1, two_phase=1).items(): eng.set_option(k, v)
             for label, o in outs.items():
                 if label == "general": continue
                 bad = int((o != outs["general"]).any(dim=1).sum())

@@ -386,7 +386,7 @@ def test_binning_small_batches_all_query_kinds(eng, which):
                 check(eng, o, case)
     finally:
         eng.set_option("bin_min_items", 98304)
-        eng.set_option("pool_min_items", 786433)
+        eng.set_option("pool_min_items", 196609)
         eng.set_option("simple_max_items", 786432)
 
 

@@ -27,7 +27,7 @@ def _worker(rank, world, port, n, q):
         s, e = bspgen.make_sweeps(m, n, 77)
         eng = Engine(rank)
         eng.load_bsp(m.data)
-        eng.set_option("pool_min_items", 100000)      # the rank's range is cut into pieces whose expansions stream to rank 0 (tracePieces)
+        eng.set_option("pipe_pool_min_items", 100000)      # the rank's range is cut into pieces whose expansions stream to rank 0 (tracePieces)
         dev = torch.device("cuda", rank)
         pr = PeerResults(eng, n)
         lo, hi = pr.local_range()

@@ -99,7 +99,10 @@ struct cmgpu_ctx_s {
 	int simpleSpread = -1;               // thread-per-item kernel: log2 of the lanes per item; -1 = as many as fill the GPU's warp slots once
 	int gridSimple = 0;                  // resident CTAs of the thread-per-item kernel
 	int simpleMaxItems = 786432;         // launches up to this size use the thread-per-item kernel (lowest latency)
-	int poolMinItems = 786433;           // smaller launches use the one-item-per-lane variant (lower latency)
+	int poolMinItems = 196609;           // device-pointer launches from this size up take the pool kernel, smaller ones the thread-per-item
+	                                     // kernel.  The crossover depends on the sweeps: ~72 Ki items for the bench's long ones (64 Ki 172 / 209 us,
+	                                     // 80 Ki 249 / 222 us, 256 Ki 402 / 353 us, 512 Ki 675 / 469 us), beyond 192 Ki for a rollout's short ones
+	int pipePoolMinItems = 786433;       // the same for the pieces of the host pipeline (PCIe-bound; each piece a launch on one of three streams)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;
 	int treeDepth = 1;                   // levels of the world BSP (validate()): the size of every traversal stack
@@ -988,7 +991,7 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
 	// the pool variant pays off once every warp has several rounds of items to work through
-	const bool pool = fast && ctx->usePool && q.n >= ctx->poolMinItems;
+	const bool pool = fast && ctx->usePool && q.n >= (external ? ctx->poolMinItems : ctx->pipePoolMinItems);
 	// out must be 16-byte aligned for the expand pass's stores (any cudaMalloc'ed or record-aligned pointer is)
 	// (not in the host pipeline: its pieces are small, their records leave over PCIe anyway, and the extra launch per
 	//  piece costs the call 8 % -- measured 764 against 826 Mtraces/s end to end)
@@ -1151,7 +1154,7 @@ int tracePieces(cmgpu_ctx *ctx, const TraceBatch &q0, cudaStream_t s) {
 	const bool hot = ctx->useFast && ctx->usePool && ctx->twoPhase && ctx->binning && !ctx->counting && !q0.mins && !q0.masks && !q0.models && !q0.origins &&
 	                 (ctx->numPatches == 0 || ctx->noCurves) && ((uintptr_t)q0.out & 15) == 0;
 	int pieces = ctx->remotePieces;
-	if (pieces > q0.n / ctx->poolMinItems) pieces = q0.n / ctx->poolMinItems;
+	if (pieces > q0.n / ctx->pipePoolMinItems) pieces = q0.n / ctx->pipePoolMinItems;
 	if (!hot || pieces < 2) return CMGPU_ERR_UNSUPPORTED_INTERNAL;
 	cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
 	if (cudaStreamIsCapturing(s, &st) != cudaSuccess) cudaGetLastError();
@@ -1352,6 +1355,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "min_chunk") ctx->minChunk = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
 	else if (k == "simple_max_items") ctx->simpleMaxItems = value < 0 ? 0 : (int)value;
 	else if (k == "pool_min_items") ctx->poolMinItems = value < 1 ? 1 : (int)value;
+	else if (k == "pipe_pool_min_items") ctx->pipePoolMinItems = value < 1 ? 1 : (int)value;
 	else if (k == "pipe_ramp") ctx->pipeRamp = value != 0;
 	else if (k == "pipe_chunks") ctx->pipeChunks = value < 1 ? 1 : (value > kPipeChunks ? kPipeChunks : (int)value);
 	else if (k == "slab") ctx->slabTest = value != 0;
