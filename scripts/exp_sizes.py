@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 ds = torch.from_numpy(starts).to(dev); de = torch.from_numpy(ends).to(dev)
 d_out = torch.empty((n, 56), dtype=torch.uint8, device=dev)
 eng = Engine(0); eng.load_bsp(m.data)
-for k in (65536, 81920, 98304, 114688, 131072, 163840, 196608):
+for k in (16384, 65536, 131072, 196608, 262144, 393216, 524288, 786432, 1 << 20, 1 << 21):
     row = []
     for label, opts in (("simple", dict(simple_max_items=1 << 30, pool=0)), ("persistent", dict(simple_max_items=0, pool=0)), ("pool", dict(simple_max_items=0, pool=1, pool_min_items=1))):
         for kk, v in opts.items(): eng.set_option(kk, v)

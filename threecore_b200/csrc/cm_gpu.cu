@@ -100,8 +100,8 @@ struct cmgpu_ctx_s {
 	int gridSimple = 0;                  // resident CTAs of the thread-per-item kernel
 	int simpleMaxItems = 786432;         // launches up to this size use the thread-per-item kernel (lowest latency)
 	int poolMinItems = 196609;           // device-pointer launches from this size up take the pool kernel, smaller ones the thread-per-item
-	                                     // kernel.  The crossover depends on the sweeps: ~72 Ki items for the bench's long ones (64 Ki 172 / 209 us,
-	                                     // 80 Ki 249 / 222 us, 256 Ki 402 / 353 us, 512 Ki 675 / 469 us), beyond 192 Ki for a rollout's short ones
+	                                     // kernel.  The crossover depends on the sweeps: ~128 Ki items for the bench's long ones (128 Ki 313 / 293 us,
+	                                     // 256 Ki 369 / 350, 512 Ki 576 / 467, 768 Ki 752 / 571), beyond 192 Ki for a rollout's short ones
 	int pipePoolMinItems = 786433;       // the same for the pieces of the host pipeline (PCIe-bound; each piece a launch on one of three streams)
 	FastMap fast{};                      // layout of the hot kernel (cm_trace_fast.cuh)
 	int numPatches = 0;

@@ -12,7 +12,7 @@
 namespace cmgpu {
 
 #ifndef CMGPU_SIMPLE_MIN_BLOCKS
-#define CMGPU_SIMPLE_MIN_BLOCKS 1
+#define CMGPU_SIMPLE_MIN_BLOCKS 6
 #endif
 template <bool COUNT, int DEPTH = kMaxDepth>
 __global__ void __launch_bounds__(kBlock, CMGPU_SIMPLE_MIN_BLOCKS)
