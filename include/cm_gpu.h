@@ -195,6 +195,28 @@ int cmgpu_point_contents_batch(cmgpu_ctx *ctx, int n, const float *points,
 int cmgpu_host_register(cmgpu_ctx *ctx, const void *ptr, size_t bytes);
 int cmgpu_host_unregister(cmgpu_ctx *ctx, const void *ptr);
 
+/* ---- who writes the records of a big host batch --------------------------------------------------------------
+ * cmgpu_box_trace_batch with one hull and one mask for the whole batch, on a map without active patches, of
+ * "hybrid_min_items" (2 Mi) items or more: every piece is traced into 16-byte results (fraction, solid flags, clip side,
+ * hit brush); per range of items the 56-byte trace_t records are then EITHER written by the device and copied into the
+ * caller's array, OR the 16-byte results are copied into pinned memory of the context and worker threads of the calling
+ * process write the records into the caller's array (endpos, plane, surface flags, contents: cm_trace.c:352-356, 671-686,
+ * same float operations in the same order -- formatting, not tracing).  The split follows the measured rates of the link
+ * and of the threads.  A pageable result array is written by the threads only.
+ *   cmgpu_set_option("host_records", v): -1 = as described (default), 0 = off: every record is written by the device
+ *       (the round-1 pipeline), 1 = every record by the threads, 2 = the new pipeline with every record by the device.
+ *   cmgpu_set_option("host_threads", t): worker threads; -1 (default) = host cores / visible GPUs - 1.
+ * cmgpu_last_batch_split: how many records of the last such call each side wrote. */
+int cmgpu_last_batch_split(const cmgpu_ctx *ctx, unsigned long long *by_host, unsigned long long *by_device);
+
+/* The host threads' record formatter on its own (no device, no context): n results of 16 bytes -- {fraction bits,
+ * allsolid | startsolid << 1, clip side or -1, hit brush or -1} -- with the sweeps they belong to and the three tables a
+ * record draws on (per brush side: plane normal + dist, plane type | signbits << 8, surfaceFlags; per brush: contents)
+ * become n trace_t records (cm_trace.c:352-356, 671-686).  Single-threaded; CMGPU_ERR_INVALID for an index out of range. */
+int cmgpu_format_records(int n, const uint32_t *results16, const float *starts, const float *ends,
+                         int num_sides, const float *side_planes, const int32_t *side_type_signbits, const int32_t *side_surface_flags,
+                         int num_brushes, const int32_t *brush_contents, cmgpu_trace_t *records, int32_t *hit_ids);
+
 /* ---- batched queries, DEVICE pointers (inputs resident in HBM) -----------
  * Same meaning as above; per-item arrays are device pointers on the context's
  * GPU.  A SHARED hull (hull_stride == 0: mins/maxs, 3 floats each, may be NULL)

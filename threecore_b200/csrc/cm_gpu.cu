@@ -14,6 +14,7 @@
 #include "cm_aas.cuh"
 #include "../../include/cm_gpu.h"
 #include "cm_patchgen.h"
+#include "cm_host_records.h"
 #include "cm_patchgen_core.h"
 
 #include <cuda.h>
@@ -24,10 +25,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <new>
 #include <stddef.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace cmgpu;
@@ -193,6 +196,26 @@ struct cmgpu_ctx_s {
 	// host regions pinned through this context (cmgpu_host_register, or "auto_register"): page-aligned [lo, hi)
 	std::vector<std::pair<uintptr_t, uintptr_t>> hostRegs;
 	bool autoRegister = false;
+	// Host half of a big host batch's results (traceHostHybrid, cm_host_records.h): a share of the pieces comes back as the
+	// walk's 16-byte results and the calling process's worker threads write the 56-byte records from them.
+	int hostRecords = -1;                // "host_records": -1 = the split follows the measured rates, 0 = off (every record over
+	                                     // PCIe), 1 = every record written by the host, 2 = the new pipeline with no host share
+	int hostThreads = -1;                // "host_threads": -1 = host cores per visible GPU, minus one for the caller
+	size_t hybridMinItems = (size_t)1 << 21, hybridWalkItems = (size_t)1 << 20;
+	hostrec::Pool *hostPool = nullptr;
+	std::vector<hostrec::SideRec> hostSides;         // [numBrushSides + 1], entry 0 = no side
+	std::vector<int32_t> hostBrushContents;          // [numBrushes + 1], entry 0 = no brush
+	char *hCompact = nullptr;            // pinned: where the 16-byte results land
+	size_t hCompactCap = 0;
+	std::vector<cudaEvent_t> hybridEvents;
+	// the share of a batch the threads get: set from the thread count before the first call, then corrected after every
+	// call by who finished later, the link or the threads (both are busy to the end when the share is right)
+	double hostShare = -1.0;
+	// big host batches, both pipelines timed (ns per item, running means): [0] = every record over PCIe (round 1), [1] = shared
+	double pipeNs[2] = {0.0, 0.0};
+	unsigned pipeCalls[2] = {0, 0};
+	double d2hRate = 50e9;               // bytes per second of a result copy, measured on the way
+	unsigned long long hostRecordsWritten = 0, deviceRecordsWritten = 0;   // of the last hybrid call
 	unsigned long long svCandidates = 0;
 };
 
@@ -539,6 +562,15 @@ int packAndUpload(cmgpu_ctx *ctx, const cmgpu_flatmap *f) {
 		sidePlanes[i] = make_float4(p[0], p[1], p[2], p[3]);
 		sideMeta[i] = make_int2(f->brushsides[2 * (size_t)i + 1], (int)f->planeType[pl] | ((int)f->planeSignbits[pl] << 8));
 	}
+	ctx->hostSides.assign((size_t)f->numBrushSides + 1, hostrec::SideRec{});
+	for (int i = 0; i < f->numBrushSides; i++) {
+		hostrec::SideRec &r = ctx->hostSides[(size_t)i + 1];
+		r.plane[0] = sidePlanes[i].x; r.plane[1] = sidePlanes[i].y; r.plane[2] = sidePlanes[i].z; r.plane[3] = sidePlanes[i].w;
+		r.typeSignbits = (uint32_t)sideMeta[i].y & 0xffffu;
+		r.surfaceFlags = (uint32_t)sideMeta[i].x;
+	}
+	ctx->hostBrushContents.assign((size_t)f->numBrushes + 1, 0);
+	for (int i = 0; i < f->numBrushes; i++) ctx->hostBrushContents[(size_t)i + 1] = f->brushes[3 * (size_t)i];
 	std::vector<int4> modelLeafs((size_t)f->numModels);
 	for (int i = 0; i < f->numModels; i++) {
 		if (i == 0 || !f->modelLeafs) { modelLeafs[i] = make_int4(0, 0, 0, 0); continue; }
@@ -931,7 +963,10 @@ int extRecord(cmgpu_ctx *ctx, cudaStream_t s) {
 
 // wsOffset: first item of this launch inside the context's binning workspace (the host pipeline gives
 // every chunk its own range); histSlot: which histogram table to use (one per pipeline stream).
-int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1, bool sideExpand = false) {
+// hybrid (traceHostHybrid): the pool kernel whatever the size of the launch, leaving the walk's 16-byte results in
+// bCompact[wsOffset + item]; 1 = and nothing more (the host writes the records), 2 = followed by expandRecordsKernel.
+int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 0, int histSlot = -1, bool sideExpand = false, int hybrid = 0) {
+	const bool compactOnly = hybrid == 1;
 	if (q.n <= 0) return CMGPU_OK;
 	const unsigned *slotOf = nullptr;
 	q.compact = nullptr;
@@ -991,15 +1026,16 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	// the hot kernel serves world traces with one hull and one mask on maps without (active) patches
 	const bool fast = ctx->useFast && !q.mins && !q.masks && !q.models && !q.origins && (ctx->numPatches == 0 || ctx->noCurves);
 	// the pool variant pays off once every warp has several rounds of items to work through
-	const bool pool = fast && ctx->usePool && q.n >= (external ? ctx->poolMinItems : ctx->pipePoolMinItems);
+	const bool pool = fast && ctx->usePool && (hybrid || q.n >= (external ? ctx->poolMinItems : ctx->pipePoolMinItems));
 	// out must be 16-byte aligned for the expand pass's stores (any cudaMalloc'ed or record-aligned pointer is)
 	// (not in the host pipeline: its pieces are small, their records leave over PCIe anyway, and the extra launch per
 	//  piece costs the call 8 % -- measured 764 against 826 Mtraces/s end to end)
 	// and not for the smaller launches of the one-item-per-lane kernels either (a rollout phase, a game tick: one more
 	// launch is 5 % of their latency; "two_phase_small" turns it on for them)
-	if (fast && (pool || ctx->twoPhaseSmall) && slotOf && ctx->twoPhase && (external || ctx->twoPhaseHost || sideExpand) && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
+	if (fast && (pool || ctx->twoPhaseSmall) && slotOf && ctx->twoPhase && (external || ctx->twoPhaseHost || sideExpand || hybrid) && !ctx->counting && ((uintptr_t)q.out & 15) == 0)
 		q.compact = (uint4 *)ctx->bCompact.p + wsOffset;
 	q.compactByItem = q.compact && pool && ctx->compactByItem ? 1 : 0;
+	if (hybrid && !q.compactByItem) return fail(ctx, CMGPU_ERR_INVALID, "internal: this launch cannot leave its results as 16-byte records by item");
 	const int resident = pool ? (ctx->counting ? ctx->gridPoolCount : ctx->gridPool)
 	                   : fast ? (ctx->counting ? ctx->gridFastCount : ctx->gridFast) : (ctx->counting ? ctx->gridCount : ctx->gridPlain);
 	// Items per cursor grab: kChunk for big batches; for small ones a share that spreads the batch over all
@@ -1069,7 +1105,9 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	}
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaGetLastError());
-	if (q.compact && sideExpand) {
+	if (compactOnly) {
+		// the records are written later, by expandRecordsKernel or by the host
+	} else if (q.compact && sideExpand) {
 		int ctas = (q.n + kExpandBlock - 1) / kExpandBlock;
 		if (ctas > ctx->remoteExpandCtas) ctas = ctx->remoteExpandCtas;
 		CUDA_TRY(ctx, cudaEventRecord(ctx->evWalked, s));
@@ -1289,6 +1327,9 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	                  &ctx->bSvPass, &ctx->bLeafLists, &ctx->bLeafCounts, &ctx->bVis, &ctx->bFlood, &ctx->bEntRecs, &ctx->bVisible}) releaseBuf(*b);
 	if (ctx->hSvTotal) cudaFreeHost(ctx->hSvTotal);
 	if (ctx->tinyHost) cudaFreeHost(ctx->tinyHost);
+	if (ctx->hostPool) hostrec::poolDestroy(ctx->hostPool);
+	if (ctx->hCompact) cudaFreeHost(ctx->hCompact);
+	for (auto &e : ctx->hybridEvents) cudaEventDestroy(e);
 	releaseBuf(ctx->bAas); releaseBuf(ctx->bAasIn); releaseBuf(ctx->bAasOut);
 	for (auto &r : ctx->hostRegs) cudaHostUnregister((void *)r.first);
 	ctx->hostRegs.clear();
@@ -1367,6 +1408,14 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "entry_grid") ctx->entryGrid = value != 0;
 	else if (k == "hull_window") ctx->hullWindow = value != 0;
 	else if (k == "auto_register") ctx->autoRegister = value != 0;
+	else if (k == "host_records") ctx->hostRecords = value < 0 ? -1 : (value > 2 ? 2 : (int)value);
+	else if (k == "host_threads") {
+		const int t = value < 0 ? -1 : (value > 256 ? 256 : (int)value);
+		if (t != ctx->hostThreads && ctx->hostPool) { hostrec::poolDestroy(ctx->hostPool); ctx->hostPool = nullptr; }
+		ctx->hostThreads = t;
+	}
+	else if (k == "hybrid_min_items") ctx->hybridMinItems = value < 1 ? 1 : (size_t)value;
+	else if (k == "hybrid_walk_items") ctx->hybridWalkItems = value < 98304 ? 98304 : (size_t)value;
 	else if (k == "tiny_calls") ctx->tinyCalls = value != 0;
 	else if (k == "remote_pipeline") ctx->remotePipeline = value != 0;
 	else if (k == "remote_pieces") ctx->remotePieces = value < 1 ? 1 : (int)value;
@@ -1501,6 +1550,35 @@ int cmgpu_host_register(cmgpu_ctx *ctx, const void *ptr, size_t bytes) {
 	if (!ptr || !bytes) return fail(ctx, CMGPU_ERR_INVALID, "cmgpu_host_register: empty region");
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	return registerRange(ctx, ptr, bytes);
+}
+
+int cmgpu_format_records(int n, const uint32_t *results16, const float *starts, const float *ends,
+                         int num_sides, const float *side_planes, const int32_t *side_type_signbits, const int32_t *side_surface_flags,
+                         int num_brushes, const int32_t *brush_contents, cmgpu_trace_t *records, int32_t *hit_ids) {
+	if (n < 0 || num_sides < 0 || num_brushes < 0 || (n > 0 && (!results16 || !starts || !ends || !records))) return CMGPU_ERR_INVALID;
+	if ((num_sides > 0 && (!side_planes || !side_type_signbits || !side_surface_flags)) || (num_brushes > 0 && !brush_contents)) return CMGPU_ERR_INVALID;
+	for (int i = 0; i < n; i++) {
+		const int32_t side = (int32_t)results16[4 * (size_t)i + 2], brush = (int32_t)results16[4 * (size_t)i + 3];
+		if (side < -1 || side >= num_sides || brush < -1 || brush >= num_brushes) return CMGPU_ERR_INVALID;
+	}
+	std::vector<hostrec::SideRec> sides((size_t)num_sides + 1, hostrec::SideRec{});
+	std::vector<int32_t> contents((size_t)num_brushes + 1, 0);
+	for (int i = 0; i < num_sides; i++) {
+		hostrec::SideRec &r = sides[(size_t)i + 1];
+		memcpy(r.plane, side_planes + 4 * (size_t)i, 16);
+		r.typeSignbits = (uint32_t)side_type_signbits[i] & 0xffffu;
+		r.surfaceFlags = (uint32_t)side_surface_flags[i];
+	}
+	for (int i = 0; i < num_brushes; i++) contents[(size_t)i + 1] = brush_contents[i];
+	hostrec::expand(hostrec::Tables{sides.data(), contents.data()}, results16, starts, ends, records, hit_ids, 0, (size_t)n);
+	return CMGPU_OK;
+}
+
+int cmgpu_last_batch_split(const cmgpu_ctx *ctx, unsigned long long *by_host, unsigned long long *by_device) {
+	if (!ctx) return CMGPU_ERR_INVALID;
+	if (by_host) *by_host = ctx->hostRecordsWritten;
+	if (by_device) *by_device = ctx->deviceRecordsWritten;
+	return CMGPU_OK;
 }
 
 int cmgpu_host_unregister(cmgpu_ctx *ctx, const void *ptr) {
@@ -1694,6 +1772,223 @@ static int traceHostTiny(cmgpu_ctx *ctx, int n, const float *starts, const float
 	return CMGPU_OK;
 }
 
+// ---- big host batches of the hot path: the records come back two ways at once ------------------------------------------
+// A host batch waits for its records: 56 bytes per trace over PCIe against 24 on the way in and ~6 ns of GPU time
+// (DESIGN.md 4.4).  The walk decides 16 of the 56 bytes; the rest follows from them, the caller's own start / end arrays
+// and three tables of the map.  The batch is cut into pieces of `hybridWalkItems` items, and when a piece is queued --
+// a few pieces ahead of the one whose results are leaving -- it is given one of two ways home:
+//   device: walk, expandRecordsKernel, copy of the 56-byte records into the caller's array, all on the piece's stream;
+//   host:   walk, copy of the 16-byte results into pinned memory of the context; worker threads of the calling process
+//           write the records into the caller's array (cm_host_records.cpp -- the same float operations in the same order).
+// The choice is list scheduling with the measured rates of the two resources: the piece goes to whichever of link and
+// workers would be done earlier with everything it has been given so far plus this piece.  Few host cores (eight ranks
+// on one box) => few pieces go to the host; neither side waits for the slower one.
+struct HybridWait { int device; cudaEvent_t ev; };
+static void hybridWaitFn(void *arg) {
+	const HybridWait *w = static_cast<const HybridWait *>(arg);
+	cudaSetDevice(w->device);
+	cudaEventSynchronize(w->ev);
+}
+
+static bool hybridEligible(const cmgpu_ctx *ctx, size_t N, int hull_stride, const int32_t *models, int mask_stride, const float *origins,
+                           const float *boxmins) {
+	return ctx->hostRecords != 0 && ctx->useFast && ctx->usePool && ctx->twoPhase && ctx->compactByItem && ctx->binning && !ctx->counting &&
+	       !hull_stride && !models && !mask_stride && !origins && !boxmins && (ctx->numPatches == 0 || ctx->noCurves) &&
+	       N >= ctx->hybridMinItems && N <= ((size_t)1 << 26) && ctx->hybridWalkItems >= (size_t)ctx->binMinItems && !ctx->hostSides.empty();
+}
+
+static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, const float *ends, const float *mins, const float *maxs,
+                           const int32_t mask, cmgpu_trace_t *results, int32_t *hit_ids) {
+	int rc;
+	const size_t v3 = 3 * sizeof(float);
+	if (!ctx->hostPool && ctx->hostRecords != 2) {
+		int t = ctx->hostThreads;
+		if (t < 0) {
+			int devs = 1;
+			if (cudaGetDeviceCount(&devs) != cudaSuccess || devs < 1) { cudaGetLastError(); devs = 1; }
+			const int hw = (int)std::thread::hardware_concurrency();
+			t = hw / devs - 1;
+			if (t > 32) t = 32;
+		}
+		if (t < 1) t = 1;
+		ctx->hostPool = hostrec::poolCreate(t);
+	}
+	hostrec::Pool *pool = ctx->hostRecords == 2 ? nullptr : ctx->hostPool;
+	if (pool && ctx->hCompactCap < N * 16) {
+		if (ctx->hCompact) { CUDA_TRY(ctx, cudaDeviceSynchronize()); cudaFreeHost(ctx->hCompact); ctx->hCompact = nullptr; ctx->hCompactCap = 0; }
+		const size_t want = N * 16 + N * 2 + 4096;
+		CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->hCompact, want, cudaHostAllocDefault));
+		ctx->hCompactCap = want;
+	}
+	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
+	if ((rc = reserve(ctx, ctx->bEnds, N * v3))) return rc;
+	if ((rc = reserve(ctx, ctx->bOut, N * sizeof(cmgpu_trace_t)))) return rc;
+	if (hit_ids && (rc = reserve(ctx, ctx->bHit, N * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bKeys, N * 4))) return rc;
+	if ((rc = reserve(ctx, ctx->bRecs, N * 32))) return rc;
+	if ((rc = reserve(ctx, ctx->bCompact, N * 16))) return rc;
+	if (ctx->extBusy) {
+		CUDA_TRY(ctx, cudaEventSynchronize(ctx->extDone));
+		ctx->extBusy = false;
+	}
+	autoRegister(ctx, starts, N * v3);
+	autoRegister(ctx, ends, N * v3);
+	autoRegister(ctx, results, N * sizeof(cmgpu_trace_t));
+	// a pageable result array is written by the CPU anyway (a copy into it would be staged by the driver, and block)
+	const bool allHost = pool && (ctx->hostRecords == 1 || isPageable(results) || isPageable((const char *)(results + N) - 1));
+
+	// pieces: 1/4, 1/2, then whole pieces of hybridWalkItems (the first records should leave early)
+	std::vector<size_t> wb;
+	wb.push_back(0);
+	{
+		const size_t piece = ctx->hybridWalkItems;
+		size_t step = piece / 4 >= (size_t)ctx->binMinItems ? piece / 4 : piece;
+		size_t at = 0;
+		while (at < N) {
+			at = at + step + step / 2 < N ? ((at + step) & ~(size_t)255) : N;
+			wb.push_back(at);
+			if (step < piece) step = step * 2 < piece ? step * 2 : piece;
+		}
+	}
+	const int pieces = (int)wb.size() - 1;
+	while (ctx->hybridEvents.size() < 4 * (size_t)pieces + 1) {
+		cudaEvent_t e;
+		CUDA_TRY(ctx, cudaEventCreate(&e));
+		ctx->hybridEvents.push_back(e);
+	}
+	cudaEvent_t *copyStart = ctx->hybridEvents.data(), *pieceDone = ctx->hybridEvents.data() + pieces, *uploaded = ctx->hybridEvents.data() + 2 * pieces;
+	cudaEvent_t *walked = ctx->hybridEvents.data() + 3 * pieces;
+	const cudaEvent_t evBase = ctx->hybridEvents[4 * (size_t)pieces];
+
+	struct Drain { hostrec::Pool *p; ~Drain() { if (p) hostrec::poolWaitAll(p); } } drain{pool};   // no worker outlives the call
+	static const bool traceTimes = getenv("CMGPU_HYBRID_TRACE") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
+	auto sinceMs = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+	if (pool) hostrec::poolSetEpoch(pool);
+	CUDA_TRY(ctx, cudaEventRecord(evBase, ctx->streams[0]));
+	std::vector<char> wentHost((size_t)pieces, 0);
+
+	std::vector<size_t> outBytes((size_t)pieces, 0);
+	std::vector<HybridWait> waits((size_t)pieces);
+	int oldest = 0;
+	double backlogBytes = 0.0;          // result bytes queued on the link and not yet seen to have arrived
+	unsigned long long hostRecs = 0, devRecs = 0;
+	auto harvest = [&](bool block) -> cudaError_t {
+		while (oldest < (int)outBytes.size() && outBytes[oldest]) {
+			cudaError_t e = block ? cudaEventSynchronize(pieceDone[oldest]) : cudaEventQuery(pieceDone[oldest]);
+			if (e == cudaErrorNotReady) return cudaSuccess;
+			if (e != cudaSuccess) return e;
+			float ms = 0.0f;
+			if (outBytes[oldest] >= ((size_t)8 << 20) && cudaEventElapsedTime(&ms, copyStart[oldest], pieceDone[oldest]) == cudaSuccess && ms > 0.0f)
+			{	// a copy that shared the link with the other kind measures its share, not the link: follow the best samples
+				const double rate = (double)outBytes[oldest] / (1e-3 * ms);
+				ctx->d2hRate = rate > ctx->d2hRate ? 0.5 * ctx->d2hRate + 0.5 * rate : 0.95 * ctx->d2hRate + 0.05 * rate;
+			}
+			backlogBytes -= (double)outBytes[oldest];
+			oldest++;
+			block = false;
+		}
+		return cudaSuccess;
+	};
+	if (pool && ctx->hostShare < 0.0) {
+		// ~60 M records per second and thread against a link that moves ~1000 M records per second: 56 / (Rp / Rh + 40)
+		const double Rh = 60e6 * hostrec::poolThreads(pool);
+		ctx->hostShare = 56.0 / (55e9 / Rh + 40.0);
+	}
+	const int inFlight = 2 * kBinSlots;
+	hostrec::Tables tables{ctx->hostSides.data(), ctx->hostBrushContents.data()};
+	for (int c = 0; c < pieces; c++) {
+		const size_t lo = wb[c], cnt = wb[c + 1] - lo;
+		CUDA_TRY(ctx, harvest(false));
+		while (c - oldest >= inFlight) CUDA_TRY(ctx, harvest(true));
+		bool host = allHost;
+		if (pool && !allHost && ctx->hostRecords < 0) {
+			// error diffusion: the threads' share of what has been handed out so far follows hostShare (the first pieces
+			// go to them: they are small, and the threads need the head start more than the link does)
+			host = (double)(hostRecs + cnt) <= ctx->hostShare * (double)(lo + cnt) + 0.5 * (double)cnt;
+			if (traceTimes) fprintf(stderr, "[hybrid] piece %d (%zu items) queued at %.2f ms -> %s; share %.3f, link %.1f GB/s, threads %.0f Mrec/s\n", c, cnt,
+			                        sinceMs(), host ? "host" : "device", ctx->hostShare, ctx->d2hRate * 1e-9, hostrec::poolRate(pool) * 1e-6);
+		}
+		// everything of a piece on its own stream, like the pieces of the round-1 pipeline
+		cudaStream_t s = ctx->streams[c % kBinSlots];
+		cudaStream_t so = s;
+		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bStarts.p + lo * v3, (const char *)starts + lo * v3, cnt * v3, cudaMemcpyHostToDevice, s));
+		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bEnds.p + lo * v3, (const char *)ends + lo * v3, cnt * v3, cudaMemcpyHostToDevice, s));
+		if (traceTimes) CUDA_TRY(ctx, cudaEventRecord(uploaded[c], s));
+		TraceBatch q{};
+		q.n = (int)cnt;
+		q.starts = (const float *)ctx->bStarts.p + 3 * lo;
+		q.ends = (const float *)ctx->bEnds.p + 3 * lo;
+		if (mins) { memcpy(q.sharedMins, mins, 12); memcpy(q.sharedMaxs, maxs, 12); }
+		q.sharedMask = mask;
+		q.out = reinterpret_cast<uint2 *>((cmgpu_trace_t *)ctx->bOut.p + lo);
+		q.hitIds = hit_ids && !host ? (int *)ctx->bHit.p + lo : nullptr;
+		q.status = ctx->dStatus;
+		q.counters = ctx->dCounters;
+		wentHost[c] = host;
+		if ((rc = launchTrace(ctx, q, s, lo, c % kBinSlots, false, host ? 1 : 2))) return rc;
+		if (traceTimes) CUDA_TRY(ctx, cudaEventRecord(walked[c], s));
+		CUDA_TRY(ctx, cudaEventRecord(copyStart[c], so));
+		if (host) {
+			outBytes[c] = cnt * 16;
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hCompact + lo * 16, (const char *)ctx->bCompact.p + lo * 16, cnt * 16, cudaMemcpyDeviceToHost, so));
+			CUDA_TRY(ctx, cudaEventRecord(pieceDone[c], so));
+			waits[c] = HybridWait{ctx->device, pieceDone[c]};
+			hostrec::Job job{};
+			job.tables = tables;
+			job.compact = reinterpret_cast<const uint32_t *>(ctx->hCompact);
+			job.starts = starts; job.ends = ends;
+			job.records = results; job.hitIds = hit_ids;
+			job.lo = lo; job.hi = lo + cnt;
+			job.wait = hybridWaitFn; job.waitArg = &waits[c];
+			hostrec::poolSubmit(pool, job);
+			hostRecs += cnt;
+		} else {
+			outBytes[c] = cnt * sizeof(cmgpu_trace_t);
+			if (hit_ids) CUDA_TRY(ctx, cudaMemcpyAsync(hit_ids + lo, (int *)ctx->bHit.p + lo, cnt * 4, cudaMemcpyDeviceToHost, so));
+			CUDA_TRY(ctx, cudaMemcpyAsync(results + lo, (cmgpu_trace_t *)ctx->bOut.p + lo, cnt * sizeof(cmgpu_trace_t), cudaMemcpyDeviceToHost, so));
+			CUDA_TRY(ctx, cudaEventRecord(pieceDone[c], so));
+			devRecs += cnt;
+		}
+		backlogBytes += (double)outBytes[c];
+	}
+	while (oldest < pieces) CUDA_TRY(ctx, harvest(true));
+	for (auto &s : ctx->streams) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	if (traceTimes) fprintf(stderr, "[hybrid] last copy done at %.2f ms\n", sinceMs());
+	if (pool) hostrec::poolWaitAll(pool);
+	if (traceTimes) {
+		fprintf(stderr, "[hybrid] threads done at %.2f ms; %llu records by the host, %llu by the device\n", sinceMs(), hostRecs, devRecs);
+		for (int c = 0; c < pieces; c++) {
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, evBase, uploaded[c]); cudaEventElapsedTime(&b, evBase, walked[c]); cudaEventElapsedTime(&d, evBase, pieceDone[c]);
+			fprintf(stderr, "[hybrid] piece %d %s: uploaded %.2f, walked%s %.2f, results on the host %.2f ms\n", c, wentHost[c] ? "host  " : "device", a, wentHost[c] ? "" : " + expanded", b, d);
+		}
+	}
+	drain.p = nullptr;
+	if (pool && !allHost && ctx->hostRecords < 0) {
+		const double tHost = hostRecs ? hostrec::poolLastDoneMs(pool) : 0.0;
+		double tLink = 0.0;
+		for (int c = 0; c < pieces; c++) {
+			float ms = 0.0f;
+			if (!wentHost[c] && cudaEventElapsedTime(&ms, evBase, pieceDone[c]) == cudaSuccess && ms > tLink) tLink = ms;
+		}
+		const double total = tHost > tLink ? tHost : tLink;
+		if (total > 0.0) {
+			double step = 0.7 * ctx->hostShare * (tLink - tHost) / total;
+			if (!hostRecs) step = 0.05;                      // nothing went to the threads: try a little
+			if (step > 0.1) step = 0.1;
+			if (step < -0.1) step = -0.1;
+			ctx->hostShare += step;
+			if (ctx->hostShare < 0.0) ctx->hostShare = 0.0;
+			if (ctx->hostShare > 1.0) ctx->hostShare = 1.0;
+		}
+		if (traceTimes) fprintf(stderr, "[hybrid] link done at %.2f ms, threads at %.2f ms: share -> %.3f\n", tLink, tHost, ctx->hostShare);
+	}
+	ctx->hostRecordsWritten = hostRecs;
+	ctx->deviceRecordsWritten = devRecs;
+	return cmgpu_check_status(ctx, ctx->streams[0]);
+}
+
 static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
                      const float *mins, const float *maxs, int hull_stride,
                      const int32_t *models, const int32_t *masks, int mask_stride,
@@ -1720,6 +2015,32 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 
 	const size_t N = (size_t)n;
 	const size_t v3 = 3 * sizeof(float);
+	// Big batches of the hot path: the pipeline that shares the records between the link and the host's threads, unless
+	// the plain one has proven faster on this machine (slow or busy host cores).  Both are timed; the first call of each
+	// (allocations, thread start) does not count; the loser is tried again every 32nd call.
+	int timedPipe = -1;
+	const auto tPipe = std::chrono::steady_clock::now();
+	if (hybridEligible(ctx, N, hull_stride, models, mask_stride, origins, boxmins)) {
+		int pipe = 1;
+		if (ctx->hostRecords < 0 && !isPageable(results)) {
+			unsigned *calls = ctx->pipeCalls;
+			if (calls[1] < 2) pipe = 1;
+			else if (calls[0] < 2) pipe = 0;
+			else {
+				pipe = ctx->pipeNs[1] <= ctx->pipeNs[0] ? 1 : 0;
+				if ((calls[0] + calls[1]) % 32 == 0) pipe ^= 1;
+			}
+			timedPipe = pipe;
+		}
+		if (pipe == 1) {
+			rc = traceHostHybrid(ctx, N, starts, ends, mins, maxs, masks[0], results, hit_ids);
+			if (timedPipe == 1 && rc == CMGPU_OK) {
+				const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tPipe).count() / (double)N;
+				if (ctx->pipeCalls[1]++ >= 1) ctx->pipeNs[1] = ctx->pipeCalls[1] == 2 ? ns : 0.5 * ctx->pipeNs[1] + 0.5 * ns;
+			}
+			return rc;
+		}
+	}
 	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
 	if ((rc = reserve(ctx, ctx->bEnds, N * v3))) return rc;
 	if (!mins) hull_stride = 0;
@@ -1827,7 +2148,12 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 		if (hit_ids) CUDA_TRY(ctx, cudaMemcpyAsync(hit_ids + lo, (int *)ctx->bHit.p + lo, cnt * 4, cudaMemcpyDeviceToHost, s));
 	}
 	for (auto &s : ctx->streams) CUDA_TRY(ctx, cudaStreamSynchronize(s));
-	return cmgpu_check_status(ctx, ctx->streams[0]);
+	rc = cmgpu_check_status(ctx, ctx->streams[0]);
+	if (timedPipe == 0 && rc == CMGPU_OK) {
+		const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tPipe).count() / (double)N;
+		if (ctx->pipeCalls[0]++ >= 1) ctx->pipeNs[0] = ctx->pipeCalls[0] == 2 ? ns : 0.5 * ctx->pipeNs[0] + 0.5 * ns;
+	}
+	return rc;
 }
 
 int cmgpu_box_trace_batch(cmgpu_ctx *ctx, int n, const float *starts, const float *ends,
