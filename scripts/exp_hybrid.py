@@ -20,7 +20,7 @@ for spec in ["host_records=0"] + sys.argv[1:]:
     for k, v in opts.items(): eng.set_option(k, v)
     f = lambda: eng.box_trace_hostptr(n, h_s.data_ptr(), h_e.data_ptr(), bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, h_out.data_ptr())
     h_out.zero_()
-    for _ in range(8): f()
+    for _ in range(10): f()
     times = []
     for _ in range(6):
         torch.cuda.synchronize(); t0 = time.perf_counter(); f(); times.append(time.perf_counter() - t0)

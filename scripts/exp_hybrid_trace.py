@@ -14,7 +14,7 @@ h_s = torch.from_numpy(starts).pin_memory(); h_e = torch.from_numpy(ends).pin_me
 for spec in sys.argv[1:]:
     opts = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in spec.split(",")}
     for k, v in opts.items(): eng.set_option(k, v)
-    for i in range(12):
+    for i in range(16):
         sys.stderr.write(f"---- {spec} call {i}\n"); sys.stderr.flush()
         t0 = time.perf_counter()
         eng.box_trace_hostptr(n, h_s.data_ptr(), h_e.data_ptr(), bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, bspgen.MASK_PLAYERSOLID, h_out.data_ptr())

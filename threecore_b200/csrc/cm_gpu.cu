@@ -211,6 +211,12 @@ struct cmgpu_ctx_s {
 	// the share of a batch the threads get: set from the thread count before the first call, then corrected after every
 	// call by who finished later, the link or the threads (both are busy to the end when the share is right)
 	double hostShare = -1.0;
+	int hybridGridEighths = 5;           // "hybrid_grid_eighths": share of the resident CTAs one piece's walk may take
+	int hybridInFlight = 2 * kBinSlots;  // pieces queued ahead of the oldest one whose results are still on their way
+	double hostShareFixed = -1.0;        // "host_share": >= 0 pins the share (experiments)
+	int hybridDecouple = 2;              // "hybrid_decouple": 0 = a piece's upload, walk and result copy on one stream; 1 = uploads on a stream
+	                                     // of their own and result copies on two more (one per kind); 2 = one stream for all result copies
+	cudaStream_t inStream = nullptr, outHostStream = nullptr, outDevStream = nullptr;
 	// big host batches, both pipelines timed (ns per item, running means): [0] = every record over PCIe (round 1), [1] = shared
 	double pipeNs[2] = {0.0, 0.0};
 	unsigned pipeCalls[2] = {0, 0};
@@ -1053,6 +1059,9 @@ int launchTrace(cmgpu_ctx *ctx, TraceBatch q, cudaStream_t s, size_t wsOffset = 
 	const long long warpsWanted = ((long long)q.n + chunk - 1) / chunk;
 	long long blocks = (warpsWanted + (kBlock / 32) - 1) / (kBlock / 32);
 	if (blocks > resident) blocks = resident;
+	// pieces of a host batch: a launch takes only a share of the GPU, so that the next piece's walk (another stream) runs
+	// next to it and fills the SMs while this one's last warps finish their items
+	if (hybrid && ctx->hybridGridEighths < 8 && blocks > (long long)resident * ctx->hybridGridEighths / 8) blocks = (long long)resident * ctx->hybridGridEighths / 8;
 	if (blocks < 1) blocks = 1;
 	cudaEvent_t tEnd = nullptr;
 	if (ctx->timing && !capturing) {
@@ -1330,6 +1339,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	if (ctx->hostPool) hostrec::poolDestroy(ctx->hostPool);
 	if (ctx->hCompact) cudaFreeHost(ctx->hCompact);
 	for (auto &e : ctx->hybridEvents) cudaEventDestroy(e);
+	for (cudaStream_t st : {ctx->inStream, ctx->outHostStream, ctx->outDevStream}) if (st) cudaStreamDestroy(st);
 	releaseBuf(ctx->bAas); releaseBuf(ctx->bAasIn); releaseBuf(ctx->bAasOut);
 	for (auto &r : ctx->hostRegs) cudaHostUnregister((void *)r.first);
 	ctx->hostRegs.clear();
@@ -1414,6 +1424,10 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 		if (t != ctx->hostThreads && ctx->hostPool) { hostrec::poolDestroy(ctx->hostPool); ctx->hostPool = nullptr; }
 		ctx->hostThreads = t;
 	}
+	else if (k == "host_share") ctx->hostShareFixed = value < 0 ? -1.0 : (value > 1 ? 1.0 : value);
+	else if (k == "hybrid_decouple") ctx->hybridDecouple = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
+	else if (k == "hybrid_grid_eighths") ctx->hybridGridEighths = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
+	else if (k == "hybrid_in_flight") ctx->hybridInFlight = value < 1 ? 1 : (int)value;
 	else if (k == "hybrid_min_items") ctx->hybridMinItems = value < 1 ? 1 : (size_t)value;
 	else if (k == "hybrid_walk_items") ctx->hybridWalkItems = value < 98304 ? 98304 : (size_t)value;
 	else if (k == "tiny_calls") ctx->tinyCalls = value != 0;
@@ -1814,6 +1828,13 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		ctx->hostPool = hostrec::poolCreate(t);
 	}
 	hostrec::Pool *pool = ctx->hostRecords == 2 ? nullptr : ctx->hostPool;
+	if (!ctx->inStream) {
+		CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->inStream, cudaStreamNonBlocking));
+		CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->outHostStream, cudaStreamNonBlocking));
+		CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->outDevStream, cudaStreamNonBlocking));
+	}
+	const int decouple = ctx->hybridDecouple;
+	if (ctx->hostShareFixed >= 0.0) ctx->hostShare = ctx->hostShareFixed;
 	if (pool && ctx->hCompactCap < N * 16) {
 		if (ctx->hCompact) { CUDA_TRY(ctx, cudaDeviceSynchronize()); cudaFreeHost(ctx->hCompact); ctx->hCompact = nullptr; ctx->hCompactCap = 0; }
 		const size_t want = N * 16 + N * 2 + 4096;
@@ -1895,7 +1916,7 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		const double Rh = 60e6 * hostrec::poolThreads(pool);
 		ctx->hostShare = 56.0 / (55e9 / Rh + 40.0);
 	}
-	const int inFlight = 2 * kBinSlots;
+	const int inFlight = ctx->hybridInFlight;
 	hostrec::Tables tables{ctx->hostSides.data(), ctx->hostBrushContents.data()};
 	for (int c = 0; c < pieces; c++) {
 		const size_t lo = wb[c], cnt = wb[c + 1] - lo;
@@ -1911,10 +1932,12 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		}
 		// everything of a piece on its own stream, like the pieces of the round-1 pipeline
 		cudaStream_t s = ctx->streams[c % kBinSlots];
-		cudaStream_t so = s;
-		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bStarts.p + lo * v3, (const char *)starts + lo * v3, cnt * v3, cudaMemcpyHostToDevice, s));
-		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bEnds.p + lo * v3, (const char *)ends + lo * v3, cnt * v3, cudaMemcpyHostToDevice, s));
-		if (traceTimes) CUDA_TRY(ctx, cudaEventRecord(uploaded[c], s));
+		cudaStream_t si = decouple ? ctx->inStream : s;
+		cudaStream_t so = decouple == 0 ? s : (decouple == 1 && host ? ctx->outHostStream : ctx->outDevStream);
+		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bStarts.p + lo * v3, (const char *)starts + lo * v3, cnt * v3, cudaMemcpyHostToDevice, si));
+		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bEnds.p + lo * v3, (const char *)ends + lo * v3, cnt * v3, cudaMemcpyHostToDevice, si));
+		if (traceTimes || decouple) CUDA_TRY(ctx, cudaEventRecord(uploaded[c], si));
+		if (decouple) CUDA_TRY(ctx, cudaStreamWaitEvent(s, uploaded[c], 0));
 		TraceBatch q{};
 		q.n = (int)cnt;
 		q.starts = (const float *)ctx->bStarts.p + 3 * lo;
@@ -1927,7 +1950,8 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		q.counters = ctx->dCounters;
 		wentHost[c] = host;
 		if ((rc = launchTrace(ctx, q, s, lo, c % kBinSlots, false, host ? 1 : 2))) return rc;
-		if (traceTimes) CUDA_TRY(ctx, cudaEventRecord(walked[c], s));
+		if (traceTimes || decouple) CUDA_TRY(ctx, cudaEventRecord(walked[c], s));
+		if (decouple) CUDA_TRY(ctx, cudaStreamWaitEvent(so, walked[c], 0));
 		CUDA_TRY(ctx, cudaEventRecord(copyStart[c], so));
 		if (host) {
 			outBytes[c] = cnt * 16;
@@ -1954,6 +1978,7 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	}
 	while (oldest < pieces) CUDA_TRY(ctx, harvest(true));
 	for (auto &s : ctx->streams) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+	if (decouple) for (cudaStream_t st : {ctx->inStream, ctx->outHostStream, ctx->outDevStream}) CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	if (traceTimes) fprintf(stderr, "[hybrid] last copy done at %.2f ms\n", sinceMs());
 	if (pool) hostrec::poolWaitAll(pool);
 	if (traceTimes) {
@@ -1965,7 +1990,7 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		}
 	}
 	drain.p = nullptr;
-	if (pool && !allHost && ctx->hostRecords < 0) {
+	if (pool && !allHost && ctx->hostRecords < 0 && ctx->hostShareFixed < 0.0) {
 		const double tHost = hostRecs ? hostrec::poolLastDoneMs(pool) : 0.0;
 		double tLink = 0.0;
 		for (int c = 0; c < pieces; c++) {
@@ -1974,15 +1999,20 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		}
 		const double total = tHost > tLink ? tHost : tLink;
 		if (total > 0.0) {
-			double step = 0.7 * ctx->hostShare * (tLink - tHost) / total;
+			// The threads are the tail: they got too much.  Otherwise they should be busy ~90 % of the call -- their last
+			// piece arrives when the link delivers it, so finishing together says nothing about whether they could take more.
+			const double util = hostrec::poolBusyMs(pool) / total;
+			double step;
+			if (tHost > 1.03 * tLink && tLink > 0.0) step = 0.7 * ctx->hostShare * (tLink - tHost) / total;
+			else step = 0.5 * (0.85 - util) * (ctx->hostShare > 0.1 ? ctx->hostShare : 0.1);
 			if (!hostRecs) step = 0.05;                      // nothing went to the threads: try a little
-			if (step > 0.1) step = 0.1;
-			if (step < -0.1) step = -0.1;
+			if (step > 0.05) step = 0.05;
+			if (step < -0.08) step = -0.08;
 			ctx->hostShare += step;
 			if (ctx->hostShare < 0.0) ctx->hostShare = 0.0;
 			if (ctx->hostShare > 1.0) ctx->hostShare = 1.0;
 		}
-		if (traceTimes) fprintf(stderr, "[hybrid] link done at %.2f ms, threads at %.2f ms: share -> %.3f\n", tLink, tHost, ctx->hostShare);
+		if (traceTimes) fprintf(stderr, "[hybrid] link done at %.2f ms, threads at %.2f ms (busy %.2f ms): share -> %.3f\n", tLink, tHost, hostrec::poolBusyMs(pool), ctx->hostShare);
 	}
 	ctx->hostRecordsWritten = hostRecs;
 	ctx->deviceRecordsWritten = devRecs;

@@ -178,6 +178,7 @@ private:
 			if (--busy_ == 0) {
 				// a stretch of uninterrupted work ends: fold its rate into the estimate (short stretches say little)
 				const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - busySince_).count();
+				busyMs_ += 1e3 * secs;
 				if (busyRecords_ >= 4 * kSlice && secs > 0) {
 					const double r = (double)busyRecords_ / secs, old = rate_.load(std::memory_order_relaxed);
 					rate_.store(old > 0 ? 0.5 * old + 0.5 * r : r, std::memory_order_relaxed);
@@ -195,12 +196,13 @@ private:
 	}
 
 public:
-	void setEpoch() { std::lock_guard<std::mutex> g(m_); epoch_ = std::chrono::steady_clock::now(); lastDoneMs_ = 0.0; }
+	void setEpoch() { std::lock_guard<std::mutex> g(m_); epoch_ = std::chrono::steady_clock::now(); lastDoneMs_ = 0.0; busyMs_ = 0.0; }
+	double busyMs() { std::lock_guard<std::mutex> g(m_); return busyMs_; }
 	double lastDoneMs() { std::lock_guard<std::mutex> g(m_); return lastDoneMs_; }
 private:
 	double sinceEpochMs() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - epoch_).count(); }
 	std::chrono::steady_clock::time_point epoch_ = std::chrono::steady_clock::now();
-	double lastDoneMs_ = 0.0;
+	double lastDoneMs_ = 0.0, busyMs_ = 0.0;    // since the epoch: when the pool last ran dry; time with at least one slice in progress
 	const bool trace_ = getenv("CMGPU_HYBRID_TRACE") != nullptr;
 	std::mutex m_;
 	std::condition_variable cv_, done_;
@@ -223,5 +225,6 @@ double poolRate(const Pool *p) { return p->rate(); }
 void poolWaitAll(Pool *p) { p->waitAll(); }
 void poolSetEpoch(Pool *p) { p->setEpoch(); }
 double poolLastDoneMs(Pool *p) { return p->lastDoneMs(); }
+double poolBusyMs(Pool *p) { return p->busyMs(); }
 
 }  // namespace hostrec

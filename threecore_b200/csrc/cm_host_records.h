@@ -60,5 +60,7 @@ void poolWaitAll(Pool *p);
 void poolSetEpoch(Pool *p);
 // when the pool last ran out of work, ms after the epoch
 double poolLastDoneMs(Pool *p);
+// time since the epoch during which at least one worker was writing records (call it when the pool is idle)
+double poolBusyMs(Pool *p);
 
 }  // namespace hostrec
