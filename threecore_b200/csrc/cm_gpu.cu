@@ -1797,11 +1797,10 @@ static int traceHostTiny(cmgpu_ctx *ctx, int n, const float *starts, const float
 // The choice is list scheduling with the measured rates of the two resources: the piece goes to whichever of link and
 // workers would be done earlier with everything it has been given so far plus this piece.  Few host cores (eight ranks
 // on one box) => few pieces go to the host; neither side waits for the slower one.
-struct HybridWait { int device; cudaEvent_t ev; };
-static void hybridWaitFn(void *arg) {
-	const HybridWait *w = static_cast<const HybridWait *>(arg);
-	cudaSetDevice(w->device);
-	cudaEventSynchronize(w->ev);
+struct HybridArrival { hostrec::Pool *pool; int ticket; };
+static void CUDART_CB hybridArrived(void *arg) {       // host function behind the copy of a piece's 16-byte results
+	const HybridArrival *a = static_cast<const HybridArrival *>(arg);
+	hostrec::poolRelease(a->pool, a->ticket);
 }
 
 static bool hybridEligible(const cmgpu_ctx *ctx, size_t N, int hull_stride, const int32_t *models, int mask_stride, const float *origins,
@@ -1881,7 +1880,12 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	cudaEvent_t *walked = ctx->hybridEvents.data() + 3 * pieces;
 	const cudaEvent_t evBase = ctx->hybridEvents[4 * (size_t)pieces];
 
-	struct Drain { hostrec::Pool *p; ~Drain() { if (p) hostrec::poolWaitAll(p); } } drain{pool};   // no worker outlives the call
+	// no worker outlives the call: on an early return every held job is released (its host function may never run) and waited for
+	std::vector<HybridArrival> arrivals((size_t)pieces, HybridArrival{nullptr, 0});
+	struct Drain {
+		hostrec::Pool *p; std::vector<HybridArrival> *held;
+		~Drain() { if (!p) return; for (auto &a : *held) if (a.pool) hostrec::poolRelease(a.pool, a.ticket); hostrec::poolWaitAll(p); }
+	} drain{pool, &arrivals};
 	static const bool traceTimes = getenv("CMGPU_HYBRID_TRACE") != nullptr;
 	const auto t0 = std::chrono::steady_clock::now();
 	auto sinceMs = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
@@ -1890,7 +1894,6 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	std::vector<char> wentHost((size_t)pieces, 0);
 
 	std::vector<size_t> outBytes((size_t)pieces, 0);
-	std::vector<HybridWait> waits((size_t)pieces);
 	int oldest = 0;
 	double backlogBytes = 0.0;          // result bytes queued on the link and not yet seen to have arrived
 	unsigned long long hostRecs = 0, devRecs = 0;
@@ -1957,15 +1960,16 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 			outBytes[c] = cnt * 16;
 			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hCompact + lo * 16, (const char *)ctx->bCompact.p + lo * 16, cnt * 16, cudaMemcpyDeviceToHost, so));
 			CUDA_TRY(ctx, cudaEventRecord(pieceDone[c], so));
-			waits[c] = HybridWait{ctx->device, pieceDone[c]};
 			hostrec::Job job{};
 			job.tables = tables;
 			job.compact = reinterpret_cast<const uint32_t *>(ctx->hCompact);
 			job.starts = starts; job.ends = ends;
 			job.records = results; job.hitIds = hit_ids;
 			job.lo = lo; job.hi = lo + cnt;
-			job.wait = hybridWaitFn; job.waitArg = &waits[c];
-			hostrec::poolSubmit(pool, job);
+			job.held = true;
+			arrivals[c] = HybridArrival{pool, hostrec::poolSubmit(pool, job)};
+			// if this fails the job would never run: release it now (the call fails anyway, Drain waits for the workers)
+			if (cudaLaunchHostFunc(so, hybridArrived, &arrivals[c]) != cudaSuccess) { hostrec::poolRelease(pool, arrivals[c].ticket); CUDA_TRY(ctx, cudaGetLastError()); return fail(ctx, CMGPU_ERR_CUDA, "cudaLaunchHostFunc failed"); }
 			hostRecs += cnt;
 		} else {
 			outBytes[c] = cnt * sizeof(cmgpu_trace_t);

@@ -85,7 +85,7 @@ void expand(const Tables &t, const uint32_t *compact, const float *starts, const
 }
 
 // ---- worker threads ----------------------------------------------------------------------------------------------
-// Jobs are released in submission order or not, workers take slices of released jobs front to back.  The pool measures
+// Workers take slices of released jobs front to back and sleep on a condition variable otherwise.  The pool measures
 // its own rate (records per second of wall time while at least one slice is in progress) for the dispatcher's split.
 constexpr size_t kSlice = 16384;
 
@@ -105,19 +105,32 @@ public:
 	}
 	int threads() const { return (int)workers_.size(); }
 
-	void submit(const Job &job) {
+	int submit(const Job &job) {
+		int ticket;
 		{
 			std::lock_guard<std::mutex> g(m_);
 			Entry e;
 			e.job = job;
 			e.next = job.lo;
 			e.left = job.hi > job.lo ? (job.hi - job.lo + kSlice - 1) / kSlice : 0;
-			e.ticket = nextTicket_++;
-			e.released = job.wait == nullptr;
-			if (e.left == 0) return;
+			ticket = e.ticket = nextTicket_++;
+			e.released = !job.held;
+			if (e.left == 0) return ticket;
 			pending_.fetch_add(job.hi - job.lo, std::memory_order_relaxed);
 			jobs_.push_back(e);
 			unfinished_++;
+		}
+		if (!job.held) cv_.notify_all();
+		return ticket;
+	}
+	void release(int ticket) {
+		{
+			std::lock_guard<std::mutex> g(m_);
+			for (auto &e : jobs_) if (e.ticket == ticket) {
+				e.released = true;
+				if (trace_) fprintf(stderr, "[hostrec] job %zu..%zu arrived at %.2f ms\n", e.job.lo, e.job.hi, sinceEpochMs());
+				break;
+			}
 		}
 		cv_.notify_all();
 	}
@@ -133,7 +146,7 @@ private:
 		Job job;
 		size_t next = 0, left = 0;      // first record not yet handed out; slices not yet finished
 		int ticket = 0;
-		bool released = false, waiting = false;
+		bool released = false;
 	};
 	void finishLocked(Entry &) {
 		unfinished_--;
@@ -146,21 +159,6 @@ private:
 			Entry *e = nullptr;
 			for (auto &j : jobs_) if (j.released && j.next < j.job.hi) { e = &j; break; }
 			if (!e) {
-				// nothing runnable: be the one who waits for the arrival of the oldest job that is still on its way
-				Entry *w = nullptr;
-				for (auto &j : jobs_) if (!j.released) { if (!j.waiting) w = &j; break; }
-				if (w) {
-					w->waiting = true;
-					const Job job = w->job;
-					const int ticket = w->ticket;
-					g.unlock();
-					job.wait(job.waitArg);
-					g.lock();
-					if (trace_) fprintf(stderr, "[hostrec] job %zu..%zu arrived at %.2f ms\n", job.lo, job.hi, sinceEpochMs());
-					for (auto &j : jobs_) if (j.ticket == ticket) { j.released = true; break; }
-					cv_.notify_all();
-					continue;
-				}
 				if (quit_) return;
 				cv_.wait(g);
 				continue;
@@ -219,7 +217,8 @@ private:
 Pool *poolCreate(int threads) { return new Pool(threads); }
 void poolDestroy(Pool *p) { delete p; }
 int poolThreads(const Pool *p) { return p->threads(); }
-void poolSubmit(Pool *p, const Job &job) { p->submit(job); }
+int poolSubmit(Pool *p, const Job &job) { return p->submit(job); }
+void poolRelease(Pool *p, int ticket) { p->release(ticket); }
 size_t poolPendingRecords(const Pool *p) { return p->pendingRecords(); }
 double poolRate(const Pool *p) { return p->rate(); }
 void poolWaitAll(Pool *p) { p->waitAll(); }

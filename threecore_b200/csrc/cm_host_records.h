@@ -42,14 +42,14 @@ struct Job {
 	void *records;
 	int32_t *hitIds;
 	size_t lo, hi;
-	// The job's 16-byte results are still on their way when it is queued: the first idle worker calls wait(waitArg),
-	// which blocks until they have arrived (a cudaEventSynchronize); then the job's slices are handed out.  null: runnable.
-	void (*wait)(void *);
-	void *waitArg;
+	// held: the job's 16-byte results are still on their way when it is queued; poolRelease(ticket) makes it runnable
+	// (called from a CUDA host function behind the copy: the workers themselves never touch the CUDA API)
+	bool held;
 };
 
-// Queue a job; jobs are taken up in the order they were queued.
-void poolSubmit(Pool *p, const Job &job);
+// Queue a job (returns its ticket); released jobs are taken up in the order they were queued.
+int poolSubmit(Pool *p, const Job &job);
+void poolRelease(Pool *p, int ticket);
 // records queued or being written, over all jobs
 size_t poolPendingRecords(const Pool *p);
 // measured rate of the whole pool, records per second (0 until a job has run)
