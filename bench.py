@@ -255,7 +255,8 @@ def arm_host_copy_ceiling(dev, world, n, h_starts, h_ends, h_out, d_starts, d_en
 
 def arm_e2e_pageable(eng, dev, world, n, starts, ends, steps=2):
     """The host-pointer call on plain malloc'ed arrays (what a caller that never heard of CUDA passes): as they are (the
-    driver stages every copy and blocks, nothing overlaps), and after cmgpu_host_register of the same three arrays."""
+    context's worker threads copy the rays into pinned memory piece by piece and write every record themselves; round 1:
+    the driver staged every copy and nothing overlapped), and after cmgpu_host_register of the same three arrays."""
     out = np.empty((n, 56), np.uint8)
 
     def step():
@@ -277,7 +278,7 @@ def arm_e2e_pageable(eng, dev, world, n, starts, ends, steps=2):
     res["registered"] = timed(steps)
     for a in (starts, ends, out):
         eng.host_unregister(a.ctypes.data)
-    res["what"] = ("cmgpu_box_trace_batch on numpy (pageable) arrays: `unregistered` = as they are, `registered` = after "
+    res["what"] = ("cmgpu_box_trace_batch on numpy (pageable) arrays: `unregistered` = as they are (rays staged and records written by the context's threads), `registered` = after "
                    "cmgpu_host_register of rays and results (one-time cost register_ms_once)")
     return res, out
 

@@ -206,6 +206,8 @@ int cmgpu_host_unregister(cmgpu_ctx *ctx, const void *ptr);
  *   cmgpu_set_option("host_records", v): -1 = as described (default), 0 = off: every record is written by the device
  *       (the round-1 pipeline), 1 = every record by the threads, 2 = the new pipeline with every record by the device.
  *   cmgpu_set_option("host_threads", t): worker threads; -1 (default) = host cores / visible GPUs - 1.
+ *   cmgpu_set_option("stage_pageable", 0): pageable start / end arrays of such a batch are uploaded as they are (staged by
+ *       the driver, blocking) instead of being copied into pinned memory of the context by the threads, a piece ahead.
  * cmgpu_last_batch_split: how many records of the last such call each side wrote. */
 int cmgpu_last_batch_split(const cmgpu_ctx *ctx, unsigned long long *by_host, unsigned long long *by_device);
 

@@ -207,6 +207,9 @@ struct cmgpu_ctx_s {
 	std::vector<int32_t> hostBrushContents;          // [numBrushes + 1], entry 0 = no brush
 	char *hCompact = nullptr;            // pinned: where the 16-byte results land
 	size_t hCompactCap = 0;
+	float *hStage = nullptr;             // pinned: pageable starts / ends on their way up (the threads copy, the link uploads)
+	size_t hStageCap = 0;
+	bool stagePageable = true;           // "stage_pageable"
 	std::vector<cudaEvent_t> hybridEvents;
 	// the share of a batch the threads get: set from the thread count before the first call, then corrected after every
 	// call by who finished later, the link or the threads (both are busy to the end when the share is right)
@@ -1338,6 +1341,7 @@ void cmgpu_destroy(cmgpu_ctx *ctx) {
 	if (ctx->tinyHost) cudaFreeHost(ctx->tinyHost);
 	if (ctx->hostPool) hostrec::poolDestroy(ctx->hostPool);
 	if (ctx->hCompact) cudaFreeHost(ctx->hCompact);
+	if (ctx->hStage) cudaFreeHost(ctx->hStage);
 	for (auto &e : ctx->hybridEvents) cudaEventDestroy(e);
 	for (cudaStream_t st : {ctx->inStream, ctx->outHostStream, ctx->outDevStream}) if (st) cudaStreamDestroy(st);
 	releaseBuf(ctx->bAas); releaseBuf(ctx->bAasIn); releaseBuf(ctx->bAasOut);
@@ -1424,6 +1428,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 		if (t != ctx->hostThreads && ctx->hostPool) { hostrec::poolDestroy(ctx->hostPool); ctx->hostPool = nullptr; }
 		ctx->hostThreads = t;
 	}
+	else if (k == "stage_pageable") ctx->stagePageable = value != 0;
 	else if (k == "host_share") ctx->hostShareFixed = value < 0 ? -1.0 : (value > 1 ? 1.0 : value);
 	else if (k == "hybrid_decouple") ctx->hybridDecouple = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
 	else if (k == "hybrid_grid_eighths") ctx->hybridGridEighths = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
@@ -1854,6 +1859,17 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	autoRegister(ctx, starts, N * v3);
 	autoRegister(ctx, ends, N * v3);
 	autoRegister(ctx, results, N * sizeof(cmgpu_trace_t));
+	// Pageable start / end arrays: an upload straight from them is staged by the driver, one blocking copy at a time.  The
+	// threads copy a piece ahead into pinned memory instead, and the link uploads from there.
+	const bool stage = pool && ctx->stagePageable && N * 24 <= ((size_t)1 << 30) &&
+	                   (isPageable(starts) || isPageable(ends) || isPageable((const char *)(starts + 3 * N) - 1) || isPageable((const char *)(ends + 3 * N) - 1));
+	if (stage && ctx->hStageCap < N * 24) {
+		if (ctx->hStage) { CUDA_TRY(ctx, cudaDeviceSynchronize()); cudaFreeHost(ctx->hStage); ctx->hStage = nullptr; ctx->hStageCap = 0; }
+		const size_t want = N * 24 + N * 3 + 4096;
+		CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->hStage, want, cudaHostAllocDefault));
+		ctx->hStageCap = want;
+	}
+	const float *upStarts = stage ? ctx->hStage : starts, *upEnds = stage ? ctx->hStage + 3 * N : ends;
 	// a pageable result array is written by the CPU anyway (a copy into it would be staged by the driver, and block)
 	const bool allHost = pool && (ctx->hostRecords == 1 || isPageable(results) || isPageable((const char *)(results + N) - 1));
 
@@ -1921,8 +1937,22 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	}
 	const int inFlight = ctx->hybridInFlight;
 	hostrec::Tables tables{ctx->hostSides.data(), ctx->hostBrushContents.data()};
+	std::vector<int> stageTicket((size_t)pieces, 0);
+	auto stagePiece = [&](int c) {
+		if (!stage || c >= pieces || stageTicket[c]) return;
+		hostrec::Job job{};
+		job.starts = starts; job.ends = ends;
+		job.stageStarts = ctx->hStage; job.stageEnds = ctx->hStage + 3 * N;
+		job.lo = wb[c]; job.hi = wb[c + 1];
+		stageTicket[c] = hostrec::poolSubmit(pool, job);
+	};
 	for (int c = 0; c < pieces; c++) {
 		const size_t lo = wb[c], cnt = wb[c + 1] - lo;
+		if (stage) {
+			stagePiece(c);
+			stagePiece(c + 1);                                  // one piece ahead of the upload
+			hostrec::poolWaitJob(pool, stageTicket[c]);
+		}
 		CUDA_TRY(ctx, harvest(false));
 		while (c - oldest >= inFlight) CUDA_TRY(ctx, harvest(true));
 		bool host = allHost;
@@ -1937,8 +1967,8 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		cudaStream_t s = ctx->streams[c % kBinSlots];
 		cudaStream_t si = decouple ? ctx->inStream : s;
 		cudaStream_t so = decouple == 0 ? s : (decouple == 1 && host ? ctx->outHostStream : ctx->outDevStream);
-		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bStarts.p + lo * v3, (const char *)starts + lo * v3, cnt * v3, cudaMemcpyHostToDevice, si));
-		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bEnds.p + lo * v3, (const char *)ends + lo * v3, cnt * v3, cudaMemcpyHostToDevice, si));
+		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bStarts.p + lo * v3, (const char *)upStarts + lo * v3, cnt * v3, cudaMemcpyHostToDevice, si));
+		CUDA_TRY(ctx, cudaMemcpyAsync((char *)ctx->bEnds.p + lo * v3, (const char *)upEnds + lo * v3, cnt * v3, cudaMemcpyHostToDevice, si));
 		if (traceTimes || decouple) CUDA_TRY(ctx, cudaEventRecord(uploaded[c], si));
 		if (decouple) CUDA_TRY(ctx, cudaStreamWaitEvent(s, uploaded[c], 0));
 		TraceBatch q{};

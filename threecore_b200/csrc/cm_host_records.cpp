@@ -134,6 +134,13 @@ public:
 		}
 		cv_.notify_all();
 	}
+	void waitJob(int ticket) {
+		std::unique_lock<std::mutex> g(m_);
+		done_.wait(g, [&] {
+			for (auto &j : jobs_) if (j.ticket == ticket) return j.left == 0;
+			return true;                                    // no longer queued: done
+		});
+	}
 	size_t pendingRecords() const { return pending_.load(std::memory_order_relaxed); }
 	double rate() const { return rate_.load(std::memory_order_relaxed); }
 	void waitAll() {
@@ -151,7 +158,8 @@ private:
 	void finishLocked(Entry &) {
 		unfinished_--;
 		while (!jobs_.empty() && jobs_.front().left == 0 && jobs_.front().released) jobs_.pop_front();
-		if (unfinished_ == 0) { lastDoneMs_ = sinceEpochMs(); done_.notify_all(); }
+		if (unfinished_ == 0) lastDoneMs_ = sinceEpochMs();
+		done_.notify_all();
 	}
 	void run() {
 		std::unique_lock<std::mutex> g(m_);
@@ -169,7 +177,12 @@ private:
 			const int ticket = e->ticket;
 			if (busy_++ == 0) busySince_ = std::chrono::steady_clock::now();
 			g.unlock();
-			expand(job.tables, job.compact, job.starts, job.ends, job.records, job.hitIds, lo, hi);
+			if (job.stageStarts) {
+				memcpy(job.stageStarts + 3 * lo, job.starts + 3 * lo, 12 * (hi - lo));
+				memcpy(job.stageEnds + 3 * lo, job.ends + 3 * lo, 12 * (hi - lo));
+			} else {
+				expand(job.tables, job.compact, job.starts, job.ends, job.records, job.hitIds, lo, hi);
+			}
 			pending_.fetch_sub(hi - lo, std::memory_order_relaxed);
 			g.lock();
 			busyRecords_ += hi - lo;
@@ -219,6 +232,7 @@ void poolDestroy(Pool *p) { delete p; }
 int poolThreads(const Pool *p) { return p->threads(); }
 int poolSubmit(Pool *p, const Job &job) { return p->submit(job); }
 void poolRelease(Pool *p, int ticket) { p->release(ticket); }
+void poolWaitJob(Pool *p, int ticket) { p->waitJob(ticket); }
 size_t poolPendingRecords(const Pool *p) { return p->pendingRecords(); }
 double poolRate(const Pool *p) { return p->rate(); }
 void poolWaitAll(Pool *p) { p->waitAll(); }

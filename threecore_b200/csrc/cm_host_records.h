@@ -45,11 +45,16 @@ struct Job {
 	// held: the job's 16-byte results are still on their way when it is queued; poolRelease(ticket) makes it runnable
 	// (called from a CUDA host function behind the copy: the workers themselves never touch the CUDA API)
 	bool held;
+	// A staging job instead: items [lo, hi) of the caller's pageable start / end arrays are copied into pinned memory
+	// (stageStarts / stageEnds non-null; tables, compact, records unused), for the upload that follows.
+	float *stageStarts, *stageEnds;
 };
 
 // Queue a job (returns its ticket); released jobs are taken up in the order they were queued.
 int poolSubmit(Pool *p, const Job &job);
 void poolRelease(Pool *p, int ticket);
+// block until this job has been done
+void poolWaitJob(Pool *p, int ticket);
 // records queued or being written, over all jobs
 size_t poolPendingRecords(const Pool *p);
 // measured rate of the whole pool, records per second (0 until a job has run)
