@@ -1900,7 +1900,13 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	std::vector<HybridArrival> arrivals((size_t)pieces, HybridArrival{nullptr, 0});
 	struct Drain {
 		hostrec::Pool *p; std::vector<HybridArrival> *held;
-		~Drain() { if (!p) return; for (auto &a : *held) if (a.pool) hostrec::poolRelease(a.pool, a.ticket); hostrec::poolWaitAll(p); }
+		~Drain() {
+			if (!p) return;
+			cudaDeviceSynchronize();                         // no host function of this call may fire after `held` is gone
+			cudaGetLastError();
+			for (auto &a : *held) if (a.pool) hostrec::poolRelease(a.pool, a.ticket);
+			hostrec::poolWaitAll(p);
+		}
 	} drain{pool, &arrivals};
 	static const bool traceTimes = getenv("CMGPU_HYBRID_TRACE") != nullptr;
 	const auto t0 = std::chrono::steady_clock::now();
