@@ -34,6 +34,7 @@ for spec in ["base"] + sys.argv[1:] + ["base"]:
     ms = a.elapsed_time(b) / 5
     same = "" if ref is None else f" same={bool(torch.equal(out, ref))}"
     if ref is None: ref = out.clone()
-    print(f"{spec:40s} step {ms:.3f} ms  {n / ms / 1e3:.0f} Mtraces/s   kernels {kms / kn:.3f} ms{same}", flush=True)
+    chk = int(out.view(torch.int64).sum().item()) & 0xffffffffffff
+    print(f"{spec:40s} step {ms:.3f} ms  {n / ms / 1e3:.0f} Mtraces/s   kernels {kms / kn:.3f} ms{same} checksum {chk:012x}", flush=True)
     for k in opts:                              # back to the defaults given on the command line as D:k=v
         eng.set_option(k, float(os.environ.get("D_" + k, "nan"))) if ("D_" + k) in os.environ else None

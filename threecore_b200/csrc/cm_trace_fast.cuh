@@ -27,6 +27,12 @@
 
 #include "cm_kernels.cuh"
 
+#ifndef CMGPU_SLAB_F32X2
+#define CMGPU_SLAB_F32X2 0
+#endif
+#ifndef CMGPU_SLAB_UNCOND
+#define CMGPU_SLAB_UNCOND 0
+#endif
 namespace cmgpu {
 
 struct FastMap {
@@ -185,6 +191,31 @@ __device__ __forceinline__ bool slabRejectPre(const SlabItem &t, const float4 e0
 	const float tLeave = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
 	return tEnter > 0.0f && ((tEnter > tLeave && tLeave < 1.0f) || tEnter > t.fraction);
 }
+
+#if CMGPU_SLAB_F32X2
+// the same test with the six subtractions and six products as three packed pairs (sub.f32x2 / mul.f32x2, sm_100: each
+// half rounds like the scalar operation)
+__device__ __forceinline__ unsigned long long pack2(const float a, const float b) {
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+	return r;
+}
+__device__ __forceinline__ void mulsub2(const float a0, const float a1, const float b0, const float b1, const float m, float &r0, float &r1) {
+	unsigned long long d;
+	asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a0, a1)), "l"(pack2(b0, b1)));
+	asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(d), "l"(pack2(m, m)));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(d));
+}
+__device__ __forceinline__ bool slabRejectPre2(const SlabItem &t, const float4 e0, const float4 e1) {
+	float x0, x1, y0, y1, z0, z1;
+	mulsub2(e0.x, e1.x, t.lx, t.hx, t.ix, x0, x1);
+	mulsub2(e0.y, e1.y, t.ly, t.hy, t.iy, y0, y1);
+	mulsub2(e0.z, e1.z, t.lz, t.hz, t.iz, z0, z1);
+	const float tEnter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+	const float tLeave = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+	return tEnter > 0.0f && ((tEnter > tLeave && tLeave < 1.0f) || tEnter > t.fraction);
+}
+#endif
 
 struct Sweep { float sx, sy, sz, ex, ey, ez; };
 struct EnterLeave { float enter, leave; int lead; };

@@ -460,7 +460,17 @@ tracePoolKernel(const FastMap fm, const TraceBatch q, const FastHull h) {
 						const bool apart = hix < e0[i].x || hiy < e0[i].y || hiz < e0[i].z || lox > e1[i].x || loy > e1[i].y || loz > e1[i].z;
 #if CMGPU_INLINE_SLAB
 						bool clipi = want && !apart;                                   // CM_BoundsIntersect passed
-#if CMGPU_SLAB_HOIST
+#if CMGPU_SLAB_HOIST && CMGPU_SLAB_UNCOND
+						// every lane runs the test on every entry (a warp skips it only when no lane has a candidate, which
+						// hardly ever happens): no divergent region per entry
+#if CMGPU_SLAB_F32X2
+						if (slabRejectPre2(S, e0[i], e1[i]) && slabOn) clipi = false;
+#else
+						if (slabRejectPre(S, e0[i], e1[i]) && slabOn) clipi = false;
+#endif
+#elif CMGPU_SLAB_HOIST && CMGPU_SLAB_F32X2
+						if (!stopped && clipi && slabOn && slabRejectPre2(S, e0[i], e1[i])) clipi = false;
+#elif CMGPU_SLAB_HOIST
 						if (!stopped && clipi && slabOn && slabRejectPre(S, e0[i], e1[i])) clipi = false;
 #else
 						if (!stopped && clipi && slabOn && slabReject(h, S, e0[i], e1[i])) clipi = false;
