@@ -580,9 +580,9 @@ def run_ours(args):
         return world * n * e2e_steps / float(tt.item()) / 1e6
 
     # The call as shipped: a big batch's records are shared between the link and the host's threads (cm_gpu.h,
-    # "host_records" -1).  The call tries both of its pipelines before it settles (two calls each, the first of each
-    # uncounted), so it gets six untimed calls here; the plain pipeline alone (every record over PCIe) is timed next to it.
-    e2e_value = e2e_timed(max(6, min(args.warmup, 8)))
+    # "host_records" -1).  The call tries both of its pipelines before it settles (four calls and two, the first of each
+    # uncounted), so it gets eight untimed calls here; the plain pipeline alone (every record over PCIe) is timed next to it.
+    e2e_value = e2e_timed(max(8, min(args.warmup, 10)))
     split = eng.last_batch_split()
     e2e_split = {"records_by_host_threads": split[0], "records_by_device": split[1]}
     same_shared = bool(torch.equal(h_out[: 1 << 16], d_out[: 1 << 16].cpu()))
