@@ -2039,12 +2039,13 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		}
 		const double total = tHost > tLink ? tHost : tLink;
 		if (total > 0.0) {
-			// The threads are the tail: they got too much.  Otherwise they should be busy ~90 % of the call -- their last
-			// piece arrives when the link delivers it, so finishing together says nothing about whether they could take more.
+			// The threads are the tail: they got too much.  Otherwise they should be busy ~72 % of the call (measured: beyond
+			// that every fourth call ends with the threads as the tail) -- their last piece arrives when the link delivers
+			// it, so finishing together says nothing about whether they could take more.
 			const double util = hostrec::poolBusyMs(pool) / total;
 			double step;
 			if (tHost > 1.03 * tLink && tLink > 0.0) step = 0.7 * ctx->hostShare * (tLink - tHost) / total;
-			else step = 0.5 * (0.85 - util) * (ctx->hostShare > 0.1 ? ctx->hostShare : 0.1);
+			else step = 0.5 * (0.72 - util) * (ctx->hostShare > 0.1 ? ctx->hostShare : 0.1);
 			if (!hostRecs) step = 0.05;                      // nothing went to the threads: try a little
 			if (step > 0.05) step = 0.05;
 			if (step < -0.08) step = -0.08;
