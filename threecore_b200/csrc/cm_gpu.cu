@@ -2089,7 +2089,7 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	// Big batches of the hot path: the pipeline that shares the records between the link and the host's threads, unless
 	// the plain one has proven faster on this machine (slow or busy host cores).  Both are timed -- the shared one over
 	// its first four calls (its share is still settling), the plain one over two; the first call of each (allocations,
-	// thread start) does not count; the score is the best recent call; the loser is tried again every 32nd call.
+	// thread start) does not count; the score is a running mean that halves the past with every call; the loser is tried again every 32nd call.
 	int timedPipe = -1;
 	const auto tPipe = std::chrono::steady_clock::now();
 	if (hybridEligible(ctx, N, hull_stride, models, mask_stride, origins, boxmins)) {
@@ -2103,14 +2103,14 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 				if ((calls[0] + calls[1]) % 32 == 0) pipe ^= 1;
 			}
 			timedPipe = pipe;
-			if (getenv("CMGPU_HYBRID_TRACE")) fprintf(stderr, "[pipe] %s pipeline; best recent: shared %.3f ns/item (%u calls), plain %.3f (%u)\n", pipe ? "shared" : "plain",
+			if (getenv("CMGPU_HYBRID_TRACE")) fprintf(stderr, "[pipe] %s pipeline; running means: shared %.3f ns/item (%u calls), plain %.3f (%u)\n", pipe ? "shared" : "plain",
 			                                          ctx->pipeNs[1], calls[1], ctx->pipeNs[0], calls[0]);
 		}
 		if (pipe == 1) {
 			rc = traceHostHybrid(ctx, N, starts, ends, mins, maxs, masks[0], results, hit_ids);
 			if (timedPipe == 1 && rc == CMGPU_OK) {
 				const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tPipe).count() / (double)N;
-				if (ctx->pipeCalls[1]++ >= 1) ctx->pipeNs[1] = ctx->pipeCalls[1] == 2 || ns < 1.02 * ctx->pipeNs[1] ? ns : 1.02 * ctx->pipeNs[1];
+				if (ctx->pipeCalls[1]++ >= 1) ctx->pipeNs[1] = ctx->pipeCalls[1] == 2 ? ns : 0.5 * ctx->pipeNs[1] + 0.5 * ns;
 			}
 			return rc;
 		}
@@ -2225,7 +2225,7 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 	rc = cmgpu_check_status(ctx, ctx->streams[0]);
 	if (timedPipe == 0 && rc == CMGPU_OK) {
 		const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tPipe).count() / (double)N;
-		if (ctx->pipeCalls[0]++ >= 1) ctx->pipeNs[0] = ctx->pipeCalls[0] == 2 || ns < 1.02 * ctx->pipeNs[0] ? ns : 1.02 * ctx->pipeNs[0];
+		if (ctx->pipeCalls[0]++ >= 1) ctx->pipeNs[0] = ctx->pipeCalls[0] == 2 ? ns : 0.5 * ctx->pipeNs[0] + 0.5 * ns;
 	}
 	return rc;
 }
