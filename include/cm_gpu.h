@@ -218,6 +218,11 @@ int cmgpu_last_batch_split(const cmgpu_ctx *ctx, unsigned long long *by_host, un
 int cmgpu_format_records(int n, const uint32_t *results16, const float *starts, const float *ends,
                          int num_sides, const float *side_planes, const int32_t *side_type_signbits, const int32_t *side_surface_flags,
                          int num_brushes, const int32_t *brush_contents, cmgpu_trace_t *records, int32_t *hit_ids);
+/* The same through the worker pool of a big host batch, driven the way cmgpu_box_trace_batch drives it (sweeps staged a piece
+ * ahead, one held job per piece, released out of order): what the CPU tests use to exercise the pool without a device. */
+int cmgpu_format_records_threads(int threads, int n, const uint32_t *results16, const float *starts, const float *ends,
+                                 int num_sides, const float *side_planes, const int32_t *side_type_signbits, const int32_t *side_surface_flags,
+                                 int num_brushes, const int32_t *brush_contents, cmgpu_trace_t *records, int32_t *hit_ids);
 
 /* ---- batched queries, DEVICE pointers (inputs resident in HBM) -----------
  * Same meaning as above; per-item arrays are device pointers on the context's

@@ -70,6 +70,24 @@ def test_formatter_rebuilds_the_reference_records(kind):
     assert rc == 0 and np.array_equal(buf[4:].reshape(-1, 56), b)
 
 
+def test_worker_pool_stages_and_formats_like_the_single_thread():
+    """the pool of a big host batch without a device: staged sweeps, held jobs released out of order, 1 to 7 threads"""
+    m = get_map("arena_small")
+    flat = engine.FlatMap.from_bsp(m.data).to_dict()
+    n = 230001
+    starts, ends = bspgen.make_sweeps(m, n, seed=47)
+    chk = cmoracle.OracleCM(flat)
+    want = chk.box_trace(starts[:40000], ends[:40000], bspgen.PLAYER_MINS, bspgen.PLAYER_MAXS, mask=bspgen.MASK_PLAYERSOLID)
+    planes, ts, sflags, contents = side_tables(flat)
+    r16 = np.tile(results16_from_records(want, planes, ts, sflags, contents), (6, 1))[:n]
+    one = engine.format_records(r16, starts, ends, planes, ts, sflags, contents)
+    assert np.array_equal(np.ascontiguousarray(one[:40000]).view(np.uint8), np.ascontiguousarray(want).view(np.uint8))
+    for threads in (1, 3, 7):
+        got, hit = engine.format_records(r16, starts, ends, planes, ts, sflags, contents, want_hit=True, threads=threads)
+        assert np.array_equal(np.ascontiguousarray(got).view(np.uint8), np.ascontiguousarray(one).view(np.uint8)), threads
+        assert np.array_equal(hit, r16[:, 3].view(np.int32))
+
+
 def test_formatter_refuses_indices_outside_the_tables():
     r16 = np.array([[0x3f800000, 0, 5, 0xffffffff]], dtype=np.uint32)
     z = np.zeros((1, 3), np.float32)

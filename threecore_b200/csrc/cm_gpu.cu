@@ -1593,6 +1593,53 @@ int cmgpu_format_records(int n, const uint32_t *results16, const float *starts, 
 	return CMGPU_OK;
 }
 
+int cmgpu_format_records_threads(int threads, int n, const uint32_t *results16, const float *starts, const float *ends,
+                                 int num_sides, const float *side_planes, const int32_t *side_type_signbits, const int32_t *side_surface_flags,
+                                 int num_brushes, const int32_t *brush_contents, cmgpu_trace_t *records, int32_t *hit_ids) {
+	// the same through the worker pool of a big host batch, the way traceHostHybrid drives it: the sweeps are staged into a
+	// scratch copy a piece ahead, every piece's job is queued held and released later (here: by this thread, last piece first)
+	if (threads < 1 || n < 0 || num_sides < 0 || num_brushes < 0 || (n > 0 && (!results16 || !starts || !ends || !records))) return CMGPU_ERR_INVALID;
+	if ((num_sides > 0 && (!side_planes || !side_type_signbits || !side_surface_flags)) || (num_brushes > 0 && !brush_contents)) return CMGPU_ERR_INVALID;
+	for (int i = 0; i < n; i++) {
+		const int32_t side = (int32_t)results16[4 * (size_t)i + 2], brush = (int32_t)results16[4 * (size_t)i + 3];
+		if (side < -1 || side >= num_sides || brush < -1 || brush >= num_brushes) return CMGPU_ERR_INVALID;
+	}
+	std::vector<hostrec::SideRec> sides((size_t)num_sides + 1, hostrec::SideRec{});
+	std::vector<int32_t> contents((size_t)num_brushes + 1, 0);
+	for (int i = 0; i < num_sides; i++) {
+		hostrec::SideRec &r = sides[(size_t)i + 1];
+		memcpy(r.plane, side_planes + 4 * (size_t)i, 16);
+		r.typeSignbits = (uint32_t)side_type_signbits[i] & 0xffffu;
+		r.surfaceFlags = (uint32_t)side_surface_flags[i];
+	}
+	for (int i = 0; i < num_brushes; i++) contents[(size_t)i + 1] = brush_contents[i];
+	const size_t N = (size_t)n, piece = 50000;
+	std::vector<float> stagedStarts(3 * N + 1), stagedEnds(3 * N + 1);
+	hostrec::Pool *pool = hostrec::poolCreate(threads);
+	hostrec::poolSetEpoch(pool);
+	std::vector<int> tickets;
+	for (size_t lo = 0; lo < N; lo += piece) {
+		const size_t hi = lo + piece < N ? lo + piece : N;
+		hostrec::Job st{};
+		st.starts = starts; st.ends = ends; st.stageStarts = stagedStarts.data(); st.stageEnds = stagedEnds.data();
+		st.lo = lo; st.hi = hi;
+		hostrec::poolWaitJob(pool, hostrec::poolSubmit(pool, st));
+		hostrec::Job job{};
+		job.tables = hostrec::Tables{sides.data(), contents.data()};
+		job.compact = results16;
+		job.starts = stagedStarts.data(); job.ends = stagedEnds.data();      // the staged copies: both jobs are checked by the result
+		job.records = records; job.hitIds = hit_ids;
+		job.lo = lo; job.hi = hi;
+		job.held = true;
+		tickets.push_back(hostrec::poolSubmit(pool, job));
+	}
+	for (size_t k = tickets.size(); k-- > 0;) hostrec::poolRelease(pool, tickets[k]);
+	hostrec::poolWaitAll(pool);
+	const bool idle = hostrec::poolPendingRecords(pool) == 0;
+	hostrec::poolDestroy(pool);
+	return idle ? CMGPU_OK : CMGPU_ERR_INVALID;
+}
+
 int cmgpu_last_batch_split(const cmgpu_ctx *ctx, unsigned long long *by_host, unsigned long long *by_device) {
 	if (!ctx) return CMGPU_ERR_INVALID;
 	if (by_host) *by_host = ctx->hostRecordsWritten;

@@ -158,6 +158,7 @@ def load_library() -> C.CDLL:
     lib.cmgpu_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
     lib.cmgpu_last_batch_split.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.cmgpu_format_records.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3
+    lib.cmgpu_format_records_threads.argtypes = [C.c_int] + lib.cmgpu_format_records.argtypes
     lib.cmgpu_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     lib.cmgpu_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.cmgpu_enable_counters.argtypes = [C.c_void_p, C.c_int]
@@ -300,8 +301,10 @@ def _f(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
 
 
-def format_records(results16, starts, ends, side_planes, side_type_signbits, side_surface_flags, brush_contents, want_hit=False):
-    """cmgpu_format_records: the host threads' record formatter on its own (no device).  results16: uint32 [n][4]."""
+def format_records(results16, starts, ends, side_planes, side_type_signbits, side_surface_flags, brush_contents, want_hit=False,
+                   threads=0):
+    """cmgpu_format_records: the host threads' record formatter on its own (no device).  results16: uint32 [n][4].
+    threads > 0: through the worker pool (cmgpu_format_records_threads)."""
     lib = load_library()
     r16 = np.ascontiguousarray(results16, dtype=np.uint32).reshape(-1, 4)
     n = r16.shape[0]
@@ -309,7 +312,8 @@ def format_records(results16, starts, ends, side_planes, side_type_signbits, sid
     sp, st, sf, bc = _f(side_planes), _i(side_type_signbits), _i(side_surface_flags), _i(brush_contents)
     out = np.zeros(n, dtype=TRACE_DTYPE)
     hit = np.zeros(n, dtype=np.int32) if want_hit else None
-    rc = lib.cmgpu_format_records(n, _p(r16), _p(starts), _p(ends), len(st), _p(sp), _p(st), _p(sf), len(bc), _p(bc), _p(out), _p(hit))
+    args = (n, _p(r16), _p(starts), _p(ends), len(st), _p(sp), _p(st), _p(sf), len(bc), _p(bc), _p(out), _p(hit))
+    rc = lib.cmgpu_format_records_threads(int(threads), *args) if threads else lib.cmgpu_format_records(*args)
     if rc:
         raise CMGPUError(rc, "cmgpu_format_records: bad argument or index out of range")
     return (out, hit) if want_hit else out
