@@ -204,7 +204,8 @@ int cmgpu_host_unregister(cmgpu_ctx *ctx, const void *ptr);
  * same float operations in the same order -- formatting, not tracing).  The split follows the measured rates of the link
  * and of the threads.  A pageable result array is written by the threads only.
  *   cmgpu_set_option("host_records", v): -1 = as described (default), 0 = off: every record is written by the device
- *       (the round-1 pipeline), 1 = every record by the threads, 2 = the new pipeline with every record by the device.
+ *       (the round-1 pipeline), 1 = every record by the threads, 2 = the new pipeline with every record by the device,
+ *       3 = the new pipeline with the measured share even where the plain one has measured faster.
  *   cmgpu_set_option("host_threads", t): worker threads; -1 (default) = host cores / visible GPUs - 1.
  *   cmgpu_set_option("stage_pageable", 0): pageable start / end arrays of such a batch are uploaded as they are (staged by
  *       the driver, blocking) instead of being copied into pinned memory of the context by the threads, a piece ahead.

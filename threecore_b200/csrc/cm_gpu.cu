@@ -199,7 +199,8 @@ struct cmgpu_ctx_s {
 	// Host half of a big host batch's results (traceHostHybrid, cm_host_records.h): a share of the pieces comes back as the
 	// walk's 16-byte results and the calling process's worker threads write the 56-byte records from them.
 	int hostRecords = -1;                // "host_records": -1 = the split follows the measured rates, 0 = off (every record over
-	                                     // PCIe), 1 = every record written by the host, 2 = the new pipeline with no host share
+	                                     // PCIe), 1 = every record written by the host, 2 = the new pipeline with no host share,
+	                                     // 3 = the new pipeline with the measured share, whatever the plain one would do
 	int hostThreads = -1;                // "host_threads": -1 = host cores per visible GPU, minus one for the caller
 	size_t hybridMinItems = (size_t)1 << 21, hybridWalkItems = (size_t)1 << 20;
 	hostrec::Pool *hostPool = nullptr;
@@ -1422,7 +1423,7 @@ int cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value) {
 	else if (k == "entry_grid") ctx->entryGrid = value != 0;
 	else if (k == "hull_window") ctx->hullWindow = value != 0;
 	else if (k == "auto_register") ctx->autoRegister = value != 0;
-	else if (k == "host_records") ctx->hostRecords = value < 0 ? -1 : (value > 2 ? 2 : (int)value);
+	else if (k == "host_records") ctx->hostRecords = value < 0 ? -1 : (value > 3 ? 3 : (int)value);
 	else if (k == "host_threads") {
 		const int t = value < 0 ? -1 : (value > 256 ? 256 : (int)value);
 		if (t != ctx->hostThreads && ctx->hostPool) { hostrec::poolDestroy(ctx->hostPool); ctx->hostPool = nullptr; }
@@ -2009,7 +2010,7 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		CUDA_TRY(ctx, harvest(false));
 		while (c - oldest >= inFlight) CUDA_TRY(ctx, harvest(true));
 		bool host = allHost;
-		if (pool && !allHost && ctx->hostRecords < 0) {
+		if (pool && !allHost && (ctx->hostRecords < 0 || ctx->hostRecords == 3)) {
 			// error diffusion: the threads' share of what has been handed out so far follows hostShare (the first pieces
 			// go to them: they are small, and the threads need the head start more than the link does)
 			host = (double)(hostRecs + cnt) <= ctx->hostShare * (double)(lo + cnt) + 0.5 * (double)cnt;
@@ -2077,7 +2078,7 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 		}
 	}
 	drain.p = nullptr;
-	if (pool && !allHost && ctx->hostRecords < 0 && ctx->hostShareFixed < 0.0) {
+	if (pool && !allHost && (ctx->hostRecords < 0 || ctx->hostRecords == 3) && ctx->hostShareFixed < 0.0) {
 		const double tHost = hostRecs ? hostrec::poolLastDoneMs(pool) : 0.0;
 		double tLink = 0.0;
 		for (int c = 0; c < pieces; c++) {
