@@ -149,7 +149,10 @@ int  cmgpu_num_inline_models(const cmgpu_ctx *ctx);
  * clip), "two_phase" (0: binned hot launches store 56-byte records by item number from the walk itself instead of
  * 16-byte results by slot plus an expansion pass), "compact_by_item" (0: the pool kernel stores those results by slot and
  * the expansion gathers them), "node_thresholds" (0: the pool kernel's node step subtracts and compares instead of using
- * the per-hull threshold table), "gang_brush", "pipe_chunks" (pieces a host batch is cut into).  Unknown names
+ * the per-hull threshold table), "gang_brush", "pipe_chunks" (pieces a host batch is cut into); for big host batches
+ * "host_records", "host_threads", "stage_pageable" (described with cmgpu_last_batch_split below), "hybrid_min_items" (2 Mi:
+ * smallest batch that shares its records), "hybrid_walk_items" (1 Mi: items per piece), and for measurements "host_share"
+ * (>= 0 pins the threads' share), "hybrid_decouple", "hybrid_grid_eighths", "hybrid_in_flight".  Unknown names
  * are CMGPU_ERR_INVALID. */
 int  cmgpu_set_option(cmgpu_ctx *ctx, const char *name, double value);
 
