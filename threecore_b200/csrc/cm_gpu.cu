@@ -211,6 +211,7 @@ struct cmgpu_ctx_s {
 	float *hStage = nullptr;             // pinned: pageable starts / ends on their way up (the threads copy, the link uploads)
 	size_t hStageCap = 0;
 	bool stagePageable = true;           // "stage_pageable"
+	bool hybridUnavailable = false;      // the host would not pin the staging memory: big batches take the plain pipeline
 	std::vector<cudaEvent_t> hybridEvents;
 	// the share of a batch the threads get: set from the thread count before the first call, then corrected after every
 	// call by who finished later, the link or the threads (both are busy to the end when the share is right)
@@ -1890,7 +1891,8 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	if (pool && ctx->hCompactCap < N * 16) {
 		if (ctx->hCompact) { CUDA_TRY(ctx, cudaDeviceSynchronize()); cudaFreeHost(ctx->hCompact); ctx->hCompact = nullptr; ctx->hCompactCap = 0; }
 		const size_t want = N * 16 + N * 2 + 4096;
-		CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->hCompact, want, cudaHostAllocDefault));
+		// a host that will not pin that much is served by the plain pipeline (traceHost), not by an error
+		if (cudaHostAlloc((void **)&ctx->hCompact, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->hCompact = nullptr; return CMGPU_ERR_UNSUPPORTED_INTERNAL; }
 		ctx->hCompactCap = want;
 	}
 	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
@@ -1914,7 +1916,7 @@ static int traceHostHybrid(cmgpu_ctx *ctx, const size_t N, const float *starts, 
 	if (stage && ctx->hStageCap < N * 24) {
 		if (ctx->hStage) { CUDA_TRY(ctx, cudaDeviceSynchronize()); cudaFreeHost(ctx->hStage); ctx->hStage = nullptr; ctx->hStageCap = 0; }
 		const size_t want = N * 24 + N * 3 + 4096;
-		CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->hStage, want, cudaHostAllocDefault));
+		if (cudaHostAlloc((void **)&ctx->hStage, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->hStage = nullptr; return CMGPU_ERR_UNSUPPORTED_INTERNAL; }
 		ctx->hStageCap = want;
 	}
 	const float *upStarts = stage ? ctx->hStage : starts, *upEnds = stage ? ctx->hStage + 3 * N : ends;
@@ -2154,14 +2156,18 @@ static int traceHost(cmgpu_ctx *ctx, int n, const float *starts, const float *en
 			if (getenv("CMGPU_HYBRID_TRACE")) fprintf(stderr, "[pipe] %s pipeline; running means: shared %.3f ns/item (%u calls), plain %.3f (%u)\n", pipe ? "shared" : "plain",
 			                                          ctx->pipeNs[1], calls[1], ctx->pipeNs[0], calls[0]);
 		}
-		if (pipe == 1) {
+		if (pipe == 1 && !ctx->hybridUnavailable) {
 			rc = traceHostHybrid(ctx, N, starts, ends, mins, maxs, masks[0], results, hit_ids);
-			if (timedPipe == 1 && rc == CMGPU_OK) {
-				const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tPipe).count() / (double)N;
-				if (ctx->pipeCalls[1]++ >= 1) ctx->pipeNs[1] = ctx->pipeCalls[1] == 2 ? ns : 0.5 * ctx->pipeNs[1] + 0.5 * ns;
+			if (rc != CMGPU_ERR_UNSUPPORTED_INTERNAL) {
+				if (timedPipe == 1 && rc == CMGPU_OK) {
+					const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tPipe).count() / (double)N;
+					if (ctx->pipeCalls[1]++ >= 1) ctx->pipeNs[1] = ctx->pipeCalls[1] == 2 ? ns : 0.5 * ctx->pipeNs[1] + 0.5 * ns;
+				}
+				return rc;
 			}
-			return rc;
-		}
+			ctx->hybridUnavailable = true;               // the staging memory could not be pinned: the plain pipeline from here on
+			timedPipe = -1;
+		} else if (pipe == 1) timedPipe = -1;
 	}
 	if ((rc = reserve(ctx, ctx->bStarts, N * v3))) return rc;
 	if ((rc = reserve(ctx, ctx->bEnds, N * v3))) return rc;
